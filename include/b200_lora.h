@@ -1,0 +1,159 @@
+/* b200_lora.h - C ABI of the B200-native LoRA / textual-inversion training-step kernels.
+ *
+ * The reference (edenartlab/sd-lora-trainer) is pure Python and has NO FFI / plugin interface of its own
+ * (SURVEY.md section 0.1, 8b); its "boundary" is the set of Python call sites listed next to each entry point
+ * below.  The host-side mirror of those call sites lives in sd_lora_trainer_b200/trainer/ and reaches this
+ * library through ctypes (sd_lora_trainer_b200/_lib.py); INTEGRATION.md shows the binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes, no torch types.  The caller (PyTorch) owns every buffer.
+ *   - every function returns 0 on success, otherwise a non-zero code; b200_last_error() gives the message
+ *     (thread-local).  No exception crosses the ABI.
+ *   - every launch is asynchronous on `stream` (a cudaStream_t passed as void*); nothing synchronises.
+ *   - bf16 tensors are `uint16_t`-sized elements (torch.bfloat16 storage); all strides are in ELEMENTS.
+ */
+#ifndef B200_LORA_H
+#define B200_LORA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_LORA_ABI_VERSION 1
+
+int b200_version(void);
+const char* b200_last_error(void);
+/* number of kernels this library has launched since load (bench.py's `gpu_launches` evidence) */
+long long b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (tcgen05 + TMA).  Replaces the cuBLASLt / cuDNN calls behind
+ *   peft lora.Linear.forward / lora.Conv2d.forward            (trainer/optimizer.py:84-95 -> [3P] peft 0.10.0)
+ *   attn.to_q/to_k/to_v/to_out[0], QK^T, the head-summed score  (trainer/ti_cross_attn_loss.py:167-220)
+ *   diffusers FeedForward / proj_in / proj_out / ResnetBlock2D convs (main.py:329-336 -> [3P] diffusers 0.29.2)
+ *   and their autograd backward (main.py:363): dX, and dA/dB of the LoRA factors only (no dW).
+ *
+ *   D[b1][b0][m, n] = alpha * sum_seg sum_k A_seg[m, k] * B_seg[n, k]  (+ bias[n]) (+ R[m, n])
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* ptr;     /* bf16 */
+    int64_t rows;        /* extent of the strided dim  (K-major: M or N index;  MN-major: K index) */
+    int64_t inner;       /* extent of the contiguous dim (K-major: K index;     MN-major: M or N index) */
+    int64_t row_stride;  /* elements; multiple of 8 (16 B) */
+    int64_t sb0, sb1;    /* batch strides in elements (multiples of 8); ignored when batched == 0 */
+    int32_t mn_major;    /* 0: K-major, 1: MN-major */
+    int32_t batched;     /* 0: shared by all batches (e.g. a weight) */
+} b200_operand_t;
+
+typedef struct {
+    int32_t M, N;                 /* per-batch output extent */
+    int32_t num_seg;              /* 1 or 2 K-segments accumulated into the same tile */
+    int32_t K[2];                 /* reduction length per segment (conv: ignored for segment 0) */
+    b200_operand_t A[2], B[2];
+    int32_t nb0, nb1;             /* batch extents (>= 1) */
+    int32_t splits;               /* split-K (>= 1); > 1 requires d_fp32 && d_atomic, num_seg == 1, conv == 0 */
+    int32_t block_n;              /* 0: library picks the tile width for whole waves */
+    /* implicit 3x3/pad1/stride1 convolution on segment 0: A[0].ptr is NHWC [conv_N, conv_H, conv_W, conv_C],
+       M must equal conv_N*conv_H*conv_W, B[0] is [N rows, 9*b_tap_k (+...)] K-major. */
+    int32_t conv;
+    int32_t conv_N, conv_H, conv_W, conv_C;
+    int32_t b_tap_k, b_tap_n;     /* B coordinate advance per tap: k += tap*b_tap_k, n += tap*b_tap_n */
+    /* output */
+    void* D;
+    int32_t d_fp32, d_atomic;
+    int64_t d_sm, d_sn, d_sb0, d_sb1;
+    float alpha;
+    const void* bias;             /* bf16 or NULL */
+    int32_t bias_rows;            /* rows sharing one bias vector (0: all rows) */
+    int64_t bias_sb;
+    const void* R;                /* bf16 residual or NULL */
+    int64_t r_sm, r_sn, r_sb0, r_sb1;
+} b200_gemm_t;
+
+int b200_gemm(const b200_gemm_t* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Row softmax for the (unfused, HBM-resident) attention path; replaces F.scaled_dot_product_attention's
+ * softmax (trainer/ti_cross_attn_loss.py:197-199).  S is fp32 [rows, ld_s] already scaled; P is bf16
+ * [rows, ld_p]; columns >= cols are written as 0.
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_softmax_fwd(const float* S, void* P, int64_t rows, int32_t cols, int64_t ld_s, int64_t ld_p, void* stream);
+/* dS = P * (dP - rowsum(P*dP)); dP fp32 [rows, ld_dp] -> dS bf16 [rows, ld_p] */
+int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int32_t cols, int64_t ld_p,
+                     int64_t ld_dp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Normalisation / activation kernels on NHWC ([rows, C]) bf16 activations; replace ATen GroupNorm / LayerNorm /
+ * SiLU / GELU kernels under diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock, GEGLU.
+ * Affine parameters are frozen, so the backward kernels emit dX only.
+ * --------------------------------------------------------------------------------------------------------- */
+/* stats: [batch, groups, 2] fp32 (mean, rstd) followed by a [batch, groups, 2] fp64 scratch area, i.e. the caller
+   allocates 6 floats per (image, group), 8-byte aligned; the backward reuses the scratch area. */
+int b200_groupnorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, int32_t batch,
+                       int64_t hw, int32_t C, int32_t groups, float eps, int32_t silu, void* stream);
+int b200_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const void* beta, const float* stats,
+                       void* dx, int32_t batch, int64_t hw, int32_t C, int32_t groups, int32_t silu, void* stream);
+/* stats: [rows, 2] fp32 (mean, rstd) */
+int b200_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, int64_t rows,
+                       int32_t C, float eps, void* stream);
+int b200_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* stats, void* dx, int64_t rows,
+                       int32_t C, void* stream);
+/* h: [rows, 2*inner] = (value | gate); y = value * gelu(gate) (exact erf gelu, rounded like torch's op-by-op bf16) */
+int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, void* stream);
+int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, void* stream);
+int b200_silu_fwd(const void* x, void* y, int64_t n, void* stream);
+int b200_silu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
+/* y = a + b (+ c), bf16 */
+int b200_add(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Layout helpers (NHWC).
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_upsample2x_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int b200_upsample2x_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* 3x3 pad-1 im2col with stride: col[N*Ho*Wo, 9*C], tap-major (kh,kw,c) */
+int b200_im2col3x3(const void* x, void* col, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, void* stream);
+int b200_col2im3x3(const void* col, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, void* stream);
+/* U9[p, tap*r + j] = U[p - offset(tap), j] (zero outside the image): lets the conv-LoRA backward run as plain GEMMs */
+int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, void* stream);
+/* sinusoidal timestep embedding (flip_sin_to_cos, shift 0): t fp32 [n] -> bf16 [n, dim] */
+int b200_timestep_embedding(const float* t, void* out, int32_t n, int32_t dim, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Step prologue / loss / optimizer (main.py:311-326, trainer/loss.py:127-170, trainer/optimizer.py:265-275).
+ * --------------------------------------------------------------------------------------------------------- */
+/* noise(bf16, in/out) += offset_scale * offset[b, c] ; noisy = sqrt(acp[t]) * bf16(latent) + sqrt(1 - acp[t]) * noise
+   with acp rounded to bf16 before the sqrt, as DDPMScheduler.add_noise does.  latent fp32 NCHW, outputs NCHW bf16
+   plus an NHWC(8-channel padded) copy of `noisy` for the conv_in TMA path. */
+int b200_noise_prologue(const float* latent, void* noise, const float* offset, float offset_scale,
+                        const float* alphas_cumprod, const int64_t* timesteps, void* noisy_nchw, void* noisy_nhwc8,
+                        int32_t B, int32_t C, int32_t HW, void* stream);
+/* min-SNR weights w[b] = (min(snr_b, gamma)/snr_b) / mean_b(.) from the fp32 alphas_cumprod table (loss.py:83-106,145-161) */
+int b200_snr_weights(const float* alphas_cumprod, const int64_t* timesteps, float snr_gamma, float* weights, int32_t B,
+                     void* stream);
+/* loss_out[0] += (1/B) sum_b w[b] * mean_chw( (pred - noise)^2 * mask )  and, when dpred != NULL,
+   dpred = loss_scale * dloss/dpred (bf16, NHWC with row stride ld_dpred).  pred: NHWC bf16 [B*HW, ld_pred];
+   noise: NCHW bf16; mask: NCHW fp32.  The caller zeroes loss_out. */
+int b200_diffusion_loss(const void* pred, int64_t ld_pred, const void* noise, const float* mask, const float* weights,
+                        float loss_scale, float* loss_out, void* dpred, int64_t ld_dpred, int32_t B, int32_t C,
+                        int32_t HW, void* stream);
+/* out[0] += sum |p| over n bf16 elements */
+int b200_abs_sum(const void* p, int64_t n, float* out, void* stream);
+/* Fused AdamW over ONE flat buffer: bf16 params / fp32 grads / bf16 moments.  Elements [0, n_first) are the LoRA
+   factors (lr, wd, and the L1 penalty's sign-gradient l1_coeff*sign(p) folded into g); elements [n_first, n) are the
+   trainable textual-inversion embedding rows (lr2, wd2).  Reproduces torch.optim.AdamW on bf16 tensors op for op
+   (every intermediate rounded to bf16 as ATen does), so a step from equal state and equal bf16 gradients is
+   bit-identical to the reference's optimizer.  g = bf16(bf16(grad*grad_scale) + l1_coeff*sign(p)).
+   Hyper-parameters are doubles because the reference forms them as Python floats.  Zeroes `grad` when zero_grad. */
+int b200_adamw(void* p, float* grad, void* m, void* v, int64_t n, int64_t n_first, double lr, double wd,
+               double l1_coeff, double lr2, double wd2, double beta1, double beta2, double eps, int32_t step,
+               double grad_scale, int32_t zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_LORA_H */

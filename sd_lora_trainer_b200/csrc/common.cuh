@@ -1,0 +1,107 @@
+// Shared helpers for the HBM-bound kernels: 16-byte bf16 vectors, warp/block reductions, error plumbing.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace b200 {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (thread-local message, integer status across the C ABI) -----------------
+std::string& last_error_ref();
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define B200_CHECK_ARG(cond, ...)                    \
+    do {                                             \
+        if (!(cond)) return set_error(2, __VA_ARGS__); \
+    } while (0)
+
+#define B200_CHECK_LAUNCH(name)                                                           \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) return set_error(3, "%s: %s", name, cudaGetErrorString(e__)); \
+        count_launch();                                                                   \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+
+// ---- bf16 helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float bfr(float x) {   // round-trip through bf16 (torch's per-op rounding)
+    return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+struct alignas(16) bf16x8 {
+    __nv_bfloat162 h[4];
+};
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+    const bf16x8 v = *reinterpret_cast<const bf16x8*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __bfloat162float(v.h[i].x);
+        f[2 * i + 1] = __bfloat162float(v.h[i].y);
+    }
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+    bf16x8 v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v.h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<bf16x8*>(p) = v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory; every thread gets the result
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : -INFINITY;
+    r = warp_max(r);
+    return r;
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float dsilu_f(float x) {
+    const float s = 1.f / (1.f + expf(-x));
+    return s * (1.f + x * (1.f - s));
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+inline int grid_for(long long work_items, int threads, int max_blocks = kNumSMs * 16) {
+    long long b = (work_items + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return static_cast<int>(b);
+}
+
+}  // namespace b200

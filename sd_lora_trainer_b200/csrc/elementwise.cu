@@ -1,0 +1,441 @@
+// HBM-bound helpers of the step: row softmax fwd/bwd (unfused attention), GEGLU, SiLU, adds, NHWC layout helpers
+// (nearest 2x upsample, strided 3x3 im2col / col2im, the 9-tap shift-stack for the conv-LoRA backward) and the
+// sinusoidal timestep embedding.  16-byte vectors everywhere the layout allows it.
+#include "common.cuh"
+#include "../../include/b200_lora.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// softmax: one warp per row (cols <= 1024, <= 32 values per lane in registers) or one 128-thread
+// block per row (cols <= 4096); rows of any other length take the 3-pass global-memory path.
+// ------------------------------------------------------------------------------------------------
+template <int kPerLane>
+__global__ void softmax_fwd_warp_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int cols,
+                                        long long ld_s, long long ld_p) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; row < rows; row += warps) {
+        const float* s = S + row * ld_s;
+        float v[kPerLane];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            const int c = lane + j * 32;
+            v[j] = (c < cols) ? s[c] : -INFINITY;
+            mx = fmaxf(mx, v[j]);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            v[j] = (lane + j * 32 < cols) ? __expf(v[j] - mx) : 0.f;
+            sum += v[j];
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.f / sum;
+        bf16* p = P + row * ld_p;
+#pragma unroll
+        for (int j = 0; j < kPerLane; ++j) {
+            const int c = lane + j * 32;
+            if (c < ld_p) p[c] = __float2bfloat16_rn(v[j] * inv);   // columns in [cols, ld_p) get exact zeros
+        }
+    }
+}
+
+template <int kPerThread>
+__global__ void softmax_fwd_block_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int cols,
+                                         long long ld_s, long long ld_p) {
+    __shared__ float red[32];
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float* s = S + row * ld_s;
+        float v[kPerThread];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+            const int c = threadIdx.x + j * blockDim.x;
+            v[j] = (c < cols) ? s[c] : -INFINITY;
+            mx = fmaxf(mx, v[j]);
+        }
+        mx = block_max(mx, red);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+            v[j] = (threadIdx.x + j * blockDim.x < cols) ? __expf(v[j] - mx) : 0.f;
+            sum += v[j];
+        }
+        sum = block_sum(sum, red);
+        const float inv = 1.f / sum;
+        bf16* p = P + row * ld_p;
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j) {
+            const int c = threadIdx.x + j * blockDim.x;
+            if (c < ld_p) p[c] = __float2bfloat16_rn(v[j] * inv);
+        }
+    }
+}
+
+__global__ void softmax_fwd_generic_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int cols,
+                                           long long ld_s, long long ld_p) {
+    __shared__ float red[32];
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const float* s = S + row * ld_s;
+        float mx = -INFINITY;
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, s[c]);
+        mx = block_max(mx, red);
+        float sum = 0.f;
+        for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += __expf(s[c] - mx);
+        sum = block_sum(sum, red);
+        const float inv = 1.f / sum;
+        bf16* p = P + row * ld_p;
+        for (int c = threadIdx.x; c < ld_p; c += blockDim.x)
+            p[c] = __float2bfloat16_rn(c < cols ? __expf(s[c] - mx) * inv : 0.f);
+    }
+}
+
+// dS = P * (dP - sum_j P_j dP_j)
+__global__ void softmax_bwd_kernel(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS,
+                                   long long rows, int cols, long long ld_p, long long ld_dp, int warp_rows) {
+    __shared__ float red[32];
+    const int lane = threadIdx.x & 31;
+    if (warp_rows) {
+        const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+        for (long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; row < rows; row += warps) {
+            const bf16* p = P + row * ld_p;
+            const float* dp = dP + row * ld_dp;
+            float dot = 0.f;
+            for (int c = lane; c < cols; c += 32) dot += __bfloat162float(p[c]) * dp[c];
+            dot = warp_sum(dot);
+            bf16* ds = dS + row * ld_p;
+            for (int c = lane; c < ld_p; c += 32)
+                ds[c] = __float2bfloat16_rn(c < cols ? __bfloat162float(p[c]) * (dp[c] - dot) : 0.f);
+        }
+    } else {
+        for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+            const bf16* p = P + row * ld_p;
+            const float* dp = dP + row * ld_dp;
+            float dot = 0.f;
+            for (int c = threadIdx.x; c < cols; c += blockDim.x) dot += __bfloat162float(p[c]) * dp[c];
+            dot = block_sum(dot, red);
+            bf16* ds = dS + row * ld_p;
+            for (int c = threadIdx.x; c < ld_p; c += blockDim.x)
+                ds[c] = __float2bfloat16_rn(c < cols ? __bfloat162float(p[c]) * (dp[c] - dot) : 0.f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEGLU / SiLU / add
+// ------------------------------------------------------------------------------------------------
+__global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ y, long long rows, int inner) {
+    const int I8 = inner >> 3;
+    const long long total = rows * I8;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = idx / I8;
+        const int v = static_cast<int>(idx % I8);
+        float a[8], g[8], o[8];
+        load8(h + r * 2 * inner + v * 8, a);
+        load8(h + r * 2 * inner + inner + v * 8, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = a[i] * bfr(gelu_f(g[i]));
+        store8(y + r * inner + v * 8, o);
+    }
+}
+
+__global__ void geglu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h, bf16* __restrict__ dh,
+                                 long long rows, int inner) {
+    const int I8 = inner >> 3;
+    const long long total = rows * I8;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = idx / I8;
+        const int v = static_cast<int>(idx % I8);
+        float a[8], g[8], d[8], da[8], dg[8];
+        load8(h + r * 2 * inner + v * 8, a);
+        load8(h + r * 2 * inner + inner + v * 8, g);
+        load8(dy + r * inner + v * 8, d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            da[i] = d[i] * bfr(gelu_f(g[i]));
+            dg[i] = bfr(d[i] * a[i]) * dgelu_f(g[i]);
+        }
+        store8(dh + r * 2 * inner + v * 8, da);
+        store8(dh + r * 2 * inner + inner + v * 8, dg);
+    }
+}
+
+__global__ void silu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        y[i] = __float2bfloat16_rn(silu_f(__bfloat162float(x[i])));
+}
+__global__ void silu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx,
+                                long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * dsilu_f(__bfloat162float(x[i])));
+}
+
+__global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ c,
+                           bf16* __restrict__ y, long long n8, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float fa[8], fb[8], o[8];
+        load8(a + i * 8, fa);
+        load8(b + i * 8, fb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fa[j] + fb[j];
+        if (c) {
+            float fc[8];
+            load8(c + i * 8, fc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = bfr(o[j]) + fc[j];
+        }
+        store8(y + i * 8, o);
+    }
+    // scalar tail
+    if (blockIdx.x == 0) {
+        for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) {
+            float o = __bfloat162float(a[i]) + __bfloat162float(b[i]);
+            if (c) o = bfr(o) + __bfloat162float(c[i]);
+            y[i] = __float2bfloat16_rn(o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NHWC layout helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C8) {
+    const long long total = static_cast<long long>(N) * (2 * H) * (2 * W) * C8;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(idx % C8);
+        long long p = idx / C8;
+        const int wo = static_cast<int>(p % (2 * W));  p /= 2 * W;
+        const int ho = static_cast<int>(p % (2 * H));
+        const int n = static_cast<int>(p / (2 * H));
+        const long long src = ((static_cast<long long>(n) * H + (ho >> 1)) * W + (wo >> 1)) * C8 + v;
+        reinterpret_cast<uint4*>(y)[idx] = reinterpret_cast<const uint4*>(x)[src];
+    }
+}
+
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int C8) {
+    const long long total = static_cast<long long>(N) * H * W * C8;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(idx % C8);
+        long long p = idx / C8;
+        const int w = static_cast<int>(p % W);  p /= W;
+        const int h = static_cast<int>(p % H);
+        const int n = static_cast<int>(p / H);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float f[8];
+                load8(dy + (((static_cast<long long>(n) * 2 * H + 2 * h + i) * 2 * W + 2 * w + j) * C8 + v) * 8, f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += f[k];
+            }
+        store8(dx + idx * 8, acc);
+    }
+}
+
+__global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C8,
+                                 int stride, int Ho, int Wo) {
+    const long long total = static_cast<long long>(N) * Ho * Wo * 9 * C8;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(idx % C8);
+        long long p = idx / C8;
+        const int tap = static_cast<int>(p % 9);  p /= 9;
+        const int wo = static_cast<int>(p % Wo);  p /= Wo;
+        const int ho = static_cast<int>(p % Ho);
+        const int n = static_cast<int>(p / Ho);
+        const int h = ho * stride + tap / 3 - 1, w = wo * stride + tap % 3 - 1;
+        uint4 val = zero;
+        if (h >= 0 && h < H && w >= 0 && w < W)
+            val = reinterpret_cast<const uint4*>(x)[((static_cast<long long>(n) * H + h) * W + w) * C8 + v];
+        reinterpret_cast<uint4*>(col)[idx] = val;
+    }
+}
+
+// gather form of the transposed im2col: dx[n,h,w,:] = sum over (tap, ho, wo) with ho*stride + kh - 1 == h, ...
+__global__ void col2im3x3_kernel(const bf16* __restrict__ col, bf16* __restrict__ dx, int N, int H, int W, int C8,
+                                 int stride, int Ho, int Wo) {
+    const long long total = static_cast<long long>(N) * H * W * C8;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(idx % C8);
+        long long p = idx / C8;
+        const int w = static_cast<int>(p % W);  p /= W;
+        const int h = static_cast<int>(p % H);
+        const int n = static_cast<int>(p / H);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hn = h + 1 - kh;
+            if (hn < 0 || hn % stride) continue;
+            const int ho = hn / stride;
+            if (ho >= Ho) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int wn = w + 1 - kw;
+                if (wn < 0 || wn % stride) continue;
+                const int wo = wn / stride;
+                if (wo >= Wo) continue;
+                float f[8];
+                load8(col + ((((static_cast<long long>(n) * Ho + ho) * Wo + wo) * 9 + kh * 3 + kw) * C8 + v) * 8, f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += f[k];
+            }
+        }
+        store8(dx + idx * 8, acc);
+    }
+}
+
+// U9[p, tap*r + j] = U[p - off(tap), j]
+__global__ void shift_stack9_kernel(const bf16* __restrict__ U, bf16* __restrict__ U9, int N, int H, int W, int r) {
+    const long long total = static_cast<long long>(N) * H * W * 9 * r;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(idx % r);
+        long long p = idx / r;
+        const int tap = static_cast<int>(p % 9);  p /= 9;
+        const int w = static_cast<int>(p % W);  p /= W;
+        const int h = static_cast<int>(p % H);
+        const int n = static_cast<int>(p / H);
+        const int hs = h - (tap / 3 - 1), ws = w - (tap % 3 - 1);
+        bf16 val = __float2bfloat16_rn(0.f);
+        if (hs >= 0 && hs < H && ws >= 0 && ws < W) val = U[((static_cast<long long>(n) * H + hs) * W + ws) * r + j];
+        U9[idx] = val;
+    }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __restrict__ out, int n, int dim) {
+    const int half = dim / 2;
+    const int total = n * dim;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int i = idx / dim, j = idx % dim;
+        const int k = j < half ? j : j - half;
+        const float freq = expf(-9.210340371976184f * static_cast<float>(k) / static_cast<float>(half));
+        const float a = t[i] * freq;
+        out[idx] = __float2bfloat16_rn(j < half ? cosf(a) : sinf(a));
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define ST static_cast<cudaStream_t>(stream)
+
+extern "C" int b200_softmax_fwd(const float* S, void* P, int64_t rows, int32_t cols, int64_t ld_s, int64_t ld_p,
+                                void* stream) {
+    B200_CHECK_ARG(cols >= 1 && ld_p >= cols && ld_s >= cols, "softmax: bad extents");
+    bf16* p = static_cast<bf16*>(P);
+    if (ld_p <= 128) {
+        softmax_fwd_warp_kernel<4><<<grid_for(rows * 32, 256), 256, 0, ST>>>(S, p, rows, cols, ld_s, ld_p);
+    } else if (ld_p <= 1024) {
+        softmax_fwd_warp_kernel<32><<<grid_for(rows * 32, 256), 256, 0, ST>>>(S, p, rows, cols, ld_s, ld_p);
+    } else if (ld_p <= 4096) {
+        softmax_fwd_block_kernel<32><<<static_cast<int>(rows < kNumSMs * 16 ? rows : kNumSMs * 16), 128, 0, ST>>>(
+            S, p, rows, cols, ld_s, ld_p);
+    } else {
+        softmax_fwd_generic_kernel<<<static_cast<int>(rows < kNumSMs * 8 ? rows : kNumSMs * 8), 256, 0, ST>>>(
+            S, p, rows, cols, ld_s, ld_p);
+    }
+    B200_CHECK_LAUNCH("softmax_fwd");
+    return 0;
+}
+
+extern "C" int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int32_t cols, int64_t ld_p,
+                                int64_t ld_dp, void* stream) {
+    B200_CHECK_ARG(cols >= 1 && ld_p >= cols && ld_dp >= cols, "softmax_bwd: bad extents");
+    const int warp_rows = cols <= 512;
+    const int blocks = warp_rows ? grid_for(rows * 32, 256) : static_cast<int>(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
+    softmax_bwd_kernel<<<blocks, 256, 0, ST>>>(static_cast<const bf16*>(P), dP, static_cast<bf16*>(dS), rows, cols, ld_p,
+                                               ld_dp, warp_rows);
+    B200_CHECK_LAUNCH("softmax_bwd");
+    return 0;
+}
+
+extern "C" int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, void* stream) {
+    B200_CHECK_ARG(inner % 8 == 0, "geglu: inner %% 8 != 0");
+    geglu_fwd_kernel<<<grid_for(rows * (inner / 8), 256), 256, 0, ST>>>(static_cast<const bf16*>(h),
+                                                                         static_cast<bf16*>(y), rows, inner);
+    B200_CHECK_LAUNCH("geglu_fwd");
+    return 0;
+}
+extern "C" int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, void* stream) {
+    B200_CHECK_ARG(inner % 8 == 0, "geglu: inner %% 8 != 0");
+    geglu_bwd_kernel<<<grid_for(rows * (inner / 8), 256), 256, 0, ST>>>(
+        static_cast<const bf16*>(dy), static_cast<const bf16*>(h), static_cast<bf16*>(dh), rows, inner);
+    B200_CHECK_LAUNCH("geglu_bwd");
+    return 0;
+}
+extern "C" int b200_silu_fwd(const void* x, void* y, int64_t n, void* stream) {
+    silu_fwd_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), n);
+    B200_CHECK_LAUNCH("silu_fwd");
+    return 0;
+}
+extern "C" int b200_silu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream) {
+    silu_bwd_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
+                                                      static_cast<bf16*>(dx), n);
+    B200_CHECK_LAUNCH("silu_bwd");
+    return 0;
+}
+extern "C" int b200_add(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                           reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const long long n8 = aligned ? n / 8 : 0;
+    add_kernel<<<grid_for(n8 > 0 ? n8 : 1, 256), 256, 0, ST>>>(static_cast<const bf16*>(a), static_cast<const bf16*>(b),
+                                                               static_cast<const bf16*>(c), static_cast<bf16*>(y), n8, n);
+    B200_CHECK_LAUNCH("add");
+    return 0;
+}
+extern "C" int b200_upsample2x_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+    B200_CHECK_ARG(C % 8 == 0, "upsample: C %% 8 != 0");
+    upsample2x_fwd_kernel<<<grid_for(4LL * N * H * W * (C / 8), 256), 256, 0, ST>>>(
+        static_cast<const bf16*>(x), static_cast<bf16*>(y), N, H, W, C / 8);
+    B200_CHECK_LAUNCH("upsample2x_fwd");
+    return 0;
+}
+extern "C" int b200_upsample2x_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
+    B200_CHECK_ARG(C % 8 == 0, "upsample: C %% 8 != 0");
+    upsample2x_bwd_kernel<<<grid_for(1LL * N * H * W * (C / 8), 256), 256, 0, ST>>>(
+        static_cast<const bf16*>(dy), static_cast<bf16*>(dx), N, H, W, C / 8);
+    B200_CHECK_LAUNCH("upsample2x_bwd");
+    return 0;
+}
+extern "C" int b200_im2col3x3(const void* x, void* col, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride,
+                              void* stream) {
+    B200_CHECK_ARG(C % 8 == 0 && (stride == 1 || stride == 2), "im2col: unsupported C/stride");
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    im2col3x3_kernel<<<grid_for(9LL * N * Ho * Wo * (C / 8), 256), 256, 0, ST>>>(
+        static_cast<const bf16*>(x), static_cast<bf16*>(col), N, H, W, C / 8, stride, Ho, Wo);
+    B200_CHECK_LAUNCH("im2col3x3");
+    return 0;
+}
+extern "C" int b200_col2im3x3(const void* col, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride,
+                              void* stream) {
+    B200_CHECK_ARG(C % 8 == 0 && (stride == 1 || stride == 2), "col2im: unsupported C/stride");
+    const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+    col2im3x3_kernel<<<grid_for(1LL * N * H * W * (C / 8), 256), 256, 0, ST>>>(
+        static_cast<const bf16*>(col), static_cast<bf16*>(dx), N, H, W, C / 8, stride, Ho, Wo);
+    B200_CHECK_LAUNCH("col2im3x3");
+    return 0;
+}
+extern "C" int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, void* stream) {
+    shift_stack9_kernel<<<grid_for(9LL * N * H * W * r, 256), 256, 0, ST>>>(static_cast<const bf16*>(U),
+                                                                            static_cast<bf16*>(U9), N, H, W, r);
+    B200_CHECK_LAUNCH("shift_stack9");
+    return 0;
+}
+extern "C" int b200_timestep_embedding(const float* t, void* out, int32_t n, int32_t dim, void* stream) {
+    B200_CHECK_ARG(dim % 2 == 0, "timestep_embedding: odd dim");
+    timestep_embedding_kernel<<<grid_for(1LL * n * dim, 256), 256, 0, ST>>>(t, static_cast<bf16*>(out), n, dim);
+    B200_CHECK_LAUNCH("timestep_embedding");
+    return 0;
+}

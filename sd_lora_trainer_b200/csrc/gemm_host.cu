@@ -1,0 +1,203 @@
+// Host side of b200_gemm: validates the C descriptor, encodes the TMA tensor maps (driver entry point resolved
+// at run time, so the library links against cudart only), picks the tile width for whole waves over 148 SMs and
+// launches the persistent tcgen05 kernel.
+#include <stdarg.h>
+#include <atomic>
+#include <cudaTypedefs.h>
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+#include "../../include/b200_lora.h"
+
+namespace b200 {
+
+std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+int set_error(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// 4-D bf16 tensor map, 128B swizzle.  dims/strides innermost first; strides in elements (dims 1..3).
+static int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const long long strides[3],
+                      const int box[4]) {
+    auto fn = get_encode_fn();
+    if (!fn) return set_error(4, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    cuuint64_t gdim[4], gstr[3];
+    cuuint32_t bdim[4], estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) {
+        gdim[i] = static_cast<cuuint64_t>(dims[i] < 1 ? 1 : dims[i]);
+        bdim[i] = static_cast<cuuint32_t>(box[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        long long s = strides[i];
+        if (s <= 0) s = 8;                       // degenerate (extent-1) dims still need a legal stride
+        gstr[i] = static_cast<cuuint64_t>(s) * 2;
+        if (gstr[i] % 16) return set_error(2, "gemm: stride %lld elements is not a multiple of 8", s);
+    }
+    if (reinterpret_cast<uintptr_t>(ptr) % 16) return set_error(2, "gemm: operand base not 16-byte aligned");
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(4, "cuTensorMapEncodeTiled failed (%d): dims %lld,%lld,%lld,%lld box %d,%d,%d,%d", (int)r,
+                         dims[0], dims[1], dims[2], dims[3], box[0], box[1], box[2], box[3]);
+    return 0;
+}
+
+static int encode_operand(CUtensorMap* map, const b200_operand_t& op, int box_rows_kmajor, int nb0, int nb1) {
+    // K-major : dims (K=inner, rows), box (64, box_rows).   MN-major: dims (MN=inner, K=rows), box (64, 64).
+    // TMA zero-fills everything outside these extents, which is what handles the M/N/K tails.
+    if (op.batched && ((nb0 > 1 && op.sb0 <= 0) || (nb1 > 1 && op.sb1 <= 0)))
+        return set_error(2, "gemm: batched operand needs positive batch strides");
+    const long long d[4] = {op.inner, op.rows, op.batched ? nb0 : 1, op.batched ? nb1 : 1};
+    const long long strides[3] = {op.row_stride, op.batched ? op.sb0 : 0, op.batched ? op.sb1 : 0};
+    const int box[4] = {64, op.mn_major ? 64 : box_rows_kmajor, 1, 1};
+    return encode_map(map, op.ptr, d, strides, box);
+}
+
+// Tile width: whole waves over 148 persistent CTAs, tie-break towards wider tiles (fewer re-reads of A).
+static int pick_block_n(long long tiles_m_total, int N) {
+    const int n16 = ((N + 15) / 16) * 16;
+    if (n16 <= 256 && tiles_m_total * 1 >= kNumSMs / 2) return n16 < 16 ? 16 : n16;
+    int best = 16;
+    double best_cost = 1e30;
+    const int hi = n16 < 256 ? n16 : 256;
+    for (int bn = hi; bn >= 32; bn -= 16) {
+        const long long tiles = tiles_m_total * ((N + bn - 1) / bn);
+        const long long waves = (tiles + kNumSMs - 1) / kNumSMs;
+        const double cost = static_cast<double>(waves) * (bn + 24.0);   // 24 ~ per-tile fixed cost in columns
+        if (cost < best_cost - 1e-9) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_version(void) { return B200_LORA_ABI_VERSION; }
+extern "C" const char* b200_last_error(void) { return last_error_ref().c_str(); }
+extern "C" long long b200_launch_count(void) { return g_launches.load(); }
+
+extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
+    B200_CHECK_ARG(d != nullptr, "gemm: null descriptor");
+    B200_CHECK_ARG(d->M >= 1 && d->N >= 1, "gemm: empty problem M=%d N=%d", d->M, d->N);
+    B200_CHECK_ARG(d->num_seg == 1 || d->num_seg == 2, "gemm: num_seg must be 1 or 2");
+    B200_CHECK_ARG(d->nb0 >= 1 && d->nb1 >= 1 && d->splits >= 1, "gemm: bad batch/split");
+    B200_CHECK_ARG(d->D != nullptr, "gemm: null output");
+    B200_CHECK_ARG(!(d->d_atomic && !d->d_fp32), "gemm: atomic accumulation needs an fp32 output");
+    B200_CHECK_ARG(d->splits == 1 || (d->d_atomic && d->num_seg == 1 && !d->conv), "gemm: split-K needs atomic fp32 output, one segment, no conv");
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+        if (e != cudaSuccess) return set_error(3, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = d->M;
+    g.N = d->N;
+    g.nb0 = d->nb0;
+    g.nb1 = d->nb1;
+    g.splits = d->splits;
+    g.num_seg = d->num_seg;
+    g.tiles_m = (d->M + kBM - 1) / kBM;
+    int bn = d->block_n;
+    if (bn <= 0) bn = pick_block_n(static_cast<long long>(g.tiles_m) * d->nb0 * d->nb1 * d->splits, d->N);
+    B200_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= kMaxBN, "gemm: block_n %d must be a multiple of 16 in [16, 256]", bn);
+    g.BN = bn;
+    g.tiles_n = (d->N + bn - 1) / bn;
+
+    for (int s = 0; s < d->num_seg; ++s) {
+        const b200_operand_t& A = d->A[s];
+        const b200_operand_t& B = d->B[s];
+        g.a_mn[s] = A.mn_major;
+        g.b_mn[s] = B.mn_major;
+        g.a_batched[s] = A.batched;
+        g.b_batched[s] = B.batched;
+        if (s == 0 && d->conv) {
+            B200_CHECK_ARG(!A.mn_major && !B.mn_major, "gemm: conv operands must be K-major");
+            const int W = d->conv_W, H = d->conv_H, Nimg = d->conv_N, C = d->conv_C;
+            B200_CHECK_ARG(W >= 1 && W <= 128 && 128 % W == 0, "gemm: conv width %d must divide 128", W);
+            int bh = 128 / W;
+            if (bh > H) bh = H;
+            B200_CHECK_ARG(H % bh == 0 && 128 % (W * bh) == 0, "gemm: conv height %d unsupported for width %d", H, W);
+            const int bimg = 128 / (W * bh);
+            B200_CHECK_ARG(bimg == 1 || bh == H, "gemm: conv tile/image mismatch");
+            B200_CHECK_ARG(static_cast<long long>(Nimg) * H * W == d->M, "gemm: conv M mismatch");
+            B200_CHECK_ARG(C % 8 == 0, "gemm: conv channels %d not a multiple of 8", C);
+            const long long dims[4] = {C, W, H, Nimg};
+            const long long strides[3] = {C, static_cast<long long>(W) * C, static_cast<long long>(H) * W * C};
+            const int box[4] = {64, W, bh, bimg};
+            if (int rc = encode_map(&g.mapA[0], A.ptr, dims, strides, box)) return rc;
+            g.conv = 1;
+            g.conv_cblocks = (C + kBK - 1) / kBK;
+            g.conv_W = W;
+            g.conv_H = H;
+            g.conv_bh = bh;
+            g.b_tap_k = d->b_tap_k;
+            g.b_tap_n = d->b_tap_n;
+            g.kblocks[0] = 9 * g.conv_cblocks;
+            // channel tails are zero-filled by TMA on the A side, so every block runs all four 16-wide MMA steps
+            g.ktail16[0] = 4;
+        } else {
+            const int K = d->K[s];
+            B200_CHECK_ARG(K >= 1, "gemm: K[%d] = %d", s, K);
+            B200_CHECK_ARG(A.mn_major ? (A.rows >= K) : (A.inner >= K), "gemm: A[%d] smaller than K", s);
+            if (int rc = encode_operand(&g.mapA[s], A, kBM, d->nb0, d->nb1)) return rc;
+            g.kblocks[s] = (K + kBK - 1) / kBK;
+            g.ktail16[s] = (K - (g.kblocks[s] - 1) * kBK + 15) / 16;
+        }
+        if (int rc = encode_operand(&g.mapB[s], B, bn, d->nb0, d->nb1)) return rc;
+    }
+    B200_CHECK_ARG(d->splits <= g.kblocks[0], "gemm: more splits (%d) than K blocks (%d)", d->splits, g.kblocks[0]);
+
+    g.D = d->D;
+    g.d_fp32 = d->d_fp32;
+    g.d_atomic = d->d_atomic;
+    g.d_sm = d->d_sm;
+    g.d_sn = d->d_sn;
+    g.d_sb0 = d->d_sb0;
+    g.d_sb1 = d->d_sb1;
+    g.alpha = d->alpha;
+    g.bias = static_cast<const __nv_bfloat16*>(d->bias);
+    g.bias_rows = d->bias_rows;
+    g.bias_sb = d->bias_sb;
+    g.R = static_cast<const __nv_bfloat16*>(d->R);
+    g.r_sm = d->r_sm;
+    g.r_sn = d->r_sn;
+    g.r_sb0 = d->r_sb0;
+    g.r_sb1 = d->r_sb1;
+
+    const long long total_tiles = static_cast<long long>(g.tiles_m) * g.tiles_n * g.splits * g.nb0 * g.nb1;
+    const int grid = static_cast<int>(total_tiles < kNumSMs ? total_tiles : kNumSMs);
+    gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    B200_CHECK_LAUNCH("gemm_tcgen05");
+    return 0;
+}

@@ -1,0 +1,316 @@
+// Generic bf16 tensor-core GEMM for sm_100a: TMA -> smem (128B swizzle) -> tcgen05.mma -> TMEM -> epilogue.
+//
+//   D[b][m, n] = epi( sum_{seg} sum_k A_seg[b][m, k] * B_seg[b][n, k] )        (fp32 accumulate in TMEM)
+//
+// One persistent CTA per SM (6 warps: TMA producer, MMA issuer, 4 epilogue warps), 128 x BN output tiles with BN a
+// RUNTIME multiple of 16 (<= 256) so the host can size the grid to a whole number of waves, 4-stage smem ring,
+// double-buffered TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// What makes it the LoRA hot-path kernel rather than a plain GEMM:
+//   * up to TWO K-segments accumulate into the SAME TMEM tile: segment 0 is the frozen W.x (or an implicit 3x3
+//     convolution), segment 1 the low-rank side path (T = s.x.A^T against B), so  W.x + s.B.(A.x)  is one kernel;
+//   * each operand is K-major or MN-major (descriptor + instruction-descriptor bits), so dX = dY.W, dA = U^T.X and
+//     dB = dY^T.T read the SAME row-major tensors the forward used - no transposed weight copies, no dW ever;
+//   * segment 0's A operand can be an NHWC activation walked as an implicit im2col: one 4-D TMA box per
+//     (tap, 64-channel block), out-of-image rows/columns zero-filled by TMA;
+//   * batched (two batch dims, per-operand) for the attention GEMMs, split-K with fp32 atomic accumulation for the
+//     skinny LoRA weight-gradient GEMMs, and an epilogue with alpha, (per-image) bias and residual add.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kBM = 128;            // tile rows (UMMA M)
+constexpr int kBK = 64;             // K elements per pipeline stage (= one 128 B swizzle row of bf16)
+constexpr int kStages = 4;
+constexpr int kMaxBN = 256;
+constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
+constexpr int kBBytes = kMaxBN * kBK * 2;   // 32 KiB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kGemmThreads = 192;
+constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmArgs {
+    CUtensorMap mapA[2];
+    CUtensorMap mapB[2];
+    int M, N;                 // per-batch output extent
+    int tiles_m, tiles_n;
+    int nb0, nb1;             // batch extents (b0 fastest)
+    int splits;               // split-K factor (segment 0 only; requires num_seg == 1, conv == 0)
+    int BN;
+    int num_seg;
+    int kblocks[2];           // 64-wide K blocks per segment (conv: 9 * conv_cblocks)
+    int ktail16[2];           // 16-wide MMA steps in the LAST block of the segment (1..4)
+    int a_mn[2], b_mn[2];     // operand is MN-major (else K-major)
+    int a_batched[2], b_batched[2];
+    // implicit 3x3 / pad 1 / stride 1 convolution on segment 0's A operand (NHWC, map dims C,W,H,N)
+    int conv;
+    int conv_cblocks;
+    int conv_W, conv_H, conv_bh;   // conv_bh = image rows per box
+    int b_tap_k, b_tap_n;          // per-tap offsets into B's (k, n) coordinates
+    // epilogue
+    void* D;
+    int d_fp32;               // 0: bf16, 1: fp32
+    int d_atomic;             // fp32 only: red.global.add instead of store
+    long long d_sm, d_sn, d_sb0, d_sb1;
+    float alpha;
+    const __nv_bfloat16* bias;
+    int bias_rows;            // rows sharing one bias vector (0: one vector for all rows)
+    long long bias_sb;        // stride between bias vectors
+    const __nv_bfloat16* R;   // residual, added after alpha/bias (nullptr: none)
+    long long r_sm, r_sn, r_sb0, r_sb1;
+};
+
+__device__ __forceinline__ void advance_stage(int& stage, uint32_t& phase) {
+    if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle atoms must sit on 1024 B boundaries.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;    // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < g.num_seg; ++s) {
+            tma_prefetch_desc(&g.mapA[s]);
+            tma_prefetch_desc(&g.mapB[s]);
+        }
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_base_ptr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_ptr;
+
+    const int tiles_per_batch = g.tiles_m * g.tiles_n * g.splits;
+    const int total_tiles = tiles_per_batch * g.nb0 * g.nb1;
+    const int BN = g.BN;
+    const int b_boxes_mn = (BN + 63) >> 6;
+    const uint32_t b_bytes_k = static_cast<uint32_t>(BN) * 128u;
+    const uint32_t b_bytes_mn = static_cast<uint32_t>(b_boxes_mn) * 8192u;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one elected lane) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int n_blk = t % g.tiles_n;  t /= g.tiles_n;
+                const int m_blk = t % g.tiles_m;  t /= g.tiles_m;
+                const int split = t % g.splits;   t /= g.splits;
+                const int b0 = t % g.nb0;
+                const int b1 = t / g.nb0;
+                const int m0 = m_blk * kBM, n0 = n_blk * BN;
+                int conv_n0 = 0, conv_h0 = 0;
+                if (g.conv) {
+                    const int hw = g.conv_H * g.conv_W;
+                    conv_n0 = m0 / hw;
+                    conv_h0 = (m0 % hw) / g.conv_W;
+                }
+                for (int seg = 0; seg < g.num_seg; ++seg) {
+                    int kb_begin = 0, kb_end = g.kblocks[seg];
+                    if (g.splits > 1) {
+                        kb_begin = static_cast<int>((static_cast<long long>(kb_end) * split) / g.splits);
+                        kb_end = static_cast<int>((static_cast<long long>(kb_end) * (split + 1)) / g.splits);
+                    }
+                    const int ab0 = g.a_batched[seg] ? b0 : 0, ab1 = g.a_batched[seg] ? b1 : 0;
+                    const int bb0 = g.b_batched[seg] ? b0 : 0, bb1 = g.b_batched[seg] ? b1 : 0;
+                    const uint32_t tx = kABytes + (g.b_mn[seg] ? b_bytes_mn : b_bytes_k);
+                    for (int kb = kb_begin; kb < kb_end; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * kStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        mbar_expect_tx(&full_bar[stage], tx);
+                        int bk = kb * kBK, bn = n0;
+                        if (g.conv && seg == 0) {
+                            const int tap = kb / g.conv_cblocks, cb = kb - tap * g.conv_cblocks;
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            tma_load_4d(sa, &g.mapA[0], &full_bar[stage], cb * kBK, kw - 1, conv_h0 + kh - 1, conv_n0);
+                            bk = tap * g.b_tap_k + cb * kBK;
+                            bn = n0 + tap * g.b_tap_n;
+                        } else if (g.a_mn[seg]) {
+                            tma_load_4d(sa, &g.mapA[seg], &full_bar[stage], m0, kb * kBK, ab0, ab1);
+                            tma_load_4d(sa + 8192, &g.mapA[seg], &full_bar[stage], m0 + 64, kb * kBK, ab0, ab1);
+                        } else {
+                            tma_load_4d(sa, &g.mapA[seg], &full_bar[stage], kb * kBK, m0, ab0, ab1);
+                        }
+                        if (g.b_mn[seg]) {
+                            for (int j = 0; j < b_boxes_mn; ++j)
+                                tma_load_4d(sb + j * 8192, &g.mapB[seg], &full_bar[stage], bn + j * 64, bk, bb0, bb1);
+                        } else {
+                            tma_load_4d(sb, &g.mapB[seg], &full_bar[stage], bk, bn, bb0, bb1);
+                        }
+                        advance_stage(stage, phase);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int split = (tile / (g.tiles_m * g.tiles_n)) % g.splits;
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
+                uint32_t accumulate = 0;
+                for (int seg = 0; seg < g.num_seg; ++seg) {
+                    int kb_begin = 0, kb_end = g.kblocks[seg];
+                    const int kb_last = kb_end - 1;
+                    if (g.splits > 1) {
+                        kb_begin = static_cast<int>((static_cast<long long>(kb_end) * split) / g.splits);
+                        kb_end = static_cast<int>((static_cast<long long>(kb_end) * (split + 1)) / g.splits);
+                    }
+                    const uint32_t idesc = umma_idesc_bf16(BN, g.a_mn[seg], g.b_mn[seg]);
+                    // per-16-K-step advance of the descriptor start address (encoded >> 4)
+                    const uint32_t a_step = g.a_mn[seg] ? (2048u >> 4) : (32u >> 4);
+                    const uint32_t b_step = g.b_mn[seg] ? (2048u >> 4) : (32u >> 4);
+                    for (int kb = kb_begin; kb < kb_end; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                        const uint32_t sb = sa + kABytes;
+                        const uint64_t adesc = g.a_mn[seg] ? umma_desc(sa, 8192, 1024) : umma_desc(sa, 16, 1024);
+                        const uint64_t bdesc = g.b_mn[seg] ? umma_desc(sb, 8192, 1024) : umma_desc(sb, 16, 1024);
+                        const int n16 = (kb == kb_last) ? g.ktail16[seg] : 4;
+                        for (int k = 0; k < n16; ++k) {
+                            umma_bf16(tmem_d, adesc + static_cast<uint64_t>(a_step * k),
+                                      bdesc + static_cast<uint64_t>(b_step * k), idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                        advance_stage(stage, phase);
+                    }
+                }
+                umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps (TMEM -> registers -> global) =====================
+        const int lane_base = (warp & 3) * 32;    // TMEM lane quarter this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int n_blk = t % g.tiles_n;  t /= g.tiles_n;
+            const int m_blk = t % g.tiles_m;  t /= g.tiles_m;
+            t /= g.splits;
+            const int b0 = t % g.nb0;
+            const int b1 = t / g.nb0;
+            const int m = m_blk * kBM + lane_base + lane;
+            const int n0 = n_blk * BN;
+            const bool row_ok = m < g.M;
+            const long long d_off = b1 * g.d_sb1 + b0 * g.d_sb0 + static_cast<long long>(m) * g.d_sm;
+            const long long r_off = b1 * g.r_sb1 + b0 * g.r_sb0 + static_cast<long long>(m) * g.r_sm;
+            const __nv_bfloat16* bias_row = nullptr;
+            if (g.bias) bias_row = g.bias + (g.bias_rows ? (m / g.bias_rows) * g.bias_sb : 0);
+
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + static_cast<uint32_t>(acc * kMaxBN);
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t raw[16];
+                tmem_ld16(taddr + c0, raw);
+                tmem_ld_wait();
+                const int n = n0 + c0;
+                if (!row_ok || n >= g.N) continue;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * g.alpha;
+                const bool full = (n + 16 <= g.N);
+                if (bias_row) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (full || n + j < g.N) v[j] += __bfloat162float(bias_row[n + j]);
+                }
+                if (g.R) {
+                    const __nv_bfloat16* rp = g.R + r_off + static_cast<long long>(n) * g.r_sn;
+                    if (full && g.r_sn == 1 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+                        const uint4 q0 = *reinterpret_cast<const uint4*>(rp);
+                        const uint4 q1 = *reinterpret_cast<const uint4*>(rp + 8);
+                        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+                            v[2 * j] += __bfloat162float(h.x);
+                            v[2 * j + 1] += __bfloat162float(h.y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (full || n + j < g.N) v[j] += __bfloat162float(rp[j * g.r_sn]);
+                    }
+                }
+                if (g.d_fp32) {
+                    float* dp = reinterpret_cast<float*>(g.D) + d_off + static_cast<long long>(n) * g.d_sn;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (full || n + j < g.N) {
+                            if (g.d_atomic) atomicAdd(dp + j * g.d_sn, v[j]);
+                            else dp[j * g.d_sn] = v[j];
+                        }
+                    }
+                } else {
+                    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.D) + d_off + static_cast<long long>(n) * g.d_sn;
+                    if (full && g.d_sn == 1 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        *reinterpret_cast<uint4*>(dp) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(dp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (full || n + j < g.N) dp[j * g.d_sn] = __float2bfloat16_rn(v[j]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace b200

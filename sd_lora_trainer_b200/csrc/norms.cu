@@ -1,0 +1,339 @@
+// GroupNorm(+SiLU) and LayerNorm, forward and input-gradient, on NHWC bf16 activations ([rows, C], C contiguous).
+// HBM-bound: every pass reads/writes whole 16-byte vectors with consecutive threads on consecutive addresses.
+// Affine parameters are frozen in LoRA training, so no d(gamma)/d(beta) reductions exist anywhere.
+#include "common.cuh"
+#include "../../include/b200_lora.h"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm.  Pass 1 reduces per-(image, group) sums into a double workspace; pass 2 finalises
+// (mean, rstd); pass 3 normalises.  A block owns `k` rows x all channels per iteration so each
+// thread keeps a FIXED 8-channel vector and accumulates in registers.
+// ---------------------------------------------------------------------------------------------
+template <bool kBackward, bool kSilu>
+__global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                 const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                 const float* __restrict__ stats, double* __restrict__ ws, long long hw, int C,
+                                 int groups, int rows_per_block) {
+    __shared__ float gsum[2 * 64];
+    const int C8 = C >> 3, cpg = C / groups;
+    const int b = blockIdx.y;
+    const int v = threadIdx.x % C8, roff = threadIdx.x / C8, k = blockDim.x / C8;
+    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, hw);
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) gsum[i] = 0.f;
+    __syncthreads();
+
+    float a0[8], a1[8], gm[8], bt[8], mean[8], rstd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+    if (kBackward) {
+        load8(gamma + v * 8, gm);
+        load8(beta + v * 8, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (v * 8 + i) / cpg;
+            mean[i] = stats[(b * groups + g) * 2];
+            rstd[i] = stats[(b * groups + g) * 2 + 1];
+        }
+    }
+    const bf16* xb = x + static_cast<long long>(b) * hw * C;
+    const bf16* dyb = kBackward ? dy + static_cast<long long>(b) * hw * C : nullptr;
+    for (long long r = r0 + roff; r < r1; r += k) {
+        float f[8];
+        load8(xb + r * C + v * 8, f);
+        if (!kBackward) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a0[i] += f[i];
+                a1[i] += f[i] * f[i];
+            }
+        } else {
+            float d[8];
+            load8(dyb + r * C + v * 8, d);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float xh = (f[i] - mean[i]) * rstd[i];
+                float dz = d[i];
+                if (kSilu) dz = bfr(dz * dsilu_f(bfr(xh * gm[i] + bt[i])));
+                const float t = dz * gm[i];
+                a0[i] += t;
+                a1[i] += t * xh;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int g = (v * 8 + i) / cpg;
+        atomicAdd(&gsum[2 * g], a0[i]);
+        atomicAdd(&gsum[2 * g + 1], a1[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
+        atomicAdd(&ws[static_cast<long long>(b) * groups * 2 + i], static_cast<double>(gsum[i]));
+}
+
+__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int n, double count,
+                                   float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mean = ws[2 * i] / count;
+    double var = ws[2 * i + 1] / count - mean * mean;
+    if (var < 0) var = 0;
+    stats[2 * i] = static_cast<float>(mean);
+    stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+
+template <bool kSilu>
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma,
+                                const bf16* __restrict__ beta, const float* __restrict__ stats, bf16* __restrict__ y,
+                                long long hw, int C, int groups, long long total_vec) {
+    const int C8 = C >> 3, cpg = C / groups;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_vec;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(idx % C8);
+        const int b = static_cast<int>(idx / (hw * C8));
+        float f[8], gm[8], bt[8], o[8];
+        load8(x + idx * 8, f);
+        load8(gamma + v * 8, gm);
+        load8(beta + v * 8, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (v * 8 + i) / cpg;
+            const float mean = stats[(b * groups + g) * 2], rstd = stats[(b * groups + g) * 2 + 1];
+            float z = (f[i] - mean) * rstd * gm[i] + bt[i];
+            if (kSilu) z = silu_f(bfr(z));
+            o[i] = z;
+        }
+        store8(y + idx * 8, o);
+    }
+}
+
+template <bool kSilu>
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                    const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                    const float* __restrict__ stats, const double* __restrict__ ws,
+                                    bf16* __restrict__ dx, long long hw, int C, int groups, long long total_vec) {
+    const int C8 = C >> 3, cpg = C / groups;
+    const float inv_n = 1.f / (static_cast<float>(hw) * cpg);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_vec;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(idx % C8);
+        const int b = static_cast<int>(idx / (hw * C8));
+        float f[8], d[8], gm[8], bt[8], o[8];
+        load8(x + idx * 8, f);
+        load8(dy + idx * 8, d);
+        load8(gamma + v * 8, gm);
+        load8(beta + v * 8, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (v * 8 + i) / cpg;
+            const int sg = b * groups + g;
+            const float mean = stats[sg * 2], rstd = stats[sg * 2 + 1];
+            const float s1 = static_cast<float>(ws[sg * 2]) * inv_n, s2 = static_cast<float>(ws[sg * 2 + 1]) * inv_n;
+            const float xh = (f[i] - mean) * rstd;
+            float dz = d[i];
+            if (kSilu) dz = bfr(dz * dsilu_f(bfr(xh * gm[i] + bt[i])));
+            o[i] = rstd * (dz * gm[i] - s1 - xh * s2);
+        }
+        store8(dx + idx * 8, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim: one warp per row, the row stays in registers (C <= 2560).
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 10;   // 10 * 32 lanes * 8 = 2560 channels
+
+template <bool kBackward, int NV>
+__global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                 const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                 float* __restrict__ stats, bf16* __restrict__ out, long long rows, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int C8 = C >> 3;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; row < rows; row += warps) {
+        float f[NV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int v = lane + j * 32;
+            if (v < C8) {
+                load8(x + row * C + v * 8, f[j]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s += f[j][i];
+            }
+        }
+        float mean, rstd;
+        if (!kBackward) {
+            mean = warp_sum(s) / C;
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                if (lane + j * 32 < C8) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float d = f[j][i] - mean;
+                        q += d * d;
+                    }
+                }
+            }
+            rstd = rsqrtf(warp_sum(q) / C + eps);
+            if (lane == 0) {
+                stats[row * 2] = mean;
+                stats[row * 2 + 1] = rstd;
+            }
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int v = lane + j * 32;
+                if (v < C8) {
+                    float gm[8], bt[8], o[8];
+                    load8(gamma + v * 8, gm);
+                    load8(beta + v * 8, bt);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = (f[j][i] - mean) * rstd * gm[i] + bt[i];
+                    store8(out + row * C + v * 8, o);
+                }
+            }
+        } else {
+            mean = stats[row * 2];
+            rstd = stats[row * 2 + 1];
+            float t[NV][8];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int v = lane + j * 32;
+                if (v < C8) {
+                    float gm[8], d[8];
+                    load8(gamma + v * 8, gm);
+                    load8(dy + row * C + v * 8, d);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        f[j][i] = (f[j][i] - mean) * rstd;   // x-hat
+                        t[j][i] = d[i] * gm[i];
+                        s1 += t[j][i];
+                        s2 += t[j][i] * f[j][i];
+                    }
+                }
+            }
+            s1 = warp_sum(s1) / C;
+            s2 = warp_sum(s2) / C;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int v = lane + j * 32;
+                if (v < C8) {
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = rstd * (t[j][i] - s1 - f[j][i] * s2);
+                    store8(out + row * C + v * 8, o);
+                }
+            }
+        }
+    }
+}
+
+static int gn_block_threads(int C8) {
+    int k = 256 / C8;
+    if (k < 1) k = 1;
+    return C8 * k;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_groupnorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats,
+                                  int32_t batch, int64_t hw, int32_t C, int32_t groups, float eps, int32_t silu,
+                                  void* stream) {
+    B200_CHECK_ARG(C % 8 == 0 && C % groups == 0 && groups <= 64 && C / 8 <= 1024, "groupnorm: unsupported C=%d groups=%d", C, groups);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // workspace: the double accumulators live right behind the float stats the caller allocated
+    // ([batch, groups, 2] fp32 stats + [batch, groups, 2] fp64 workspace => caller passes 6 floats per (b, g)).
+    double* ws = reinterpret_cast<double*>(stats + static_cast<size_t>(batch) * groups * 2);
+    cudaMemsetAsync(ws, 0, sizeof(double) * batch * groups * 2, st);
+    const int C8 = C / 8, T = gn_block_threads(C8), k = T / C8;
+    long long splits = (kNumSMs * 4 + batch - 1) / batch;
+    long long rpb = (hw + splits - 1) / splits;
+    if (rpb < k * 4) rpb = k * 4;
+    splits = (hw + rpb - 1) / rpb;
+    dim3 grid(static_cast<unsigned>(splits), batch);
+    gn_reduce_kernel<false, false><<<grid, T, 0, st>>>(static_cast<const bf16*>(x), nullptr, nullptr, nullptr, nullptr,
+                                                       ws, hw, C, groups, static_cast<int>(rpb));
+    B200_CHECK_LAUNCH("gn_reduce");
+    gn_finalize_kernel<<<(batch * groups + 127) / 128, 128, 0, st>>>(ws, stats, batch * groups,
+                                                                     static_cast<double>(hw) * (C / groups), eps);
+    B200_CHECK_LAUNCH("gn_finalize");
+    const long long total = static_cast<long long>(batch) * hw * C8;
+    const int blocks = grid_for(total, 256);
+    if (silu)
+        gn_apply_kernel<true><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(gamma),
+                                                      static_cast<const bf16*>(beta), stats, static_cast<bf16*>(y), hw,
+                                                      C, groups, total);
+    else
+        gn_apply_kernel<false><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(gamma),
+                                                       static_cast<const bf16*>(beta), stats, static_cast<bf16*>(y), hw,
+                                                       C, groups, total);
+    B200_CHECK_LAUNCH("gn_apply");
+    return 0;
+}
+
+extern "C" int b200_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const void* beta,
+                                  const float* stats, void* dx, int32_t batch, int64_t hw, int32_t C, int32_t groups,
+                                  int32_t silu, void* stream) {
+    B200_CHECK_ARG(C % 8 == 0 && C % groups == 0 && groups <= 64 && C / 8 <= 1024, "groupnorm_bwd: unsupported C=%d groups=%d", C, groups);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* ws = reinterpret_cast<double*>(const_cast<float*>(stats) + static_cast<size_t>(batch) * groups * 2);
+    cudaMemsetAsync(ws, 0, sizeof(double) * batch * groups * 2, st);
+    const int C8 = C / 8, T = gn_block_threads(C8), k = T / C8;
+    long long splits = (kNumSMs * 4 + batch - 1) / batch;
+    long long rpb = (hw + splits - 1) / splits;
+    if (rpb < k * 4) rpb = k * 4;
+    splits = (hw + rpb - 1) / rpb;
+    dim3 grid(static_cast<unsigned>(splits), batch);
+    const bf16 *xp = static_cast<const bf16*>(x), *dyp = static_cast<const bf16*>(dy);
+    const bf16 *gp = static_cast<const bf16*>(gamma), *bp = static_cast<const bf16*>(beta);
+    if (silu)
+        gn_reduce_kernel<true, true><<<grid, T, 0, st>>>(xp, dyp, gp, bp, stats, ws, hw, C, groups, static_cast<int>(rpb));
+    else
+        gn_reduce_kernel<true, false><<<grid, T, 0, st>>>(xp, dyp, gp, bp, stats, ws, hw, C, groups, static_cast<int>(rpb));
+    B200_CHECK_LAUNCH("gn_bwd_reduce");
+    const long long total = static_cast<long long>(batch) * hw * C8;
+    const int blocks = grid_for(total, 256);
+    if (silu)
+        gn_bwd_apply_kernel<true><<<blocks, 256, 0, st>>>(dyp, xp, gp, bp, stats, ws, static_cast<bf16*>(dx), hw, C, groups, total);
+    else
+        gn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(dyp, xp, gp, bp, stats, ws, static_cast<bf16*>(dx), hw, C, groups, total);
+    B200_CHECK_LAUNCH("gn_bwd_apply");
+    return 0;
+}
+
+extern "C" int b200_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats,
+                                  int64_t rows, int32_t C, float eps, void* stream) {
+    B200_CHECK_ARG(C % 8 == 0 && C <= kLnMaxVec * 256, "layernorm: unsupported C=%d", C);
+    const int blocks = grid_for(rows * 32, 256);
+    const int nv = (C / 8 + 31) / 32;
+#define LN_FWD(NV)                                                                                              \
+    layernorm_kernel<false, NV><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(                         \
+        static_cast<const bf16*>(x), nullptr, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), stats, \
+        static_cast<bf16*>(y), rows, C, eps)
+    if (nv <= 2) LN_FWD(2); else if (nv <= 5) LN_FWD(5); else LN_FWD(10);
+#undef LN_FWD
+    B200_CHECK_LAUNCH("layernorm_fwd");
+    return 0;
+}
+
+extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* stats, void* dx,
+                                  int64_t rows, int32_t C, void* stream) {
+    B200_CHECK_ARG(C % 8 == 0 && C <= kLnMaxVec * 256, "layernorm_bwd: unsupported C=%d", C);
+    const int blocks = grid_for(rows * 32, 256);
+    const int nv = (C / 8 + 31) / 32;
+#define LN_BWD(NV)                                                                                              \
+    layernorm_kernel<true, NV><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(                          \
+        static_cast<const bf16*>(x), static_cast<const bf16*>(dy), static_cast<const bf16*>(gamma), nullptr,    \
+        const_cast<float*>(stats), static_cast<bf16*>(dx), rows, C, 0.f)
+    if (nv <= 2) LN_BWD(2); else if (nv <= 5) LN_BWD(5); else LN_BWD(10);
+#undef LN_BWD
+    B200_CHECK_LAUNCH("layernorm_bwd");
+    return 0;
+}

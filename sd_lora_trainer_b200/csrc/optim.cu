@@ -1,0 +1,183 @@
+// Step prologue (offset noise + DDPM add_noise), min-SNR weights, masked epsilon-MSE loss with fused dPred, the
+// L1 |p| reduction, and the fused AdamW (+ L1 sign-gradient, + textual-inversion rows) update.
+// All HBM-bound, one pass each.
+#include "common.cuh"
+#include "../../include/b200_lora.h"
+
+namespace b200 {
+
+// main.py:311-326 + diffusers DDPMScheduler.add_noise, with torch's per-op bf16 roundings reproduced:
+//   x0 = bf16(latent); noise = bf16(noise + s*offset); a = bf16(acp[t]); sa = bf16(sqrt(a)); so = bf16(sqrt(bf16(1-a)))
+//   noisy = bf16(bf16(sa*x0) + bf16(so*noise))
+__global__ void noise_prologue_kernel(const float* __restrict__ latent, bf16* __restrict__ noise,
+                                      const float* __restrict__ offset, float offset_scale,
+                                      const float* __restrict__ acp, const long long* __restrict__ timesteps,
+                                      bf16* __restrict__ noisy_nchw, bf16* __restrict__ noisy_nhwc8, int B, int C, int HW) {
+    const long long total = static_cast<long long>(B) * C * HW;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int p = static_cast<int>(idx % HW);
+        const int c = static_cast<int>((idx / HW) % C);
+        const int b = static_cast<int>(idx / (static_cast<long long>(HW) * C));
+        const float a = bfr(acp[timesteps[b]]);
+        const float sa = bfr(sqrtf(a)), so = bfr(sqrtf(bfr(1.f - a)));
+        const float x0 = bfr(latent[idx]);
+        float nz = __bfloat162float(noise[idx]);
+        if (offset) nz = bfr(nz + offset_scale * offset[b * C + c]);
+        noise[idx] = __float2bfloat16_rn(nz);
+        const bf16 out = __float2bfloat16_rn(bfr(sa * x0) + bfr(so * nz));
+        noisy_nchw[idx] = out;
+        if (noisy_nhwc8) noisy_nhwc8[(static_cast<long long>(b) * HW + p) * 8 + c] = out;
+    }
+}
+
+// trainer/loss.py:83-106,145-161: w_b = (min(snr_b, gamma) / snr_b) / mean_b(...)   (epsilon prediction)
+__global__ void snr_weights_kernel(const float* __restrict__ acp, const long long* __restrict__ timesteps,
+                                   float snr_gamma, float* __restrict__ weights, int B) {
+    __shared__ float red[32];
+    float w = 0.f;
+    if (threadIdx.x < B) {
+        const float a = acp[timesteps[threadIdx.x]];
+        const float sa = sqrtf(a), so = sqrtf(1.f - a);
+        const float r = sa / so;
+        const float snr = r * r;
+        w = fminf(snr, snr_gamma) / snr;
+    }
+    const float total = block_sum(w, red);
+    if (threadIdx.x < B) weights[threadIdx.x] = w / (total / B);
+}
+
+// loss = (1/B) sum_b w_b * mean_{c,p}( bf16((bf16(pred - noise))^2) * mask ); dpred NHWC (ld_dpred) bf16.
+__global__ void diffusion_loss_kernel(const bf16* __restrict__ pred, long long ld_pred, const bf16* __restrict__ noise,
+                                      const float* __restrict__ mask, const float* __restrict__ weights,
+                                      float loss_scale, float* __restrict__ loss_out, bf16* __restrict__ dpred,
+                                      long long ld_dpred, int B, int C, int HW) {
+    __shared__ float red[32];
+    const long long total = static_cast<long long>(B) * HW * C;
+    const float inv = 1.f / (static_cast<float>(C) * HW * B);
+    float acc = 0.f;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % C);
+        const long long bp = idx / C;          // b*HW + p
+        const int p = static_cast<int>(bp % HW);
+        const int b = static_cast<int>(bp / HW);
+        const long long nchw = (static_cast<long long>(b) * C + c) * HW + p;
+        const float e = bfr(__bfloat162float(pred[bp * ld_pred + c]) - __bfloat162float(noise[nchw]));
+        const float m = mask[nchw];
+        const float w = weights[b];
+        acc += bfr(e * e) * m * w;
+        if (dpred) dpred[bp * ld_dpred + c] = __float2bfloat16_rn(loss_scale * inv * w * m * 2.f * e);
+    }
+    acc = block_sum(acc * inv, red);
+    if (threadIdx.x == 0) atomicAdd(loss_out, acc);
+}
+
+__global__ void abs_sum_kernel(const bf16* __restrict__ p, long long n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        acc += fabsf(__bfloat162float(p[i]));
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// torch.optim.AdamW on bf16 tensors, op for op (torch/optim/adam.py _single_tensor_adam/_multi_tensor_adam):
+//   p  = bf16(p * (1 - lr*wd))
+//   m  = bf16(m + (1-b1) * (g - m))                      (lerp, weight < 0.5 branch)
+//   v  = bf16(bf16(v * b2) + (1-b2) * g * g)             (mul_, addcmul_)
+//   d  = bf16(bf16(bf16(sqrt(v)) / sqrt(bc2)) + eps)     (sqrt, div, add)
+//   p  = bf16(p - (lr/bc1) * (m / d))                    (addcdiv_)
+// with g = bf16(bf16(grad*grad_scale) + l1_coeff*sign(p)) - the L1 penalty's autograd contribution (main.py:353-356).
+struct AdamSeg {
+    float decay;      // (float)(1 - lr*wd), 1.0 => skip the decay op (torch skips it when weight_decay == 0)
+    float neg_step;   // (float)(-(lr / bias_correction1))
+    float l1;
+};
+__global__ void adamw_kernel(bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ m, bf16* __restrict__ v,
+                             long long n, long long n_first, AdamSeg s0, AdamSeg s1, float one_minus_b1, float beta2,
+                             float one_minus_b2, float eps, float bc2_sqrt, float grad_scale, int zero_grad) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const AdamSeg s = i < n_first ? s0 : s1;
+        float pv = __bfloat162float(p[i]);
+        float g = bfr(grad[i] * grad_scale);
+        if (s.l1 != 0.f) g = bfr(g + s.l1 * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f)));
+        if (zero_grad) grad[i] = 0.f;
+        if (s.decay != 1.f) pv = bfr(pv * s.decay);
+        float mv = __bfloat162float(m[i]);
+        mv = bfr(mv + one_minus_b1 * (g - mv));
+        float vv = bfr(__bfloat162float(v[i]) * beta2);
+        vv = bfr(vv + one_minus_b2 * g * g);
+        float d = bfr(sqrtf(vv));
+        d = bfr(d / bc2_sqrt);
+        d = bfr(d + eps);
+        pv = bfr(pv + s.neg_step * (mv / d));
+        p[i] = __float2bfloat16_rn(pv);
+        m[i] = __float2bfloat16_rn(mv);
+        v[i] = __float2bfloat16_rn(vv);
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define ST static_cast<cudaStream_t>(stream)
+
+extern "C" int b200_noise_prologue(const float* latent, void* noise, const float* offset, float offset_scale,
+                                   const float* alphas_cumprod, const int64_t* timesteps, void* noisy_nchw,
+                                   void* noisy_nhwc8, int32_t B, int32_t C, int32_t HW, void* stream) {
+    B200_CHECK_ARG(C <= 8, "noise_prologue: C > 8");
+    noise_prologue_kernel<<<grid_for(1LL * B * C * HW, 256), 256, 0, ST>>>(
+        latent, static_cast<bf16*>(noise), offset, offset_scale, alphas_cumprod,
+        reinterpret_cast<const long long*>(timesteps), static_cast<bf16*>(noisy_nchw), static_cast<bf16*>(noisy_nhwc8), B,
+        C, HW);
+    B200_CHECK_LAUNCH("noise_prologue");
+    return 0;
+}
+
+extern "C" int b200_snr_weights(const float* alphas_cumprod, const int64_t* timesteps, float snr_gamma, float* weights,
+                                int32_t B, void* stream) {
+    B200_CHECK_ARG(B >= 1 && B <= 1024, "snr_weights: B out of range");
+    snr_weights_kernel<<<1, ((B + 31) / 32) * 32, 0, ST>>>(alphas_cumprod, reinterpret_cast<const long long*>(timesteps),
+                                                           snr_gamma, weights, B);
+    B200_CHECK_LAUNCH("snr_weights");
+    return 0;
+}
+
+extern "C" int b200_diffusion_loss(const void* pred, int64_t ld_pred, const void* noise, const float* mask,
+                                   const float* weights, float loss_scale, float* loss_out, void* dpred,
+                                   int64_t ld_dpred, int32_t B, int32_t C, int32_t HW, void* stream) {
+    diffusion_loss_kernel<<<grid_for(1LL * B * C * HW, 256, kNumSMs * 4), 256, 0, ST>>>(
+        static_cast<const bf16*>(pred), ld_pred, static_cast<const bf16*>(noise), mask, weights, loss_scale, loss_out,
+        static_cast<bf16*>(dpred), ld_dpred, B, C, HW);
+    B200_CHECK_LAUNCH("diffusion_loss");
+    return 0;
+}
+
+extern "C" int b200_abs_sum(const void* p, int64_t n, float* out, void* stream) {
+    abs_sum_kernel<<<grid_for(n, 256, kNumSMs * 4), 256, 0, ST>>>(static_cast<const bf16*>(p), n, out);
+    B200_CHECK_LAUNCH("abs_sum");
+    return 0;
+}
+
+extern "C" int b200_adamw(void* p, float* grad, void* m, void* v, int64_t n, int64_t n_first, double lr, double wd,
+                          double l1_coeff, double lr2, double wd2, double beta1, double beta2, double eps, int32_t step,
+                          double grad_scale, int32_t zero_grad, void* stream) {
+    B200_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
+    // scalars are formed in double exactly as torch's Python code forms them, then narrowed once
+    const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+    const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+    AdamSeg s0{wd != 0.0 ? static_cast<float>(1.0 - lr * wd) : 1.f, static_cast<float>(-(lr / bc1)),
+               static_cast<float>(l1_coeff)};
+    AdamSeg s1{wd2 != 0.0 ? static_cast<float>(1.0 - lr2 * wd2) : 1.f, static_cast<float>(-(lr2 / bc1)), 0.f};
+    adamw_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
+                                                   static_cast<bf16*>(v), n, n_first, s0, s1,
+                                                   static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
+                                                   static_cast<float>(1.0 - beta2), static_cast<float>(eps),
+                                                   static_cast<float>(sqrt(bc2)), static_cast<float>(grad_scale),
+                                                   zero_grad);
+    B200_CHECK_LAUNCH("adamw");
+    return 0;
+}

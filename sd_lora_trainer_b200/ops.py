@@ -1,0 +1,280 @@
+"""Torch-tensor front end of the C ABI (include/b200_lora.h).  PyTorch provides memory and the stream; every
+arithmetic op below is one of our sm_100a kernels.  No op here has a torch/CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, Operand, check
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk_dev(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.B200Error("b200 ops need CUDA tensors (there is no CPU path)")
+
+
+@dataclass
+class Mat:
+    """A GEMM operand view.  K-major: [rows = M|N index, inner = K]; MN-major: [rows = K, inner = M|N index]."""
+    t: torch.Tensor
+    rows: int
+    inner: int
+    row_stride: int
+    mn: bool = False
+    sb0: int = 0
+    sb1: int = 0
+    batched: bool = False
+
+    def c(self) -> Operand:
+        return Operand(self.t.data_ptr(), self.rows, self.inner, self.row_stride, self.sb0, self.sb1,
+                       int(self.mn), int(self.batched))
+
+
+def kmajor(t: torch.Tensor) -> Mat:
+    """2-D tensor [rows, K] with unit inner stride used as the K-contiguous operand."""
+    assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    return Mat(t, t.shape[0], t.shape[1], t.stride(0), mn=False)
+
+
+def mnmajor(t: torch.Tensor) -> Mat:
+    """2-D tensor [K, MN] with unit inner stride used as the operand whose M|N index is contiguous."""
+    assert t.dim() == 2 and t.stride(1) == 1, (t.shape, t.stride())
+    return Mat(t, t.shape[0], t.shape[1], t.stride(0), mn=True)
+
+
+@dataclass
+class Conv3x3:
+    """Implicit 3x3 / pad 1 / stride 1 convolution source: NHWC activation [N, H, W, C]."""
+    t: torch.Tensor
+    N: int
+    H: int
+    W: int
+    C: int
+    b_tap_k: int
+    b_tap_n: int = 0
+
+
+def conv_supported(H: int, W: int) -> bool:
+    if W < 1 or W > 128 or 128 % W:
+        return False
+    bh = min(128 // W, H)
+    return H % bh == 0 and 128 % (W * bh) == 0 and (128 // (W * bh) == 1 or bh == H)
+
+
+def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, int]], *,
+         d_strides: Optional[Tuple[int, int, int, int]] = None, alpha: float = 1.0,
+         bias: Optional[torch.Tensor] = None, bias_rows: int = 0, bias_sb: int = 0,
+         residual: Optional[torch.Tensor] = None, r_strides: Optional[Tuple[int, int, int, int]] = None,
+         nb0: int = 1, nb1: int = 1, splits: int = 1, atomic: bool = False, block_n: int = 0) -> torch.Tensor:
+    """out[b1][b0][m, n] = alpha * sum_seg A_seg.B_seg^T (+bias) (+residual).  segs: (A | Conv3x3, B, K)."""
+    _chk_dev(out, bias, residual)
+    d = GemmDesc()
+    d.M, d.N, d.num_seg = M, N, len(segs)
+    for i, (a, b, k) in enumerate(segs):
+        d.K[i] = k
+        if isinstance(a, Conv3x3):
+            assert i == 0
+            d.conv, d.conv_N, d.conv_H, d.conv_W, d.conv_C = 1, a.N, a.H, a.W, a.C
+            d.b_tap_k, d.b_tap_n = a.b_tap_k, a.b_tap_n
+            d.A[i] = Operand(a.t.data_ptr(), 0, 0, 0, 0, 0, 0, 0)
+        else:
+            d.A[i] = a.c()
+        d.B[i] = b.c()
+    d.nb0, d.nb1, d.splits, d.block_n = nb0, nb1, splits, block_n
+    d.D = out.data_ptr()
+    d.d_fp32 = int(out.dtype == torch.float32)
+    assert out.dtype in (torch.float32, BF16)
+    d.d_atomic = int(atomic)
+    if d_strides is None:
+        assert out.dim() == 2 and out.stride(1) == 1
+        d_strides = (out.stride(0), 1, 0, 0)
+    d.d_sm, d.d_sn, d.d_sb0, d.d_sb1 = d_strides
+    d.alpha = alpha
+    d.bias, d.bias_rows, d.bias_sb = _p(bias), bias_rows, bias_sb
+    if residual is not None:
+        assert residual.dtype == BF16
+        if r_strides is None:
+            assert residual.dim() == 2 and residual.stride(1) == 1
+            r_strides = (residual.stride(0), 1, 0, 0)
+        d.R = residual.data_ptr()
+        d.r_sm, d.r_sn, d.r_sb0, d.r_sb1 = r_strides
+    check(_lib.load().b200_gemm(C.byref(d), _stream()), "b200_gemm")
+    return out
+
+
+# ---- softmax ------------------------------------------------------------------------------------
+def softmax_fwd(S: torch.Tensor, P: torch.Tensor, rows: int, cols: int, ld_s: int, ld_p: int):
+    check(_lib.load().b200_softmax_fwd(S.data_ptr(), P.data_ptr(), rows, cols, ld_s, ld_p, _stream()), "softmax_fwd")
+
+
+def softmax_bwd(P: torch.Tensor, dP: torch.Tensor, dS: torch.Tensor, rows: int, cols: int, ld_p: int, ld_dp: int):
+    check(_lib.load().b200_softmax_bwd(P.data_ptr(), dP.data_ptr(), dS.data_ptr(), rows, cols, ld_p, ld_dp, _stream()),
+          "softmax_bwd")
+
+
+# ---- norms / activations -------------------------------------------------------------------------
+def groupnorm_fwd(x: torch.Tensor, gamma, beta, batch: int, hw: int, C_: int, groups: int, eps: float, silu: bool):
+    """x: [batch*hw, C] NHWC.  Returns (y, stats) where stats also carries the fp64 scratch area."""
+    y = torch.empty_like(x)
+    stats = torch.empty(batch * groups * 6, dtype=torch.float32, device=x.device)
+    check(_lib.load().b200_groupnorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                         stats.data_ptr(), batch, hw, C_, groups, eps, int(silu), _stream()), "groupnorm_fwd")
+    return y, stats
+
+
+def groupnorm_bwd(dy, x, gamma, beta, stats, batch: int, hw: int, C_: int, groups: int, silu: bool):
+    dx = torch.empty_like(x)
+    check(_lib.load().b200_groupnorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                         stats.data_ptr(), dx.data_ptr(), batch, hw, C_, groups, int(silu), _stream()),
+          "groupnorm_bwd")
+    return dx
+
+
+def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5):
+    rows, C_ = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty(rows * 2, dtype=torch.float32, device=x.device)
+    check(_lib.load().b200_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                         stats.data_ptr(), rows, C_, eps, _stream()), "layernorm_fwd")
+    return y, stats
+
+
+def layernorm_bwd(dy, x, gamma, stats):
+    rows, C_ = x.shape
+    dx = torch.empty_like(x)
+    check(_lib.load().b200_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), stats.data_ptr(), dx.data_ptr(),
+                                         rows, C_, _stream()), "layernorm_bwd")
+    return dx
+
+
+def geglu_fwd(h: torch.Tensor):
+    rows, two_inner = h.shape
+    y = torch.empty(rows, two_inner // 2, dtype=BF16, device=h.device)
+    check(_lib.load().b200_geglu_fwd(h.data_ptr(), y.data_ptr(), rows, two_inner // 2, _stream()), "geglu_fwd")
+    return y
+
+
+def geglu_bwd(dy: torch.Tensor, h: torch.Tensor):
+    rows, two_inner = h.shape
+    dh = torch.empty_like(h)
+    check(_lib.load().b200_geglu_bwd(dy.data_ptr(), h.data_ptr(), dh.data_ptr(), rows, two_inner // 2, _stream()), "geglu_bwd")
+    return dh
+
+
+def silu_fwd(x: torch.Tensor):
+    y = torch.empty_like(x)
+    check(_lib.load().b200_silu_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "silu_fwd")
+    return y
+
+
+def silu_bwd(dy: torch.Tensor, x: torch.Tensor):
+    dx = torch.empty_like(x)
+    check(_lib.load().b200_silu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "silu_bwd")
+    return dx
+
+
+def add(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    y = torch.empty_like(a) if out is None else out
+    check(_lib.load().b200_add(a.data_ptr(), b.data_ptr(), _p(c), y.data_ptr(), a.numel(), _stream()), "add")
+    return y
+
+
+# ---- layout helpers ------------------------------------------------------------------------------
+def upsample2x_fwd(x: torch.Tensor, N: int, H: int, W: int, C_: int):
+    y = torch.empty(N * 4 * H * W, C_, dtype=BF16, device=x.device)
+    check(_lib.load().b200_upsample2x_fwd(x.data_ptr(), y.data_ptr(), N, H, W, C_, _stream()), "upsample2x_fwd")
+    return y
+
+
+def upsample2x_bwd(dy: torch.Tensor, N: int, H: int, W: int, C_: int):
+    dx = torch.empty(N * H * W, C_, dtype=BF16, device=dy.device)
+    check(_lib.load().b200_upsample2x_bwd(dy.data_ptr(), dx.data_ptr(), N, H, W, C_, _stream()), "upsample2x_bwd")
+    return dx
+
+
+def im2col3x3(x: torch.Tensor, N: int, H: int, W: int, C_: int, stride: int):
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    col = torch.empty(N * Ho * Wo, 9 * C_, dtype=BF16, device=x.device)
+    check(_lib.load().b200_im2col3x3(x.data_ptr(), col.data_ptr(), N, H, W, C_, stride, _stream()), "im2col3x3")
+    return col
+
+
+def col2im3x3(col: torch.Tensor, N: int, H: int, W: int, C_: int, stride: int):
+    dx = torch.empty(N * H * W, C_, dtype=BF16, device=col.device)
+    check(_lib.load().b200_col2im3x3(col.data_ptr(), dx.data_ptr(), N, H, W, C_, stride, _stream()), "col2im3x3")
+    return dx
+
+
+def shift_stack9(U: torch.Tensor, N: int, H: int, W: int, r: int):
+    U9 = torch.empty(N * H * W, 9 * r, dtype=BF16, device=U.device)
+    check(_lib.load().b200_shift_stack9(U.data_ptr(), U9.data_ptr(), N, H, W, r, _stream()), "shift_stack9")
+    return U9
+
+
+def timestep_embedding(t: torch.Tensor, dim: int):
+    t = t.to(torch.float32).contiguous()
+    out = torch.empty(t.numel(), dim, dtype=BF16, device=t.device)
+    check(_lib.load().b200_timestep_embedding(t.data_ptr(), out.data_ptr(), t.numel(), dim, _stream()), "timestep_embedding")
+    return out
+
+
+# ---- prologue / loss / optimizer -------------------------------------------------------------------
+def noise_prologue(latent: torch.Tensor, noise: torch.Tensor, offset: Optional[torch.Tensor], offset_scale: float,
+                   alphas_cumprod: torch.Tensor, timesteps: torch.Tensor):
+    """In-place on `noise`; returns (noisy NCHW bf16, noisy NHWC padded to 8 channels)."""
+    B, Cc, H, W = latent.shape
+    assert latent.dtype == torch.float32 and noise.dtype == BF16 and timesteps.dtype == torch.int64
+    noisy = torch.empty(B, Cc, H, W, dtype=BF16, device=latent.device)
+    nhwc8 = torch.zeros(B * H * W, 8, dtype=BF16, device=latent.device)
+    check(_lib.load().b200_noise_prologue(latent.data_ptr(), noise.data_ptr(), _p(offset), offset_scale,
+                                          alphas_cumprod.data_ptr(), timesteps.data_ptr(), noisy.data_ptr(),
+                                          nhwc8.data_ptr(), B, Cc, H * W, _stream()), "noise_prologue")
+    return noisy, nhwc8
+
+
+def snr_weights(alphas_cumprod: torch.Tensor, timesteps: torch.Tensor, snr_gamma: float):
+    w = torch.empty(timesteps.numel(), dtype=torch.float32, device=timesteps.device)
+    check(_lib.load().b200_snr_weights(alphas_cumprod.data_ptr(), timesteps.data_ptr(), snr_gamma, w.data_ptr(),
+                                       timesteps.numel(), _stream()), "snr_weights")
+    return w
+
+
+def diffusion_loss(pred: torch.Tensor, ld_pred: int, noise: torch.Tensor, mask: torch.Tensor, weights: torch.Tensor,
+                   loss_scale: float, want_grad: bool = True):
+    B, Cc, H, W = noise.shape
+    loss = torch.zeros(1, dtype=torch.float32, device=noise.device)
+    dpred = torch.zeros(B * H * W, 8, dtype=BF16, device=noise.device) if want_grad else None
+    check(_lib.load().b200_diffusion_loss(pred.data_ptr(), ld_pred, noise.data_ptr(), mask.data_ptr(),
+                                          weights.data_ptr(), loss_scale, loss.data_ptr(), _p(dpred), 8, B, Cc, H * W,
+                                          _stream()), "diffusion_loss")
+    return loss, dpred
+
+
+def abs_sum(p: torch.Tensor, out: torch.Tensor):
+    check(_lib.load().b200_abs_sum(p.data_ptr(), p.numel(), out.data_ptr(), _stream()), "abs_sum")
+    return out
+
+
+def adamw(p, grad, m, v, n_first: int, *, lr: float, wd: float, l1_coeff: float, lr2: float, wd2: float,
+          beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, step: int, grad_scale: float = 1.0,
+          zero_grad: bool = True):
+    assert p.dtype == BF16 and m.dtype == BF16 and v.dtype == BF16 and grad.dtype == torch.float32
+    check(_lib.load().b200_adamw(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), n_first,
+                                 lr, wd, l1_coeff, lr2, wd2, beta1, beta2, eps, step, grad_scale, int(zero_grad),
+                                 _stream()), "adamw")
