@@ -95,13 +95,15 @@ int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int
    allocates 6 floats per (image, group), 8-byte aligned; the backward reuses the scratch area. */
 int b200_groupnorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, int32_t batch,
                        int64_t hw, int32_t C, int32_t groups, float eps, int32_t silu, void* stream);
+/* dx = dGroupNorm(dy) (+ dres when non-NULL: the gradient arriving through the residual/shortcut branch) */
 int b200_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const void* beta, const float* stats,
-                       void* dx, int32_t batch, int64_t hw, int32_t C, int32_t groups, int32_t silu, void* stream);
+                       const void* dres, void* dx, int32_t batch, int64_t hw, int32_t C, int32_t groups, int32_t silu,
+                       void* stream);
 /* stats: [rows, 2] fp32 (mean, rstd) */
 int b200_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, int64_t rows,
                        int32_t C, float eps, void* stream);
-int b200_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* stats, void* dx, int64_t rows,
-                       int32_t C, void* stream);
+int b200_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* stats, const void* dres, void* dx,
+                       int64_t rows, int32_t C, void* stream);
 /* h: [rows, 2*inner] = (value | gate); y = value * gelu(gate) (exact erf gelu, rounded like torch's op-by-op bf16) */
 int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, void* stream);
 int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, void* stream);
@@ -119,7 +121,10 @@ int b200_upsample2x_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t 
 int b200_im2col3x3(const void* x, void* col, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, void* stream);
 int b200_col2im3x3(const void* col, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t stride, void* stream);
 /* U9[p, tap*r + j] = U[p - offset(tap), j] (zero outside the image): lets the conv-LoRA backward run as plain GEMMs */
-int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, void* stream);
+int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, int32_t ld_in, int32_t ld_out,
+                      void* stream);
+/* out[b, c] = sum_p x[b, p, c]  (x: [batch, hw, C] bf16) - gradient of the per-image time-embedding bias */
+int b200_colsum(const void* x, void* out, int32_t batch, int64_t hw, int32_t C, void* stream);
 /* sinusoidal timestep embedding (flip_sin_to_cos, shift 0): t fp32 [n] -> bf16 [n, dim] */
 int b200_timestep_embedding(const float* t, void* out, int32_t n, int32_t dim, void* stream);
 

@@ -37,10 +37,10 @@ SIGNATURES = {
     "b200_softmax_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_groupnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32,
                            c_float, c_int32, c_void_p],
-    "b200_groupnorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32,
-                           c_int32, c_int32, c_void_p],
+    "b200_groupnorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
+                           c_int32, c_int32, c_int32, c_void_p],
     "b200_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p],
-    "b200_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
+    "b200_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
     "b200_geglu_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_void_p],
     "b200_geglu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
     "b200_silu_fwd": [c_void_p, c_void_p, c_int64, c_void_p],
@@ -50,7 +50,8 @@ SIGNATURES = {
     "b200_upsample2x_bwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_im2col3x3": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_col2im3x3": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
-    "b200_shift_stack9": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    "b200_shift_stack9": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    "b200_colsum": [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p],
     "b200_timestep_embedding": [c_void_p, c_void_p, c_int32, c_int32, c_void_p],
     "b200_noise_prologue": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                             c_int32, c_int32, c_void_p],

@@ -296,8 +296,28 @@ __global__ void col2im3x3_kernel(const bf16* __restrict__ col, bf16* __restrict_
     }
 }
 
+// out[b, c] = sum_p x[b, p, c]   (d(time-embedding projection) = per-image column sum of d(conv1 output))
+__global__ void colsum_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long hw, int C) {
+    __shared__ float part[8][32];
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;    // 8 row lanes
+    float acc = 0.f;
+    if (c < C)
+        for (long long p = ry; p < hw; p += 8) acc += __bfloat162float(x[(static_cast<long long>(b) * hw + p) * C + c]);
+    part[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
+        out[static_cast<long long>(b) * C + c] = __float2bfloat16_rn(s);
+    }
+}
+
 // U9[p, tap*r + j] = U[p - off(tap), j]
-__global__ void shift_stack9_kernel(const bf16* __restrict__ U, bf16* __restrict__ U9, int N, int H, int W, int r) {
+__global__ void shift_stack9_kernel(const bf16* __restrict__ U, bf16* __restrict__ U9, int N, int H, int W, int r,
+                                    int ld_in, int ld_out) {
     const long long total = static_cast<long long>(N) * H * W * 9 * r;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -309,8 +329,8 @@ __global__ void shift_stack9_kernel(const bf16* __restrict__ U, bf16* __restrict
         const int n = static_cast<int>(p / H);
         const int hs = h - (tap / 3 - 1), ws = w - (tap % 3 - 1);
         bf16 val = __float2bfloat16_rn(0.f);
-        if (hs >= 0 && hs < H && ws >= 0 && ws < W) val = U[((static_cast<long long>(n) * H + hs) * W + ws) * r + j];
-        U9[idx] = val;
+        if (hs >= 0 && hs < H && ws >= 0 && ws < W) val = U[((static_cast<long long>(n) * H + hs) * W + ws) * ld_in + j];
+        U9[((static_cast<long long>(n) * H + h) * W + w) * ld_out + tap * r + j] = val;
     }
 }
 
@@ -427,9 +447,17 @@ extern "C" int b200_col2im3x3(const void* col, void* dx, int32_t N, int32_t H, i
     B200_CHECK_LAUNCH("col2im3x3");
     return 0;
 }
-extern "C" int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, void* stream) {
-    shift_stack9_kernel<<<grid_for(9LL * N * H * W * r, 256), 256, 0, ST>>>(static_cast<const bf16*>(U),
-                                                                            static_cast<bf16*>(U9), N, H, W, r);
+extern "C" int b200_colsum(const void* x, void* out, int32_t batch, int64_t hw, int32_t C, void* stream) {
+    dim3 grid((C + 31) / 32, batch);
+    colsum_kernel<<<grid, 256, 0, ST>>>(static_cast<const bf16*>(x), static_cast<bf16*>(out), hw, C);
+    B200_CHECK_LAUNCH("colsum");
+    return 0;
+}
+extern "C" int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, int32_t ld_in,
+                                 int32_t ld_out, void* stream) {
+    B200_CHECK_ARG(ld_in >= r && ld_out >= 9 * r, "shift_stack9: bad leading dims");
+    shift_stack9_kernel<<<grid_for(9LL * N * H * W * r, 256), 256, 0, ST>>>(
+        static_cast<const bf16*>(U), static_cast<bf16*>(U9), N, H, W, r, ld_in, ld_out);
     B200_CHECK_LAUNCH("shift_stack9");
     return 0;
 }

@@ -114,7 +114,8 @@ template <bool kSilu>
 __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                     const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
                                     const float* __restrict__ stats, const double* __restrict__ ws,
-                                    bf16* __restrict__ dx, long long hw, int C, int groups, long long total_vec) {
+                                    const bf16* __restrict__ dres, bf16* __restrict__ dx, long long hw, int C,
+                                    int groups, long long total_vec) {
     const int C8 = C >> 3, cpg = C / groups;
     const float inv_n = 1.f / (static_cast<float>(hw) * cpg);
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_vec;
@@ -136,6 +137,12 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
             float dz = d[i];
             if (kSilu) dz = bfr(dz * dsilu_f(bfr(xh * gm[i] + bt[i])));
             o[i] = rstd * (dz * gm[i] - s1 - xh * s2);
+        }
+        if (dres) {
+            float rr[8];
+            load8(dres + idx * 8, rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = bfr(o[i]) + rr[i];
         }
         store8(dx + idx * 8, o);
     }
@@ -226,6 +233,12 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restr
                     float o[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] = rstd * (t[j][i] - s1 - f[j][i] * s2);
+                    if (beta) {   // backward: `beta` carries the residual-branch gradient to add
+                        float rr[8];
+                        load8(beta + row * C + v * 8, rr);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = bfr(o[i]) + rr[i];
+                    }
                     store8(out + row * C + v * 8, o);
                 }
             }
@@ -279,8 +292,8 @@ extern "C" int b200_groupnorm_fwd(const void* x, const void* gamma, const void* 
 }
 
 extern "C" int b200_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const void* beta,
-                                  const float* stats, void* dx, int32_t batch, int64_t hw, int32_t C, int32_t groups,
-                                  int32_t silu, void* stream) {
+                                  const float* stats, const void* dres, void* dx, int32_t batch, int64_t hw, int32_t C,
+                                  int32_t groups, int32_t silu, void* stream) {
     B200_CHECK_ARG(C % 8 == 0 && C % groups == 0 && groups <= 64 && C / 8 <= 1024, "groupnorm_bwd: unsupported C=%d groups=%d", C, groups);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* ws = reinterpret_cast<double*>(const_cast<float*>(stats) + static_cast<size_t>(batch) * groups * 2);
@@ -301,9 +314,9 @@ extern "C" int b200_groupnorm_bwd(const void* dy, const void* x, const void* gam
     const long long total = static_cast<long long>(batch) * hw * C8;
     const int blocks = grid_for(total, 256);
     if (silu)
-        gn_bwd_apply_kernel<true><<<blocks, 256, 0, st>>>(dyp, xp, gp, bp, stats, ws, static_cast<bf16*>(dx), hw, C, groups, total);
+        gn_bwd_apply_kernel<true><<<blocks, 256, 0, st>>>(dyp, xp, gp, bp, stats, ws, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), hw, C, groups, total);
     else
-        gn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(dyp, xp, gp, bp, stats, ws, static_cast<bf16*>(dx), hw, C, groups, total);
+        gn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(dyp, xp, gp, bp, stats, ws, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), hw, C, groups, total);
     B200_CHECK_LAUNCH("gn_bwd_apply");
     return 0;
 }
@@ -323,14 +336,15 @@ extern "C" int b200_layernorm_fwd(const void* x, const void* gamma, const void* 
     return 0;
 }
 
-extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* stats, void* dx,
-                                  int64_t rows, int32_t C, void* stream) {
+extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* stats,
+                                  const void* dres, void* dx, int64_t rows, int32_t C, void* stream) {
     B200_CHECK_ARG(C % 8 == 0 && C <= kLnMaxVec * 256, "layernorm_bwd: unsupported C=%d", C);
     const int blocks = grid_for(rows * 32, 256);
     const int nv = (C / 8 + 31) / 32;
 #define LN_BWD(NV)                                                                                              \
     layernorm_kernel<true, NV><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(                          \
-        static_cast<const bf16*>(x), static_cast<const bf16*>(dy), static_cast<const bf16*>(gamma), nullptr,    \
+        static_cast<const bf16*>(x), static_cast<const bf16*>(dy), static_cast<const bf16*>(gamma),             \
+        static_cast<const bf16*>(dres),                                                                         \
         const_cast<float*>(stats), static_cast<bf16*>(dx), rows, C, 0.f)
     if (nv <= 2) LN_BWD(2); else if (nv <= 5) LN_BWD(5); else LN_BWD(10);
 #undef LN_BWD

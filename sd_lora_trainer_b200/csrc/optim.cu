@@ -109,7 +109,7 @@ __global__ void adamw_kernel(bf16* __restrict__ p, float* __restrict__ grad, bf1
         float mv = __bfloat162float(m[i]);
         mv = bfr(mv + one_minus_b1 * (g - mv));
         float vv = bfr(__bfloat162float(v[i]) * beta2);
-        vv = bfr(vv + one_minus_b2 * g * g);
+        vv = bfr(vv + one_minus_b2 * (g * g));   // ATen foreach addcmul: self + scalar * (t1 * t2)
         float d = bfr(sqrtf(vv));
         d = bfr(d / bc2_sqrt);
         d = bfr(d + eps);

@@ -137,10 +137,10 @@ def groupnorm_fwd(x: torch.Tensor, gamma, beta, batch: int, hw: int, C_: int, gr
     return y, stats
 
 
-def groupnorm_bwd(dy, x, gamma, beta, stats, batch: int, hw: int, C_: int, groups: int, silu: bool):
+def groupnorm_bwd(dy, x, gamma, beta, stats, batch: int, hw: int, C_: int, groups: int, silu: bool, dres=None):
     dx = torch.empty_like(x)
     check(_lib.load().b200_groupnorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                         stats.data_ptr(), dx.data_ptr(), batch, hw, C_, groups, int(silu), _stream()),
+                                         stats.data_ptr(), _p(dres), dx.data_ptr(), batch, hw, C_, groups, int(silu), _stream()),
           "groupnorm_bwd")
     return dx
 
@@ -154,11 +154,11 @@ def layernorm_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5):
     return y, stats
 
 
-def layernorm_bwd(dy, x, gamma, stats):
+def layernorm_bwd(dy, x, gamma, stats, dres=None):
     rows, C_ = x.shape
     dx = torch.empty_like(x)
-    check(_lib.load().b200_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), stats.data_ptr(), dx.data_ptr(),
-                                         rows, C_, _stream()), "layernorm_bwd")
+    check(_lib.load().b200_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), stats.data_ptr(), _p(dres),
+                                         dx.data_ptr(), rows, C_, _stream()), "layernorm_bwd")
     return dx
 
 
@@ -222,9 +222,18 @@ def col2im3x3(col: torch.Tensor, N: int, H: int, W: int, C_: int, stride: int):
 
 
 def shift_stack9(U: torch.Tensor, N: int, H: int, W: int, r: int):
-    U9 = torch.empty(N * H * W, 9 * r, dtype=BF16, device=U.device)
-    check(_lib.load().b200_shift_stack9(U.data_ptr(), U9.data_ptr(), N, H, W, r, _stream()), "shift_stack9")
+    """U: [N*H*W, ld_in >= r] -> U9: [N*H*W, roundup8(9 r)] (only the first 9r columns are written)."""
+    ld_in = U.stride(0)
+    ld_out = (9 * r + 7) // 8 * 8
+    U9 = torch.empty(N * H * W, ld_out, dtype=BF16, device=U.device)
+    check(_lib.load().b200_shift_stack9(U.data_ptr(), U9.data_ptr(), N, H, W, r, ld_in, ld_out, _stream()), "shift_stack9")
     return U9
+
+
+def colsum(x: torch.Tensor, batch: int, hw: int, C_: int):
+    out = torch.empty(batch, C_, dtype=BF16, device=x.device)
+    check(_lib.load().b200_colsum(x.data_ptr(), out.data_ptr(), batch, hw, C_, _stream()), "colsum")
+    return out
 
 
 def timestep_embedding(t: torch.Tensor, dim: int):
