@@ -15,6 +15,8 @@ BF16 = torch.bfloat16
 
 
 def _stream() -> int:
+    if not torch.cuda.is_available():
+        raise _lib.B200Error("no CUDA device: the B200 training step has no CPU path")
     return torch.cuda.current_stream().cuda_stream
 
 

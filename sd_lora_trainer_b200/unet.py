@@ -1,0 +1,681 @@
+"""B200-native LoRA UNet executor: explicit forward AND backward over the sm_100a kernels (ops.py), no autograd
+inside.  Stands in for ``unet(...)`` + ``loss.backward()`` of the reference step (main.py:329-336, 363) with the
+PEFT-wrapped diffusers UNet2DConditionModel behind it:
+
+  * activations are NHWC ``[B*H*W, C]`` bf16 so every conv / linear is a K-major tcgen05 GEMM operand;
+  * every LoRA target (to_q/to_k/to_v/to_out.0/conv2, trainer/optimizer.py:84) runs ``W.x + s.B.(A.x)`` as ONE
+    dual-segment GEMM; its backward emits dX (frozen W read MN-major - no transposed copies, no dW) and
+    accumulates dA/dB straight into one flat fp32 gradient buffer (split-K atomics);
+  * frozen affine/bias parameters never get gradients;
+  * attention keeps P = softmax(QK^T/sqrt(d)) resident in HBM for the backward (180 GB makes that the cheap
+    choice) and exposes the head-summed pre-softmax cross-attention scores the reference's
+    DAAMLossAttnProcessor2_0 captures (trainer/ti_cross_attn_loss.py:201-212) as ONE full-width GEMM, since
+    sum_h q_h.k_h == q.k over all channels.
+Parameter names follow diffusers / PEFT so reference checkpoints load unchanged.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .arch import UNetArch
+from .ops import BF16, Conv3x3, Mat, kmajor, mnmajor
+
+LORA_TARGETS = ("to_k", "to_q", "to_v", "to_out.0", "conv2")      # trainer/optimizer.py:84
+_SMS = 148
+
+
+def _r8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _wgrad_splits(out_rows: int, reduce_len: int) -> int:
+    tiles = (out_rows + 127) // 128
+    kblocks = (reduce_len + 63) // 64
+    return max(1, min(_SMS // max(tiles, 1), kblocks, 32))
+
+
+# =================================================================================================
+# LoRA parameter store: ONE flat bf16 parameter buffer, ONE flat fp32 gradient buffer, bf16 Adam moments
+# =================================================================================================
+class LoraSlot:
+    __slots__ = ("name", "kind", "r", "rs", "fan_in", "fan_out", "offA", "offB", "store")
+
+    def __init__(self, name, kind, r, fan_in, fan_out):
+        self.name, self.kind, self.r, self.rs = name, kind, r, _r8(r)
+        self.fan_in, self.fan_out = fan_in, fan_out
+        self.offA = self.offB = -1
+        self.store = None
+
+    # A: linear [r, K]; conv [9*r, Cin] (tap-major master layout).  B: [N, rs] with columns >= r kept at zero.
+    @property
+    def a_rows(self):
+        return self.r if self.kind == "linear" else 9 * self.r
+
+    @property
+    def numel_logical(self):
+        return self.a_rows * self.fan_in + self.fan_out * self.r
+
+    def A(self):
+        return self.store.params[self.offA:self.offA + self.a_rows * self.fan_in].view(self.a_rows, self.fan_in)
+
+    def B(self):
+        return self.store.params[self.offB:self.offB + self.fan_out * self.rs].view(self.fan_out, self.rs)
+
+    def gA(self):
+        return self.store.grads[self.offA:self.offA + self.a_rows * self.fan_in].view(self.a_rows, self.fan_in)
+
+    def gB(self):
+        return self.store.grads[self.offB:self.offB + self.fan_out * self.rs].view(self.fan_out, self.rs)
+
+
+class LoraStore:
+    def __init__(self, device, scaling: float):
+        self.device = device
+        self.scaling = scaling
+        self.slots: List[LoraSlot] = []
+        self.total = 0
+        self.params = self.grads = self.m = self.v = None
+
+    def add(self, name: str, kind: str, r: int, fan_in: int, fan_out: int) -> LoraSlot:
+        s = LoraSlot(name, kind, r, fan_in, fan_out)
+        s.offA = self.total
+        self.total += _r8(s.a_rows * fan_in)
+        s.offB = self.total
+        self.total += _r8(fan_out * s.rs)
+        s.store = self
+        self.slots.append(s)
+        return s
+
+    def finalize(self, extra: int = 0):
+        """`extra` trailing elements hold the trainable textual-inversion rows (same optimizer kernel)."""
+        n = self.total + extra
+        self.n_lora = self.total
+        self.params = torch.zeros(n, dtype=BF16, device=self.device)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.m = torch.zeros(n, dtype=BF16, device=self.device)
+        self.v = torch.zeros(n, dtype=BF16, device=self.device)
+
+    @property
+    def numel_logical(self) -> int:
+        return sum(s.numel_logical for s in self.slots)
+
+    def init_gaussian(self, seed: int):
+        """PEFT init_lora_weights='gaussian': A ~ N(0, (1/r)^2), B = 0."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for s in self.slots:
+            a = torch.randn(s.a_rows, s.fan_in, generator=g) * (1.0 / s.r)
+            s.A().copy_(a.to(BF16))
+            s.B().zero_()
+
+    # ---- PEFT-layout import / export ----------------------------------------------------------
+    def load_peft(self, sd: Dict[str, torch.Tensor]):
+        for s in self.slots:
+            a = sd[f"{s.name}.lora_A.default.weight"].to(self.device, BF16)
+            b = sd[f"{s.name}.lora_B.default.weight"].to(self.device, BF16)
+            if s.kind == "conv":
+                a = a.permute(2, 3, 0, 1).reshape(9 * s.r, s.fan_in)       # [r,Cin,3,3] -> [(kh,kw,r), Cin]
+                b = b.reshape(s.fan_out, s.r)
+            s.A().copy_(a)
+            s.B().zero_()
+            s.B()[:, :s.r].copy_(b)
+
+    def export_peft(self, grads: bool = False) -> Dict[str, torch.Tensor]:
+        out = {}
+        for s in self.slots:
+            a = (s.gA() if grads else s.A()).clone()
+            b = (s.gB() if grads else s.B())[:, :s.r].clone()
+            if s.kind == "conv":
+                a = a.view(3, 3, s.r, s.fan_in).permute(2, 3, 0, 1).contiguous()
+                b = b.reshape(s.fan_out, s.r, 1, 1)
+            out[f"{s.name}.lora_A.default.weight"] = a
+            out[f"{s.name}.lora_B.default.weight"] = b.contiguous()
+        return out
+
+
+# =================================================================================================
+# layers
+# =================================================================================================
+class Lin:
+    """Frozen linear y = x.W^T + b, optionally with the fused low-rank side path."""
+
+    def __init__(self, W: torch.Tensor, b: Optional[torch.Tensor], lora: Optional[LoraSlot] = None):
+        self.W, self.b, self.lora = W.contiguous(), b, lora
+        self.N, self.K = W.shape
+        self.x = self.T = None
+
+    def fwd(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, save: bool = True, bias=None,
+            bias_rows: int = 0) -> torch.Tensor:
+        M = x.shape[0]
+        y = torch.empty(M, self.N, dtype=BF16, device=x.device)
+        segs = [(kmajor(x), kmajor(self.W), self.K)]
+        T = None
+        if self.lora is not None:
+            lo = self.lora
+            T = torch.empty(M, lo.rs, dtype=BF16, device=x.device)
+            ops.gemm(T, M, lo.r, [(kmajor(x), Mat(lo.A(), lo.r, self.K, self.K), self.K)],
+                     d_strides=(lo.rs, 1, 0, 0), alpha=lo.store.scaling)
+            segs.append((Mat(T, M, lo.r, lo.rs), Mat(lo.B(), self.N, lo.r, lo.rs), lo.r))
+        ops.gemm(y, M, self.N, segs, bias=self.b if bias is None else bias, bias_rows=bias_rows,
+                 bias_sb=self.N if bias_rows else 0, residual=residual)
+        if save:
+            self.x, self.T = x, T
+        return y
+
+    def bwd(self, dy: torch.Tensor, need_dx: bool = True, accum: Optional[torch.Tensor] = None):
+        M = dy.shape[0]
+        x, lo = self.x, self.lora
+        segs = [(kmajor(dy), mnmajor(self.W), self.N)]
+        if lo is not None:
+            r, rs = lo.r, lo.rs
+            U = torch.empty(M, rs, dtype=BF16, device=dy.device)
+            ops.gemm(U, M, r, [(kmajor(dy), Mat(lo.B(), self.N, r, rs, mn=True), self.N)], d_strides=(rs, 1, 0, 0),
+                     alpha=lo.store.scaling)
+            # dB[N, r] += dY^T . T      dA[r, K] += U^T . X   (both operands MN-major, split-K fp32 atomics)
+            ops.gemm(lo.gB(), self.N, r, [(Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(self.T, M, r, rs, mn=True), M)],
+                     d_strides=(rs, 1, 0, 0), splits=_wgrad_splits(self.N, M), atomic=True)
+            ops.gemm(lo.gA(), self.K, r, [(Mat(x, M, self.K, x.stride(0), mn=True), Mat(U, M, r, rs, mn=True), M)],
+                     d_strides=(1, self.K, 0, 0), splits=_wgrad_splits(self.K, M), atomic=True)
+            segs.append((Mat(U, M, r, rs), Mat(lo.A(), r, self.K, self.K, mn=True), r))
+        self.x = self.T = None
+        if not need_dx:
+            return None
+        dx = accum if accum is not None else torch.empty(M, self.K, dtype=BF16, device=dy.device)
+        ops.gemm(dx, M, self.K, segs, residual=accum)
+        return dx
+
+
+class Conv3:
+    """Frozen 3x3 / pad 1 convolution on NHWC activations as an implicit GEMM (stride 1) or im2col GEMM (stride 2),
+    optionally with the PEFT conv-LoRA side path (3x3 A: C->r, 1x1 B: r->C)."""
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, lora: Optional[LoraSlot] = None,
+                 need_dgrad: bool = True):
+        cout, cin = w.shape[0], w.shape[1]
+        self.cin, self.cout, self.stride, self.lora, self.b = cin, cout, stride, lora, b
+        self.cin_p = _r8(cin)                                    # TMA needs 16-byte pixel strides
+        wp = torch.zeros(cout, 3, 3, self.cin_p, dtype=BF16, device=w.device)
+        wp[..., :cin] = w.permute(0, 2, 3, 1)
+        self.wk = wp.reshape(cout, 9 * self.cin_p).contiguous()   # [Cout, (kh, kw, c)]
+        self.wd = None
+        if need_dgrad and stride == 1:
+            self.cout_p = _r8(cout)
+            wd = torch.zeros(cin, 3, 3, self.cout_p, dtype=BF16, device=w.device)
+            wd[..., :cout] = w.flip(2, 3).permute(1, 2, 3, 0)    # dgrad = conv with flipped, transposed taps
+            self.wd = wd.reshape(cin, 9 * self.cout_p).contiguous()
+        self.sv = None
+
+    def fwd(self, x: torch.Tensor, N: int, H: int, W: int, bias=None, bias_rows: int = 0,
+            residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x: [N*H*W, cin_p].  Returns [N*Ho*Wo, cout]."""
+        assert x.shape[1] == self.cin_p, (x.shape, self.cin_p)
+        s = self.stride
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        Mo = N * Ho * Wo
+        bias = self.b if bias is None else bias
+        lo, T, col = self.lora, None, None
+        if s == 1 and ops.conv_supported(H, W):
+            a0 = Conv3x3(x, N, H, W, self.cin_p, b_tap_k=self.cin_p)
+        else:
+            col = ops.im2col3x3(x, N, H, W, self.cin_p, s)
+            a0 = kmajor(col)
+        segs = [(a0, kmajor(self.wk), 9 * self.cin_p)]
+        if lo is not None:
+            assert s == 1
+            T = torch.empty(Mo, lo.rs, dtype=BF16, device=x.device)
+            if col is None:
+                ops.gemm(T, Mo, lo.r, [(Conv3x3(x, N, H, W, self.cin_p, b_tap_k=0, b_tap_n=lo.r),
+                                        Mat(lo.A(), 9 * lo.r, self.cin, self.cin), 9 * self.cin_p)],
+                         d_strides=(lo.rs, 1, 0, 0), alpha=lo.store.scaling)
+            else:   # unsupported image geometry: T = col . A_flat^T needs A as [r, (tap, c)]
+                af = lo.A().view(9, lo.r, self.cin).permute(1, 0, 2).reshape(lo.r, 9 * self.cin).contiguous()
+                ops.gemm(T, Mo, lo.r, [(kmajor(col), kmajor(af), 9 * self.cin)], d_strides=(lo.rs, 1, 0, 0),
+                         alpha=lo.store.scaling)
+            segs.append((Mat(T, Mo, lo.r, lo.rs), Mat(lo.B(), self.cout, lo.r, lo.rs), lo.r))
+        ld_out = self.cout if self.cout % 8 == 0 else _r8(self.cout)
+        y = (torch.empty if ld_out == self.cout else torch.zeros)(Mo, ld_out, dtype=BF16, device=x.device)
+        ops.gemm(y, Mo, self.cout, segs, d_strides=(ld_out, 1, 0, 0), bias=bias, bias_rows=bias_rows,
+                 bias_sb=self.cout if bias_rows else 0, residual=residual)
+        self.sv = (x if lo is not None else None, T, N, H, W)
+        return y
+
+    def bwd(self, dy: torch.Tensor, need_dx: bool = True) -> Optional[torch.Tensor]:
+        """dy: [N*Ho*Wo, cout_p].  Returns dx [N*H*W, cin]."""
+        x, T, N, H, W = self.sv
+        self.sv = None
+        s, lo = self.stride, self.lora
+        Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+        Mo, Mi = N * Ho * Wo, N * H * W
+        extra = []
+        if lo is not None:
+            r, rs = lo.r, lo.rs
+            U = torch.empty(Mo, rs, dtype=BF16, device=dy.device)
+            ops.gemm(U, Mo, r, [(kmajor(dy), Mat(lo.B(), self.cout, r, rs, mn=True), self.cout)],
+                     d_strides=(rs, 1, 0, 0), alpha=lo.store.scaling)
+            ops.gemm(lo.gB(), self.cout, r, [(Mat(dy, Mo, self.cout, dy.stride(0), mn=True), Mat(T, Mo, r, rs, mn=True), Mo)],
+                     d_strides=(rs, 1, 0, 0), splits=_wgrad_splits(self.cout, Mo), atomic=True)
+            # U9[p, (tap, j)] = U[p - off(tap), j] turns both conv-LoRA backward pieces into plain GEMMs:
+            #   dA[(tap, j), c] += U9^T . X          dX += U9 . A
+            U9 = ops.shift_stack9(U, N, H, W, r)
+            ops.gemm(lo.gA(), self.cin, 9 * r, [(Mat(x, Mi, self.cin, x.stride(0), mn=True),
+                                                 Mat(U9, Mi, 9 * r, U9.stride(0), mn=True), Mi)],
+                     d_strides=(1, self.cin, 0, 0), splits=_wgrad_splits(self.cin, Mi), atomic=True)
+            extra = [(Mat(U9, Mi, 9 * r, U9.stride(0)), Mat(lo.A(), 9 * r, self.cin, self.cin, mn=True), 9 * r)]
+        if not need_dx:
+            return None
+        dx = torch.empty(Mi, self.cin, dtype=BF16, device=dy.device)
+        if s == 1 and ops.conv_supported(H, W):
+            assert dy.shape[1] == self.cout_p
+            ops.gemm(dx, Mi, self.cin, [(Conv3x3(dy, N, H, W, self.cout_p, b_tap_k=self.cout_p), kmajor(self.wd),
+                                         9 * self.cout_p)] + extra)
+        else:
+            dcol = torch.empty(Mo, 9 * self.cin_p, dtype=BF16, device=dy.device)
+            ops.gemm(dcol, Mo, 9 * self.cin_p, [(Mat(dy, Mo, self.cout, dy.stride(0)), mnmajor(self.wk), self.cout)])
+            dxc = ops.col2im3x3(dcol, N, H, W, self.cin_p, s)
+            if extra:
+                ops.gemm(dx, Mi, self.cin, extra, residual=dxc[:, :self.cin] if self.cin_p != self.cin else dxc)
+            else:
+                dx = dxc if self.cin_p == self.cin else dxc[:, :self.cin].contiguous()
+        return dx
+
+
+class GN:
+    def __init__(self, gamma, beta, groups: int, eps: float, silu: bool):
+        self.g, self.b, self.groups, self.eps, self.silu = gamma, beta, groups, eps, silu
+        self.C = gamma.numel()
+        self.sv = None
+
+    def fwd(self, x, batch: int, hw: int):
+        y, stats = ops.groupnorm_fwd(x, self.g, self.b, batch, hw, self.C, self.groups, self.eps, self.silu)
+        self.sv = (x, stats, batch, hw)
+        return y
+
+    def bwd(self, dy, dres=None):
+        x, stats, batch, hw = self.sv
+        self.sv = None
+        return ops.groupnorm_bwd(dy, x, self.g, self.b, stats, batch, hw, self.C, self.groups, self.silu, dres)
+
+
+class LN:
+    def __init__(self, gamma, beta):
+        self.g, self.b = gamma, beta
+        self.sv = None
+
+    def fwd(self, x):
+        y, stats = ops.layernorm_fwd(x, self.g, self.b, 1e-5)
+        self.sv = (x, stats)
+        return y
+
+    def bwd(self, dy, dres=None):
+        x, stats = self.sv
+        self.sv = None
+        return ops.layernorm_bwd(dy, x, self.g, stats, dres)
+
+
+class Attn:
+    """Multi-head attention over [B*L, C] projections; P stays in HBM for the backward."""
+
+    def __init__(self, heads: int, to_q: Lin, to_k: Lin, to_v: Lin, to_out: Lin, cross: bool):
+        self.h, self.to_q, self.to_k, self.to_v, self.to_out, self.cross = heads, to_q, to_k, to_v, to_out, cross
+        self.capture = False
+        self.scores = None
+        self.sv = None
+
+    def fwd(self, x, ctx, B: int, L: int, Lk: int, residual):
+        C = self.to_q.N
+        H, d = self.h, C // self.h
+        src = ctx if self.cross else x
+        q, k, v = self.to_q.fwd(x), self.to_k.fwd(src), self.to_v.fwd(src)
+        scale = d ** -0.5
+        Lp = _r8(Lk)
+        dev = x.device
+        S = torch.empty(B, H, L, Lp, dtype=torch.float32, device=dev)
+        P = torch.empty(B, H, L, Lp, dtype=BF16, device=dev)
+        sS = (Lp, 1, L * Lp, H * L * Lp)
+        qm = Mat(q, L, d, C, sb0=d, sb1=L * C, batched=True)
+        km = Mat(k, Lk, d, C, sb0=d, sb1=Lk * C, batched=True)
+        ops.gemm(S, L, Lk, [(qm, km, d)], d_strides=sS, alpha=scale, nb0=H, nb1=B)
+        ops.softmax_fwd(S, P, B * H * L, Lk, Lp, Lp)
+        del S
+        O = torch.empty(B * L, C, dtype=BF16, device=dev)
+        pm = Mat(P, L, Lk, Lp, sb0=L * Lp, sb1=H * L * Lp, batched=True)
+        vm = Mat(v, Lk, d, C, mn=True, sb0=d, sb1=Lk * C, batched=True)
+        ops.gemm(O, L, d, [(pm, vm, Lk)], d_strides=(C, 1, d, L * C), nb0=H, nb1=B)
+        if self.capture and self.cross:
+            # sum over heads of q_h.k_h / sqrt(d)  ==  (q.k over all C channels) / sqrt(d): one batched GEMM
+            sc = torch.empty(B, L, Lp, dtype=BF16, device=dev)
+            ops.gemm(sc, L, Lk, [(Mat(q, L, C, C, sb1=L * C, batched=True), Mat(k, Lk, C, C, sb1=Lk * C, batched=True), C)],
+                     d_strides=(Lp, 1, 0, L * Lp), alpha=scale, nb0=1, nb1=B)
+            self.scores = sc[:, :, :Lk]
+        y = self.to_out.fwd(O, residual=residual)
+        self.sv = (q, k, v, P, B, L, Lk)
+        return y
+
+    def bwd(self, dy, d_ctx_accum, dscores: Optional[torch.Tensor]):
+        q, k, v, P, B, L, Lk = self.sv
+        self.sv = None
+        C = self.to_q.N
+        H, d = self.h, C // self.h
+        scale = d ** -0.5
+        Lp = _r8(Lk)
+        dev = dy.device
+        dO = self.to_out.bwd(dy)
+        sS = (Lp, 1, L * Lp, H * L * Lp)
+        # dV = P^T dO
+        dV = torch.empty(B * Lk, C, dtype=BF16, device=dev)
+        ops.gemm(dV, Lk, d, [(Mat(P, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
+                              Mat(dO, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
+                 d_strides=(C, 1, d, Lk * C), nb0=H, nb1=B)
+        # dP = dO V^T ; dS = P * (dP - rowsum(P dP))
+        dP = torch.empty(B, H, L, Lp, dtype=torch.float32, device=dev)
+        ops.gemm(dP, L, Lk, [(Mat(dO, L, d, C, sb0=d, sb1=L * C, batched=True),
+                              Mat(v, Lk, d, C, sb0=d, sb1=Lk * C, batched=True), d)], d_strides=sS, nb0=H, nb1=B)
+        dS = torch.empty(B, H, L, Lp, dtype=BF16, device=dev)
+        ops.softmax_bwd(P, dP, dS, B * H * L, Lk, Lp, Lp)
+        del dP, P
+        # dQ = scale dS K ; dK = scale dS^T Q
+        dQ = torch.empty(B * L, C, dtype=BF16, device=dev)
+        ops.gemm(dQ, L, d, [(Mat(dS, L, Lk, Lp, sb0=L * Lp, sb1=H * L * Lp, batched=True),
+                             Mat(k, Lk, d, C, mn=True, sb0=d, sb1=Lk * C, batched=True), Lk)],
+                 d_strides=(C, 1, d, L * C), alpha=scale, nb0=H, nb1=B)
+        dK = torch.empty(B * Lk, C, dtype=BF16, device=dev)
+        ops.gemm(dK, Lk, d, [(Mat(dS, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
+                              Mat(q, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
+                 d_strides=(C, 1, d, Lk * C), alpha=scale, nb0=H, nb1=B)
+        if dscores is not None:
+            dsc = torch.zeros(B, L, Lp, dtype=BF16, device=dev)
+            dsc[:, :, :Lk] = dscores
+            ops.gemm(dQ, L, C, [(Mat(dsc, L, Lk, Lp, sb1=L * Lp, batched=True),
+                                 Mat(k, Lk, C, C, mn=True, sb1=Lk * C, batched=True), Lk)],
+                     d_strides=(C, 1, 0, L * C), alpha=scale, residual=dQ, r_strides=(C, 1, 0, L * C), nb0=1, nb1=B)
+            ops.gemm(dK, Lk, C, [(Mat(dsc, L, Lk, Lp, mn=True, sb1=L * Lp, batched=True),
+                                  Mat(q, L, C, C, mn=True, sb1=L * C, batched=True), L)],
+                     d_strides=(C, 1, 0, Lk * C), alpha=scale, residual=dK, r_strides=(C, 1, 0, Lk * C), nb0=1, nb1=B)
+        self.scores = None
+        dx = self.to_q.bwd(dQ)
+        if self.cross:
+            self.to_k.bwd(dK, accum=d_ctx_accum)
+            self.to_v.bwd(dV, accum=d_ctx_accum)
+        else:
+            self.to_k.bwd(dK, accum=dx)
+            self.to_v.bwd(dV, accum=dx)
+        return dx
+
+
+class TBlock:
+    def __init__(self, ln1, attn1, ln2, attn2, ln3, ff1: Lin, ff2: Lin):
+        self.ln1, self.attn1, self.ln2, self.attn2, self.ln3, self.ff1, self.ff2 = ln1, attn1, ln2, attn2, ln3, ff1, ff2
+        self.h = None
+
+    def fwd(self, x, ctx, B, L, Lctx):
+        x1 = self.attn1.fwd(self.ln1.fwd(x), None, B, L, L, residual=x)
+        x2 = self.attn2.fwd(self.ln2.fwd(x1), ctx, B, L, Lctx, residual=x1)
+        h = self.ff1.fwd(self.ln3.fwd(x2))
+        self.h = h
+        return self.ff2.fwd(ops.geglu_fwd(h), residual=x2)
+
+    def bwd(self, dx3, d_ctx, dscores):
+        dh = ops.geglu_bwd(self.ff2.bwd(dx3), self.h)
+        self.h = None
+        dx2 = self.ln3.bwd(self.ff1.bwd(dh), dres=dx3)
+        dx1 = self.ln2.bwd(self.attn2.bwd(dx2, d_ctx, dscores), dres=dx2)
+        return self.ln1.bwd(self.attn1.bwd(dx1, None, None), dres=dx1)
+
+
+class Transformer2D:
+    def __init__(self, norm: GN, proj_in: Lin, blocks: List[TBlock], proj_out: Lin):
+        self.norm, self.proj_in, self.blocks, self.proj_out = norm, proj_in, blocks, proj_out
+
+    def fwd(self, x, ctx, B, HW, Lctx):
+        y = self.proj_in.fwd(self.norm.fwd(x, B, HW))
+        for blk in self.blocks:
+            y = blk.fwd(y, ctx, B, HW, Lctx)
+        return self.proj_out.fwd(y, residual=x)
+
+    def bwd(self, dy, d_ctx, dscore_list):
+        d = self.proj_out.bwd(dy)
+        for blk in reversed(self.blocks):
+            d = blk.bwd(d, d_ctx, dscore_list.pop() if dscore_list is not None and blk.attn2.capture else None)
+        return self.norm.bwd(self.proj_in.bwd(d), dres=dy)
+
+
+class Resnet:
+    def __init__(self, norm1: GN, conv1: Conv3, tproj: Lin, norm2: GN, conv2: Conv3, shortcut: Optional[Lin]):
+        self.norm1, self.conv1, self.tproj, self.norm2, self.conv2, self.shortcut = norm1, conv1, tproj, norm2, conv2, shortcut
+
+    def fwd(self, x, temb_act, N, H, W):
+        hw = H * W
+        tb = self.tproj.fwd(temb_act)                             # [N, Cout] = time_emb_proj(silu(emb)) + both biases
+        h = self.conv1.fwd(self.norm1.fwd(x, N, hw), N, H, W, bias=tb, bias_rows=hw)
+        sc = self.shortcut.fwd(x) if self.shortcut is not None else x
+        return self.conv2.fwd(self.norm2.fwd(h, N, hw), N, H, W, residual=sc)
+
+    def bwd(self, dout, d_temb_act, N, H, W):
+        dh1 = self.norm2.bwd(self.conv2.bwd(dout))
+        self.tproj.bwd(ops.colsum(dh1, N, H * W, dh1.shape[1]), accum=d_temb_act)
+        dsc = self.shortcut.bwd(dout) if self.shortcut is not None else dout
+        return self.norm1.bwd(self.conv1.bwd(dh1), dres=dsc)
+
+
+# =================================================================================================
+# the UNet
+# =================================================================================================
+class UNetB200:
+    def __init__(self, arch: UNetArch, state_dict: Dict[str, torch.Tensor], lora_rank: int,
+                 lora_alpha_multiplier: float = 1.0, device="cuda:0", ti_elems: int = 0, lora_seed: int = 0):
+        self.arch, self.device = arch, torch.device(device)
+        sd = {k.replace("base_model.model.", "").replace(".base_layer.", "."): v for k, v in state_dict.items()}
+        self._sd = sd
+        self.store = LoraStore(self.device, scaling=(lora_rank * lora_alpha_multiplier) / lora_rank)
+        self.rank = lora_rank
+        self.hooked: List[Attn] = []
+        a, boc, g = arch, arch.block_out_channels, arch.norm_num_groups
+        ted = a.time_embed_dim
+        self.time1, self.time2 = self._lin("time_embedding.linear_1"), self._lin("time_embedding.linear_2")
+        if a.addition_embed_type == "text_time":
+            self.add1, self.add2 = self._lin("add_embedding.linear_1"), self._lin("add_embedding.linear_2")
+        self.conv_in = self._conv("conv_in", need_dgrad=False)
+        self.down: List[Tuple[List[Resnet], Optional[List[Transformer2D]], Optional[Conv3]]] = []
+        for i in range(len(boc)):
+            p = f"down_blocks.{i}"
+            rs = [self._resnet(f"{p}.resnets.{j}") for j in range(a.layers_per_block)]
+            at = [self._transformer(f"{p}.attentions.{j}", boc[i], a.num_attention_heads[i],
+                                    a.transformer_layers_per_block[i], True) for j in range(a.layers_per_block)] \
+                if a.down_has_attn[i] else None
+            ds = self._conv(f"{p}.downsamplers.0.conv", stride=2) if i < len(boc) - 1 else None
+            self.down.append((rs, at, ds))
+        self.mid_res = [self._resnet("mid_block.resnets.0"), self._resnet("mid_block.resnets.1")]
+        self.mid_attn = self._transformer("mid_block.attentions.0", boc[-1], a.num_attention_heads[-1],
+                                          a.transformer_layers_per_block[-1], False)
+        self.up: List[Tuple[List[Resnet], Optional[List[Transformer2D]], Optional[Conv3]]] = []
+        rev_attn = list(reversed(a.down_has_attn))
+        for i in range(len(boc)):
+            p = f"up_blocks.{i}"
+            ri = len(boc) - 1 - i
+            n = a.layers_per_block + 1
+            rs = [self._resnet(f"{p}.resnets.{j}") for j in range(n)]
+            at = [self._transformer(f"{p}.attentions.{j}", boc[ri], a.num_attention_heads[ri],
+                                    a.transformer_layers_per_block[ri], True) for j in range(n)] if rev_attn[i] else None
+            us = self._conv(f"{p}.upsamplers.0.conv") if i < len(boc) - 1 else None
+            self.up.append((rs, at, us))
+        self.norm_out = GN(self._w("conv_norm_out.weight"), self._w("conv_norm_out.bias"), g, 1e-5, True)
+        self.conv_out = self._conv("conv_out")
+        # the reference enumerates hooked processors down_blocks first, then up_blocks (ti_cross_attn_loss.py:95-110)
+        self.store.finalize(extra=ti_elems)
+        lora_keys = [k for k in sd if ".lora_A." in k]
+        if lora_keys:
+            self.store.load_peft(sd)
+        else:
+            self.store.init_gaussian(lora_seed)
+        self._sd = None
+        self._fw = None
+
+    # ---- construction helpers -------------------------------------------------------------------
+    def _w(self, name: str) -> torch.Tensor:
+        return self._sd[name].detach().to(self.device, BF16).contiguous()
+
+    def _is_target(self, name: str) -> bool:
+        return self.rank > 0 and any(name == t or name.endswith("." + t) for t in LORA_TARGETS)
+
+    def _lin(self, name: str, extra_bias: Optional[torch.Tensor] = None) -> Lin:
+        W = self._w(f"{name}.weight")
+        if W.dim() == 4:                                          # SD1.5 1x1 conv projections / shortcuts
+            W = W.reshape(W.shape[0], W.shape[1]).contiguous()
+        b = self._w(f"{name}.bias") if f"{name}.bias" in self._sd else None
+        if extra_bias is not None:
+            b = (b.float() + extra_bias.float()).to(BF16) if b is not None else extra_bias
+        lora = self.store.add(name, "linear", self.rank, W.shape[1], W.shape[0]) if self._is_target(name) else None
+        return Lin(W, b, lora)
+
+    def _conv(self, name: str, stride: int = 1, need_dgrad: bool = True, use_bias: bool = True) -> Conv3:
+        w = self._w(f"{name}.weight")
+        b = self._w(f"{name}.bias") if use_bias else None
+        lora = self.store.add(name, "conv", self.rank, w.shape[1], w.shape[0]) if self._is_target(name) else None
+        return Conv3(w, b, stride=stride, lora=lora, need_dgrad=need_dgrad)
+
+    def _resnet(self, p: str) -> Resnet:
+        g = self.arch.norm_num_groups
+        n1 = GN(self._w(f"{p}.norm1.weight"), self._w(f"{p}.norm1.bias"), g, 1e-5, True)
+        n2 = GN(self._w(f"{p}.norm2.weight"), self._w(f"{p}.norm2.bias"), g, 1e-5, True)
+        conv1 = self._conv(f"{p}.conv1", use_bias=False)
+        tproj = self._lin(f"{p}.time_emb_proj", extra_bias=self._w(f"{p}.conv1.bias"))   # conv1 bias rides along
+        conv2 = self._conv(f"{p}.conv2")
+        sc = self._lin(f"{p}.conv_shortcut") if f"{p}.conv_shortcut.weight" in self._sd else None
+        return Resnet(n1, conv1, tproj, n2, conv2, sc)
+
+    def _attn(self, p: str, heads: int, cross: bool, hook: bool) -> Attn:
+        at = Attn(heads, self._lin(f"{p}.to_q"), self._lin(f"{p}.to_k"), self._lin(f"{p}.to_v"),
+                  self._lin(f"{p}.to_out.0"), cross)
+        if cross and hook:
+            self.hooked.append(at)
+        return at
+
+    def _transformer(self, p: str, dim: int, heads: int, depth: int, hook: bool) -> Transformer2D:
+        norm = GN(self._w(f"{p}.norm.weight"), self._w(f"{p}.norm.bias"), self.arch.norm_num_groups, 1e-6, False)
+        blocks = []
+        for j in range(depth):
+            b = f"{p}.transformer_blocks.{j}"
+            blocks.append(TBlock(LN(self._w(f"{b}.norm1.weight"), self._w(f"{b}.norm1.bias")),
+                                 self._attn(f"{b}.attn1", heads, False, False),
+                                 LN(self._w(f"{b}.norm2.weight"), self._w(f"{b}.norm2.bias")),
+                                 self._attn(f"{b}.attn2", heads, True, hook),
+                                 LN(self._w(f"{b}.norm3.weight"), self._w(f"{b}.norm3.bias")),
+                                 self._lin(f"{b}.ff.net.0.proj"), self._lin(f"{b}.ff.net.2")))
+        return Transformer2D(norm, self._lin(f"{p}.proj_in"), blocks, self._lin(f"{p}.proj_out"))
+
+    def set_capture(self, on: bool):
+        """Install / remove the reference's cross-attention score hook (init_daam_loss, main.py:50-52)."""
+        for at in self.hooked:
+            at.capture = on
+
+    # ---- forward --------------------------------------------------------------------------------
+    def forward(self, x8: torch.Tensor, B: int, H: int, W: int, timesteps: torch.Tensor, ctx: torch.Tensor,
+                text_embeds: Optional[torch.Tensor] = None, time_ids: Optional[torch.Tensor] = None):
+        """x8: noisy latents NHWC padded to 8 channels [B*H*W, 8]; ctx: [B, Lctx, Dc] bf16.
+        Returns (pred [B*H*W, 8] with channels 0..3 valid, [head-summed scores [B, HW_l, Lctx]] per hooked layer)."""
+        a = self.arch
+        Lctx = ctx.shape[1]
+        ctx2 = ctx.reshape(B * Lctx, ctx.shape[2]).contiguous()
+        t_emb = ops.timestep_embedding(timesteps, a.block_out_channels[0])
+        e1 = self.time1.fwd(t_emb)
+        emb = self.time2.fwd(ops.silu_fwd(e1))
+        a1 = None
+        if a.addition_embed_type == "text_time":
+            tid = ops.timestep_embedding(time_ids.flatten(), a.addition_time_embed_dim).view(B, -1)
+            add_in = torch.cat([text_embeds.to(BF16), tid], dim=1).contiguous()
+            a1 = self.add1.fwd(add_in)
+            emb = self.add2.fwd(ops.silu_fwd(a1), residual=emb)
+        temb_act = ops.silu_fwd(emb)
+        x = self.conv_in.fwd(x8, B, H, W)
+        skips = [x]
+        dims = [(H, W)]
+        h, w = H, W
+        for rs, at, ds in self.down:
+            for j, r in enumerate(rs):
+                x = r.fwd(x, temb_act, B, h, w)
+                if at is not None:
+                    x = at[j].fwd(x, ctx2, B, h * w, Lctx)
+                skips.append(x)
+            if ds is not None:
+                x = ds.fwd(x, B, h, w)
+                h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                skips.append(x)
+        x = self.mid_res[0].fwd(x, temb_act, B, h, w)
+        x = self.mid_attn.fwd(x, ctx2, B, h * w, Lctx)
+        x = self.mid_res[1].fwd(x, temb_act, B, h, w)
+        cat_splits = []
+        for rs, at, us in self.up:
+            for j, r in enumerate(rs):
+                sk = skips.pop()
+                cat_splits.append(x.shape[1])
+                x = r.fwd(torch.cat([x, sk], dim=1), temb_act, B, h, w)
+                if at is not None:
+                    x = at[j].fwd(x, ctx2, B, h * w, Lctx)
+            if us is not None:
+                x = us.fwd(ops.upsample2x_fwd(x, B, h, w, x.shape[1]), B, 2 * h, 2 * w)
+                h, w = 2 * h, 2 * w
+        pred = self.conv_out.fwd(self.norm_out.fwd(x, B, h * w), B, h, w)
+        scores = [at_.scores for at_ in self.hooked if at_.capture]
+        self._fw = (B, H, W, Lctx, ctx.shape[2], e1, emb, a1, cat_splits)
+        return pred, scores
+
+    # ---- backward -------------------------------------------------------------------------------
+    def backward(self, dpred8: torch.Tensor, dscores: Optional[List[torch.Tensor]] = None):
+        """dpred8: [B*H*W, 8] bf16 (channels >= 4 zero).  LoRA gradients ACCUMULATE into store.grads.
+        Returns (d_ctx [B, Lctx, Dc], d_text_embeds [B, P] or None)."""
+        a = self.arch
+        B, H, W, Lctx, Dc, e1, emb, a1, cat_splits = self._fw
+        self._fw = None
+        dev = dpred8.device
+        d_ctx = torch.zeros(B * Lctx, Dc, dtype=BF16, device=dev)
+        d_temb_act = torch.zeros(B, a.time_embed_dim, dtype=BF16, device=dev)
+        # hooked layers were enumerated down_blocks..., up_blocks...; backward visits up (reversed) then down (reversed)
+        n_down_hooks = sum(len(t.blocks) for rs, at, ds in self.down if at is not None for t in at)
+        ds_down = list(dscores[:n_down_hooks]) if dscores is not None else None
+        ds_up = list(dscores[n_down_hooks:]) if dscores is not None else None
+        nlev = len(a.block_out_channels)
+        h, w = H, W
+        d = self.norm_out.bwd(self.conv_out.bwd(dpred8))
+        dskips: List[torch.Tensor] = []
+        for rs, at, us in reversed(self.up):
+            if us is not None:
+                d = ops.upsample2x_bwd(us.bwd(d), B, h // 2, w // 2, us.cin)
+                h, w = h // 2, w // 2
+            for j in reversed(range(len(rs))):
+                if at is not None:
+                    d = at[j].bwd(d, d_ctx, ds_up)
+                dcat = rs[j].bwd(d, d_temb_act, B, h, w)
+                c1 = cat_splits.pop()
+                d = dcat[:, :c1].contiguous()
+                dskips.append(dcat[:, c1:].contiguous())
+        d = self.mid_res[1].bwd(d, d_temb_act, B, h, w)
+        d = self.mid_attn.bwd(d, d_ctx, None)
+        d = self.mid_res[0].bwd(d, d_temb_act, B, h, w)
+        # the up path consumed skips last-pushed-first, so walking it backwards filled dskips in PUSH order:
+        # dskips[-1] belongs to the deepest (last pushed) skip, dskips[0] to conv_in's output
+        for li in reversed(range(nlev)):
+            rs, at, ds = self.down[li]
+            if ds is not None:
+                d = ops.add(d, dskips.pop())
+                d = ds.bwd(d)
+                h, w = h * 2, w * 2
+            for j in reversed(range(len(rs))):
+                d = ops.add(d, dskips.pop())
+                if at is not None:
+                    d = at[j].bwd(d, d_ctx, ds_down)
+                d = rs[j].bwd(d, d_temb_act, B, h, w)
+        d = ops.add(d, dskips.pop())
+        assert not dskips
+        self.conv_in.bwd(d, need_dx=False)          # the input latents need no gradient
+        # time / added-condition embedding path (only the pooled text embedding needs a gradient)
+        d_emb = ops.silu_bwd(d_temb_act, emb)
+        d_text = None
+        if a.addition_embed_type == "text_time":
+            da1 = ops.silu_bwd(self.add2.bwd(d_emb), a1)
+            d_add_in = self.add1.bwd(da1)
+            d_text = d_add_in[:, :a.projection_class_embeddings_input_dim - 6 * a.addition_time_embed_dim].contiguous()
+        self.time1.x = self.time2.x = None
+        return d_ctx.view(B, Lctx, Dc), d_text

@@ -1,0 +1,277 @@
+"""TEST INFRASTRUCTURE: a torch/CPU stand-in for sd_lora_trainer_b200.ops with the SAME call signatures, used only by
+the `not gpu` tests to check the HOST logic of the executor (operand descriptors, strides, gradient plumbing, skip
+bookkeeping) against the oracle without a GPU.  It interprets the exact Mat / Conv3x3 descriptors the product code
+builds, so a wrong stride or transposition fails here before any GPU time is spent.  Never imported by the product."""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from sd_lora_trainer_b200 import ops as real
+
+BF16 = torch.bfloat16
+Mat, Conv3x3, kmajor, mnmajor, conv_supported = real.Mat, real.Conv3x3, real.kmajor, real.mnmajor, real.conv_supported
+
+
+def _bf(x):
+    return x.to(BF16).contiguous()
+
+
+def _view(t: torch.Tensor, shape, strides, extra_off=0):
+    need = extra_off + sum((s - 1) * st for s, st in zip(shape, strides)) + 1
+    flat = t.as_strided((t.untyped_storage().nbytes() // t.element_size(),), (1,), 0)
+    assert t.storage_offset() + need <= flat.numel(), "descriptor reaches outside the tensor's storage"
+    return flat.as_strided(shape, strides, t.storage_offset() + extra_off)
+
+
+def _operand(m: Mat, b0: int, b1: int, mn_extent: int, k_extent: int) -> torch.Tensor:
+    """Returns the logical [MN, K] fp32 matrix with TMA-style zero fill outside (rows, inner)."""
+    off = (b0 * m.sb0 + b1 * m.sb1) if m.batched else 0
+    v = _view(m.t, (m.rows, m.inner), (m.row_stride, 1), off).float()
+    if m.mn:
+        v = v.t()                                   # stored [K, MN]
+    out = torch.zeros(mn_extent, k_extent)
+    r, c = min(mn_extent, v.shape[0]), min(k_extent, v.shape[1])
+    out[:r, :c] = v[:r, :c]
+    return out
+
+
+def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, bias_sb=0, residual=None,
+         r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0):
+    if d_strides is None:
+        d_strides = (out.stride(0), 1, 0, 0)
+    if residual is not None and r_strides is None:
+        r_strides = (residual.stride(0), 1, 0, 0)
+    for b1 in range(nb1):
+        for b0 in range(nb0):
+            acc = torch.zeros(M, N)
+            for a, b, k in segs:
+                if isinstance(a, Conv3x3):
+                    x = _view(a.t, (a.N, a.H, a.W, a.C), (a.H * a.W * a.C, a.W * a.C, a.C, 1)).float()
+                    xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+                    bv = _view(b.t, (b.rows, b.inner), (b.row_stride, 1)).float()
+                    for tap in range(9):
+                        kh, kw = tap // 3, tap % 3
+                        xs = xp[:, kh:kh + a.H, kw:kw + a.W, :].reshape(M, a.C)
+                        rows = torch.zeros(N, a.C)
+                        r0, c0 = tap * a.b_tap_n, tap * a.b_tap_k
+                        rr = max(0, min(N, bv.shape[0] - r0))
+                        cc = max(0, min(a.C, bv.shape[1] - c0))
+                        rows[:rr, :cc] = bv[r0:r0 + rr, c0:c0 + cc]
+                        acc += xs @ rows.t()
+                else:
+                    A = _operand(a, b0, b1, M, k)
+                    Bm = _operand(b, b0, b1, N, k)
+                    acc += A @ Bm.t()
+            acc = acc * alpha
+            if bias is not None:
+                if bias_rows:
+                    idx = torch.arange(M) // bias_rows
+                    bv = _view(bias, (int(idx.max()) + 1, N), (bias_sb, 1)).float()
+                    acc += bv[idx]
+                else:
+                    acc += bias.float()[:N]
+            if residual is not None:
+                acc += _view(residual, (M, N), (r_strides[0], r_strides[1]), b0 * r_strides[2] + b1 * r_strides[3]).float()
+            dv = _view(out, (M, N), (d_strides[0], d_strides[1]), b0 * d_strides[2] + b1 * d_strides[3])
+            if atomic:
+                dv += acc.to(out.dtype)
+            else:
+                dv.copy_(acc.to(out.dtype))
+    return out
+
+
+def softmax_fwd(S, P, rows, cols, ld_s, ld_p):
+    s = _view(S, (rows, cols), (ld_s, 1))
+    p = _view(P, (rows, ld_p), (ld_p, 1))
+    p.zero_()
+    p[:, :cols] = torch.softmax(s.float(), -1).to(BF16)
+
+
+def softmax_bwd(P, dP, dS, rows, cols, ld_p, ld_dp):
+    p = _view(P, (rows, cols), (ld_p, 1)).float()
+    dp = _view(dP, (rows, cols), (ld_dp, 1)).float()
+    ds = _view(dS, (rows, ld_p), (ld_p, 1))
+    ds.zero_()
+    ds[:, :cols] = (p * (dp - (p * dp).sum(-1, keepdim=True))).to(BF16)
+
+
+def groupnorm_fwd(x, gamma, beta, batch, hw, C_, groups, eps, silu):
+    xr = x.float().view(batch, hw, C_).permute(0, 2, 1)
+    y = F.group_norm(xr, groups, gamma.float(), beta.float(), eps)
+    if silu:
+        y = F.silu(_bf(y).float())
+    return _bf(y.permute(0, 2, 1).reshape(batch * hw, C_)), (eps,)
+
+
+def groupnorm_bwd(dy, x, gamma, beta, stats, batch, hw, C_, groups, silu, dres=None):
+    xr = x.float().view(batch, hw, C_).permute(0, 2, 1).detach().requires_grad_(True)
+    y = F.group_norm(xr, groups, gamma.float(), beta.float(), stats[0])
+    if silu:
+        y = F.silu(y)
+    y.backward(dy.float().view(batch, hw, C_).permute(0, 2, 1))
+    dx = xr.grad.permute(0, 2, 1).reshape(batch * hw, C_)
+    if dres is not None:
+        dx = _bf(dx).float() + dres.float()
+    return _bf(dx)
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    return _bf(F.layer_norm(x.float(), (x.shape[1],), gamma.float(), beta.float(), eps)), None
+
+
+def layernorm_bwd(dy, x, gamma, stats, dres=None):
+    xr = x.float().detach().requires_grad_(True)
+    F.layer_norm(xr, (x.shape[1],), gamma.float(), torch.zeros_like(gamma).float(), 1e-5).backward(dy.float())
+    dx = xr.grad
+    if dres is not None:
+        dx = _bf(dx).float() + dres.float()
+    return _bf(dx)
+
+
+def geglu_fwd(h):
+    a, g = h.float().chunk(2, -1)
+    return _bf(a * _bf(F.gelu(g)).float())
+
+
+def geglu_bwd(dy, h):
+    hr = h.float().detach().requires_grad_(True)
+    a, g = hr.chunk(2, -1)
+    (a * F.gelu(g)).backward(dy.float())
+    return _bf(hr.grad)
+
+
+def silu_fwd(x):
+    return _bf(F.silu(x.float()))
+
+
+def silu_bwd(dy, x):
+    xr = x.float().detach().requires_grad_(True)
+    F.silu(xr).backward(dy.float())
+    return _bf(xr.grad)
+
+
+def add(a, b, c=None, out=None):
+    y = a.float() + b.float()
+    if c is not None:
+        y = _bf(y).float() + c.float()
+    y = _bf(y)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def upsample2x_fwd(x, N, H, W, C_):
+    xn = x.float().view(N, H, W, C_).permute(0, 3, 1, 2)
+    return _bf(F.interpolate(xn, scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).reshape(-1, C_))
+
+
+def upsample2x_bwd(dy, N, H, W, C_):
+    return _bf(dy.float().view(N, H, 2, W, 2, C_).sum(dim=(2, 4)).reshape(-1, C_))
+
+
+def im2col3x3(x, N, H, W, C_, stride):
+    xn = x.float().view(N, H, W, C_).permute(0, 3, 1, 2)
+    unf = F.unfold(xn, 3, padding=1, stride=stride)
+    L = unf.shape[-1]
+    return _bf(unf.view(N, C_, 9, L).permute(0, 3, 2, 1).reshape(N * L, 9 * C_))
+
+
+def col2im3x3(col, N, H, W, C_, stride):
+    L = col.shape[0] // N
+    f = F.fold(col.float().view(N, L, 9, C_).permute(0, 3, 2, 1).reshape(N, C_ * 9, L), (H, W), 3, padding=1, stride=stride)
+    return _bf(f.permute(0, 2, 3, 1).reshape(-1, C_))
+
+
+def shift_stack9(U, N, H, W, r):
+    ld_out = (9 * r + 7) // 8 * 8
+    Un = _view(U, (N, H, W, r), (H * W * U.stride(0), W * U.stride(0), U.stride(0), 1)).float()
+    out = torch.zeros(N, H, W, ld_out)
+    for tap in range(9):
+        dh, dw = tap // 3 - 1, tap % 3 - 1
+        hs, ws = slice(max(dh, 0), H + min(dh, 0)), slice(max(dw, 0), W + min(dw, 0))
+        hsrc, wsrc = slice(max(-dh, 0), H + min(-dh, 0)), slice(max(-dw, 0), W + min(-dw, 0))
+        out[:, hs, ws, tap * r:(tap + 1) * r] = Un[:, hsrc, wsrc]
+    return _bf(out.reshape(N * H * W, ld_out))
+
+
+def colsum(x, batch, hw, C_):
+    return _bf(x.float().view(batch, hw, C_).sum(1))
+
+
+def timestep_embedding(t, dim):
+    half = dim // 2
+    ex = -math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half
+    e = t.float()[:, None] * torch.exp(ex)[None]
+    return _bf(torch.cat([torch.cos(e), torch.sin(e)], -1))
+
+
+def noise_prologue(latent, noise, offset, offset_scale, acp, timesteps):
+    B, Cc, H, W = latent.shape
+    if offset is not None:
+        noise += offset_scale * offset.view(B, Cc, 1, 1)
+    a = acp.to(BF16)
+    sa = (a[timesteps] ** 0.5).view(B, 1, 1, 1)
+    so = ((1 - a[timesteps]) ** 0.5).view(B, 1, 1, 1)
+    noisy = sa * latent.to(BF16) + so * noise
+    n8 = torch.zeros(B * H * W, 8, dtype=BF16)
+    n8[:, :Cc] = noisy.permute(0, 2, 3, 1).reshape(-1, Cc)
+    return noisy, n8
+
+
+def snr_weights(acp, timesteps, snr_gamma):
+    snr = ((acp ** 0.5)[timesteps] / ((1 - acp) ** 0.5)[timesteps]) ** 2
+    w = torch.minimum(snr, torch.full_like(snr, snr_gamma)) / snr
+    return (w / w.mean()).float()
+
+
+def diffusion_loss(pred, ld_pred, noise, mask, weights, loss_scale, want_grad=True):
+    B, Cc, H, W = noise.shape
+    pr = pred[:, :Cc].reshape(B, H, W, Cc).permute(0, 3, 1, 2).clone().requires_grad_(True)
+    l = (((pr - noise).pow(2) * mask).mean(dim=[1, 2, 3]) * weights).mean()
+    (l * loss_scale).backward()
+    d8 = torch.zeros(B * H * W, 8, dtype=BF16)
+    d8[:, :Cc] = pr.grad.permute(0, 2, 3, 1).reshape(-1, Cc).to(BF16)
+    return l.detach().float().view(1), (d8 if want_grad else None)
+
+
+def abs_sum(p, out):
+    out += p.float().abs().sum()
+    return out
+
+
+def adamw(p, grad, m, v, n_first, *, lr, wd, l1_coeff, lr2, wd2, beta1=0.9, beta2=0.999, eps=1e-8, step,
+          grad_scale=1.0, zero_grad=True):
+    """Same op-by-op bf16 arithmetic as the CUDA kernel (== torch.optim.AdamW on bf16 tensors)."""
+    def seg(sl, lr_, wd_, l1_):
+        pv = p[sl]
+        g = (grad[sl] * grad_scale).to(BF16)
+        if l1_:
+            g = (g.float() + l1_ * torch.sign(pv.float())).to(BF16)
+        if wd_:
+            pv.mul_(1 - lr_ * wd_)
+        m[sl].lerp_(g, 1 - beta1)
+        v[sl].mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+        denom = (v[sl].sqrt() / (bc2 ** 0.5)).add_(eps)
+        pv.addcdiv_(m[sl], denom, value=-(lr_ / bc1))
+    seg(slice(0, n_first), lr, wd, l1_coeff)
+    if p.numel() > n_first:
+        seg(slice(n_first, p.numel()), lr2, wd2, 0.0)
+    if zero_grad:
+        grad.zero_()
+
+
+def install(monkeypatch):
+    """Patch every product module that holds a reference to ops."""
+    import sd_lora_trainer_b200.step as step_mod
+    import sd_lora_trainer_b200.unet as unet_mod
+    import sd_lora_trainer_b200.trainer.loss as loss_mod
+    import sys
+    me = sys.modules[__name__]
+    for mod in (step_mod, unet_mod, loss_mod):
+        monkeypatch.setattr(mod, "ops", me)

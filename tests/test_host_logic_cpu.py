@@ -1,0 +1,119 @@
+"""CPU tests of the executor's HOST logic: the product's forward/backward graph (operand descriptors, strides, skip and
+gradient plumbing, LoRA slot layout, optimizer wiring) driven through tests/cpu_mock_ops.py and compared with the
+oracle.  The CUDA kernels themselves are covered by the `-m gpu` tests."""
+import copy
+
+import pytest
+import torch
+
+from tests import cpu_mock_ops
+
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _setup(family, rank, batch, hw, disable_ti=False):
+    from oracle.step import OracleTrainer, StepConfig, make_inputs
+    from oracle.text import build_text_encoders
+    from sd_lora_trainer_b200.step import StepConfig as PCfg, TrainerB200
+    cfg = StepConfig(family=family, tiny=True, resolution=hw * 8, lora_rank=rank, disable_ti=disable_ti)
+    orc = OracleTrainer(cfg, device="cpu")
+    g = torch.Generator().manual_seed(7)
+    for n, p in orc.unet.named_parameters():
+        if "lora_B" in n:
+            p.data.copy_((torch.randn(p.shape, generator=g) * 0.05).to(BF))
+    inputs = make_inputs(cfg, batch=batch, latent_hw=hw, face_mask=True, train_ids=orc.train_ids)
+    pcfg = PCfg(**{k: getattr(cfg, k) for k in PCfg.__dataclass_fields__ if hasattr(cfg, k)})
+    tes = build_text_encoders(cfg.family, cfg.tiny, seed=cfg.seed + 1)
+    ti_init = None
+    if not disable_ti:
+        ti_init = [te.text_model.embeddings.token_embedding.weight.data[-cfg.n_tokens:].clone()
+                   for te in orc.text_encoders if te is not None]
+    tr = TrainerB200(pcfg, orc.unet.state_dict(), tes, device="cpu", ti_init=ti_init)
+    return cfg, orc, tr, inputs
+
+
+@pytest.mark.parametrize("family,rank,batch,hw", [("sdxl", 8, 2, 8), ("sd15", 4, 1, 8)])
+def test_step_host_logic_matches_oracle(monkeypatch, family, rank, batch, hw):
+    cpu_mock_ops.install(monkeypatch)
+    cfg, orc, tr, inputs = _setup(family, rank, batch, hw)
+    p_before = tr.store.export_peft()
+    out_o = orc.step(inputs, do_optimizer=False)
+    out_p = tr.step(inputs, do_optimizer=False)
+    assert torch.equal(out_p["noisy_latent"], out_o["noisy_latent"])
+    for key in ("img_loss", "token_attention_loss", "token_std_loss", "tot_loss"):
+        a, b = float(out_p[key]), float(out_o[key])
+        assert abs(a - b) / abs(b) <= 2e-3, f"{key}: ours {a} vs oracle {b}"
+    pred = out_p["model_pred8"][:, :4].reshape(batch, hw, hw, 4).permute(0, 3, 1, 2)
+    assert rel(pred, out_o["model_pred"]) < 2e-2
+    for s, so in zip(out_p["attention_scores"], out_o["attention_scores"]):
+        assert rel(s, so) < 8e-2          # bf16 noise floor of the per-head-rounded oracle scores; fp32-referenced bound is in the GPU test
+    ours = tr.store.export_peft(grads=True)
+    n_checked = 0
+    for n, p in orc.unet.named_parameters():
+        if p.grad is not None:
+            assert rel(ours[n].reshape(p.grad.shape), p.grad) < 0.25, n   # bf16-vs-bf16 backward noise; fp32-referenced bound: GPU test
+            n_checked += 1
+    assert n_checked == 2 * len(tr.store.slots)
+    off = tr.store.n_lora
+    for te, rows in zip([t for t in orc.text_encoders if t is not None], tr.ti_rows):
+        gref = te.text_model.embeddings.token_embedding.weight.grad[-cfg.n_tokens:]
+        assert rel(tr.store.grads[off:off + rows.numel()].view_as(rows), gref) < 0.25
+        off += rows.numel()
+    orc.optimizer_step()
+    tr.optimizer_step()
+    after = tr.store.export_peft()
+    changed = 0
+    for n, p in orc.unet.named_parameters():
+        if "lora_" in n:
+            d_o = p.detach().float() - p_before[n].reshape(p.shape).float()
+            d_p = after[n].reshape(p.shape).float() - p_before[n].reshape(p.shape).float()
+            changed += int((d_o != 0).sum())
+            assert float((d_o - d_p).abs().max()) <= 2.5 * float(d_o.abs().max() + 1e-12), n
+    assert changed > 0
+    assert float(tr.store.grads.abs().max()) == 0.0
+
+
+def test_lora_store_roundtrip_and_layout():
+    from sd_lora_trainer_b200.unet import LoraStore
+    st = LoraStore("cpu", 1.0)
+    a = st.add("x.to_q", "linear", 4, 64, 32)
+    c = st.add("y.conv2", "conv", 4, 16, 24)
+    st.finalize(extra=10)
+    assert a.offA % 8 == 0 and a.offB % 8 == 0 and c.offA % 8 == 0 and c.offB % 8 == 0
+    assert st.params.numel() == st.n_lora + 10
+    assert st.numel_logical == 4 * 64 + 32 * 4 + 9 * 4 * 16 + 24 * 4
+    sd = {"x.to_q.lora_A.default.weight": torch.randn(4, 64), "x.to_q.lora_B.default.weight": torch.randn(32, 4),
+          "y.conv2.lora_A.default.weight": torch.randn(4, 16, 3, 3), "y.conv2.lora_B.default.weight": torch.randn(24, 4, 1, 1)}
+    st.load_peft(sd)
+    back = st.export_peft()
+    for k, v in sd.items():
+        assert torch.equal(back[k], v.to(torch.bfloat16)), k
+    assert float(a.B()[:, 4:].abs().max()) == 0.0          # rank padding stays zero
+
+
+def test_product_never_imports_oracle():
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sd_lora_trainer_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+@pytest.mark.parametrize("name", ["tiny_sdxl", "tiny_sd15", "sdxl", "sd15"])
+def test_param_shapes_match_oracle_state_dict(name):
+    """The product's own parameter enumeration (used for random init) names and shapes every diffusers parameter."""
+    from oracle.unet import UNet2DConditionModel, UNetConfig
+    from sd_lora_trainer_b200.arch import by_name
+    from sd_lora_trainer_b200.init import param_shapes
+    with torch.device("meta"):
+        ref = UNet2DConditionModel(getattr(UNetConfig, name)())
+    want = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    got = dict(param_shapes(by_name(name)))
+    assert got == want
