@@ -100,6 +100,8 @@ class OracleTrainer:
             self.opt_ti = None
         self.unet, self.lora_params = inject_lora(self.unet, cfg.lora_rank, cfg.lora_alpha_multiplier,
                                                   seed=cfg.seed + 2)
+        self.unet.to(self.device)                                         # adapters were created on the host
+        self.lora_params = [p for p in self.unet.parameters() if p.requires_grad]
         self.opt_unet = torch.optim.AdamW(
             [{"params": self.lora_params, "weight_decay": cfg.lora_weight_decay}],
             lr=1e-4, weight_decay=cfg.lora_weight_decay)                  # optimizer.py:16-17

@@ -1,7 +1,11 @@
 """Developer probe: time fwd / bwd / optimizer of one full-size step (random-init weights, synthetic inputs)."""
 import argparse
 import json
+import os
+import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 
