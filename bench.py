@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200-native LoRA + textual-inversion training step.
+
+Workload (BASELINE.json metric): SDXL LoRA rank-16 'face' mode + 3 textual-inversion tokens, 1024x1024 (latent
+128x128), bf16, batch 2 per GPU, random-init weights of the full SDXL-base architecture (UNet 2.57 B, CLIP-L,
+OpenCLIP-bigG), synthetic inputs.  One "step" = text encoders fwd -> noise prologue -> UNet fwd (LoRA fused) ->
+losses -> UNet bwd (dA/dB only) -> CLIP bwd to the TI rows -> [all-reduce] -> fused AdamW.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run)
+  python bench.py --impl reference ...                     (CPU oracle of the same step on the host cores)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRAIN_TFLOP_PER_IMAGE = {("sdxl", 16): 14.505, ("sdxl", 32): 14.676, ("sd15", 16): 1.761, ("sd15", 4): 1.742}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_text_encoders(family: str, device):
+    from transformers import CLIPTextConfig, CLIPTextModel, CLIPTextModelWithProjection
+    kw = dict(vocab_size=49408, max_position_embeddings=77, bos_token_id=49406, eos_token_id=49407, pad_token_id=49407)
+    c1 = CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12,
+                        hidden_act="quick_gelu", projection_dim=768, **kw)
+    torch.manual_seed(1)
+    with torch.device(device):
+        te1 = CLIPTextModel(c1).to(torch.bfloat16)
+        te2 = None
+        if family == "sdxl":
+            c2 = CLIPTextConfig(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=20,
+                                hidden_act="gelu", projection_dim=1280, **kw)
+            te2 = CLIPTextModelWithProjection(c2).to(torch.bfloat16)
+    return te1, te2
+
+
+def run_ours(args):
+    from sd_lora_trainer_b200 import _lib, ops
+    from sd_lora_trainer_b200.data import synthetic_inputs
+    from sd_lora_trainer_b200.init import random_state_dict
+    from sd_lora_trainer_b200.step import StepConfig, TrainerB200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    pg = None
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device(dev))
+        pg = torch.distributed.group.WORLD
+    cfg = StepConfig(family=args.family, resolution=args.res, lora_rank=args.rank, disable_ti=False,
+                     max_train_steps=max(args.steps + args.warmup, 300))
+    sd = random_state_dict(cfg.arch(), seed=0, device=dev)
+    tes = build_text_encoders(args.family, dev)
+    tr = TrainerB200(cfg, sd, tes, device=dev, process_group=pg, use_cuda_graph=not args.no_graph)
+    del sd
+    B = args.batch
+    host_batches = [synthetic_inputs(args.family, B, args.res, cfg.n_tokens, seed=1000 + rank * 97 + i, face_mask=True,
+                                     vae_scaling_factor=cfg.arch().vae_scaling_factor, pin=True) for i in range(4)]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (captures the graph) ------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        out = tr.step(host_batches[i % 4], completion_f=0.0)
+    float(out["tot_loss"])
+    sync_all()
+
+    # ---- timed region 1: inputs resident in HBM (the staged static buffers), K steps -----------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        out = tr.step_resident(completion_f=0.0)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches_timed = _lib.launch_count() - l0
+    # ---- timed region 2: end to end through the public API, host (pinned) inputs, loss read back -------
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e2.record()
+    for i in range(args.steps):
+        out = tr.step(host_batches[i % 4], completion_f=0.0)
+        loss_val = float(out["tot_loss"])                     # device -> host read of the step's result
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.finish()
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    launches_per_step = tr.launches_per_step
+
+    result = None
+    if rank == 0:
+        pk, pk_src = peaks()
+        imgs = B * world * args.steps
+        value = imgs / (ms / 1e3)
+        e2e_value = imgs / (ms_e2e / 1e3)
+        tf_img = TRAIN_TFLOP_PER_IMAGE.get((args.family, args.rank))
+        result = {
+            "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.family.upper()} LoRA r={args.rank} face+TI(3 tokens) {args.res}x{args.res} "
+                                   f"bf16 batch {B}/GPU, fwd+bwd+AdamW, random-init full-size weights",
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2_policy": "working set (5 GB weights + ~25 GB activations per step) exceeds the 126 MB L2",
+                       "cuda_graph": not args.no_graph},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": tr.h2d_bytes_last, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps if not launches_timed else launches_timed,
+            "gpu_launches_per_step": launches_per_step,
+            "loss": loss_val,
+        }
+        if tf_img:
+            result["step_roofline"] = {"bound": "tensor", "achieved": tf_img * value / world, "peak": pk["bf16_tflops_sustained"],
+                                       "unit": "TFLOP/s", "frac": tf_img * value / world / pk["bf16_tflops_sustained"],
+                                       "peak_source": pk_src + " (sustained)", "train_tflop_per_image": tf_img}
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), measured live with CUDA events, eager pass ------
+    if rank == 0 and not args.skip_roofline:
+        prof = tr.profile_gemms(host_batches[0])
+        pk, pk_src = peaks()
+        result["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": prof["tflops"],
+                              "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                              "frac": prof["tflops"] / pk["bf16_tflops_sustained"], "traffic": None,
+                              "peak_source": pk_src + " (sustained: timed inside the step)",
+                              "launches_per_step": prof["launches"], "gemm_ms_per_step": prof["ms"],
+                              "gemm_share_of_step": prof["ms"] / (ms / args.steps),
+                              "algorithmic_tflop_per_step": prof["tflop"]}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(prof["by_shape"], open(os.path.join(ROOT, "gpurun_out", "gemm_by_shape.json"), "w"), indent=1)
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def cpu_baseline(args, steps: int, warmup: int):
+    """The oracle (a port of the reference step, oracle/) on the host cores: SAME model and config, batch 1 so that a
+    step stays bounded.  fp32 on the CPU - the reference's bf16 path is several times slower there (no AMX needed)."""
+    from oracle.step import OracleTrainer, StepConfig as OCfg, make_inputs
+    torch.set_num_threads(os.cpu_count() or 1)
+    dtype = torch.float32 if args.cpu_dtype == "fp32" else torch.bfloat16
+    cfg = OCfg(family=args.family, resolution=args.cpu_res, lora_rank=args.rank, weight_dtype=dtype)
+    t0 = time.time()
+    orc = OracleTrainer(cfg, device="cpu")
+    build_s = time.time() - t0
+    inp = make_inputs(cfg, batch=args.cpu_batch, face_mask=True, train_ids=orc.train_ids)
+    for _ in range(warmup):
+        orc.step(inp)
+    t0 = time.time()
+    for _ in range(steps):
+        out = orc.step(inp)
+        float(out["tot_loss"])
+    dt = time.time() - t0
+    return {"value": args.cpu_batch * steps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} step(s) of the same SDXL r={args.rank} face+TI step, batch {args.cpu_batch}, "
+                      f"{args.cpu_res}x{args.cpu_res}, {args.cpu_dtype} oracle on the host cores (fwd+bwd+AdamW), "
+                      f"build {build_s:.0f}s not timed",
+            "seconds": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = min(args.steps, args.ref_max_steps), min(args.warmup, 1)
+    cb = cpu_baseline(args, steps=steps, warmup=warmup)
+    line = {"impl": "reference", "metric": "training images/sec", "value": cb["value"], "unit": "images/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warmup,
+            "ms_per_step": cb["seconds"] / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.cpu_dtype, "data": "synthetic",
+            "config": {"workload": f"{args.family.upper()} LoRA r={args.rank} face+TI {args.cpu_res}x{args.cpu_res} "
+                                   f"batch {args.cpu_batch}, CPU oracle (port of the reference step; diffusers/peft absent)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--family", default="sdxl")
+    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--rank", type=int, default=16)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--cpu-res", type=int, default=1024)
+    ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--cpu-dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--ref-max-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

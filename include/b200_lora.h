@@ -158,6 +158,13 @@ int b200_adamw(void* p, float* grad, void* m, void* v, int64_t n, int64_t n_firs
                double l1_coeff, double lr2, double wd2, double beta1, double beta2, double eps, int32_t step,
                double grad_scale, int32_t zero_grad, void* stream);
 
+/* CUDA-graph form of the same update: the 12 hyper-parameter floats live in DEVICE memory (refreshed by a
+   memcpy between replays), packed on the host by b200_adamw_pack_hyper from the same doubles. */
+int b200_adamw_pack_hyper(double lr, double wd, double l1_coeff, double lr2, double wd2, double beta1, double beta2,
+                          double eps, int32_t step, double grad_scale, float* out_host12);
+int b200_adamw_dev(void* p, float* grad, void* m, void* v, int64_t n, int64_t n_first, const float* hyper_dev12,
+                   int32_t zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,7 @@
 // Step prologue (offset noise + DDPM add_noise), min-SNR weights, masked epsilon-MSE loss with fused dPred, the
 // L1 |p| reduction, and the fused AdamW (+ L1 sign-gradient, + textual-inversion rows) update.
 // All HBM-bound, one pass each.
+#include <string.h>
 #include "common.cuh"
 #include "../../include/b200_lora.h"
 
@@ -95,29 +96,57 @@ struct AdamSeg {
     float neg_step;   // (float)(-(lr / bias_correction1))
     float l1;
 };
+struct AdamHyper {    // 12 floats; also the layout of the device-resident copy used under CUDA graphs
+    AdamSeg s0, s1;
+    float one_minus_b1, beta2, one_minus_b2, eps, bc2_sqrt, grad_scale;
+};
+
+__device__ __forceinline__ void adam_update(bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ m,
+                                            bf16* __restrict__ v, long long i, const AdamSeg s, const AdamHyper& h,
+                                            int zero_grad) {
+    float pv = __bfloat162float(p[i]);
+    float g = bfr(grad[i] * h.grad_scale);
+    if (s.l1 != 0.f) g = bfr(g + s.l1 * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f)));
+    if (zero_grad) grad[i] = 0.f;
+    if (s.decay != 1.f) pv = bfr(pv * s.decay);
+    float mv = __bfloat162float(m[i]);
+    mv = bfr(mv + h.one_minus_b1 * (g - mv));
+    float vv = bfr(__bfloat162float(v[i]) * h.beta2);
+    vv = bfr(vv + h.one_minus_b2 * (g * g));   // ATen foreach addcmul: self + scalar * (t1 * t2)
+    float d = bfr(sqrtf(vv));
+    d = bfr(d / h.bc2_sqrt);
+    d = bfr(d + h.eps);
+    pv = bfr(pv + s.neg_step * (mv / d));
+    p[i] = __float2bfloat16_rn(pv);
+    m[i] = __float2bfloat16_rn(mv);
+    v[i] = __float2bfloat16_rn(vv);
+}
+
 __global__ void adamw_kernel(bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ m, bf16* __restrict__ v,
-                             long long n, long long n_first, AdamSeg s0, AdamSeg s1, float one_minus_b1, float beta2,
-                             float one_minus_b2, float eps, float bc2_sqrt, float grad_scale, int zero_grad) {
+                             long long n, long long n_first, AdamHyper h, const AdamHyper* __restrict__ h_dev,
+                             int zero_grad) {
+    if (h_dev) h = *h_dev;     // CUDA-graph replay: hyper-parameters live in device memory, refreshed by a memcpy
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const AdamSeg s = i < n_first ? s0 : s1;
-        float pv = __bfloat162float(p[i]);
-        float g = bfr(grad[i] * grad_scale);
-        if (s.l1 != 0.f) g = bfr(g + s.l1 * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f)));
-        if (zero_grad) grad[i] = 0.f;
-        if (s.decay != 1.f) pv = bfr(pv * s.decay);
-        float mv = __bfloat162float(m[i]);
-        mv = bfr(mv + one_minus_b1 * (g - mv));
-        float vv = bfr(__bfloat162float(v[i]) * beta2);
-        vv = bfr(vv + one_minus_b2 * (g * g));   // ATen foreach addcmul: self + scalar * (t1 * t2)
-        float d = bfr(sqrtf(vv));
-        d = bfr(d / bc2_sqrt);
-        d = bfr(d + eps);
-        pv = bfr(pv + s.neg_step * (mv / d));
-        p[i] = __float2bfloat16_rn(pv);
-        m[i] = __float2bfloat16_rn(mv);
-        v[i] = __float2bfloat16_rn(vv);
-    }
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        adam_update(p, grad, m, v, i, i < n_first ? h.s0 : h.s1, h, zero_grad);
+}
+
+static AdamHyper make_hyper(double lr, double wd, double l1_coeff, double lr2, double wd2, double beta1, double beta2,
+                            double eps, int step, double grad_scale) {
+    // scalars are formed in double exactly as torch's Python code forms them, then narrowed once
+    const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
+    const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
+    AdamHyper h;
+    h.s0 = AdamSeg{wd != 0.0 ? static_cast<float>(1.0 - lr * wd) : 1.f, static_cast<float>(-(lr / bc1)),
+                   static_cast<float>(l1_coeff)};
+    h.s1 = AdamSeg{wd2 != 0.0 ? static_cast<float>(1.0 - lr2 * wd2) : 1.f, static_cast<float>(-(lr2 / bc1)), 0.f};
+    h.one_minus_b1 = static_cast<float>(1.0 - beta1);
+    h.beta2 = static_cast<float>(beta2);
+    h.one_minus_b2 = static_cast<float>(1.0 - beta2);
+    h.eps = static_cast<float>(eps);
+    h.bc2_sqrt = static_cast<float>(sqrt(bc2));
+    h.grad_scale = static_cast<float>(grad_scale);
+    return h;
 }
 
 }  // namespace b200
@@ -166,18 +195,30 @@ extern "C" int b200_adamw(void* p, float* grad, void* m, void* v, int64_t n, int
                           double l1_coeff, double lr2, double wd2, double beta1, double beta2, double eps, int32_t step,
                           double grad_scale, int32_t zero_grad, void* stream) {
     B200_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
-    // scalars are formed in double exactly as torch's Python code forms them, then narrowed once
-    const double bc1 = 1.0 - pow(beta1, static_cast<double>(step));
-    const double bc2 = 1.0 - pow(beta2, static_cast<double>(step));
-    AdamSeg s0{wd != 0.0 ? static_cast<float>(1.0 - lr * wd) : 1.f, static_cast<float>(-(lr / bc1)),
-               static_cast<float>(l1_coeff)};
-    AdamSeg s1{wd2 != 0.0 ? static_cast<float>(1.0 - lr2 * wd2) : 1.f, static_cast<float>(-(lr2 / bc1)), 0.f};
+    const AdamHyper h = make_hyper(lr, wd, l1_coeff, lr2, wd2, beta1, beta2, eps, step, grad_scale);
     adamw_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
-                                                   static_cast<bf16*>(v), n, n_first, s0, s1,
-                                                   static_cast<float>(1.0 - beta1), static_cast<float>(beta2),
-                                                   static_cast<float>(1.0 - beta2), static_cast<float>(eps),
-                                                   static_cast<float>(sqrt(bc2)), static_cast<float>(grad_scale),
-                                                   zero_grad);
+                                                   static_cast<bf16*>(v), n, n_first, h, nullptr, zero_grad);
     B200_CHECK_LAUNCH("adamw");
+    return 0;
+}
+
+extern "C" int b200_adamw_pack_hyper(double lr, double wd, double l1_coeff, double lr2, double wd2, double beta1,
+                                     double beta2, double eps, int32_t step, double grad_scale, float* out_host12) {
+    B200_CHECK_ARG(step >= 1 && out_host12 != nullptr, "adamw_pack_hyper: bad arguments");
+    static_assert(sizeof(AdamHyper) == 12 * sizeof(float), "AdamHyper layout");
+    const AdamHyper h = make_hyper(lr, wd, l1_coeff, lr2, wd2, beta1, beta2, eps, step, grad_scale);
+    memcpy(out_host12, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int b200_adamw_dev(void* p, float* grad, void* m, void* v, int64_t n, int64_t n_first,
+                              const float* hyper_dev12, int32_t zero_grad, void* stream) {
+    B200_CHECK_ARG(hyper_dev12 != nullptr, "adamw_dev: null hyper-parameter buffer");
+    AdamHyper h;
+    memset(&h, 0, sizeof(h));
+    adamw_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
+                                                   static_cast<bf16*>(v), n, n_first, h,
+                                                   reinterpret_cast<const AdamHyper*>(hyper_dev12), zero_grad);
+    B200_CHECK_LAUNCH("adamw_dev");
     return 0;
 }

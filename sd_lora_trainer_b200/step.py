@@ -19,7 +19,7 @@ from . import ops
 from .arch import UNetArch, by_name
 from .text import TIEmbedding, add_time_ids, encode_prompt, init_ti_rows, install_ti_rows
 from .trainer.loss import (DistributionLoss, alphas_cumprod_table, compute_diffusion_loss,
-                           compute_token_attention_loss)
+                           token_attention_loss_tensors)
 from .unet import UNetB200
 
 BF16 = torch.bfloat16
@@ -70,7 +70,8 @@ class TrainerB200:
     """Owns the UNet executor, the flat parameter/gradient/moment buffers and the text encoders."""
 
     def __init__(self, cfg: StepConfig, unet_state_dict: Dict[str, torch.Tensor], text_encoders: Sequence,
-                 device="cuda:0", ti_init: Optional[List[torch.Tensor]] = None, process_group=None):
+                 device="cuda:0", ti_init: Optional[List[torch.Tensor]] = None, process_group=None,
+                 use_cuda_graph: bool = False):
         self.cfg, self.device = cfg, torch.device(device)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
@@ -108,21 +109,66 @@ class TrainerB200:
         self.opt_step = 0
         self._accum = 0
         self.last_lrs = (None, None)
+        self.use_graph = use_cuda_graph
+        self._static: Optional[Dict[str, torch.Tensor]] = None
+        self._static_key = None
+        self._graphs: Dict[object, object] = {}
+        self.h2d_bytes_last = 0
+        self.launches_per_step = 0
+        self._hyper_dev = torch.zeros(12, dtype=torch.float32, device=self.device)
+        self._hyper_host = torch.zeros(12, dtype=torch.float32)
+        if torch.cuda.is_available():
+            self._hyper_host = self._hyper_host.pin_memory()
+
+    # ---- inputs: host dict -> device tensors (static buffers when the step is graph-captured) ------
+    def _stage_inputs(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Copies one step's inputs to the device.  Returns the dict the step body reads; under CUDA graphs the
+        same tensors are reused (and overwritten) every step so the captured pointers stay valid."""
+        cfg, dev = self.cfg, self.device
+        B, Cc = inputs["vae_latent"].shape[:2]
+        staged = {
+            "vae_latent": inputs["vae_latent"].to(torch.float32),
+            "noise": inputs["noise"].to(BF16),
+            "mask": inputs["mask"].to(torch.float32),
+            "timesteps": inputs["timesteps"].long(),
+            "offset_noise": inputs["offset_noise"].to(torch.float32).reshape(B, Cc),
+        }
+        for i, t in enumerate(inputs["token_ids"]):
+            staged[f"token_ids_{i}"] = t.long()
+        if not cfg.disable_ti:
+            from .trainer.loss import token_index_tensors
+            staged["tok_len"], staged["ti_pos"] = token_index_tensors(inputs["token_indices"], self.train_ids)
+        key = tuple((k, tuple(v.shape)) for k, v in staged.items())
+        if self._static is None or self._static_key != key:
+            self._static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in staged.items()}
+            self._static_key = key
+            self._graphs = {}
+        nbytes = 0
+        for k, v in staged.items():
+            src = v if (v.is_cuda or v.is_pinned() or not torch.cuda.is_available()) else v.contiguous().pin_memory()
+            self._static[k].copy_(src, non_blocking=True)
+            nbytes += v.numel() * v.element_size()
+        self.h2d_bytes_last = nbytes
+        return self._static
 
     # ---- one micro-step: forward, losses, backward ------------------------------------------------
     def forward_backward(self, inputs: Dict[str, torch.Tensor], ti_active: bool = True) -> Dict[str, torch.Tensor]:
+        return self._body(self._stage_inputs(inputs), ti_active)
+
+    def _body(self, st: Dict[str, torch.Tensor], ti_active: bool) -> Dict[str, torch.Tensor]:
         cfg, dev = self.cfg, self.device
         ga = cfg.gradient_accumulation_steps * self.world       # DP-N == accumulation-N (SURVEY 8e)
-        latent = inputs["vae_latent"].to(dev, torch.float32).contiguous()
-        noise = inputs["noise"].to(dev, BF16).contiguous().clone()
-        mask = inputs["mask"].to(dev, torch.float32).contiguous()
-        timesteps = inputs["timesteps"].to(dev).long().contiguous()
+        latent, mask, timesteps = st["vae_latent"], st["mask"], st["timesteps"]
+        noise = st["noise"].clone()
         B, Cc, H, W = latent.shape
-        offset = inputs["offset_noise"].to(dev, torch.float32).reshape(B, Cc).contiguous() if cfg.noise_offset > 0 else None
-        token_ids = [t.to(dev) for t in inputs["token_ids"]]
+        offset = st["offset_noise"] if cfg.noise_offset > 0 else None
+        token_ids = [st[f"token_ids_{i}"] for i in range(2 if self.sdxl else 1)]
         need_text_grad = bool(self.ti_rows)
-        with torch.set_grad_enabled(need_text_grad):
-            prompt_embeds, pooled = encode_prompt(self.sdxl, self.text_encoders, token_ids)
+        if self.text_encoders[0] is not None:
+            with torch.set_grad_enabled(need_text_grad):
+                prompt_embeds, pooled = encode_prompt(self.sdxl, self.text_encoders, token_ids)
+        else:                                                   # kernel-only probes: synthetic conditioning
+            prompt_embeds, pooled = st["prompt_embeds"], st.get("pooled")
         time_ids = add_time_ids(B, cfg.resolution, BF16, dev) if self.sdxl else None
 
         noisy, noisy8 = ops.noise_prologue(latent, noise, offset, cfg.noise_offset, self.acp, timesteps)
@@ -136,7 +182,7 @@ class TrainerB200:
         dscores = None
         if not cfg.disable_ti:
             leaves = [s.detach().requires_grad_(True) for s in scores]
-            tal = compute_token_attention_loss(leaves, mask, inputs["token_indices"], self.train_ids)
+            tal = token_attention_loss_tensors(leaves, mask, st["tok_len"], st["ti_pos"])
             (cfg.token_attention_loss_w * tal / ga).backward()
             dscores = [l.grad if l.grad is not None else torch.zeros_like(l) for l in leaves]
             out["token_attention_loss"] = tal.detach()
@@ -170,27 +216,141 @@ class TrainerB200:
         return out
 
     # ---- optimizer: ONE kernel over LoRA factors + TI rows -------------------------------------------
-    def optimizer_step(self):
-        cfg = self.cfg
+    def _l1_coeff(self) -> float:
+        if self.cfg.l1_penalty <= 0.0:
+            return 0.0
+        # what autograd hands to every LoRA element for  loss += l1_penalty * sum|p| / numel  in bf16
+        return float(torch.tensor(self.cfg.l1_penalty, dtype=BF16) / self.store.numel_logical)
+
+    def _set_hyper(self):
+        """Pack this optimizer step's scalars on the host and refresh the device copy (outside any graph)."""
         ti_lr, unet_lr = self.last_lrs
+        ops.adamw_pack_hyper(self._hyper_host, lr=unet_lr, wd=self.cfg.lora_weight_decay, l1_coeff=self._l1_coeff(),
+                             lr2=ti_lr or 0.0, wd2=self.cfg.ti_weight_decay, step=self.opt_step + 1, grad_scale=1.0)
+        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+
+    def _optimizer_body(self):
         if self.pg is not None and self.world > 1:
             torch.distributed.all_reduce(self.store.grads, group=self.pg)     # the step's only collective
+        ops.adamw_dev(self.store.params, self.store.grads, self.store.m, self.store.v, self.store.n_lora,
+                      self._hyper_dev, zero_grad=True)
+
+    def optimizer_step(self):
+        self._set_hyper()
+        self._optimizer_body()
         self.opt_step += 1
-        l1c = 0.0
-        if cfg.l1_penalty > 0.0:
-            # what autograd hands to every LoRA element for  loss += l1_penalty * sum|p| / numel  in bf16
-            c = torch.tensor(cfg.l1_penalty, dtype=BF16) / self.store.numel_logical
-            l1c = float(c)
-        ops.adamw(self.store.params, self.store.grads, self.store.m, self.store.v, self.store.n_lora,
-                  lr=unet_lr, wd=cfg.lora_weight_decay, l1_coeff=l1c, lr2=ti_lr or 0.0, wd2=cfg.ti_weight_decay,
-                  step=self.opt_step, grad_scale=1.0, zero_grad=True)
 
     def step(self, inputs, completion_f: float = 0.0, do_optimizer: bool = True):
         ti_lr, unet_lr = lr_schedule(self.cfg, self.global_step, completion_f)
         self.last_lrs = (ti_lr, unet_lr)
-        out = self.forward_backward(inputs, ti_active=bool(ti_lr and ti_lr > 0.0))
+        ti_active = bool(ti_lr and ti_lr > 0.0)
         self._accum += 1
-        if do_optimizer and self._accum % self.cfg.gradient_accumulation_steps == 0:
+        opt_now = do_optimizer and self._accum % self.cfg.gradient_accumulation_steps == 0
+        if self.use_graph:
+            out = self._graph_step(inputs, ti_active, opt_now)
+        else:
+            from . import _lib
+            l0 = _lib.launch_count() if torch.cuda.is_available() else 0
+            out = self.forward_backward(inputs, ti_active=ti_active)
+            if opt_now:
+                self.optimizer_step()
+            if torch.cuda.is_available():
+                self.launches_per_step = _lib.launch_count() - l0
+        self.global_step += 1
+        return out
+
+    # ---- CUDA-graph path: the whole step (text encoders, UNet fwd/bwd, losses, all-reduce, AdamW) is ONE graph ----
+    def _graph_step(self, inputs, ti_active: bool, opt_now: bool):
+        st = self._stage_inputs(inputs)
+        if opt_now:
+            self._set_hyper()
+        key = (ti_active, opt_now)
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(st, ti_active, opt_now)
+            self._graphs[key] = entry
+        graph, out = entry
+        graph.replay()
+        if opt_now:
+            self.opt_step += 1
+        return out
+
+    def step_resident(self, completion_f: float = 0.0):
+        """One more step on the inputs already staged in HBM (no host->device traffic): bench.py's `value` leg."""
+        assert self._static is not None, "stage a batch with step() first"
+        ti_lr, unet_lr = lr_schedule(self.cfg, self.global_step, completion_f)
+        self.last_lrs = (ti_lr, unet_lr)
+        ti_active = bool(ti_lr and ti_lr > 0.0)
+        if self.use_graph:
+            self._set_hyper()
+            graph, out = self._graphs[(ti_active, True)]
+            graph.replay()
+            self.opt_step += 1
+        else:
+            out = self._body(self._static, ti_active)
             self.optimizer_step()
         self.global_step += 1
         return out
+
+    def profile_gemms(self, inputs) -> Dict[str, object]:
+        """Eager, instrumented pass: every tcgen05 GEMM launch of one step timed with CUDA events on its stream.
+        Training state is restored afterwards."""
+        snap = [t.clone() for t in (self.store.params, self.store.grads, self.store.m, self.store.v)]
+        st = self._stage_inputs(inputs)
+        ops.GEMM_PROFILE = []
+        try:
+            self._body(st, True)
+            self._set_hyper()
+            self._optimizer_body()
+            torch.cuda.synchronize()
+            recs = ops.GEMM_PROFILE
+        finally:
+            ops.GEMM_PROFILE = None
+        for t, s_ in zip((self.store.params, self.store.grads, self.store.m, self.store.v), snap):
+            t.copy_(s_)
+        for rows in self.ti_rows:
+            rows.grad = None
+        by_shape: Dict[str, Dict[str, float]] = {}
+        tot_ms = tot_fl = 0.0
+        for key, fl, e0, e1 in recs:
+            ms = e0.elapsed_time(e1)
+            tot_ms += ms
+            tot_fl += fl
+            d = by_shape.setdefault(str(key), {"count": 0, "ms": 0.0, "flop": 0.0})
+            d["count"] += 1
+            d["ms"] += ms
+            d["flop"] += fl
+        for d in by_shape.values():
+            d["tflops"] = d["flop"] / max(d["ms"], 1e-9) / 1e9
+        return {"launches": len(recs), "ms": tot_ms, "tflop": tot_fl / 1e12, "tflops": tot_fl / max(tot_ms, 1e-9) / 1e9,
+                "by_shape": dict(sorted(by_shape.items(), key=lambda kv: -kv[1]["ms"]))}
+
+    def _capture(self, st, ti_active: bool, opt_now: bool):
+        """Warm up eagerly on a side stream, then capture.  The warm-up runs must not change training state, so the
+        flat buffers are snapshotted and restored around them."""
+        snap = [t.clone() for t in (self.store.params, self.store.grads, self.store.m, self.store.v)]
+
+        def run():
+            out = self._body(st, ti_active)
+            if opt_now:
+                self._optimizer_body()
+            return out
+
+        from . import _lib
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                l0 = _lib.launch_count()
+                run()
+                self.launches_per_step = _lib.launch_count() - l0     # our kernels per step (graph replays them)
+        torch.cuda.current_stream().wait_stream(side)
+        for t, s_ in zip((self.store.params, self.store.grads, self.store.m, self.store.v), snap):
+            t.copy_(s_)
+        for rows in self.ti_rows:
+            rows.grad = None
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = run()
+        # the capture itself executed nothing; state is still the snapshot
+        return graph, out

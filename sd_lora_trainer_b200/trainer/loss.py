@@ -61,34 +61,56 @@ def process_and_stack_attention_scores(scores: Sequence[torch.Tensor], img_ratio
     return torch.stack(reshaped, dim=0)
 
 
+def token_index_tensors(token_indices: List[List[int]], train_ids: List[int], device="cpu"):
+    """Host-side part of loss.py:32-43: caption lengths and the positions of the trainable tokens
+    (``token_indices.index(token_id)``; -1 marks a caption that lacks one, which the reference skips)."""
+    tok_len = torch.tensor([len(t) for t in token_indices], dtype=torch.long)
+    pos = torch.full((len(token_indices), max(len(train_ids), 1)), -1, dtype=torch.long)
+    for b, tok in enumerate(token_indices):
+        try:
+            pos[b, :len(train_ids)] = torch.tensor([tok.index(t) for t in train_ids], dtype=torch.long)
+        except ValueError:
+            pos[b] = -1
+    return tok_len.to(device), pos.to(device)
+
+
+def token_attention_loss_tensors(scores: Sequence[torch.Tensor], masks: torch.Tensor, tok_len: torch.Tensor,
+                                 ti_pos: torch.Tensor) -> torch.Tensor:
+    """trainer/loss.py:10-80 with the per-caption Python loop replaced by index tensors (same arithmetic, same
+    dtypes), so the whole regulariser is shape-static and can sit inside a CUDA graph."""
+    masks = masks[:, 0].float()
+    img_ratio = masks.shape[-1] / masks.shape[-2]
+    maps = process_and_stack_attention_scores(scores, img_ratio)              # [layers, B, h, w, 77]
+    n_layers, B, h, w, n_text = maps.shape
+    masks = F.interpolate(masks.unsqueeze(1), size=(h, w)).squeeze(1)         # [B, h, w] (nearest)
+    # (1) mean attention of every real caption token (positions 1 .. len-2)
+    per_tok = maps.mean(dim=[0, 2, 3])                                        # [B, 77], maps' dtype
+    sq = torch.relu(per_tok - 0.0) ** 2
+    t = torch.arange(n_text, device=maps.device)[None, :]
+    sel = ((t >= 1) & (t < (tok_len[:, None] - 1))).float()
+    att_L2 = ((sq.float() * sel).sum(-1) / sel.sum(-1)).to(maps.dtype)        # [B]
+    reg0 = 5.0 * att_L2.mean()
+    # (2) heat-maps of the trainable tokens
+    valid = (ti_pos >= 0).all(dim=1)                                          # captions holding every TI token
+    nv = valid.float().sum()
+    layer_mean = maps.mean(dim=0)                                             # [B, h, w, 77]
+    idx = ti_pos.clamp(min=0)[:, None, None, :].expand(B, h, w, ti_pos.shape[1])
+    hm = torch.gather(layer_mean, 3, idx).permute(0, 3, 1, 2).float()         # [B, n_tok, h, w]
+    mk = masks[:, None]                                                       # [B, 1, h, w]
+    vw = valid.float()[:, None, None, None]
+    denom = nv * hm.shape[1] * h * w
+    reg1 = 1.0 * ((torch.relu(hm * mk) ** 2) * vw).sum() / denom
+    reg2 = 2.0 * ((torch.relu(hm * (1 - mk) + 10) ** 2) * vw).sum() / denom
+    reg3 = 1.0 * (hm.mean(dim=[2, 3]).var(dim=1) * valid.float()).sum() / nv
+    total = (reg0 + reg1 + reg2 + reg3).to(masks.dtype)
+    return torch.where(nv > 0, total, torch.zeros_like(total))                # loss.py:55-56
+
+
 def compute_token_attention_loss(scores: Sequence[torch.Tensor], masks: torch.Tensor,
                                  token_indices: List[List[int]], train_ids: List[int]) -> torch.Tensor:
     """trainer/loss.py:10-80; ``token_indices[b]`` is ``pipe.tokenizer.encode(captions[b])``."""
-    masks = masks[:, 0].float()
-    img_ratio = masks.shape[-1] / masks.shape[-2]
-    att_L2_losses, ti_heatmaps, ti_masks = [], [], []
-    attention_maps = process_and_stack_attention_scores(scores, img_ratio)
-    n_layers, batch_size, w, h, n_tokens = attention_maps.shape
-    masks = F.interpolate(masks.unsqueeze(1), size=(attention_maps.shape[-3], attention_maps.shape[-2])).squeeze(1)
-    masks = masks.unsqueeze(0).unsqueeze(-1).repeat(n_layers, 1, 1, 1, n_tokens)
-    for b, tok in enumerate(token_indices):
-        mean_att = attention_maps[:, b, :, :, 1:len(tok) - 1].mean(dim=[0, 1, 2])
-        att_L2_losses.append((torch.relu(mean_att - 0.0) ** 2).mean())
-        try:
-            ti_idx = [tok.index(t) for t in train_ids]
-        except ValueError:
-            continue
-        ti_heatmaps.append(torch.stack([attention_maps[:, b, :, :, i].mean(dim=0).float() for i in ti_idx]))
-        ti_masks.append(torch.stack([masks[:, b, :, :, i].mean(dim=0) for i in ti_idx]))
-    if len(ti_heatmaps) == 0:
-        return torch.tensor(0.0).to(masks.dtype)
-    ti_heatmaps, ti_masks = torch.stack(ti_heatmaps), torch.stack(ti_masks)
-    token_attention_scores = ti_heatmaps.mean(dim=[2, 3]).var(dim=1)
-    reg0 = 5.0 * torch.stack(att_L2_losses).mean()
-    reg1 = 1.0 * (torch.relu(ti_heatmaps * ti_masks) ** 2).mean()
-    reg2 = 2.0 * (torch.relu(ti_heatmaps * (1 - ti_masks) + 10) ** 2).mean()
-    reg3 = 1.0 * token_attention_scores.mean()
-    return (reg0 + reg1 + reg2 + reg3).to(masks.dtype)
+    tok_len, ti_pos = token_index_tensors(token_indices, train_ids, device=masks.device)
+    return token_attention_loss_tensors(scores, masks, tok_len, ti_pos)
 
 
 class DistributionLoss:

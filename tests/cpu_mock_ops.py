@@ -266,6 +266,41 @@ def adamw(p, grad, m, v, n_first, *, lr, wd, l1_coeff, lr2, wd2, beta1=0.9, beta
         grad.zero_()
 
 
+adamw_pack_hyper = real.adamw_pack_hyper          # pure host code inside the library: packs the 12 floats
+
+
+def adamw_dev(p, grad, m, v, n_first, hyper_dev, zero_grad=True):
+    """Interprets the packed hyper-parameters exactly as the CUDA kernel does (op-by-op bf16 arithmetic)."""
+    h = hyper_dev.tolist()
+    s0, s1 = h[0:3], h[3:6]
+    one_minus_b1, beta2, one_minus_b2, eps, bc2_sqrt, grad_scale = h[6:12]
+    f32 = torch.float32
+
+    def seg(sl, decay, neg_step, l1):
+        pv = p[sl].float()
+        g = (grad[sl] * grad_scale).to(BF16).float()
+        if l1 != 0.0:
+            g = (g + l1 * torch.sign(pv)).to(BF16).float()
+        if decay != 1.0:
+            pv = (pv * torch.tensor(decay, dtype=f32)).to(BF16).float()
+        mv = m[sl].float()
+        mv = (mv + torch.tensor(one_minus_b1, dtype=f32) * (g - mv)).to(BF16).float()
+        vv = (v[sl].float() * torch.tensor(beta2, dtype=f32)).to(BF16).float()
+        vv = (vv + torch.tensor(one_minus_b2, dtype=f32) * (g * g)).to(BF16).float()
+        d = vv.sqrt().to(BF16).float()
+        d = (d / torch.tensor(bc2_sqrt, dtype=f32)).to(BF16).float()
+        d = (d + torch.tensor(eps, dtype=f32)).to(BF16).float()
+        pv = (pv + torch.tensor(neg_step, dtype=f32) * (mv / d)).to(BF16)
+        p[sl] = pv
+        m[sl] = mv.to(BF16)
+        v[sl] = vv.to(BF16)
+    seg(slice(0, n_first), *s0)
+    if p.numel() > n_first:
+        seg(slice(n_first, p.numel()), *s1)
+    if zero_grad:
+        grad.zero_()
+
+
 def install(monkeypatch):
     """Patch every product module that holds a reference to ops."""
     import sd_lora_trainer_b200.step as step_mod
