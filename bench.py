@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--cpu-res", type=int, default=1024)
     ap.add_argument("--cpu-batch", type=int, default=1)
     ap.add_argument("--cpu-dtype", default="fp32", choices=["fp32", "bf16"])
-    ap.add_argument("--ref-max-steps", type=int, default=2)
+    ap.add_argument("--ref-max-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

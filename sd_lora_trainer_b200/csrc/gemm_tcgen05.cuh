@@ -28,7 +28,9 @@ constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
 constexpr int kBBytes = kMaxBN * kBK * 2;   // 32 KiB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 192;
-constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kEpiLd = 36;                 // floats per staged row: 32 + 4 pad (144 B keeps float4 alignment, no bank conflicts)
+constexpr int kEpiBytes = 4 * 32 * kEpiLd * 4;
+constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
 
 struct GemmArgs {
     CUtensorMap mapA[2];
@@ -218,8 +220,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         }
         __syncwarp();
     } else {
-        // ===================== epilogue warps (TMEM -> registers -> global) =====================
+        // ===================== epilogue warps (TMEM -> registers -> smem transpose -> coalesced global) ==========
+        // tcgen05.ld hands every thread ONE ROW of the tile; writing that straight out would touch 32 rows per store
+        // instruction.  Each warp therefore bounces 32x32 fp32 sub-tiles through a padded smem patch and re-reads
+        // them so that 8 consecutive lanes own one 128-byte row segment: alpha / bias / residual are applied in that
+        // coalesced layout and leave as 16-byte (fp32) or 8-byte (bf16) vector stores.
+        const int ew = warp - 2;
         const int lane_base = (warp & 3) * 32;    // TMEM lane quarter this warp may read
+        float* stage = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256) + ew * (32 * kEpiLd);
+        const bool row_major = (g.d_sn == 1) && !g.d_atomic;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -229,74 +238,107 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             t /= g.splits;
             const int b0 = t % g.nb0;
             const int b1 = t / g.nb0;
-            const int m = m_blk * kBM + lane_base + lane;
+            const int m_warp = m_blk * kBM + lane_base;
             const int n0 = n_blk * BN;
-            const bool row_ok = m < g.M;
-            const long long d_off = b1 * g.d_sb1 + b0 * g.d_sb0 + static_cast<long long>(m) * g.d_sm;
-            const long long r_off = b1 * g.r_sb1 + b0 * g.r_sb0 + static_cast<long long>(m) * g.r_sm;
-            const __nv_bfloat16* bias_row = nullptr;
-            if (g.bias) bias_row = g.bias + (g.bias_rows ? (m / g.bias_rows) * g.bias_sb : 0);
+            const long long d_boff = b1 * g.d_sb1 + b0 * g.d_sb0;
+            const long long r_boff = b1 * g.r_sb1 + b0 * g.r_sb0;
 
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + static_cast<uint32_t>(acc * kMaxBN);
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t raw[16];
-                tmem_ld16(taddr + c0, raw);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t raw[32];
+                tmem_ld32(taddr + c0, raw);
                 tmem_ld_wait();
-                const int n = n0 + c0;
-                if (!row_ok || n >= g.N) continue;
-                float v[16];
+                if (n0 + c0 >= g.N) continue;          // warp-uniform
+                const int cvalid = min(32, BN - c0);
+                if (row_major) {
+                    float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiLd);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]) * g.alpha;
-                const bool full = (n + 16 <= g.N);
-                if (bias_row) {
+                    for (int j = 0; j < 8; ++j)
+                        srow[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
+                                              __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
+                    __syncwarp();
+                    const int sub = lane >> 3, col = (lane & 7) * 4;
+                    const int n = n0 + c0 + col;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (full || n + j < g.N) v[j] += __bfloat162float(bias_row[n + j]);
-                }
-                if (g.R) {
-                    const __nv_bfloat16* rp = g.R + r_off + static_cast<long long>(n) * g.r_sn;
-                    if (full && g.r_sn == 1 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-                        const uint4 q0 = *reinterpret_cast<const uint4*>(rp);
-                        const uint4 q1 = *reinterpret_cast<const uint4*>(rp + 8);
-                        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    for (int it = 0; it < 8; ++it) {
+                        const int row = it * 4 + sub;
+                        const int m = m_warp + row;
+                        if (m >= g.M || col >= cvalid || n >= g.N) continue;
+                        const float4 q = *reinterpret_cast<const float4*>(stage + row * kEpiLd + col);
+                        float v[4] = {q.x * g.alpha, q.y * g.alpha, q.z * g.alpha, q.w * g.alpha};
+                        const int nv = min(4, g.N - n);
+                        if (g.bias) {
+                            const __nv_bfloat16* bp = g.bias + (g.bias_rows ? (m / g.bias_rows) * g.bias_sb : 0) + n;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-                            v[2 * j] += __bfloat162float(h.x);
-                            v[2 * j + 1] += __bfloat162float(h.y);
+                            for (int e = 0; e < 4; ++e)
+                                if (e < nv) v[e] += __bfloat162float(bp[e]);
                         }
-                    } else {
+                        if (g.R) {
+                            const __nv_bfloat16* rp = g.R + r_boff + static_cast<long long>(m) * g.r_sm + static_cast<long long>(n) * g.r_sn;
+                            if (nv == 4 && g.r_sn == 1 && ((reinterpret_cast<uintptr_t>(rp) & 7) == 0)) {
+                                const uint2 w2 = *reinterpret_cast<const uint2*>(rp);
+                                const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w2.x);
+                                const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&w2.y);
+                                v[0] += __bfloat162float(h0.x);
+                                v[1] += __bfloat162float(h0.y);
+                                v[2] += __bfloat162float(h1.x);
+                                v[3] += __bfloat162float(h1.y);
+                            } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (full || n + j < g.N) v[j] += __bfloat162float(rp[j * g.r_sn]);
-                    }
-                }
-                if (g.d_fp32) {
-                    float* dp = reinterpret_cast<float*>(g.D) + d_off + static_cast<long long>(n) * g.d_sn;
+                                for (int e = 0; e < 4; ++e)
+                                    if (e < nv) v[e] += __bfloat162float(rp[e * g.r_sn]);
+                            }
+                        }
+                        const long long doff = d_boff + static_cast<long long>(m) * g.d_sm + n;
+                        if (g.d_fp32) {
+                            float* dp = reinterpret_cast<float*>(g.D) + doff;
+                            if (nv == 4 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+                                *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+                            } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (full || n + j < g.N) {
-                            if (g.d_atomic) atomicAdd(dp + j * g.d_sn, v[j]);
-                            else dp[j * g.d_sn] = v[j];
+                                for (int e = 0; e < 4; ++e)
+                                    if (e < nv) dp[e] = v[e];
+                            }
+                        } else {
+                            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.D) + doff;
+                            if (nv == 4 && ((reinterpret_cast<uintptr_t>(dp) & 7) == 0)) {
+                                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
+                                const __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2], v[3]);
+                                uint2 w2;
+                                w2.x = *reinterpret_cast<const uint32_t*>(&h0);
+                                w2.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                *reinterpret_cast<uint2*>(dp) = w2;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (e < nv) dp[e] = __float2bfloat16_rn(v[e]);
+                            }
                         }
                     }
+                    __syncwarp();
                 } else {
-                    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.D) + d_off + static_cast<long long>(n) * g.d_sn;
-                    if (full && g.d_sn == 1 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-                        uint32_t w[8];
+                    // transposed (d_sm == 1) or atomic outputs: lane <-> row is already the coalesced direction
+                    const int m = m_warp + lane;
+                    if (m < g.M) {
+                        const __nv_bfloat16* bias_row = g.bias ? g.bias + (g.bias_rows ? (m / g.bias_rows) * g.bias_sb : 0) : nullptr;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                        for (int j = 0; j < 32; ++j) {
+                            const int n = n0 + c0 + j;
+                            if (j >= cvalid || n >= g.N) continue;
+                            float v = __uint_as_float(raw[j]) * g.alpha;
+                            if (bias_row) v += __bfloat162float(bias_row[n]);
+                            if (g.R) v += __bfloat162float(g.R[r_boff + static_cast<long long>(m) * g.r_sm + static_cast<long long>(n) * g.r_sn]);
+                            const long long doff = d_boff + static_cast<long long>(m) * g.d_sm + static_cast<long long>(n) * g.d_sn;
+                            if (g.d_fp32) {
+                                float* dp = reinterpret_cast<float*>(g.D) + doff;
+                                if (g.d_atomic) atomicAdd(dp, v);
+                                else *dp = v;
+                            } else {
+                                reinterpret_cast<__nv_bfloat16*>(g.D)[doff] = __float2bfloat16_rn(v);
+                            }
                         }
-                        *reinterpret_cast<uint4*>(dp) = make_uint4(w[0], w[1], w[2], w[3]);
-                        *reinterpret_cast<uint4*>(dp + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (full || n + j < g.N) dp[j * g.d_sn] = __float2bfloat16_rn(v[j]);
                     }
                 }
             }

@@ -114,11 +114,17 @@ class TrainerB200:
         self._static_key = None
         self._graphs: Dict[object, object] = {}
         self.h2d_bytes_last = 0
+        self._tid = None
         self.launches_per_step = 0
         self._hyper_dev = torch.zeros(12, dtype=torch.float32, device=self.device)
         self._hyper_host = torch.zeros(12, dtype=torch.float32)
         if torch.cuda.is_available():
             self._hyper_host = self._hyper_host.pin_memory()
+
+    def _time_ids(self, B: int) -> torch.Tensor:
+        if self._tid is None or self._tid.shape[0] != B:      # built once, outside any graph capture
+            self._tid = add_time_ids(B, self.cfg.resolution, BF16, self.device)
+        return self._tid
 
     # ---- inputs: host dict -> device tensors (static buffers when the step is graph-captured) ------
     def _stage_inputs(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -139,6 +145,8 @@ class TrainerB200:
             from .trainer.loss import token_index_tensors
             staged["tok_len"], staged["ti_pos"] = token_index_tensors(inputs["token_indices"], self.train_ids)
         key = tuple((k, tuple(v.shape)) for k, v in staged.items())
+        if self.sdxl:
+            self._time_ids(B)
         if self._static is None or self._static_key != key:
             self._static = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in staged.items()}
             self._static_key = key
@@ -169,7 +177,7 @@ class TrainerB200:
                 prompt_embeds, pooled = encode_prompt(self.sdxl, self.text_encoders, token_ids)
         else:                                                   # kernel-only probes: synthetic conditioning
             prompt_embeds, pooled = st["prompt_embeds"], st.get("pooled")
-        time_ids = add_time_ids(B, cfg.resolution, BF16, dev) if self.sdxl else None
+        time_ids = self._time_ids(B) if self.sdxl else None
 
         noisy, noisy8 = ops.noise_prologue(latent, noise, offset, cfg.noise_offset, self.acp, timesteps)
         pred8, scores = self.unet.forward(noisy8, B, H, W, timesteps, prompt_embeds.detach(),

@@ -60,8 +60,8 @@ def test_unet_forward_backward_matches_oracle(family):
     dpred = torch.randn(B, 4, hw, hw, device="cuda", generator=g).to(BF)
 
     def run_oracle(unet, dtype):
-        xx, cc = x.to(dtype), ctx.to(dtype).requires_grad_(True)
-        pp = pooled.to(dtype).requires_grad_(True) if sdxl else None
+        xx, cc = x.to(dtype), ctx.detach().to(dtype).clone().requires_grad_(True)
+        pp = pooled.detach().to(dtype).clone().requires_grad_(True) if sdxl else None
         for m in unet.modules():
             if hasattr(m, "capture"):
                 m.capture = True
