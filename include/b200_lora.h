@@ -87,6 +87,19 @@ int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int
                      int64_t ld_dp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Fused attention for head_dim 64 (every SDXL head): replaces F.scaled_dot_product_attention forward and its
+ * autograd backward (trainer/ti_cross_attn_loss.py:197-199, diffusers AttnProcessor2_0) without ever writing an
+ * [L, Lk] tensor to HBM.  q: [B*L, ld], k/v: [B*Lk, ld] bf16 with head h at columns [h*64, h*64+64); o likewise.
+ * lse: [B, H, L] fp32 (natural log), saved by the forward for the backward.
+ * Backward workspaces (caller-owned): delta_ws fp32 [B*H*L], dq_acc_ws fp32 [B*L*ld].
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t H,
+                        int32_t L, int32_t Lk, int64_t ld, float scale, void* stream);
+int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
+                        float* delta_ws, float* dq_acc_ws, void* dq, void* dk, void* dv, int32_t B, int32_t H,
+                        int32_t L, int32_t Lk, int64_t ld, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Normalisation / activation kernels on NHWC ([rows, C]) bf16 activations; replace ATen GroupNorm / LayerNorm /
  * SiLU / GELU kernels under diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock, GEGLU.
  * Affine parameters are frozen, so the backward kernels emit dX only.

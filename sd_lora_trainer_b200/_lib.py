@@ -33,6 +33,10 @@ SIGNATURES = {
     "b200_last_error": [],
     "b200_launch_count": [],
     "b200_gemm": [C.POINTER(GemmDesc), c_void_p],
+    "b200_flash_attn_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64,
+                            c_float, c_void_p],
+    "b200_flash_attn_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64, c_float, c_void_p],
     "b200_softmax_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_softmax_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_groupnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32,

@@ -29,6 +29,13 @@ void count_launch(int n = 1);
 
 constexpr int kNumSMs = 148;
 
+}  // namespace b200
+#include <cuda.h>
+namespace b200 {
+// 4-D bf16 TMA tensor map with 128B swizzle (gemm_host.cu); dims/strides innermost first, strides in elements.
+int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const long long strides[3], const int box[4]);
+
+
 // ---- bf16 helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float bfr(float x) {   // round-trip through bf16 (torch's per-op rounding)
     return __bfloat162float(__float2bfloat16_rn(x));

@@ -1,0 +1,83 @@
+// Host side of the fused attention kernels (head_dim 64): tensor maps over the [B*L, C] projection outputs with the
+// head as a strided batch dimension, launch configuration, and the small helper kernels of the backward.
+#include "common.cuh"
+#include "flash_attn.cuh"
+#include "../../include/b200_lora.h"
+
+using namespace b200;
+
+static int head_map(CUtensorMap* map, const void* ptr, int rows, int H, int B, long long ld, int box_rows) {
+    const long long dims[4] = {64, rows, H, B};
+    const long long strides[3] = {ld, 64, static_cast<long long>(rows) * ld};
+    const int box[4] = {64, box_rows, 1, 1};
+    return encode_map(map, ptr, dims, strides, box);
+}
+
+extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B,
+                                   int32_t H, int32_t L, int32_t Lk, int64_t ld, float scale, void* stream) {
+    B200_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && Lk >= 1 && ld >= static_cast<int64_t>(H) * 64 && ld % 8 == 0,
+                   "flash_attn_fwd: bad extents");
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+        if (e != cudaSuccess) return set_error(3, "flash_attn_fwd: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    FlashFwdArgs g;
+    memset(&g, 0, sizeof(g));
+    if (int rc = head_map(&g.mapQ, q, L, H, B, ld, 128)) return rc;
+    if (int rc = head_map(&g.mapK, k, Lk, H, B, ld, 128)) return rc;
+    if (int rc = head_map(&g.mapV, v, Lk, H, B, ld, 64)) return rc;
+    g.O = static_cast<__nv_bfloat16*>(o);
+    g.LSE = lse;
+    g.L = L;
+    g.Lk = Lk;
+    g.H = H;
+    g.o_ld = ld;
+    g.scale = scale;
+    dim3 grid((L + 127) / 128, H, B);
+    flash_fwd_kernel<<<grid, kFaThreads, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(g);
+    B200_CHECK_LAUNCH("flash_fwd");
+    return 0;
+}
+
+extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                                   const float* lse, float* delta_ws, float* dq_acc_ws, void* dq, void* dk, void* dv,
+                                   int32_t B, int32_t H, int32_t L, int32_t Lk, int64_t ld, float scale, void* stream) {
+    B200_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && Lk >= 1 && ld == static_cast<int64_t>(H) * 64,
+                   "flash_attn_bwd: needs contiguous [rows, H*64] tensors");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+        if (e != cudaSuccess) return set_error(3, "flash_attn_bwd: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    const long long nq_elems = static_cast<long long>(B) * L * ld;
+    cudaMemsetAsync(dq_acc_ws, 0, sizeof(float) * nq_elems, st);
+    flash_delta_kernel<<<grid_for(static_cast<long long>(B) * L * H, 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta_ws, B, L, H, ld);
+    B200_CHECK_LAUNCH("flash_delta");
+    FlashBwdArgs g;
+    memset(&g, 0, sizeof(g));
+    if (int rc = head_map(&g.mapQ, q, L, H, B, ld, 128)) return rc;
+    if (int rc = head_map(&g.mapDO, d_o, L, H, B, ld, 128)) return rc;
+    if (int rc = head_map(&g.mapK, k, Lk, H, B, ld, 128)) return rc;
+    if (int rc = head_map(&g.mapV, v, Lk, H, B, ld, 128)) return rc;
+    g.LSE = lse;
+    g.Delta = delta_ws;
+    g.dQacc = dq_acc_ws;
+    g.dK = static_cast<__nv_bfloat16*>(dk);
+    g.dV = static_cast<__nv_bfloat16*>(dv);
+    g.L = L;
+    g.Lk = Lk;
+    g.H = H;
+    g.ld = ld;
+    g.scale = scale;
+    dim3 grid((Lk + 127) / 128, H, B);
+    flash_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(g);
+    B200_CHECK_LAUNCH("flash_bwd");
+    f32_to_bf16_kernel<<<grid_for(nq_elems / 4, 256), 256, 0, st>>>(dq_acc_ws, static_cast<__nv_bfloat16*>(dq), nq_elems / 4);
+    B200_CHECK_LAUNCH("flash_dq_convert");
+    return 0;
+}

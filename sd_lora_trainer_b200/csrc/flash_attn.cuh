@@ -1,0 +1,521 @@
+// Fused attention for head_dim 64 on sm_100a (the SDXL case: every head is 64 wide).
+//
+// Forward  (one CTA = 128 queries of one (batch, head); two CTAs per SM):
+//     TMA: Q once, K/V in 128-key blocks through a 2-stage ring
+//     tcgen05: S = Q.K^T into TMEM (128 lanes x 128 fp32 columns), O += P.V into TMEM (128 x 64)
+//     softmax warps: one thread per query row reads its S row from TMEM (no shuffles), online max / exp2 / sum,
+//     rescales O in TMEM, writes P as bf16 into a 128B-swizzled smem tile that is the next MMA's A operand.
+//   Emits O (bf16, [B*L, C] with the head at column h*64) and LSE (fp32 [B, H, L]) for the backward.
+//
+// Backward (one CTA = 128 keys of one (batch, head); loops over 128-query blocks):
+//     S = Q.K^T and dP = dO.V^T into TMEM; softmax warps rebuild P = exp(S*scale - LSE), dS = P*(dP - delta)*scale and
+//     stage both as bf16 smem tiles; dV += P^T.dO, dK += dS^T.Q (the SAME smem tiles read MN-major) and
+//     dQ_blk = dS.K, which leaves through fp32 red.global.add (it is summed over key blocks).
+// No [L, L] tensor ever reaches HBM.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int kFaThreads = 192;
+constexpr int kFaTile = 128 * 64 * 2;          // one [128 x 64] bf16 tile: 16 KiB
+// forward smem map
+constexpr int kFwdQ = 0;
+constexpr int kFwdK = kFwdQ + kFaTile;         // 2 stages
+constexpr int kFwdV = kFwdK + 2 * kFaTile;     // 2 stages
+constexpr int kFwdP = kFwdV + 2 * kFaTile;     // [128 q x 128 k] bf16 = 2 column blocks of 16 KiB
+constexpr int kFwdBar = kFwdP + 2 * kFaTile;
+constexpr int kFwdSmem = kFwdBar + 128;
+
+struct FlashFwdArgs {
+    CUtensorMap mapQ, mapK, mapV;              // dims (64, rows, H, B); box (64, 128) K-major / (64, 64) for V
+    __nv_bfloat16* O;
+    float* LSE;                                // [B, H, L], natural-log domain
+    int L, Lk, H;
+    long long o_ld;                            // row stride of O in elements (= C)
+    float scale;                               // 1/sqrt(d)
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Store 32 consecutive columns [c0, c0+32) of row `row` of a [128 x 128] bf16 tile kept as two 128B-swizzled
+// K-major column blocks (the layout tcgen05.mma reads as an A operand, and - transposed - as an MN-major one).
+__device__ __forceinline__ void store_p_chunk(uint8_t* tile, int row, int c0, const float (&v)[32]) {
+    uint8_t* base = tile + (c0 >> 6) * kFaTile + row * 128;
+    const int j0 = (c0 & 63) >> 3;             // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int phys = (j0 + j) ^ (row & 7);
+        uint4 q;
+        q.x = pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+        q.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+        q.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+        q.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(base + phys * 16) = q;
+    }
+}
+
+__global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_constant__ FlashFwdArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFwdBar);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;      // [2]
+    uint64_t* v_full = bars + 3;      // [2]
+    uint64_t* kv_empty = bars + 5;    // [2]
+    uint64_t* s_full = bars + 7;
+    uint64_t* s_free = bars + 8;
+    uint64_t* p_full = bars + 9;
+    uint64_t* o_done = bars + 10;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int nkv = (g.Lk + 127) >> 7;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&g.mapQ);
+        tma_prefetch_desc(&g.mapK);
+        tma_prefetch_desc(&g.mapV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 4);
+        mbar_init(p_full, 4);
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, kFaTile);
+            tma_load_4d(smem + kFwdQ, &g.mapQ, q_full, 0, q0, h, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&k_full[s], kFaTile);
+                tma_load_4d(smem + kFwdK + s * kFaTile, &g.mapK, &k_full[s], 0, j * 128, h, b);
+                mbar_expect_tx(&v_full[s], kFaTile);
+                tma_load_4d(smem + kFwdV + s * kFaTile, &g.mapV, &v_full[s], 0, j * 128, h, b);
+                tma_load_4d(smem + kFwdV + s * kFaTile + 8192, &g.mapV, &v_full[s], 0, j * 128 + 64, h, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);     // S[128q x 128k] = Q (K-major) . K^T (K-major)
+            const uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);      // O[128q x 64d] += P (K-major) . V (MN-major)
+            const uint32_t sq = smem_u32(smem + kFwdQ), sp = smem_u32(smem + kFwdP);
+            auto issue_s = [&](int j) {
+                const uint32_t sk = smem_u32(smem + kFwdK + (j & 1) * kFaTile);
+                const uint64_t ad = umma_desc(sq, 16, 1024), bd = umma_desc(sk, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
+                umma_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                if (j + 1 < nkv) {
+                    mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    mbar_wait(s_free, j & 1);              // the softmax warps have drained S_j out of TMEM
+                    tc_fence_after();
+                    issue_s(j + 1);
+                }
+                mbar_wait(p_full, j & 1);                   // P_j staged in smem, O rescaled
+                mbar_wait(&v_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t sv = smem_u32(smem + kFwdV + s * kFaTile);
+                const uint64_t vd = umma_desc(sv, 8192, 1024);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint64_t pd = umma_desc(sp + (k >> 2) * kFaTile, 16, 1024) + 2 * (k & 3);
+                    umma_bf16(tmem_O, pd, vd + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(o_done);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- softmax / correction / epilogue: thread <-> query row ----
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(lane_base) << 16;
+        const float sl2 = g.scale * 1.4426950408889634f;           // scores are used in the log2 domain
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kvalid = min(128, g.Lk - j * 128);
+            // pass 1: row maximum
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_S + lane_off + c * 32, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+            }
+            const float m_new = fmaxf(m, mx);
+            const float alpha = exp2f((m - m_new) * sl2);           // 0 on the first block (m = -inf)
+            const float moff = m_new * sl2;
+            if (j > 0) {
+                // the previous P.V must have retired before O is rescaled and before sP is overwritten
+                mbar_wait(o_done, (j - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(tmem_O + lane_off + c * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st32(tmem_O + lane_off + c * 32, o);
+                }
+                tmem_st_wait();
+            }
+            // pass 2: exponentials, row sum, P -> smem (bf16)
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_S + lane_off + c * 32, raw);
+                tmem_ld_wait();
+                float p[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    p[i] = (c * 32 + i < kvalid) ? exp2f(__uint_as_float(raw[i]) * sl2 - moff) : 0.f;
+                    sum += p[i];
+                }
+                store_p_chunk(smem + kFwdP, row, c * 32, p);
+            }
+            l = l * alpha + sum;
+            m = m_new;
+            tc_fence_before();
+            fence_proxy_async();                                    // generic-proxy smem writes -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(s_free);
+                mbar_arrive(p_full);
+            }
+        }
+        mbar_wait(o_done, (nkv - 1) & 1);
+        tc_fence_after();
+        const int q = q0 + row;
+        const float inv = 1.f / l;
+        __nv_bfloat16* op = g.O + (static_cast<long long>(b) * g.L + q) * g.o_ld + h * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off + c * 32, o);
+            tmem_ld_wait();
+            if (q < g.L) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 w;
+                    w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+                    w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+                    w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+                    w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = w;
+                }
+            }
+        }
+        if (q < g.L) g.LSE[(static_cast<long long>(b) * g.H + h) * g.L + q] = m * g.scale + logf(l);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+
+// =================================================================================================================
+// backward
+// =================================================================================================================
+constexpr int kBwdThreads = 320;               // TMA, MMA, 4 softmax warps, 4 dQ-epilogue warps
+constexpr int kBwdK = 0;
+constexpr int kBwdV = kBwdK + kFaTile;
+constexpr int kBwdQ = kBwdV + kFaTile;         // 2 stages
+constexpr int kBwdDO = kBwdQ + 2 * kFaTile;    // 2 stages
+constexpr int kBwdP = kBwdDO + 2 * kFaTile;    // [128 q x 128 k] bf16
+constexpr int kBwdDS = kBwdP + 2 * kFaTile;    // [128 q x 128 k] bf16
+constexpr int kBwdBar = kBwdDS + 2 * kFaTile;
+constexpr int kBwdSmem = kBwdBar + 256;
+
+struct FlashBwdArgs {
+    CUtensorMap mapQ, mapDO, mapK, mapV;       // dims (64, rows, H, B); box (64, 128)
+    const float* LSE;                          // [B, H, L]
+    const float* Delta;                        // [B, H, L] = rowsum(dO * O)
+    float* dQacc;                              // fp32 [B*L, ld] accumulated over key blocks (zeroed by the caller)
+    __nv_bfloat16* dK;                         // [B*Lk, ld]
+    __nv_bfloat16* dV;
+    int L, Lk, H;
+    long long ld;
+    float scale;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_constant__ FlashBwdArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdBar);
+    uint64_t* kv_full = bars + 0;
+    uint64_t* qdo_full = bars + 1;     // [2]
+    uint64_t* qdo_empty = bars + 3;    // [2]
+    uint64_t* sdp_full = bars + 5;
+    uint64_t* sdp_free = bars + 6;
+    uint64_t* pds_full = bars + 7;
+    uint64_t* pds_free = bars + 8;
+    uint64_t* dq_full = bars + 9;
+    uint64_t* dq_free = bars + 10;
+    uint64_t* dkv_full = bars + 11;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int nq = (g.L + 127) >> 7;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&g.mapQ);
+        tma_prefetch_desc(&g.mapDO);
+        tma_prefetch_desc(&g.mapK);
+        tma_prefetch_desc(&g.mapV);
+        mbar_init(kv_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&qdo_full[i], 1);
+            mbar_init(&qdo_empty[i], 1);
+        }
+        mbar_init(sdp_full, 1);
+        mbar_init(sdp_free, 4);
+        mbar_init(pds_full, 4);
+        mbar_init(pds_free, 1);
+        mbar_init(dq_full, 1);
+        mbar_init(dq_free, 4);
+        mbar_init(dkv_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t t_S = tmem, t_dP = tmem + 128, t_dV = tmem + 256, t_dK = tmem + 320, t_dQ = tmem + 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(kv_full, 2 * kFaTile);
+            tma_load_4d(smem + kBwdK, &g.mapK, kv_full, 0, k0, h, b);
+            tma_load_4d(smem + kBwdV, &g.mapV, kv_full, 0, k0, h, b);
+            for (int i = 0; i < nq; ++i) {
+                const int s = i & 1;
+                mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
+                mbar_expect_tx(&qdo_full[s], 2 * kFaTile);
+                tma_load_4d(smem + kBwdQ + s * kFaTile, &g.mapQ, &qdo_full[s], 0, i * 128, h, b);
+                tma_load_4d(smem + kBwdDO + s * kFaTile, &g.mapDO, &qdo_full[s], 0, i * 128, h, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t id_kk = umma_idesc_bf16(128, 0, 0);   // [128q x 128k]: A K-major, B K-major
+            const uint32_t id_mm = umma_idesc_bf16(64, 1, 1);    // [128k x 64d]:  A MN-major (P^T / dS^T), B MN-major
+            const uint32_t id_km = umma_idesc_bf16(64, 0, 1);    // [128q x 64d]:  A K-major (dS), B MN-major (K)
+            const uint32_t sk = smem_u32(smem + kBwdK), sv = smem_u32(smem + kBwdV);
+            const uint32_t sp = smem_u32(smem + kBwdP), sds = smem_u32(smem + kBwdDS);
+            mbar_wait(kv_full, 0);
+            for (int i = 0; i < nq; ++i) {
+                const int s = i & 1;
+                const uint32_t sq = smem_u32(smem + kBwdQ + s * kFaTile), sdo = smem_u32(smem + kBwdDO + s * kFaTile);
+                mbar_wait(&qdo_full[s], (i >> 1) & 1);
+                mbar_wait(sdp_free, (i & 1) ^ 1);
+                tc_fence_after();
+                {
+                    const uint64_t aq = umma_desc(sq, 16, 1024), bk = umma_desc(sk, 16, 1024);
+                    const uint64_t ado = umma_desc(sdo, 16, 1024), bv = umma_desc(sv, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_S, aq + 2 * k, bk + 2 * k, id_kk, k > 0);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_bf16(t_dP, ado + 2 * k, bv + 2 * k, id_kk, k > 0);
+                }
+                umma_commit(sdp_full);
+                mbar_wait(pds_full, i & 1);
+                mbar_wait(dq_free, (i & 1) ^ 1);
+                tc_fence_after();
+                {
+                    const uint64_t apT = umma_desc(sp, kFaTile, 1024), adsT = umma_desc(sds, kFaTile, 1024);
+                    const uint64_t bdo = umma_desc(sdo, 8192, 1024), bq = umma_desc(sq, 8192, 1024);
+                    const uint64_t bkm = umma_desc(sk, 8192, 1024);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) umma_bf16(t_dV, apT + 128 * k, bdo + 128 * k, id_mm, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) umma_bf16(t_dK, adsT + 128 * k, bq + 128 * k, id_mm, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint64_t ads = umma_desc(sds + (k >> 2) * kFaTile, 16, 1024) + 2 * (k & 3);
+                        umma_bf16(t_dQ, ads, bkm + 128 * k, id_km, k > 0);
+                    }
+                }
+                umma_commit(&qdo_empty[s]);
+                umma_commit(pds_free);
+                umma_commit(dq_full);
+            }
+            umma_commit(dkv_full);
+        }
+        __syncwarp();
+    } else {
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(lane_base) << 16;
+        const float sl2 = g.scale * 1.4426950408889634f;
+        const int kvalid = min(128, g.Lk - k0);
+        const long long stat_base = (static_cast<long long>(b) * g.H + h) * g.L;
+        if (warp < 6) {
+            // ---- softmax warps: rebuild P, form dS, stage both for the MMAs (thread <-> query row) ----
+            for (int i = 0; i < nq; ++i) {
+                const int q = i * 128 + row;
+                const bool qok = q < g.L;
+                const float lse2 = qok ? g.LSE[stat_base + q] * 1.4426950408889634f : 0.f;
+                const float delta = qok ? g.Delta[stat_base + q] : 0.f;
+                mbar_wait(sdp_full, i & 1);
+                mbar_wait(pds_free, (i & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t rs[32], rp[32];
+                    tmem_ld32(t_S + lane_off + c * 32, rs);
+                    tmem_ld32(t_dP + lane_off + c * 32, rp);
+                    tmem_ld_wait();
+                    float p[32], ds[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const bool ok = qok && (c * 32 + e < kvalid);
+                        p[e] = ok ? exp2f(__uint_as_float(rs[e]) * sl2 - lse2) : 0.f;
+                        ds[e] = p[e] * (__uint_as_float(rp[e]) - delta) * g.scale;
+                    }
+                    store_p_chunk(smem + kBwdP, row, c * 32, p);
+                    store_p_chunk(smem + kBwdDS, row, c * 32, ds);
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(sdp_free);
+                    mbar_arrive(pds_full);
+                }
+            }
+        } else {
+            // ---- dQ epilogue warps: dQ_blk leaves as fp32 reductions (summed over key blocks) ----
+            for (int i = 0; i < nq; ++i) {
+                const int q = i * 128 + row;
+                mbar_wait(dq_full, i & 1);
+                tc_fence_after();
+                float* dst = g.dQacc + (static_cast<long long>(b) * g.L + q) * g.ld + h * 64;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(t_dQ + lane_off + c * 32, r);
+                    tmem_ld_wait();
+                    if (q < g.L) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + e * 4),
+                                      make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
+                                                  __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3])));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dq_free);
+            }
+        }
+        // ---- dV (softmax warps) / dK (epilogue warps): thread <-> key row ----
+        mbar_wait(dkv_full, 0);
+        tc_fence_after();
+        const int key = k0 + row;
+        const uint32_t src = (warp < 6) ? t_dV : t_dK;
+        __nv_bfloat16* out = ((warp < 6) ? g.dV : g.dK) + (static_cast<long long>(b) * g.Lk + key) * g.ld + h * 64;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(src + lane_off + c * 32, r);
+            tmem_ld_wait();
+            if (key < g.Lk) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    uint4 w;
+                    w.x = pack_bf16(__uint_as_float(r[8 * e + 0]), __uint_as_float(r[8 * e + 1]));
+                    w.y = pack_bf16(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]));
+                    w.z = pack_bf16(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]));
+                    w.w = pack_bf16(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]));
+                    *reinterpret_cast<uint4*>(out + c * 32 + e * 8) = w;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// delta[b, h, l] = sum_d dO * O   (one thread per (row, head), 64-wide dot product)
+__global__ void flash_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
+                                   float* __restrict__ delta, int B, int L, int H, long long ld) {
+    const long long total = static_cast<long long>(B) * L * H;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int hh = static_cast<int>(idx % H);
+        const long long bl = idx / H;
+        const int l = static_cast<int>(bl % L);
+        const int bb = static_cast<int>(bl / L);
+        const uint4* po = reinterpret_cast<const uint4*>(O + bl * ld + hh * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(dO + bl * ld + hh * 64);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 a = po[i], c = pd[i];
+            const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* hc = reinterpret_cast<const __nv_bfloat162*>(&c);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                acc += __bfloat162float(ha[e].x) * __bfloat162float(hc[e].x);
+                acc += __bfloat162float(ha[e].y) * __bfloat162float(hc[e].y);
+            }
+        }
+        delta[(static_cast<long long>(bb) * H + hh) * L + l] = acc;
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        uint2 w;
+        w.x = pack_bf16(v.x, v.y);
+        w.y = pack_bf16(v.z, v.w);
+        reinterpret_cast<uint2*>(y)[i] = w;
+    }
+}
+
+}  // namespace b200

@@ -39,7 +39,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // 4-D bf16 tensor map, 128B swizzle.  dims/strides innermost first; strides in elements (dims 1..3).
-static int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const long long strides[3],
+int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const long long strides[3],
                       const int box[4]) {
     auto fn = get_encode_fn();
     if (!fn) return set_error(4, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");

@@ -133,6 +133,33 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
     return out
 
 
+# ---- fused attention (head_dim 64) -----------------------------------------------------------------
+def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, L: int, Lk: int, scale: float):
+    """q: [B*L, H*64], k/v: [B*Lk, H*64] bf16.  Returns (o [B*L, H*64] bf16, lse [B, H, L] fp32)."""
+    ld = q.stride(0)
+    assert k.stride(0) == ld and v.stride(0) == ld and q.stride(1) == 1
+    o = torch.empty(B * L, H * 64, dtype=BF16, device=q.device)
+    lse = torch.empty(B, H, L, dtype=torch.float32, device=q.device)
+    check(_lib.load().b200_flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
+                                          B, H, L, Lk, ld, scale, _stream()), "flash_attn_fwd")
+    return o, lse
+
+
+def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale: float):
+    """Returns (dq [B*L, C], dk [B*Lk, C], dv [B*Lk, C]) bf16."""
+    C_ = H * 64
+    dev = q.device
+    dq = torch.empty(B * L, C_, dtype=BF16, device=dev)
+    dk = torch.empty(B * Lk, C_, dtype=BF16, device=dev)
+    dv = torch.empty(B * Lk, C_, dtype=BF16, device=dev)
+    delta = torch.empty(B * H * L, dtype=torch.float32, device=dev)
+    dq_acc = torch.empty(B * L * C_, dtype=torch.float32, device=dev)
+    check(_lib.load().b200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
+                                          lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr(), dq.data_ptr(),
+                                          dk.data_ptr(), dv.data_ptr(), B, H, L, Lk, C_, scale, _stream()), "flash_attn_bwd")
+    return dq, dk, dv
+
+
 # ---- softmax ------------------------------------------------------------------------------------
 def softmax_fwd(S: torch.Tensor, P: torch.Tensor, rows: int, cols: int, ld_s: int, ld_p: int):
     check(_lib.load().b200_softmax_fwd(S.data_ptr(), P.data_ptr(), rows, cols, ld_s, ld_p, _stream()), "softmax_fwd")

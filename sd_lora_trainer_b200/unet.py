@@ -332,18 +332,23 @@ class Attn:
         scale = d ** -0.5
         Lp = _r8(Lk)
         dev = x.device
-        S = torch.empty(B, H, L, Lp, dtype=torch.float32, device=dev)
-        P = torch.empty(B, H, L, Lp, dtype=BF16, device=dev)
-        sS = (Lp, 1, L * Lp, H * L * Lp)
-        qm = Mat(q, L, d, C, sb0=d, sb1=L * C, batched=True)
-        km = Mat(k, Lk, d, C, sb0=d, sb1=Lk * C, batched=True)
-        ops.gemm(S, L, Lk, [(qm, km, d)], d_strides=sS, alpha=scale, nb0=H, nb1=B)
-        ops.softmax_fwd(S, P, B * H * L, Lk, Lp, Lp)
-        del S
-        O = torch.empty(B * L, C, dtype=BF16, device=dev)
-        pm = Mat(P, L, Lk, Lp, sb0=L * Lp, sb1=H * L * Lp, batched=True)
-        vm = Mat(v, Lk, d, C, mn=True, sb0=d, sb1=Lk * C, batched=True)
-        ops.gemm(O, L, d, [(pm, vm, Lk)], d_strides=(C, 1, d, L * C), nb0=H, nb1=B)
+        P = lse = None
+        if d == 64:
+            # fused tcgen05 attention: S and O live in TMEM, P only ever exists as a swizzled smem tile
+            O, lse = ops.flash_attn_fwd(q, k, v, B, H, L, Lk, scale)
+        else:
+            S = torch.empty(B, H, L, Lp, dtype=torch.float32, device=dev)
+            P = torch.empty(B, H, L, Lp, dtype=BF16, device=dev)
+            sS = (Lp, 1, L * Lp, H * L * Lp)
+            qm = Mat(q, L, d, C, sb0=d, sb1=L * C, batched=True)
+            km = Mat(k, Lk, d, C, sb0=d, sb1=Lk * C, batched=True)
+            ops.gemm(S, L, Lk, [(qm, km, d)], d_strides=sS, alpha=scale, nb0=H, nb1=B)
+            ops.softmax_fwd(S, P, B * H * L, Lk, Lp, Lp)
+            del S
+            O = torch.empty(B * L, C, dtype=BF16, device=dev)
+            pm = Mat(P, L, Lk, Lp, sb0=L * Lp, sb1=H * L * Lp, batched=True)
+            vm = Mat(v, Lk, d, C, mn=True, sb0=d, sb1=Lk * C, batched=True)
+            ops.gemm(O, L, d, [(pm, vm, Lk)], d_strides=(C, 1, d, L * C), nb0=H, nb1=B)
         if self.capture and self.cross:
             # sum over heads of q_h.k_h / sqrt(d)  ==  (q.k over all C channels) / sqrt(d): one batched GEMM
             sc = torch.empty(B, L, Lp, dtype=BF16, device=dev)
@@ -351,11 +356,11 @@ class Attn:
                      d_strides=(Lp, 1, 0, L * Lp), alpha=scale, nb0=1, nb1=B)
             self.scores = sc[:, :, :Lk]
         y = self.to_out.fwd(O, residual=residual)
-        self.sv = (q, k, v, P, B, L, Lk)
+        self.sv = (q, k, v, P, B, L, Lk, O if d == 64 else None, lse)
         return y
 
     def bwd(self, dy, d_ctx_accum, dscores: Optional[torch.Tensor]):
-        q, k, v, P, B, L, Lk = self.sv
+        q, k, v, P, B, L, Lk, O, lse = self.sv
         self.sv = None
         C = self.to_q.N
         H, d = self.h, C // self.h
@@ -363,28 +368,31 @@ class Attn:
         Lp = _r8(Lk)
         dev = dy.device
         dO = self.to_out.bwd(dy)
-        sS = (Lp, 1, L * Lp, H * L * Lp)
-        # dV = P^T dO
-        dV = torch.empty(B * Lk, C, dtype=BF16, device=dev)
-        ops.gemm(dV, Lk, d, [(Mat(P, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
-                              Mat(dO, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
-                 d_strides=(C, 1, d, Lk * C), nb0=H, nb1=B)
-        # dP = dO V^T ; dS = P * (dP - rowsum(P dP))
-        dP = torch.empty(B, H, L, Lp, dtype=torch.float32, device=dev)
-        ops.gemm(dP, L, Lk, [(Mat(dO, L, d, C, sb0=d, sb1=L * C, batched=True),
-                              Mat(v, Lk, d, C, sb0=d, sb1=Lk * C, batched=True), d)], d_strides=sS, nb0=H, nb1=B)
-        dS = torch.empty(B, H, L, Lp, dtype=BF16, device=dev)
-        ops.softmax_bwd(P, dP, dS, B * H * L, Lk, Lp, Lp)
-        del dP, P
-        # dQ = scale dS K ; dK = scale dS^T Q
-        dQ = torch.empty(B * L, C, dtype=BF16, device=dev)
-        ops.gemm(dQ, L, d, [(Mat(dS, L, Lk, Lp, sb0=L * Lp, sb1=H * L * Lp, batched=True),
-                             Mat(k, Lk, d, C, mn=True, sb0=d, sb1=Lk * C, batched=True), Lk)],
-                 d_strides=(C, 1, d, L * C), alpha=scale, nb0=H, nb1=B)
-        dK = torch.empty(B * Lk, C, dtype=BF16, device=dev)
-        ops.gemm(dK, Lk, d, [(Mat(dS, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
-                              Mat(q, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
-                 d_strides=(C, 1, d, Lk * C), alpha=scale, nb0=H, nb1=B)
+        if d == 64:
+            dQ, dK, dV = ops.flash_attn_bwd(q, k, v, O, dO, lse, B, H, L, Lk, scale)
+        else:
+            sS = (Lp, 1, L * Lp, H * L * Lp)
+            # dV = P^T dO
+            dV = torch.empty(B * Lk, C, dtype=BF16, device=dev)
+            ops.gemm(dV, Lk, d, [(Mat(P, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
+                                  Mat(dO, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
+                     d_strides=(C, 1, d, Lk * C), nb0=H, nb1=B)
+            # dP = dO V^T ; dS = P * (dP - rowsum(P dP))
+            dP = torch.empty(B, H, L, Lp, dtype=torch.float32, device=dev)
+            ops.gemm(dP, L, Lk, [(Mat(dO, L, d, C, sb0=d, sb1=L * C, batched=True),
+                                  Mat(v, Lk, d, C, sb0=d, sb1=Lk * C, batched=True), d)], d_strides=sS, nb0=H, nb1=B)
+            dS = torch.empty(B, H, L, Lp, dtype=BF16, device=dev)
+            ops.softmax_bwd(P, dP, dS, B * H * L, Lk, Lp, Lp)
+            del dP, P
+            # dQ = scale dS K ; dK = scale dS^T Q
+            dQ = torch.empty(B * L, C, dtype=BF16, device=dev)
+            ops.gemm(dQ, L, d, [(Mat(dS, L, Lk, Lp, sb0=L * Lp, sb1=H * L * Lp, batched=True),
+                                 Mat(k, Lk, d, C, mn=True, sb0=d, sb1=Lk * C, batched=True), Lk)],
+                     d_strides=(C, 1, d, L * C), alpha=scale, nb0=H, nb1=B)
+            dK = torch.empty(B * Lk, C, dtype=BF16, device=dev)
+            ops.gemm(dK, Lk, d, [(Mat(dS, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
+                                  Mat(q, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
+                     d_strides=(C, 1, d, Lk * C), alpha=scale, nb0=H, nb1=B)
         if dscores is not None:
             dsc = torch.zeros(B, L, Lp, dtype=BF16, device=dev)
             dsc[:, :, :Lk] = dscores

@@ -84,6 +84,27 @@ def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, 
     return out
 
 
+def flash_attn_fwd(q, k, v, B, H, L, Lk, scale):
+    C_ = H * 64
+    q4 = q.float().view(B, L, H, 64).transpose(1, 2)
+    k4 = k.float().view(B, Lk, H, 64).transpose(1, 2)
+    v4 = v.float().view(B, Lk, H, 64).transpose(1, 2)
+    s = q4 @ k4.transpose(-1, -2) * scale
+    o = torch.softmax(s, -1).to(BF16).float() @ v4
+    return _bf(o.transpose(1, 2).reshape(B * L, C_)), torch.logsumexp(s, -1)
+
+
+def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale):
+    C_ = H * 64
+    q4 = q.float().view(B, L, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    k4 = k.float().view(B, Lk, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    v4 = v.float().view(B, Lk, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    out = torch.softmax(q4 @ k4.transpose(-1, -2) * scale, -1) @ v4
+    out.backward(d_o.float().view(B, L, H, 64).transpose(1, 2))
+    unh = lambda t, n: _bf(t.transpose(1, 2).reshape(B * n, C_))
+    return unh(q4.grad, L), unh(k4.grad, Lk), unh(v4.grad, Lk)
+
+
 def softmax_fwd(S, P, rows, cols, ld_s, ld_p):
     s = _view(S, (rows, cols), (ld_s, 1))
     p = _view(P, (rows, ld_p), (ld_p, 1))
