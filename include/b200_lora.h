@@ -72,6 +72,17 @@ typedef struct {
     int64_t bias_sb;
     const void* R;                /* bf16 residual or NULL */
     int64_t r_sm, r_sn, r_sb0, r_sb1;
+    /* fused low-rank side path (num_seg == 1, no conv, no batch, no split-K):
+         D += (side_alpha * A[0] . S^T) . B2^T ,  T_out[m, 0..side_r) = bf16(side_alpha * A[0] . S^T)
+       forward : S = lora_A [r, K] (K-major),            B2 = lora_B [N, r] (K-major)
+       dgrad   : S = lora_B [N_layer, r] (MN-major),     B2 = lora_A [r, K_layer] (MN-major)
+       so  W.x + s.B.(A.x)  and its input gradient are ONE launch each, and T/U come out for the dA/dB GEMMs. */
+    int32_t side;
+    int32_t side_r;               /* rank (<= 32) */
+    b200_operand_t S, B2;
+    float side_alpha;
+    void* T_out;                  /* bf16 [M, t_ld] or NULL */
+    int64_t t_ld;
 } b200_gemm_t;
 
 int b200_gemm(const b200_gemm_t* desc, void* stream);

@@ -24,7 +24,9 @@ class GemmDesc(C.Structure):
                 ("D", c_void_p), ("d_fp32", c_int32), ("d_atomic", c_int32),
                 ("d_sm", c_int64), ("d_sn", c_int64), ("d_sb0", c_int64), ("d_sb1", c_int64),
                 ("alpha", c_float), ("bias", c_void_p), ("bias_rows", c_int32), ("bias_sb", c_int64),
-                ("R", c_void_p), ("r_sm", c_int64), ("r_sn", c_int64), ("r_sb0", c_int64), ("r_sb1", c_int64)]
+                ("R", c_void_p), ("r_sm", c_int64), ("r_sn", c_int64), ("r_sb0", c_int64), ("r_sb1", c_int64),
+                ("side", c_int32), ("side_r", c_int32), ("S", Operand), ("B2", Operand), ("side_alpha", c_float),
+                ("T_out", c_void_p), ("t_ld", c_int64)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); must match include/b200_lora.h exactly.

@@ -77,12 +77,12 @@ static int encode_operand(CUtensorMap* map, const b200_operand_t& op, int box_ro
 }
 
 // Tile width: whole waves over 148 persistent CTAs, tie-break towards wider tiles (fewer re-reads of A).
-static int pick_block_n(long long tiles_m_total, int N) {
+static int pick_block_n(long long tiles_m_total, int N, int max_bn) {
     const int n16 = ((N + 15) / 16) * 16;
-    if (n16 <= 256 && tiles_m_total * 1 >= kNumSMs / 2) return n16 < 16 ? 16 : n16;
+    if (n16 <= max_bn && tiles_m_total * 1 >= kNumSMs / 2) return n16 < 16 ? 16 : n16;
     int best = 16;
     double best_cost = 1e30;
-    const int hi = n16 < 256 ? n16 : 256;
+    const int hi = n16 < max_bn ? n16 : max_bn;
     for (int bn = hi; bn >= 32; bn -= 16) {
         const long long tiles = tiles_m_total * ((N + bn - 1) / bn);
         const long long waves = (tiles + kNumSMs - 1) / kNumSMs;
@@ -129,7 +129,14 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     g.num_seg = d->num_seg;
     g.tiles_m = (d->M + kBM - 1) / kBM;
     int bn = d->block_n;
-    if (bn <= 0) bn = pick_block_n(static_cast<long long>(g.tiles_m) * d->nb0 * d->nb1 * d->splits, d->N);
+    if (d->side) {
+        B200_CHECK_ARG(d->num_seg == 1 && !d->conv && d->nb0 == 1 && d->nb1 == 1 && d->splits == 1,
+                       "gemm: the fused side path needs one segment, no conv, no batch, no split-K");
+        B200_CHECK_ARG(d->side_r >= 1 && d->side_r <= 32, "gemm: side rank %d out of range", d->side_r);
+    }
+    if (bn <= 0) bn = pick_block_n(static_cast<long long>(g.tiles_m) * d->nb0 * d->nb1 * d->splits, d->N,
+                                   d->side ? kSideMaxBN : kMaxBN);
+    if (d->side) B200_CHECK_ARG(bn <= kSideMaxBN, "gemm: block_n %d too wide for the side path", bn);
     B200_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= kMaxBN, "gemm: block_n %d must be a multiple of 16 in [16, 256]", bn);
     g.BN = bn;
     g.tiles_n = (d->N + bn - 1) / bn;
@@ -177,6 +184,18 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
         if (int rc = encode_operand(&g.mapB[s], B, bn, d->nb0, d->nb1)) return rc;
     }
     B200_CHECK_ARG(d->splits <= g.kblocks[0], "gemm: more splits (%d) than K blocks (%d)", d->splits, g.kblocks[0]);
+    if (d->side) {
+        g.side = 1;
+        g.side_r = d->side_r;
+        g.side_r16 = ((d->side_r + 15) / 16) * 16;
+        g.side_mn = d->S.mn_major;
+        g.b2_mn = d->B2.mn_major;
+        g.side_alpha = d->side_alpha;
+        g.T_out = static_cast<__nv_bfloat16*>(d->T_out);
+        g.t_ld = d->t_ld;
+        if (int rc = encode_operand(&g.mapS, d->S, g.side_r16, 1, 1)) return rc;
+        if (int rc = encode_operand(&g.mapB2, d->B2, bn, 1, 1)) return rc;
+    }
 
     g.D = d->D;
     g.d_fp32 = d->d_fp32;

@@ -30,7 +30,14 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 192;
 constexpr int kEpiLd = 36;                 // floats per staged row: 32 + 4 pad (144 B keeps float4 alignment, no bank conflicts)
 constexpr int kEpiBytes = 4 * 32 * kEpiLd * 4;
-constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
+constexpr int kSideOff = 24 * 1024;         // side-path operand tile lives in the last 8 KiB of a stage's B region
+constexpr int kSideMaxBN = 192;             // => the main B tile may use at most 24 KiB when the side path is on
+constexpr int kSideCol = 192;               // TMEM column (inside an accumulator stage) of the rank-r side accumulator
+constexpr int kTBytes = kBM * 128;          // T/U staged as a 128B-swizzled K-major A operand (only r columns used)
+constexpr int kBarOff = kStages * kStageBytes;
+constexpr int kEpiOff = kBarOff + 256;
+constexpr int kTOff = kEpiOff + kEpiBytes;
+constexpr int kGemmSmemBytes = kTOff + kTBytes;
 
 struct GemmArgs {
     CUtensorMap mapA[2];
@@ -61,6 +68,18 @@ struct GemmArgs {
     long long bias_sb;        // stride between bias vectors
     const __nv_bfloat16* R;   // residual, added after alpha/bias (nullptr: none)
     long long r_sm, r_sn, r_sb0, r_sb1;
+    // fused low-rank side path (single segment only):  D += (side_alpha * A . S^T) . B2^T
+    //   main loop : Tacc[128 x r16] += A_tile . S_tile   (S = LoRA A fwd / LoRA B bwd), in TMEM next to the main tile
+    //   T-phase   : epilogue warps scale + round Tacc to bf16, stage it in smem as an A operand, n_blk 0 writes it out
+    //   final MMA : main tile += T . B2_tile              (B2 = LoRA B fwd / LoRA A bwd)
+    int side;
+    int side_mn, b2_mn;       // operand majorness of S and B2
+    int side_r16;             // rank rounded up to 16 (16 or 32): MMA N of the side accumulate, K of the final MMA
+    int side_r;               // true rank (columns written to T_out)
+    float side_alpha;
+    __nv_bfloat16* T_out;     // [M, t_ld] bf16 (batch 0 only; the side path is not batched)
+    long long t_ld;
+    CUtensorMap mapS, mapB2;
 };
 
 __device__ __forceinline__ void advance_stage(int& stage, uint32_t& phase) {
@@ -71,14 +90,15 @@ __device__ __forceinline__ void advance_stage(int& stage, uint32_t& phase) {
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmArgs g) {
-    extern __shared__ uint8_t smem_raw[];
     // 128B swizzle atoms must sit on 1024 B boundaries.
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOff);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;    // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
-    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* side_full_bar = tmem_empty_bar + 2;     // [2]  side accumulator complete (MMA -> epilogue warps)
+    uint64_t* t_ready_bar = side_full_bar + 2;        // T staged in smem (epilogue warps -> MMA)
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(t_ready_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -95,6 +115,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], 4);
+            mbar_init(&side_full_bar[i], 1);
+        }
+        mbar_init(t_ready_bar, 4);
+        if (g.side) {
+            tma_prefetch_desc(&g.mapS);
+            tma_prefetch_desc(&g.mapB2);
         }
         fence_barrier_init();
     }
@@ -141,7 +167,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     }
                     const int ab0 = g.a_batched[seg] ? b0 : 0, ab1 = g.a_batched[seg] ? b1 : 0;
                     const int bb0 = g.b_batched[seg] ? b0 : 0, bb1 = g.b_batched[seg] ? b1 : 0;
-                    const uint32_t tx = kABytes + (g.b_mn[seg] ? b_bytes_mn : b_bytes_k);
+                    const uint32_t side_bytes = g.side ? (g.side_mn ? 8192u : static_cast<uint32_t>(g.side_r16) * 128u) : 0u;
+                    const uint32_t tx = kABytes + (g.b_mn[seg] ? b_bytes_mn : b_bytes_k) + side_bytes;
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * kStageBytes;
@@ -166,8 +193,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                         } else {
                             tma_load_4d(sb, &g.mapB[seg], &full_bar[stage], bk, bn, bb0, bb1);
                         }
+                        if (g.side) {
+                            if (g.side_mn) tma_load_4d(sb + kSideOff, &g.mapS, &full_bar[stage], 0, kb * kBK, 0, 0);
+                            else tma_load_4d(sb + kSideOff, &g.mapS, &full_bar[stage], kb * kBK, 0, 0, 0);
+                        }
                         advance_stage(stage, phase);
                     }
+                }
+                if (g.side) {
+                    // one more ring slot per tile: the B2 tile the final rank-r MMA multiplies T with
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sb = smem + stage * kStageBytes + kABytes;
+                    mbar_expect_tx(&full_bar[stage], g.b2_mn ? b_bytes_mn : b_bytes_k);
+                    if (g.b2_mn) {
+                        for (int j = 0; j < b_boxes_mn; ++j)
+                            tma_load_4d(sb + j * 8192, &g.mapB2, &full_bar[stage], n0 + j * 64, 0, 0, 0);
+                    } else {
+                        tma_load_4d(sb, &g.mapB2, &full_bar[stage], 0, n0, 0, 0);
+                    }
+                    advance_stage(stage, phase);
                 }
             }
         }
@@ -178,12 +222,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
-            uint32_t acc_phase = 0;
+            uint32_t acc_phase = 0, t_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int split = (tile / (g.tiles_m * g.tiles_n)) % g.splits;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
+                const uint32_t tmem_side = tmem_d + kSideCol;
+                const uint32_t idesc_side = umma_idesc_bf16(g.side_r16, g.a_mn[0], g.side_mn);
+                const uint32_t s_step = g.side_mn ? (2048u >> 4) : (32u >> 4);
                 uint32_t accumulate = 0;
                 for (int seg = 0; seg < g.num_seg; ++seg) {
                     int kb_begin = 0, kb_end = g.kblocks[seg];
@@ -204,6 +251,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                         const uint64_t adesc = g.a_mn[seg] ? umma_desc(sa, 8192, 1024) : umma_desc(sa, 16, 1024);
                         const uint64_t bdesc = g.b_mn[seg] ? umma_desc(sb, 8192, 1024) : umma_desc(sb, 16, 1024);
                         const int n16 = (kb == kb_last) ? g.ktail16[seg] : 4;
+                        if (g.side) {
+                            const uint64_t sdesc = g.side_mn ? umma_desc(sb + kSideOff, 8192, 1024)
+                                                             : umma_desc(sb + kSideOff, 16, 1024);
+                            for (int k = 0; k < n16; ++k)
+                                umma_bf16(tmem_side, adesc + static_cast<uint64_t>(a_step * k),
+                                          sdesc + static_cast<uint64_t>(s_step * k), idesc_side, accumulate | (k > 0));
+                        }
                         for (int k = 0; k < n16; ++k) {
                             umma_bf16(tmem_d, adesc + static_cast<uint64_t>(a_step * k),
                                       bdesc + static_cast<uint64_t>(b_step * k), idesc, accumulate);
@@ -212,6 +266,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                         umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
                         advance_stage(stage, phase);
                     }
+                }
+                if (g.side) {
+                    umma_commit(&side_full_bar[acc]);     // rank-r accumulator complete -> T-phase of the epilogue warps
+                    mbar_wait(&full_bar[stage], phase);   // B2 tile landed
+                    mbar_wait(t_ready_bar, t_phase);      // T (bf16) staged in smem
+                    t_phase ^= 1;
+                    tc_fence_after();
+                    const uint32_t sb2 = smem_u32(smem + stage * kStageBytes) + kABytes;
+                    const uint64_t tdesc = umma_desc(smem_u32(smem + kTOff), 16, 1024);
+                    const uint64_t b2desc = g.b2_mn ? umma_desc(sb2, 8192, 1024) : umma_desc(sb2, 16, 1024);
+                    const uint32_t idesc2 = umma_idesc_bf16(BN, 0, g.b2_mn);
+                    const uint32_t b2_step = g.b2_mn ? (2048u >> 4) : (32u >> 4);
+                    for (int k = 0; k < (g.side_r16 >> 4); ++k)
+                        umma_bf16(tmem_d, tdesc + static_cast<uint64_t>(2 * k), b2desc + static_cast<uint64_t>(b2_step * k),
+                                  idesc2, 1);
+                    umma_commit(&empty_bar[stage]);
+                    advance_stage(stage, phase);
                 }
                 umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
                 acc ^= 1;
@@ -227,7 +298,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         // coalesced layout and leave as 16-byte (fp32) or 8-byte (bf16) vector stores.
         const int ew = warp - 2;
         const int lane_base = (warp & 3) * 32;    // TMEM lane quarter this warp may read
-        float* stage = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256) + ew * (32 * kEpiLd);
+        float* stage = reinterpret_cast<float*>(smem + kEpiOff) + ew * (32 * kEpiLd);
         const bool row_major = (g.d_sn == 1) && !g.d_atomic;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -243,9 +314,52 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             const long long d_boff = b1 * g.d_sb1 + b0 * g.d_sb0;
             const long long r_boff = b1 * g.r_sb1 + b0 * g.r_sb0;
 
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + static_cast<uint32_t>(acc * kMaxBN);
+            if (g.side) {
+                // ---- T-phase: Tacc (fp32, TMEM) -> alpha, bf16 -> swizzled smem A operand (+ global copy from n_blk 0)
+                mbar_wait(&side_full_bar[acc], acc_phase);
+                tc_fence_after();
+                uint32_t raw[32];
+                tmem_ld32(taddr + kSideCol, raw);
+                tmem_ld_wait();
+                const int row = lane_base + lane;
+                uint8_t* trow = smem + kTOff + row * 128;
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(raw[2 * j]) * g.side_alpha,
+                                                                    __uint_as_float(raw[2 * j + 1]) * g.side_alpha);
+                    packed[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j * 8 < g.side_r16)
+                        *reinterpret_cast<uint4*>(trow + ((j ^ (row & 7)) * 16)) =
+                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+                const int m = m_warp + row - lane_base;
+                if (n_blk == 0 && g.T_out != nullptr && m < g.M) {
+                    __nv_bfloat16* tp = g.T_out + static_cast<long long>(m) * g.t_ld;
+                    const __nv_bfloat16* pv = reinterpret_cast<const __nv_bfloat16*>(packed);
+                    if ((g.side_r & 7) == 0 && (g.t_ld & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j * 8 < g.side_r)
+                                *reinterpret_cast<uint4*>(tp + j * 8) =
+                                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < g.side_r) tp[j] = pv[j];
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_ready_bar);
+            }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + static_cast<uint32_t>(acc * kMaxBN);
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t raw[32];
                 tmem_ld32(taddr + c0, raw);

@@ -87,8 +87,11 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
          d_strides: Optional[Tuple[int, int, int, int]] = None, alpha: float = 1.0,
          bias: Optional[torch.Tensor] = None, bias_rows: int = 0, bias_sb: int = 0,
          residual: Optional[torch.Tensor] = None, r_strides: Optional[Tuple[int, int, int, int]] = None,
-         nb0: int = 1, nb1: int = 1, splits: int = 1, atomic: bool = False, block_n: int = 0) -> torch.Tensor:
-    """out[b1][b0][m, n] = alpha * sum_seg A_seg.B_seg^T (+bias) (+residual).  segs: (A | Conv3x3, B, K)."""
+         nb0: int = 1, nb1: int = 1, splits: int = 1, atomic: bool = False, block_n: int = 0,
+         side: Optional[Tuple[Mat, Mat, int, float, Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    """out[b1][b0][m, n] = alpha * sum_seg A_seg.B_seg^T (+bias) (+residual).  segs: (A | Conv3x3, B, K).
+    side = (S, B2, r, side_alpha, T_out): fused low-rank path  out += (side_alpha * A.S^T).B2^T, T_out <- the inner
+    product (bf16) - see include/b200_lora.h."""
     _chk_dev(out, bias, residual)
     d = GemmDesc()
     d.M, d.N, d.num_seg = M, N, len(segs)
@@ -103,6 +106,11 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
             d.A[i] = a.c()
         d.B[i] = b.c()
     d.nb0, d.nb1, d.splits, d.block_n = nb0, nb1, splits, block_n
+    if side is not None:
+        s_mat, b2_mat, r, s_alpha, t_out = side
+        d.side, d.side_r, d.S, d.B2, d.side_alpha = 1, r, s_mat.c(), b2_mat.c(), s_alpha
+        if t_out is not None:
+            d.T_out, d.t_ld = t_out.data_ptr(), t_out.stride(0)
     d.D = out.data_ptr()
     d.d_fp32 = int(out.dtype == torch.float32)
     assert out.dtype in (torch.float32, BF16)

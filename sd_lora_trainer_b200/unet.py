@@ -151,40 +151,42 @@ class Lin:
             bias_rows: int = 0) -> torch.Tensor:
         M = x.shape[0]
         y = torch.empty(M, self.N, dtype=BF16, device=x.device)
-        segs = [(kmajor(x), kmajor(self.W), self.K)]
-        T = None
+        T, side = None, None
         if self.lora is not None:
+            # ONE launch: the rank-r product T = s.x.A^T accumulates in TMEM beside the main tile, is rounded to bf16
+            # in-kernel and multiplied with B by a final MMA; T also leaves for the dB weight-gradient GEMM.
             lo = self.lora
             T = torch.empty(M, lo.rs, dtype=BF16, device=x.device)
-            ops.gemm(T, M, lo.r, [(kmajor(x), Mat(lo.A(), lo.r, self.K, self.K), self.K)],
-                     d_strides=(lo.rs, 1, 0, 0), alpha=lo.store.scaling)
-            segs.append((Mat(T, M, lo.r, lo.rs), Mat(lo.B(), self.N, lo.r, lo.rs), lo.r))
-        ops.gemm(y, M, self.N, segs, bias=self.b if bias is None else bias, bias_rows=bias_rows,
-                 bias_sb=self.N if bias_rows else 0, residual=residual)
+            side = (Mat(lo.A(), lo.r, self.K, self.K), Mat(lo.B(), self.N, lo.r, lo.rs), lo.r, lo.store.scaling, T)
+        ops.gemm(y, M, self.N, [(kmajor(x), kmajor(self.W), self.K)], bias=self.b if bias is None else bias,
+                 bias_rows=bias_rows, bias_sb=self.N if bias_rows else 0, residual=residual, side=side)
         if save:
             self.x, self.T = x, T
         return y
 
     def bwd(self, dy: torch.Tensor, need_dx: bool = True, accum: Optional[torch.Tensor] = None):
         M = dy.shape[0]
-        x, lo = self.x, self.lora
-        segs = [(kmajor(dy), mnmajor(self.W), self.N)]
+        x, lo, T = self.x, self.lora, self.T
+        self.x = self.T = None
+        dx, U, side = None, None, None
         if lo is not None:
             r, rs = lo.r, lo.rs
             U = torch.empty(M, rs, dtype=BF16, device=dy.device)
-            ops.gemm(U, M, r, [(kmajor(dy), Mat(lo.B(), self.N, r, rs, mn=True), self.N)], d_strides=(rs, 1, 0, 0),
-                     alpha=lo.store.scaling)
+            if need_dx:
+                # dX = dY.W + (s.dY.B).A in ONE launch; U = s.dY.B leaves for the dA weight-gradient GEMM
+                side = (Mat(lo.B(), self.N, r, rs, mn=True), Mat(lo.A(), r, self.K, self.K, mn=True), r, lo.store.scaling, U)
+            else:
+                ops.gemm(U, M, r, [(kmajor(dy), Mat(lo.B(), self.N, r, rs, mn=True), self.N)], d_strides=(rs, 1, 0, 0),
+                         alpha=lo.store.scaling)
+        if need_dx:
+            dx = accum if accum is not None else torch.empty(M, self.K, dtype=BF16, device=dy.device)
+            ops.gemm(dx, M, self.K, [(kmajor(dy), mnmajor(self.W), self.N)], residual=accum, side=side)
+        if lo is not None:
             # dB[N, r] += dY^T . T      dA[r, K] += U^T . X   (both operands MN-major, split-K fp32 atomics)
-            ops.gemm(lo.gB(), self.N, r, [(Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(self.T, M, r, rs, mn=True), M)],
+            ops.gemm(lo.gB(), self.N, r, [(Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(T, M, r, rs, mn=True), M)],
                      d_strides=(rs, 1, 0, 0), splits=_wgrad_splits(self.N, M), atomic=True)
             ops.gemm(lo.gA(), self.K, r, [(Mat(x, M, self.K, x.stride(0), mn=True), Mat(U, M, r, rs, mn=True), M)],
                      d_strides=(1, self.K, 0, 0), splits=_wgrad_splits(self.K, M), atomic=True)
-            segs.append((Mat(U, M, r, rs), Mat(lo.A(), r, self.K, self.K, mn=True), r))
-        self.x = self.T = None
-        if not need_dx:
-            return None
-        dx = accum if accum is not None else torch.empty(M, self.K, dtype=BF16, device=dy.device)
-        ops.gemm(dx, M, self.K, segs, residual=accum)
         return dx
 
 

@@ -40,7 +40,7 @@ def _operand(m: Mat, b0: int, b1: int, mn_extent: int, k_extent: int) -> torch.T
 
 
 def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, bias_sb=0, residual=None,
-         r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0):
+         r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0, side=None):
     if d_strides is None:
         d_strides = (out.stride(0), 1, 0, 0)
     if residual is not None and r_strides is None:
@@ -67,6 +67,13 @@ def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, 
                     Bm = _operand(b, b0, b1, N, k)
                     acc += A @ Bm.t()
             acc = acc * alpha
+            if side is not None:
+                s_mat, b2_mat, r, s_alpha, t_out = side
+                a0, _, k0 = segs[0]
+                T = (_operand(a0, 0, 0, M, k0) @ _operand(s_mat, 0, 0, r, k0).t() * s_alpha).to(BF16)
+                if t_out is not None:
+                    _view(t_out, (M, r), (t_out.stride(0), 1)).copy_(T)
+                acc += T.float() @ _operand(b2_mat, 0, 0, N, r).t()
             if bias is not None:
                 if bias_rows:
                     idx = torch.arange(M) // bias_rows

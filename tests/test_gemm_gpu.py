@@ -196,3 +196,44 @@ def test_conv_lora_fused_and_tapped_b():
                                   (ops.kmajor(T), ops.kmajor(Bm), r)])
     ref = F.conv2d(xn, w.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout) + T.float() @ Bm.float().T
     _close(y, ref, what="conv + lora")
+
+
+@pytest.mark.parametrize("M,N,K,r", [(256, 128, 128, 16), (2048, 1280, 1280, 16), (300, 640, 320, 8), (2048, 640, 2048, 32),
+                                     (154, 1280, 2048, 16), (1000, 200, 136, 4), (8192, 640, 640, 16)])
+def test_fused_side_path_forward(M, N, K, r):
+    """Y = X.W^T + (s.X.A^T).B^T as ONE launch (rank-r product accumulated in TMEM, staged through smem)."""
+    from sd_lora_trainer_b200 import ops
+    rs = (r + 7) // 8 * 8
+    x, w = _rand(M, K), _rand(N, K, seed=1, scale=0.05)
+    A = _rand(r, K, seed=2, scale=0.1)
+    Bp = torch.zeros(N, rs, dtype=BF, device="cuda")
+    Bp[:, :r] = _rand(N, r, seed=3, scale=0.1)
+    bias, res = _rand(N, seed=4), _rand(M, N, seed=5)
+    T = torch.full((M, rs), 7.0, dtype=BF, device="cuda")
+    y = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(y, M, N, [(ops.kmajor(x), ops.kmajor(w), K)], bias=bias, residual=res,
+             side=(ops.Mat(A, r, K, K), ops.Mat(Bp, N, r, rs), r, 0.5, T))
+    Tref = (0.5 * (x.float() @ A.float().T)).to(BF)
+    _close(T[:, :r], Tref, what="T out")
+    ref = x.float() @ w.float().T + Tref.float() @ Bp[:, :r].float().T + bias.float() + res.float()
+    _close(y, ref, what="fused side fwd")
+
+
+@pytest.mark.parametrize("M,N,K,r", [(512, 640, 320, 16), (2048, 1280, 1280, 16), (154, 2048, 1280, 16), (300, 264, 200, 8),
+                                     (2048, 1280, 1280, 32), (333, 128, 96, 4)])
+def test_fused_side_path_dgrad(M, N, K, r):
+    """dX[M, K] = dY.W + (s.dY.B).A as ONE launch; every operand read MN-major from its forward layout."""
+    from sd_lora_trainer_b200 import ops
+    rs = (r + 7) // 8 * 8
+    dy, w = _rand(M, N), _rand(N, K, seed=1, scale=0.05)
+    A = _rand(r, K, seed=2, scale=0.1)
+    Bp = torch.zeros(N, rs, dtype=BF, device="cuda")
+    Bp[:, :r] = _rand(N, r, seed=3, scale=0.1)
+    acc = _rand(M, K, seed=6)
+    U = torch.empty(M, rs, dtype=BF, device="cuda")
+    dx = acc.clone()
+    ops.gemm(dx, M, K, [(ops.kmajor(dy), ops.mnmajor(w), N)], residual=dx,
+             side=(ops.Mat(Bp, N, r, rs, mn=True), ops.Mat(A, r, K, K, mn=True), r, 2.0, U))
+    Uref = (2.0 * (dy.float() @ Bp[:, :r].float())).to(BF)
+    _close(U[:, :r], Uref, what="U out")
+    _close(dx, dy.float() @ w.float() + Uref.float() @ A.float() + acc.float(), what="fused side dgrad")
