@@ -34,10 +34,11 @@ constexpr int kSideOff = 24 * 1024;         // side-path operand tile lives in t
 constexpr int kSideMaxBN = 192;             // => the main B tile may use at most 24 KiB when the side path is on
 constexpr int kSideCol = 192;               // TMEM column (inside an accumulator stage) of the rank-r side accumulator
 constexpr int kTBytes = kBM * 128;          // T/U staged as a 128B-swizzled K-major A operand (only r columns used)
-constexpr int kBarOff = kStages * kStageBytes;
+constexpr int kTOff = kStages * kStageBytes;            // 1024-byte aligned: it is read through a swizzled descriptor
+constexpr int kBarOff = kTOff + kTBytes;
 constexpr int kEpiOff = kBarOff + 256;
-constexpr int kTOff = kEpiOff + kEpiBytes;
-constexpr int kGemmSmemBytes = kTOff + kTBytes;
+constexpr int kGemmSmemBytes = kEpiOff + kEpiBytes;
+static_assert(kTOff % 1024 == 0 && kStageBytes % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct GemmArgs {
     CUtensorMap mapA[2];
