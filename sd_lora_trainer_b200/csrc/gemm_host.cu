@@ -214,6 +214,24 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     g.r_sb0 = d->r_sb0;
     g.r_sb1 = d->r_sb1;
 
+    // ring geometry: every slot holds the A tile, the widest B tile any segment / the B2 tile needs, and the side tile
+    {
+        int b_bytes = 0;
+        for (int s = 0; s < d->num_seg; ++s) {
+            const int bb = g.b_mn[s] ? ((bn + 63) / 64) * 8192 : bn * 128;
+            b_bytes = bb > b_bytes ? bb : b_bytes;
+        }
+        if (g.side) {
+            const int bb = g.b2_mn ? ((bn + 63) / 64) * 8192 : bn * 128;
+            b_bytes = bb > b_bytes ? bb : b_bytes;
+        }
+        b_bytes = (b_bytes + 1023) / 1024 * 1024;
+        const int side_bytes = g.side ? (g.side_mn ? 8192 : (g.side_r16 * 128 + 1023) / 1024 * 1024) : 0;
+        g.side_off = b_bytes;
+        g.stage_bytes = kABytes + b_bytes + side_bytes;
+        g.num_stages = (kStages * kStageBytes) / g.stage_bytes;
+        if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
+    }
     const long long total_tiles = static_cast<long long>(g.tiles_m) * g.tiles_n * g.splits * g.nb0 * g.nb1;
     const int grid = static_cast<int>(total_tiles < kNumSMs ? total_tiles : kNumSMs);
     gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);

@@ -22,7 +22,8 @@ namespace b200 {
 
 constexpr int kBM = 128;            // tile rows (UMMA M)
 constexpr int kBK = 64;             // K elements per pipeline stage (= one 128 B swizzle row of bf16)
-constexpr int kStages = 4;
+constexpr int kStages = 4;            // ring slots at the widest tile (48 KiB each); narrower tiles get more slots
+constexpr int kMaxStages = 12;
 constexpr int kMaxBN = 256;
 constexpr int kABytes = kBM * kBK * 2;      // 16 KiB
 constexpr int kBBytes = kMaxBN * kBK * 2;   // 32 KiB
@@ -30,13 +31,12 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kGemmThreads = 192;
 constexpr int kEpiLd = 36;                 // floats per staged row: 32 + 4 pad (144 B keeps float4 alignment, no bank conflicts)
 constexpr int kEpiBytes = 4 * 32 * kEpiLd * 4;
-constexpr int kSideOff = 24 * 1024;         // side-path operand tile lives in the last 8 KiB of a stage's B region
-constexpr int kSideMaxBN = 192;             // => the main B tile may use at most 24 KiB when the side path is on
+constexpr int kSideMaxBN = 192;             // side accumulator sits at TMEM column 192 of an accumulator stage
 constexpr int kSideCol = 192;               // TMEM column (inside an accumulator stage) of the rank-r side accumulator
 constexpr int kTBytes = kBM * 128;          // T/U staged as a 128B-swizzled K-major A operand (only r columns used)
 constexpr int kTOff = kStages * kStageBytes;            // 1024-byte aligned: it is read through a swizzled descriptor
 constexpr int kBarOff = kTOff + kTBytes;
-constexpr int kEpiOff = kBarOff + 256;
+constexpr int kEpiOff = kBarOff + 512;
 constexpr int kGemmSmemBytes = kEpiOff + kEpiBytes;
 static_assert(kTOff % 1024 == 0 && kStageBytes % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
@@ -73,6 +73,8 @@ struct GemmArgs {
     //   main loop : Tacc[128 x r16] += A_tile . S_tile   (S = LoRA A fwd / LoRA B bwd), in TMEM next to the main tile
     //   T-phase   : epilogue warps scale + round Tacc to bf16, stage it in smem as an A operand, n_blk 0 writes it out
     //   final MMA : main tile += T . B2_tile              (B2 = LoRA B fwd / LoRA A bwd)
+    // smem ring geometry (host-computed): slot = A tile | B tile | side tile; as many slots as fit in 192 KiB
+    int stage_bytes, num_stages, side_off;
     int side;
     int side_mn, b2_mn;       // operand majorness of S and B2
     int side_r16;             // rank rounded up to 16 (16 or 32): MMA N of the side accumulate, K of the final MMA
@@ -83,8 +85,8 @@ struct GemmArgs {
     CUtensorMap mapS, mapB2;
 };
 
-__device__ __forceinline__ void advance_stage(int& stage, uint32_t& phase) {
-    if (++stage == kStages) {
+__device__ __forceinline__ void advance_stage(int& stage, uint32_t& phase, int num_stages) {
+    if (++stage == num_stages) {
         stage = 0;
         phase ^= 1;
     }
@@ -94,8 +96,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     // 128B swizzle atoms must sit on 1024 B boundaries.
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOff);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full_bar = empty_bar + kStages;    // [2]
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;    // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
     uint64_t* side_full_bar = tmem_empty_bar + 2;     // [2]  side accumulator complete (MMA -> epilogue warps)
     uint64_t* t_ready_bar = side_full_bar + 2;        // T staged in smem (epilogue warps -> MMA)
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             tma_prefetch_desc(&g.mapA[s]);
             tma_prefetch_desc(&g.mapB[s]);
         }
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < g.num_stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     const uint32_t tx = kABytes + (g.b_mn[seg] ? b_bytes_mn : b_bytes_k) + side_bytes;
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = smem + stage * kStageBytes;
+                        uint8_t* sa = smem + stage * g.stage_bytes;
                         uint8_t* sb = sa + kABytes;
                         mbar_expect_tx(&full_bar[stage], tx);
                         int bk = kb * kBK, bn = n0;
@@ -195,16 +197,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                             tma_load_4d(sb, &g.mapB[seg], &full_bar[stage], bk, bn, bb0, bb1);
                         }
                         if (g.side) {
-                            if (g.side_mn) tma_load_4d(sb + kSideOff, &g.mapS, &full_bar[stage], 0, kb * kBK, 0, 0);
-                            else tma_load_4d(sb + kSideOff, &g.mapS, &full_bar[stage], kb * kBK, 0, 0, 0);
+                            if (g.side_mn) tma_load_4d(sb + g.side_off, &g.mapS, &full_bar[stage], 0, kb * kBK, 0, 0);
+                            else tma_load_4d(sb + g.side_off, &g.mapS, &full_bar[stage], kb * kBK, 0, 0, 0);
                         }
-                        advance_stage(stage, phase);
+                        advance_stage(stage, phase, g.num_stages);
                     }
                 }
                 if (g.side) {
                     // one more ring slot per tile: the B2 tile the final rank-r MMA multiplies T with
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sb = smem + stage * kStageBytes + kABytes;
+                    uint8_t* sb = smem + stage * g.stage_bytes + kABytes;
                     mbar_expect_tx(&full_bar[stage], g.b2_mn ? b_bytes_mn : b_bytes_k);
                     if (g.b2_mn) {
                         for (int j = 0; j < b_boxes_mn; ++j)
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     } else {
                         tma_load_4d(sb, &g.mapB2, &full_bar[stage], 0, n0, 0, 0);
                     }
-                    advance_stage(stage, phase);
+                    advance_stage(stage, phase, g.num_stages);
                 }
             }
         }
@@ -247,14 +249,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                        const uint32_t sa = smem_u32(smem + stage * g.stage_bytes);
                         const uint32_t sb = sa + kABytes;
                         const uint64_t adesc = g.a_mn[seg] ? umma_desc(sa, 8192, 1024) : umma_desc(sa, 16, 1024);
                         const uint64_t bdesc = g.b_mn[seg] ? umma_desc(sb, 8192, 1024) : umma_desc(sb, 16, 1024);
                         const int n16 = (kb == kb_last) ? g.ktail16[seg] : 4;
                         if (g.side) {
-                            const uint64_t sdesc = g.side_mn ? umma_desc(sb + kSideOff, 8192, 1024)
-                                                             : umma_desc(sb + kSideOff, 16, 1024);
+                            const uint64_t sdesc = g.side_mn ? umma_desc(sb + g.side_off, 8192, 1024)
+                                                             : umma_desc(sb + g.side_off, 16, 1024);
                             for (int k = 0; k < n16; ++k)
                                 umma_bf16(tmem_side, adesc + static_cast<uint64_t>(a_step * k),
                                           sdesc + static_cast<uint64_t>(s_step * k), idesc_side, accumulate | (k > 0));
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                             accumulate = 1;
                         }
                         umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-                        advance_stage(stage, phase);
+                        advance_stage(stage, phase, g.num_stages);
                     }
                 }
                 if (g.side) {
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     mbar_wait(t_ready_bar, t_phase);      // T (bf16) staged in smem
                     t_phase ^= 1;
                     tc_fence_after();
-                    const uint32_t sb2 = smem_u32(smem + stage * kStageBytes) + kABytes;
+                    const uint32_t sb2 = smem_u32(smem + stage * g.stage_bytes) + kABytes;
                     const uint64_t tdesc = umma_desc(smem_u32(smem + kTOff), 16, 1024);
                     const uint64_t b2desc = g.b2_mn ? umma_desc(sb2, 8192, 1024) : umma_desc(sb2, 16, 1024);
                     const uint32_t idesc2 = umma_idesc_bf16(BN, 0, g.b2_mn);
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                         umma_bf16(tmem_d, tdesc + static_cast<uint64_t>(2 * k), b2desc + static_cast<uint64_t>(b2_step * k),
                                   idesc2, 1);
                     umma_commit(&empty_bar[stage]);
-                    advance_stage(stage, phase);
+                    advance_stage(stage, phase, g.num_stages);
                 }
                 umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
                 acc ^= 1;

@@ -41,6 +41,10 @@ def _fp32_twin(cfg, orc):
     for t32, t16 in zip(o32.text_encoders, orc.text_encoders):
         if t32 is not None:
             t32.load_state_dict({k: v.float() for k, v in t16.state_dict().items()})
+    from oracle.losses import DistributionLossOracle
+    for key in list(o32.std_regs):
+        i = int(key.rsplit("_", 1)[1])
+        o32.std_regs[key] = DistributionLossOracle(o32.text_encoders[i].text_model.embeddings.token_embedding.weight.data)
     return o32
 
 
