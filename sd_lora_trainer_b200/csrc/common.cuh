@@ -36,6 +36,28 @@ namespace b200 {
 int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const long long strides[3], const int box[4]);
 
 
+// ---- programmatic dependent launch -------------------------------------------------------------
+// Every kernel of this library is launched with programmaticStreamSerialization and begins with
+// pdl_launch(); pdl_wait(): the next kernel's CTAs may be scheduled (and run their prologue) while this grid drains,
+// and no kernel touches global memory before its predecessor has fully completed and flushed.
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- bf16 helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ float bfr(float x) {   // round-trip through bf16 (torch's per-op rounding)
     return __bfloat162float(__float2bfloat16_rn(x));

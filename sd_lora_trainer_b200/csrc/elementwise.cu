@@ -13,6 +13,8 @@ namespace b200 {
 template <int kPerLane>
 __global__ void softmax_fwd_warp_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int cols,
                                         long long ld_s, long long ld_p) {
+    pdl_launch();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     for (long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; row < rows; row += warps) {
@@ -46,6 +48,8 @@ __global__ void softmax_fwd_warp_kernel(const float* __restrict__ S, bf16* __res
 template <int kPerThread>
 __global__ void softmax_fwd_block_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int cols,
                                          long long ld_s, long long ld_p) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float red[32];
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const float* s = S + row * ld_s;
@@ -77,6 +81,8 @@ __global__ void softmax_fwd_block_kernel(const float* __restrict__ S, bf16* __re
 
 __global__ void softmax_fwd_generic_kernel(const float* __restrict__ S, bf16* __restrict__ P, long long rows, int cols,
                                            long long ld_s, long long ld_p) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float red[32];
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const float* s = S + row * ld_s;
@@ -96,6 +102,8 @@ __global__ void softmax_fwd_generic_kernel(const float* __restrict__ S, bf16* __
 // dS = P * (dP - sum_j P_j dP_j)
 __global__ void softmax_bwd_kernel(const bf16* __restrict__ P, const float* __restrict__ dP, bf16* __restrict__ dS,
                                    long long rows, int cols, long long ld_p, long long ld_dp, int warp_rows) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float red[32];
     const int lane = threadIdx.x & 31;
     if (warp_rows) {
@@ -128,6 +136,8 @@ __global__ void softmax_bwd_kernel(const bf16* __restrict__ P, const float* __re
 // GEGLU / SiLU / add
 // ------------------------------------------------------------------------------------------------
 __global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ y, long long rows, int inner) {
+    pdl_launch();
+    pdl_wait();
     const int I8 = inner >> 3;
     const long long total = rows * I8;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -145,6 +155,8 @@ __global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ 
 
 __global__ void geglu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h, bf16* __restrict__ dh,
                                  long long rows, int inner) {
+    pdl_launch();
+    pdl_wait();
     const int I8 = inner >> 3;
     const long long total = rows * I8;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -166,12 +178,16 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __rest
 }
 
 __global__ void silu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n) {
+    pdl_launch();
+    pdl_wait();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
         y[i] = __float2bfloat16_rn(silu_f(__bfloat162float(x[i])));
 }
 __global__ void silu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx,
                                 long long n) {
+    pdl_launch();
+    pdl_wait();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
         dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * dsilu_f(__bfloat162float(x[i])));
@@ -179,6 +195,8 @@ __global__ void silu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
 
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ c,
                            bf16* __restrict__ y, long long n8, long long n) {
+    pdl_launch();
+    pdl_wait();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         float fa[8], fb[8], o[8];
@@ -208,6 +226,8 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
 // NHWC layout helpers
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C8) {
+    pdl_launch();
+    pdl_wait();
     const long long total = static_cast<long long>(N) * (2 * H) * (2 * W) * C8;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -222,6 +242,8 @@ __global__ void upsample2x_fwd_kernel(const bf16* __restrict__ x, bf16* __restri
 }
 
 __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int C8) {
+    pdl_launch();
+    pdl_wait();
     const long long total = static_cast<long long>(N) * H * W * C8;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -246,6 +268,8 @@ __global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restr
 
 __global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int N, int H, int W, int C8,
                                  int stride, int Ho, int Wo) {
+    pdl_launch();
+    pdl_wait();
     const long long total = static_cast<long long>(N) * Ho * Wo * 9 * C8;
     const uint4 zero = make_uint4(0, 0, 0, 0);
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -267,6 +291,8 @@ __global__ void im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
 // gather form of the transposed im2col: dx[n,h,w,:] = sum over (tap, ho, wo) with ho*stride + kh - 1 == h, ...
 __global__ void col2im3x3_kernel(const bf16* __restrict__ col, bf16* __restrict__ dx, int N, int H, int W, int C8,
                                  int stride, int Ho, int Wo) {
+    pdl_launch();
+    pdl_wait();
     const long long total = static_cast<long long>(N) * H * W * C8;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -298,6 +324,8 @@ __global__ void col2im3x3_kernel(const bf16* __restrict__ col, bf16* __restrict_
 
 // out[b, c] = sum_p x[b, p, c]   (d(time-embedding projection) = per-image column sum of d(conv1 output))
 __global__ void colsum_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long hw, int C) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float part[8][32];
     const int b = blockIdx.y;
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -318,6 +346,8 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, bf16* __restrict__ out
 // U9[p, tap*r + j] = U[p - off(tap), j]
 __global__ void shift_stack9_kernel(const bf16* __restrict__ U, bf16* __restrict__ U9, int N, int H, int W, int r,
                                     int ld_in, int ld_out) {
+    pdl_launch();
+    pdl_wait();
     const long long total = static_cast<long long>(N) * H * W * 9 * r;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -335,6 +365,8 @@ __global__ void shift_stack9_kernel(const bf16* __restrict__ U, bf16* __restrict
 }
 
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __restrict__ out, int n, int dim) {
+    pdl_launch();
+    pdl_wait();
     const int half = dim / 2;
     const int total = n * dim;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -356,15 +388,15 @@ extern "C" int b200_softmax_fwd(const float* S, void* P, int64_t rows, int32_t c
     B200_CHECK_ARG(cols >= 1 && ld_p >= cols && ld_s >= cols, "softmax: bad extents");
     bf16* p = static_cast<bf16*>(P);
     if (ld_p <= 128) {
-        softmax_fwd_warp_kernel<4><<<grid_for(rows * 32, 256), 256, 0, ST>>>(S, p, rows, cols, ld_s, ld_p);
+        launch_pdl(softmax_fwd_warp_kernel<4>, dim3(grid_for(rows * 32, 256)), dim3(256), 0, ST, S, p, rows, cols, ld_s, ld_p);
     } else if (ld_p <= 1024) {
-        softmax_fwd_warp_kernel<32><<<grid_for(rows * 32, 256), 256, 0, ST>>>(S, p, rows, cols, ld_s, ld_p);
+        launch_pdl(softmax_fwd_warp_kernel<32>, dim3(grid_for(rows * 32, 256)), dim3(256), 0, ST, S, p, rows, cols, ld_s, ld_p);
     } else if (ld_p <= 4096) {
-        softmax_fwd_block_kernel<32><<<static_cast<int>(rows < kNumSMs * 16 ? rows : kNumSMs * 16), 128, 0, ST>>>(
-            S, p, rows, cols, ld_s, ld_p);
+        launch_pdl(softmax_fwd_block_kernel<32>, dim3(static_cast<int>(rows < kNumSMs * 16 ? rows : kNumSMs * 16)), dim3(128), 0, ST,
+                   S, p, rows, cols, ld_s, ld_p);
     } else {
-        softmax_fwd_generic_kernel<<<static_cast<int>(rows < kNumSMs * 8 ? rows : kNumSMs * 8), 256, 0, ST>>>(
-            S, p, rows, cols, ld_s, ld_p);
+        launch_pdl(softmax_fwd_generic_kernel, dim3(static_cast<int>(rows < kNumSMs * 8 ? rows : kNumSMs * 8)), dim3(256), 0, ST,
+                   S, p, rows, cols, ld_s, ld_p);
     }
     B200_CHECK_LAUNCH("softmax_fwd");
     return 0;
@@ -375,7 +407,7 @@ extern "C" int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_
     B200_CHECK_ARG(cols >= 1 && ld_p >= cols && ld_dp >= cols, "softmax_bwd: bad extents");
     const int warp_rows = cols <= 512;
     const int blocks = warp_rows ? grid_for(rows * 32, 256) : static_cast<int>(rows < kNumSMs * 16 ? rows : kNumSMs * 16);
-    softmax_bwd_kernel<<<blocks, 256, 0, ST>>>(static_cast<const bf16*>(P), dP, static_cast<bf16*>(dS), rows, cols, ld_p,
+    launch_pdl(softmax_bwd_kernel, dim3(blocks), dim3(256), 0, ST, static_cast<const bf16*>(P), dP, static_cast<bf16*>(dS), rows, cols, ld_p,
                                                ld_dp, warp_rows);
     B200_CHECK_LAUNCH("softmax_bwd");
     return 0;
@@ -383,25 +415,25 @@ extern "C" int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_
 
 extern "C" int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, void* stream) {
     B200_CHECK_ARG(inner % 8 == 0, "geglu: inner %% 8 != 0");
-    geglu_fwd_kernel<<<grid_for(rows * (inner / 8), 256), 256, 0, ST>>>(static_cast<const bf16*>(h),
+    launch_pdl(geglu_fwd_kernel, dim3(grid_for(rows * (inner / 8), 256)), dim3(256), 0, ST, static_cast<const bf16*>(h),
                                                                          static_cast<bf16*>(y), rows, inner);
     B200_CHECK_LAUNCH("geglu_fwd");
     return 0;
 }
 extern "C" int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, void* stream) {
     B200_CHECK_ARG(inner % 8 == 0, "geglu: inner %% 8 != 0");
-    geglu_bwd_kernel<<<grid_for(rows * (inner / 8), 256), 256, 0, ST>>>(
+    launch_pdl(geglu_bwd_kernel, dim3(grid_for(rows * (inner / 8), 256)), dim3(256), 0, ST, 
         static_cast<const bf16*>(dy), static_cast<const bf16*>(h), static_cast<bf16*>(dh), rows, inner);
     B200_CHECK_LAUNCH("geglu_bwd");
     return 0;
 }
 extern "C" int b200_silu_fwd(const void* x, void* y, int64_t n, void* stream) {
-    silu_fwd_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), n);
+    launch_pdl(silu_fwd_kernel, dim3(grid_for(n, 256)), dim3(256), 0, ST, static_cast<const bf16*>(x), static_cast<bf16*>(y), n);
     B200_CHECK_LAUNCH("silu_fwd");
     return 0;
 }
 extern "C" int b200_silu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream) {
-    silu_bwd_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
+    launch_pdl(silu_bwd_kernel, dim3(grid_for(n, 256)), dim3(256), 0, ST, static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
                                                       static_cast<bf16*>(dx), n);
     B200_CHECK_LAUNCH("silu_bwd");
     return 0;
@@ -410,21 +442,21 @@ extern "C" int b200_add(const void* a, const void* b, const void* c, void* y, in
     const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
                            reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
     const long long n8 = aligned ? n / 8 : 0;
-    add_kernel<<<grid_for(n8 > 0 ? n8 : 1, 256), 256, 0, ST>>>(static_cast<const bf16*>(a), static_cast<const bf16*>(b),
+    launch_pdl(add_kernel, dim3(grid_for(n8 > 0 ? n8 : 1, 256)), dim3(256), 0, ST, static_cast<const bf16*>(a), static_cast<const bf16*>(b),
                                                                static_cast<const bf16*>(c), static_cast<bf16*>(y), n8, n);
     B200_CHECK_LAUNCH("add");
     return 0;
 }
 extern "C" int b200_upsample2x_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
     B200_CHECK_ARG(C % 8 == 0, "upsample: C %% 8 != 0");
-    upsample2x_fwd_kernel<<<grid_for(4LL * N * H * W * (C / 8), 256), 256, 0, ST>>>(
+    launch_pdl(upsample2x_fwd_kernel, dim3(grid_for(4LL * N * H * W * (C / 8), 256)), dim3(256), 0, ST, 
         static_cast<const bf16*>(x), static_cast<bf16*>(y), N, H, W, C / 8);
     B200_CHECK_LAUNCH("upsample2x_fwd");
     return 0;
 }
 extern "C" int b200_upsample2x_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {
     B200_CHECK_ARG(C % 8 == 0, "upsample: C %% 8 != 0");
-    upsample2x_bwd_kernel<<<grid_for(1LL * N * H * W * (C / 8), 256), 256, 0, ST>>>(
+    launch_pdl(upsample2x_bwd_kernel, dim3(grid_for(1LL * N * H * W * (C / 8), 256)), dim3(256), 0, ST, 
         static_cast<const bf16*>(dy), static_cast<bf16*>(dx), N, H, W, C / 8);
     B200_CHECK_LAUNCH("upsample2x_bwd");
     return 0;
@@ -433,7 +465,7 @@ extern "C" int b200_im2col3x3(const void* x, void* col, int32_t N, int32_t H, in
                               void* stream) {
     B200_CHECK_ARG(C % 8 == 0 && (stride == 1 || stride == 2), "im2col: unsupported C/stride");
     const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-    im2col3x3_kernel<<<grid_for(9LL * N * Ho * Wo * (C / 8), 256), 256, 0, ST>>>(
+    launch_pdl(im2col3x3_kernel, dim3(grid_for(9LL * N * Ho * Wo * (C / 8), 256)), dim3(256), 0, ST, 
         static_cast<const bf16*>(x), static_cast<bf16*>(col), N, H, W, C / 8, stride, Ho, Wo);
     B200_CHECK_LAUNCH("im2col3x3");
     return 0;
@@ -442,28 +474,28 @@ extern "C" int b200_col2im3x3(const void* col, void* dx, int32_t N, int32_t H, i
                               void* stream) {
     B200_CHECK_ARG(C % 8 == 0 && (stride == 1 || stride == 2), "col2im: unsupported C/stride");
     const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-    col2im3x3_kernel<<<grid_for(1LL * N * H * W * (C / 8), 256), 256, 0, ST>>>(
+    launch_pdl(col2im3x3_kernel, dim3(grid_for(1LL * N * H * W * (C / 8), 256)), dim3(256), 0, ST, 
         static_cast<const bf16*>(col), static_cast<bf16*>(dx), N, H, W, C / 8, stride, Ho, Wo);
     B200_CHECK_LAUNCH("col2im3x3");
     return 0;
 }
 extern "C" int b200_colsum(const void* x, void* out, int32_t batch, int64_t hw, int32_t C, void* stream) {
     dim3 grid((C + 31) / 32, batch);
-    colsum_kernel<<<grid, 256, 0, ST>>>(static_cast<const bf16*>(x), static_cast<bf16*>(out), hw, C);
+    launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, ST, static_cast<const bf16*>(x), static_cast<bf16*>(out), hw, C);
     B200_CHECK_LAUNCH("colsum");
     return 0;
 }
 extern "C" int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, int32_t ld_in,
                                  int32_t ld_out, void* stream) {
     B200_CHECK_ARG(ld_in >= r && ld_out >= 9 * r, "shift_stack9: bad leading dims");
-    shift_stack9_kernel<<<grid_for(9LL * N * H * W * r, 256), 256, 0, ST>>>(
+    launch_pdl(shift_stack9_kernel, dim3(grid_for(9LL * N * H * W * r, 256)), dim3(256), 0, ST, 
         static_cast<const bf16*>(U), static_cast<bf16*>(U9), N, H, W, r, ld_in, ld_out);
     B200_CHECK_LAUNCH("shift_stack9");
     return 0;
 }
 extern "C" int b200_timestep_embedding(const float* t, void* out, int32_t n, int32_t dim, void* stream) {
     B200_CHECK_ARG(dim % 2 == 0, "timestep_embedding: odd dim");
-    timestep_embedding_kernel<<<grid_for(1LL * n * dim, 256), 256, 0, ST>>>(t, static_cast<bf16*>(out), n, dim);
+    launch_pdl(timestep_embedding_kernel, dim3(grid_for(1LL * n * dim, 256)), dim3(256), 0, ST, t, static_cast<bf16*>(out), n, dim);
     B200_CHECK_LAUNCH("timestep_embedding");
     return 0;
 }

@@ -36,7 +36,7 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
     g.o_ld = ld;
     g.scale = scale;
     dim3 grid((L + 127) / 128, H, B);
-    flash_fwd_kernel<<<grid, kFaThreads, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(g);
+    launch_pdl(flash_fwd_kernel, dim3(grid), dim3(kFaThreads), kFwdSmem, static_cast<cudaStream_t>(stream), g);
     B200_CHECK_LAUNCH("flash_fwd");
     return 0;
 }
@@ -55,7 +55,7 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     }
     const long long nq_elems = static_cast<long long>(B) * L * ld;
     cudaMemsetAsync(dq_acc_ws, 0, sizeof(float) * nq_elems, st);
-    flash_delta_kernel<<<grid_for(static_cast<long long>(B) * L * H, 256), 256, 0, st>>>(
+    launch_pdl(flash_delta_kernel, dim3(grid_for(static_cast<long long>(B) * L * H, 256)), dim3(256), 0, st, 
         static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta_ws, B, L, H, ld);
     B200_CHECK_LAUNCH("flash_delta");
     FlashBwdArgs g;
@@ -75,9 +75,9 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     g.ld = ld;
     g.scale = scale;
     dim3 grid((Lk + 127) / 128, H, B);
-    flash_bwd_kernel<<<grid, kBwdThreads, kBwdSmem, st>>>(g);
+    launch_pdl(flash_bwd_kernel, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     B200_CHECK_LAUNCH("flash_bwd");
-    f32_to_bf16_kernel<<<grid_for(nq_elems / 4, 256), 256, 0, st>>>(dq_acc_ws, static_cast<__nv_bfloat16*>(dq), nq_elems / 4);
+    launch_pdl(f32_to_bf16_kernel, dim3(grid_for(nq_elems / 4, 256)), dim3(256), 0, st, dq_acc_ws, static_cast<__nv_bfloat16*>(dq), nq_elems / 4);
     B200_CHECK_LAUNCH("flash_dq_convert");
     return 0;
 }

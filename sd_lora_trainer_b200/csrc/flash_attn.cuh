@@ -14,6 +14,7 @@
 // No [L, L] tensor ever reaches HBM.
 #pragma once
 #include "ptx.cuh"
+#include "common.cuh"
 
 namespace b200 {
 
@@ -95,9 +96,11 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
         tmem_alloc(tmem_ptr, 256);
         tmem_relinquish();
     }
+    pdl_launch();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                                   // nothing above touched global memory
     const uint32_t tmem = *tmem_ptr;
     const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
 
@@ -317,9 +320,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
         tmem_alloc(tmem_ptr, 512);
         tmem_relinquish();
     }
+    pdl_launch();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();
     const uint32_t tmem = *tmem_ptr;
     const uint32_t t_S = tmem, t_dP = tmem + 128, t_dV = tmem + 256, t_dK = tmem + 320, t_dQ = tmem + 384;
 
@@ -482,6 +487,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
 // delta[b, h, l] = sum_d dO * O   (one thread per (row, head), 64-wide dot product)
 __global__ void flash_delta_kernel(const __nv_bfloat16* __restrict__ O, const __nv_bfloat16* __restrict__ dO,
                                    float* __restrict__ delta, int B, int L, int H, long long ld) {
+    pdl_launch();
+    pdl_wait();
     const long long total = static_cast<long long>(B) * L * H;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -508,6 +515,8 @@ __global__ void flash_delta_kernel(const __nv_bfloat16* __restrict__ O, const __
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+    pdl_launch();
+    pdl_wait();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float4 v = reinterpret_cast<const float4*>(x)[i];

@@ -2,6 +2,7 @@
 // at run time, so the library links against cudart only), picks the tile width for whole waves over 148 SMs and
 // launches the persistent tcgen05 kernel.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <cudaTypedefs.h>
 #include "common.cuh"
@@ -231,10 +232,12 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
         g.stage_bytes = kABytes + b_bytes + side_bytes;
         g.num_stages = (kStages * kStageBytes) / g.stage_bytes;
         if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
+        static const int cap = getenv("B200_GEMM_STAGES") ? atoi(getenv("B200_GEMM_STAGES")) : 0;   // tuning probe
+        if (cap > 0 && g.num_stages > cap) g.num_stages = cap;
     }
     const long long total_tiles = static_cast<long long>(g.tiles_m) * g.tiles_n * g.splits * g.nb0 * g.nb1;
     const int grid = static_cast<int>(total_tiles < kNumSMs ? total_tiles : kNumSMs);
-    gemm_tcgen05_kernel<<<grid, kGemmThreads, kGemmSmemBytes, static_cast<cudaStream_t>(stream)>>>(g);
+    launch_pdl(gemm_tcgen05_kernel, dim3(grid), dim3(kGemmThreads), kGemmSmemBytes, static_cast<cudaStream_t>(stream), g);
     B200_CHECK_LAUNCH("gemm_tcgen05");
     return 0;
 }

@@ -17,6 +17,7 @@
 //     skinny LoRA weight-gradient GEMMs, and an epilogue with alpha, (per-image) bias and residual add.
 #pragma once
 #include "ptx.cuh"
+#include "common.cuh"
 
 namespace b200 {
 
@@ -131,9 +132,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         tmem_alloc(tmem_base_ptr, 512);
         tmem_relinquish();
     }
+    pdl_launch();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                                   // barrier init / TMEM alloc above overlap the previous grid's tail
     const uint32_t tmem_base = *tmem_base_ptr;
 
     const int tiles_per_batch = g.tiles_m * g.tiles_n * g.splits;

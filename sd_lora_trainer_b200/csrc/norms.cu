@@ -16,6 +16,8 @@ __global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restr
                                  const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
                                  const float* __restrict__ stats, double* __restrict__ ws, long long hw, int C,
                                  int groups, int rows_per_block) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float gsum[2 * 64];
     const int C8 = C >> 3, cpg = C / groups;
     const int b = blockIdx.y;
@@ -76,6 +78,8 @@ __global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restr
 
 __global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int n, double count,
                                    float eps) {
+    pdl_launch();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double mean = ws[2 * i] / count;
@@ -89,6 +93,8 @@ template <bool kSilu>
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma,
                                 const bf16* __restrict__ beta, const float* __restrict__ stats, bf16* __restrict__ y,
                                 long long hw, int C, int groups, long long total_vec) {
+    pdl_launch();
+    pdl_wait();
     const int C8 = C >> 3, cpg = C / groups;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_vec;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -116,6 +122,8 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
                                     const float* __restrict__ stats, const double* __restrict__ ws,
                                     const bf16* __restrict__ dres, bf16* __restrict__ dx, long long hw, int C,
                                     int groups, long long total_vec) {
+    pdl_launch();
+    pdl_wait();
     const int C8 = C >> 3, cpg = C / groups;
     const float inv_n = 1.f / (static_cast<float>(hw) * cpg);
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total_vec;
@@ -157,6 +165,8 @@ template <bool kBackward, int NV>
 __global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                  const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
                                  float* __restrict__ stats, bf16* __restrict__ out, long long rows, int C, float eps) {
+    pdl_launch();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int C8 = C >> 3;
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -271,20 +281,20 @@ extern "C" int b200_groupnorm_fwd(const void* x, const void* gamma, const void* 
     if (rpb < k * 4) rpb = k * 4;
     splits = (hw + rpb - 1) / rpb;
     dim3 grid(static_cast<unsigned>(splits), batch);
-    gn_reduce_kernel<false, false><<<grid, T, 0, st>>>(static_cast<const bf16*>(x), nullptr, nullptr, nullptr, nullptr,
+    launch_pdl(gn_reduce_kernel<false, false>, dim3(grid), dim3(T), 0, st, static_cast<const bf16*>(x), nullptr, nullptr, nullptr, nullptr,
                                                        ws, hw, C, groups, static_cast<int>(rpb));
     B200_CHECK_LAUNCH("gn_reduce");
-    gn_finalize_kernel<<<(batch * groups + 127) / 128, 128, 0, st>>>(ws, stats, batch * groups,
+    launch_pdl(gn_finalize_kernel, dim3((batch * groups + 127) / 128), dim3(128), 0, st, ws, stats, batch * groups,
                                                                      static_cast<double>(hw) * (C / groups), eps);
     B200_CHECK_LAUNCH("gn_finalize");
     const long long total = static_cast<long long>(batch) * hw * C8;
     const int blocks = grid_for(total, 256);
     if (silu)
-        gn_apply_kernel<true><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(gamma),
+        launch_pdl(gn_apply_kernel<true>, dim3(blocks), dim3(256), 0, st, static_cast<const bf16*>(x), static_cast<const bf16*>(gamma),
                                                       static_cast<const bf16*>(beta), stats, static_cast<bf16*>(y), hw,
                                                       C, groups, total);
     else
-        gn_apply_kernel<false><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(gamma),
+        launch_pdl(gn_apply_kernel<false>, dim3(blocks), dim3(256), 0, st, static_cast<const bf16*>(x), static_cast<const bf16*>(gamma),
                                                        static_cast<const bf16*>(beta), stats, static_cast<bf16*>(y), hw,
                                                        C, groups, total);
     B200_CHECK_LAUNCH("gn_apply");
@@ -307,16 +317,16 @@ extern "C" int b200_groupnorm_bwd(const void* dy, const void* x, const void* gam
     const bf16 *xp = static_cast<const bf16*>(x), *dyp = static_cast<const bf16*>(dy);
     const bf16 *gp = static_cast<const bf16*>(gamma), *bp = static_cast<const bf16*>(beta);
     if (silu)
-        gn_reduce_kernel<true, true><<<grid, T, 0, st>>>(xp, dyp, gp, bp, stats, ws, hw, C, groups, static_cast<int>(rpb));
+        launch_pdl(gn_reduce_kernel<true, true>, dim3(grid), dim3(T), 0, st, xp, dyp, gp, bp, stats, ws, hw, C, groups, static_cast<int>(rpb));
     else
-        gn_reduce_kernel<true, false><<<grid, T, 0, st>>>(xp, dyp, gp, bp, stats, ws, hw, C, groups, static_cast<int>(rpb));
+        launch_pdl(gn_reduce_kernel<true, false>, dim3(grid), dim3(T), 0, st, xp, dyp, gp, bp, stats, ws, hw, C, groups, static_cast<int>(rpb));
     B200_CHECK_LAUNCH("gn_bwd_reduce");
     const long long total = static_cast<long long>(batch) * hw * C8;
     const int blocks = grid_for(total, 256);
     if (silu)
-        gn_bwd_apply_kernel<true><<<blocks, 256, 0, st>>>(dyp, xp, gp, bp, stats, ws, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), hw, C, groups, total);
+        launch_pdl(gn_bwd_apply_kernel<true>, dim3(blocks), dim3(256), 0, st, dyp, xp, gp, bp, stats, ws, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), hw, C, groups, total);
     else
-        gn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(dyp, xp, gp, bp, stats, ws, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), hw, C, groups, total);
+        launch_pdl(gn_bwd_apply_kernel<false>, dim3(blocks), dim3(256), 0, st, dyp, xp, gp, bp, stats, ws, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), hw, C, groups, total);
     B200_CHECK_LAUNCH("gn_bwd_apply");
     return 0;
 }
@@ -327,7 +337,7 @@ extern "C" int b200_layernorm_fwd(const void* x, const void* gamma, const void* 
     const int blocks = grid_for(rows * 32, 256);
     const int nv = (C / 8 + 31) / 32;
 #define LN_FWD(NV)                                                                                              \
-    layernorm_kernel<false, NV><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(                         \
+    launch_pdl(layernorm_kernel<false, NV>, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),                          \
         static_cast<const bf16*>(x), nullptr, static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), stats, \
         static_cast<bf16*>(y), rows, C, eps)
     if (nv <= 2) LN_FWD(2); else if (nv <= 5) LN_FWD(5); else LN_FWD(10);
@@ -342,7 +352,7 @@ extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const void* gam
     const int blocks = grid_for(rows * 32, 256);
     const int nv = (C / 8 + 31) / 32;
 #define LN_BWD(NV)                                                                                              \
-    layernorm_kernel<true, NV><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(                          \
+    launch_pdl(layernorm_kernel<true, NV>, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream),                           \
         static_cast<const bf16*>(x), static_cast<const bf16*>(dy), static_cast<const bf16*>(gamma),             \
         static_cast<const bf16*>(dres),                                                                         \
         const_cast<float*>(stats), static_cast<bf16*>(dx), rows, C, 0.f)

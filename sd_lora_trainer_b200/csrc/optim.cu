@@ -14,6 +14,8 @@ __global__ void noise_prologue_kernel(const float* __restrict__ latent, bf16* __
                                       const float* __restrict__ offset, float offset_scale,
                                       const float* __restrict__ acp, const long long* __restrict__ timesteps,
                                       bf16* __restrict__ noisy_nchw, bf16* __restrict__ noisy_nhwc8, int B, int C, int HW) {
+    pdl_launch();
+    pdl_wait();
     const long long total = static_cast<long long>(B) * C * HW;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -35,6 +37,8 @@ __global__ void noise_prologue_kernel(const float* __restrict__ latent, bf16* __
 // trainer/loss.py:83-106,145-161: w_b = (min(snr_b, gamma) / snr_b) / mean_b(...)   (epsilon prediction)
 __global__ void snr_weights_kernel(const float* __restrict__ acp, const long long* __restrict__ timesteps,
                                    float snr_gamma, float* __restrict__ weights, int B) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float red[32];
     float w = 0.f;
     if (threadIdx.x < B) {
@@ -53,6 +57,8 @@ __global__ void diffusion_loss_kernel(const bf16* __restrict__ pred, long long l
                                       const float* __restrict__ mask, const float* __restrict__ weights,
                                       float loss_scale, float* __restrict__ loss_out, bf16* __restrict__ dpred,
                                       long long ld_dpred, int B, int C, int HW) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float red[32];
     const long long total = static_cast<long long>(B) * HW * C;
     const float inv = 1.f / (static_cast<float>(C) * HW * B);
@@ -75,6 +81,8 @@ __global__ void diffusion_loss_kernel(const bf16* __restrict__ pred, long long l
 }
 
 __global__ void abs_sum_kernel(const bf16* __restrict__ p, long long n, float* __restrict__ out) {
+    pdl_launch();
+    pdl_wait();
     __shared__ float red[32];
     float acc = 0.f;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
@@ -125,6 +133,8 @@ __device__ __forceinline__ void adam_update(bf16* __restrict__ p, float* __restr
 __global__ void adamw_kernel(bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ m, bf16* __restrict__ v,
                              long long n, long long n_first, AdamHyper h, const AdamHyper* __restrict__ h_dev,
                              int zero_grad) {
+    pdl_launch();
+    pdl_wait();
     if (h_dev) h = *h_dev;     // CUDA-graph replay: hyper-parameters live in device memory, refreshed by a memcpy
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -158,7 +168,7 @@ extern "C" int b200_noise_prologue(const float* latent, void* noise, const float
                                    const float* alphas_cumprod, const int64_t* timesteps, void* noisy_nchw,
                                    void* noisy_nhwc8, int32_t B, int32_t C, int32_t HW, void* stream) {
     B200_CHECK_ARG(C <= 8, "noise_prologue: C > 8");
-    noise_prologue_kernel<<<grid_for(1LL * B * C * HW, 256), 256, 0, ST>>>(
+    launch_pdl(noise_prologue_kernel, dim3(grid_for(1LL * B * C * HW, 256)), dim3(256), 0, ST, 
         latent, static_cast<bf16*>(noise), offset, offset_scale, alphas_cumprod,
         reinterpret_cast<const long long*>(timesteps), static_cast<bf16*>(noisy_nchw), static_cast<bf16*>(noisy_nhwc8), B,
         C, HW);
@@ -169,7 +179,7 @@ extern "C" int b200_noise_prologue(const float* latent, void* noise, const float
 extern "C" int b200_snr_weights(const float* alphas_cumprod, const int64_t* timesteps, float snr_gamma, float* weights,
                                 int32_t B, void* stream) {
     B200_CHECK_ARG(B >= 1 && B <= 1024, "snr_weights: B out of range");
-    snr_weights_kernel<<<1, ((B + 31) / 32) * 32, 0, ST>>>(alphas_cumprod, reinterpret_cast<const long long*>(timesteps),
+    launch_pdl(snr_weights_kernel, dim3(1), dim3(((B + 31) / 32) * 32), 0, ST, alphas_cumprod, reinterpret_cast<const long long*>(timesteps),
                                                            snr_gamma, weights, B);
     B200_CHECK_LAUNCH("snr_weights");
     return 0;
@@ -178,7 +188,7 @@ extern "C" int b200_snr_weights(const float* alphas_cumprod, const int64_t* time
 extern "C" int b200_diffusion_loss(const void* pred, int64_t ld_pred, const void* noise, const float* mask,
                                    const float* weights, float loss_scale, float* loss_out, void* dpred,
                                    int64_t ld_dpred, int32_t B, int32_t C, int32_t HW, void* stream) {
-    diffusion_loss_kernel<<<grid_for(1LL * B * C * HW, 256, kNumSMs * 4), 256, 0, ST>>>(
+    launch_pdl(diffusion_loss_kernel, dim3(grid_for(1LL * B * C * HW, 256, kNumSMs * 4)), dim3(256), 0, ST, 
         static_cast<const bf16*>(pred), ld_pred, static_cast<const bf16*>(noise), mask, weights, loss_scale, loss_out,
         static_cast<bf16*>(dpred), ld_dpred, B, C, HW);
     B200_CHECK_LAUNCH("diffusion_loss");
@@ -186,7 +196,7 @@ extern "C" int b200_diffusion_loss(const void* pred, int64_t ld_pred, const void
 }
 
 extern "C" int b200_abs_sum(const void* p, int64_t n, float* out, void* stream) {
-    abs_sum_kernel<<<grid_for(n, 256, kNumSMs * 4), 256, 0, ST>>>(static_cast<const bf16*>(p), n, out);
+    launch_pdl(abs_sum_kernel, dim3(grid_for(n, 256, kNumSMs * 4)), dim3(256), 0, ST, static_cast<const bf16*>(p), n, out);
     B200_CHECK_LAUNCH("abs_sum");
     return 0;
 }
@@ -196,7 +206,7 @@ extern "C" int b200_adamw(void* p, float* grad, void* m, void* v, int64_t n, int
                           double grad_scale, int32_t zero_grad, void* stream) {
     B200_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
     const AdamHyper h = make_hyper(lr, wd, l1_coeff, lr2, wd2, beta1, beta2, eps, step, grad_scale);
-    adamw_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
+    launch_pdl(adamw_kernel, dim3(grid_for(n, 256)), dim3(256), 0, ST, static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
                                                    static_cast<bf16*>(v), n, n_first, h, nullptr, zero_grad);
     B200_CHECK_LAUNCH("adamw");
     return 0;
@@ -216,7 +226,7 @@ extern "C" int b200_adamw_dev(void* p, float* grad, void* m, void* v, int64_t n,
     B200_CHECK_ARG(hyper_dev12 != nullptr, "adamw_dev: null hyper-parameter buffer");
     AdamHyper h;
     memset(&h, 0, sizeof(h));
-    adamw_kernel<<<grid_for(n, 256), 256, 0, ST>>>(static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
+    launch_pdl(adamw_kernel, dim3(grid_for(n, 256)), dim3(256), 0, ST, static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
                                                    static_cast<bf16*>(v), n, n_first, h,
                                                    reinterpret_cast<const AdamHyper*>(hyper_dev12), zero_grad);
     B200_CHECK_LAUNCH("adamw_dev");
