@@ -104,6 +104,10 @@ extern "C" int b200_version(void) { return B200_LORA_ABI_VERSION; }
 extern "C" const char* b200_last_error(void) { return last_error_ref().c_str(); }
 extern "C" long long b200_launch_count(void) { return g_launches.load(); }
 
+static long long* g_gemm_dbg = nullptr;
+// developer probe (not part of the public header): per-CTA globaltimer stamps of the next GEMM launches
+extern "C" void b200_debug_gemm_stamps(long long* dev_buf) { g_gemm_dbg = dev_buf; }
+
 extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     B200_CHECK_ARG(d != nullptr, "gemm: null descriptor");
     B200_CHECK_ARG(d->M >= 1 && d->N >= 1, "gemm: empty problem M=%d N=%d", d->M, d->N);
@@ -115,7 +119,9 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
         if (e != cudaSuccess) return set_error(3, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
@@ -198,6 +204,7 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
         if (int rc = encode_operand(&g.mapB2, d->B2, bn, 1, 1)) return rc;
     }
 
+    g.dbg = g_gemm_dbg;
     g.D = d->D;
     g.d_fp32 = d->d_fp32;
     g.d_atomic = d->d_atomic;
@@ -237,7 +244,16 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     }
     const long long total_tiles = static_cast<long long>(g.tiles_m) * g.tiles_n * g.splits * g.nb0 * g.nb1;
     const int grid = static_cast<int>(total_tiles < kNumSMs ? total_tiles : kNumSMs);
-    launch_pdl(gemm_tcgen05_kernel, dim3(grid), dim3(kGemmThreads), kGemmSmemBytes, static_cast<cudaStream_t>(stream), g);
+    const bool row_major = d->d_sn == 1 && !d->d_atomic;
+    const int esz = d->d_fp32 ? 4 : 2;
+    g.vec_ok = row_major && (reinterpret_cast<uintptr_t>(d->D) % (4 * esz) == 0) && (d->d_sm % 4 == 0) &&
+               (d->d_sb0 % 4 == 0) && (d->d_sb1 % 4 == 0) &&
+               (!d->R || (d->r_sn == 1 && reinterpret_cast<uintptr_t>(d->R) % 8 == 0 && d->r_sm % 4 == 0 &&
+                          d->r_sb0 % 4 == 0 && d->r_sb1 % 4 == 0));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!row_major) launch_pdl(gemm_tcgen05_kernel<2>, dim3(grid), dim3(kGemmThreads), kGemmSmemBytes, st, g);
+    else if (d->d_fp32) launch_pdl(gemm_tcgen05_kernel<1>, dim3(grid), dim3(kGemmThreads), kGemmSmemBytes, st, g);
+    else launch_pdl(gemm_tcgen05_kernel<0>, dim3(grid), dim3(kGemmThreads), kGemmSmemBytes, st, g);
     B200_CHECK_LAUNCH("gemm_tcgen05");
     return 0;
 }

@@ -84,7 +84,17 @@ struct GemmArgs {
     __nv_bfloat16* T_out;     // [M, t_ld] bf16 (batch 0 only; the side path is not batched)
     long long t_ld;
     CUtensorMap mapS, mapB2;
+    int vec_ok;               // epilogue may use 8/16-byte vector accesses (host-checked alignment)
+    long long* dbg;           // developer probe: per-CTA globaltimer stamps [cta][8] (nullptr in production)
 };
+
+__device__ __forceinline__ void dbg_stamp(long long* dbg, int slot) {
+    if (dbg) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        dbg[blockIdx.x * 8 + slot] = t;
+    }
+}
 
 __device__ __forceinline__ void advance_stage(int& stage, uint32_t& phase, int num_stages) {
     if (++stage == num_stages) {
@@ -93,6 +103,8 @@ __device__ __forceinline__ void advance_stage(int& stage, uint32_t& phase, int n
     }
 }
 
+// kEpi: 0 = bf16 row-major output, 1 = fp32 row-major output, 2 = transposed / strided / atomic output
+template <int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmArgs g) {
     // 128B swizzle atoms must sit on 1024 B boundaries.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -106,6 +118,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) dbg_stamp(g.dbg, 0);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < g.num_seg; ++s) {
@@ -137,6 +150,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     __syncthreads();
     tc_fence_after();
     pdl_wait();                                   // barrier init / TMEM alloc above overlap the previous grid's tail
+    if (threadIdx.x == 0) dbg_stamp(g.dbg, 1);
     const uint32_t tmem_base = *tmem_base_ptr;
 
     const int tiles_per_batch = g.tiles_m * g.tiles_n * g.splits;
@@ -203,6 +217,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                             if (g.side_mn) tma_load_4d(sb + g.side_off, &g.mapS, &full_bar[stage], 0, kb * kBK, 0, 0);
                             else tma_load_4d(sb + g.side_off, &g.mapS, &full_bar[stage], kb * kBK, 0, 0, 0);
                         }
+                        if (kb == kb_begin && seg == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 2);
                         advance_stage(stage, phase, g.num_stages);
                     }
                 }
@@ -252,6 +267,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
+                        if (kb == kb_begin && seg == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 3);
                         const uint32_t sa = smem_u32(smem + stage * g.stage_bytes);
                         const uint32_t sb = sa + kABytes;
                         const uint64_t adesc = g.a_mn[seg] ? umma_desc(sa, 8192, 1024) : umma_desc(sa, 16, 1024);
@@ -291,6 +307,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     advance_stage(stage, phase, g.num_stages);
                 }
                 umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
+                if (tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 4);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -305,7 +322,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         const int ew = warp - 2;
         const int lane_base = (warp & 3) * 32;    // TMEM lane quarter this warp may read
         float* stage = reinterpret_cast<float*>(smem + kEpiOff) + ew * (32 * kEpiLd);
-        const bool row_major = (g.d_sn == 1) && !g.d_atomic;
+        // vector stores / residual loads need 8-byte (bf16) or 16-byte (fp32) aligned rows: decided once, warp-uniform
+        const bool vec_ok = g.vec_ok != 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -366,13 +384,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
+            if (warp == 2 && lane == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 5);
+            // Code size matters here: 148 SMs enter this at once and an unrolled, branchy epilogue thrashes the
+            // instruction cache (it cost more than the whole K loop).  Hence: one template instance per output kind,
+            // rolled loops, and a single warp-uniform choice between the vector and the scalar body.
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t raw[32];
                 tmem_ld32(taddr + c0, raw);
                 tmem_ld_wait();
                 if (n0 + c0 >= g.N) continue;          // warp-uniform
                 const int cvalid = min(32, BN - c0);
-                if (row_major) {
+                if (kEpi != 2) {
                     float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiLd);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -381,65 +403,56 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     __syncwarp();
                     const int sub = lane >> 3, col = (lane & 7) * 4;
                     const int n = n0 + c0 + col;
-#pragma unroll
+                    const int nv = min(4, min(g.N - n, cvalid - col));     // columns this lane owns (<= 0: none)
+#pragma unroll 1
                     for (int it = 0; it < 8; ++it) {
                         const int row = it * 4 + sub;
                         const int m = m_warp + row;
-                        if (m >= g.M || col >= cvalid || n >= g.N) continue;
+                        if (m >= g.M || nv <= 0) continue;
                         const float4 q = *reinterpret_cast<const float4*>(stage + row * kEpiLd + col);
                         float v[4] = {q.x * g.alpha, q.y * g.alpha, q.z * g.alpha, q.w * g.alpha};
-                        const int nv = min(4, g.N - n);
                         if (g.bias) {
                             const __nv_bfloat16* bp = g.bias + (g.bias_rows ? (m / g.bias_rows) * g.bias_sb : 0) + n;
 #pragma unroll
                             for (int e = 0; e < 4; ++e)
                                 if (e < nv) v[e] += __bfloat162float(bp[e]);
                         }
-                        if (g.R) {
-                            const __nv_bfloat16* rp = g.R + r_boff + static_cast<long long>(m) * g.r_sm + static_cast<long long>(n) * g.r_sn;
-                            if (nv == 4 && g.r_sn == 1 && ((reinterpret_cast<uintptr_t>(rp) & 7) == 0)) {
-                                const uint2 w2 = *reinterpret_cast<const uint2*>(rp);
+                        const long long doff = d_boff + static_cast<long long>(m) * g.d_sm + n;
+                        if (vec_ok && nv == 4) {
+                            if (g.R) {
+                                const uint2 w2 = *reinterpret_cast<const uint2*>(g.R + r_boff + static_cast<long long>(m) * g.r_sm + n);
                                 const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w2.x);
                                 const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&w2.y);
                                 v[0] += __bfloat162float(h0.x);
                                 v[1] += __bfloat162float(h0.y);
                                 v[2] += __bfloat162float(h1.x);
                                 v[3] += __bfloat162float(h1.y);
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (e < nv) v[e] += __bfloat162float(rp[e * g.r_sn]);
                             }
-                        }
-                        const long long doff = d_boff + static_cast<long long>(m) * g.d_sm + n;
-                        if (g.d_fp32) {
-                            float* dp = reinterpret_cast<float*>(g.D) + doff;
-                            if (nv == 4 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-                                *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+                            if (kEpi == 1) {
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.D) + doff) = make_float4(v[0], v[1], v[2], v[3]);
                             } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (e < nv) dp[e] = v[e];
-                            }
-                        } else {
-                            __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.D) + doff;
-                            if (nv == 4 && ((reinterpret_cast<uintptr_t>(dp) & 7) == 0)) {
                                 const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
                                 const __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2], v[3]);
                                 uint2 w2;
                                 w2.x = *reinterpret_cast<const uint32_t*>(&h0);
                                 w2.y = *reinterpret_cast<const uint32_t*>(&h1);
-                                *reinterpret_cast<uint2*>(dp) = w2;
-                            } else {
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.D) + doff) = w2;
+                            }
+                        } else {
 #pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (e < nv) dp[e] = __float2bfloat16_rn(v[e]);
+                            for (int e = 0; e < 4; ++e) {
+                                if (e < nv) {
+                                    float x = v[e];
+                                    if (g.R) x += __bfloat162float(g.R[r_boff + static_cast<long long>(m) * g.r_sm + static_cast<long long>(n + e) * g.r_sn]);
+                                    if (kEpi == 1) reinterpret_cast<float*>(g.D)[doff + e] = x;
+                                    else reinterpret_cast<__nv_bfloat16*>(g.D)[doff + e] = __float2bfloat16_rn(x);
+                                }
                             }
                         }
                     }
                     __syncwarp();
                 } else {
-                    // transposed (d_sm == 1) or atomic outputs: lane <-> row is already the coalesced direction
+                    // transposed (d_sm == 1), strided or atomic outputs: lane <-> row is already the coalesced direction
                     const int m = m_warp + lane;
                     if (m < g.M) {
                         const __nv_bfloat16* bias_row = g.bias ? g.bias + (g.bias_rows ? (m / g.bias_rows) * g.bias_sb : 0) : nullptr;
@@ -464,6 +477,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             }
             tc_fence_before();
             __syncwarp();
+            if (warp == 2 && lane == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 6);
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -472,6 +486,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
 
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) dbg_stamp(g.dbg, 7);
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
