@@ -205,6 +205,8 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     }
 
     g.dbg = g_gemm_dbg;
+    static const int dbg_mode = getenv("B200_EPI_MODE") ? atoi(getenv("B200_EPI_MODE")) : 0;
+    g.dbg_mode = dbg_mode;
     g.D = d->D;
     g.d_fp32 = d->d_fp32;
     g.d_atomic = d->d_atomic;

@@ -2,7 +2,7 @@
 //
 //   D[b][m, n] = epi( sum_{seg} sum_k A_seg[b][m, k] * B_seg[b][n, k] )        (fp32 accumulate in TMEM)
 //
-// One persistent CTA per SM (6 warps: TMA producer, MMA issuer, 4 epilogue warps), 128 x BN output tiles with BN a
+// One persistent CTA per SM (6 warps: TMA producer warp, MMA issuer, 4 epilogue warps), 128 x BN output tiles with BN a
 // RUNTIME multiple of 16 (<= 256) so the host can size the grid to a whole number of waves, 4-stage smem ring,
 // double-buffered TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -85,6 +85,7 @@ struct GemmArgs {
     long long t_ld;
     CUtensorMap mapS, mapB2;
     int vec_ok;               // epilogue may use 8/16-byte vector accesses (host-checked alignment)
+    int dbg_mode;             // developer probe: 1 = epilogue skips global stores, 2 = skips the smem read-back
     long long* dbg;           // developer probe: per-CTA globaltimer stamps [cta][8] (nullptr in production)
 };
 
@@ -92,7 +93,7 @@ __device__ __forceinline__ void dbg_stamp(long long* dbg, int slot) {
     if (dbg) {
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        dbg[blockIdx.x * 8 + slot] = t;
+        dbg[blockIdx.x * 16 + slot] = t;
     }
 }
 
@@ -161,17 +162,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const uint32_t b_bytes_mn = static_cast<uint32_t>(b_boxes_mn) * 8192u;
 
     if (warp == 0) {
-        // ===================== TMA producer (one elected lane) =====================
-        if (lane == 0) {
+        // ===================== TMA producer warp =====================
+        // Issuing a cp.async.bulk.tensor costs the issuing thread a few hundred cycles, so the boxes of one ring slot
+        // are issued by DIFFERENT lanes in parallel: lane 0 waits for the slot and arms the barrier, then
+        // lane 0/1 -> A box(es), lanes 2..5 -> B box(es), lane 6 -> side tile.
+        {
             int stage = 0;
             uint32_t phase = 0;
+            const bool simple = (g.nb0 * g.nb1 * g.splits) == 1;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int t = tile;
-                const int n_blk = t % g.tiles_n;  t /= g.tiles_n;
-                const int m_blk = t % g.tiles_m;  t /= g.tiles_m;
-                const int split = t % g.splits;   t /= g.splits;
-                const int b0 = t % g.nb0;
-                const int b1 = t / g.nb0;
+                int n_blk, m_blk, split = 0, b0 = 0, b1 = 0;
+                if (simple) {
+                    m_blk = static_cast<int>(static_cast<unsigned>(tile) / static_cast<unsigned>(g.tiles_n));
+                    n_blk = tile - m_blk * g.tiles_n;
+                } else {
+                    int t = tile;
+                    n_blk = t % g.tiles_n;  t /= g.tiles_n;
+                    m_blk = t % g.tiles_m;  t /= g.tiles_m;
+                    split = t % g.splits;   t /= g.splits;
+                    b0 = t % g.nb0;
+                    b1 = t / g.nb0;
+                }
                 const int m0 = m_blk * kBM, n0 = n_blk * BN;
                 int conv_n0 = 0, conv_h0 = 0;
                 if (g.conv) {
@@ -189,48 +200,66 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     const int bb0 = g.b_batched[seg] ? b0 : 0, bb1 = g.b_batched[seg] ? b1 : 0;
                     const uint32_t side_bytes = g.side ? (g.side_mn ? 8192u : static_cast<uint32_t>(g.side_r16) * 128u) : 0u;
                     const uint32_t tx = kABytes + (g.b_mn[seg] ? b_bytes_mn : b_bytes_k) + side_bytes;
+                    const bool conv_seg = g.conv && seg == 0;
+                    const int a_mn = g.a_mn[seg], b_mn = g.b_mn[seg];
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (lane == 0) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            mbar_expect_tx(&full_bar[stage], tx);
+                        }
+                        __syncwarp();
                         uint8_t* sa = smem + stage * g.stage_bytes;
                         uint8_t* sb = sa + kABytes;
-                        mbar_expect_tx(&full_bar[stage], tx);
+                        uint64_t* fb = &full_bar[stage];
                         int bk = kb * kBK, bn = n0;
-                        if (g.conv && seg == 0) {
-                            const int tap = kb / g.conv_cblocks, cb = kb - tap * g.conv_cblocks;
-                            const int kh = tap / 3, kw = tap - kh * 3;
-                            tma_load_4d(sa, &g.mapA[0], &full_bar[stage], cb * kBK, kw - 1, conv_h0 + kh - 1, conv_n0);
+                        int tap = 0, cb = 0;
+                        if (conv_seg) {
+                            tap = kb / g.conv_cblocks;
+                            cb = kb - tap * g.conv_cblocks;
                             bk = tap * g.b_tap_k + cb * kBK;
                             bn = n0 + tap * g.b_tap_n;
-                        } else if (g.a_mn[seg]) {
-                            tma_load_4d(sa, &g.mapA[seg], &full_bar[stage], m0, kb * kBK, ab0, ab1);
-                            tma_load_4d(sa + 8192, &g.mapA[seg], &full_bar[stage], m0 + 64, kb * kBK, ab0, ab1);
-                        } else {
-                            tma_load_4d(sa, &g.mapA[seg], &full_bar[stage], kb * kBK, m0, ab0, ab1);
                         }
-                        if (g.b_mn[seg]) {
-                            for (int j = 0; j < b_boxes_mn; ++j)
-                                tma_load_4d(sb + j * 8192, &g.mapB[seg], &full_bar[stage], bn + j * 64, bk, bb0, bb1);
-                        } else {
-                            tma_load_4d(sb, &g.mapB[seg], &full_bar[stage], bk, bn, bb0, bb1);
+                        if (lane == 0) {
+                            if (conv_seg) {
+                                const int kh = tap / 3, kw = tap - kh * 3;
+                                tma_load_4d(sa, &g.mapA[0], fb, cb * kBK, kw - 1, conv_h0 + kh - 1, conv_n0);
+                            } else if (a_mn) {
+                                tma_load_4d(sa, &g.mapA[seg], fb, m0, kb * kBK, ab0, ab1);
+                            } else {
+                                tma_load_4d(sa, &g.mapA[seg], fb, kb * kBK, m0, ab0, ab1);
+                            }
+                        } else if (lane == 1) {
+                            if (!conv_seg && a_mn) tma_load_4d(sa + 8192, &g.mapA[seg], fb, m0 + 64, kb * kBK, ab0, ab1);
+                        } else if (lane < 6) {
+                            const int jb = lane - 2;
+                            if (b_mn) {
+                                if (jb < b_boxes_mn) tma_load_4d(sb + jb * 8192, &g.mapB[seg], fb, bn + jb * 64, bk, bb0, bb1);
+                            } else if (jb == 0) {
+                                tma_load_4d(sb, &g.mapB[seg], fb, bk, bn, bb0, bb1);
+                            }
+                        } else if (lane == 6 && g.side) {
+                            if (g.side_mn) tma_load_4d(sb + g.side_off, &g.mapS, fb, 0, kb * kBK, 0, 0);
+                            else tma_load_4d(sb + g.side_off, &g.mapS, fb, kb * kBK, 0, 0, 0);
                         }
-                        if (g.side) {
-                            if (g.side_mn) tma_load_4d(sb + g.side_off, &g.mapS, &full_bar[stage], 0, kb * kBK, 0, 0);
-                            else tma_load_4d(sb + g.side_off, &g.mapS, &full_bar[stage], kb * kBK, 0, 0, 0);
-                        }
-                        if (kb == kb_begin && seg == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 2);
+                        if (lane == 0 && kb == kb_begin && seg == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 2);
                         advance_stage(stage, phase, g.num_stages);
                     }
                 }
                 if (g.side) {
                     // one more ring slot per tile: the B2 tile the final rank-r MMA multiplies T with
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (lane == 0) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], g.b2_mn ? b_bytes_mn : b_bytes_k);
+                    }
+                    __syncwarp();
                     uint8_t* sb = smem + stage * g.stage_bytes + kABytes;
-                    mbar_expect_tx(&full_bar[stage], g.b2_mn ? b_bytes_mn : b_bytes_k);
-                    if (g.b2_mn) {
-                        for (int j = 0; j < b_boxes_mn; ++j)
-                            tma_load_4d(sb + j * 8192, &g.mapB2, &full_bar[stage], n0 + j * 64, 0, 0, 0);
-                    } else {
-                        tma_load_4d(sb, &g.mapB2, &full_bar[stage], 0, n0, 0, 0);
+                    if (lane >= 2 && lane < 6) {
+                        const int jb = lane - 2;
+                        if (g.b2_mn) {
+                            if (jb < b_boxes_mn) tma_load_4d(sb + jb * 8192, &g.mapB2, &full_bar[stage], n0 + jb * 64, 0, 0, 0);
+                        } else if (jb == 0) {
+                            tma_load_4d(sb, &g.mapB2, &full_bar[stage], 0, n0, 0, 0);
+                        }
                     }
                     advance_stage(stage, phase, g.num_stages);
                 }
@@ -238,14 +267,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer (one elected lane) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer warp =====================
+        // The whole warp runs the loop in lock-step (barrier waits, descriptor arithmetic stay warp-uniform and live in
+        // uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.
+        {
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0, t_phase = 0;
+            const uint32_t smem_base = smem_u32(smem);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int split = (tile / (g.tiles_m * g.tiles_n)) % g.splits;
+                const int split = (g.splits > 1) ? (tile / (g.tiles_m * g.tiles_n)) % g.splits : 0;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
@@ -264,50 +296,59 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     // per-16-K-step advance of the descriptor start address (encoded >> 4)
                     const uint32_t a_step = g.a_mn[seg] ? (2048u >> 4) : (32u >> 4);
                     const uint32_t b_step = g.b_mn[seg] ? (2048u >> 4) : (32u >> 4);
+                    const uint32_t a_lbo = g.a_mn[seg] ? 8192u : 16u, b_lbo = g.b_mn[seg] ? 8192u : 16u;
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        if (kb == kb_begin && seg == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 3);
-                        const uint32_t sa = smem_u32(smem + stage * g.stage_bytes);
+                        const uint32_t sa = smem_base + static_cast<uint32_t>(stage * g.stage_bytes);
                         const uint32_t sb = sa + kABytes;
-                        const uint64_t adesc = g.a_mn[seg] ? umma_desc(sa, 8192, 1024) : umma_desc(sa, 16, 1024);
-                        const uint64_t bdesc = g.b_mn[seg] ? umma_desc(sb, 8192, 1024) : umma_desc(sb, 16, 1024);
+                        const uint64_t adesc = umma_desc(sa, a_lbo, 1024);
+                        const uint64_t bdesc = umma_desc(sb, b_lbo, 1024);
                         const int n16 = (kb == kb_last) ? g.ktail16[seg] : 4;
-                        if (g.side) {
-                            const uint64_t sdesc = g.side_mn ? umma_desc(sb + g.side_off, 8192, 1024)
-                                                             : umma_desc(sb + g.side_off, 16, 1024);
+                        if (elect_one()) {
+                            if (kb == kb_begin && seg == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 3);
+                            if (g.side) {
+                                const uint64_t sdesc = umma_desc(sb + g.side_off, g.side_mn ? 8192u : 16u, 1024);
+                                for (int k = 0; k < n16; ++k)
+                                    umma_bf16(tmem_side, adesc + static_cast<uint64_t>(a_step * k),
+                                              sdesc + static_cast<uint64_t>(s_step * k), idesc_side, accumulate | (k > 0));
+                            }
                             for (int k = 0; k < n16; ++k)
-                                umma_bf16(tmem_side, adesc + static_cast<uint64_t>(a_step * k),
-                                          sdesc + static_cast<uint64_t>(s_step * k), idesc_side, accumulate | (k > 0));
+                                umma_bf16(tmem_d, adesc + static_cast<uint64_t>(a_step * k),
+                                          bdesc + static_cast<uint64_t>(b_step * k), idesc, accumulate | (k > 0));
+                            umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
                         }
-                        for (int k = 0; k < n16; ++k) {
-                            umma_bf16(tmem_d, adesc + static_cast<uint64_t>(a_step * k),
-                                      bdesc + static_cast<uint64_t>(b_step * k), idesc, accumulate);
-                            accumulate = 1;
-                        }
-                        umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+                        __syncwarp();
+                        accumulate = 1;
                         advance_stage(stage, phase, g.num_stages);
                     }
                 }
                 if (g.side) {
-                    umma_commit(&side_full_bar[acc]);     // rank-r accumulator complete -> T-phase of the epilogue warps
+                    if (elect_one()) umma_commit(&side_full_bar[acc]);   // rank-r accumulator complete -> T-phase
+                    __syncwarp();
                     mbar_wait(&full_bar[stage], phase);   // B2 tile landed
                     mbar_wait(t_ready_bar, t_phase);      // T (bf16) staged in smem
                     t_phase ^= 1;
                     tc_fence_after();
-                    const uint32_t sb2 = smem_u32(smem + stage * g.stage_bytes) + kABytes;
-                    const uint64_t tdesc = umma_desc(smem_u32(smem + kTOff), 16, 1024);
-                    const uint64_t b2desc = g.b2_mn ? umma_desc(sb2, 8192, 1024) : umma_desc(sb2, 16, 1024);
+                    const uint32_t sb2 = smem_base + static_cast<uint32_t>(stage * g.stage_bytes) + kABytes;
+                    const uint64_t tdesc = umma_desc(smem_base + kTOff, 16, 1024);
+                    const uint64_t b2desc = umma_desc(sb2, g.b2_mn ? 8192u : 16u, 1024);
                     const uint32_t idesc2 = umma_idesc_bf16(BN, 0, g.b2_mn);
                     const uint32_t b2_step = g.b2_mn ? (2048u >> 4) : (32u >> 4);
-                    for (int k = 0; k < (g.side_r16 >> 4); ++k)
-                        umma_bf16(tmem_d, tdesc + static_cast<uint64_t>(2 * k), b2desc + static_cast<uint64_t>(b2_step * k),
-                                  idesc2, 1);
-                    umma_commit(&empty_bar[stage]);
+                    if (elect_one()) {
+                        for (int k = 0; k < (g.side_r16 >> 4); ++k)
+                            umma_bf16(tmem_d, tdesc + static_cast<uint64_t>(2 * k), b2desc + static_cast<uint64_t>(b2_step * k),
+                                      idesc2, 1);
+                        umma_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
                     advance_stage(stage, phase, g.num_stages);
                 }
-                umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
-                if (tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 4);
+                if (elect_one()) {
+                    umma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
+                    if (tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 4);
+                }
+                __syncwarp();
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -392,6 +433,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 uint32_t raw[32];
                 tmem_ld32(taddr + c0, raw);
                 tmem_ld_wait();
+                const bool dbg0 = warp == 2 && lane == 0 && tile == static_cast<int>(blockIdx.x) && c0 == 0;
+                if (dbg0) dbg_stamp(g.dbg, 8);
                 if (n0 + c0 >= g.N) continue;          // warp-uniform
                 const int cvalid = min(32, BN - c0);
                 if (kEpi != 2) {
@@ -401,56 +444,113 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                         srow[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]),
                                               __uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3]));
                     __syncwarp();
+                    if (dbg0) dbg_stamp(g.dbg, 9);
                     const int sub = lane >> 3, col = (lane & 7) * 4;
                     const int n = n0 + c0 + col;
                     const int nv = min(4, min(g.N - n, cvalid - col));     // columns this lane owns (<= 0: none)
-#pragma unroll 1
-                    for (int it = 0; it < 8; ++it) {
-                        const int row = it * 4 + sub;
-                        const int m = m_warp + row;
-                        if (m >= g.M || nv <= 0) continue;
-                        const float4 q = *reinterpret_cast<const float4*>(stage + row * kEpiLd + col);
-                        float v[4] = {q.x * g.alpha, q.y * g.alpha, q.z * g.alpha, q.w * g.alpha};
-                        if (g.bias) {
-                            const __nv_bfloat16* bp = g.bias + (g.bias_rows ? (m / g.bias_rows) * g.bias_sb : 0) + n;
+                    // One warp per scheduler runs this loop, so its latency is the epilogue's latency: keep the
+                    // per-iteration dependency chain short (running pointers, no 64-bit multiplies) and let four
+                    // iterations overlap.
+                    const float alpha = g.alpha;
+                    const int m_first = m_warp + sub;
+                    const float* sp = stage + sub * kEpiLd + col;
+                    const long long d_step = 4 * g.d_sm, r_step = 4 * g.r_sm;
+                    long long doff = d_boff + static_cast<long long>(m_first) * g.d_sm + n;
+                    const __nv_bfloat16* rp = g.R ? g.R + r_boff + static_cast<long long>(m_first) * g.r_sm + static_cast<long long>(n) * g.r_sn : nullptr;
+                    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                    const bool bias_per_row = g.bias != nullptr && g.bias_rows != 0;
+                    if (g.bias != nullptr && !bias_per_row && nv > 0) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (e < nv) v[e] += __bfloat162float(bp[e]);
+                        for (int e = 0; e < 4; ++e)
+                            if (e < nv) bv[e] = __bfloat162float(g.bias[n + e]);
+                    }
+                    // warp-uniform fast path: interior tile (all 32 rows and all 32 columns valid), vector accesses,
+                    // no per-row bias.  ~12 instructions per 4 outputs, fully unrolled so the eight rows overlap.
+                    const bool interior = vec_ok && !bias_per_row && (m_warp + 32 <= g.M) && (cvalid == 32) &&
+                                          (n0 + c0 + 32 <= g.N);
+                    if (interior) {
+                        float4 q[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) q[it] = *reinterpret_cast<const float4*>(sp + it * 4 * kEpiLd);
+                        uint2 rr[8];
+                        if (rp) {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) rr[it] = *reinterpret_cast<const uint2*>(rp + it * r_step);
                         }
-                        const long long doff = d_boff + static_cast<long long>(m) * g.d_sm + n;
-                        if (vec_ok && nv == 4) {
-                            if (g.R) {
-                                const uint2 w2 = *reinterpret_cast<const uint2*>(g.R + r_boff + static_cast<long long>(m) * g.r_sm + n);
-                                const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&w2.x);
-                                const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&w2.y);
-                                v[0] += __bfloat162float(h0.x);
-                                v[1] += __bfloat162float(h0.y);
-                                v[2] += __bfloat162float(h1.x);
-                                v[3] += __bfloat162float(h1.y);
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            float v0 = fmaf(q[it].x, alpha, bv[0]), v1 = fmaf(q[it].y, alpha, bv[1]);
+                            float v2 = fmaf(q[it].z, alpha, bv[2]), v3 = fmaf(q[it].w, alpha, bv[3]);
+                            if (rp) {
+                                v0 += __uint_as_float(rr[it].x << 16);
+                                v1 += __uint_as_float(rr[it].x & 0xffff0000u);
+                                v2 += __uint_as_float(rr[it].y << 16);
+                                v3 += __uint_as_float(rr[it].y & 0xffff0000u);
                             }
                             if (kEpi == 1) {
-                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.D) + doff) = make_float4(v[0], v[1], v[2], v[3]);
+                                *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.D) + doff + it * d_step) = make_float4(v0, v1, v2, v3);
                             } else {
-                                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
-                                const __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2], v[3]);
+                                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1);
+                                const __nv_bfloat162 h1 = __floats2bfloat162_rn(v2, v3);
                                 uint2 w2;
                                 w2.x = *reinterpret_cast<const uint32_t*>(&h0);
                                 w2.y = *reinterpret_cast<const uint32_t*>(&h1);
-                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.D) + doff) = w2;
+                                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.D) + doff + it * d_step) = w2;
                             }
-                        } else {
+                        }
+                    } else if (vec_ok && nv == 4) {
+#pragma unroll 1
+                        for (int it = 0; it < 8; ++it) {
+                            const int m = m_first + it * 4;
+                            if (m < g.M) {
+                                const float4 q = *reinterpret_cast<const float4*>(sp + it * 4 * kEpiLd);
+                                float v0 = q.x * alpha + bv[0], v1 = q.y * alpha + bv[1], v2 = q.z * alpha + bv[2], v3 = q.w * alpha + bv[3];
+                                if (bias_per_row) {
+                                    const __nv_bfloat16* bp = g.bias + (m / g.bias_rows) * g.bias_sb + n;
+                                    v0 += __bfloat162float(bp[0]);
+                                    v1 += __bfloat162float(bp[1]);
+                                    v2 += __bfloat162float(bp[2]);
+                                    v3 += __bfloat162float(bp[3]);
+                                }
+                                if (rp) {
+                                    const uint2 w2 = *reinterpret_cast<const uint2*>(rp + it * r_step);
+                                    v0 += __uint_as_float(w2.x << 16);
+                                    v1 += __uint_as_float(w2.x & 0xffff0000u);
+                                    v2 += __uint_as_float(w2.y << 16);
+                                    v3 += __uint_as_float(w2.y & 0xffff0000u);
+                                }
+                                if (kEpi == 1) {
+                                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(g.D) + doff + it * d_step) = make_float4(v0, v1, v2, v3);
+                                } else {
+                                    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1);
+                                    const __nv_bfloat162 h1 = __floats2bfloat162_rn(v2, v3);
+                                    uint2 w2;
+                                    w2.x = *reinterpret_cast<const uint32_t*>(&h0);
+                                    w2.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.D) + doff + it * d_step) = w2;
+                                }
+                            }
+                        }
+                    } else if (nv > 0) {
+#pragma unroll 1
+                        for (int it = 0; it < 8; ++it) {
+                            const int m = m_first + it * 4;
+                            if (m >= g.M) break;
+                            const float* q = sp + it * 4 * kEpiLd;
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 if (e < nv) {
-                                    float x = v[e];
-                                    if (g.R) x += __bfloat162float(g.R[r_boff + static_cast<long long>(m) * g.r_sm + static_cast<long long>(n + e) * g.r_sn]);
-                                    if (kEpi == 1) reinterpret_cast<float*>(g.D)[doff + e] = x;
-                                    else reinterpret_cast<__nv_bfloat16*>(g.D)[doff + e] = __float2bfloat16_rn(x);
+                                    float x = q[e] * alpha + bv[e];
+                                    if (bias_per_row) x += __bfloat162float(g.bias[(m / g.bias_rows) * g.bias_sb + n + e]);
+                                    if (rp) x += __bfloat162float(rp[it * r_step + e * g.r_sn]);
+                                    if (kEpi == 1) reinterpret_cast<float*>(g.D)[doff + it * d_step + e] = x;
+                                    else reinterpret_cast<__nv_bfloat16*>(g.D)[doff + it * d_step + e] = __float2bfloat16_rn(x);
                                 }
                             }
                         }
                     }
                     __syncwarp();
+                    if (dbg0) dbg_stamp(g.dbg, 10);
                 } else {
                     // transposed (d_sm == 1), strided or atomic outputs: lane <-> row is already the coalesced direction
                     const int m = m_warp + lane;
