@@ -313,9 +313,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                                     umma_bf16(tmem_side, adesc + static_cast<uint64_t>(a_step * k),
                                               sdesc + static_cast<uint64_t>(s_step * k), idesc_side, accumulate | (k > 0));
                             }
-                            for (int k = 0; k < n16; ++k)
-                                umma_bf16(tmem_d, adesc + static_cast<uint64_t>(a_step * k),
-                                          bdesc + static_cast<uint64_t>(b_step * k), idesc, accumulate | (k > 0));
+                            if (g.dbg_mode == 3 && !g.b_mn[seg] && (BN % 32) == 0) {
+                                // experiment: two independent accumulation chains (N halves) interleaved
+                                const uint32_t idesc_h = umma_idesc_bf16(BN / 2, g.a_mn[seg], 0);
+                                const uint64_t bdesc_h = umma_desc(sb + static_cast<uint32_t>(BN / 2) * 128u, 16, 1024);
+                                for (int k = 0; k < n16; ++k) {
+                                    umma_bf16(tmem_d, adesc + static_cast<uint64_t>(a_step * k),
+                                              bdesc + static_cast<uint64_t>(b_step * k), idesc_h, accumulate | (k > 0));
+                                    umma_bf16(tmem_d + BN / 2, adesc + static_cast<uint64_t>(a_step * k),
+                                              bdesc_h + static_cast<uint64_t>(b_step * k), idesc_h, accumulate | (k > 0));
+                                }
+                            } else {
+                                for (int k = 0; k < n16; ++k)
+                                    umma_bf16(tmem_d, adesc + static_cast<uint64_t>(a_step * k),
+                                              bdesc + static_cast<uint64_t>(b_step * k), idesc, accumulate | (k > 0));
+                            }
                             umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
                         }
                         __syncwarp();

@@ -153,13 +153,14 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H:
     return o, lse
 
 
-def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale: float):
-    """Returns (dq [B*L, C], dk [B*Lk, C], dv [B*Lk, C]) bf16."""
+def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale: float, dk=None, dv=None):
+    """Returns (dq [B*L, C], dk [B*Lk, C], dv [B*Lk, C]) bf16; dk / dv may be caller-provided contiguous buffers."""
     C_ = H * 64
     dev = q.device
     dq = torch.empty(B * L, C_, dtype=BF16, device=dev)
-    dk = torch.empty(B * Lk, C_, dtype=BF16, device=dev)
-    dv = torch.empty(B * Lk, C_, dtype=BF16, device=dev)
+    dk = torch.empty(B * Lk, C_, dtype=BF16, device=dev) if dk is None else dk
+    dv = torch.empty(B * Lk, C_, dtype=BF16, device=dev) if dv is None else dv
+    assert dk.is_contiguous() and dv.is_contiguous()
     delta = torch.empty(B * H * L, dtype=torch.float32, device=dev)
     dq_acc = torch.empty(B * L * C_, dtype=torch.float32, device=dev)
     check(_lib.load().b200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),

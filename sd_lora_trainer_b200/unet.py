@@ -77,10 +77,13 @@ class LoraStore:
         self.device = device
         self.scaling = scaling
         self.slots: List[LoraSlot] = []
+        self.by_name: Dict[str, LoraSlot] = {}
         self.total = 0
         self.params = self.grads = self.m = self.v = None
 
     def add(self, name: str, kind: str, r: int, fan_in: int, fan_out: int) -> LoraSlot:
+        if name in self.by_name:                       # pre-allocated (contiguous batched groups)
+            return self.by_name[name]
         s = LoraSlot(name, kind, r, fan_in, fan_out)
         s.offA = self.total
         self.total += _r8(s.a_rows * fan_in)
@@ -88,6 +91,7 @@ class LoraStore:
         self.total += _r8(fan_out * s.rs)
         s.store = self
         self.slots.append(s)
+        self.by_name[name] = s
         return s
 
     def finalize(self, extra: int = 0):
@@ -325,12 +329,18 @@ class Attn:
         self.capture = False
         self.scores = None
         self.sv = None
+        self.kv_batch: Optional["CrossKVBatch"] = None     # set for cross-attention layers whose K/V are batched
+        self.kv_index = -1
 
     def fwd(self, x, ctx, B: int, L: int, Lk: int, residual):
         C = self.to_q.N
         H, d = self.h, C // self.h
         src = ctx if self.cross else x
-        q, k, v = self.to_q.fwd(x), self.to_k.fwd(src), self.to_v.fwd(src)
+        q = self.to_q.fwd(x)
+        if self.kv_batch is not None:
+            k, v = self.kv_batch.kv(self.kv_index)
+        else:
+            k, v = self.to_k.fwd(src), self.to_v.fwd(src)
         scale = d ** -0.5
         Lp = _r8(Lk)
         dev = x.device
@@ -370,12 +380,15 @@ class Attn:
         Lp = _r8(Lk)
         dev = dy.device
         dO = self.to_out.bwd(dy)
+        dK_out = dV_out = None
+        if self.kv_batch is not None:
+            dK_out, dV_out = self.kv_batch.dkv(self.kv_index)
         if d == 64:
-            dQ, dK, dV = ops.flash_attn_bwd(q, k, v, O, dO, lse, B, H, L, Lk, scale)
+            dQ, dK, dV = ops.flash_attn_bwd(q, k, v, O, dO, lse, B, H, L, Lk, scale, dk=dK_out, dv=dV_out)
         else:
             sS = (Lp, 1, L * Lp, H * L * Lp)
             # dV = P^T dO
-            dV = torch.empty(B * Lk, C, dtype=BF16, device=dev)
+            dV = torch.empty(B * Lk, C, dtype=BF16, device=dev) if dV_out is None else dV_out
             ops.gemm(dV, Lk, d, [(Mat(P, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
                                   Mat(dO, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
                      d_strides=(C, 1, d, Lk * C), nb0=H, nb1=B)
@@ -391,7 +404,7 @@ class Attn:
             ops.gemm(dQ, L, d, [(Mat(dS, L, Lk, Lp, sb0=L * Lp, sb1=H * L * Lp, batched=True),
                                  Mat(k, Lk, d, C, mn=True, sb0=d, sb1=Lk * C, batched=True), Lk)],
                      d_strides=(C, 1, d, L * C), alpha=scale, nb0=H, nb1=B)
-            dK = torch.empty(B * Lk, C, dtype=BF16, device=dev)
+            dK = torch.empty(B * Lk, C, dtype=BF16, device=dev) if dK_out is None else dK_out
             ops.gemm(dK, Lk, d, [(Mat(dS, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
                                   Mat(q, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
                      d_strides=(C, 1, d, Lk * C), alpha=scale, nb0=H, nb1=B)
@@ -406,13 +419,84 @@ class Attn:
                      d_strides=(C, 1, 0, Lk * C), alpha=scale, residual=dK, r_strides=(C, 1, 0, Lk * C), nb0=1, nb1=B)
         self.scores = None
         dx = self.to_q.bwd(dQ)
-        if self.cross:
+        if self.kv_batch is not None:
+            pass                                       # dK / dV already sit in the group's buffer; handled at the end
+        elif self.cross:
             self.to_k.bwd(dK, accum=d_ctx_accum)
             self.to_v.bwd(dV, accum=d_ctx_accum)
         else:
             self.to_k.bwd(dK, accum=dx)
             self.to_v.bwd(dV, accum=dx)
         return dx
+
+
+class CrossKVBatch:
+    """All cross-attention to_k / to_v projections of one channel width share the same input (the prompt embedding),
+    so they run as ONE batched GEMM pair up front instead of 2 launches per layer, and their backward
+    (dX, dA, dB of every layer) as four batched GEMMs at the end.  Frozen weights are stacked once; the LoRA slots of
+    the group are allocated contiguously so A / B / their gradients are strided batches of the flat buffers."""
+
+    def __init__(self, store: LoraStore, names: List[str], W_all: torch.Tensor, rank: int):
+        self.store, self.names, self.W_all, self.r = store, names, W_all, rank
+        self.n, self.C, self.Kc = W_all.shape
+        self.slots = [store.by_name[n] for n in names] if rank > 0 else []
+        if self.slots:
+            self.rs = self.slots[0].rs
+            self.stride = self.slots[1].offA - self.slots[0].offA if len(self.slots) > 1 else 0
+            for a, b in zip(self.slots[:-1], self.slots[1:]):
+                assert b.offA - a.offA == self.stride and b.offB - a.offB == self.stride
+        self.sv = None
+
+    def _ab(self, buf):
+        s0 = self.slots[0]
+        return buf[s0.offA:], buf[s0.offB:]
+
+    def fwd(self, ctx2: torch.Tensor):
+        M, n, C, Kc = ctx2.shape[0], self.n, self.C, self.Kc
+        dev = ctx2.device
+        KV = torch.empty(n, M, C, dtype=BF16, device=dev)
+        segs = [(kmajor(ctx2), Mat(self.W_all, C, Kc, Kc, sb0=C * Kc, batched=True), Kc)]
+        T = None
+        if self.slots:
+            r, rs = self.r, self.rs
+            A_all, B_all = self._ab(self.store.params)
+            T = torch.empty(n, M, rs, dtype=BF16, device=dev)
+            ops.gemm(T, M, r, [(kmajor(ctx2), Mat(A_all, r, Kc, Kc, sb0=self.stride, batched=True), Kc)],
+                     d_strides=(rs, 1, M * rs, 0), alpha=self.store.scaling, nb0=n)
+            segs.append((Mat(T, M, r, rs, sb0=M * rs, batched=True), Mat(B_all, C, r, rs, sb0=self.stride, batched=True), r))
+        ops.gemm(KV, M, C, segs, d_strides=(C, 1, M * C, 0), nb0=n)
+        self.sv = (ctx2, T, KV, torch.empty(n, M, C, dtype=BF16, device=dev))
+        return KV
+
+    def kv(self, i: int):
+        return self.sv[2][2 * i], self.sv[2][2 * i + 1]
+
+    def dkv(self, i: int):
+        return self.sv[3][2 * i], self.sv[3][2 * i + 1]
+
+    def bwd(self, d_ctx: torch.Tensor):
+        ctx2, T, _, dKV = self.sv
+        self.sv = None
+        M, n, C, Kc = ctx2.shape[0], self.n, self.C, self.Kc
+        dev = ctx2.device
+        dkv_k = Mat(dKV, M, C, C, sb0=M * C, batched=True)
+        segs = [(dkv_k, Mat(self.W_all, C, Kc, Kc, mn=True, sb0=C * Kc, batched=True), C)]
+        if self.slots:
+            r, rs = self.r, self.rs
+            A_all, B_all = self._ab(self.store.params)
+            gA_all, gB_all = self._ab(self.store.grads)
+            U = torch.empty(n, M, rs, dtype=BF16, device=dev)
+            ops.gemm(U, M, r, [(dkv_k, Mat(B_all, C, r, rs, mn=True, sb0=self.stride, batched=True), C)],
+                     d_strides=(rs, 1, M * rs, 0), alpha=self.store.scaling, nb0=n)
+            ops.gemm(gB_all, C, r, [(Mat(dKV, M, C, C, mn=True, sb0=M * C, batched=True),
+                                     Mat(T, M, r, rs, mn=True, sb0=M * rs, batched=True), M)],
+                     d_strides=(rs, 1, self.stride, 0), nb0=n, atomic=True)
+            ops.gemm(gA_all, Kc, r, [(Mat(ctx2, M, Kc, Kc, mn=True), Mat(U, M, r, rs, mn=True, sb0=M * rs, batched=True), M)],
+                     d_strides=(1, Kc, self.stride, 0), nb0=n, atomic=True)
+            segs.append((Mat(U, M, r, rs, sb0=M * rs, batched=True), Mat(A_all, r, Kc, Kc, mn=True, sb0=self.stride, batched=True), r))
+        dctx_all = torch.empty(n, M, Kc, dtype=BF16, device=dev)
+        ops.gemm(dctx_all, M, Kc, segs, d_strides=(Kc, 1, M * Kc, 0), nb0=n)
+        d_ctx.add_(dctx_all.sum(dim=0))               # plumbing: one reduction over the layer axis
 
 
 class TBlock:
@@ -475,13 +559,29 @@ class Resnet:
 # =================================================================================================
 class UNetB200:
     def __init__(self, arch: UNetArch, state_dict: Dict[str, torch.Tensor], lora_rank: int,
-                 lora_alpha_multiplier: float = 1.0, device="cuda:0", ti_elems: int = 0, lora_seed: int = 0):
+                 lora_alpha_multiplier: float = 1.0, device="cuda:0", ti_elems: int = 0, lora_seed: int = 0,
+                 batch_cross_kv: bool = True):
         self.arch, self.device = arch, torch.device(device)
         sd = {k.replace("base_model.model.", "").replace(".base_layer.", "."): v for k, v in state_dict.items()}
         self._sd = sd
         self.store = LoraStore(self.device, scaling=(lora_rank * lora_alpha_multiplier) / lora_rank)
         self.rank = lora_rank
         self.hooked: List[Attn] = []
+        self._cross: Dict[str, Attn] = {}
+        self.kv_groups: List[CrossKVBatch] = []
+        # cross-attention K/V projections all read the prompt embedding: group them by width and give each group
+        # contiguous LoRA slots so they can run as strided batches (CrossKVBatch)
+        groups: Dict[int, List[str]] = {}
+        if batch_cross_kv:
+            for key in sd:
+                if key.endswith(".attn2.to_k.weight"):
+                    groups.setdefault(sd[key].shape[0], []).append(key[:-len(".to_k.weight")])
+            if lora_rank > 0:
+                for width, paths in groups.items():
+                    for pth in paths:
+                        for proj in ("to_k", "to_v"):
+                            w = sd[f"{pth}.{proj}.weight"]
+                            self.store.add(f"{pth}.{proj}", "linear", lora_rank, w.shape[1], w.shape[0])
         a, boc, g = arch, arch.block_out_channels, arch.norm_num_groups
         ted = a.time_embed_dim
         self.time1, self.time2 = self._lin("time_embedding.linear_1"), self._lin("time_embedding.linear_2")
@@ -513,6 +613,19 @@ class UNetB200:
             self.up.append((rs, at, us))
         self.norm_out = GN(self._w("conv_norm_out.weight"), self._w("conv_norm_out.bias"), g, 1e-5, True)
         self.conv_out = self._conv("conv_out")
+        for width, paths in groups.items():
+            names, ws = [], []
+            for i, pth in enumerate(paths):
+                at = self._cross[pth]
+                names += [f"{pth}.to_k", f"{pth}.to_v"]
+                ws += [at.to_k.W, at.to_v.W]
+            W_all = torch.stack(ws, dim=0).contiguous()
+            grp = CrossKVBatch(self.store, names, W_all, lora_rank)
+            for i, pth in enumerate(paths):
+                at = self._cross[pth]
+                at.to_k.W, at.to_v.W = W_all[2 * i], W_all[2 * i + 1]      # views: the stacked copy is the only copy
+                at.kv_batch, at.kv_index = grp, i
+            self.kv_groups.append(grp)
         # the reference enumerates hooked processors down_blocks first, then up_blocks (ti_cross_attn_loss.py:95-110)
         self.store.finalize(extra=ti_elems)
         lora_keys = [k for k in sd if ".lora_A." in k]
@@ -559,6 +672,8 @@ class UNetB200:
     def _attn(self, p: str, heads: int, cross: bool, hook: bool) -> Attn:
         at = Attn(heads, self._lin(f"{p}.to_q"), self._lin(f"{p}.to_k"), self._lin(f"{p}.to_v"),
                   self._lin(f"{p}.to_out.0"), cross)
+        if cross:
+            self._cross[p] = at
         if cross and hook:
             self.hooked.append(at)
         return at
@@ -599,6 +714,8 @@ class UNetB200:
             a1 = self.add1.fwd(add_in)
             emb = self.add2.fwd(ops.silu_fwd(a1), residual=emb)
         temb_act = ops.silu_fwd(emb)
+        for grp in self.kv_groups:
+            grp.fwd(ctx2)
         x = self.conv_in.fwd(x8, B, H, W)
         skips = [x]
         dims = [(H, W)]
@@ -680,6 +797,8 @@ class UNetB200:
         d = ops.add(d, dskips.pop())
         assert not dskips
         self.conv_in.bwd(d, need_dx=False)          # the input latents need no gradient
+        for grp in self.kv_groups:
+            grp.bwd(d_ctx)
         # time / added-condition embedding path (only the pooled text embedding needs a gradient)
         d_emb = ops.silu_bwd(d_temb_act, emb)
         d_text = None

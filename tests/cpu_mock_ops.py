@@ -101,7 +101,7 @@ def flash_attn_fwd(q, k, v, B, H, L, Lk, scale):
     return _bf(o.transpose(1, 2).reshape(B * L, C_)), torch.logsumexp(s, -1)
 
 
-def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale):
+def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale, dk=None, dv=None):
     C_ = H * 64
     q4 = q.float().view(B, L, H, 64).transpose(1, 2).detach().requires_grad_(True)
     k4 = k.float().view(B, Lk, H, 64).transpose(1, 2).detach().requires_grad_(True)
@@ -109,7 +109,14 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale):
     out = torch.softmax(q4 @ k4.transpose(-1, -2) * scale, -1) @ v4
     out.backward(d_o.float().view(B, L, H, 64).transpose(1, 2))
     unh = lambda t, n: _bf(t.transpose(1, 2).reshape(B * n, C_))
-    return unh(q4.grad, L), unh(k4.grad, Lk), unh(v4.grad, Lk)
+    gk, gv = unh(k4.grad, Lk), unh(v4.grad, Lk)
+    if dk is not None:
+        dk.copy_(gk)
+        gk = dk
+    if dv is not None:
+        dv.copy_(gv)
+        gv = dv
+    return unh(q4.grad, L), gk, gv
 
 
 def softmax_fwd(S, P, rows, cols, ld_s, ld_p):
