@@ -147,8 +147,17 @@ int b200_col2im3x3(const void* col, void* dx, int32_t N, int32_t H, int32_t W, i
 /* U9[p, tap*r + j] = U[p - offset(tap), j] (zero outside the image): lets the conv-LoRA backward run as plain GEMMs */
 int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, int32_t ld_in, int32_t ld_out,
                       void* stream);
-/* out[b, c] = sum_p x[b, p, c]  (x: [batch, hw, C] bf16) - gradient of the per-image time-embedding bias */
-int b200_colsum(const void* x, void* out, int32_t batch, int64_t hw, int32_t C, void* stream);
+/* out[b, c] = sum_p x[b, p, c]  (x: [batch, hw, C] bf16, C % 8 == 0) - gradient of the per-image time-embedding bias.
+ * scratch: batch*C fp32 (zeroed by the call; rows are split over CTAs and combined with fp32 reductions). */
+int b200_colsum(const void* x, void* out, float* scratch, int32_t batch, int64_t hw, int32_t C, void* stream);
+/* Bicubic resize of channels-last bf16 maps: F.interpolate(x, size=(Ho, Wo), mode="bicubic") exactly as the reference
+ * applies it to the captured cross-attention maps (trainer/ti_cross_attn_loss.py:262-266: align_corners=False, no
+ * antialias, A = -0.75, clamped taps).  x: [B, Hi, Wi, C] with pixel stride ld_in, y: [B, Ho, Wo, C] with pixel stride
+ * ld_out (elements).  _bwd is the adjoint: dx[B, Hi, Wi, C] = J^T dy, written (not accumulated), gather form. */
+int b200_bicubic_fwd(const void* x, void* y, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
+                     int64_t ld_in, int64_t ld_out, void* stream);
+int b200_bicubic_bwd(const void* dy, void* dx, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
+                     int64_t ld_dy, int64_t ld_dx, void* stream);
 /* sinusoidal timestep embedding (flip_sin_to_cos, shift 0): t fp32 [n] -> bf16 [n, dim] */
 int b200_timestep_embedding(const float* t, void* out, int32_t n, int32_t dim, void* stream);
 

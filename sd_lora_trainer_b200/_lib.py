@@ -57,7 +57,9 @@ SIGNATURES = {
     "b200_im2col3x3": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_col2im3x3": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_shift_stack9": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
-    "b200_colsum": [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p],
+    "b200_colsum": [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p],
+    "b200_bicubic_fwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
+    "b200_bicubic_bwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
     "b200_timestep_embedding": [c_void_p, c_void_p, c_int32, c_int32, c_void_p],
     "b200_noise_prologue": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                             c_int32, c_int32, c_void_p],

@@ -323,23 +323,145 @@ __global__ void col2im3x3_kernel(const bf16* __restrict__ col, bf16* __restrict_
 }
 
 // out[b, c] = sum_p x[b, p, c]   (d(time-embedding projection) = per-image column sum of d(conv1 output))
-__global__ void colsum_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long hw, int C) {
+// out[b, c] = sum_p x[b, p, c]: 16-byte vector loads, rows split over gridDim.z, fp32 partial sums combined with
+// red.global.add into a zeroed scratch row, converted to bf16 by colsum_finish_kernel.
+__global__ void colsum_partial_kernel(const bf16* __restrict__ x, float* __restrict__ acc, long long hw, int C,
+                                      int rows_per_block) {
     pdl_launch();
     pdl_wait();
-    __shared__ float part[8][32];
+    __shared__ float part[16][128 + 4];
     const int b = blockIdx.y;
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int ry = threadIdx.x >> 5;    // 8 row lanes
-    float acc = 0.f;
-    if (c < C)
-        for (long long p = ry; p < hw; p += 8) acc += __bfloat162float(x[(static_cast<long long>(b) * hw + p) * C + c]);
-    part[ry][threadIdx.x & 31] = acc;
-    __syncthreads();
-    if (ry == 0 && c < C) {
-        float s = 0.f;
+    const int cg = threadIdx.x & 15;                 // 16 column groups of 8 channels = 128 channels per block
+    const int ry = threadIdx.x >> 4;                 // 16 row lanes
+    const int c0 = blockIdx.x * 128 + cg * 8;
+    const long long p0 = static_cast<long long>(blockIdx.z) * rows_per_block;
+    const long long p1 = min(hw, p0 + rows_per_block);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c0 < C) {
+        const bf16* base = x + static_cast<long long>(b) * hw * C + c0;
+        for (long long p = p0 + ry; p < p1; p += 16) {
+            float f[8];
+            load8(base + p * C, f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
-        out[static_cast<long long>(b) * C + c] = __float2bfloat16_rn(s);
+            for (int i = 0; i < 8; ++i) a[i] += f[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[ry][cg * 8 + i] = a[i];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int c = blockIdx.x * 128 + threadIdx.x;
+        if (c < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s += part[i][threadIdx.x];
+            atomicAdd(acc + static_cast<long long>(b) * C + c, s);
+        }
+    }
+}
+__global__ void colsum_finish_kernel(const float* __restrict__ acc, bf16* __restrict__ out, long long n) {
+    pdl_launch();
+    pdl_wait();
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bicubic resize of channels-last maps (F.interpolate(mode="bicubic", align_corners=False, antialias=False) as the
+// reference applies it to the captured cross-attention maps, ti_cross_attn_loss.py:262-266): A = -0.75, taps clamped
+// to the image, fp32 arithmetic, one rounding to bf16.  x: [B, Hi, Wi, C] with pixel stride ld_in; y: [B, Ho, Wo, C].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+    const float A = -0.75f;
+    const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+    w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+    w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+    w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+    w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void bicubic_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo,
+                                   int C, long long ld_in, long long ld_out, float sh, float sw) {
+    pdl_launch();
+    pdl_wait();
+    const long long total = static_cast<long long>(B) * Ho * Wo * C;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % C);
+        long long p = idx / C;
+        const int ox = static_cast<int>(p % Wo);  p /= Wo;
+        const int oy = static_cast<int>(p % Ho);
+        const int b = static_cast<int>(p / Ho);
+        const float ry = sh * (oy + 0.5f) - 0.5f, rx = sw * (ox + 0.5f) - 0.5f;
+        const int iy = static_cast<int>(floorf(ry)), ix = static_cast<int>(floorf(rx));
+        float wy[4], wx[4];
+        cubic_coeffs(ry - iy, wy);
+        cubic_coeffs(rx - ix, wx);
+        const bf16* img = x + static_cast<long long>(b) * Hi * Wi * ld_in + c;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int yy = clampi(iy - 1 + i, 0, Hi - 1);
+            float row = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xx = clampi(ix - 1 + j, 0, Wi - 1);
+                row += __bfloat162float(img[(static_cast<long long>(yy) * Wi + xx) * ld_in]) * wx[j];
+            }
+            acc += row * wy[i];
+        }
+        y[((static_cast<long long>(b) * Ho + oy) * Wo + ox) * ld_out + c] = __float2bfloat16_rn(acc);
+    }
+}
+
+// Gather form of the adjoint (no atomics): every input pixel sums the output pixels whose clamped taps land on it.
+__global__ void bicubic_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int Hi, int Wi, int Ho, int Wo,
+                                   int C, long long ld_dy, long long ld_dx, float sh, float sw) {
+    pdl_launch();
+    pdl_wait();
+    const long long total = static_cast<long long>(B) * Hi * Wi * C;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % C);
+        long long p = idx / C;
+        const int xx = static_cast<int>(p % Wi);  p /= Wi;
+        const int yy = static_cast<int>(p % Hi);
+        const int b = static_cast<int>(p / Hi);
+        // candidate outputs: |src(o) - in| <= 2 (+ clamped taps at the borders, which the tap test below catches)
+        int oy0 = static_cast<int>(floorf((yy - 2.5f) / sh)) - 1, oy1 = static_cast<int>(ceilf((yy + 2.5f) / sh)) + 1;
+        int ox0 = static_cast<int>(floorf((xx - 2.5f) / sw)) - 1, ox1 = static_cast<int>(ceilf((xx + 2.5f) / sw)) + 1;
+        if (yy == 0) oy0 = 0;
+        if (yy == Hi - 1) oy1 = Ho - 1;
+        if (xx == 0) ox0 = 0;
+        if (xx == Wi - 1) ox1 = Wo - 1;
+        oy0 = max(oy0, 0);  oy1 = min(oy1, Ho - 1);
+        ox0 = max(ox0, 0);  ox1 = min(ox1, Wo - 1);
+        const bf16* g = dy + static_cast<long long>(b) * Ho * Wo * ld_dy + c;
+        float acc = 0.f;
+        for (int oy = oy0; oy <= oy1; ++oy) {
+            const float ry = sh * (oy + 0.5f) - 0.5f;
+            const int iy = static_cast<int>(floorf(ry));
+            float wy[4];
+            cubic_coeffs(ry - iy, wy);
+            float cy = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (clampi(iy - 1 + i, 0, Hi - 1) == yy) cy += wy[i];
+            if (cy == 0.f) continue;
+            for (int ox = ox0; ox <= ox1; ++ox) {
+                const float rx = sw * (ox + 0.5f) - 0.5f;
+                const int ix = static_cast<int>(floorf(rx));
+                float wx[4];
+                cubic_coeffs(rx - ix, wx);
+                float cx = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (clampi(ix - 1 + j, 0, Wi - 1) == xx) cx += wx[j];
+                if (cx != 0.f) acc += cy * cx * __bfloat162float(g[(static_cast<long long>(oy) * Wo + ox) * ld_dy]);
+            }
+        }
+        dx[((static_cast<long long>(b) * Hi + yy) * Wi + xx) * ld_dx + c] = __float2bfloat16_rn(acc);
     }
 }
 
@@ -479,10 +601,44 @@ extern "C" int b200_col2im3x3(const void* col, void* dx, int32_t N, int32_t H, i
     B200_CHECK_LAUNCH("col2im3x3");
     return 0;
 }
-extern "C" int b200_colsum(const void* x, void* out, int32_t batch, int64_t hw, int32_t C, void* stream) {
-    dim3 grid((C + 31) / 32, batch);
-    launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, ST, static_cast<const bf16*>(x), static_cast<bf16*>(out), hw, C);
-    B200_CHECK_LAUNCH("colsum");
+extern "C" int b200_colsum(const void* x, void* out, float* scratch, int32_t batch, int64_t hw, int32_t C, void* stream) {
+    B200_CHECK_ARG(C % 8 == 0, "colsum: C %% 8 != 0");
+    B200_CHECK_ARG(scratch != nullptr, "colsum: needs a batch*C fp32 scratch buffer");
+    const long long n = static_cast<long long>(batch) * C;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, n * sizeof(float), ST);
+    if (e != cudaSuccess) return set_error(3, "colsum: memset: %s", cudaGetErrorString(e));
+    const int cblocks = (C + 127) / 128;
+    int nz = static_cast<int>((2LL * kNumSMs + static_cast<long long>(cblocks) * batch - 1) / (static_cast<long long>(cblocks) * batch));
+    const int max_z = static_cast<int>((hw + 63) / 64);
+    if (nz > max_z) nz = max_z;
+    if (nz < 1) nz = 1;
+    const int rows_per_block = static_cast<int>((hw + nz - 1) / nz);
+    launch_pdl(colsum_partial_kernel, dim3(cblocks, batch, nz), dim3(256), 0, ST, static_cast<const bf16*>(x), scratch, hw, C,
+               rows_per_block);
+    B200_CHECK_LAUNCH("colsum_partial");
+    launch_pdl(colsum_finish_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, ST, static_cast<const float*>(scratch),
+               static_cast<bf16*>(out), n);
+    B200_CHECK_LAUNCH("colsum_finish");
+    return 0;
+}
+extern "C" int b200_bicubic_fwd(const void* x, void* y, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
+                                int64_t ld_in, int64_t ld_out, void* stream) {
+    B200_CHECK_ARG(B >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1, "bicubic: empty extents");
+    B200_CHECK_ARG(ld_in >= C && ld_out >= C, "bicubic: pixel stride smaller than C");
+    const float sh = static_cast<float>(Hi) / Ho, sw = static_cast<float>(Wi) / Wo;
+    launch_pdl(bicubic_fwd_kernel, dim3(grid_for(1LL * B * Ho * Wo * C, 256)), dim3(256), 0, ST, static_cast<const bf16*>(x),
+               static_cast<bf16*>(y), B, Hi, Wi, Ho, Wo, C, static_cast<long long>(ld_in), static_cast<long long>(ld_out), sh, sw);
+    B200_CHECK_LAUNCH("bicubic_fwd");
+    return 0;
+}
+extern "C" int b200_bicubic_bwd(const void* dy, void* dx, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,
+                                int64_t ld_dy, int64_t ld_dx, void* stream) {
+    B200_CHECK_ARG(B >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1, "bicubic: empty extents");
+    B200_CHECK_ARG(ld_dy >= C && ld_dx >= C, "bicubic: pixel stride smaller than C");
+    const float sh = static_cast<float>(Hi) / Ho, sw = static_cast<float>(Wi) / Wo;
+    launch_pdl(bicubic_bwd_kernel, dim3(grid_for(1LL * B * Hi * Wi * C, 256)), dim3(256), 0, ST, static_cast<const bf16*>(dy),
+               static_cast<bf16*>(dx), B, Hi, Wi, Ho, Wo, C, static_cast<long long>(ld_dy), static_cast<long long>(ld_dx), sh, sw);
+    B200_CHECK_LAUNCH("bicubic_bwd");
     return 0;
 }
 extern "C" int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, int32_t ld_in,

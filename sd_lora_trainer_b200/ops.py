@@ -284,8 +284,29 @@ def shift_stack9(U: torch.Tensor, N: int, H: int, W: int, r: int):
 
 def colsum(x: torch.Tensor, batch: int, hw: int, C_: int):
     out = torch.empty(batch, C_, dtype=BF16, device=x.device)
-    check(_lib.load().b200_colsum(x.data_ptr(), out.data_ptr(), batch, hw, C_, _stream()), "colsum")
+    scratch = torch.empty(batch, C_, dtype=torch.float32, device=x.device)
+    check(_lib.load().b200_colsum(x.data_ptr(), out.data_ptr(), scratch.data_ptr(), batch, hw, C_, _stream()), "colsum")
     return out
+
+
+def bicubic_fwd(x: torch.Tensor, Ho: int, Wo: int):
+    """x: [B, Hi, Wi, C] bf16 channels-last view (unit channel stride, dense rows) -> [B, Ho, Wo, C]."""
+    B, Hi, Wi, C_ = x.shape
+    assert x.dtype == BF16 and x.stride(3) == 1 and x.stride(1) == Wi * x.stride(2) and x.stride(0) == Hi * x.stride(1)
+    y = torch.empty(B, Ho, Wo, C_, dtype=BF16, device=x.device)
+    check(_lib.load().b200_bicubic_fwd(x.data_ptr(), y.data_ptr(), B, Hi, Wi, Ho, Wo, C_, x.stride(2), C_, _stream()),
+          "bicubic_fwd")
+    return y
+
+
+def bicubic_bwd(dy: torch.Tensor, Hi: int, Wi: int):
+    """Adjoint of bicubic_fwd: dy [B, Ho, Wo, C] bf16 -> dx [B, Hi, Wi, C] bf16."""
+    dy = dy.contiguous()
+    B, Ho, Wo, C_ = dy.shape
+    dx = torch.empty(B, Hi, Wi, C_, dtype=BF16, device=dy.device)
+    check(_lib.load().b200_bicubic_bwd(dy.data_ptr(), dx.data_ptr(), B, Hi, Wi, Ho, Wo, C_, C_, C_, _stream()),
+          "bicubic_bwd")
+    return dx
 
 
 def timestep_embedding(t: torch.Tensor, dim: int):

@@ -2,7 +2,8 @@
 
 compute_diffusion_loss / compute_snr dispatch into the fused sm_100a kernels; the token-attention regulariser
 (loss.py:10-80) and the heat-map stacking (ti_cross_attn_loss.py:239-268) operate on [layers, B, 32, 32, 77]-sized
-maps and run as stock torch ops on the device for now (next to be fused).
+maps; the bicubic map resize is an sm_100a kernel pair (ops.bicubic_fwd/bwd), the remaining reductions are stock
+torch ops on the device.
 """
 from __future__ import annotations
 
@@ -45,6 +46,20 @@ def compute_diffusion_loss(snr_gamma: Optional[float], pred8: torch.Tensor, nois
     return ops.diffusion_loss(pred8, pred8.stride(0), noise, mask, weights, loss_scale, want_grad)
 
 
+class _BicubicResize(torch.autograd.Function):
+    """F.interpolate(hm.permute(0, 3, 1, 2), size, mode="bicubic").permute(0, 2, 3, 1) on channels-last maps, as one
+    sm_100a kernel each way (ti_cross_attn_loss.py:262-266); the stock ATen bicubic kernels cost 26 ms per SDXL step."""
+
+    @staticmethod
+    def forward(ctx, hm: torch.Tensor, size):
+        ctx.in_hw = (hm.shape[1], hm.shape[2])
+        return ops.bicubic_fwd(hm, size[0], size[1])
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        return ops.bicubic_bwd(dy, *ctx.in_hw), None
+
+
 def process_and_stack_attention_scores(scores: Sequence[torch.Tensor], img_ratio: float) -> torch.Tensor:
     """trainer/ti_cross_attn_loss.py:239-268."""
     reshaped, min_px, min_shape = [], math.inf, None
@@ -57,7 +72,7 @@ def process_and_stack_attention_scores(scores: Sequence[torch.Tensor], img_ratio
             min_px, min_shape = height * width, (height, width)
     for i, hm in enumerate(reshaped):
         if hm.shape[1] * hm.shape[2] != min_px:
-            reshaped[i] = F.interpolate(hm.permute(0, 3, 1, 2), size=min_shape, mode="bicubic").permute(0, 2, 3, 1)
+            reshaped[i] = _BicubicResize.apply(hm, min_shape)
     return torch.stack(reshaped, dim=0)
 
 

@@ -238,6 +238,19 @@ def colsum(x, batch, hw, C_):
     return _bf(x.float().view(batch, hw, C_).sum(1))
 
 
+def bicubic_fwd(x, Ho, Wo):
+    return _bf(F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bicubic").permute(0, 2, 3, 1).contiguous())
+
+
+def bicubic_bwd(dy, Hi, Wi):
+    B, Ho, Wo, C_ = dy.shape
+    with torch.enable_grad():                       # called from inside an autograd backward
+        x = torch.zeros(B, C_, Hi, Wi, requires_grad=True)
+        y = F.interpolate(x, size=(Ho, Wo), mode="bicubic")
+        (g,) = torch.autograd.grad(y, x, dy.float().permute(0, 3, 1, 2))
+    return _bf(g.permute(0, 2, 3, 1).contiguous())
+
+
 def timestep_embedding(t, dim):
     half = dim // 2
     ex = -math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half

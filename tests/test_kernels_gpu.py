@@ -182,3 +182,38 @@ def test_adamw_bit_exact_vs_torch(wd, l1):
         assert float(g32.abs().max()) == 0.0
         diff = (p.float() - p_ref.detach().float()).abs()
         assert torch.equal(p, p_ref.detach()), f"step {step}: {int((diff > 0).sum())} of {n} differ, max {float(diff.max())}"
+
+
+@pytest.mark.parametrize("B,hw,C", [(2, 1024, 1280), (2, 4096, 640), (2, 16384, 320), (4, 64, 1280), (1, 100, 8)])
+def test_colsum(B, hw, C):
+    from sd_lora_trainer_b200 import ops
+    x = _rand(B * hw, C, seed=5)
+    out = ops.colsum(x, B, hw, C)
+    ref = x.float().view(B, hw, C).sum(dim=1)
+    _close(out, ref, tol=1e-2, what="colsum")
+
+
+@pytest.mark.parametrize("B,Hi,Wi,Ho,Wo,C,ld", [(2, 64, 64, 32, 32, 77, 80), (4, 64, 64, 8, 8, 77, 80),
+                                                (2, 32, 32, 8, 8, 77, 77), (1, 16, 24, 8, 12, 5, 8),
+                                                (2, 8, 8, 16, 16, 7, 7)])
+def test_bicubic_resize_matches_interpolate(B, Hi, Wi, Ho, Wo, C, ld):
+    """ops.bicubic_fwd/bwd against F.interpolate(mode="bicubic") in fp32 (ti_cross_attn_loss.py:262-266), on the
+    strided channels-last views the score hook produces ([B, L, 80] sliced to 77 text tokens)."""
+    from sd_lora_trainer_b200 import ops
+    buf = _rand(B, Hi * Wi, ld, seed=6)
+    x = buf[:, :, :C].reshape(B, Hi, Wi, C)
+    y = ops.bicubic_fwd(x, Ho, Wo)
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ref = F.interpolate(xr, size=(Ho, Wo), mode="bicubic")
+    refl = ref.permute(0, 2, 3, 1)
+    # one bf16 rounding of an fp32 result: within half an ulp of the fp32 reference (2^-9 relative) + summation slack
+    assert ((y.float() - refl).abs() <= 2.0 ** -8 * refl.abs() + 1e-6).all()
+    dy = _rand(B, Ho, Wo, C, seed=7)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dx = ops.bicubic_bwd(dy, Hi, Wi)
+    gref = xr.grad.permute(0, 2, 3, 1)
+    assert ((dx.float() - gref).abs() <= 2.0 ** -8 * gref.abs() + 1e-5).all()
+    # adjoint identity <J x, dy> == <x, J^T dy> in fp64 on the fp32 references
+    lhs = (refl.double() * dy.double()).sum()
+    rhs = (x.double() * gref.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-6 * abs(float(lhs)) + 1e-6
