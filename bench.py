@@ -126,6 +126,18 @@ def run_ours(args):
     float(out["tot_loss"])
     sync_all()
 
+    if args.profile_step:
+        # ncu window (`ncu --profile-from-start off`): exactly one step between cudaProfilerStart / Stop, then leave
+        rt = torch.cuda.cudart()
+        torch.cuda.synchronize()
+        rt.cudaProfilerStart()
+        tr.step_resident(completion_f=0.0)
+        torch.cuda.synchronize()
+        rt.cudaProfilerStop()
+        if rank == 0:
+            print(json.dumps({"profiled_step": True, "gpu_launches_per_step": tr.launches_per_step}), flush=True)
+        return
+
     # ---- timed region 1: inputs resident in HBM (the staged static buffers), K steps -----------------------
     sampler = ClockSampler(local)
     sampler.start()
@@ -260,6 +272,8 @@ def main():
     ap.add_argument("--rank", type=int, default=16)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after warm-up run ONE step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--skip-roofline", action="store_true")
     ap.add_argument("--cpu-res", type=int, default=1024)
     ap.add_argument("--cpu-batch", type=int, default=1)

@@ -57,6 +57,9 @@ typedef struct {
     int32_t nb0, nb1;             /* batch extents (>= 1) */
     int32_t splits;               /* split-K (>= 1); > 1 requires d_fp32 && d_atomic, num_seg == 1, conv == 0 */
     int32_t block_n;              /* 0: library picks the tile width for whole waves */
+    int32_t pair_mode;            /* 0: library picks; 1: force the CTA-pair (cta_group::2, 256-row tiles) kernel;
+                                     -1: never use it.  The pair kernel covers one K-major A segment, no conv / batch /
+                                     split-K, row-major output (incl. the fused side path). */
     /* implicit 3x3/pad1/stride1 convolution on segment 0: A[0].ptr is NHWC [conv_N, conv_H, conv_W, conv_C],
        M must equal conv_N*conv_H*conv_W, B[0] is [N rows, 9*b_tap_k (+...)] K-major. */
     int32_t conv;

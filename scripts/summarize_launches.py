@@ -23,14 +23,17 @@ def main(path, out_json=None):
     marks = [i for i, n in enumerate(names) if "timestep_embedding" in n]
     # a step starts at its first timestep_embedding launch; take the last complete one
     starts = [m for j, m in enumerate(marks) if j == 0 or m - marks[j - 1] > 50]
-    lo, hi = (starts[-2], starts[-1]) if len(starts) >= 2 else (starts[0], len(rows))
+    if len(starts) >= 2:
+        lo, hi = starts[-2], starts[-1]
+    else:                       # the capture window was exactly one step (bench.py --profile-step)
+        lo, hi = 0, len(rows)
     step = rows[lo:hi]
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot = 0.0
     for d in step:
         n = d["Kernel Name"].split("(")[0]
-        if "gemm_tcgen05" in n:
-            n = f"b200::gemm_tcgen05_kernel grid={d['Grid Size']}"
+        if "gemm_tcgen05" in n or "gemm2_kernel" in n:
+            n = f"{n.split('<')[0]} grid={d['Grid Size']}"
         ns = to_ns(d)
         agg[n][0] += 1
         agg[n][1] += ns
@@ -38,7 +41,7 @@ def main(path, out_json=None):
     out = {"launches": len(step), "total_ms": tot / 1e6,
            "kernels": [{"name": k, "count": v[0], "ms": v[1] / 1e6, "share": v[1] / tot}
                        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])]}
-    gemm = sum(k["ms"] for k in out["kernels"] if "gemm_tcgen05" in k["name"])
+    gemm = sum(k["ms"] for k in out["kernels"] if "gemm_tcgen05" in k["name"] or "gemm2_kernel" in k["name"])
     out["gemm_tcgen05_ms"], out["gemm_tcgen05_share"] = gemm, gemm / (tot / 1e6)
     print(f"launches {out['launches']}  total {out['total_ms']:.2f} ms  gemm_tcgen05 {gemm:.2f} ms ({out['gemm_tcgen05_share']:.1%})")
     for k in out["kernels"][:32]:

@@ -18,7 +18,7 @@ class Operand(C.Structure):
 class GemmDesc(C.Structure):
     _fields_ = [("M", c_int32), ("N", c_int32), ("num_seg", c_int32), ("K", c_int32 * 2),
                 ("A", Operand * 2), ("B", Operand * 2), ("nb0", c_int32), ("nb1", c_int32),
-                ("splits", c_int32), ("block_n", c_int32),
+                ("splits", c_int32), ("block_n", c_int32), ("pair_mode", c_int32),
                 ("conv", c_int32), ("conv_N", c_int32), ("conv_H", c_int32), ("conv_W", c_int32), ("conv_C", c_int32),
                 ("b_tap_k", c_int32), ("b_tap_n", c_int32),
                 ("D", c_void_p), ("d_fp32", c_int32), ("d_atomic", c_int32),

@@ -1,0 +1,418 @@
+// CTA-pair (cta_group::2) bf16 GEMM for sm_100a: the big, plain projections of the step.
+//
+//   D[m, n] = alpha * sum_k A[m, k] * B[n, k]  (+ bias[n]) (+ R[m, n])   (+ the fused LoRA side path, see below)
+//
+// Why a second kernel: with 128 x BN single-CTA tiles the K loop of gemm_tcgen05_kernel is bound by L2 -> SM traffic
+// (profiles/r01a_gemm_ncu_full.md: 663 MB for 2048x10240x1280 = the ~11 TB/s fabric limit), not by the tensor pipe.
+// Here two CTAs of a cluster (one TPC) own a 256 x BN tile: each loads ITS 128 rows of A and HALF of the B tile, one
+// tcgen05.mma.cta_group::2 (M = 256) issued by the leader CTA reads both halves, so a 256 x 256 tile streams
+// 64 KiB per k-block for 2x the FLOPs of the 48 KiB a 128 x 256 tile needs.
+//
+//   warp 0      TMA producer (both CTAs; transaction bytes complete on the LEADER's full barrier)
+//   warp 1      MMA issuer (leader CTA only) + TMEM alloc/dealloc (both CTAs, cta_group::2)
+//   warps 2-9   epilogue (each CTA drains its own 128 accumulator rows; two warps per TMEM lane quarter)
+//
+// Hot loops are deliberately lean: every kernel parameter they need is copied to registers up front, descriptors are
+// formed from hoisted constants, and nothing but barrier waits, TMA / MMA issues and ring bookkeeping sits in them
+// (the first kernel spent ~170 SASS instructions per k-block in each of these two warps).
+//
+// Fused LoRA side path (same contract as gemm_tcgen05_kernel): while the K loop accumulates A.B^T, a second
+// cta_group::2 MMA per k-step accumulates A.S^T (N = 16 / 32) next to the main tile; the epilogue warps of BOTH CTAs
+// scale + round their 128 rows of it to bf16 into a swizzled smem tile (and to T_out), the leader issues one more MMA
+// T.B2^T into the main accumulator.
+#pragma once
+#include "ptx.cuh"
+#include "common.cuh"
+#include "gemm_tcgen05.cuh"
+
+namespace b200 {
+
+constexpr int k2Threads = 320;
+constexpr int k2ABytes = 128 * 64 * 2;           // one CTA's A tile per stage
+constexpr int k2RingBytes = 160 * 1024;
+constexpr int k2TOff = k2RingBytes;              // T tile (16 KiB, 128B-swizzled K-major A operand of the final MMA)
+constexpr int k2BarOff = k2TOff + 16384;
+constexpr int k2EpiOff = k2BarOff + 512;
+constexpr int k2EpiBytes = 8 * 32 * kEpiLd * 4;
+constexpr int k2SmemBytes = k2EpiOff + k2EpiBytes;
+static_assert(k2SmemBytes <= 232448, "shared memory budget");
+
+struct Gemm2Args {
+    // scalars first: they fit in a few constant-cache lines and are read once, before griddepcontrol.wait
+    int M, N, BN, tiles_n, total_tiles, kblocks, ktail16;
+    int b_mn, side, side_mn, b2_mn, side_r16, side_r;
+    int stage_bytes, num_stages, side_off, acc_stages;
+    int vec_ok, bias_rows;
+    float alpha, side_alpha;
+    long long d_sm, r_sm, t_ld, bias_sb;
+    void* D;
+    const __nv_bfloat16* bias;
+    const __nv_bfloat16* R;
+    __nv_bfloat16* T_out;
+    CUtensorMap mapA, mapB, mapS, mapB2;
+};
+
+struct Epi2 {
+    void* D;
+    const __nv_bfloat16* bias;
+    const __nv_bfloat16* R;
+    long long d_sm, r_sm, bias_sb;
+    int M, N, bias_rows, vec_ok;
+    float alpha;
+};
+
+// One 32-row x 32-column chunk of the tile: registers (one row per thread) -> padded smem patch -> 8 lanes per
+// 128-byte row segment -> alpha / bias / residual -> vector stores.  Row-major outputs only.
+template <int kEpi>
+__device__ __forceinline__ void epi2_chunk(const Epi2& e, const uint32_t (&raw)[32], float* stage, int lane, int m_warp,
+                                           int n_chunk, int cvalid) {
+    float4* srow = reinterpret_cast<float4*>(stage + lane * kEpiLd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        srow[j] = make_float4(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1]), __uint_as_float(raw[4 * j + 2]),
+                              __uint_as_float(raw[4 * j + 3]));
+    __syncwarp();
+    const int sub = lane >> 3, col = (lane & 7) * 4;
+    const int n = n_chunk + col;
+    const int nv = min(4, min(e.N - n, cvalid - col));
+    const float alpha = e.alpha;
+    const int m_first = m_warp + sub;
+    const float* sp = stage + sub * kEpiLd + col;
+    const long long d_step = 4 * e.d_sm, r_step = 4 * e.r_sm;
+    const long long doff = static_cast<long long>(m_first) * e.d_sm + n;
+    const __nv_bfloat16* rp = e.R ? e.R + static_cast<long long>(m_first) * e.r_sm + n : nullptr;
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool bias_per_row = e.bias != nullptr && e.bias_rows != 0;
+    if (e.bias != nullptr && !bias_per_row && nv > 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < nv) bv[q] = __bfloat162float(e.bias[n + q]);
+    }
+    const bool interior = e.vec_ok && !bias_per_row && (m_warp + 32 <= e.M) && (cvalid == 32) && (n_chunk + 32 <= e.N);
+    if (interior) {
+        float4 q[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) q[it] = *reinterpret_cast<const float4*>(sp + it * 4 * kEpiLd);
+        uint2 rr[8];
+        if (rp) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) rr[it] = *reinterpret_cast<const uint2*>(rp + it * r_step);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            float v0 = fmaf(q[it].x, alpha, bv[0]), v1 = fmaf(q[it].y, alpha, bv[1]);
+            float v2 = fmaf(q[it].z, alpha, bv[2]), v3 = fmaf(q[it].w, alpha, bv[3]);
+            if (rp) {
+                v0 += __uint_as_float(rr[it].x << 16);
+                v1 += __uint_as_float(rr[it].x & 0xffff0000u);
+                v2 += __uint_as_float(rr[it].y << 16);
+                v3 += __uint_as_float(rr[it].y & 0xffff0000u);
+            }
+            if (kEpi == 1) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.D) + doff + it * d_step) = make_float4(v0, v1, v2, v3);
+            } else {
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1);
+                const __nv_bfloat162 h1 = __floats2bfloat162_rn(v2, v3);
+                uint2 w2;
+                w2.x = *reinterpret_cast<const uint32_t*>(&h0);
+                w2.y = *reinterpret_cast<const uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.D) + doff + it * d_step) = w2;
+            }
+        }
+    } else if (nv > 0) {
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+            const int m = m_first + it * 4;
+            if (m >= e.M) break;
+            const float* q = sp + it * 4 * kEpiLd;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (c < nv) {
+                    float x = q[c] * alpha + bv[c];
+                    if (bias_per_row) x += __bfloat162float(e.bias[(m / e.bias_rows) * e.bias_sb + n + c]);
+                    if (rp) x += __bfloat162float(rp[it * r_step + c]);
+                    if (kEpi == 1) reinterpret_cast<float*>(e.D)[doff + it * d_step + c] = x;
+                    else reinterpret_cast<__nv_bfloat16*>(e.D)[doff + it * d_step + c] = __float2bfloat16_rn(x);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int kEpi>
+__global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_constant__ Gemm2Args g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + k2BarOff);   // [kMaxStages]  (used in the leader CTA)
+    uint64_t* empty_bar = full_bar + kMaxStages;                           // [kMaxStages]  (both CTAs, multicast commit)
+    uint64_t* tmem_full_bar = empty_bar + kMaxStages;                      // [2]           (both CTAs, multicast commit)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;                          // [2]           (leader; 8 warps x 2 CTAs)
+    uint64_t* side_full_bar = tmem_empty_bar + 2;                          // [2]           (both CTAs, multicast commit)
+    uint64_t* t_ready_bar = side_full_bar + 2;                             //               (leader; 4 warps x 2 CTAs)
+    uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(t_ready_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    // ---- everything the loops need, read once (constant bank), before the dependency wait ----
+    const int BN = g.BN, tiles_n = g.tiles_n, total_tiles = g.total_tiles, kblocks = g.kblocks;
+    const int num_stages = g.num_stages, stage_bytes = g.stage_bytes, acc_stages = g.acc_stages;
+    const int side = g.side, side_off = g.side_off, r16 = g.side_r16;
+    const int b_mn = g.b_mn, side_mn = g.side_mn, b2_mn = g.b2_mn;
+    const int npairs = static_cast<int>(gridDim.x >> 1), pair = static_cast<int>(blockIdx.x >> 1);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&g.mapA);
+        tma_prefetch_desc(&g.mapB);
+        if (side) {
+            tma_prefetch_desc(&g.mapS);
+            tma_prefetch_desc(&g.mapB2);
+        }
+        for (int i = 0; i < num_stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 16);
+            mbar_init(&side_full_bar[i], 1);
+        }
+        mbar_init(t_ready_bar, 8);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc2(tmem_base_ptr, 512);
+        tmem_relinquish2();
+    }
+    pdl_launch();
+    tc_fence_before();
+    cluster_sync_all();       // the peer's barriers are initialised and its TMEM allocated before anything targets them
+    tc_fence_after();
+    pdl_wait();
+    const uint32_t tmem_base = *tmem_base_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread per CTA) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t full0 = mapa_u32(smem_u32(full_bar), 0);      // the LEADER's full barriers
+            const int bn_half = BN >> 1;
+            const int b_boxes = bn_half >> 6;
+            const uint32_t b_bytes = b_mn ? static_cast<uint32_t>(b_boxes) * 8192u : static_cast<uint32_t>(bn_half) * 128u;
+            const int sr_half = r16 >> 1;
+            const uint32_t s_bytes = side ? (side_mn ? 8192u : static_cast<uint32_t>(sr_half) * 128u) : 0u;
+            const uint32_t tx = 2u * (static_cast<uint32_t>(k2ABytes) + b_bytes + s_bytes);
+            const uint32_t b2_bytes = b2_mn ? static_cast<uint32_t>(b_boxes) * 8192u : static_cast<uint32_t>(bn_half) * 128u;
+            const int s_row = static_cast<int>(rank) * sr_half;
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+                const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
+                const int nh0 = n_blk * BN + static_cast<int>(rank) * bn_half;
+                int k = 0;
+                for (int kb = 0; kb < kblocks; ++kb, k += kBK) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    uint8_t* sb = sa + k2ABytes;
+                    const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+                    tma2_load_4d(sa, &g.mapA, fb, k, m0, 0, 0);
+                    if (!b_mn) {
+                        tma2_load_4d(sb, &g.mapB, fb, k, nh0, 0, 0);
+                    } else {
+                        for (int jb = 0; jb < b_boxes; ++jb) tma2_load_4d(sb + jb * 8192, &g.mapB, fb, nh0 + jb * 64, k, 0, 0);
+                    }
+                    if (side) {
+                        if (side_mn) tma2_load_4d(sb + side_off, &g.mapS, fb, s_row, k, 0, 0);
+                        else tma2_load_4d(sb + side_off, &g.mapS, fb, k, s_row, 0, 0);
+                    }
+                    advance_stage(stage, phase, num_stages);
+                }
+                if (side) {
+                    // one more ring slot per tile: this CTA's half of the B2 tile for the final rank-r MMA
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * b2_bytes);
+                    uint8_t* sb = smem + stage * stage_bytes + k2ABytes;
+                    const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+                    if (!b2_mn) {
+                        tma2_load_4d(sb, &g.mapB2, fb, 0, nh0, 0, 0);
+                    } else {
+                        for (int jb = 0; jb < b_boxes; ++jb) tma2_load_4d(sb + jb * 8192, &g.mapB2, fb, nh0 + jb * 64, 0, 0, 0);
+                    }
+                    advance_stage(stage, phase, num_stages);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA; warp-uniform loop, one elected lane issues) =====================
+        if (rank == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, t_phase = 0;
+            const uint32_t smem_base = smem_u32(smem);
+            const bool leader = elect_one();
+            const uint32_t idesc = umma2_idesc_bf16(BN, 0, b_mn);
+            const uint32_t idesc_s = umma2_idesc_bf16(r16, 0, side_mn);
+            const uint32_t idesc_2 = umma2_idesc_bf16(BN, 0, b2_mn);
+            const uint64_t a_hi = umma_desc(0, 16, 1024);
+            const uint64_t b_hi = umma_desc(0, b_mn ? 8192u : 16u, 1024);
+            const uint64_t s_hi = umma_desc(0, side_mn ? 8192u : 16u, 1024);
+            const uint64_t b2_hi = umma_desc(0, b2_mn ? 8192u : 16u, 1024);
+            const uint64_t b_step = b_mn ? 128u : 2u, s_step = side_mn ? 128u : 2u, b2_step = b2_mn ? 128u : 2u;
+            const int ktail = g.ktail16;
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
+                const uint32_t tmem_s = tmem_base + static_cast<uint32_t>(acc_stages == 1 ? 256 : acc * 256 + kSideCol);
+                uint32_t accum = 0;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t sa = smem_base + static_cast<uint32_t>(stage * stage_bytes);
+                        const uint64_t ad = a_hi | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
+                        const uint64_t bd = b_hi | static_cast<uint64_t>(((sa + k2ABytes) & 0x3FFFF) >> 4);
+                        const int n16 = (kb == kblocks - 1) ? ktail : 4;
+                        if (side) {
+                            const uint64_t sd = s_hi | static_cast<uint64_t>(((sa + k2ABytes + side_off) & 0x3FFFF) >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < n16) umma2_bf16(tmem_s, ad + 2u * k, sd + s_step * k, idesc_s, accum | (k > 0));
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (k < n16) umma2_bf16(tmem_d, ad + 2u * k, bd + b_step * k, idesc, accum | (k > 0));
+                        umma2_commit_mc(&empty_bar[stage]);      // frees this ring slot in BOTH CTAs
+                    }
+                    __syncwarp();
+                    accum = 1;
+                    advance_stage(stage, phase, num_stages);
+                }
+                if (side) {
+                    if (leader) umma2_commit_mc(&side_full_bar[acc]);     // rank-r accumulator complete -> T-phase
+                    __syncwarp();
+                    mbar_wait(&full_bar[stage], phase);                   // both halves of the B2 tile landed
+                    mbar_wait_cluster(t_ready_bar, t_phase);              // T staged in smem by both CTAs
+                    t_phase ^= 1;
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t sb2 = smem_base + static_cast<uint32_t>(stage * stage_bytes) + k2ABytes;
+                        const uint64_t td = a_hi | static_cast<uint64_t>(((smem_base + k2TOff) & 0x3FFFF) >> 4);
+                        const uint64_t b2d = b2_hi | static_cast<uint64_t>((sb2 & 0x3FFFF) >> 4);
+                        for (int k = 0; k < (r16 >> 4); ++k) umma2_bf16(tmem_d, td + 2u * k, b2d + b2_step * k, idesc_2, 1);
+                        umma2_commit_mc(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    advance_stage(stage, phase, num_stages);
+                }
+                if (leader) umma2_commit_mc(&tmem_full_bar[acc]);         // accumulator complete -> both epilogues
+                __syncwarp();
+                if (++acc == acc_stages) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: each CTA drains its own 128 rows; 2 warps per TMEM lane quarter ============
+        const int ew = warp - 2;
+        const int half = ew >> 2;                     // which 32-column chunks this warp takes (even / odd)
+        const int lane_base = (warp & 3) * 32;
+        float* stage_buf = reinterpret_cast<float*>(smem + k2EpiOff) + ew * (32 * kEpiLd);
+        const uint32_t tmem_empty_leader = mapa_u32(smem_u32(tmem_empty_bar), 0);
+        const uint32_t t_ready_leader = mapa_u32(smem_u32(t_ready_bar), 0);
+        Epi2 e;
+        e.D = g.D;
+        e.bias = g.bias;
+        e.R = g.R;
+        e.d_sm = g.d_sm;
+        e.r_sm = g.r_sm;
+        e.bias_sb = g.bias_sb;
+        e.M = g.M;
+        e.N = g.N;
+        e.bias_rows = g.bias_rows;
+        e.vec_ok = g.vec_ok;
+        e.alpha = g.alpha;
+        const float side_alpha = g.side_alpha;
+        const int side_r = g.side_r;
+        __nv_bfloat16* const T_out = g.T_out;
+        const long long t_ld = g.t_ld;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair; tile < total_tiles; tile += npairs) {
+            const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+            const int m_warp = m_blk * 256 + static_cast<int>(rank) * 128 + lane_base;
+            const int n0 = n_blk * BN;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + static_cast<uint32_t>(acc * 256);
+            if (side && half == 0) {
+                // ---- T-phase: this CTA's 128 rows of Tacc -> alpha, bf16 -> swizzled smem A operand (+ T_out) ----
+                mbar_wait(&side_full_bar[acc], acc_phase);
+                tc_fence_after();
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
+                              static_cast<uint32_t>(acc_stages == 1 ? 256 : acc * 256 + kSideCol), raw);
+                tmem_ld_wait();
+                const int row = lane_base + lane;
+                uint8_t* trow = smem + k2TOff + row * 128;
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(raw[2 * j]) * side_alpha,
+                                                                    __uint_as_float(raw[2 * j + 1]) * side_alpha);
+                    packed[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j * 8 < r16)
+                        *reinterpret_cast<uint4*>(trow + ((j ^ (row & 7)) * 16)) =
+                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(t_ready_leader);      // release.cluster: the leader's MMA reads this smem
+                // T also leaves for the dB / dA weight-gradient GEMM (after the hand-off: it is not on the critical path)
+                const int m = m_warp + lane;
+                if (n_blk == 0 && T_out != nullptr && m < e.M) {
+                    __nv_bfloat16* tp = T_out + static_cast<long long>(m) * t_ld;
+                    const __nv_bfloat16* pv = reinterpret_cast<const __nv_bfloat16*>(packed);
+                    if ((side_r & 7) == 0 && (t_ld & 7) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j * 8 < side_r)
+                                *reinterpret_cast<uint4*>(tp + j * 8) =
+                                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < side_r) tp[j] = pv[j];
+                    }
+                }
+            }
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                uint32_t raw[32];
+                tmem_ld32(taddr + c0, raw);
+                tmem_ld_wait();
+                if (n0 + c0 >= e.N) continue;          // warp-uniform
+                epi2_chunk<kEpi>(e, raw, stage_buf, lane, m_warp, n0 + c0, min(32, BN - c0));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_nofence(tmem_empty_leader + static_cast<uint32_t>(acc) * 8u);
+            if (++acc == acc_stages) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still read its smem / signal its barriers
+    if (warp == 1) tmem_dealloc2(tmem_base, 512);
+}
+
+}  // namespace b200

@@ -7,6 +7,7 @@
 #include <cudaTypedefs.h>
 #include "common.cuh"
 #include "gemm_tcgen05.cuh"
+#include "gemm2_tcgen05.cuh"
 #include "../../include/b200_lora.h"
 
 namespace b200 {
@@ -108,6 +109,132 @@ static long long* g_gemm_dbg = nullptr;
 // developer probe (not part of the public header): per-CTA globaltimer stamps of the next GEMM launches
 extern "C" void b200_debug_gemm_stamps(long long* dev_buf) { g_gemm_dbg = dev_buf; }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-pair kernel (gemm2_tcgen05.cuh): eligibility, tile width, launch
+// ---------------------------------------------------------------------------------------------------------
+static bool pair_eligible(const b200_gemm_t* d) {
+    if (d->conv || d->num_seg != 1 || d->nb0 != 1 || d->nb1 != 1 || d->splits != 1 || d->d_atomic) return false;
+    if (d->A[0].mn_major || d->d_sn != 1) return false;
+    if (d->M < 256 || d->N < 64 || d->K[0] < 64) return false;
+    if (d->R && d->r_sn != 1) return false;
+    return true;
+}
+
+// Estimated time of the pair kernel for tile width bn (seconds); drives the choice of bn and of the kernel.
+static double pair_cost(const b200_gemm_t* d, int bn, bool side) {
+    const long long tiles = static_cast<long long>((d->M + 255) / 256) * ((d->N + bn - 1) / bn);
+    const int pairs = kNumSMs / 2;
+    const long long waves = (tiles + pairs - 1) / pairs;
+    const double kblocks = (d->K[0] + 63) / 64;
+    const double active = tiles < pairs ? tiles : pairs;
+    const double t_mma = kblocks * 2.0 * bn / 1.8e9;                                    // 4 MMAs of bn/2 clocks per block
+    const double t_l2 = kblocks * (32768.0 + 128.0 * bn) * active / 11.0e12;            // L2 -> SM fabric shared by the pairs
+    const double t_tile = t_mma > t_l2 ? t_mma : t_l2;
+    const double t_epi = (bn / 64.0) * 0.55e-6 + 0.4e-6;
+    const bool single_acc = side && bn > kSideMaxBN;
+    return waves * t_tile + (single_acc ? waves : 1) * t_epi + 2.0e-6;
+}
+
+static int pick_pair_bn(const b200_gemm_t* d, double* cost_out) {
+    const bool side = d->side != 0;
+    const bool need64 = d->B[0].mn_major || (side && d->B2.mn_major);
+    int best = 0;
+    double best_cost = 1e30;
+    for (int bn = 256; bn >= 64; bn -= 32) {
+        if (need64 && (bn % 128)) continue;
+        if (bn > ((d->N + 31) / 32) * 32 && bn != 64 && !(need64 && bn == 128)) continue;   // wider than the problem
+        const double c = pair_cost(d, bn, side);
+        if (c < best_cost - 1e-12) {
+            best_cost = c;
+            best = bn;
+        }
+    }
+    if (cost_out) *cost_out = best_cost;
+    return best;
+}
+
+static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+        if (e != cudaSuccess) return set_error(3, "gemm2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const b200_operand_t& A = d->A[0];
+    const b200_operand_t& B = d->B[0];
+    const int K = d->K[0];
+    B200_CHECK_ARG(bn % 16 == 0 && bn >= 32 && bn <= 256, "gemm2: block_n %d must be a multiple of 16 in [32, 256]", bn);
+    B200_CHECK_ARG(!(B.mn_major || (d->side && d->B2.mn_major)) || bn % 128 == 0, "gemm2: MN-major B needs block_n 128 or 256");
+    B200_CHECK_ARG(A.inner >= K, "gemm2: A smaller than K");
+    Gemm2Args g;
+    memset(&g, 0, sizeof(g));
+    g.M = d->M;
+    g.N = d->N;
+    g.BN = bn;
+    g.tiles_n = (d->N + bn - 1) / bn;
+    g.total_tiles = ((d->M + 255) / 256) * g.tiles_n;
+    g.kblocks = (K + kBK - 1) / kBK;
+    g.ktail16 = (K - (g.kblocks - 1) * kBK + 15) / 16;
+    g.b_mn = B.mn_major;
+    {   // A: K-major [M, K], box 64 x 128.   B: K-major box 64 x bn/2, MN-major box 64 x 64
+        const long long dA[4] = {A.inner, A.rows, 1, 1}, sA[3] = {A.row_stride, 0, 0};
+        const int boxA[4] = {64, 128, 1, 1};
+        if (int rc = encode_map(&g.mapA, A.ptr, dA, sA, boxA)) return rc;
+        const long long dB[4] = {B.inner, B.rows, 1, 1}, sB[3] = {B.row_stride, 0, 0};
+        const int boxB[4] = {64, B.mn_major ? 64 : bn / 2, 1, 1};
+        if (int rc = encode_map(&g.mapB, B.ptr, dB, sB, boxB)) return rc;
+    }
+    int b_bytes = B.mn_major ? (bn / 128) * 8192 : (bn / 2) * 128;
+    int side_bytes = 0;
+    if (d->side) {
+        B200_CHECK_ARG(d->side_r >= 1 && d->side_r <= 32, "gemm2: side rank %d out of range", d->side_r);
+        g.side = 1;
+        g.side_r = d->side_r;
+        g.side_r16 = ((d->side_r + 15) / 16) * 16;
+        g.side_mn = d->S.mn_major;
+        g.b2_mn = d->B2.mn_major;
+        g.side_alpha = d->side_alpha;
+        g.T_out = static_cast<__nv_bfloat16*>(d->T_out);
+        g.t_ld = d->t_ld;
+        const long long dS[4] = {d->S.inner, d->S.rows, 1, 1}, sS[3] = {d->S.row_stride, 0, 0};
+        const int boxS[4] = {64, d->S.mn_major ? 64 : g.side_r16 / 2, 1, 1};
+        if (int rc = encode_map(&g.mapS, d->S.ptr, dS, sS, boxS)) return rc;
+        const long long dB2[4] = {d->B2.inner, d->B2.rows, 1, 1}, sB2[3] = {d->B2.row_stride, 0, 0};
+        const int boxB2[4] = {64, d->B2.mn_major ? 64 : bn / 2, 1, 1};
+        if (int rc = encode_map(&g.mapB2, d->B2.ptr, dB2, sB2, boxB2)) return rc;
+        const int b2_bytes = d->B2.mn_major ? (bn / 128) * 8192 : (bn / 2) * 128;
+        if (b2_bytes > b_bytes) b_bytes = b2_bytes;
+        side_bytes = d->S.mn_major ? 8192 : ((g.side_r16 / 2) * 128 + 1023) / 1024 * 1024;
+    }
+    b_bytes = (b_bytes + 1023) / 1024 * 1024;
+    g.side_off = b_bytes;
+    g.stage_bytes = k2ABytes + b_bytes + side_bytes;
+    g.num_stages = k2RingBytes / g.stage_bytes;
+    if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
+    g.acc_stages = (d->side && bn > kSideMaxBN) ? 1 : 2;
+    g.D = d->D;
+    g.d_sm = d->d_sm;
+    g.alpha = d->alpha;
+    g.bias = static_cast<const __nv_bfloat16*>(d->bias);
+    g.bias_rows = d->bias_rows;
+    g.bias_sb = d->bias_sb;
+    g.R = static_cast<const __nv_bfloat16*>(d->R);
+    g.r_sm = d->r_sm;
+    const int esz = d->d_fp32 ? 4 : 2;
+    g.vec_ok = (reinterpret_cast<uintptr_t>(d->D) % (4 * esz) == 0) && (d->d_sm % 4 == 0) &&
+               (!d->R || (reinterpret_cast<uintptr_t>(d->R) % 8 == 0 && d->r_sm % 4 == 0));
+    const int pairs = g.total_tiles < kNumSMs / 2 ? g.total_tiles : kNumSMs / 2;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t le;
+    if (d->d_fp32) le = launch_pdl_cluster(gemm2_kernel<1>, dim3(2 * pairs), dim3(k2Threads), k2SmemBytes, st, 2u, g);
+    else le = launch_pdl_cluster(gemm2_kernel<0>, dim3(2 * pairs), dim3(k2Threads), k2SmemBytes, st, 2u, g);
+    if (le != cudaSuccess) return set_error(3, "gemm2 launch: %s", cudaGetErrorString(le));
+    B200_CHECK_LAUNCH("gemm2_tcgen05");
+    return 0;
+}
+
 extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     B200_CHECK_ARG(d != nullptr, "gemm: null descriptor");
     B200_CHECK_ARG(d->M >= 1 && d->N >= 1, "gemm: empty problem M=%d N=%d", d->M, d->N);
@@ -116,6 +243,19 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     B200_CHECK_ARG(d->D != nullptr, "gemm: null output");
     B200_CHECK_ARG(!(d->d_atomic && !d->d_fp32), "gemm: atomic accumulation needs an fp32 output");
     B200_CHECK_ARG(d->splits == 1 || (d->d_atomic && d->num_seg == 1 && !d->conv), "gemm: split-K needs atomic fp32 output, one segment, no conv");
+
+    // CTA-pair kernel for the big plain projections (pair_mode: 0 auto, 1 force, -1 never)
+    static const int pair_env = getenv("B200_GEMM2") ? atoi(getenv("B200_GEMM2")) : 1;
+    if (d->pair_mode >= 0 && (pair_env || d->pair_mode > 0) && pair_eligible(d)) {
+        int bn2 = d->block_n;
+        if (bn2 <= 0) bn2 = pick_pair_bn(d, nullptr);
+        const bool bn_ok = bn2 >= 32 && bn2 % 16 == 0 && bn2 <= 256 &&
+                           (!(d->B[0].mn_major || (d->side && d->B2.mn_major)) || bn2 % 128 == 0);
+        if (bn_ok && (d->pair_mode > 0 || d->M * static_cast<long long>(d->N) >= 256LL * 512)) return launch_gemm2(d, bn2, stream);
+        B200_CHECK_ARG(d->pair_mode <= 0, "gemm: pair_mode forced but block_n %d is not usable by the pair kernel", bn2);
+    } else {
+        B200_CHECK_ARG(d->pair_mode <= 0, "gemm: pair_mode forced on a problem the pair kernel does not cover");
+    }
 
     static bool attr_set = false;
     if (!attr_set) {

@@ -88,7 +88,7 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
          bias: Optional[torch.Tensor] = None, bias_rows: int = 0, bias_sb: int = 0,
          residual: Optional[torch.Tensor] = None, r_strides: Optional[Tuple[int, int, int, int]] = None,
          nb0: int = 1, nb1: int = 1, splits: int = 1, atomic: bool = False, block_n: int = 0,
-         side: Optional[Tuple[Mat, Mat, int, float, Optional[torch.Tensor]]] = None) -> torch.Tensor:
+         side: Optional[Tuple[Mat, Mat, int, float, Optional[torch.Tensor]]] = None, pair_mode: int = 0) -> torch.Tensor:
     """out[b1][b0][m, n] = alpha * sum_seg A_seg.B_seg^T (+bias) (+residual).  segs: (A | Conv3x3, B, K).
     side = (S, B2, r, side_alpha, T_out): fused low-rank path  out += (side_alpha * A.S^T).B2^T, T_out <- the inner
     product (bf16) - see include/b200_lora.h."""
@@ -105,7 +105,7 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
         else:
             d.A[i] = a.c()
         d.B[i] = b.c()
-    d.nb0, d.nb1, d.splits, d.block_n = nb0, nb1, splits, block_n
+    d.nb0, d.nb1, d.splits, d.block_n, d.pair_mode = nb0, nb1, splits, block_n, pair_mode
     if side is not None:
         s_mat, b2_mat, r, s_alpha, t_out = side
         d.side, d.side_r, d.S, d.B2, d.side_alpha = 1, r, s_mat.c(), b2_mat.c(), s_alpha

@@ -1,0 +1,146 @@
+"""GPU parity of the CTA-pair (cta_group::2, 256-row tiles) GEMM against a plain torch fp32 reference, and against the
+single-CTA kernel on the same inputs.  Every case forces pair_mode=1 so the pair kernel is the one that runs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(BF)
+
+
+def _close(out, ref, tol=2e-2, what=""):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs().max().item()
+    den = ref.abs().max().item() + 1e-6
+    assert err / den < tol, f"{what}: max abs err {err:.4g} vs max ref {den:.4g}"
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (256, 256, 128), (300, 200, 136), (2048, 1280, 1280), (2048, 10240, 1280),
+                                   (8192, 640, 640), (4096, 5120, 640), (257, 72, 1000), (1000, 1000, 72)])
+def test_pair_plain_kmajor(M, N, K):
+    from sd_lora_trainer_b200 import ops
+    a, b = _rand(M, K), _rand(N, K, seed=1)
+    out = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(out, M, N, [(ops.kmajor(a), ops.kmajor(b), K)], pair_mode=1)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ b.float().T, what=f"pair plain {M}x{N}x{K}")
+    # bit-level agreement with the single-CTA kernel is not required (different summation grouping), closeness is
+    ref1 = torch.empty_like(out)
+    ops.gemm(ref1, M, N, [(ops.kmajor(a), ops.kmajor(b), K)], pair_mode=-1)
+    _close(out, ref1, tol=1e-2, what="pair vs single-CTA")
+
+
+@pytest.mark.parametrize("bn", [32, 64, 96, 128, 160, 192, 224, 256])
+def test_pair_block_n_sweep(bn):
+    from sd_lora_trainer_b200 import ops
+    M, N, K = 640, 528, 192
+    a, b = _rand(M, K), _rand(N, K, seed=1)
+    out = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(out, M, N, [(ops.kmajor(a), ops.kmajor(b), K)], block_n=bn, pair_mode=1)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ b.float().T, what=f"pair bn={bn}")
+
+
+def test_pair_epilogue_alpha_bias_residual_fp32():
+    from sd_lora_trainer_b200 import ops
+    M, N, K = 300, 200, 136
+    a, b, bias, res = _rand(M, K), _rand(N, K, seed=1), _rand(N, seed=2), _rand(M, N, seed=3)
+    ref = 0.5 * (a.float() @ b.float().T) + bias.float() + res.float()
+    out = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(out, M, N, [(ops.kmajor(a), ops.kmajor(b), K)], alpha=0.5, bias=bias, residual=res, pair_mode=1)
+    _close(out, ref, what="pair bf16 epilogue")
+    out32 = torch.empty(M, N, dtype=torch.float32, device="cuda")
+    ops.gemm(out32, M, N, [(ops.kmajor(a), ops.kmajor(b), K)], alpha=0.5, bias=bias, residual=res, pair_mode=1)
+    _close(out32, ref, tol=5e-3, what="pair fp32 epilogue")
+    bias2 = _rand(3, N, seed=4)
+    ops.gemm(out, M, N, [(ops.kmajor(a), ops.kmajor(b), K)], bias=bias2, bias_rows=100, bias_sb=N, pair_mode=1)
+    ref2 = a.float() @ b.float().T + bias2.float().repeat_interleave(100, 0)
+    _close(out, ref2, what="pair row-batched bias")
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 640, 320), (2048, 1280, 1280), (2048, 1280, 10240), (300, 264, 200), (8192, 640, 5120)])
+def test_pair_b_mn_major_dgrad(M, N, K):
+    """dX[M, K_out] = dY[M, N] . W[N, K_out]: the frozen weight read MN-major (forward layout)."""
+    from sd_lora_trainer_b200 import ops
+    dy, w = _rand(M, N), _rand(N, K, seed=1, scale=0.05)
+    dx = torch.empty(M, K, dtype=BF, device="cuda")
+    ops.gemm(dx, M, K, [(ops.kmajor(dy), ops.mnmajor(w), N)], pair_mode=1)
+    _close(dx, dy.float() @ w.float(), what=f"pair dgrad {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K,r", [(256, 128, 128, 16), (2048, 1280, 1280, 16), (300, 640, 320, 8), (2048, 640, 2048, 32),
+                                     (1000, 200, 136, 4), (8192, 640, 640, 16), (4096, 2560, 640, 16)])
+def test_pair_fused_side_path_forward(M, N, K, r):
+    """Y = X.W^T + (s.X.A^T).B^T as ONE launch on CTA pairs (incl. the single-accumulator BN = 256 configuration)."""
+    from sd_lora_trainer_b200 import ops
+    rs = (r + 7) // 8 * 8
+    x, w = _rand(M, K), _rand(N, K, seed=1, scale=0.05)
+    A = _rand(r, K, seed=2, scale=0.1)
+    Bp = torch.zeros(N, rs, dtype=BF, device="cuda")
+    Bp[:, :r] = _rand(N, r, seed=3, scale=0.1)
+    bias, res = _rand(N, seed=4), _rand(M, N, seed=5)
+    T = torch.full((M, rs), 7.0, dtype=BF, device="cuda")
+    y = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(y, M, N, [(ops.kmajor(x), ops.kmajor(w), K)], bias=bias, residual=res,
+             side=(ops.Mat(A, r, K, K), ops.Mat(Bp, N, r, rs), r, 0.5, T), pair_mode=1)
+    Tref = (0.5 * (x.float() @ A.float().T)).to(BF)
+    _close(T[:, :r], Tref, what="pair T out")
+    ref = x.float() @ w.float().T + Tref.float() @ Bp[:, :r].float().T + bias.float() + res.float()
+    _close(y, ref, what="pair fused side fwd")
+
+
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+def test_pair_fused_side_block_n(bn):
+    from sd_lora_trainer_b200 import ops
+    M, N, K, r = 1024, 768, 256, 16
+    x, w = _rand(M, K), _rand(N, K, seed=1, scale=0.05)
+    A, Bm = _rand(r, K, seed=2, scale=0.1), _rand(N, r, seed=3, scale=0.1)
+    T = torch.empty(M, r, dtype=BF, device="cuda")
+    y = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(y, M, N, [(ops.kmajor(x), ops.kmajor(w), K)], side=(ops.Mat(A, r, K, K), ops.Mat(Bm, N, r, r), r, 1.0, T),
+             block_n=bn, pair_mode=1)
+    Tref = (x.float() @ A.float().T).to(BF)
+    _close(T, Tref, what=f"pair T bn={bn}")
+    _close(y, x.float() @ w.float().T + Tref.float() @ Bm.float().T, what=f"pair side bn={bn}")
+
+
+@pytest.mark.parametrize("M,N,K,r", [(512, 640, 320, 16), (2048, 1280, 1280, 16), (300, 264, 200, 8), (2048, 1280, 1280, 32),
+                                     (333, 128, 96, 4), (8192, 640, 640, 16)])
+def test_pair_fused_side_path_dgrad(M, N, K, r):
+    """dX[M, K] = dY.W + (s.dY.B).A as ONE launch on CTA pairs; every operand read MN-major from its forward layout."""
+    from sd_lora_trainer_b200 import ops
+    rs = (r + 7) // 8 * 8
+    dy, w = _rand(M, N), _rand(N, K, seed=1, scale=0.05)
+    A = _rand(r, K, seed=2, scale=0.1)
+    Bp = torch.zeros(N, rs, dtype=BF, device="cuda")
+    Bp[:, :r] = _rand(N, r, seed=3, scale=0.1)
+    acc = _rand(M, K, seed=6)
+    U = torch.empty(M, rs, dtype=BF, device="cuda")
+    dx = acc.clone()
+    ops.gemm(dx, M, K, [(ops.kmajor(dy), ops.mnmajor(w), N)], residual=dx,
+             side=(ops.Mat(Bp, N, r, rs, mn=True), ops.Mat(A, r, K, K, mn=True), r, 2.0, U), pair_mode=1)
+    Uref = (2.0 * (dy.float() @ Bp[:, :r].float())).to(BF)
+    _close(U[:, :r], Uref, what="pair U out")
+    _close(dx, dy.float() @ w.float() + Uref.float() @ A.float() + acc.float(), what="pair fused side dgrad")
+
+
+def test_pair_back_to_back_launches_are_ordered():
+    """Programmatic dependent launch + clusters: a chain of dependent GEMMs (each reads the previous output)."""
+    from sd_lora_trainer_b200 import ops
+    M, C = 2048, 1280
+    x = _rand(M, C, scale=0.5)
+    ws = [_rand(C, C, seed=10 + i, scale=0.03) for i in range(6)]
+    cur = x
+    ref = x.float()
+    for w in ws:
+        nxt = torch.empty(M, C, dtype=BF, device="cuda")
+        ops.gemm(nxt, M, C, [(ops.kmajor(cur), ops.kmajor(w), C)], pair_mode=1)
+        ref = (ref @ w.float().T).to(BF).float()
+        cur = nxt
+    torch.cuda.synchronize()
+    _close(cur, ref, tol=3e-2, what="pair chain")
