@@ -16,6 +16,7 @@ Parameter names follow diffusers / PEFT so reference checkpoints load unchanged.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -30,6 +31,40 @@ _SMS = 148
 
 def _r8(n: int) -> int:
     return (n + 7) // 8 * 8
+
+
+class _WgradLane:
+    """The LoRA weight-gradient GEMMs (dA, dB) are skinny, launch-latency-bound and feed nothing but the optimizer, so
+    they run on a second stream: inside the step's CUDA graph that is a fork per layer and ONE join at the end of the
+    backward, and they fill the SMs the CTA-pair GEMMs of the main chain leave idle.  Operands are kept alive until
+    the join (the caching allocator must not hand their memory to the main stream while the side stream reads it)."""
+
+    def __init__(self):
+        self.stream: Optional[torch.cuda.Stream] = None
+        self.keep: List[torch.Tensor] = []
+
+    def begin(self, enabled: bool):
+        self.keep = []
+        self.stream = torch.cuda.Stream() if (enabled and torch.cuda.is_available()) else None
+
+    def run(self, fn, *operands):
+        """fn() launches the weight-gradient GEMMs; everything they read was produced on the current stream."""
+        if self.stream is None:
+            fn()
+            return
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(t for t in operands if t is not None)
+
+    def join(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.keep = []
+        self.stream = None
+
+
+WGRAD = _WgradLane()
 
 
 def _wgrad_splits(out_rows: int, reduce_len: int) -> int:
@@ -187,10 +222,12 @@ class Lin:
             ops.gemm(dx, M, self.K, [(kmajor(dy), mnmajor(self.W), self.N)], residual=accum, side=side)
         if lo is not None:
             # dB[N, r] += dY^T . T      dA[r, K] += U^T . X   (both operands MN-major, split-K fp32 atomics)
-            ops.gemm(lo.gB(), self.N, r, [(Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(T, M, r, rs, mn=True), M)],
-                     d_strides=(rs, 1, 0, 0), splits=_wgrad_splits(self.N, M), atomic=True)
-            ops.gemm(lo.gA(), self.K, r, [(Mat(x, M, self.K, x.stride(0), mn=True), Mat(U, M, r, rs, mn=True), M)],
-                     d_strides=(1, self.K, 0, 0), splits=_wgrad_splits(self.K, M), atomic=True)
+            def wgrad():
+                ops.gemm(lo.gB(), self.N, r, [(Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(T, M, r, rs, mn=True), M)],
+                         d_strides=(rs, 1, 0, 0), splits=_wgrad_splits(self.N, M), atomic=True)
+                ops.gemm(lo.gA(), self.K, r, [(Mat(x, M, self.K, x.stride(0), mn=True), Mat(U, M, r, rs, mn=True), M)],
+                         d_strides=(1, self.K, 0, 0), splits=_wgrad_splits(self.K, M), atomic=True)
+            WGRAD.run(wgrad, dy, T, x, U)
         return dx
 
 
@@ -759,6 +796,7 @@ class UNetB200:
         dev = dpred8.device
         d_ctx = torch.zeros(B * Lctx, Dc, dtype=BF16, device=dev)
         d_temb_act = torch.zeros(B, a.time_embed_dim, dtype=BF16, device=dev)
+        WGRAD.begin(os.environ.get("B200_WGRAD_STREAM", "1") != "0" and dev.type == "cuda")
         # hooked layers were enumerated down_blocks..., up_blocks...; backward visits up (reversed) then down (reversed)
         n_down_hooks = sum(len(t.blocks) for rs, at, ds in self.down if at is not None for t in at)
         ds_down = list(dscores[:n_down_hooks]) if dscores is not None else None
@@ -807,4 +845,5 @@ class UNetB200:
             d_add_in = self.add1.bwd(da1)
             d_text = d_add_in[:, :a.projection_class_embeddings_input_dim - 6 * a.addition_time_embed_dim].contiguous()
         self.time1.x = self.time2.x = None
+        WGRAD.join()                                 # every dA / dB has landed in store.grads before the optimizer
         return d_ctx.view(B, Lctx, Dc), d_text
