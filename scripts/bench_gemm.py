@@ -62,6 +62,27 @@ def main():
             t = graph_time(lambda: ops.gemm(out, M, N, [(ops.kmajor(a), ops.kmajor(b), K)], pair_mode=1, block_n=bn))
             rows.append({"kind": "pair_bn_sweep", "M": M, "N": N, "K": K, "bn": bn, "us": round(t, 2)})
             print(json.dumps(rows[-1]), flush=True)
+    if pair_ok:
+        # where does the MN-major (dgrad) form lose time?  plain K-major vs plain MN-major B at the same tile width
+        M, N, K = 2048, 1280, 1280
+        a, w, out = r(M, K), r(N, K), torch.empty(M, N, dtype=BF, device=dev)
+        for bn in (128, 256):
+            tk = graph_time(lambda: ops.gemm(out, M, N, [(ops.kmajor(a), ops.kmajor(w), K)], pair_mode=1, block_n=bn))
+            tm = graph_time(lambda: ops.gemm(out, M, N, [(ops.kmajor(a), ops.mnmajor(w), K)], pair_mode=1, block_n=bn))
+            rows.append({"kind": "pair_major", "bn": bn, "b_kmajor_us": round(tk, 2), "b_mnmajor_us": round(tm, 2)})
+            print(json.dumps(rows[-1]), flush=True)
+        rr = 16
+        A, Bm, T = r(rr, K), r(N, rr), torch.empty(M, rr, dtype=BF, device=dev)
+        for bn in (128, 192, 224, 256):
+            t = graph_time(lambda: ops.gemm(out, M, N, [(ops.kmajor(a), ops.kmajor(w), K)], pair_mode=1, block_n=bn,
+                                            side=(ops.Mat(A, rr, K, K), ops.Mat(Bm, N, rr, rr), rr, 1.0, T)))
+            rows.append({"kind": "pair_side_fwd_bn", "bn": bn, "us": round(t, 2)})
+            print(json.dumps(rows[-1]), flush=True)
+        for bn in (128, 256):
+            t = graph_time(lambda: ops.gemm(out, M, K, [(ops.kmajor(a), ops.mnmajor(w), N)], pair_mode=1, block_n=bn,
+                                            side=(ops.Mat(Bm, N, rr, rr, mn=True), ops.Mat(A, rr, K, K, mn=True), rr, 1.0, T)))
+            rows.append({"kind": "pair_side_dgrad_bn", "bn": bn, "us": round(t, 2)})
+            print(json.dumps(rows[-1]), flush=True)
     for M, N, K, rr in [(2048, 1280, 1280, 16), (8192, 640, 640, 16)]:
         x, w, A, Bm = r(M, K), r(N, K), r(rr, K), r(N, rr)
         T, y = torch.empty(M, rr, dtype=BF, device=dev), torch.empty(M, N, dtype=BF, device=dev)

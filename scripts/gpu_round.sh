@@ -31,6 +31,11 @@ if [ "${SKIP_BENCH:-0}" != "1" ]; then
   echo "bench exit $?"; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 fi
 
+if [ "${AB_WGRAD:-0}" == "1" ]; then
+  B200_WGRAD_STREAM=0 timeout 600 python bench.py --steps 10 --warmup 3 --skip-cpu --skip-roofline > gpurun_out/bench_wgrad_inline.json 2> gpurun_out/bench_wgrad_inline.err
+  echo "bench (weight-gradient GEMMs inline) exit $?"; cat gpurun_out/bench_wgrad_inline.json; tail -3 gpurun_out/bench_wgrad_inline.err
+fi
+
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   # launch list of ONE eager step: bench.py --profile-step brackets it with cudaProfilerStart/Stop
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off \

@@ -43,13 +43,17 @@ struct Gemm2Args {
     int b_mn, side, side_mn, b2_mn, side_r16, side_r;
     int stage_bytes, num_stages, side_off, acc_stages;
     int vec_ok, bias_rows;
+    // implicit 3x3 / pad 1 / stride 1 convolution on segment 0's A operand (NHWC; mapA dims C, W, H, N)
+    int conv, conv_cblocks, conv_W, conv_H, b_tap_k, b_tap_n;
+    // optional second K segment accumulated into the same tile: plain K-major A2 [M, K2], B2 via mapB2 / b2_mn
+    int nseg, kblocks2, ktail16_2;
     float alpha, side_alpha;
     long long d_sm, r_sm, t_ld, bias_sb;
     void* D;
     const __nv_bfloat16* bias;
     const __nv_bfloat16* R;
     __nv_bfloat16* T_out;
-    CUtensorMap mapA, mapB, mapS, mapB2;
+    CUtensorMap mapA, mapB, mapS, mapB2, mapA2;
 };
 
 struct Epi2 {
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     const int num_stages = g.num_stages, stage_bytes = g.stage_bytes, acc_stages = g.acc_stages;
     const int side = g.side, side_off = g.side_off, r16 = g.side_r16;
     const int b_mn = g.b_mn, side_mn = g.side_mn, b2_mn = g.b2_mn;
+    const int conv = g.conv, nseg = g.nseg, kblocks2 = g.kblocks2;
     const int npairs = static_cast<int>(gridDim.x >> 1), pair = static_cast<int>(blockIdx.x >> 1);
 
     if (warp == 0 && lane == 0) {
@@ -166,6 +171,10 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
         tma_prefetch_desc(&g.mapB);
         if (side) {
             tma_prefetch_desc(&g.mapS);
+            tma_prefetch_desc(&g.mapB2);
+        }
+        if (nseg == 2) {
+            tma_prefetch_desc(&g.mapA2);
             tma_prefetch_desc(&g.mapB2);
         }
         for (int i = 0; i < num_stages; ++i) {
@@ -205,28 +214,73 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             const uint32_t tx = 2u * (static_cast<uint32_t>(k2ABytes) + b_bytes + s_bytes);
             const uint32_t b2_bytes = b2_mn ? static_cast<uint32_t>(b_boxes) * 8192u : static_cast<uint32_t>(bn_half) * 128u;
             const int s_row = static_cast<int>(rank) * sr_half;
+            const int conv_H = g.conv_H, conv_W = g.conv_W, conv_cblocks = g.conv_cblocks;
+            const int conv_tap_k = g.b_tap_k, conv_tap_n = g.b_tap_n;
             for (int tile = pair; tile < total_tiles; tile += npairs) {
                 const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
                 const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
                 const int nh0 = n_blk * BN + static_cast<int>(rank) * bn_half;
-                int k = 0;
-                for (int kb = 0; kb < kblocks; ++kb, k += kBK) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
-                    uint8_t* sa = smem + stage * stage_bytes;
-                    uint8_t* sb = sa + k2ABytes;
-                    const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
-                    tma2_load_4d(sa, &g.mapA, fb, k, m0, 0, 0);
-                    if (!b_mn) {
-                        tma2_load_4d(sb, &g.mapB, fb, k, nh0, 0, 0);
-                    } else {
-                        for (int jb = 0; jb < b_boxes; ++jb) tma2_load_4d(sb + jb * 8192, &g.mapB, fb, nh0 + jb * 64, k, 0, 0);
+                if (conv) {
+                    // implicit im2col: one box per (tap, 64-channel block) with shifted coordinates; TMA zero-fills the halo
+                    const int hw = conv_H * conv_W;
+                    const int cn0 = m0 / hw, ch0 = (m0 - cn0 * hw) / conv_W;
+                    int cb = 0, kw = 0, kh = 0, bk_tap = 0, bn_tap = 0;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+                        uint8_t* sa = smem + stage * stage_bytes;
+                        const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+                        tma2_load_4d(sa, &g.mapA, fb, cb * kBK, kw - 1, ch0 + kh - 1, cn0);
+                        tma2_load_4d(sa + k2ABytes, &g.mapB, fb, bk_tap + cb * kBK, nh0 + bn_tap, 0, 0);
+                        if (++cb == conv_cblocks) {
+                            cb = 0;
+                            bk_tap += conv_tap_k;
+                            bn_tap += conv_tap_n;
+                            if (++kw == 3) {
+                                kw = 0;
+                                ++kh;
+                            }
+                        }
+                        advance_stage(stage, phase, num_stages);
                     }
-                    if (side) {
-                        if (side_mn) tma2_load_4d(sb + side_off, &g.mapS, fb, s_row, k, 0, 0);
-                        else tma2_load_4d(sb + side_off, &g.mapS, fb, k, s_row, 0, 0);
+                } else {
+                    int k = 0;
+                    for (int kb = 0; kb < kblocks; ++kb, k += kBK) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
+                        uint8_t* sa = smem + stage * stage_bytes;
+                        uint8_t* sb = sa + k2ABytes;
+                        const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+                        tma2_load_4d(sa, &g.mapA, fb, k, m0, 0, 0);
+                        if (!b_mn) {
+                            tma2_load_4d(sb, &g.mapB, fb, k, nh0, 0, 0);
+                        } else {
+                            for (int jb = 0; jb < b_boxes; ++jb) tma2_load_4d(sb + jb * 8192, &g.mapB, fb, nh0 + jb * 64, k, 0, 0);
+                        }
+                        if (side) {
+                            if (side_mn) tma2_load_4d(sb + side_off, &g.mapS, fb, s_row, k, 0, 0);
+                            else tma2_load_4d(sb + side_off, &g.mapS, fb, k, s_row, 0, 0);
+                        }
+                        advance_stage(stage, phase, num_stages);
                     }
-                    advance_stage(stage, phase, num_stages);
+                }
+                if (nseg == 2) {
+                    // second K segment (conv-LoRA side products): plain K-major A2, B2 K- or MN-major
+                    int k = 0;
+                    for (int kb = 0; kb < kblocks2; ++kb, k += kBK) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (static_cast<uint32_t>(k2ABytes) + b2_bytes));
+                        uint8_t* sa = smem + stage * stage_bytes;
+                        uint8_t* sb = sa + k2ABytes;
+                        const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+                        tma2_load_4d(sa, &g.mapA2, fb, k, m0, 0, 0);
+                        if (!b2_mn) {
+                            tma2_load_4d(sb, &g.mapB2, fb, k, nh0, 0, 0);
+                        } else {
+                            for (int jb = 0; jb < b_boxes; ++jb) tma2_load_4d(sb + jb * 8192, &g.mapB2, fb, nh0 + jb * 64, k, 0, 0);
+                        }
+                        advance_stage(stage, phase, num_stages);
+                    }
                 }
                 if (side) {
                     // one more ring slot per tile: this CTA's half of the B2 tile for the final rank-r MMA
@@ -259,7 +313,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             const uint64_t s_hi = umma_desc(0, side_mn ? 8192u : 16u, 1024);
             const uint64_t b2_hi = umma_desc(0, b2_mn ? 8192u : 16u, 1024);
             const uint64_t b_step = b_mn ? 128u : 2u, s_step = side_mn ? 128u : 2u, b2_step = b2_mn ? 128u : 2u;
-            const int ktail = g.ktail16;
+            const int ktail = g.ktail16, ktail2 = g.ktail16_2;
             for (int tile = pair; tile < total_tiles; tile += npairs) {
                 mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -288,6 +342,24 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     __syncwarp();
                     accum = 1;
                     advance_stage(stage, phase, num_stages);
+                }
+                if (nseg == 2) {
+                    for (int kb = 0; kb < kblocks2; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t sa = smem_base + static_cast<uint32_t>(stage * stage_bytes);
+                            const uint64_t ad = a_hi | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
+                            const uint64_t bd = b2_hi | static_cast<uint64_t>(((sa + k2ABytes) & 0x3FFFF) >> 4);
+                            const int n16 = (kb == kblocks2 - 1) ? ktail2 : 4;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (k < n16) umma2_bf16(tmem_d, ad + 2u * k, bd + b2_step * k, idesc_2, 1);
+                            umma2_commit_mc(&empty_bar[stage]);
+                        }
+                        __syncwarp();
+                        advance_stage(stage, phase, num_stages);
+                    }
                 }
                 if (side) {
                     if (leader) umma2_commit_mc(&side_full_bar[acc]);     // rank-r accumulator complete -> T-phase

@@ -113,10 +113,25 @@ extern "C" void b200_debug_gemm_stamps(long long* dev_buf) { g_gemm_dbg = dev_bu
 // ---------------------------------------------------------------------------------------------------------
 // CTA-pair kernel (gemm2_tcgen05.cuh): eligibility, tile width, launch
 // ---------------------------------------------------------------------------------------------------------
+static int pair_k0(const b200_gemm_t* d) { return d->conv ? 9 * ((d->conv_C + 63) / 64) * 64 : d->K[0]; }
+
 static bool pair_eligible(const b200_gemm_t* d) {
-    if (d->conv || d->num_seg != 1 || d->nb0 != 1 || d->nb1 != 1 || d->splits != 1 || d->d_atomic) return false;
-    if (d->A[0].mn_major || d->d_sn != 1) return false;
-    if (d->M < 256 || d->N < 64 || d->K[0] < 64) return false;
+    if (d->nb0 != 1 || d->nb1 != 1 || d->splits != 1 || d->d_atomic || d->d_sn != 1) return false;
+    if (d->num_seg < 1 || d->num_seg > 2 || (d->side && (d->num_seg != 1 || d->conv))) return false;
+    if (d->conv) {
+        const int W = d->conv_W, H = d->conv_H;
+        if (d->B[0].mn_major || W < 1 || W > 128 || 128 % W) return false;
+        int bh = 128 / W;
+        if (bh > H) bh = H;
+        if (H % bh || 128 % (W * bh)) return false;
+        const int bimg = 128 / (W * bh);
+        if (!(bimg == 1 || bh == H) || d->conv_C % 8) return false;
+        if (static_cast<long long>(d->conv_N) * H * W != d->M) return false;
+    } else if (d->A[0].mn_major) {
+        return false;
+    }
+    if (d->num_seg == 2 && (d->A[1].mn_major || d->A[1].batched || d->B[1].batched)) return false;
+    if (d->M < 256 || d->N < 64 || pair_k0(d) < 64) return false;
     if (d->R && d->r_sn != 1) return false;
     return true;
 }
@@ -126,7 +141,7 @@ static double pair_cost(const b200_gemm_t* d, int bn, bool side) {
     const long long tiles = static_cast<long long>((d->M + 255) / 256) * ((d->N + bn - 1) / bn);
     const int pairs = kNumSMs / 2;
     const long long waves = (tiles + pairs - 1) / pairs;
-    const double kblocks = (d->K[0] + 63) / 64;
+    const double kblocks = (pair_k0(d) + 63) / 64 + (d->num_seg == 2 ? (d->K[1] + 63) / 64 : 0);
     const double active = tiles < pairs ? tiles : pairs;
     const double t_mma = kblocks * 2.0 * bn / 1.8e9;                                    // 4 MMAs of bn/2 clocks per block
     const double t_l2 = kblocks * (32768.0 + 128.0 * bn) * active / 11.0e12;            // L2 -> SM fabric shared by the pairs
@@ -138,7 +153,7 @@ static double pair_cost(const b200_gemm_t* d, int bn, bool side) {
 
 static int pick_pair_bn(const b200_gemm_t* d, double* cost_out) {
     const bool side = d->side != 0;
-    const bool need64 = d->B[0].mn_major || (side && d->B2.mn_major);
+    const bool need64 = d->B[0].mn_major || (side && d->B2.mn_major) || (d->num_seg == 2 && d->B[1].mn_major);
     int best = 0;
     double best_cost = 1e30;
     for (int bn = 256; bn >= 64; bn -= 32) {
@@ -165,9 +180,10 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
     const b200_operand_t& A = d->A[0];
     const b200_operand_t& B = d->B[0];
     const int K = d->K[0];
+    const bool seg2 = d->num_seg == 2;
     B200_CHECK_ARG(bn % 16 == 0 && bn >= 32 && bn <= 256, "gemm2: block_n %d must be a multiple of 16 in [32, 256]", bn);
-    B200_CHECK_ARG(!(B.mn_major || (d->side && d->B2.mn_major)) || bn % 128 == 0, "gemm2: MN-major B needs block_n 128 or 256");
-    B200_CHECK_ARG(A.inner >= K, "gemm2: A smaller than K");
+    B200_CHECK_ARG(!(B.mn_major || (d->side && d->B2.mn_major) || (seg2 && d->B[1].mn_major)) || bn % 128 == 0,
+                   "gemm2: MN-major B needs block_n 128 or 256");
     Gemm2Args g;
     memset(&g, 0, sizeof(g));
     g.M = d->M;
@@ -175,19 +191,57 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
     g.BN = bn;
     g.tiles_n = (d->N + bn - 1) / bn;
     g.total_tiles = ((d->M + 255) / 256) * g.tiles_n;
-    g.kblocks = (K + kBK - 1) / kBK;
-    g.ktail16 = (K - (g.kblocks - 1) * kBK + 15) / 16;
     g.b_mn = B.mn_major;
-    {   // A: K-major [M, K], box 64 x 128.   B: K-major box 64 x bn/2, MN-major box 64 x 64
+    g.nseg = d->num_seg;
+    if (d->conv) {
+        const int W = d->conv_W, H = d->conv_H, C = d->conv_C;
+        int bh = 128 / W;
+        if (bh > H) bh = H;
+        const int bimg = 128 / (W * bh);
+        const long long dims[4] = {C, W, H, d->conv_N};
+        const long long strides[3] = {C, static_cast<long long>(W) * C, static_cast<long long>(H) * W * C};
+        const int box[4] = {64, W, bh, bimg};
+        if (int rc = encode_map(&g.mapA, A.ptr, dims, strides, box)) return rc;
+        g.conv = 1;
+        g.conv_cblocks = (C + kBK - 1) / kBK;
+        g.conv_W = W;
+        g.conv_H = H;
+        g.b_tap_k = d->b_tap_k;
+        g.b_tap_n = d->b_tap_n;
+        g.kblocks = 9 * g.conv_cblocks;
+        g.ktail16 = 4;                       // channel tails are zero-filled by TMA on the A side
+    } else {
+        B200_CHECK_ARG(A.inner >= K, "gemm2: A smaller than K");
         const long long dA[4] = {A.inner, A.rows, 1, 1}, sA[3] = {A.row_stride, 0, 0};
         const int boxA[4] = {64, 128, 1, 1};
         if (int rc = encode_map(&g.mapA, A.ptr, dA, sA, boxA)) return rc;
+        g.kblocks = (K + kBK - 1) / kBK;
+        g.ktail16 = (K - (g.kblocks - 1) * kBK + 15) / 16;
+    }
+    {   // B: K-major box 64 x bn/2, MN-major box 64 x 64
         const long long dB[4] = {B.inner, B.rows, 1, 1}, sB[3] = {B.row_stride, 0, 0};
         const int boxB[4] = {64, B.mn_major ? 64 : bn / 2, 1, 1};
         if (int rc = encode_map(&g.mapB, B.ptr, dB, sB, boxB)) return rc;
     }
     int b_bytes = B.mn_major ? (bn / 128) * 8192 : (bn / 2) * 128;
     int side_bytes = 0;
+    if (seg2) {
+        const b200_operand_t& A2 = d->A[1];
+        const b200_operand_t& Bs = d->B[1];
+        const int K2 = d->K[1];
+        B200_CHECK_ARG(K2 >= 1 && A2.inner >= K2, "gemm2: segment 1 A smaller than K");
+        const long long dA2[4] = {A2.inner, A2.rows, 1, 1}, sA2[3] = {A2.row_stride, 0, 0};
+        const int boxA2[4] = {64, 128, 1, 1};
+        if (int rc = encode_map(&g.mapA2, A2.ptr, dA2, sA2, boxA2)) return rc;
+        const long long dB2[4] = {Bs.inner, Bs.rows, 1, 1}, sB2[3] = {Bs.row_stride, 0, 0};
+        const int boxB2[4] = {64, Bs.mn_major ? 64 : bn / 2, 1, 1};
+        if (int rc = encode_map(&g.mapB2, Bs.ptr, dB2, sB2, boxB2)) return rc;
+        g.b2_mn = Bs.mn_major;
+        g.kblocks2 = (K2 + kBK - 1) / kBK;
+        g.ktail16_2 = (K2 - (g.kblocks2 - 1) * kBK + 15) / 16;
+        const int b2_bytes = Bs.mn_major ? (bn / 128) * 8192 : (bn / 2) * 128;
+        if (b2_bytes > b_bytes) b_bytes = b2_bytes;
+    }
     if (d->side) {
         B200_CHECK_ARG(d->side_r >= 1 && d->side_r <= 32, "gemm2: side rank %d out of range", d->side_r);
         g.side = 1;
@@ -250,7 +304,8 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
         int bn2 = d->block_n;
         if (bn2 <= 0) bn2 = pick_pair_bn(d, nullptr);
         const bool bn_ok = bn2 >= 32 && bn2 % 16 == 0 && bn2 <= 256 &&
-                           (!(d->B[0].mn_major || (d->side && d->B2.mn_major)) || bn2 % 128 == 0);
+                           (!(d->B[0].mn_major || (d->side && d->B2.mn_major) || (d->num_seg == 2 && d->B[1].mn_major)) ||
+                            bn2 % 128 == 0);
         if (bn_ok && (d->pair_mode > 0 || d->M * static_cast<long long>(d->N) >= 256LL * 512)) return launch_gemm2(d, bn2, stream);
         B200_CHECK_ARG(d->pair_mode <= 0, "gemm: pair_mode forced but block_n %d is not usable by the pair kernel", bn2);
     } else {

@@ -144,3 +144,55 @@ def test_pair_back_to_back_launches_are_ordered():
         cur = nxt
     torch.cuda.synchronize()
     _close(cur, ref, tol=3e-2, what="pair chain")
+
+
+@pytest.mark.parametrize("N,H,W,C,Cout", [(2, 16, 16, 64, 128), (2, 32, 32, 320, 320), (2, 128, 128, 64, 64), (2, 64, 64, 8, 320),
+                                          (1, 32, 32, 192, 96), (4, 8, 8, 128, 640), (2, 32, 32, 1280, 1280)])
+def test_pair_implicit_conv3x3(N, H, W, C, Cout):
+    import torch.nn.functional as F
+    from sd_lora_trainer_b200 import ops
+    x = _rand(N * H * W, C)
+    w = _rand(Cout, C, 3, 3, seed=1, scale=0.05)
+    bias = _rand(Cout, seed=2)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()          # [Cout, (kh, kw, c)]
+    out = torch.empty(N * H * W, Cout, dtype=BF, device="cuda")
+    ops.gemm(out, N * H * W, Cout, [(ops.Conv3x3(x, N, H, W, C, b_tap_k=C), ops.kmajor(wk), 9 * C)], bias=bias, pair_mode=1)
+    xn = x.float().view(N, H, W, C).permute(0, 3, 1, 2)
+    ref = F.conv2d(xn, w.float(), bias.float(), padding=1).permute(0, 2, 3, 1).reshape(N * H * W, Cout)
+    _close(out, ref, what=f"pair conv {N}x{H}x{W}x{C}->{Cout}")
+
+
+def test_pair_conv_plus_lora_segment_and_dgrad_extra():
+    """conv2(x) + T.B^T (segment 1 K-major) and the dgrad form  conv_T(dy) + U9.A  (segment 1 with an MN-major B)."""
+    import torch.nn.functional as F
+    from sd_lora_trainer_b200 import ops
+    N, H, W, C, Cout, r = 2, 32, 32, 128, 256, 16
+    M = N * H * W
+    x = _rand(M, C)
+    w = _rand(Cout, C, 3, 3, seed=1, scale=0.05)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()
+    T, Bm = _rand(M, r, seed=2, scale=0.3), _rand(Cout, r, seed=3, scale=0.1)
+    res = _rand(M, Cout, seed=4)
+    y = torch.empty(M, Cout, dtype=BF, device="cuda")
+    ops.gemm(y, M, Cout, [(ops.Conv3x3(x, N, H, W, C, b_tap_k=C), ops.kmajor(wk), 9 * C), (ops.kmajor(T), ops.kmajor(Bm), r)],
+             residual=res, pair_mode=1)
+    xn = x.float().view(N, H, W, C).permute(0, 3, 1, 2)
+    ref = F.conv2d(xn, w.float(), padding=1).permute(0, 2, 3, 1).reshape(M, Cout) + T.float() @ Bm.float().T + res.float()
+    _close(y, ref, what="pair conv + lora segment")
+    # dgrad-like: segment 1 = U9 [M, 9r] (K-major) against A [9r, C] read MN-major
+    U9, A = _rand(M, 9 * r, seed=5, scale=0.2), _rand(9 * r, Cout, seed=6, scale=0.1)
+    z = torch.empty(M, Cout, dtype=BF, device="cuda")
+    ops.gemm(z, M, Cout, [(ops.Conv3x3(x, N, H, W, C, b_tap_k=C), ops.kmajor(wk), 9 * C),
+                          (ops.kmajor(U9), ops.Mat(A, 9 * r, Cout, Cout, mn=True), 9 * r)], pair_mode=1)
+    ref2 = F.conv2d(xn, w.float(), padding=1).permute(0, 2, 3, 1).reshape(M, Cout) + U9.float() @ A.float()
+    _close(z, ref2, what="pair conv + MN-major segment")
+
+
+def test_pair_two_plain_segments():
+    from sd_lora_trainer_b200 import ops
+    M, N, K, r = 1024, 640, 320, 16
+    x, w = _rand(M, K), _rand(N, K, seed=1, scale=0.05)
+    T, Bm = _rand(M, r, seed=2, scale=0.3), _rand(N, r, seed=3, scale=0.1)
+    y = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(y, M, N, [(ops.kmajor(x), ops.kmajor(w), K), (ops.kmajor(T), ops.kmajor(Bm), r)], pair_mode=1)
+    _close(y, x.float() @ w.float().T + T.float() @ Bm.float().T, what="pair two segments")
