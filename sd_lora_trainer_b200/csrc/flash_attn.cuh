@@ -37,6 +37,14 @@ struct FlashFwdArgs {
     float scale;                               // 1/sqrt(d)
 };
 
+// 2^x on the MUFU pipe, denormal results flushed to zero (softmax weights below 2^-126 are zero for every purpose
+// here); exp2f() wraps the same instruction in a range fix-up that costs three more instructions per element.
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -164,11 +172,15 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
         const int row = lane_base + lane;
         const uint32_t lane_off = static_cast<uint32_t>(lane_base) << 16;
         const float sl2 = g.scale * 1.4426950408889634f;           // scores are used in the log2 domain
+        // m: the reference maximum the exponentials are taken against.  It only moves when a row's running maximum
+        // outgrows it by more than 2^8 (log2 domain), so O (in TMEM) is rescaled on a few blocks instead of on every one;
+        // the final O / l and LSE = m.scale + ln(l) are exact whatever reference was used.
         float m = -INFINITY, l = 0.f;
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             const int kvalid = min(128, g.Lk - j * 128);
+            const bool full_blk = kvalid == 128;                    // warp-uniform
             // pass 1: row maximum
             float mx = -INFINITY;
 #pragma unroll
@@ -176,28 +188,41 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
                 uint32_t raw[32];
                 tmem_ld32(tmem_S + lane_off + c * 32, raw);
                 tmem_ld_wait();
+                if (full_blk) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+                }
             }
-            const float m_new = fmaxf(m, mx);
-            const float alpha = exp2f((m - m_new) * sl2);           // 0 on the first block (m = -inf)
-            const float moff = m_new * sl2;
+            const float m_cand = fmaxf(m, mx);
+            const bool need = (m_cand - m) * sl2 > 8.f;             // true on the first block (m = -inf)
+            const bool any_need = __any_sync(0xffffffffu, need);
             if (j > 0) {
                 // the previous P.V must have retired before O is rescaled and before sP is overwritten
                 mbar_wait(o_done, (j - 1) & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t o[32];
-                    tmem_ld32(tmem_O + lane_off + c * 32, o);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st32(tmem_O + lane_off + c * 32, o);
-                }
-                tmem_st_wait();
             }
+            if (any_need) {
+                const float alpha = need ? fast_exp2((m - m_cand) * sl2) : 1.f;   // 0 on the first block
+                if (need) m = m_cand;
+                l *= alpha;
+                if (j > 0) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_O + lane_off + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tmem_O + lane_off + c * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+            const float moff = m * sl2;
             // pass 2: exponentials, row sum, P -> smem (bf16)
             float sum = 0.f;
 #pragma unroll
@@ -206,15 +231,22 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
                 tmem_ld32(tmem_S + lane_off + c * 32, raw);
                 tmem_ld_wait();
                 float p[32];
+                if (full_blk) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    p[i] = (c * 32 + i < kvalid) ? exp2f(__uint_as_float(raw[i]) * sl2 - moff) : 0.f;
-                    sum += p[i];
+                    for (int i = 0; i < 32; ++i) {
+                        p[i] = fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, -moff));
+                        sum += p[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        p[i] = (c * 32 + i < kvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, -moff)) : 0.f;
+                        sum += p[i];
+                    }
                 }
                 store_p_chunk(smem + kFwdP, row, c * 32, p);
             }
-            l = l * alpha + sum;
-            m = m_new;
+            l += sum;
             tc_fence_before();
             fence_proxy_async();                                    // generic-proxy smem writes -> visible to the MMA
             __syncwarp();
@@ -406,6 +438,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 mbar_wait(sdp_full, i & 1);
                 mbar_wait(pds_free, (i & 1) ^ 1);
                 tc_fence_after();
+                const bool full_blk = (kvalid == 128) && (i * 128 + 128 <= g.L);     // warp-uniform
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t rs[32], rp[32];
@@ -413,11 +446,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                     tmem_ld32(t_dP + lane_off + c * 32, rp);
                     tmem_ld_wait();
                     float p[32], ds[32];
+                    if (full_blk) {
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const bool ok = qok && (c * 32 + e < kvalid);
-                        p[e] = ok ? exp2f(__uint_as_float(rs[e]) * sl2 - lse2) : 0.f;
-                        ds[e] = p[e] * (__uint_as_float(rp[e]) - delta) * g.scale;
+                        for (int e = 0; e < 32; ++e) {
+                            p[e] = fast_exp2(fmaf(__uint_as_float(rs[e]), sl2, -lse2));
+                            ds[e] = p[e] * (__uint_as_float(rp[e]) - delta) * g.scale;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const bool ok = qok && (c * 32 + e < kvalid);
+                            p[e] = ok ? fast_exp2(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
+                            ds[e] = p[e] * (__uint_as_float(rp[e]) - delta) * g.scale;
+                        }
                     }
                     store_p_chunk(smem + kBwdP, row, c * 32, p);
                     store_p_chunk(smem + kBwdDS, row, c * 32, ds);

@@ -34,10 +34,11 @@ def _r8(n: int) -> int:
 
 
 class _WgradLane:
-    """The LoRA weight-gradient GEMMs (dA, dB) are skinny, launch-latency-bound and feed nothing but the optimizer, so
-    they run on a second stream: inside the step's CUDA graph that is a fork per layer and ONE join at the end of the
-    backward, and they fill the SMs the CTA-pair GEMMs of the main chain leave idle.  Operands are kept alive until
-    the join (the caching allocator must not hand their memory to the main stream while the side stream reads it)."""
+    """Optional (B200_WGRAD_STREAM=1): run the LoRA weight-gradient GEMMs (dA, dB) on a second stream - inside the
+    step's CUDA graph a fork per layer and ONE join at the end of the backward.  Measured on the B200 it does NOT help
+    (91.7 vs 91.1 ms/step, profiles/r01c_*): every GEMM CTA holds > 200 KB of shared memory, so the forked kernels cannot
+    co-reside with the main chain and only add dependency edges.  Off by default; kept for the A/B.  Operands are kept
+    alive until the join (the caching allocator must not hand their memory to the main stream meanwhile)."""
 
     def __init__(self):
         self.stream: Optional[torch.cuda.Stream] = None
@@ -796,7 +797,7 @@ class UNetB200:
         dev = dpred8.device
         d_ctx = torch.zeros(B * Lctx, Dc, dtype=BF16, device=dev)
         d_temb_act = torch.zeros(B, a.time_embed_dim, dtype=BF16, device=dev)
-        WGRAD.begin(os.environ.get("B200_WGRAD_STREAM", "1") != "0" and dev.type == "cuda")
+        WGRAD.begin(os.environ.get("B200_WGRAD_STREAM", "0") == "1" and dev.type == "cuda")
         # hooked layers were enumerated down_blocks..., up_blocks...; backward visits up (reversed) then down (reversed)
         n_down_hooks = sum(len(t.blocks) for rs, at, ds in self.down if at is not None for t in at)
         ds_down = list(dscores[:n_down_hooks]) if dscores is not None else None
