@@ -86,6 +86,12 @@ typedef struct {
     float side_alpha;
     void* T_out;                  /* bf16 [M, t_ld] or NULL */
     int64_t t_ld;
+    /* group mode (num_seg == 2, fp32 atomic outputs): the two segments are two INDEPENDENT problems of the same
+       M x N x K tiling sharing one launch - the dB = dY^T.T and dA = U^T.X weight-gradient GEMMs of one LoRA layer.
+       Segment 0 accumulates into D (d_sm, d_sn), segment 1 into D2 (d2_sm, d2_sn). */
+    int32_t group;
+    void* D2;
+    int64_t d2_sm, d2_sn;
 } b200_gemm_t;
 
 int b200_gemm(const b200_gemm_t* desc, void* stream);

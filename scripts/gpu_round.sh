@@ -23,8 +23,14 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
   tail -12 gpurun_out/pytest_gpu.log
 fi
 
-timeout 600 python scripts/bench_gemm.py > gpurun_out/bench_gemm.log 2>&1
-cat gpurun_out/bench_gemm.log
+if [ "${SKIP_GEMM_BENCH:-0}" != "1" ]; then
+  timeout 600 python scripts/bench_gemm.py > gpurun_out/bench_gemm.log 2>&1
+  cat gpurun_out/bench_gemm.log
+fi
+if [ "${PROBE_STAMPS:-0}" == "1" ]; then
+  timeout 300 python scripts/probe_stamps2.py > gpurun_out/probe_stamps2.log 2>&1
+  cat gpurun_out/probe_stamps2.log
+fi
 
 if [ "${SKIP_BENCH:-0}" != "1" ]; then
   timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err

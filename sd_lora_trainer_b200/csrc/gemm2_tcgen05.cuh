@@ -53,6 +53,7 @@ struct Gemm2Args {
     const __nv_bfloat16* bias;
     const __nv_bfloat16* R;
     __nv_bfloat16* T_out;
+    long long* dbg;           // developer probe: per-CTA globaltimer stamps [cta][16] (nullptr in production)
     CUtensorMap mapA, mapB, mapS, mapB2, mapA2;
 };
 
@@ -165,6 +166,8 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     const int b_mn = g.b_mn, side_mn = g.side_mn, b2_mn = g.b2_mn;
     const int conv = g.conv, nseg = g.nseg, kblocks2 = g.kblocks2;
     const int npairs = static_cast<int>(gridDim.x >> 1), pair = static_cast<int>(blockIdx.x >> 1);
+    long long* const dbg = g.dbg;
+    if (threadIdx.x == 0) dbg_stamp(dbg, 0);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&g.mapA);
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     tc_fence_after();
     pdl_wait();
     const uint32_t tmem_base = *tmem_base_ptr;
+    if (threadIdx.x == 0) dbg_stamp(dbg, 1);
 
     if (warp == 0) {
         // ===================== TMA producer (one thread per CTA) =====================
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                         advance_stage(stage, phase, num_stages);
                     }
                 }
+                if (tile == pair) dbg_stamp(dbg, 2);          // every load of the first tile issued
                 if (side) {
                     // one more ring slot per tile: this CTA's half of the B2 tile for the final rank-r MMA
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -324,6 +329,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (leader) {
+                        if (dbg != nullptr && tile == pair && (kb == 0 || kb == kblocks - 1)) dbg_stamp(dbg, kb == 0 ? 3 : 4);
                         const uint32_t sa = smem_base + static_cast<uint32_t>(stage * stage_bytes);
                         const uint64_t ad = a_hi | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
                         const uint64_t bd = b_hi | static_cast<uint64_t>(((sa + k2ABytes) & 0x3FFFF) >> 4);
@@ -368,6 +374,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     mbar_wait_cluster(t_ready_bar, t_phase);              // T staged in smem by both CTAs
                     t_phase ^= 1;
                     tc_fence_after();
+                    if (leader && tile == pair) dbg_stamp(dbg, 9);
                     if (leader) {
                         const uint32_t sb2 = smem_base + static_cast<uint32_t>(stage * stage_bytes) + k2ABytes;
                         const uint64_t td = a_hi | static_cast<uint64_t>(((smem_base + k2TOff) & 0x3FFFF) >> 4);
@@ -422,6 +429,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                 // ---- T-phase: this CTA's 128 rows of Tacc -> alpha, bf16 -> swizzled smem A operand (+ T_out) ----
                 mbar_wait(&side_full_bar[acc], acc_phase);
                 tc_fence_after();
+                if (warp == 2 && lane == 0 && tile == pair) dbg_stamp(dbg, 8);
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
                               static_cast<uint32_t>(acc_stages == 1 ? 256 : acc * 256 + kSideCol), raw);
@@ -465,6 +473,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
+            if (warp == 2 && lane == 0 && tile == pair) dbg_stamp(dbg, 5);
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 uint32_t raw[32];
                 tmem_ld32(taddr + c0, raw);
@@ -474,6 +483,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
+            if (warp == 2 && lane == 0 && tile == pair) dbg_stamp(dbg, 6);
             if (lane == 0) mbar_arrive_cluster_nofence(tmem_empty_leader + static_cast<uint32_t>(acc) * 8u);
             if (++acc == acc_stages) {
                 acc = 0;
@@ -483,6 +493,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     }
 
     tc_fence_before();
+    if (threadIdx.x == 0) dbg_stamp(dbg, 7);
     cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still read its smem / signal its barriers
     if (warp == 1) tmem_dealloc2(tmem_base, 512);
 }

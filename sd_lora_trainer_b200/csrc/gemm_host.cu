@@ -105,10 +105,11 @@ extern "C" int b200_version(void) { return B200_LORA_ABI_VERSION; }
 extern "C" const char* b200_last_error(void) { return last_error_ref().c_str(); }
 extern "C" long long b200_launch_count(void) { return g_launches.load(); }
 
+
+
 static long long* g_gemm_dbg = nullptr;
 // developer probe (not part of the public header): per-CTA globaltimer stamps of the next GEMM launches
 extern "C" void b200_debug_gemm_stamps(long long* dev_buf) { g_gemm_dbg = dev_buf; }
-
 
 // ---------------------------------------------------------------------------------------------------------
 // CTA-pair kernel (gemm2_tcgen05.cuh): eligibility, tile width, launch
@@ -133,6 +134,7 @@ static bool pair_eligible(const b200_gemm_t* d) {
     if (d->num_seg == 2 && (d->A[1].mn_major || d->A[1].batched || d->B[1].batched)) return false;
     if (d->M < 256 || d->N < 64 || pair_k0(d) < 64) return false;
     if (d->R && d->r_sn != 1) return false;
+    if (d->group) return false;
     return true;
 }
 
@@ -268,6 +270,7 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
     g.num_stages = k2RingBytes / g.stage_bytes;
     if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
     g.acc_stages = (d->side && bn > kSideMaxBN) ? 1 : 2;
+    g.dbg = g_gemm_dbg;
     g.D = d->D;
     g.d_sm = d->d_sm;
     g.alpha = d->alpha;
@@ -296,7 +299,8 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     B200_CHECK_ARG(d->nb0 >= 1 && d->nb1 >= 1 && d->splits >= 1, "gemm: bad batch/split");
     B200_CHECK_ARG(d->D != nullptr, "gemm: null output");
     B200_CHECK_ARG(!(d->d_atomic && !d->d_fp32), "gemm: atomic accumulation needs an fp32 output");
-    B200_CHECK_ARG(d->splits == 1 || (d->d_atomic && d->num_seg == 1 && !d->conv), "gemm: split-K needs atomic fp32 output, one segment, no conv");
+    B200_CHECK_ARG(d->splits == 1 || (d->d_atomic && (d->num_seg == 1 || d->group) && !d->conv),
+                   "gemm: split-K needs atomic fp32 output, one segment (or group mode), no conv");
 
     // CTA-pair kernel for the big plain projections (pair_mode: 0 auto, 1 force, -1 never)
     static const int pair_env = getenv("B200_GEMM2") ? atoi(getenv("B200_GEMM2")) : 1;
@@ -321,8 +325,17 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
         attr_set = true;
     }
 
+    if (d->group) {
+        B200_CHECK_ARG(d->num_seg == 2 && !d->conv && !d->side && d->nb0 == 1 && d->nb1 == 1, "gemm: group mode needs two plain segments");
+        B200_CHECK_ARG(d->d_fp32 && d->d_atomic && d->D2 != nullptr, "gemm: group mode needs fp32 atomic outputs D and D2");
+        B200_CHECK_ARG(d->K[0] == d->K[1], "gemm: group mode needs equal reduction lengths");
+    }
     GemmArgs g;
     memset(&g, 0, sizeof(g));
+    g.group = d->group;
+    g.D2 = d->D2;
+    g.d2_sm = d->d2_sm;
+    g.d2_sn = d->d2_sn;
     g.M = d->M;
     g.N = d->N;
     g.nb0 = d->nb0;
@@ -336,7 +349,7 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
                        "gemm: the fused side path needs one segment, no conv, no batch, no split-K");
         B200_CHECK_ARG(d->side_r >= 1 && d->side_r <= 32, "gemm: side rank %d out of range", d->side_r);
     }
-    if (bn <= 0) bn = pick_block_n(static_cast<long long>(g.tiles_m) * d->nb0 * d->nb1 * d->splits, d->N,
+    if (bn <= 0) bn = pick_block_n(static_cast<long long>(g.tiles_m) * d->nb0 * d->nb1 * d->splits * (d->group ? 2 : 1), d->N,
                                    d->side ? kSideMaxBN : kMaxBN);
     if (d->side) B200_CHECK_ARG(bn <= kSideMaxBN, "gemm: block_n %d too wide for the side path", bn);
     B200_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= kMaxBN, "gemm: block_n %d must be a multiple of 16 in [16, 256]", bn);
@@ -439,7 +452,7 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
         static const int cap = getenv("B200_GEMM_STAGES") ? atoi(getenv("B200_GEMM_STAGES")) : 0;   // tuning probe
         if (cap > 0 && g.num_stages > cap) g.num_stages = cap;
     }
-    const long long total_tiles = static_cast<long long>(g.tiles_m) * g.tiles_n * g.splits * g.nb0 * g.nb1;
+    const long long total_tiles = static_cast<long long>(g.tiles_m) * g.tiles_n * g.splits * g.nb0 * g.nb1 * (g.group ? 2 : 1);
     const int grid = static_cast<int>(total_tiles < kNumSMs ? total_tiles : kNumSMs);
     const bool row_major = d->d_sn == 1 && !d->d_atomic;
     const int esz = d->d_fp32 ? 4 : 2;

@@ -85,6 +85,11 @@ struct GemmArgs {
     long long t_ld;
     CUtensorMap mapS, mapB2;
     int vec_ok;               // epilogue may use 8/16-byte vector accesses (host-checked alignment)
+    // group mode: the two "segments" are two INDEPENDENT problems of identical tiling (the dB and dA weight-gradient
+    // GEMMs of one LoRA layer) sharing one launch; problem 1 writes D2 with its own strides
+    int group;
+    void* D2;
+    long long d2_sm, d2_sn;
     int dbg_mode;             // developer probe: 1 = epilogue skips global stores, 2 = skips the smem read-back
     long long* dbg;           // developer probe: per-CTA globaltimer stamps [cta][8] (nullptr in production)
 };
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const uint32_t tmem_base = *tmem_base_ptr;
 
     const int tiles_per_batch = g.tiles_m * g.tiles_n * g.splits;
-    const int total_tiles = tiles_per_batch * g.nb0 * g.nb1;
+    const int total_tiles = tiles_per_batch * g.nb0 * g.nb1 * (g.group ? 2 : 1);
     const int BN = g.BN;
     const int b_boxes_mn = (BN + 63) >> 6;
     const uint32_t b_bytes_k = static_cast<uint32_t>(BN) * 128u;
@@ -169,14 +174,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         {
             int stage = 0;
             uint32_t phase = 0;
-            const bool simple = (g.nb0 * g.nb1 * g.splits) == 1;
+            const bool simple = (g.nb0 * g.nb1 * g.splits) == 1 && !g.group;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int n_blk, m_blk, split = 0, b0 = 0, b1 = 0;
+                int seg_lo = 0, seg_hi = g.num_seg, tl = tile;
+                if (g.group) {
+                    seg_lo = tile / tiles_per_batch;
+                    seg_hi = seg_lo + 1;
+                    tl = tile - seg_lo * tiles_per_batch;
+                }
                 if (simple) {
                     m_blk = static_cast<int>(static_cast<unsigned>(tile) / static_cast<unsigned>(g.tiles_n));
                     n_blk = tile - m_blk * g.tiles_n;
                 } else {
-                    int t = tile;
+                    int t = tl;
                     n_blk = t % g.tiles_n;  t /= g.tiles_n;
                     m_blk = t % g.tiles_m;  t /= g.tiles_m;
                     split = t % g.splits;   t /= g.splits;
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                     conv_n0 = m0 / hw;
                     conv_h0 = (m0 % hw) / g.conv_W;
                 }
-                for (int seg = 0; seg < g.num_seg; ++seg) {
+                for (int seg = seg_lo; seg < seg_hi; ++seg) {
                     int kb_begin = 0, kb_end = g.kblocks[seg];
                     if (g.splits > 1) {
                         kb_begin = static_cast<int>((static_cast<long long>(kb_end) * split) / g.splits);
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                             if (g.side_mn) tma_load_4d(sb + g.side_off, &g.mapS, fb, 0, kb * kBK, 0, 0);
                             else tma_load_4d(sb + g.side_off, &g.mapS, fb, kb * kBK, 0, 0, 0);
                         }
-                        if (lane == 0 && kb == kb_begin && seg == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 2);
+                        if (lane == 0 && kb == kb_begin && seg == seg_lo && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 2);
                         advance_stage(stage, phase, g.num_stages);
                     }
                 }
@@ -277,7 +288,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             uint32_t acc_phase = 0, t_phase = 0;
             const uint32_t smem_base = smem_u32(smem);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int split = (g.splits > 1) ? (tile / (g.tiles_m * g.tiles_n)) % g.splits : 0;
+                int seg_lo = 0, seg_hi = g.num_seg, tl = tile;
+                if (g.group) {
+                    seg_lo = tile / tiles_per_batch;
+                    seg_hi = seg_lo + 1;
+                    tl = tile - seg_lo * tiles_per_batch;
+                }
+                const int split = (g.splits > 1) ? (tl / (g.tiles_m * g.tiles_n)) % g.splits : 0;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kMaxBN);
@@ -285,7 +302,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                 const uint32_t idesc_side = umma_idesc_bf16(g.side_r16, g.a_mn[0], g.side_mn);
                 const uint32_t s_step = g.side_mn ? (2048u >> 4) : (32u >> 4);
                 uint32_t accumulate = 0;
-                for (int seg = 0; seg < g.num_seg; ++seg) {
+                for (int seg = seg_lo; seg < seg_hi; ++seg) {
                     int kb_begin = 0, kb_end = g.kblocks[seg];
                     const int kb_last = kb_end - 1;
                     if (g.splits > 1) {
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                         const uint64_t bdesc = umma_desc(sb, b_lbo, 1024);
                         const int n16 = (kb == kb_last) ? g.ktail16[seg] : 4;
                         if (elect_one()) {
-                            if (kb == kb_begin && seg == 0 && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 3);
+                            if (kb == kb_begin && seg == seg_lo && tile == static_cast<int>(blockIdx.x)) dbg_stamp(g.dbg, 3);
                             if (g.side) {
                                 const uint64_t sdesc = umma_desc(sb + g.side_off, g.side_mn ? 8192u : 16u, 1024);
                                 for (int k = 0; k < n16; ++k)
@@ -381,6 +398,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int t = tile;
+            void* Dp = g.D;
+            long long dsm = g.d_sm, dsn = g.d_sn;
+            if (g.group && tile >= tiles_per_batch) {
+                t = tile - tiles_per_batch;
+                Dp = g.D2;
+                dsm = g.d2_sm;
+                dsn = g.d2_sn;
+            }
             const int n_blk = t % g.tiles_n;  t /= g.tiles_n;
             const int m_blk = t % g.tiles_m;  t /= g.tiles_m;
             t /= g.splits;
@@ -575,13 +600,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
                             float v = __uint_as_float(raw[j]) * g.alpha;
                             if (bias_row) v += __bfloat162float(bias_row[n]);
                             if (g.R) v += __bfloat162float(g.R[r_boff + static_cast<long long>(m) * g.r_sm + static_cast<long long>(n) * g.r_sn]);
-                            const long long doff = d_boff + static_cast<long long>(m) * g.d_sm + static_cast<long long>(n) * g.d_sn;
+                            const long long doff = d_boff + static_cast<long long>(m) * dsm + static_cast<long long>(n) * dsn;
                             if (g.d_fp32) {
-                                float* dp = reinterpret_cast<float*>(g.D) + doff;
+                                float* dp = reinterpret_cast<float*>(Dp) + doff;
                                 if (g.d_atomic) atomicAdd(dp, v);
                                 else *dp = v;
                             } else {
-                                reinterpret_cast<__nv_bfloat16*>(g.D)[doff] = __float2bfloat16_rn(v);
+                                reinterpret_cast<__nv_bfloat16*>(Dp)[doff] = __float2bfloat16_rn(v);
                             }
                         }
                     }

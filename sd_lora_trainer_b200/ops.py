@@ -88,10 +88,12 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
          bias: Optional[torch.Tensor] = None, bias_rows: int = 0, bias_sb: int = 0,
          residual: Optional[torch.Tensor] = None, r_strides: Optional[Tuple[int, int, int, int]] = None,
          nb0: int = 1, nb1: int = 1, splits: int = 1, atomic: bool = False, block_n: int = 0,
-         side: Optional[Tuple[Mat, Mat, int, float, Optional[torch.Tensor]]] = None, pair_mode: int = 0) -> torch.Tensor:
+         side: Optional[Tuple[Mat, Mat, int, float, Optional[torch.Tensor]]] = None, pair_mode: int = 0,
+         group_out: Optional[Tuple[torch.Tensor, Tuple[int, int]]] = None) -> torch.Tensor:
     """out[b1][b0][m, n] = alpha * sum_seg A_seg.B_seg^T (+bias) (+residual).  segs: (A | Conv3x3, B, K).
     side = (S, B2, r, side_alpha, T_out): fused low-rank path  out += (side_alpha * A.S^T).B2^T, T_out <- the inner
-    product (bf16) - see include/b200_lora.h."""
+    product (bf16) - see include/b200_lora.h.
+    group_out = (out2, (sm, sn)): the two segments are independent problems; segment 1 accumulates into out2."""
     _chk_dev(out, bias, residual)
     d = GemmDesc()
     d.M, d.N, d.num_seg = M, N, len(segs)
@@ -111,6 +113,10 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
         d.side, d.side_r, d.S, d.B2, d.side_alpha = 1, r, s_mat.c(), b2_mat.c(), s_alpha
         if t_out is not None:
             d.T_out, d.t_ld = t_out.data_ptr(), t_out.stride(0)
+    if group_out is not None:
+        out2, (sm2, sn2) = group_out
+        assert atomic and len(segs) == 2 and out2.dtype == torch.float32
+        d.group, d.D2, d.d2_sm, d.d2_sn = 1, out2.data_ptr(), sm2, sn2
     d.D = out.data_ptr()
     d.d_fp32 = int(out.dtype == torch.float32)
     assert out.dtype in (torch.float32, BF16)

@@ -66,6 +66,7 @@ class _WgradLane:
 
 
 WGRAD = _WgradLane()
+GROUP_WGRAD = os.environ.get("B200_GROUP_WGRAD", "1") != "0"
 
 
 def _wgrad_splits(out_rows: int, reduce_len: int) -> int:
@@ -224,10 +225,15 @@ class Lin:
         if lo is not None:
             # dB[N, r] += dY^T . T      dA[r, K] += U^T . X   (both operands MN-major, split-K fp32 atomics)
             def wgrad():
-                ops.gemm(lo.gB(), self.N, r, [(Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(T, M, r, rs, mn=True), M)],
-                         d_strides=(rs, 1, 0, 0), splits=_wgrad_splits(self.N, M), atomic=True)
-                ops.gemm(lo.gA(), self.K, r, [(Mat(x, M, self.K, x.stride(0), mn=True), Mat(U, M, r, rs, mn=True), M)],
-                         d_strides=(1, self.K, 0, 0), splits=_wgrad_splits(self.K, M), atomic=True)
+                seg_b = (Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(T, M, r, rs, mn=True), M)
+                seg_a = (Mat(x, M, self.K, x.stride(0), mn=True), Mat(U, M, r, rs, mn=True), M)
+                if self.N == self.K and GROUP_WGRAD:
+                    # square projection: both weight gradients have the same tiling -> ONE grouped launch
+                    ops.gemm(lo.gB(), self.N, r, [seg_b, seg_a], d_strides=(rs, 1, 0, 0), atomic=True,
+                             splits=_wgrad_splits(2 * self.N, M), group_out=(lo.gA(), (1, self.K)))
+                else:
+                    ops.gemm(lo.gB(), self.N, r, [seg_b], d_strides=(rs, 1, 0, 0), splits=_wgrad_splits(self.N, M), atomic=True)
+                    ops.gemm(lo.gA(), self.K, r, [seg_a], d_strides=(1, self.K, 0, 0), splits=_wgrad_splits(self.K, M), atomic=True)
             WGRAD.run(wgrad, dy, T, x, U)
         return dx
 

@@ -237,3 +237,23 @@ def test_fused_side_path_dgrad(M, N, K, r):
     Uref = (2.0 * (dy.float() @ Bp[:, :r].float())).to(BF)
     _close(U[:, :r], Uref, what="U out")
     _close(dx, dy.float() @ w.float() + Uref.float() @ A.float() + acc.float(), what="fused side dgrad")
+
+
+@pytest.mark.parametrize("Mred,C,r", [(2048, 1280, 16), (8192, 640, 16), (1000, 320, 8), (2048, 1280, 32), (300, 200, 4)])
+def test_grouped_weight_gradients(Mred, C, r):
+    """dB[C, r] += dY^T.T and dA[r, C] += U^T.X of one square LoRA layer as ONE grouped launch (split-K, fp32 atomics)."""
+    from sd_lora_trainer_b200 import ops
+    rs = (r + 7) // 8 * 8
+    dy, x = _rand(Mred, C), _rand(Mred, C, seed=1)
+    T, U = _rand(Mred, rs, seed=2, scale=0.3), _rand(Mred, rs, seed=3, scale=0.3)
+    gB = torch.zeros(C, rs, dtype=torch.float32, device="cuda")
+    gA = torch.zeros(r, C, dtype=torch.float32, device="cuda")
+    gB += 1.0                                                       # accumulation, not overwrite
+    tiles = (C + 127) // 128
+    splits = max(1, min(148 // (2 * tiles), (Mred + 63) // 64, 32))
+    ops.gemm(gB, C, r, [(ops.Mat(dy, Mred, C, C, mn=True), ops.Mat(T, Mred, r, rs, mn=True), Mred),
+                        (ops.Mat(x, Mred, C, C, mn=True), ops.Mat(U, Mred, r, rs, mn=True), Mred)],
+             d_strides=(rs, 1, 0, 0), atomic=True, splits=splits, group_out=(gA, (1, C)))
+    torch.cuda.synchronize()
+    _close(gB[:, :r], 1.0 + dy.float().T @ T[:, :r].float(), tol=5e-3, what="grouped dB")
+    _close(gA, (x.float().T @ U[:, :r].float()).T, tol=5e-3, what="grouped dA")
