@@ -23,6 +23,7 @@ if [ "${SKIP_TESTS:-0}" != "1" ]; then
   tail -12 gpurun_out/pytest_gpu.log
 fi
 
+timeout 300 python -m pytest tests/test_flash_gpu.py -q -s -k 4096 2>&1 | grep -a "flash fwd" > gpurun_out/flash_timing.txt; cat gpurun_out/flash_timing.txt
 if [ "${SKIP_GEMM_BENCH:-0}" != "1" ]; then
   timeout 600 python scripts/bench_gemm.py > gpurun_out/bench_gemm.log 2>&1
   cat gpurun_out/bench_gemm.log
@@ -50,9 +51,11 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   python scripts/summarize_launches.py gpurun_out/launches.csv gpurun_out/launches_summary.json > gpurun_out/launches_summary.txt 2>&1
   head -45 gpurun_out/launches_summary.txt
   gzip -f gpurun_out/launches.csv
+  if [ "${NCU_FULL:-1}" == "1" ]; then
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 3 -c 1 \
       -o gpurun_out/gemm2_lora_full python scripts/one_gemm.py 2048 1280 1280 lora > gpurun_out/ncu_full.log 2>&1
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 3 -c 1 \
       -o gpurun_out/gemm2_ff_full python scripts/one_gemm.py 2048 10240 1280 plain >> gpurun_out/ncu_full.log 2>&1
   tail -5 gpurun_out/ncu_full.log
+  fi
 fi

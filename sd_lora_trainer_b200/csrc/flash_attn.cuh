@@ -18,7 +18,7 @@
 
 namespace b200 {
 
-constexpr int kFaThreads = 192;
+constexpr int kFaThreads = 320;                // TMA, MMA, 2 x 4 softmax warps (keys 0-63 / 64-127 of every block)
 constexpr int kFaTile = 128 * 64 * 2;          // one [128 x 64] bf16 tile: 16 KiB
 // forward smem map
 constexpr int kFwdQ = 0;
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
             mbar_init(&kv_empty[i], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(s_free, 4);
-        mbar_init(p_full, 4);
+        mbar_init(s_free, 8);
+        mbar_init(p_full, 8);
         mbar_init(o_done, 1);
         fence_barrier_init();
     }
@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
     tc_fence_after();
     pdl_wait();                                   // nothing above touched global memory
     const uint32_t tmem = *tmem_ptr;
+    // TMEM: S [128 x 128] at columns 0-127; TWO output accumulators O_a (keys 0-63 of every block) at 128-191 and
+    // O_b (keys 64-127) at 192-255.  Each softmax warp group runs its own online softmax over its half of the keys
+    // (own running reference and row sum, no per-block exchange); the halves are merged once, in the epilogue.
     const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
 
     if (warp == 0) {
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint64_t pd = umma_desc(sp + (k >> 2) * kFaTile, 16, 1024) + 2 * (k & 3);
-                    umma_bf16(tmem_O, pd, vd + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem_O + (k >> 2) * 64, pd, vd + 128 * k, idesc_o, (j > 0 || (k & 3) > 0) ? 1u : 0u);
                 }
                 umma_commit(&kv_empty[s]);
                 umma_commit(o_done);
@@ -167,10 +170,14 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
         }
         __syncwarp();
     } else {
-        // ---- softmax / correction / epilogue: thread <-> query row ----
+        // ---- softmax / correction / epilogue: thread <-> (query row, half of the keys of every block) ----
+        // One warp per scheduler could not keep up with the tensor pipe (issue-bound); two warp groups halve the work
+        // per thread, and because each owns its own accumulator they never have to agree on a running maximum.
         const int lane_base = (warp & 3) * 32;
         const int row = lane_base + lane;
+        const int half = (warp >= 6) ? 1 : 0;
         const uint32_t lane_off = static_cast<uint32_t>(lane_base) << 16;
+        const uint32_t tmem_Oh = tmem_O + half * 64;
         const float sl2 = g.scale * 1.4426950408889634f;           // scores are used in the log2 domain
         // m: the reference maximum the exponentials are taken against.  It only moves when a row's running maximum
         // outgrows it by more than 2^8 (log2 domain), so O (in TMEM) is rescaled on a few blocks instead of on every one;
@@ -179,14 +186,14 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            const int kvalid = min(128, g.Lk - j * 128);
-            const bool full_blk = kvalid == 128;                    // warp-uniform
-            // pass 1: row maximum
+            const int kvalid = min(128, g.Lk - j * 128) - half * 64;   // valid keys among this group's 64 (may be <= 0)
+            const bool full_blk = kvalid >= 64;                     // warp-uniform
+            // pass 1: row maximum over this group's keys
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t raw[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, raw);
+                tmem_ld32(tmem_S + lane_off + half * 64 + c * 32, raw);
                 tmem_ld_wait();
                 if (full_blk) {
 #pragma unroll
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
                 }
             }
             const float m_cand = fmaxf(m, mx);
-            const bool need = (m_cand - m) * sl2 > 8.f;             // true on the first block (m = -inf)
+            const bool need = (m_cand - m) * sl2 > 8.f;             // true on the first block with a valid key (m = -inf)
             const bool any_need = __any_sync(0xffffffffu, need);
             if (j > 0) {
                 // the previous P.V must have retired before O is rescaled and before sP is overwritten
@@ -206,18 +213,18 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
                 tc_fence_after();
             }
             if (any_need) {
-                const float alpha = need ? fast_exp2((m - m_cand) * sl2) : 1.f;   // 0 on the first block
+                const float alpha = need ? fast_exp2((m - m_cand) * sl2) : 1.f;   // 0 when m was -inf
                 if (need) m = m_cand;
                 l *= alpha;
                 if (j > 0) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint32_t o[32];
-                        tmem_ld32(tmem_O + lane_off + c * 32, o);
+                        tmem_ld32(tmem_Oh + lane_off + c * 32, o);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(tmem_O + lane_off + c * 32, o);
+                        tmem_st32(tmem_Oh + lane_off + c * 32, o);
                     }
                     tmem_st_wait();
                 }
@@ -226,9 +233,9 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
             // pass 2: exponentials, row sum, P -> smem (bf16)
             float sum = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 uint32_t raw[32];
-                tmem_ld32(tmem_S + lane_off + c * 32, raw);
+                tmem_ld32(tmem_S + lane_off + half * 64 + c * 32, raw);
                 tmem_ld_wait();
                 float p[32];
                 if (full_blk) {
@@ -244,7 +251,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
                         sum += p[i];
                     }
                 }
-                store_p_chunk(smem + kFwdP, row, c * 32, p);
+                store_p_chunk(smem + kFwdP, row, half * 64 + c * 32, p);
             }
             l += sum;
             tc_fence_before();
@@ -257,27 +264,41 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
         }
         mbar_wait(o_done, (nkv - 1) & 1);
         tc_fence_after();
+        // ---- merge the two halves: (m, l) of the other group through smem (the P tile is free now) ----
+        float2* xch = reinterpret_cast<float2*>(smem + kFwdP);      // [2][128]
+        xch[half * 128 + row] = make_float2(m, l);
+        asm volatile("bar.sync 1, 256;" ::: "memory");              // the 8 softmax warps
+        const float2 other = xch[(half ^ 1) * 128 + row];
+        const float m_all = fmaxf(m, other.x);
+        const float w_me = fast_exp2((m - m_all) * sl2), w_ot = fast_exp2((other.x - m_all) * sl2);   // 0 for an empty half
+        const float l_all = l * w_me + other.y * w_ot;
+        const float wa = half ? w_ot : w_me, wb = half ? w_me : w_ot;                                 // weights of O_a, O_b
         const int q = q0 + row;
-        const float inv = 1.f / l;
-        __nv_bfloat16* op = g.O + (static_cast<long long>(b) * g.L + q) * g.o_ld + h * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld32(tmem_O + lane_off + c * 32, o);
+        const float inv = 1.f / l_all;
+        // this thread writes output columns [half*32, half*32 + 32) of its row
+        __nv_bfloat16* op = g.O + (static_cast<long long>(b) * g.L + q) * g.o_ld + h * 64 + half * 32;
+        {
+            uint32_t oa[32], ob[32];
+            tmem_ld32(tmem_O + lane_off + half * 32, oa);
+            tmem_ld32(tmem_O + 64 + lane_off + half * 32, ob);
             tmem_ld_wait();
             if (q < g.L) {
+                const float ca = wa * inv, cb = wb * inv;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(oa[8 * i + e]) * ca + __uint_as_float(ob[8 * i + e]) * cb;
                     uint4 w;
-                    w.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-                    w.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-                    w.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-                    w.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(op + c * 32 + i * 8) = w;
+                    w.x = pack_bf16(v[0], v[1]);
+                    w.y = pack_bf16(v[2], v[3]);
+                    w.z = pack_bf16(v[4], v[5]);
+                    w.w = pack_bf16(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(op + i * 8) = w;
                 }
             }
         }
-        if (q < g.L) g.LSE[(static_cast<long long>(b) * g.H + h) * g.L + q] = m * g.scale + logf(l);
+        if (half == 0 && q < g.L) g.LSE[(static_cast<long long>(b) * g.H + h) * g.L + q] = m_all * g.scale + logf(l_all);
         tc_fence_before();
     }
     __syncthreads();
@@ -288,7 +309,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
 // =================================================================================================================
 // backward
 // =================================================================================================================
-constexpr int kBwdThreads = 320;               // TMA, MMA, 4 softmax warps, 4 dQ-epilogue warps
+constexpr int kBwdThreads = 448;               // TMA, MMA, 4 softmax warps (keys 0-63), 4 dQ-epilogue warps, 4 softmax warps (keys 64-127)
 constexpr int kBwdK = 0;
 constexpr int kBwdV = kBwdK + kFaTile;
 constexpr int kBwdQ = kBwdV + kFaTile;         // 2 stages
@@ -340,8 +361,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             mbar_init(&qdo_empty[i], 1);
         }
         mbar_init(sdp_full, 1);
-        mbar_init(sdp_free, 4);
-        mbar_init(pds_full, 4);
+        mbar_init(sdp_free, 8);
+        mbar_init(pds_full, 8);
         mbar_init(pds_free, 1);
         mbar_init(dq_full, 1);
         mbar_init(dq_free, 4);
@@ -428,8 +449,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
         const float sl2 = g.scale * 1.4426950408889634f;
         const int kvalid = min(128, g.Lk - k0);
         const long long stat_base = (static_cast<long long>(b) * g.H + h) * g.L;
-        if (warp < 6) {
-            // ---- softmax warps: rebuild P, form dS, stage both for the MMAs (thread <-> query row) ----
+        if (warp < 6 || warp >= 10) {
+            // ---- softmax warps: rebuild P, form dS, stage both for the MMAs.  Thread <-> (query row, half of the
+            //      128 keys): one warp per scheduler was the bottleneck of this kernel (issue-bound at ~1500
+            //      instructions per row and block), so two warps share every TMEM lane quarter. ----
+            const int chalf = (warp >= 10) ? 2 : 0;
             for (int i = 0; i < nq; ++i) {
                 const int q = i * 128 + row;
                 const bool qok = q < g.L;
@@ -440,7 +464,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 tc_fence_after();
                 const bool full_blk = (kvalid == 128) && (i * 128 + 128 <= g.L);     // warp-uniform
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = chalf + cc;
                     uint32_t rs[32], rp[32];
                     tmem_ld32(t_S + lane_off + c * 32, rs);
                     tmem_ld32(t_dP + lane_off + c * 32, rp);
@@ -504,6 +529,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
         __nv_bfloat16* out = ((warp < 6) ? g.dV : g.dK) + (static_cast<long long>(b) * g.Lk + key) * g.ld + h * 64;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+            if (warp >= 10) break;                 // the second softmax group has no output tile of its own (warp-uniform)
             uint32_t r[32];
             tmem_ld32(src + lane_off + c * 32, r);
             tmem_ld_wait();
