@@ -92,6 +92,9 @@ typedef struct {
     int32_t group;
     void* D2;
     int64_t d2_sm, d2_sn;
+    /* 1: the B operands (B[*], S, B2 - frozen weights and LoRA factors) are NOT written by the kernel that precedes
+       this launch on the stream, so the pair kernel may fetch them before its programmatic-dependency wait. */
+    int32_t b_static;
 } b200_gemm_t;
 
 int b200_gemm(const b200_gemm_t* desc, void* stream);

@@ -47,6 +47,9 @@ struct Gemm2Args {
     int conv, conv_cblocks, conv_W, conv_H, b_tap_k, b_tap_n;
     // optional second K segment accumulated into the same tile: plain K-major A2 [M, K2], B2 via mapB2 / b2_mn
     int nseg, kblocks2, ktail16_2;
+    // B / S / B2 (weights, LoRA factors) are not written by the preceding kernel of the stream: the producer fetches
+    // the first ring-full of them BEFORE griddepcontrol.wait, overlapping the predecessor's tail
+    int b_static;
     float alpha, side_alpha;
     long long d_sm, r_sm, t_ld, bias_sb;
     void* D;
@@ -200,9 +203,8 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     tc_fence_before();
     cluster_sync_all();       // the peer's barriers are initialised and its TMEM allocated before anything targets them
     tc_fence_after();
-    pdl_wait();
+    if (threadIdx.x != 0) pdl_wait();         // thread 0 (the TMA producer) waits after its weight prefetch
     const uint32_t tmem_base = *tmem_base_ptr;
-    if (threadIdx.x == 0) dbg_stamp(dbg, 1);
 
     if (warp == 0) {
         // ===================== TMA producer (one thread per CTA) =====================
@@ -220,16 +222,68 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             const int s_row = static_cast<int>(rank) * sr_half;
             const int conv_H = g.conv_H, conv_W = g.conv_W, conv_cblocks = g.conv_cblocks;
             const int conv_tap_k = g.b_tap_k, conv_tap_n = g.b_tap_n;
+            // B-side loads of k-block kb of a tile (weights + LoRA side factor) into ring slot st
+            auto issue_b = [&](int st, int kb, int nh0) {
+                uint8_t* sb = smem + st * stage_bytes + k2ABytes;
+                const uint32_t fb = full0 + static_cast<uint32_t>(st) * 8u;
+                if (conv) {
+                    const int tap = kb / conv_cblocks, cb = kb - tap * conv_cblocks;
+                    tma2_load_4d(sb, &g.mapB, fb, tap * conv_tap_k + cb * kBK, nh0 + tap * conv_tap_n, 0, 0);
+                } else if (!b_mn) {
+                    tma2_load_4d(sb, &g.mapB, fb, kb * kBK, nh0, 0, 0);
+                } else {
+                    for (int jb = 0; jb < b_boxes; ++jb) tma2_load_4d(sb + jb * 8192, &g.mapB, fb, nh0 + jb * 64, kb * kBK, 0, 0);
+                }
+                if (side) {
+                    if (side_mn) tma2_load_4d(sb + side_off, &g.mapS, fb, s_row, kb * kBK, 0, 0);
+                    else tma2_load_4d(sb + side_off, &g.mapS, fb, kb * kBK, s_row, 0, 0);
+                }
+            };
+            auto issue_a = [&](int st, int kb, int m0) {
+                uint8_t* sa = smem + st * stage_bytes;
+                const uint32_t fb = full0 + static_cast<uint32_t>(st) * 8u;
+                if (conv) {
+                    const int hw = conv_H * conv_W;
+                    const int cn0 = m0 / hw, ch0 = (m0 - cn0 * hw) / conv_W;
+                    const int tap = kb / conv_cblocks, cb = kb - tap * conv_cblocks;
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    tma2_load_4d(sa, &g.mapA, fb, cb * kBK, kw - 1, ch0 + kh - 1, cn0);
+                } else {
+                    tma2_load_4d(sa, &g.mapA, fb, kb * kBK, m0, 0, 0);
+                }
+            };
+            // ---- weight prefetch: the first ring-full of B tiles does not depend on the previous kernel ----
+            int npre = 0;
+            if (g.b_static) {
+                const int n_blk0 = pair % tiles_n;
+                const int nh00 = n_blk0 * BN + static_cast<int>(rank) * bn_half;
+                npre = kblocks < num_stages ? kblocks : num_stages;
+                for (int st = 0; st < npre; ++st) {
+                    if (rank == 0) mbar_expect_tx(&full_bar[st], tx);
+                    issue_b(st, st, nh00);
+                }
+            }
+            pdl_wait();
+            dbg_stamp(dbg, 1);
             for (int tile = pair; tile < total_tiles; tile += npairs) {
                 const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
                 const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
                 const int nh0 = n_blk * BN + static_cast<int>(rank) * bn_half;
+                int kb_first = 0;
+                if (tile == pair && npre > 0) {
+                    for (int st = 0; st < npre; ++st) issue_a(st, st, m0);
+                    kb_first = npre;
+                    stage = (npre == num_stages) ? 0 : npre;
+                    phase = (npre == num_stages) ? 1u : 0u;
+                }
                 if (conv) {
                     // implicit im2col: one box per (tap, 64-channel block) with shifted coordinates; TMA zero-fills the halo
                     const int hw = conv_H * conv_W;
                     const int cn0 = m0 / hw, ch0 = (m0 - cn0 * hw) / conv_W;
-                    int cb = 0, kw = 0, kh = 0, bk_tap = 0, bn_tap = 0;
-                    for (int kb = 0; kb < kblocks; ++kb) {
+                    int tap0 = kb_first / conv_cblocks;
+                    int cb = kb_first - tap0 * conv_cblocks, kh = tap0 / 3;
+                    int kw = tap0 - kh * 3, bk_tap = tap0 * conv_tap_k, bn_tap = tap0 * conv_tap_n;
+                    for (int kb = kb_first; kb < kblocks; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
                         uint8_t* sa = smem + stage * stage_bytes;
@@ -248,8 +302,8 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                         advance_stage(stage, phase, num_stages);
                     }
                 } else {
-                    int k = 0;
-                    for (int kb = 0; kb < kblocks; ++kb, k += kBK) {
+                    int k = kb_first * kBK;
+                    for (int kb = kb_first; kb < kblocks; ++kb, k += kBK) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
                         uint8_t* sa = smem + stage * stage_bytes;

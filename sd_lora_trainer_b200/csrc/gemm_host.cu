@@ -271,6 +271,8 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
     if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
     g.acc_stages = (d->side && bn > kSideMaxBN) ? 1 : 2;
     g.dbg = g_gemm_dbg;
+    static const int prefetch_env = getenv("B200_PREFETCH_B") ? atoi(getenv("B200_PREFETCH_B")) : 1;
+    g.b_static = (d->b_static && prefetch_env) ? 1 : 0;
     g.D = d->D;
     g.d_sm = d->d_sm;
     g.alpha = d->alpha;

@@ -89,11 +89,12 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
          residual: Optional[torch.Tensor] = None, r_strides: Optional[Tuple[int, int, int, int]] = None,
          nb0: int = 1, nb1: int = 1, splits: int = 1, atomic: bool = False, block_n: int = 0,
          side: Optional[Tuple[Mat, Mat, int, float, Optional[torch.Tensor]]] = None, pair_mode: int = 0,
-         group_out: Optional[Tuple[torch.Tensor, Tuple[int, int]]] = None) -> torch.Tensor:
+         group_out: Optional[Tuple[torch.Tensor, Tuple[int, int]]] = None, static_b: bool = False) -> torch.Tensor:
     """out[b1][b0][m, n] = alpha * sum_seg A_seg.B_seg^T (+bias) (+residual).  segs: (A | Conv3x3, B, K).
     side = (S, B2, r, side_alpha, T_out): fused low-rank path  out += (side_alpha * A.S^T).B2^T, T_out <- the inner
     product (bf16) - see include/b200_lora.h.
-    group_out = (out2, (sm, sn)): the two segments are independent problems; segment 1 accumulates into out2."""
+    group_out = (out2, (sm, sn)): the two segments are independent problems; segment 1 accumulates into out2.
+    static_b: every B-side operand is a parameter tensor the preceding kernel does not write (weights, LoRA factors)."""
     _chk_dev(out, bias, residual)
     d = GemmDesc()
     d.M, d.N, d.num_seg = M, N, len(segs)
@@ -108,6 +109,7 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
             d.A[i] = a.c()
         d.B[i] = b.c()
     d.nb0, d.nb1, d.splits, d.block_n, d.pair_mode = nb0, nb1, splits, block_n, pair_mode
+    d.b_static = int(static_b)
     if side is not None:
         s_mat, b2_mat, r, s_alpha, t_out = side
         d.side, d.side_r, d.S, d.B2, d.side_alpha = 1, r, s_mat.c(), b2_mat.c(), s_alpha

@@ -200,7 +200,7 @@ class Lin:
             T = torch.empty(M, lo.rs, dtype=BF16, device=x.device)
             side = (Mat(lo.A(), lo.r, self.K, self.K), Mat(lo.B(), self.N, lo.r, lo.rs), lo.r, lo.store.scaling, T)
         ops.gemm(y, M, self.N, [(kmajor(x), kmajor(self.W), self.K)], bias=self.b if bias is None else bias,
-                 bias_rows=bias_rows, bias_sb=self.N if bias_rows else 0, residual=residual, side=side)
+                 bias_rows=bias_rows, bias_sb=self.N if bias_rows else 0, residual=residual, side=side, static_b=True)
         if save:
             self.x, self.T = x, T
         return y
@@ -221,7 +221,7 @@ class Lin:
                          alpha=lo.store.scaling)
         if need_dx:
             dx = accum if accum is not None else torch.empty(M, self.K, dtype=BF16, device=dy.device)
-            ops.gemm(dx, M, self.K, [(kmajor(dy), mnmajor(self.W), self.N)], residual=accum, side=side)
+            ops.gemm(dx, M, self.K, [(kmajor(dy), mnmajor(self.W), self.N)], residual=accum, side=side, static_b=True)
         if lo is not None:
             # dB[N, r] += dY^T . T      dA[r, K] += U^T . X   (both operands MN-major, split-K fp32 atomics)
             def wgrad():
@@ -288,7 +288,7 @@ class Conv3:
         ld_out = self.cout if self.cout % 8 == 0 else _r8(self.cout)
         y = (torch.empty if ld_out == self.cout else torch.zeros)(Mo, ld_out, dtype=BF16, device=x.device)
         ops.gemm(y, Mo, self.cout, segs, d_strides=(ld_out, 1, 0, 0), bias=bias, bias_rows=bias_rows,
-                 bias_sb=self.cout if bias_rows else 0, residual=residual)
+                 bias_sb=self.cout if bias_rows else 0, residual=residual, static_b=True)
         self.sv = (x if lo is not None else None, T, N, H, W)
         return y
 
@@ -320,7 +320,7 @@ class Conv3:
         if s == 1 and ops.conv_supported(H, W):
             assert dy.shape[1] == self.cout_p
             ops.gemm(dx, Mi, self.cin, [(Conv3x3(dy, N, H, W, self.cout_p, b_tap_k=self.cout_p), kmajor(self.wd),
-                                         9 * self.cout_p)] + extra)
+                                         9 * self.cout_p)] + extra, static_b=True)
         else:
             dcol = torch.empty(Mo, 9 * self.cin_p, dtype=BF16, device=dy.device)
             ops.gemm(dcol, Mo, 9 * self.cin_p, [(Mat(dy, Mo, self.cout, dy.stride(0)), mnmajor(self.wk), self.cout)])

@@ -40,7 +40,7 @@ def _operand(m: Mat, b0: int, b1: int, mn_extent: int, k_extent: int) -> torch.T
 
 
 def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, bias_sb=0, residual=None,
-         r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0, side=None, pair_mode=0, group_out=None):
+         r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0, side=None, pair_mode=0, group_out=None, static_b=False):
     if group_out is not None:                       # two independent problems sharing one launch
         out2, (sm2, sn2) = group_out
         gemm(out, M, N, [segs[0]], d_strides=d_strides, alpha=alpha, atomic=atomic)

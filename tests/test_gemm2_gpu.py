@@ -87,7 +87,7 @@ def test_pair_fused_side_path_forward(M, N, K, r):
     T = torch.full((M, rs), 7.0, dtype=BF, device="cuda")
     y = torch.empty(M, N, dtype=BF, device="cuda")
     ops.gemm(y, M, N, [(ops.kmajor(x), ops.kmajor(w), K)], bias=bias, residual=res,
-             side=(ops.Mat(A, r, K, K), ops.Mat(Bp, N, r, rs), r, 0.5, T), pair_mode=1)
+             side=(ops.Mat(A, r, K, K), ops.Mat(Bp, N, r, rs), r, 0.5, T), pair_mode=1, static_b=(r != 8))
     Tref = (0.5 * (x.float() @ A.float().T)).to(BF)
     _close(T[:, :r], Tref, what="pair T out")
     ref = x.float() @ w.float().T + Tref.float() @ Bp[:, :r].float().T + bias.float() + res.float()
@@ -123,7 +123,7 @@ def test_pair_fused_side_path_dgrad(M, N, K, r):
     U = torch.empty(M, rs, dtype=BF, device="cuda")
     dx = acc.clone()
     ops.gemm(dx, M, K, [(ops.kmajor(dy), ops.mnmajor(w), N)], residual=dx,
-             side=(ops.Mat(Bp, N, r, rs, mn=True), ops.Mat(A, r, K, K, mn=True), r, 2.0, U), pair_mode=1)
+             side=(ops.Mat(Bp, N, r, rs, mn=True), ops.Mat(A, r, K, K, mn=True), r, 2.0, U), pair_mode=1, static_b=(r == 16))
     Uref = (2.0 * (dy.float() @ Bp[:, :r].float())).to(BF)
     _close(U[:, :r], Uref, what="pair U out")
     _close(dx, dy.float() @ w.float() + Uref.float() @ A.float() + acc.float(), what="pair fused side dgrad")
@@ -139,7 +139,7 @@ def test_pair_back_to_back_launches_are_ordered():
     ref = x.float()
     for w in ws:
         nxt = torch.empty(M, C, dtype=BF, device="cuda")
-        ops.gemm(nxt, M, C, [(ops.kmajor(cur), ops.kmajor(w), C)], pair_mode=1)
+        ops.gemm(nxt, M, C, [(ops.kmajor(cur), ops.kmajor(w), C)], pair_mode=1, static_b=True)   # weights prefetched before the PDL wait
         ref = (ref @ w.float().T).to(BF).float()
         cur = nxt
     torch.cuda.synchronize()
@@ -156,7 +156,8 @@ def test_pair_implicit_conv3x3(N, H, W, C, Cout):
     bias = _rand(Cout, seed=2)
     wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()          # [Cout, (kh, kw, c)]
     out = torch.empty(N * H * W, Cout, dtype=BF, device="cuda")
-    ops.gemm(out, N * H * W, Cout, [(ops.Conv3x3(x, N, H, W, C, b_tap_k=C), ops.kmajor(wk), 9 * C)], bias=bias, pair_mode=1)
+    ops.gemm(out, N * H * W, Cout, [(ops.Conv3x3(x, N, H, W, C, b_tap_k=C), ops.kmajor(wk), 9 * C)], bias=bias, pair_mode=1,
+             static_b=(C % 128 == 0))
     xn = x.float().view(N, H, W, C).permute(0, 3, 1, 2)
     ref = F.conv2d(xn, w.float(), bias.float(), padding=1).permute(0, 2, 3, 1).reshape(N * H * W, Cout)
     _close(out, ref, what=f"pair conv {N}x{H}x{W}x{C}->{Cout}")
