@@ -34,6 +34,9 @@ constexpr int kNumSMs = 148;
 namespace b200 {
 // 4-D bf16 TMA tensor map with 128B swizzle (gemm_host.cu); dims/strides innermost first, strides in elements.
 int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const long long strides[3], const int box[4]);
+// general form: elem_bytes 2 (bf16) | 4 (fp32), swizzle_bytes 128 | 64 | 32 | 0
+int encode_map_ex(CUtensorMap* map, const void* ptr, int elem_bytes, const long long dims[4], const long long strides[3],
+                  const int box[4], int swizzle_bytes);
 
 
 // ---- programmatic dependent launch -------------------------------------------------------------

@@ -64,6 +64,12 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     if (int rc = head_map(&g.mapDO, d_o, L, H, B, ld, 128)) return rc;
     if (int rc = head_map(&g.mapK, k, Lk, H, B, ld, 128)) return rc;
     if (int rc = head_map(&g.mapV, v, Lk, H, B, ld, 128)) return rc;
+    {
+        const long long dims[4] = {ld, L, B, 1};
+        const long long strides[3] = {ld, static_cast<long long>(L) * ld, 0};
+        const int box[4] = {32, 128, 1, 1};
+        if (int rc = encode_map_ex(&g.mapDQ, dq_acc_ws, 4, dims, strides, box, 128)) return rc;
+    }
     g.LSE = lse;
     g.Delta = delta_ws;
     g.dQacc = dq_acc_ws;

@@ -316,11 +316,13 @@ constexpr int kBwdQ = kBwdV + kFaTile;         // 2 stages
 constexpr int kBwdDO = kBwdQ + 2 * kFaTile;    // 2 stages
 constexpr int kBwdP = kBwdDO + 2 * kFaTile;    // [128 q x 128 k] bf16
 constexpr int kBwdDS = kBwdP + 2 * kFaTile;    // [128 q x 128 k] bf16
-constexpr int kBwdBar = kBwdDS + 2 * kFaTile;
+constexpr int kBwdDQ = kBwdDS + 2 * kFaTile;   // dQ block staged as fp32: two [128 q x 32 d] 128B-swizzled boxes (32 KiB)
+constexpr int kBwdBar = kBwdDQ + 2 * kFaTile;
 constexpr int kBwdSmem = kBwdBar + 256;
 
 struct FlashBwdArgs {
     CUtensorMap mapQ, mapDO, mapK, mapV;       // dims (64, rows, H, B); box (64, 128)
+    CUtensorMap mapDQ;                         // fp32 dQ accumulator, dims (ld, L, B); box (32, 128, 1): TMA reduce-add target
     const float* LSE;                          // [B, H, L]
     const float* Delta;                        // [B, H, L] = rowsum(dO * O)
     float* dQacc;                              // fp32 [B*L, ld] accumulated over key blocks (zeroed by the caller)
@@ -497,29 +499,42 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 }
             }
         } else {
-            // ---- dQ epilogue warps: dQ_blk leaves as fp32 reductions (summed over key blocks) ----
+            // ---- dQ epilogue warps: dQ_blk is summed over key blocks in an fp32 global accumulator.  It leaves through
+            //      TMA reduce-add (cp.reduce.async.bulk.tensor .add.f32) from a swizzled smem staging tile: one bulk
+            //      operation per [128 x 32] box instead of 2048 red.global.add.v4 per block, which had this kernel bound
+            //      by the L2 atomic units. ----
+            const bool issuer = (warp == 6 && lane == 0);
+            uint8_t* stg = smem + kBwdDQ;
             for (int i = 0; i < nq; ++i) {
-                const int q = i * 128 + row;
                 mbar_wait(dq_full, i & 1);
                 tc_fence_after();
-                float* dst = g.dQacc + (static_cast<long long>(b) * g.L + q) * g.ld + h * 64;
+                if (i > 0) {
+                    if (issuer) bulk_wait_read<0>();            // the previous block's reductions have read the staging tile
+                    named_bar_sync(2, 128);
+                }
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t r[32];
                     tmem_ld32(t_dQ + lane_off + c * 32, r);
                     tmem_ld_wait();
-                    if (q < g.L) {
+                    uint8_t* rowp = stg + c * kFaTile + row * 128;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + e * 4),
-                                      make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
-                                                  __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3])));
-                    }
+                    for (int e = 0; e < 8; ++e)
+                        *reinterpret_cast<uint4*>(rowp + ((e ^ (row & 7)) * 16)) =
+                            make_uint4(r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
                 }
                 tc_fence_before();
+                fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(dq_free);
+                if (lane == 0) mbar_arrive(dq_free);            // TMEM dQ drained: the next block's MMA may overwrite it
+                named_bar_sync(2, 128);
+                if (issuer) {
+                    tma_reduce_add_3d(&g.mapDQ, stg, h * 64, i * 128, b);
+                    tma_reduce_add_3d(&g.mapDQ, stg + kFaTile, h * 64 + 32, i * 128, b);
+                    bulk_commit();
+                }
             }
+            if (issuer) bulk_wait<0>();                         // every reduction performed before the grid completes
         }
         // ---- dV (softmax warps) / dK (epilogue warps): thread <-> key row ----
         mbar_wait(dkv_full, 0);

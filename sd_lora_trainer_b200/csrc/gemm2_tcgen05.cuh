@@ -32,8 +32,8 @@ constexpr int k2ABytes = 128 * 64 * 2;           // one CTA's A tile per stage
 constexpr int k2RingBytes = 160 * 1024;
 constexpr int k2TOff = k2RingBytes;              // T tile (16 KiB, 128B-swizzled K-major A operand of the final MMA)
 constexpr int k2BarOff = k2TOff + 16384;
-constexpr int k2EpiOff = k2BarOff + 512;
-constexpr int k2EpiBytes = 8 * 32 * kEpiLd * 4;
+constexpr int k2EpiOff = k2BarOff + 1024;        // 1024-aligned: the TMA-store staging boxes are 64B-swizzled
+constexpr int k2EpiBytes = 8 * 32 * kEpiLd * 4;  // >= 8 warps x 2 x 2 KiB TMA-store boxes
 constexpr int k2SmemBytes = k2EpiOff + k2EpiBytes;
 static_assert(k2SmemBytes <= 232448, "shared memory budget");
 
@@ -50,6 +50,9 @@ struct Gemm2Args {
     // B / S / B2 (weights, LoRA factors) are not written by the preceding kernel of the stream: the producer fetches
     // the first ring-full of them BEFORE griddepcontrol.wait, overlapping the predecessor's tail
     int b_static;
+    // bf16 row-major output through TMA: each epilogue warp stages [32 rows x 32 columns] boxes (64B swizzle) and one
+    // lane issues cp.async.bulk.tensor stores (mapD); needs 16-byte aligned rows of D (and R); M / N edges are clipped
+    int tma_store;
     float alpha, side_alpha;
     long long d_sm, r_sm, t_ld, bias_sb;
     void* D;
@@ -57,7 +60,7 @@ struct Gemm2Args {
     const __nv_bfloat16* R;
     __nv_bfloat16* T_out;
     long long* dbg;           // developer probe: per-CTA globaltimer stamps [cta][16] (nullptr in production)
-    CUtensorMap mapA, mapB, mapS, mapB2, mapA2;
+    CUtensorMap mapA, mapB, mapS, mapB2, mapA2, mapD;
 };
 
 struct Epi2 {
@@ -146,6 +149,89 @@ __device__ __forceinline__ void epi2_chunk(const Epi2& e, const uint32_t (&raw)[
         }
     }
     __syncwarp();
+}
+
+// One [32 x 32] chunk, bf16 row-major output, through a TMA store: thread <-> row does alpha / bias / residual on its 32
+// accumulators with 16-byte loads, packs to bf16, writes its 64-byte row into the 64B-swizzled staging box (conflict
+// free) and lane 0 issues the bulk tensor store.  ~90 instructions per chunk and no st.global at all.
+__device__ __forceinline__ void epi2_chunk_tma(const Epi2& e, const CUtensorMap* mapD, const uint32_t (&raw)[32], uint8_t* box,
+                                               int lane, int m_warp, int n_chunk) {
+    const int m = m_warp + lane;
+    float v[32];
+    const float alpha = e.alpha;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * alpha;
+    if (e.bias != nullptr) {
+        const int mb = e.bias_rows ? min(m, e.M - 1) / e.bias_rows : 0;
+        const uint4* bp = reinterpret_cast<const uint4*>(e.bias + mb * e.bias_sb + n_chunk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 w = __ldg(bp + j);
+            const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[8 * j + 2 * q] += __uint_as_float(u[q] << 16);
+                v[8 * j + 2 * q + 1] += __uint_as_float(u[q] & 0xffff0000u);
+            }
+        }
+    }
+    if (e.R != nullptr && m < e.M) {
+        const uint4* rp = reinterpret_cast<const uint4*>(e.R + static_cast<long long>(m) * e.r_sm + n_chunk);
+        uint4 w4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w4[j] = rp[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t u[4] = {w4[j].x, w4[j].y, w4[j].z, w4[j].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[8 * j + 2 * q] += __uint_as_float(u[q] << 16);
+                v[8 * j + 2 * q + 1] += __uint_as_float(u[q] & 0xffff0000u);
+            }
+        }
+    }
+    uint8_t* rowp = box + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+        w.x = *reinterpret_cast<const uint32_t*>(&h0);
+        w.y = *reinterpret_cast<const uint32_t*>(&h1);
+        w.z = *reinterpret_cast<const uint32_t*>(&h2);
+        w.w = *reinterpret_cast<const uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) * 16)) = w;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(mapD, box, n_chunk, m_warp);
+        bulk_commit();
+    }
+}
+
+// Ragged chunk (fewer than 32 valid columns at the N edge) when the TMA-store path owns the staging memory: plain
+// thread <-> row scalar stores.  Rare (none of the step's shapes has a ragged edge), so simplicity wins.
+__device__ __forceinline__ void epi2_chunk_direct(const Epi2& e, const uint32_t (&raw)[32], int lane, int m_warp, int n_chunk,
+                                                  int ncols) {
+    const int m = m_warp + lane;
+    if (m >= e.M) return;
+    const __nv_bfloat16* bp = e.bias ? e.bias + (e.bias_rows ? (m / e.bias_rows) * e.bias_sb : 0) : nullptr;
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(e.D) + static_cast<long long>(m) * e.d_sm;
+    const __nv_bfloat16* rp = e.R ? e.R + static_cast<long long>(m) * e.r_sm : nullptr;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int n = n_chunk + j;
+        if (j < ncols && n < e.N) {
+            float x = __uint_as_float(raw[j]) * e.alpha;
+            if (bp) x += __bfloat162float(bp[n]);
+            if (rp) x += __bfloat162float(rp[n]);
+            dp[n] = __float2bfloat16_rn(x);
+        }
+    }
 }
 
 template <int kEpi>
@@ -454,6 +540,11 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
         const int half = ew >> 2;                     // which 32-column chunks this warp takes (even / odd)
         const int lane_base = (warp & 3) * 32;
         float* stage_buf = reinterpret_cast<float*>(smem + k2EpiOff) + ew * (32 * kEpiLd);
+        // TMA-store staging: this warp's two 2 KiB boxes.  They alias the padded patches of the staged path, so a launch
+        // uses one or the other (tma_store is per launch); ragged chunks of a TMA launch take epi2_chunk_direct.
+        uint8_t* tma_box = smem + k2EpiOff + ew * 4096;
+        const int tma_store = g.tma_store;
+        int tma_buf = 0;
         const uint32_t tmem_empty_leader = mapa_u32(smem_u32(tmem_empty_bar), 0);
         const uint32_t t_ready_leader = mapa_u32(smem_u32(t_ready_bar), 0);
         Epi2 e;
@@ -533,7 +624,20 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                 tmem_ld32(taddr + c0, raw);
                 tmem_ld_wait();
                 if (n0 + c0 >= e.N) continue;          // warp-uniform
-                epi2_chunk<kEpi>(e, raw, stage_buf, lane, m_warp, n0 + c0, min(32, BN - c0));
+                if (kEpi == 0 && tma_store) {
+                    if (m_warp >= e.M) continue;       // rows past the M edge (warp-uniform)
+                    if (n0 + c0 + 32 <= e.N) {
+                        // double-buffered staging box: the store issued two chunks ago must have read its smem
+                        if (lane == 0) bulk_wait_read<1>();
+                        __syncwarp();
+                        epi2_chunk_tma(e, &g.mapD, raw, tma_box + (tma_buf & 1) * 2048, lane, m_warp, n0 + c0);
+                        ++tma_buf;
+                    } else {
+                        epi2_chunk_direct(e, raw, lane, m_warp, n0 + c0, min(32, BN - c0));
+                    }
+                } else {
+                    epi2_chunk<kEpi>(e, raw, stage_buf, lane, m_warp, n0 + c0, min(32, BN - c0));
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -546,6 +650,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
         }
     }
 
+    if (warp >= 2 && lane == 0) bulk_wait<0>();       // this warp's TMA stores are complete before the grid is
     tc_fence_before();
     if (threadIdx.x == 0) dbg_stamp(dbg, 7);
     cluster_sync_all();       // no CTA leaves (or frees TMEM) while its peer may still read its smem / signal its barriers

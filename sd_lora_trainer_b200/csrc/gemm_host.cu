@@ -40,9 +40,10 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
-// 4-D bf16 tensor map, 128B swizzle.  dims/strides innermost first; strides in elements (dims 1..3).
-int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const long long strides[3],
-                      const int box[4]) {
+// 4-D tensor map.  dims/strides innermost first; strides in ELEMENTS (dims 1..3).  elem_bytes 2 = bf16, 4 = fp32;
+// swizzle_bytes 128 | 64 | 32 | 0.
+int encode_map_ex(CUtensorMap* map, const void* ptr, int elem_bytes, const long long dims[4], const long long strides[3],
+                  const int box[4], int swizzle_bytes) {
     auto fn = get_encode_fn();
     if (!fn) return set_error(4, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint64_t gdim[4], gstr[3];
@@ -53,18 +54,26 @@ int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const
     }
     for (int i = 0; i < 3; ++i) {
         long long s = strides[i];
-        if (s <= 0) s = 8;                       // degenerate (extent-1) dims still need a legal stride
-        gstr[i] = static_cast<cuuint64_t>(s) * 2;
-        if (gstr[i] % 16) return set_error(2, "gemm: stride %lld elements is not a multiple of 8", s);
+        if (s <= 0) s = 16 / elem_bytes;         // degenerate (extent-1) dims still need a legal stride
+        gstr[i] = static_cast<cuuint64_t>(s) * elem_bytes;
+        if (gstr[i] % 16) return set_error(2, "tensor map: stride %lld elements is not a multiple of 16 bytes", s);
     }
-    if (reinterpret_cast<uintptr_t>(ptr) % 16) return set_error(2, "gemm: operand base not 16-byte aligned");
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, bdim, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (reinterpret_cast<uintptr_t>(ptr) % 16) return set_error(2, "tensor map: base not 16-byte aligned");
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(map, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                    const_cast<void*>(ptr), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return set_error(4, "cuTensorMapEncodeTiled failed (%d): dims %lld,%lld,%lld,%lld box %d,%d,%d,%d", (int)r,
                          dims[0], dims[1], dims[2], dims[3], box[0], box[1], box[2], box[3]);
     return 0;
+}
+// 4-D bf16 tensor map, 128B swizzle (every GEMM / attention operand).
+int encode_map(CUtensorMap* map, const void* ptr, const long long dims[4], const long long strides[3],
+                      const int box[4]) {
+    return encode_map_ex(map, ptr, 2, dims, strides, box, 128);
 }
 
 static int encode_operand(CUtensorMap* map, const b200_operand_t& op, int box_rows_kmajor, int nb0, int nb1) {
@@ -284,6 +293,15 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
     const int esz = d->d_fp32 ? 4 : 2;
     g.vec_ok = (reinterpret_cast<uintptr_t>(d->D) % (4 * esz) == 0) && (d->d_sm % 4 == 0) &&
                (!d->R || (reinterpret_cast<uintptr_t>(d->R) % 8 == 0 && d->r_sm % 4 == 0));
+    static const int tma_epi_env = getenv("B200_TMA_EPI") ? atoi(getenv("B200_TMA_EPI")) : 1;
+    auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+    if (tma_epi_env && !d->d_fp32 && bn % 32 == 0 && al16(d->D) && d->d_sm % 8 == 0 &&
+        (!d->R || (al16(d->R) && d->r_sm % 8 == 0)) && (!d->bias || (al16(d->bias) && d->bias_sb % 8 == 0))) {
+        const long long dD[4] = {d->N, d->M, 1, 1}, sD[3] = {d->d_sm, 0, 0};
+        const int boxD[4] = {32, 32, 1, 1};
+        if (int rc = encode_map_ex(&g.mapD, d->D, 2, dD, sD, boxD, 64)) return rc;
+        g.tma_store = 1;
+    }
     const int pairs = g.total_tiles < kNumSMs / 2 ? g.total_tiles : kNumSMs / 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t le;

@@ -70,6 +70,33 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uin
         : "memory");
 }
 
+// ---- TMA stores / reductions from shared memory (bulk async-group completion) -------------------
+__device__ __forceinline__ void tma_store_2d(const void* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// global[tile] += smem[tile] (element type from the tensor map), performed by the TMA / L2 at line granularity
+__device__ __forceinline__ void tma_reduce_add_3d(const void* map, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {      // the source smem of all but kPending groups may be reused
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void bulk_wait() {           // all but kPending groups are complete (writes performed)
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- tcgen05 / TMEM ------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
