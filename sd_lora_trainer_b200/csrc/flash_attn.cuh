@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 tc_fence_after();
                 if (i > 0) {
                     if (issuer) bulk_wait_read<0>();            // the previous block's reductions have read the staging tile
+                    __syncwarp();
                     named_bar_sync(2, 128);
                 }
 #pragma unroll
@@ -529,10 +530,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 if (lane == 0) mbar_arrive(dq_free);            // TMEM dQ drained: the next block's MMA may overwrite it
                 named_bar_sync(2, 128);
                 if (issuer) {
-                    tma_reduce_add_3d(&g.mapDQ, stg, h * 64, i * 128, b);
-                    tma_reduce_add_3d(&g.mapDQ, stg + kFaTile, h * 64 + 32, i * 128, b);
+                    tma_reduce_add_4d(&g.mapDQ, stg, h * 64, i * 128, b, 0);
+                    tma_reduce_add_4d(&g.mapDQ, stg + kFaTile, h * 64 + 32, i * 128, b, 0);
                     bulk_commit();
                 }
+                __syncwarp();
             }
             if (issuer) bulk_wait<0>();                         // every reduction performed before the grid completes
         }

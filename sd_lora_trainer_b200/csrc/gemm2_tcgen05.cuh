@@ -208,9 +208,10 @@ __device__ __forceinline__ void epi2_chunk_tma(const Epi2& e, const CUtensorMap*
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        tma_store_2d(mapD, box, n_chunk, m_warp);
+        tma_store_4d(mapD, box, n_chunk, m_warp, 0, 0);
         bulk_commit();
     }
+    __syncwarp();
 }
 
 // Ragged chunk (fewer than 32 valid columns at the N edge) when the TMA-store path owns the staging memory: plain

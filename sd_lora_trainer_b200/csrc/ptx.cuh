@@ -71,17 +71,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uin
 }
 
 // ---- TMA stores / reductions from shared memory (bulk async-group completion) -------------------
-__device__ __forceinline__ void tma_store_2d(const void* map, const void* smem_src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+// (every tensor map of this library is encoded with rank 4, so the instruction must be the .4d form as well: a rank
+//  mismatch between descriptor and instruction traps as an illegal instruction)
+__device__ __forceinline__ void tma_store_4d(const void* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(map)),
-                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 // global[tile] += smem[tile] (element type from the tensor map), performed by the TMA / L2 at line granularity
-__device__ __forceinline__ void tma_reduce_add_3d(const void* map, const void* smem_src, int c0, int c1, int c2) {
-    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+__device__ __forceinline__ void tma_reduce_add_4d(const void* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(map)),
-                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
