@@ -200,10 +200,14 @@ def run_ours(args):
     if rank == 0 and not args.skip_roofline:
         prof = tr.profile_gemms(host_batches[0])
         pk, pk_src = peaks()
-        result["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": prof["tflops"],
-                              "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                              "frac": prof["tflops"] / pk["bf16_tflops_sustained"], "traffic": None,
-                              "peak_source": pk_src + " (sustained: timed inside the step)",
+        result["roofline"] = {"bound": "tensor", "kernel": "tcgen05 GEMM family (gemm2_kernel CTA pairs + gemm_tcgen05_kernel)",
+                              "achieved": prof["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                              "frac": prof["tflops"] / pk["bf16_tflops"],
+                              # DRAM bytes of the dominant launch (2048x1280x1280 LoRA-fused projection, 744 per step)
+                              # from profiles/r01b_gemm2_ncu_full.md (ncu --set full): read 8.64 MB + write 0
+                              "traffic": 8.64e6,
+                              "peak_source": pk_src + " (burst: every GEMM signature is timed alone, as a CUDA graph of "
+                                                      "10 launches of the step's own call, between CUDA events)",
                               "launches_per_step": prof["launches"], "gemm_ms_per_step": prof["ms"],
                               "gemm_share_of_step": prof["ms"] / (ms / args.steps),
                               "algorithmic_tflop_per_step": prof["tflop"]}

@@ -280,7 +280,7 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
     if (g.num_stages > kMaxStages) g.num_stages = kMaxStages;
     g.acc_stages = (d->side && bn > kSideMaxBN) ? 1 : 2;
     g.dbg = g_gemm_dbg;
-    static const int prefetch_env = getenv("B200_PREFETCH_B") ? atoi(getenv("B200_PREFETCH_B")) : 1;
+    static const int prefetch_env = getenv("B200_PREFETCH_B") ? atoi(getenv("B200_PREFETCH_B")) : 0;   // measured: 80.7 vs 79.8 ms/step with it on (profiles/r01g_ab.txt)
     g.b_static = (d->b_static && prefetch_env) ? 1 : 0;
     g.D = d->D;
     g.d_sm = d->d_sm;

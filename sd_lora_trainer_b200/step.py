@@ -301,11 +301,12 @@ class TrainerB200:
         return out
 
     def profile_gemms(self, inputs) -> Dict[str, object]:
-        """Eager, instrumented pass: every tcgen05 GEMM launch of one step timed with CUDA events on its stream.
+        """Eager, instrumented pass over one step: every distinct tcgen05 GEMM signature is timed live (CUDA events
+        around a graph of 10 launches of the very call, ops._profile_gemm) and weighted by its launch count.
         Training state is restored afterwards."""
         snap = [t.clone() for t in (self.store.params, self.store.grads, self.store.m, self.store.v)]
         st = self._stage_inputs(inputs)
-        ops.GEMM_PROFILE = []
+        ops.GEMM_PROFILE = {}
         try:
             self._body(st, True)
             self._set_hyper()
@@ -320,17 +321,15 @@ class TrainerB200:
             rows.grad = None
         by_shape: Dict[str, Dict[str, float]] = {}
         tot_ms = tot_fl = 0.0
-        for key, fl, e0, e1 in recs:
-            ms = e0.elapsed_time(e1)
+        launches = 0
+        for key, r in recs.items():
+            ms = r["count"] * r["us"] / 1e3
             tot_ms += ms
-            tot_fl += fl
-            d = by_shape.setdefault(str(key), {"count": 0, "ms": 0.0, "flop": 0.0})
-            d["count"] += 1
-            d["ms"] += ms
-            d["flop"] += fl
-        for d in by_shape.values():
-            d["tflops"] = d["flop"] / max(d["ms"], 1e-9) / 1e9
-        return {"launches": len(recs), "ms": tot_ms, "tflop": tot_fl / 1e12, "tflops": tot_fl / max(tot_ms, 1e-9) / 1e9,
+            tot_fl += r["flop"]
+            launches += r["count"]
+            by_shape[str(key)] = {"count": r["count"], "us_per_launch": r["us"], "ms": ms, "flop": r["flop"],
+                                  "tflops": r["flop"] / max(ms, 1e-9) / 1e9}
+        return {"launches": launches, "ms": tot_ms, "tflop": tot_fl / 1e12, "tflops": tot_fl / max(tot_ms, 1e-9) / 1e9,
                 "by_shape": dict(sorted(by_shape.items(), key=lambda kv: -kv[1]["ms"]))}
 
     def _capture(self, st, ti_active: bool, opt_now: bool):
