@@ -67,6 +67,17 @@ __device__ __forceinline__ void store_p_chunk(uint8_t* tile, int row, int c0, co
     }
 }
 
+// same, for 32 values already packed to bf16 pairs
+__device__ __forceinline__ void store_packed_chunk(uint8_t* tile, int row, int c0, const uint32_t (&v)[16]) {
+    uint8_t* base = tile + (c0 >> 6) * kFaTile + row * 128;
+    const int j0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int phys = (j0 + j) ^ (row & 7);
+        *reinterpret_cast<uint4*>(base + phys * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+}
+
 __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_constant__ FlashFwdArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFwdBar);
@@ -405,21 +416,28 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             const uint32_t sk = smem_u32(smem + kBwdK), sv = smem_u32(smem + kBwdV);
             const uint32_t sp = smem_u32(smem + kBwdP), sds = smem_u32(smem + kBwdDS);
             mbar_wait(kv_full, 0);
-            for (int i = 0; i < nq; ++i) {
+            // Software-pipelined: S / dP of block i+1 are issued BEFORE dV / dK / dQ of block i, as soon as the softmax
+            // warps have pulled S / dP of block i out of TMEM, so the softmax of block i+1 overlaps the three
+            // gradient MMAs of block i (the loop used to be a strict MMA -> softmax -> MMA chain).
+            auto issue_sdp = [&](int i) {
                 const int s = i & 1;
                 const uint32_t sq = smem_u32(smem + kBwdQ + s * kFaTile), sdo = smem_u32(smem + kBwdDO + s * kFaTile);
                 mbar_wait(&qdo_full[s], (i >> 1) & 1);
                 mbar_wait(sdp_free, (i & 1) ^ 1);
                 tc_fence_after();
-                {
-                    const uint64_t aq = umma_desc(sq, 16, 1024), bk = umma_desc(sk, 16, 1024);
-                    const uint64_t ado = umma_desc(sdo, 16, 1024), bv = umma_desc(sv, 16, 1024);
+                const uint64_t aq = umma_desc(sq, 16, 1024), bk = umma_desc(sk, 16, 1024);
+                const uint64_t ado = umma_desc(sdo, 16, 1024), bv = umma_desc(sv, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(t_S, aq + 2 * k, bk + 2 * k, id_kk, k > 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(t_S, aq + 2 * k, bk + 2 * k, id_kk, k > 0);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(t_dP, ado + 2 * k, bv + 2 * k, id_kk, k > 0);
-                }
+                for (int k = 0; k < 4; ++k) umma_bf16(t_dP, ado + 2 * k, bv + 2 * k, id_kk, k > 0);
                 umma_commit(sdp_full);
+            };
+            issue_sdp(0);
+            for (int i = 0; i < nq; ++i) {
+                const int s = i & 1;
+                const uint32_t sq = smem_u32(smem + kBwdQ + s * kFaTile), sdo = smem_u32(smem + kBwdDO + s * kFaTile);
+                if (i + 1 < nq) issue_sdp(i + 1);
                 mbar_wait(pds_full, i & 1);
                 mbar_wait(dq_free, (i & 1) ^ 1);
                 tc_fence_after();
@@ -462,9 +480,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 const float lse2 = qok ? g.LSE[stat_base + q] * 1.4426950408889634f : 0.f;
                 const float delta = qok ? g.Delta[stat_base + q] : 0.f;
                 mbar_wait(sdp_full, i & 1);
-                mbar_wait(pds_free, (i & 1) ^ 1);
                 tc_fence_after();
                 const bool full_blk = (kvalid == 128) && (i * 128 + 128 <= g.L);     // warp-uniform
+                uint32_t pp[2][16], pd[2][16];                 // this thread's 64 P and dS values, packed bf16
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     const int c = chalf + cc;
@@ -487,16 +505,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                             ds[e] = p[e] * (__uint_as_float(rp[e]) - delta) * g.scale;
                         }
                     }
-                    store_p_chunk(smem + kBwdP, row, c * 32, p);
-                    store_p_chunk(smem + kBwdDS, row, c * 32, ds);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        pp[cc][e] = pack_bf16(p[2 * e], p[2 * e + 1]);
+                        pd[cc][e] = pack_bf16(ds[2 * e], ds[2 * e + 1]);
+                    }
                 }
+                // S / dP are out of TMEM: the MMA warp may start block i+1 while this block's tiles are still being staged
                 tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sdp_free);
+                mbar_wait(pds_free, (i & 1) ^ 1);             // the gradient MMAs of block i-1 have read the P / dS tiles
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    store_packed_chunk(smem + kBwdP, row, (chalf + cc) * 32, pp[cc]);
+                    store_packed_chunk(smem + kBwdDS, row, (chalf + cc) * 32, pd[cc]);
+                }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(sdp_free);
-                    mbar_arrive(pds_full);
-                }
+                if (lane == 0) mbar_arrive(pds_full);
             }
         } else {
             // ---- dQ epilogue warps: dQ_blk is summed over key blocks in an fp32 global accumulator.  It leaves through
