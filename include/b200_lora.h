@@ -162,6 +162,10 @@ int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, 
 /* out[b, c] = sum_p x[b, p, c]  (x: [batch, hw, C] bf16, C % 8 == 0) - gradient of the per-image time-embedding bias.
  * scratch: batch*C fp32 (zeroed by the call; rows are split over CTAs and combined with fp32 reductions). */
 int b200_colsum(const void* x, void* out, float* scratch, int32_t batch, int64_t hw, int32_t C, void* stream);
+/* K-major copies of all LoRA-B factors in one launch: for every table row (off_B, off_Bt, N, rs) - offsets in
+ * elements into the flat buffers - bt[off_Bt + j*N + n] = params[off_B + n*rs + j].  The fused input-gradient GEMM
+ * (dX = dY.W + (s.dY.B).A, peft lora.Linear backward) reads the copy as its side operand. table: device int64 [n, 4]. */
+int b200_lora_transpose_b(const void* params, void* bt, const int64_t* table, int32_t n_entries, void* stream);
 /* Bicubic resize of channels-last bf16 maps: F.interpolate(x, size=(Ho, Wo), mode="bicubic") exactly as the reference
  * applies it to the captured cross-attention maps (trainer/ti_cross_attn_loss.py:262-266: align_corners=False, no
  * antialias, A = -0.75, clamped taps).  x: [B, Hi, Wi, C] with pixel stride ld_in, y: [B, Ho, Wo, C] with pixel stride

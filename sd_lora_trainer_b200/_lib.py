@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200_col2im3x3": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_shift_stack9": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_colsum": [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p],
+    "b200_lora_transpose_b": [c_void_p, c_void_p, c_void_p, c_int32, c_void_p],
     "b200_bicubic_fwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
     "b200_bicubic_bwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
     "b200_timestep_embedding": [c_void_p, c_void_p, c_int32, c_int32, c_void_p],

@@ -366,6 +366,23 @@ __global__ void colsum_finish_kernel(const float* __restrict__ acc, bf16* __rest
     if (i < n) out[i] = __float2bfloat16_rn(acc[i]);
 }
 
+// K-major copies of every LoRA-B factor: bt[j, n] = B[n, j].  One launch for all layers (table rows: offset of B in
+// the flat parameter buffer, offset of the copy, N, row stride rs); one CTA per layer.  The input-gradient GEMM reads
+// the copy as its rank-r side operand: read in place (MN-major) that operand is a 64 x 32-byte box every CTA re-fetches
+// at every k-block - an L2 hot spot that cost 3.7 us per launch.
+__global__ void lora_bt_kernel(const bf16* __restrict__ params, bf16* __restrict__ bt, const long long* __restrict__ table) {
+    pdl_launch();
+    pdl_wait();
+    const long long* e = table + 4LL * blockIdx.x;
+    const bf16* src = params + e[0];
+    bf16* dst = bt + e[1];
+    const int N = static_cast<int>(e[2]), rs = static_cast<int>(e[3]);
+    for (int idx = threadIdx.x; idx < N * rs; idx += blockDim.x) {
+        const int j = idx / N, n = idx - j * N;           // consecutive threads -> consecutive n: coalesced writes
+        dst[idx] = src[static_cast<long long>(n) * rs + j];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Bicubic resize of channels-last maps (F.interpolate(mode="bicubic", align_corners=False, antialias=False) as the
 // reference applies it to the captured cross-attention maps, ti_cross_attn_loss.py:262-266): A = -0.75, taps clamped
@@ -619,6 +636,13 @@ extern "C" int b200_colsum(const void* x, void* out, float* scratch, int32_t bat
     launch_pdl(colsum_finish_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, ST, static_cast<const float*>(scratch),
                static_cast<bf16*>(out), n);
     B200_CHECK_LAUNCH("colsum_finish");
+    return 0;
+}
+extern "C" int b200_lora_transpose_b(const void* params, void* bt, const int64_t* table, int32_t n_entries, void* stream) {
+    B200_CHECK_ARG(n_entries >= 1 && params && bt && table, "lora_transpose_b: bad arguments");
+    launch_pdl(lora_bt_kernel, dim3(n_entries), dim3(256), 0, ST, static_cast<const bf16*>(params), static_cast<bf16*>(bt),
+               reinterpret_cast<const long long*>(table));
+    B200_CHECK_LAUNCH("lora_transpose_b");
     return 0;
 }
 extern "C" int b200_bicubic_fwd(const void* x, void* y, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,

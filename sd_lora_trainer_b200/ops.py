@@ -318,6 +318,13 @@ def colsum(x: torch.Tensor, batch: int, hw: int, C_: int):
     return out
 
 
+def lora_transpose_b(params: torch.Tensor, bt: torch.Tensor, table: torch.Tensor):
+    """bt <- K-major copies [rs, N] of every LoRA-B [N, rs] listed in `table` (device int64 [n, 4])."""
+    assert table.dtype == torch.int64 and table.is_cuda and table.dim() == 2 and table.shape[1] == 4
+    check(_lib.load().b200_lora_transpose_b(params.data_ptr(), bt.data_ptr(), table.data_ptr(), table.shape[0], _stream()),
+          "lora_transpose_b")
+
+
 def bicubic_fwd(x: torch.Tensor, Ho: int, Wo: int):
     """x: [B, Hi, Wi, C] bf16 channels-last view (unit channel stride, dense rows) -> [B, Ho, Wo, C]."""
     B, Hi, Wi, C_ = x.shape

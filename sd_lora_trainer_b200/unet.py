@@ -79,12 +79,12 @@ def _wgrad_splits(out_rows: int, reduce_len: int) -> int:
 # LoRA parameter store: ONE flat bf16 parameter buffer, ONE flat fp32 gradient buffer, bf16 Adam moments
 # =================================================================================================
 class LoraSlot:
-    __slots__ = ("name", "kind", "r", "rs", "fan_in", "fan_out", "offA", "offB", "store")
+    __slots__ = ("name", "kind", "r", "rs", "fan_in", "fan_out", "offA", "offB", "offBt", "store")
 
     def __init__(self, name, kind, r, fan_in, fan_out):
         self.name, self.kind, self.r, self.rs = name, kind, r, _r8(r)
         self.fan_in, self.fan_out = fan_in, fan_out
-        self.offA = self.offB = -1
+        self.offA = self.offB = self.offBt = -1
         self.store = None
 
     # A: linear [r, K]; conv [9*r, Cin] (tap-major master layout).  B: [N, rs] with columns >= r kept at zero.
@@ -101,6 +101,10 @@ class LoraSlot:
 
     def B(self):
         return self.store.params[self.offB:self.offB + self.fan_out * self.rs].view(self.fan_out, self.rs)
+
+    def Bt(self):
+        """K-major copy [rs, N] of B (linear layers), refreshed once per step by LoraStore.refresh_bt()."""
+        return self.store.params_bt[self.offBt:self.offBt + self.fan_out * self.rs].view(self.rs, self.fan_out)
 
     def gA(self):
         return self.store.grads[self.offA:self.offA + self.a_rows * self.fan_in].view(self.a_rows, self.fan_in)
@@ -136,9 +140,22 @@ class LoraStore:
         n = self.total + extra
         self.n_lora = self.total
         self.params = torch.zeros(n, dtype=BF16, device=self.device)
+        # K-major copies of the linear layers' B factors (side operand of the fused input-gradient GEMM)
+        rows, off = [], 0
+        for s in self.slots:
+            if s.kind == "linear":
+                s.offBt = off
+                rows.append([s.offB, off, s.fan_out, s.rs])
+                off += _r8(s.fan_out * s.rs)
+        self.params_bt = torch.zeros(max(off, 8), dtype=BF16, device=self.device)
+        self.bt_table = torch.tensor(rows, dtype=torch.int64, device=self.device) if rows else None
         self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.m = torch.zeros(n, dtype=BF16, device=self.device)
         self.v = torch.zeros(n, dtype=BF16, device=self.device)
+
+    def refresh_bt(self):
+        if self.bt_table is not None:
+            ops.lora_transpose_b(self.params, self.params_bt, self.bt_table)
 
     @property
     def numel_logical(self) -> int:
@@ -215,7 +232,8 @@ class Lin:
             U = torch.empty(M, rs, dtype=BF16, device=dy.device)
             if need_dx:
                 # dX = dY.W + (s.dY.B).A in ONE launch; U = s.dY.B leaves for the dA weight-gradient GEMM
-                side = (Mat(lo.B(), self.N, r, rs, mn=True), Mat(lo.A(), r, self.K, self.K, mn=True), r, lo.store.scaling, U)
+                # (S = the K-major copy of B: read in place it is a tiny MN-major box every CTA re-fetches per k-block)
+                side = (Mat(lo.Bt(), r, self.N, self.N), Mat(lo.A(), r, self.K, self.K, mn=True), r, lo.store.scaling, U)
             else:
                 ops.gemm(U, M, r, [(kmajor(dy), Mat(lo.B(), self.N, r, rs, mn=True), self.N)], d_strides=(rs, 1, 0, 0),
                          alpha=lo.store.scaling)
@@ -804,6 +822,7 @@ class UNetB200:
         d_ctx = torch.zeros(B * Lctx, Dc, dtype=BF16, device=dev)
         d_temb_act = torch.zeros(B, a.time_embed_dim, dtype=BF16, device=dev)
         WGRAD.begin(os.environ.get("B200_WGRAD_STREAM", "0") == "1" and dev.type == "cuda")
+        self.store.refresh_bt()                        # LoRA-B does not change between here and the optimizer
         # hooked layers were enumerated down_blocks..., up_blocks...; backward visits up (reversed) then down (reversed)
         n_down_hooks = sum(len(t.blocks) for rs, at, ds in self.down if at is not None for t in at)
         ds_down = list(dscores[:n_down_hooks]) if dscores is not None else None

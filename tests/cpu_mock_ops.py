@@ -243,6 +243,11 @@ def colsum(x, batch, hw, C_):
     return _bf(x.float().view(batch, hw, C_).sum(1))
 
 
+def lora_transpose_b(params, bt, table):
+    for off_b, off_bt, n, rs in table.tolist():
+        bt[off_bt:off_bt + n * rs].view(rs, n).copy_(params[off_b:off_b + n * rs].view(n, rs).t())
+
+
 def bicubic_fwd(x, Ho, Wo):
     return _bf(F.interpolate(x.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bicubic").permute(0, 2, 3, 1).contiguous())
 

@@ -197,3 +197,29 @@ def test_pair_two_plain_segments():
     y = torch.empty(M, N, dtype=BF, device="cuda")
     ops.gemm(y, M, N, [(ops.kmajor(x), ops.kmajor(w), K), (ops.kmajor(T), ops.kmajor(Bm), r)], pair_mode=1)
     _close(y, x.float() @ w.float().T + T.float() @ Bm.float().T, what="pair two segments")
+
+
+@pytest.mark.parametrize("M,N,K,r,pair", [(2048, 1280, 1280, 16, 1), (512, 640, 320, 16, 1), (300, 264, 200, 8, 1),
+                                          (2048, 1280, 1280, 32, 1), (154, 2048, 1280, 16, -1), (2048, 1280, 1280, 16, -1)])
+def test_fused_side_dgrad_with_kmajor_b_copy(M, N, K, r, pair):
+    """The step's input-gradient form: W read MN-major, the side operand a K-major COPY of LoRA-B (ops.lora_transpose_b),
+    LoRA-A read MN-major."""
+    from sd_lora_trainer_b200 import ops
+    rs = (r + 7) // 8 * 8
+    dy, w = _rand(M, N), _rand(N, K, seed=1, scale=0.05)
+    A = _rand(r, K, seed=2, scale=0.1)
+    flat = torch.zeros(N * rs + 64, dtype=BF, device="cuda")
+    Bp = flat[32:32 + N * rs].view(N, rs)
+    Bp[:, :r] = _rand(N, r, seed=3, scale=0.1)
+    bt_flat = torch.full((N * rs + 16,), 3.0, dtype=BF, device="cuda")
+    table = torch.tensor([[32, 8, N, rs]], dtype=torch.int64, device="cuda")
+    ops.lora_transpose_b(flat, bt_flat, table)
+    Bt = bt_flat[8:8 + N * rs].view(rs, N)
+    assert torch.equal(Bt, Bp.t())
+    U = torch.empty(M, rs, dtype=BF, device="cuda")
+    dx = torch.empty(M, K, dtype=BF, device="cuda")
+    ops.gemm(dx, M, K, [(ops.kmajor(dy), ops.mnmajor(w), N)],
+             side=(ops.Mat(Bt, r, N, N), ops.Mat(A, r, K, K, mn=True), r, 2.0, U), pair_mode=pair, static_b=True)
+    Uref = (2.0 * (dy.float() @ Bp[:, :r].float())).to(BF)
+    _close(U[:, :r], Uref, what="U out (K-major B copy)")
+    _close(dx, dy.float() @ w.float() + Uref.float() @ A.float(), what="fused side dgrad (K-major B copy)")
