@@ -53,6 +53,10 @@ struct Gemm2Args {
     // bf16 row-major output through TMA: each epilogue warp stages [32 rows x 32 columns] boxes (64B swizzle) and one
     // lane issues cp.async.bulk.tensor stores (mapD); needs 16-byte aligned rows of D (and R); M / N edges are clipped
     int tma_store;
+    // stream-K: when a problem has fewer 256 x BN tiles than CTA pairs but a long K, the (tile, k-block) space is cut
+    // into 74 equal contiguous ranges; every range's partial tile is added to D with a TMA reduce-add (D pre-set by the
+    // host to the residual or zero; bias rides with the range that holds k-block 0).  Needs tma_store.
+    int streamk;
     float alpha, side_alpha;
     long long d_sm, r_sm, t_ld, bias_sb;
     void* D;
@@ -61,6 +65,35 @@ struct Gemm2Args {
     __nv_bfloat16* T_out;
     long long* dbg;           // developer probe: per-CTA globaltimer stamps [cta][16] (nullptr in production)
     CUtensorMap mapA, mapB, mapS, mapB2, mapA2, mapD;
+};
+
+// The (tile, k-block range) work items of one CTA pair; producer, MMA and epilogue warps walk the same sequence.
+struct WorkIter2 {
+    int streamk, kblocks, total_tiles, npairs, tile;
+    long long u, u_end;
+    __device__ __forceinline__ WorkIter2(int streamk_, int kblocks_, int total_tiles_, int npairs_, int pair)
+        : streamk(streamk_), kblocks(kblocks_), total_tiles(total_tiles_), npairs(npairs_), tile(pair) {
+        const long long U = static_cast<long long>(total_tiles_) * kblocks_;
+        u = U * pair / npairs_;
+        u_end = U * (pair + 1) / npairs_;
+    }
+    __device__ __forceinline__ bool next(int& t, int& kb0, int& kb1) {
+        if (!streamk) {
+            if (tile >= total_tiles) return false;
+            t = tile;
+            kb0 = 0;
+            kb1 = kblocks;
+            tile += npairs;
+            return true;
+        }
+        if (u >= u_end) return false;
+        t = static_cast<int>(u / kblocks);
+        kb0 = static_cast<int>(u - static_cast<long long>(t) * kblocks);
+        const long long len = min(static_cast<long long>(kblocks - kb0), u_end - u);
+        kb1 = kb0 + static_cast<int>(len);
+        u += len;
+        return true;
+    }
 };
 
 struct Epi2 {
@@ -155,13 +188,13 @@ __device__ __forceinline__ void epi2_chunk(const Epi2& e, const uint32_t (&raw)[
 // accumulators with 16-byte loads, packs to bf16, writes its 64-byte row into the 64B-swizzled staging box (conflict
 // free) and lane 0 issues the bulk tensor store.  ~90 instructions per chunk and no st.global at all.
 __device__ __forceinline__ void epi2_chunk_tma(const Epi2& e, const CUtensorMap* mapD, const uint32_t (&raw)[32], uint8_t* box,
-                                               int lane, int m_warp, int n_chunk) {
+                                               int lane, int m_warp, int n_chunk, bool reduce, bool with_bias) {
     const int m = m_warp + lane;
     float v[32];
     const float alpha = e.alpha;
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * alpha;
-    if (e.bias != nullptr) {
+    if (e.bias != nullptr && with_bias) {
         const int mb = e.bias_rows ? min(m, e.M - 1) / e.bias_rows : 0;
         const uint4* bp = reinterpret_cast<const uint4*>(e.bias + mb * e.bias_sb + n_chunk);
 #pragma unroll
@@ -208,7 +241,8 @@ __device__ __forceinline__ void epi2_chunk_tma(const Epi2& e, const CUtensorMap*
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-        tma_store_4d(mapD, box, n_chunk, m_warp, 0, 0);
+        if (reduce) tma_reduce_add_4d(mapD, box, n_chunk, m_warp, 0, 0);
+        else tma_store_4d(mapD, box, n_chunk, m_warp, 0, 0);
         bulk_commit();
     }
     __syncwarp();
@@ -217,10 +251,10 @@ __device__ __forceinline__ void epi2_chunk_tma(const Epi2& e, const CUtensorMap*
 // Ragged chunk (fewer than 32 valid columns at the N edge) when the TMA-store path owns the staging memory: plain
 // thread <-> row scalar stores.  Rare (none of the step's shapes has a ragged edge), so simplicity wins.
 __device__ __forceinline__ void epi2_chunk_direct(const Epi2& e, const uint32_t (&raw)[32], int lane, int m_warp, int n_chunk,
-                                                  int ncols) {
+                                                  int ncols, bool with_bias) {
     const int m = m_warp + lane;
     if (m >= e.M) return;
-    const __nv_bfloat16* bp = e.bias ? e.bias + (e.bias_rows ? (m / e.bias_rows) * e.bias_sb : 0) : nullptr;
+    const __nv_bfloat16* bp = (e.bias && with_bias) ? e.bias + (e.bias_rows ? (m / e.bias_rows) * e.bias_sb : 0) : nullptr;
     __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(e.D) + static_cast<long long>(m) * e.d_sm;
     const __nv_bfloat16* rp = e.R ? e.R + static_cast<long long>(m) * e.r_sm : nullptr;
 #pragma unroll
@@ -254,7 +288,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     const int num_stages = g.num_stages, stage_bytes = g.stage_bytes, acc_stages = g.acc_stages;
     const int side = g.side, side_off = g.side_off, r16 = g.side_r16;
     const int b_mn = g.b_mn, side_mn = g.side_mn, b2_mn = g.b2_mn;
-    const int conv = g.conv, nseg = g.nseg, kblocks2 = g.kblocks2;
+    const int conv = g.conv, nseg = g.nseg, kblocks2 = g.kblocks2, streamk = g.streamk;
     const int npairs = static_cast<int>(gridDim.x >> 1), pair = static_cast<int>(blockIdx.x >> 1);
     long long* const dbg = g.dbg;
     if (threadIdx.x == 0) dbg_stamp(dbg, 0);
@@ -341,7 +375,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             };
             // ---- weight prefetch: the first ring-full of B tiles does not depend on the previous kernel ----
             int npre = 0;
-            if (g.b_static) {
+            if (g.b_static && !streamk) {
                 const int n_blk0 = pair % tiles_n;
                 const int nh00 = n_blk0 * BN + static_cast<int>(rank) * bn_half;
                 npre = kblocks < num_stages ? kblocks : num_stages;
@@ -352,12 +386,15 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             }
             pdl_wait();
             dbg_stamp(dbg, 1);
-            for (int tile = pair; tile < total_tiles; tile += npairs) {
+            WorkIter2 wit(streamk, kblocks, total_tiles, npairs, pair);
+            int tile, kb0, kb1;
+            bool first_item = true;
+            while (wit.next(tile, kb0, kb1)) {
                 const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
                 const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
                 const int nh0 = n_blk * BN + static_cast<int>(rank) * bn_half;
-                int kb_first = 0;
-                if (tile == pair && npre > 0) {
+                int kb_first = kb0;
+                if (first_item && npre > 0) {
                     for (int st = 0; st < npre; ++st) issue_a(st, st, m0);
                     kb_first = npre;
                     stage = (npre == num_stages) ? 0 : npre;
@@ -370,7 +407,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     int tap0 = kb_first / conv_cblocks;
                     int cb = kb_first - tap0 * conv_cblocks, kh = tap0 / 3;
                     int kw = tap0 - kh * 3, bk_tap = tap0 * conv_tap_k, bn_tap = tap0 * conv_tap_n;
-                    for (int kb = kb_first; kb < kblocks; ++kb) {
+                    for (int kb = kb_first; kb < kb1; ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
                         uint8_t* sa = smem + stage * stage_bytes;
@@ -390,7 +427,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     }
                 } else {
                     int k = kb_first * kBK;
-                    for (int kb = kb_first; kb < kblocks; ++kb, k += kBK) {
+                    for (int kb = kb_first; kb < kb1; ++kb, k += kBK) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         if (rank == 0) mbar_expect_tx(&full_bar[stage], tx);
                         uint8_t* sa = smem + stage * stage_bytes;
@@ -409,7 +446,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                         advance_stage(stage, phase, num_stages);
                     }
                 }
-                if (nseg == 2) {
+                if (nseg == 2 && kb1 == kblocks) {
                     // second K segment (conv-LoRA side products): plain K-major A2, B2 K- or MN-major
                     int k = 0;
                     for (int kb = 0; kb < kblocks2; ++kb, k += kBK) {
@@ -427,7 +464,8 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                         advance_stage(stage, phase, num_stages);
                     }
                 }
-                if (tile == pair) dbg_stamp(dbg, 2);          // every load of the first tile issued
+                if (first_item) dbg_stamp(dbg, 2);           // every load of the first work item issued
+                first_item = false;
                 if (side) {
                     // one more ring slot per tile: this CTA's half of the B2 tile for the final rank-r MMA
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -460,17 +498,20 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             const uint64_t b2_hi = umma_desc(0, b2_mn ? 8192u : 16u, 1024);
             const uint64_t b_step = b_mn ? 128u : 2u, s_step = side_mn ? 128u : 2u, b2_step = b2_mn ? 128u : 2u;
             const int ktail = g.ktail16, ktail2 = g.ktail16_2;
-            for (int tile = pair; tile < total_tiles; tile += npairs) {
+            WorkIter2 wit(streamk, kblocks, total_tiles, npairs, pair);
+            int tile, kb0, kb1;
+            bool first_item = true;
+            while (wit.next(tile, kb0, kb1)) {
                 mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * 256);
                 const uint32_t tmem_s = tmem_base + static_cast<uint32_t>(acc_stages == 1 ? 256 : acc * 256 + kSideCol);
                 uint32_t accum = 0;
-                for (int kb = 0; kb < kblocks; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (leader) {
-                        if (dbg != nullptr && tile == pair && (kb == 0 || kb == kblocks - 1)) dbg_stamp(dbg, kb == 0 ? 3 : 4);
+                        if (dbg != nullptr && first_item && (kb == kb0 || kb == kb1 - 1)) dbg_stamp(dbg, kb == kb0 ? 3 : 4);
                         const uint32_t sa = smem_base + static_cast<uint32_t>(stage * stage_bytes);
                         const uint64_t ad = a_hi | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
                         const uint64_t bd = b_hi | static_cast<uint64_t>(((sa + k2ABytes) & 0x3FFFF) >> 4);
@@ -490,7 +531,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     accum = 1;
                     advance_stage(stage, phase, num_stages);
                 }
-                if (nseg == 2) {
+                if (nseg == 2 && kb1 == kblocks) {
                     for (int kb = 0; kb < kblocks2; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
@@ -515,7 +556,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     mbar_wait_cluster(t_ready_bar, t_phase);              // T staged in smem by both CTAs
                     t_phase ^= 1;
                     tc_fence_after();
-                    if (leader && tile == pair) dbg_stamp(dbg, 9);
+                    if (leader && first_item) dbg_stamp(dbg, 9);
                     if (leader) {
                         const uint32_t sb2 = smem_base + static_cast<uint32_t>(stage * stage_bytes) + k2ABytes;
                         const uint64_t td = a_hi | static_cast<uint64_t>(((smem_base + k2TOff) & 0x3FFFF) >> 4);
@@ -528,6 +569,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                 }
                 if (leader) umma2_commit_mc(&tmem_full_bar[acc]);         // accumulator complete -> both epilogues
                 __syncwarp();
+                first_item = false;
                 if (++acc == acc_stages) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -566,7 +608,11 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
         const long long t_ld = g.t_ld;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = pair; tile < total_tiles; tile += npairs) {
+        WorkIter2 wit(streamk, kblocks, total_tiles, npairs, pair);
+        int tile, kb0, kb1;
+        bool first_item = true;
+        while (wit.next(tile, kb0, kb1)) {
+            const bool with_bias = !streamk || kb0 == 0;      // stream-K: the bias rides with the range holding k-block 0
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             const int m_warp = m_blk * 256 + static_cast<int>(rank) * 128 + lane_base;
             const int n0 = n_blk * BN;
@@ -575,7 +621,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                 // ---- T-phase: this CTA's 128 rows of Tacc -> alpha, bf16 -> swizzled smem A operand (+ T_out) ----
                 mbar_wait(&side_full_bar[acc], acc_phase);
                 tc_fence_after();
-                if (warp == 2 && lane == 0 && tile == pair) dbg_stamp(dbg, 8);
+                if (warp == 2 && lane == 0 && first_item) dbg_stamp(dbg, 8);
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
                               static_cast<uint32_t>(acc_stages == 1 ? 256 : acc * 256 + kSideCol), raw);
@@ -619,7 +665,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            if (warp == 2 && lane == 0 && tile == pair) dbg_stamp(dbg, 5);
+            if (warp == 2 && lane == 0 && first_item) dbg_stamp(dbg, 5);
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 uint32_t raw[32];
                 tmem_ld32(taddr + c0, raw);
@@ -631,10 +677,12 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                         // double-buffered staging box: the store issued two chunks ago must have read its smem
                         if (lane == 0) bulk_wait_read<1>();
                         __syncwarp();
-                        epi2_chunk_tma(e, &g.mapD, raw, tma_box + (tma_buf & 1) * 2048, lane, m_warp, n0 + c0);
+                        epi2_chunk_tma(e, &g.mapD, raw, tma_box + (tma_buf & 1) * 2048, lane, m_warp, n0 + c0, streamk != 0,
+                                       with_bias);
                         ++tma_buf;
                     } else {
-                        epi2_chunk_direct(e, raw, lane, m_warp, n0 + c0, min(32, BN - c0));
+                        // (the host only selects stream-K for problems without a ragged N edge)
+                        epi2_chunk_direct(e, raw, lane, m_warp, n0 + c0, min(32, BN - c0), with_bias);
                     }
                 } else {
                     epi2_chunk<kEpi>(e, raw, stage_buf, lane, m_warp, n0 + c0, min(32, BN - c0));
@@ -642,7 +690,8 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (warp == 2 && lane == 0 && tile == pair) dbg_stamp(dbg, 6);
+            if (warp == 2 && lane == 0 && first_item) dbg_stamp(dbg, 6);
+            first_item = false;
             if (lane == 0) mbar_arrive_cluster_nofence(tmem_empty_leader + static_cast<uint32_t>(acc) * 8u);
             if (++acc == acc_stages) {
                 acc = 0;

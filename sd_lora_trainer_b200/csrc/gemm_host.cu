@@ -302,8 +302,24 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
         if (int rc = encode_map_ex(&g.mapD, d->D, 2, dD, sD, boxD, 64)) return rc;
         g.tma_store = 1;
     }
-    const int pairs = g.total_tiles < kNumSMs / 2 ? g.total_tiles : kNumSMs / 2;
+    int pairs = g.total_tiles < kNumSMs / 2 ? g.total_tiles : kNumSMs / 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // stream-K: few tiles, long K (FF down-projection and its input gradient, the deep convs): cut the (tile, k-block)
+    // space into 74 equal ranges so every SM works; partial tiles are added to D by TMA reduce-add, so D is pre-set
+    // here to the residual (or zero) and the kernel sees no residual.
+    static const int streamk_env = getenv("B200_STREAMK") ? atoi(getenv("B200_STREAMK")) : 1;
+    if (streamk_env && g.tma_store && !d->side && g.kblocks >= 32 && g.total_tiles * 4 <= (kNumSMs / 2) * 3 &&
+        d->N % 32 == 0 && static_cast<long long>(g.total_tiles) * g.kblocks >= kNumSMs / 2) {
+        const size_t row_bytes = static_cast<size_t>(d->N) * 2;
+        cudaError_t e = cudaSuccess;
+        if (d->R == nullptr) e = cudaMemset2DAsync(d->D, static_cast<size_t>(d->d_sm) * 2, 0, row_bytes, d->M, st);
+        else if (d->R != d->D) e = cudaMemcpy2DAsync(d->D, static_cast<size_t>(d->d_sm) * 2, d->R, static_cast<size_t>(d->r_sm) * 2,
+                                                     row_bytes, d->M, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return set_error(3, "gemm2: stream-K output initialisation: %s", cudaGetErrorString(e));
+        g.streamk = 1;
+        g.R = nullptr;
+        pairs = kNumSMs / 2;
+    }
     cudaError_t le;
     if (d->d_fp32) le = launch_pdl_cluster(gemm2_kernel<1>, dim3(2 * pairs), dim3(k2Threads), k2SmemBytes, st, 2u, g);
     else le = launch_pdl_cluster(gemm2_kernel<0>, dim3(2 * pairs), dim3(k2Threads), k2SmemBytes, st, 2u, g);

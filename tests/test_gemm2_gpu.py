@@ -223,3 +223,45 @@ def test_fused_side_dgrad_with_kmajor_b_copy(M, N, K, r, pair):
     Uref = (2.0 * (dy.float() @ Bp[:, :r].float())).to(BF)
     _close(U[:, :r], Uref, what="U out (K-major B copy)")
     _close(dx, dy.float() @ w.float() + Uref.float() @ A.float(), what="fused side dgrad (K-major B copy)")
+
+
+@pytest.mark.parametrize("M,N,K,mn,res,bias", [(2048, 1280, 10240, True, False, False), (2048, 1280, 5120, False, True, True),
+                                               (2048, 1280, 5120, False, "inplace", False), (1024, 512, 4096, False, False, True),
+                                               (8192, 640, 5120, True, True, False), (512, 256, 2048, False, True, True)])
+def test_pair_stream_k(M, N, K, mn, res, bias):
+    """Few tiles + long K -> stream-K ranges with TMA reduce-add partial tiles (D pre-set to residual / zero)."""
+    from sd_lora_trainer_b200 import ops
+    a = _rand(M, K, scale=0.5)
+    w = _rand(K, N, seed=1, scale=0.05) if mn else _rand(N, K, seed=1, scale=0.05)
+    bvec = _rand(N, seed=2) if bias else None
+    ref = a.float() @ (w.float() if mn else w.float().T)
+    if bias:
+        ref = ref + bvec.float()
+    out = torch.full((M, N), 5.0, dtype=BF, device="cuda")
+    R = None
+    if res == "inplace":
+        out = _rand(M, N, seed=3)
+        R = out
+        ref = ref + out.float()
+    elif res:
+        R = _rand(M, N, seed=3)
+        ref = ref + R.float()
+    ops.gemm(out, M, N, [(ops.kmajor(a), ops.mnmajor(w) if mn else ops.kmajor(w), K)], bias=bvec, residual=R, pair_mode=1)
+    torch.cuda.synchronize()
+    _close(out, ref, what=f"stream-K {M}x{N}x{K}")
+
+
+def test_pair_stream_k_conv():
+    import torch.nn.functional as F
+    from sd_lora_trainer_b200 import ops
+    N, H, W, C, Cout = 2, 32, 32, 1280, 1280
+    x = _rand(N * H * W, C, scale=0.5)
+    w = _rand(Cout, C, 3, 3, seed=1, scale=0.02)
+    bias, res = _rand(Cout, seed=2), _rand(N * H * W, Cout, seed=3)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()
+    out = torch.empty(N * H * W, Cout, dtype=BF, device="cuda")
+    ops.gemm(out, N * H * W, Cout, [(ops.Conv3x3(x, N, H, W, C, b_tap_k=C), ops.kmajor(wk), 9 * C)], bias=bias, residual=res,
+             pair_mode=1)
+    xn = x.float().view(N, H, W, C).permute(0, 3, 1, 2)
+    ref = F.conv2d(xn, w.float(), bias.float(), padding=1).permute(0, 2, 3, 1).reshape(N * H * W, Cout) + res.float()
+    _close(out, ref, what="stream-K conv")
