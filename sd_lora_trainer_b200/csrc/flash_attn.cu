@@ -54,7 +54,8 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
         attr = true;
     }
     const long long nq_elems = static_cast<long long>(B) * L * ld;
-    cudaMemsetAsync(dq_acc_ws, 0, sizeof(float) * nq_elems, st);
+    const bool dq_direct = Lk <= 128;          // one key block: dQ is written once, as bf16, by the kernel itself
+    if (!dq_direct) cudaMemsetAsync(dq_acc_ws, 0, sizeof(float) * nq_elems, st);
     launch_pdl(flash_delta_kernel, dim3(grid_for(static_cast<long long>(B) * L * H, 256)), dim3(256), 0, st, 
         static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta_ws, B, L, H, ld);
     B200_CHECK_LAUNCH("flash_delta");
@@ -73,6 +74,8 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     g.LSE = lse;
     g.Delta = delta_ws;
     g.dQacc = dq_acc_ws;
+    g.dQ = static_cast<__nv_bfloat16*>(dq);
+    g.dq_direct = dq_direct ? 1 : 0;
     g.dK = static_cast<__nv_bfloat16*>(dk);
     g.dV = static_cast<__nv_bfloat16*>(dv);
     g.L = L;
@@ -83,7 +86,9 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     dim3 grid((Lk + 127) / 128, H, B);
     launch_pdl(flash_bwd_kernel, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     B200_CHECK_LAUNCH("flash_bwd");
-    launch_pdl(f32_to_bf16_kernel, dim3(grid_for(nq_elems / 4, 256)), dim3(256), 0, st, dq_acc_ws, static_cast<__nv_bfloat16*>(dq), nq_elems / 4);
-    B200_CHECK_LAUNCH("flash_dq_convert");
+    if (!dq_direct) {
+        launch_pdl(f32_to_bf16_kernel, dim3(grid_for(nq_elems / 4, 256)), dim3(256), 0, st, dq_acc_ws, static_cast<__nv_bfloat16*>(dq), nq_elems / 4);
+        B200_CHECK_LAUNCH("flash_dq_convert");
+    }
     return 0;
 }

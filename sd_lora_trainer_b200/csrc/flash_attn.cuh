@@ -337,6 +337,9 @@ struct FlashBwdArgs {
     const float* LSE;                          // [B, H, L]
     const float* Delta;                        // [B, H, L] = rowsum(dO * O)
     float* dQacc;                              // fp32 [B*L, ld] accumulated over key blocks (zeroed by the caller)
+    __nv_bfloat16* dQ;                         // Lk <= 128 (one key block, e.g. every cross-attention layer): dQ has a
+                                               // single contribution and is written here directly as bf16
+    int dq_direct;
     __nv_bfloat16* dK;                         // [B*Lk, ld]
     __nv_bfloat16* dV;
     int L, Lk, H;
@@ -535,6 +538,32 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             for (int i = 0; i < nq; ++i) {
                 mbar_wait(dq_full, i & 1);
                 tc_fence_after();
+                if (g.dq_direct) {
+                    // single key block: no accumulation over blocks -> straight to bf16, thread <-> query row
+                    const int q = i * 128 + row;
+                    __nv_bfloat16* dst = g.dQ + (static_cast<long long>(b) * g.L + q) * g.ld + h * 64;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_dQ + lane_off + c * 32, r);
+                        tmem_ld_wait();
+                        if (q < g.L) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                uint4 w;
+                                w.x = pack_bf16(__uint_as_float(r[8 * e + 0]), __uint_as_float(r[8 * e + 1]));
+                                w.y = pack_bf16(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]));
+                                w.z = pack_bf16(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]));
+                                w.w = pack_bf16(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]));
+                                *reinterpret_cast<uint4*>(dst + c * 32 + e * 8) = w;
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dq_free);
+                    continue;
+                }
                 if (i > 0) {
                     if (issuer) bulk_wait_read<0>();            // the previous block's reductions have read the staging tile
                     __syncwarp();
