@@ -151,16 +151,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         tmem_alloc(tmem_base_ptr, 512);
         tmem_relinquish();
     }
-    if (warp >= 2) {
-        // Warm the constant cache with the whole parameter block (one word per 64-byte line) while the previous grid
-        // drains: the role loops below read ~18 different lines of it, and their first-touch misses used to sit
-        // between "barriers ready" and the first TMA issue (1.5 us in profiles/r01a_gemm_stamps.txt).
-        const uint32_t* gp = reinterpret_cast<const uint32_t*>(&g);
-        const int line = static_cast<int>(threadIdx.x) - 64;
-        uint32_t touch = 0;
-        if (line * 16 < static_cast<int>(sizeof(GemmArgs) / 4)) touch = gp[line * 16];
-        asm volatile("" ::"r"(touch));
-    }
     pdl_launch();
     tc_fence_before();
     __syncthreads();
