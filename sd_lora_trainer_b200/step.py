@@ -237,8 +237,8 @@ class TrainerB200:
                              lr2=ti_lr or 0.0, wd2=self.cfg.ti_weight_decay, step=self.opt_step + 1, grad_scale=1.0)
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
 
-    def _optimizer_body(self):
-        if self.pg is not None and self.world > 1:
+    def _optimizer_body(self, collective: bool = True):
+        if collective and self.pg is not None and self.world > 1:
             torch.distributed.all_reduce(self.store.grads, group=self.pg)     # the step's only collective
         ops.adamw_dev(self.store.params, self.store.grads, self.store.m, self.store.v, self.store.n_lora,
                       self._hyper_dev, zero_grad=True)
@@ -310,7 +310,7 @@ class TrainerB200:
         try:
             self._body(st, True)
             self._set_hyper()
-            self._optimizer_body()
+            self._optimizer_body(collective=False)      # rank-local pass (bench.py runs it on rank 0 only)
             torch.cuda.synchronize()
             recs = ops.GEMM_PROFILE
         finally:
