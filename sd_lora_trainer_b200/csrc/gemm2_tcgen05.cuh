@@ -666,13 +666,12 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (warp == 2 && lane == 0 && first_item) dbg_stamp(dbg, 5);
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
-                uint32_t raw[32];
-                tmem_ld32(taddr + c0, raw);
-                tmem_ld_wait();
-                if (n0 + c0 >= e.N) continue;          // warp-uniform
+            // chunks half, half+2, ... of 32 columns; the tcgen05.ld of the next chunk is in flight while this one is
+            // converted / staged / stored (two register buffers)
+            auto drain = [&](const uint32_t (&raw)[32], int c0) {
+                if (n0 + c0 >= e.N) return;            // warp-uniform
                 if (kEpi == 0 && tma_store) {
-                    if (m_warp >= e.M) continue;       // rows past the M edge (warp-uniform)
+                    if (m_warp >= e.M) return;         // rows past the M edge (warp-uniform)
                     if (n0 + c0 + 32 <= e.N) {
                         // double-buffered staging box: the store issued two chunks ago must have read its smem
                         if (lane == 0) bulk_wait_read<1>();
@@ -686,6 +685,22 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     }
                 } else {
                     epi2_chunk<kEpi>(e, raw, stage_buf, lane, m_warp, n0 + c0, min(32, BN - c0));
+                }
+            };
+            {
+                uint32_t ra[32], rb[32];
+                int c0 = half * 32;
+                if (c0 < BN) tmem_ld32(taddr + c0, ra);
+                for (; c0 < BN; c0 += 128) {
+                    tmem_ld_wait();
+                    const int c1 = c0 + 64;
+                    if (c1 < BN) tmem_ld32(taddr + c1, rb);
+                    drain(ra, c0);
+                    if (c1 < BN) {
+                        tmem_ld_wait();
+                        if (c1 + 64 < BN) tmem_ld32(taddr + c1 + 64, ra);
+                        drain(rb, c1);
+                    }
                 }
             }
             tc_fence_before();

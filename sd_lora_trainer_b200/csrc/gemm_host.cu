@@ -157,9 +157,11 @@ static double pair_cost(const b200_gemm_t* d, int bn, bool side) {
     const double t_mma = kblocks * 2.0 * bn / 1.8e9;                                    // 4 MMAs of bn/2 clocks per block
     const double t_l2 = kblocks * (32768.0 + 128.0 * bn) * active / 11.0e12;            // L2 -> SM fabric shared by the pairs
     const double t_tile = t_mma > t_l2 ? t_mma : t_l2;
-    const double t_epi = (bn / 64.0) * 0.55e-6 + 0.4e-6;
+    // drain of the queued MMAs + epilogue of the last tile: measured 2.1 us at bn = 160, 3.4 us at bn = 256
+    // (profiles/r01f_gemm2_timeline.txt); a single accumulator stage (side path, bn > 192) serialises it on every wave
+    const double t_epi = bn * 0.0135e-6;
     const bool single_acc = side && bn > kSideMaxBN;
-    return waves * t_tile + (single_acc ? waves : 1) * t_epi + 2.0e-6;
+    return waves * t_tile + (single_acc ? waves : 1) * t_epi + (single_acc ? 0.5e-6 : 0.0) + 2.0e-6;
 }
 
 static int pick_pair_bn(const b200_gemm_t* d, double* cost_out) {
