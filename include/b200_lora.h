@@ -180,6 +180,11 @@ int b200_timestep_embedding(const float* t, void* out, int32_t n, int32_t dim, v
 /* ---------------------------------------------------------------------------------------------------------
  * Step prologue / loss / optimizer (main.py:311-326, trainer/loss.py:127-170, trainer/optimizer.py:265-275).
  * --------------------------------------------------------------------------------------------------------- */
+/* PreprocessedDataset.__getitem__ (trainer/dataset.py:181-193): latent_dist.sample() * vae.config.scaling_factor on the
+   cached DiagonalGaussianDistribution parameters, fp32; eps is the injected N(0,1) draw.
+   out = (mean + exp(0.5 * clamp(logvar, -30, 20)) * eps) * scaling_factor */
+int b200_latent_sample(const float* mean, const float* logvar, const float* eps, float scaling_factor, float* out, int64_t n,
+                       void* stream);
 /* noise(bf16, in/out) += offset_scale * offset[b, c] ; noisy = sqrt(acp[t]) * bf16(latent) + sqrt(1 - acp[t]) * noise
    with acp rounded to bf16 before the sqrt, as DDPMScheduler.add_noise does.  latent fp32 NCHW, outputs NCHW bf16
    plus an NHWC(8-channel padded) copy of `noisy` for the conv_in TMA path. */

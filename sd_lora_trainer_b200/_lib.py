@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200_bicubic_fwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
     "b200_bicubic_bwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
     "b200_timestep_embedding": [c_void_p, c_void_p, c_int32, c_int32, c_void_p],
+    "b200_latent_sample": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p],
     "b200_noise_prologue": [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                             c_int32, c_int32, c_void_p],
     "b200_snr_weights": [c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p],

@@ -34,6 +34,20 @@ __global__ void noise_prologue_kernel(const float* __restrict__ latent, bf16* __
     }
 }
 
+// trainer/dataset.py:181-193 -> [3P] DiagonalGaussianDistribution.sample() * scaling_factor, fp32 (main.py:186 keeps the
+// VAE in fp32):  x0 = (mean + exp(0.5 * clamp(logvar, -30, 20)) * eps) * scaling_factor, the Gaussian draw eps injected.
+__global__ void latent_sample_kernel(const float* __restrict__ mean, const float* __restrict__ logvar,
+                                     const float* __restrict__ eps, float scaling_factor, float* __restrict__ out, long long n) {
+    pdl_launch();
+    pdl_wait();
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float lv = fminf(fmaxf(logvar[i], -30.f), 20.f);
+        const float std = expf(0.5f * lv);
+        out[i] = (mean[i] + std * eps[i]) * scaling_factor;
+    }
+}
+
 // trainer/loss.py:83-106,145-161: w_b = (min(snr_b, gamma) / snr_b) / mean_b(...)   (epsilon prediction)
 __global__ void snr_weights_kernel(const float* __restrict__ acp, const long long* __restrict__ timesteps,
                                    float snr_gamma, float* __restrict__ weights, int B) {
@@ -173,6 +187,15 @@ extern "C" int b200_noise_prologue(const float* latent, void* noise, const float
         reinterpret_cast<const long long*>(timesteps), static_cast<bf16*>(noisy_nchw), static_cast<bf16*>(noisy_nhwc8), B,
         C, HW);
     B200_CHECK_LAUNCH("noise_prologue");
+    return 0;
+}
+
+extern "C" int b200_latent_sample(const float* mean, const float* logvar, const float* eps, float scaling_factor, float* out,
+                                  int64_t n, void* stream) {
+    B200_CHECK_ARG(n >= 1 && mean && logvar && eps && out, "latent_sample: bad arguments");
+    launch_pdl(latent_sample_kernel, dim3(grid_for(n, 256)), dim3(256), 0, ST, mean, logvar, eps, scaling_factor, out,
+               static_cast<long long>(n));
+    B200_CHECK_LAUNCH("latent_sample");
     return 0;
 }
 

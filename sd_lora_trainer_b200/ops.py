@@ -353,6 +353,17 @@ def timestep_embedding(t: torch.Tensor, dim: int):
 
 
 # ---- prologue / loss / optimizer -------------------------------------------------------------------
+def latent_sample(mean: torch.Tensor, logvar: torch.Tensor, eps: torch.Tensor, scaling_factor: float):
+    """latent_dist.sample() * scaling_factor (trainer/dataset.py:186) with the Gaussian draw injected; fp32."""
+    _chk_dev(mean, logvar, eps)
+    assert mean.dtype == logvar.dtype == eps.dtype == torch.float32 and mean.shape == logvar.shape == eps.shape
+    mean, logvar, eps = mean.contiguous(), logvar.contiguous(), eps.contiguous()
+    out = torch.empty_like(mean)
+    check(_lib.load().b200_latent_sample(mean.data_ptr(), logvar.data_ptr(), eps.data_ptr(), scaling_factor, out.data_ptr(),
+                                         mean.numel(), _stream()), "latent_sample")
+    return out
+
+
 def noise_prologue(latent: torch.Tensor, noise: torch.Tensor, offset: Optional[torch.Tensor], offset_scale: float,
                    alphas_cumprod: torch.Tensor, timesteps: torch.Tensor):
     """In-place on `noise`; returns (noisy NCHW bf16, noisy NHWC padded to 8 channels)."""

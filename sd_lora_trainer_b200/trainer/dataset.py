@@ -1,0 +1,38 @@
+"""Mirror of the per-step part of the reference's trainer/dataset.py: ``__getitem__`` draws the
+training latent from the cached VAE posterior and scales it (dataset.py:181-193).  The one-time VAE encode that fills the
+cache (dataset.py:141-179) is outside the step; this class takes its result - the posterior
+``parameters`` tensor diffusers' ``DiagonalGaussianDistribution`` wraps ([1, 8, h, w]: mean | logvar) - as given."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import ops
+
+
+class CachedLatentDataset:
+    """``PreprocessedDataset`` with ``do_cache=True`` after its constructor ran: captions, posterior parameters, masks."""
+
+    def __init__(self, captions: Sequence[str], posterior_parameters: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
+                 vae_scaling_factor: float):
+        assert len(captions) == len(posterior_parameters) == len(masks)
+        self.captions = list(captions)
+        self.params = [p.to(torch.float32) for p in posterior_parameters]
+        self.masks = list(masks)
+        self.vae_scaling_factor = float(vae_scaling_factor)
+
+    def __len__(self) -> int:
+        return len(self.captions)
+
+    def sample(self, idx: int, eps: Optional[torch.Tensor] = None, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """``self.vae_latents[idx].sample() * self.vae_scaling_factor`` (dataset.py:186); ``eps`` injects the draw."""
+        p = self.params[idx]
+        mean, logvar = torch.chunk(p, 2, dim=1)
+        if eps is None:
+            eps = torch.randn(mean.shape, generator=generator, device=mean.device, dtype=torch.float32)
+        return ops.latent_sample(mean.contiguous(), logvar.contiguous(), eps.to(mean.device, torch.float32),
+                                 self.vae_scaling_factor)
+
+    def __getitem__(self, idx: int) -> Tuple[str, torch.Tensor, torch.Tensor]:
+        return self.captions[idx], self.sample(idx).squeeze().detach(), self.masks[idx].detach()

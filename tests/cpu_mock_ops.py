@@ -268,6 +268,10 @@ def timestep_embedding(t, dim):
     return _bf(torch.cat([torch.cos(e), torch.sin(e)], -1))
 
 
+def latent_sample(mean, logvar, eps, scaling_factor):
+    return (mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * eps) * scaling_factor
+
+
 def noise_prologue(latent, noise, offset, offset_scale, acp, timesteps):
     B, Cc, H, W = latent.shape
     if offset is not None:
