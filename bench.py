@@ -218,8 +218,14 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(result), flush=True)
     if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        # Measured on 2 x B200 (gpurun_out of round 1): every rank finished its work and rank 0 printed its line, but the
+        # closing barrier + destroy_process_group() never returned - the step's CUDA graphs hold the NCCL kernels they
+        # captured, and tearing the communicator down under them blocks.  Nothing is left to communicate, so: flush
+        # and leave without running the NCCL / graph destructors.  (The rank-0-only passes above issue no collective.)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def cpu_baseline(args, steps: int, warmup: int):

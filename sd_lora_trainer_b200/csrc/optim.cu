@@ -44,7 +44,8 @@ __global__ void latent_sample_kernel(const float* __restrict__ mean, const float
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const float lv = fminf(fmaxf(logvar[i], -30.f), 20.f);
         const float std = expf(0.5f * lv);
-        out[i] = (mean[i] + std * eps[i]) * scaling_factor;
+        // one rounding per op, like the three ATen kernels behind mean + std * randn (no FMA contraction)
+        out[i] = __fmul_rn(__fadd_rn(mean[i], __fmul_rn(std, eps[i])), scaling_factor);
     }
 }
 
