@@ -222,6 +222,17 @@ def run_ours(args):
         # closing barrier + destroy_process_group() never returned - the step's CUDA graphs hold the NCCL kernels they
         # captured, and tearing the communicator down under them blocks.  Nothing is left to communicate, so: flush
         # and leave without running the NCCL / graph destructors.  (The rank-0-only passes above issue no collective.)
+        # Non-zero ranks stay alive until rank 0 has printed (its peers' communicators must not vanish while it still
+        # runs GPU work); the hand-shake goes through the rendezvous store, not through NCCL.
+        try:
+            import datetime
+            store = torch.distributed.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("b200_bench_done", "1")
+            else:
+                store.wait(["b200_bench_done"], datetime.timedelta(seconds=900))
+        except Exception:                                    # best effort: never turn a finished run into a failure
+            pass
         sys.stdout.flush()
         sys.stderr.flush()
         torch.cuda.synchronize()
