@@ -12,6 +12,7 @@ losses -> UNet bwd (dA/dB only) -> CLIP bwd to the TI rows -> [all-reduce] -> fu
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -98,6 +99,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # a rank that dies leaves its peers spinning in NCCL: bound the whole run (stacks go to stderr, exit code 1)
+    faulthandler.dump_traceback_later(args.watchdog, exit=True)
+    # stdout carries the ONE JSON line and nothing else: NCCL's version / debug chatter goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     pg = None
@@ -217,6 +222,7 @@ def run_ours(args):
         result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
     if rank == 0:
         print(json.dumps(result), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         # Measured on 2 x B200 (gpurun_out of round 1): every rank finished its work and rank 0 printed its line, but the
         # closing barrier + destroy_process_group() never returned - the step's CUDA graphs hold the NCCL kernels they
@@ -300,6 +306,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=1)
     ap.add_argument("--cpu-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--ref-max-steps", type=int, default=10)
+    ap.add_argument("--watchdog", type=int, default=1500, help="seconds after which a stuck run dumps its stacks and exits 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
