@@ -22,6 +22,28 @@ class CachedLatentDataset:
         self.masks = list(masks)
         self.vae_scaling_factor = float(vae_scaling_factor)
 
+    @classmethod
+    def from_images(cls, vae_encoder, captions: Sequence[str], images: Sequence[torch.Tensor],
+                    masks: Optional[Sequence[Optional[torch.Tensor]]], vae_scaling_factor: float) -> "CachedLatentDataset":
+        """The constructor's caching pass (dataset.py:85-99 -> ``_process`` 141-179): every image ([3, H, W] in [-1, 1],
+        what ``prepare_image`` returns) goes through the VAE encoder once and its posterior parameters are kept; a mask
+        ([1, H, W] or [H, W] in [0, 1], what ``prepare_mask`` returns) is resized to the latent grid with nearest
+        neighbour and repeated over the latent channels, no mask means all ones (dataset.py:160-175).
+        ``vae_encoder`` is a ``sd_lora_trainer_b200.vae.VAEEncoderB200``."""
+        params, out_masks = [], []
+        for i, img in enumerate(images):
+            p = vae_encoder.encode_moments(img[None] if img.dim() == 3 else img)
+            c, h, w = p.shape[1] // 2, p.shape[2], p.shape[3]
+            m = None if masks is None else masks[i]
+            if m is None:
+                m = torch.ones(c, h, w, dtype=torch.float32, device=p.device)
+            else:
+                m = m.to(p.device, torch.float32).reshape(1, 1, *m.shape[-2:])
+                m = torch.nn.functional.interpolate(m, size=(h, w), mode="nearest").repeat(1, c, 1, 1).squeeze(0)
+            params.append(p)
+            out_masks.append(m)
+        return cls(captions, params, out_masks, vae_scaling_factor)
+
     def __len__(self) -> int:
         return len(self.captions)
 
