@@ -145,6 +145,11 @@ int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, void* st
 int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, void* stream);
 int b200_silu_fwd(const void* x, void* y, int64_t n, void* stream);
 int b200_silu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
+/* CLIP text-encoder MLP activation ([3P] transformers CLIPMLP.activation_fn on the get_conditioning_signals path,
+   trainer/inference.py:131-177): kind 0 = exact (erf) GELU, kind 1 = quick_gelu x * sigmoid(1.702 x); bf16 in / out,
+   n elements; the backward reads the pre-activation x:  dx = dy * act'(x). */
+int b200_act_fwd(const void* x, void* y, int64_t n, int32_t kind, void* stream);
+int b200_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int32_t kind, void* stream);
 /* y = a + b (+ c), bf16 */
 int b200_add(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
 

@@ -193,6 +193,49 @@ __global__ void silu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restr
         dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * dsilu_f(__bfloat162float(x[i])));
 }
 
+// CLIP text-encoder MLP activations (transformers CLIPMLP, inference.py:131-177 path): kind 0 = exact (erf) GELU
+// (OpenCLIP bigG), kind 1 = quick_gelu x * sigmoid(1.702 x) (CLIP-L).  fp32 math, one bf16 rounding.
+template <int kKind>
+__global__ void act_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long n8, long long n) {
+    pdl_launch();
+    pdl_wait();
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float f[8], o[8];
+        load8(x + i * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = kKind == 0 ? gelu_f(f[j]) : silu_f(1.702f * f[j]) * (1.f / 1.702f);
+        store8(y + i * 8, o);
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) {
+            const float f = __bfloat162float(x[i]);
+            y[i] = __float2bfloat16_rn(kKind == 0 ? gelu_f(f) : silu_f(1.702f * f) * (1.f / 1.702f));
+        }
+    }
+}
+template <int kKind>
+__global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx,
+                               long long n8, long long n) {
+    pdl_launch();
+    pdl_wait();
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float f[8], d[8], o[8];
+        load8(x + i * 8, f);
+        load8(dy + i * 8, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = d[j] * (kKind == 0 ? dgelu_f(f[j]) : dsilu_f(1.702f * f[j]));
+        store8(dx + i * 8, o);
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) {
+            const float f = __bfloat162float(x[i]);
+            dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * (kKind == 0 ? dgelu_f(f) : dsilu_f(1.702f * f)));
+        }
+    }
+}
+
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ c,
                            bf16* __restrict__ y, long long n8, long long n) {
     pdl_launch();
@@ -575,6 +618,26 @@ extern "C" int b200_silu_bwd(const void* dy, const void* x, void* dx, int64_t n,
     launch_pdl(silu_bwd_kernel, dim3(grid_for(n, 256)), dim3(256), 0, ST, static_cast<const bf16*>(dy), static_cast<const bf16*>(x),
                                                       static_cast<bf16*>(dx), n);
     B200_CHECK_LAUNCH("silu_bwd");
+    return 0;
+}
+extern "C" int b200_act_fwd(const void* x, void* y, int64_t n, int32_t kind, void* stream) {
+    B200_CHECK_ARG(n >= 1 && x && y && (kind == 0 || kind == 1), "act_fwd: bad arguments (kind %d)", kind);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const long long n8 = aligned ? n / 8 : 0;
+    const dim3 grid(grid_for(n8 > 0 ? n8 : 1, 256));
+    if (kind == 0) launch_pdl(act_fwd_kernel<0>, grid, dim3(256), 0, ST, static_cast<const bf16*>(x), static_cast<bf16*>(y), n8, static_cast<long long>(n));
+    else launch_pdl(act_fwd_kernel<1>, grid, dim3(256), 0, ST, static_cast<const bf16*>(x), static_cast<bf16*>(y), n8, static_cast<long long>(n));
+    B200_CHECK_LAUNCH("act_fwd");
+    return 0;
+}
+extern "C" int b200_act_bwd(const void* dy, const void* x, void* dx, int64_t n, int32_t kind, void* stream) {
+    B200_CHECK_ARG(n >= 1 && dy && x && dx && (kind == 0 || kind == 1), "act_bwd: bad arguments (kind %d)", kind);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+    const long long n8 = aligned ? n / 8 : 0;
+    const dim3 grid(grid_for(n8 > 0 ? n8 : 1, 256));
+    if (kind == 0) launch_pdl(act_bwd_kernel<0>, grid, dim3(256), 0, ST, static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<bf16*>(dx), n8, static_cast<long long>(n));
+    else launch_pdl(act_bwd_kernel<1>, grid, dim3(256), 0, ST, static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<bf16*>(dx), n8, static_cast<long long>(n));
+    B200_CHECK_LAUNCH("act_bwd");
     return 0;
 }
 extern "C" int b200_add(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream) {

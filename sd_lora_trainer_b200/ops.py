@@ -269,6 +269,24 @@ def silu_bwd(dy: torch.Tensor, x: torch.Tensor):
     return dx
 
 
+ACT_GELU, ACT_QUICK_GELU = 0, 1
+
+
+def act_fwd(x: torch.Tensor, kind: int):
+    """CLIP MLP activation on a contiguous bf16 tensor: ACT_GELU (erf) or ACT_QUICK_GELU."""
+    assert x.is_contiguous() and x.dtype == BF16
+    y = torch.empty_like(x)
+    check(_lib.load().b200_act_fwd(x.data_ptr(), y.data_ptr(), x.numel(), kind, _stream()), "act_fwd")
+    return y
+
+
+def act_bwd(dy: torch.Tensor, x: torch.Tensor, kind: int):
+    assert x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape and x.dtype == BF16 and dy.dtype == BF16
+    dx = torch.empty_like(x)
+    check(_lib.load().b200_act_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), kind, _stream()), "act_bwd")
+    return dx
+
+
 def add(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
     assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
     y = torch.empty_like(a) if out is None else out

@@ -10,6 +10,7 @@ against the oracle from identical state.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -71,7 +72,7 @@ class TrainerB200:
 
     def __init__(self, cfg: StepConfig, unet_state_dict: Dict[str, torch.Tensor], text_encoders: Sequence,
                  device="cuda:0", ti_init: Optional[List[torch.Tensor]] = None, process_group=None,
-                 use_cuda_graph: bool = False):
+                 use_cuda_graph: bool = False, native_text: Optional[bool] = None):
         self.cfg, self.device = cfg, torch.device(device)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
@@ -105,6 +106,14 @@ class TrainerB200:
                 self.train_ids = list(range(vocab, vocab + ntok))
                 off += ntok * dim
             self.unet.set_capture(True)                        # init_daam_loss, main.py:50-52
+        # Text encoders: stock transformers modules under autograd (default), or the explicit fwd/bwd executor over
+        # our kernels (clip.py; B200_NATIVE_CLIP=1 / native_text=True).
+        if native_text is None:
+            native_text = os.environ.get("B200_NATIVE_CLIP", "0") == "1"
+        self.text = None
+        if native_text and self.text_encoders[0] is not None:
+            from .clip import TextStackB200
+            self.text = TextStackB200(self.sdxl, self.text_encoders, self.ti_rows, self.device)
         self.global_step = 0
         self.opt_step = 0
         self._accum = 0
@@ -172,7 +181,10 @@ class TrainerB200:
         offset = st["offset_noise"] if cfg.noise_offset > 0 else None
         token_ids = [st[f"token_ids_{i}"] for i in range(2 if self.sdxl else 1)]
         need_text_grad = bool(self.ti_rows)
-        if self.text_encoders[0] is not None:
+        if self.text is not None:
+            self.text.prepare(token_ids[0].shape[1])
+            prompt_embeds, pooled = self.text.encode_prompt(token_ids, need_bwd=need_text_grad)
+        elif self.text_encoders[0] is not None:
             with torch.set_grad_enabled(need_text_grad):
                 prompt_embeds, pooled = encode_prompt(self.sdxl, self.text_encoders, token_ids)
         else:                                                   # kernel-only probes: synthetic conditioning
@@ -203,22 +215,32 @@ class TrainerB200:
         d_ctx, d_text = self.unet.backward(dpred8, dscores)
         out["d_prompt_embeds"] = d_ctx
         if need_text_grad:
-            roots, grads = [prompt_embeds], [d_ctx.to(prompt_embeds.dtype)]
-            if pooled is not None and d_text is not None:
-                roots.append(pooled)
-                grads.append(d_text.to(pooled.dtype))
+            roots, grads = [], []
+            if self.text is not None:                         # explicit CLIP backward: TI-row gradients land in the flat buffer
+                off, views = self.store.n_lora, []
+                for rows in self.ti_rows:
+                    views.append(self.store.grads[off:off + rows.numel()].view(rows.shape))
+                    off += rows.numel()
+                self.text.backward(d_ctx, d_text if pooled is not None else None, views)
+            else:
+                roots, grads = [prompt_embeds], [d_ctx.to(prompt_embeds.dtype)]
+                if pooled is not None and d_text is not None:
+                    roots.append(pooled)
+                    grads.append(d_text.to(pooled.dtype))
             if ti_active:                                     # token-std regulariser, loss.py:222-231
                 std = torch.stack([reg.compute_std_loss(rows) for reg, rows in zip(self.std_regs, self.ti_rows)]).mean()
                 out["token_std_loss"] = std.detach()
                 total = total + 0.01 * std.detach().float()
                 roots.append(0.01 * std / ga)
                 grads.append(torch.ones_like(std))
-            torch.autograd.backward(roots, grads)
+            if roots:
+                torch.autograd.backward(roots, grads)
             off = self.store.n_lora
             for rows in self.ti_rows:                         # move the 3-row gradients into the flat fp32 buffer
                 n = rows.numel()
-                self.store.grads[off:off + n] += rows.grad.float().flatten()
-                rows.grad = None
+                if rows.grad is not None:
+                    self.store.grads[off:off + n] += rows.grad.float().flatten()
+                    rows.grad = None
                 off += n
         out["tot_loss"] = total
         return out

@@ -194,6 +194,25 @@ def silu_bwd(dy, x):
     return _bf(xr.grad)
 
 
+ACT_GELU, ACT_QUICK_GELU = real.ACT_GELU, real.ACT_QUICK_GELU
+
+
+def _act(x, kind):
+    return F.gelu(x) if kind == ACT_GELU else x * torch.sigmoid(1.702 * x)
+
+
+def act_fwd(x, kind):
+    assert x.is_contiguous() and x.dtype == BF16
+    return _bf(_act(x.float(), kind))
+
+
+def act_bwd(dy, x, kind):
+    assert x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape
+    xf = x.float().detach().requires_grad_(True)
+    _act(xf, kind).backward(dy.float())
+    return _bf(xf.grad)
+
+
 def add(a, b, c=None, out=None):
     y = a.float() + b.float()
     if c is not None:
@@ -368,7 +387,10 @@ def install(monkeypatch):
     import sd_lora_trainer_b200.step as step_mod
     import sd_lora_trainer_b200.unet as unet_mod
     import sd_lora_trainer_b200.trainer.loss as loss_mod
+    import sd_lora_trainer_b200.clip as clip_mod
+    import sd_lora_trainer_b200.vae as vae_mod
+    import sd_lora_trainer_b200.trainer.dataset as dataset_mod
     import sys
     me = sys.modules[__name__]
-    for mod in (step_mod, unet_mod, loss_mod):
+    for mod in (step_mod, unet_mod, loss_mod, clip_mod, vae_mod, dataset_mod):
         monkeypatch.setattr(mod, "ops", me)
