@@ -48,6 +48,7 @@ class StepConfig:
     max_train_steps: int = 300
     unet_lr_warmup_steps: Optional[int] = None
     freeze_ti_after_completion_f: float = 0.7
+    freeze_unet_before_completion_f: float = 0.0
     seed: int = 0
 
     def arch(self) -> UNetArch:
@@ -64,7 +65,10 @@ def lr_schedule(cfg: StepConfig, global_step: int, completion_f: float):
             ti_lr = 0.0
     base = 2.0e-4 if cfg.disable_ti else 5.0e-5
     warm = cfg.unet_lr_warmup_steps if cfg.unet_lr_warmup_steps is not None else cfg.max_train_steps
-    return ti_lr, base * (cfg.unet_lr / base) ** (global_step / warm)
+    unet_lr = base * (cfg.unet_lr / base) ** (global_step / warm)
+    if completion_f < cfg.freeze_unet_before_completion_f:     # main.py:290-291
+        unet_lr = 0.0
+    return ti_lr, unet_lr
 
 
 class TrainerB200:
@@ -270,12 +274,16 @@ class TrainerB200:
         self._optimizer_body()
         self.opt_step += 1
 
-    def step(self, inputs, completion_f: float = 0.0, do_optimizer: bool = True):
+    def step(self, inputs, completion_f: float = 0.0, do_optimizer: bool = True, optimizer_now: Optional[bool] = None):
+        """One micro-step.  The optimizer runs every ``gradient_accumulation_steps`` calls unless ``optimizer_now``
+        states it explicitly (main.py:365-366 also steps on the last batch of an epoch)."""
         ti_lr, unet_lr = lr_schedule(self.cfg, self.global_step, completion_f)
         self.last_lrs = (ti_lr, unet_lr)
         ti_active = bool(ti_lr and ti_lr > 0.0)
         self._accum += 1
         opt_now = do_optimizer and self._accum % self.cfg.gradient_accumulation_steps == 0
+        if optimizer_now is not None:
+            opt_now = bool(optimizer_now)
         if self.use_graph:
             out = self._graph_step(inputs, ti_active, opt_now)
         else:
