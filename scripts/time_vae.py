@@ -5,11 +5,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle.vae import VAEConfig, build_vae, state_dict_of            # noqa: E402  (weights only; not timed)
+from sd_lora_trainer_b200.init import random_vae_encoder_state_dict  # noqa: E402
 from sd_lora_trainer_b200.vae import VAEEncoderB200                   # noqa: E402
 
-orc = build_vae(VAEConfig(), seed=0)
-enc = VAEEncoderB200(state_dict_of(orc), device="cuda:0")
+enc = VAEEncoderB200(random_vae_encoder_state_dict(seed=0, device="cuda"), device="cuda:0")
 for side in (512, 1024):
     img = torch.rand(1, 3, side, side, device="cuda") * 2 - 1
     for _ in range(2):

@@ -120,3 +120,66 @@ def random_state_dict(a: UNetArch, seed: int = 0, device="cpu", dtype=torch.bflo
         bound = fan[base] ** -0.5
         sd[name] = ((torch.rand(shape, device=device, generator=g) * 2 - 1) * bound).to(dtype)
     return sd
+
+
+def vae_encoder_param_shapes(block_out_channels=(128, 256, 512, 512), layers_per_block: int = 2, in_channels: int = 3,
+                             latent_channels: int = 4) -> List[Tuple[str, Tuple[int, ...]]]:
+    """diffusers AutoencoderKL keys the VAE-encode prologue reads (``encoder.*`` + ``quant_conv.*``), in vae.py's order."""
+    out: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def conv(n, i, o, k):
+        out.append((f"{n}.weight", (o, i, k, k)))
+        out.append((f"{n}.bias", (o,)))
+
+    def norm(n, c):
+        out.append((f"{n}.weight", (c,)))
+        out.append((f"{n}.bias", (c,)))
+
+    def resnet(p, cin, cout):
+        norm(f"{p}.norm1", cin)
+        conv(f"{p}.conv1", cin, cout, 3)
+        norm(f"{p}.norm2", cout)
+        conv(f"{p}.conv2", cout, cout, 3)
+        if cin != cout:
+            conv(f"{p}.conv_shortcut", cin, cout, 1)
+
+    boc = block_out_channels
+    conv("encoder.conv_in", in_channels, boc[0], 3)
+    cout = boc[0]
+    for i, c in enumerate(boc):
+        cin, cout = cout, c
+        for j in range(layers_per_block):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout)
+        if i < len(boc) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
+    c = boc[-1]
+    resnet("encoder.mid_block.resnets.0", c, c)
+    resnet("encoder.mid_block.resnets.1", c, c)
+    a = "encoder.mid_block.attentions.0"
+    norm(f"{a}.group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        out.append((f"{a}.{n}.weight", (c, c)))
+        out.append((f"{a}.{n}.bias", (c,)))
+    norm("encoder.conv_norm_out", c)
+    conv("encoder.conv_out", c, 2 * latent_channels, 3)
+    conv("quant_conv", 2 * latent_channels, 2 * latent_channels, 1)
+    return out
+
+
+def random_vae_encoder_state_dict(seed: int = 0, device="cpu", dtype=torch.float32, **arch) -> Dict[str, torch.Tensor]:
+    """Random-init VAE encoder weights (torch default U(-1/sqrt(fan_in), 1/sqrt(fan_in)); norms at 1 / 0)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    fan: Dict[str, int] = {}
+    for name, shape in vae_encoder_param_shapes(**arch):
+        base = name.rsplit(".", 1)[0]
+        if "norm" in base.rsplit(".", 1)[-1]:
+            sd[name] = (torch.ones if name.endswith("weight") else torch.zeros)(shape, device=device, dtype=dtype)
+            continue
+        if name.endswith(".weight"):
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            fan[base] = fan_in
+        sd[name] = ((torch.rand(shape, device=device, generator=g) * 2 - 1) * fan[base] ** -0.5).to(dtype)
+    return sd

@@ -130,3 +130,19 @@ def test_cached_dataset_from_images(monkeypatch):
     assert torch.equal(ds.masks[0], want) and float(ds.masks[1].min()) == 1.0 and ds.masks[1].shape == (4, 4, 4)
     cap, lat, m = ds[1]
     assert cap == "b" and lat.shape == (4, 4, 4) and m.shape == (4, 4, 4)
+
+
+@pytest.mark.parametrize("tiny", [False, True])
+def test_vae_param_shapes_match_oracle_state_dict(tiny):
+    """The product's own enumeration of the VAE keys (random init for benches) names and shapes every oracle parameter."""
+    from oracle.vae import AutoencoderKLEncoder, VAEConfig
+    from sd_lora_trainer_b200.init import random_vae_encoder_state_dict, vae_encoder_param_shapes
+    cfg = VAEConfig.tiny() if tiny else VAEConfig()
+    with torch.device("meta"):
+        ref = AutoencoderKLEncoder(cfg)
+    want = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    kw = dict(block_out_channels=cfg.block_out_channels, layers_per_block=cfg.layers_per_block)
+    assert dict(vae_encoder_param_shapes(**kw)) == want
+    if tiny:
+        sd = random_vae_encoder_state_dict(seed=1, **kw)
+        assert float(sd["encoder.conv_norm_out.weight"].min()) == 1.0 and float(sd["encoder.conv_in.weight"].abs().max()) <= 27 ** -0.5
