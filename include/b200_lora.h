@@ -135,6 +135,13 @@ int b200_groupnorm_fwd(const void* x, const void* gamma, const void* beta, void*
 int b200_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const void* beta, const float* stats,
                        const void* dres, void* dx, int32_t batch, int64_t hw, int32_t C, int32_t groups, int32_t silu,
                        void* stream);
+/* Affine-parameter gradients of a frozen-no-more norm layer (dense / full-UNet fine-tune backward, BASELINE config 5;
+   main.py:143-148 `unet.requires_grad_(True)`): dgamma[c] += sum dz * xhat, dbeta[c] += sum dz (fp32, accumulating).
+   groups > 0: GroupNorm over x [rows = batch*hw, C] with stats [(batch*groups) x (mean, rstd)] as groupnorm_fwd wrote
+   them, silu = 1 when the layer fused SiLU (dz = dy * silu'(xhat*gamma+beta)); groups == 0: LayerNorm, stats per row. */
+int b200_norm_param_grad(const void* dy, const void* x, const void* gamma, const void* beta, const float* stats,
+                         float* dgamma, float* dbeta, int64_t rows, int64_t hw, int32_t C, int32_t groups, int32_t silu,
+                         void* stream);
 /* stats: [rows, 2] fp32 (mean, rstd) */
 int b200_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, int64_t rows,
                        int32_t C, float eps, void* stream);

@@ -26,6 +26,7 @@ class StepConfig:
     tiny: bool = False
     resolution: int = 1024
     lora_rank: int = 16
+    is_lora: bool = True               # False: full-UNet fine-tune (main.py:143-148)
     lora_alpha_multiplier: float = 1.0
     lora_weight_decay: float = 0.004
     unet_lr: float = 0.0003
@@ -58,6 +59,8 @@ def lr_schedule(cfg: StepConfig, global_step: int, completion_f: float):
         if completion_f > cfg.freeze_ti_after_completion_f:
             ti_lr = 0.0
     base = 2.0e-4 if cfg.disable_ti else 5.0e-5
+    if not cfg.is_lora:
+        base = 1.0e-5                                                     # main.py:239-240
     warm = cfg.unet_lr_warmup_steps if cfg.unet_lr_warmup_steps is not None else cfg.max_train_steps
     unet_lr = base * (cfg.unet_lr / base) ** (global_step / warm)
     return ti_lr, unet_lr
@@ -98,12 +101,19 @@ class OracleTrainer:
                 weight_decay=cfg.ti_weight_decay)                         # optimizer.py:144-148
         else:
             self.opt_ti = None
-        self.unet, self.lora_params = inject_lora(self.unet, cfg.lora_rank, cfg.lora_alpha_multiplier,
-                                                  seed=cfg.seed + 2)
-        self.unet.to(self.device)                                         # adapters were created on the host
-        self.lora_params = [p for p in self.unet.parameters() if p.requires_grad]
+        if cfg.is_lora:
+            self.unet.requires_grad_(False)                               # main.py:108
+            self.unet, self.lora_params = inject_lora(self.unet, cfg.lora_rank, cfg.lora_alpha_multiplier,
+                                                      seed=cfg.seed + 2)
+            self.unet.to(self.device)                                     # adapters were created on the host
+            self.lora_params = [p for p in self.unet.parameters() if p.requires_grad]
+            trainable = self.lora_params
+        else:                                                             # main.py:143-148: full fine-tuning
+            self.unet.requires_grad_(True)
+            self.lora_params = []                                         # unet_lora_parameters = None: no L1 penalty
+            trainable = list(self.unet.parameters())
         self.opt_unet = torch.optim.AdamW(
-            [{"params": self.lora_params, "weight_decay": cfg.lora_weight_decay}],
+            [{"params": trainable, "weight_decay": cfg.lora_weight_decay}],
             lr=1e-4, weight_decay=cfg.lora_weight_decay)                  # optimizer.py:16-17
         self.global_step = 0
         self._accum = 0

@@ -52,6 +52,8 @@ SIGNATURES = {
     "b200_geglu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
     "b200_silu_fwd": [c_void_p, c_void_p, c_int64, c_void_p],
     "b200_silu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
+    "b200_norm_param_grad": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                             c_int32, c_int32, c_int32, c_void_p],
     "b200_act_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_void_p],
     "b200_act_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
     "b200_add": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],

@@ -331,6 +331,98 @@ extern "C" int b200_groupnorm_bwd(const void* dy, const void* x, const void* gam
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Affine-parameter gradients of GroupNorm(+SiLU) / LayerNorm for the dense (full fine-tune) backward, BASELINE config 5:
+//   dgamma[c] += sum_rows dz * xhat      dbeta[c] += sum_rows dz,     dz = dy (* silu'(xhat*gamma+beta) when fused)
+// kGroup: statistics per (sample, group) [GroupNorm] instead of per row [LayerNorm].  A block owns 32 channel vectors
+// (256 channels) x `rows_per_block` rows: 8 row lanes accumulate in registers, are combined through shared memory and
+// leave as one fp32 atomicAdd per channel and block.
+// ---------------------------------------------------------------------------------------------
+template <bool kGroup, bool kSilu>
+__global__ void norm_param_grad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                       const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                       const float* __restrict__ stats, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, long long rows, long long hw, int C, int groups,
+                                       long long rows_per_block) {
+    pdl_launch();
+    pdl_wait();
+    __shared__ float red[8][32][17];
+    const int C8 = C >> 3, cpg = kGroup ? C / groups : 1;
+    const int vl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int v = blockIdx.x * 32 + vl;
+    const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+    const long long r1 = min(r0 + rows_per_block, rows);
+    float ag[8], ab[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ag[i] = ab[i] = 0.f;
+    if (v < C8) {
+        float gm[8], bt[8];
+        if (kSilu) {
+            load8(gamma + v * 8, gm);
+            load8(beta + v * 8, bt);
+        }
+        for (long long r = r0 + rl; r < r1; r += 8) {
+            float f[8], d[8];
+            load8(x + r * C + v * 8, f);
+            load8(dy + r * C + v * 8, d);
+            const long long b = kGroup ? r / hw : 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long si = kGroup ? (b * groups + (v * 8 + i) / cpg) : r;
+                const float xh = (f[i] - stats[si * 2]) * stats[si * 2 + 1];
+                float dz = d[i];
+                if (kSilu) dz = bfr(dz * dsilu_f(bfr(xh * gm[i] + bt[i])));
+                ag[i] += dz * xh;
+                ab[i] += dz;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        red[rl][vl][i] = ag[i];
+        red[rl][vl][8 + i] = ab[i];
+    }
+    __syncthreads();
+    // 32 vectors x 16 values = 512 sums per block; 256 threads take two each
+    for (int t = threadIdx.x; t < 32 * 16; t += blockDim.x) {
+        const int tv = t >> 4, j = t & 15;
+        const int cv = blockIdx.x * 32 + tv;
+        if (cv >= C8) continue;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += red[k][tv][j];
+        if (j < 8) atomicAdd(dgamma + cv * 8 + j, sum);
+        else atomicAdd(dbeta + cv * 8 + (j - 8), sum);
+    }
+}
+
+extern "C" int b200_norm_param_grad(const void* dy, const void* x, const void* gamma, const void* beta, const float* stats,
+                                    float* dgamma, float* dbeta, int64_t rows, int64_t hw, int32_t C, int32_t groups,
+                                    int32_t silu, void* stream) {
+    B200_CHECK_ARG(dy && x && stats && dgamma && dbeta && rows >= 1 && C >= 8 && C % 8 == 0, "norm_param_grad: bad arguments");
+    B200_CHECK_ARG(groups == 0 || (groups >= 1 && C % groups == 0 && hw >= 1 && rows % hw == 0),
+                   "norm_param_grad: C=%d groups=%d", C, groups);
+    B200_CHECK_ARG(!silu || (groups > 0 && gamma && beta), "norm_param_grad: the fused SiLU needs GroupNorm gamma / beta");
+    const int cblocks = (C / 8 + 31) / 32;
+    long long splits = (kNumSMs * 4 + cblocks - 1) / cblocks;
+    long long rpb = (rows + splits - 1) / splits;
+    if (rpb < 64) rpb = 64;
+    splits = (rows + rpb - 1) / rpb;
+    B200_CHECK_ARG(splits <= 65535, "norm_param_grad: too many row blocks");
+    const dim3 grid(cblocks, static_cast<unsigned>(splits));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define NPG(G, S)                                                                                                     \
+    launch_pdl(norm_param_grad_kernel<G, S>, grid, dim3(256), 0, st, static_cast<const bf16*>(dy), static_cast<const bf16*>(x), \
+               static_cast<const bf16*>(gamma), static_cast<const bf16*>(beta), stats, dgamma, dbeta,                  \
+               static_cast<long long>(rows), static_cast<long long>(hw), C, groups, rpb)
+    if (groups > 0 && silu) NPG(true, true);
+    else if (groups > 0) NPG(true, false);
+    else NPG(false, false);
+#undef NPG
+    B200_CHECK_LAUNCH("norm_param_grad");
+    return 0;
+}
+
 extern "C" int b200_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats,
                                   int64_t rows, int32_t C, float eps, void* stream) {
     B200_CHECK_ARG(C % 8 == 0 && C <= kLnMaxVec * 256, "layernorm: unsupported C=%d", C);

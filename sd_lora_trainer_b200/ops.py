@@ -243,6 +243,17 @@ def layernorm_bwd(dy, x, gamma, stats, dres=None):
     return dx
 
 
+def norm_param_grad(dy: torch.Tensor, x: torch.Tensor, gamma, beta, stats: torch.Tensor, dgamma: torch.Tensor,
+                    dbeta: torch.Tensor, hw: int = 0, groups: int = 0, silu: bool = False):
+    """dgamma / dbeta (fp32, accumulated in place) of a GroupNorm(+SiLU) (groups > 0) or LayerNorm (groups == 0)."""
+    rows, C_ = x.shape
+    assert dy.shape == x.shape and dy.is_contiguous() and x.is_contiguous()
+    assert dgamma.dtype == torch.float32 and dbeta.dtype == torch.float32 and dgamma.numel() == C_ == dbeta.numel()
+    check(_lib.load().b200_norm_param_grad(dy.data_ptr(), x.data_ptr(), _p(gamma), _p(beta), stats.data_ptr(),
+                                           dgamma.data_ptr(), dbeta.data_ptr(), rows, hw if groups else rows, C_, groups,
+                                           int(silu), _stream()), "norm_param_grad")
+
+
 def geglu_fwd(h: torch.Tensor):
     rows, two_inner = h.shape
     y = torch.empty(rows, two_inner // 2, dtype=BF16, device=h.device)

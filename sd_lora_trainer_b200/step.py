@@ -33,6 +33,7 @@ class StepConfig:
     tiny: bool = False
     resolution: int = 1024
     lora_rank: int = 16
+    is_lora: bool = True               # False: full-UNet fine-tune (BASELINE config 5; needs disable_ti=True here)
     lora_alpha_multiplier: float = 1.0
     lora_weight_decay: float = 0.004
     unet_lr: float = 0.0003
@@ -64,6 +65,8 @@ def lr_schedule(cfg: StepConfig, global_step: int, completion_f: float):
         if completion_f > cfg.freeze_ti_after_completion_f:
             ti_lr = 0.0
     base = 2.0e-4 if cfg.disable_ti else 5.0e-5
+    if not cfg.is_lora:
+        base = 1.0e-5                                           # main.py:239-240
     warm = cfg.unet_lr_warmup_steps if cfg.unet_lr_warmup_steps is not None else cfg.max_train_steps
     unet_lr = base * (cfg.unet_lr / base) ** (global_step / warm)
     if completion_f < cfg.freeze_unet_before_completion_f:     # main.py:290-291
@@ -88,9 +91,14 @@ class TrainerB200:
         dims = [te.text_model.embeddings.token_embedding.weight.shape[1] for te in self.text_encoders if te is not None]
         ntok = 0 if cfg.disable_ti else cfg.n_tokens
         ti_elems = sum(ntok * d for d in dims)
-        self.unet = UNetB200(cfg.arch(), unet_state_dict, cfg.lora_rank, cfg.lora_alpha_multiplier, self.device,
-                             ti_elems=ti_elems, lora_seed=cfg.seed + 2)
+        self.dense_mode = not cfg.is_lora
+        if self.dense_mode and ntok:
+            raise NotImplementedError("full-UNet fine-tuning runs with disable_ti=True here (BASELINE config 5, SURVEY.md 8d)")
+        self.unet = UNetB200(cfg.arch(), unet_state_dict, 0 if self.dense_mode else cfg.lora_rank,
+                             cfg.lora_alpha_multiplier, self.device, ti_elems=ti_elems, lora_seed=cfg.seed + 2,
+                             dense=self.dense_mode)
         self.store = self.unet.store
+        self.dense = self.unet.dense
         self.acp = alphas_cumprod_table(device=self.device)
         self.train_ids: List[int] = []
         self.ti_rows: List[torch.Tensor] = []
@@ -212,7 +220,7 @@ class TrainerB200:
             out["token_attention_loss"] = tal.detach()
             out["attention_scores"] = scores
             total = total + cfg.token_attention_loss_w * tal.detach().float()
-        if cfg.l1_penalty > 0.0:
+        if cfg.l1_penalty > 0.0 and self.store.n_lora > 0:      # main.py:353: only with LoRA parameters
             l1 = torch.zeros(1, dtype=torch.float32, device=dev)
             ops.abs_sum(self.store.params[:self.store.n_lora], l1)
             total = total + cfg.l1_penalty * l1 / self.store.numel_logical
@@ -251,7 +259,7 @@ class TrainerB200:
 
     # ---- optimizer: ONE kernel over LoRA factors + TI rows -------------------------------------------
     def _l1_coeff(self) -> float:
-        if self.cfg.l1_penalty <= 0.0:
+        if self.cfg.l1_penalty <= 0.0 or self.store.n_lora == 0:
             return 0.0
         # what autograd hands to every LoRA element for  loss += l1_penalty * sum|p| / numel  in bf16
         return float(torch.tensor(self.cfg.l1_penalty, dtype=BF16) / self.store.numel_logical)
@@ -263,11 +271,19 @@ class TrainerB200:
                              lr2=ti_lr or 0.0, wd2=self.cfg.ti_weight_decay, step=self.opt_step + 1, grad_scale=1.0)
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
 
+    def _train_state(self):
+        """(params, grads, m, v, n_first) of the buffer set the optimizer walks: the flat LoRA + TI buffers, or every UNet
+        parameter in dense (full fine-tune) mode."""
+        if self.dense_mode:
+            d = self.dense
+            return d.params, d.grads, d.m, d.v, d.params.numel()
+        return self.store.params, self.store.grads, self.store.m, self.store.v, self.store.n_lora
+
     def _optimizer_body(self, collective: bool = True):
+        p, g, m, v, n_first = self._train_state()
         if collective and self.pg is not None and self.world > 1:
-            torch.distributed.all_reduce(self.store.grads, group=self.pg)     # the step's only collective
-        ops.adamw_dev(self.store.params, self.store.grads, self.store.m, self.store.v, self.store.n_lora,
-                      self._hyper_dev, zero_grad=True)
+            torch.distributed.all_reduce(g, group=self.pg)                    # the step's only collective
+        ops.adamw_dev(p, g, m, v, n_first, self._hyper_dev, zero_grad=True)
 
     def optimizer_step(self):
         self._set_hyper()
@@ -334,7 +350,7 @@ class TrainerB200:
         """Eager, instrumented pass over one step: every distinct tcgen05 GEMM signature is timed live (CUDA events
         around a graph of 10 launches of the very call, ops._profile_gemm) and weighted by its launch count.
         Training state is restored afterwards."""
-        snap = [t.clone() for t in (self.store.params, self.store.grads, self.store.m, self.store.v)]
+        snap = [t.clone() for t in self._train_state()[:4]]
         st = self._stage_inputs(inputs)
         ops.GEMM_PROFILE = {}
         try:
@@ -345,7 +361,7 @@ class TrainerB200:
             recs = ops.GEMM_PROFILE
         finally:
             ops.GEMM_PROFILE = None
-        for t, s_ in zip((self.store.params, self.store.grads, self.store.m, self.store.v), snap):
+        for t, s_ in zip(self._train_state()[:4], snap):
             t.copy_(s_)
         for rows in self.ti_rows:
             rows.grad = None
@@ -365,7 +381,7 @@ class TrainerB200:
     def _capture(self, st, ti_active: bool, opt_now: bool):
         """Warm up eagerly on a side stream, then capture.  The warm-up runs must not change training state, so the
         flat buffers are snapshotted and restored around them."""
-        snap = [t.clone() for t in (self.store.params, self.store.grads, self.store.m, self.store.v)]
+        snap = [t.clone() for t in self._train_state()[:4]]
 
         def run():
             out = self._body(st, ti_active)
@@ -382,7 +398,7 @@ class TrainerB200:
                 run()
                 self.launches_per_step = _lib.launch_count() - l0     # our kernels per step (graph replays them)
         torch.cuda.current_stream().wait_stream(side)
-        for t, s_ in zip((self.store.params, self.store.grads, self.store.m, self.store.v), snap):
+        for t, s_ in zip(self._train_state()[:4], snap):
             t.copy_(s_)
         for rows in self.ti_rows:
             rows.grad = None

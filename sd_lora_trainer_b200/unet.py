@@ -195,6 +195,70 @@ class LoraStore:
 
 
 # =================================================================================================
+# Dense parameter store (full-UNet fine-tune, BASELINE config 5 / main.py:143-148): EVERY UNet parameter in one flat
+# bf16 buffer (in the executor's native layouts), one flat fp32 gradient buffer, bf16 Adam moments
+# =================================================================================================
+class DenseStore:
+    def __init__(self, device):
+        self.device = device
+        self.entries: List[Tuple[object, str, str, str, str, Tuple[int, ...]]] = []
+        self.total = 0
+        self.params = self.grads = self.m = self.v = None
+        self.views: Dict[str, Tuple[torch.Tensor, torch.Tensor, str, Tuple[int, ...]]] = {}
+
+    def add(self, owner, attr: str, gattr: str, key: str, kind: str, meta: Tuple[int, ...] = ()):
+        """owner.attr holds the parameter now; finalize() re-points it (and owner.gattr, its fp32 gradient) at views of
+        the flat buffers.  kind: 'mat' ([N, K] <-> diffusers [N, K] or [N, K, 1, 1]), 'vec', 'conv' ([Cout, (kh,kw,c_p)]
+        <-> [Cout, Cin, 3, 3], meta = (cout, cin, cin_p))."""
+        self.entries.append((owner, attr, gattr, key, kind, meta))
+
+    def finalize(self):
+        offs = []
+        for owner, attr, *_ in self.entries:
+            offs.append(self.total)
+            self.total += _r8(getattr(owner, attr).numel())
+        n = max(self.total, 8)
+        self.params = torch.zeros(n, dtype=BF16, device=self.device)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.m = torch.zeros(n, dtype=BF16, device=self.device)
+        self.v = torch.zeros(n, dtype=BF16, device=self.device)
+        for off, (owner, attr, gattr, key, kind, meta) in zip(offs, self.entries):
+            t = getattr(owner, attr)
+            pv = self.params[off:off + t.numel()].view(t.shape)
+            pv.copy_(t)
+            gv = self.grads[off:off + t.numel()].view(t.shape)
+            setattr(owner, attr, pv)
+            setattr(owner, gattr, gv)
+            self.views[key] = (pv, gv, kind, meta)
+
+    @property
+    def numel_logical(self) -> int:
+        n = 0
+        for pv, _, kind, meta in self.views.values():
+            n += meta[0] * meta[1] * 9 if kind == "conv" else pv.numel()
+        return n
+
+    def export(self, grads: bool = False) -> Dict[str, torch.Tensor]:
+        """diffusers-layout state dict (or gradients) of the trained UNet."""
+        out = {}
+        for key, (pv, gv, kind, meta) in self.views.items():
+            t = gv if grads else pv
+            if kind == "conv":
+                cout, cin, cin_p = meta
+                t = t.view(cout, 3, 3, cin_p)[..., :cin].permute(0, 3, 1, 2)
+            elif kind == "mat" and meta:
+                t = t.reshape(meta)
+            out[key] = t.contiguous().clone()
+        return out
+
+
+def _dense_splits(out_rows: int, out_cols: int, reduce_len: int) -> int:
+    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
+    kblocks = (reduce_len + 63) // 64
+    return max(1, min(_SMS // max(tiles, 1), kblocks, 32))
+
+
+# =================================================================================================
 # layers
 # =================================================================================================
 class Lin:
@@ -204,6 +268,7 @@ class Lin:
         self.W, self.b, self.lora = W.contiguous(), b, lora
         self.N, self.K = W.shape
         self.x = self.T = None
+        self.gW = self.gb = None                      # fp32 gradient views (DenseStore) when the layer itself trains
 
     def fwd(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, save: bool = True, bias=None,
             bias_rows: int = 0) -> torch.Tensor:
@@ -253,6 +318,13 @@ class Lin:
                     ops.gemm(lo.gB(), self.N, r, [seg_b], d_strides=(rs, 1, 0, 0), splits=_wgrad_splits(self.N, M), atomic=True)
                     ops.gemm(lo.gA(), self.K, r, [seg_a], d_strides=(1, self.K, 0, 0), splits=_wgrad_splits(self.K, M), atomic=True)
             WGRAD.run(wgrad, dy, T, x, U)
+        if self.gW is not None:
+            # dense fine-tune: dW[N, K] += dY^T . X (both operands MN-major, split-K fp32 atomics), db += colsum(dY)
+            ops.gemm(self.gW, self.N, self.K, [(Mat(dy, M, self.N, dy.stride(0), mn=True),
+                                                Mat(x, M, self.K, x.stride(0), mn=True), M)],
+                     d_strides=(self.K, 1, 0, 0), splits=_dense_splits(self.N, self.K, M), atomic=True)
+            if self.gb is not None:
+                self.gb += ops.colsum(dy if dy.is_contiguous() else dy.contiguous(), 1, M, self.N)[0].float()
         return dx
 
 
@@ -275,6 +347,13 @@ class Conv3:
             wd[..., :cout] = w.flip(2, 3).permute(1, 2, 3, 0)    # dgrad = conv with flipped, transposed taps
             self.wd = wd.reshape(cin, 9 * self.cout_p).contiguous()
         self.sv = None
+        self.gwk = self.gb = None                     # fp32 gradient views (DenseStore) when the layer itself trains
+
+    def refresh_dgrad(self):
+        """Dense fine-tune: the input-gradient copy of the taps follows the trained forward copy (once per step)."""
+        if self.wd is not None:
+            wk4 = self.wk.view(self.cout, 3, 3, self.cin_p)[..., :self.cin]
+            self.wd.view(self.cin, 3, 3, self.cout_p)[..., :self.cout].copy_(wk4.flip(1, 2).permute(3, 1, 2, 0))
 
     def fwd(self, x: torch.Tensor, N: int, H: int, W: int, bias=None, bias_rows: int = 0,
             residual: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -307,7 +386,7 @@ class Conv3:
         y = (torch.empty if ld_out == self.cout else torch.zeros)(Mo, ld_out, dtype=BF16, device=x.device)
         ops.gemm(y, Mo, self.cout, segs, d_strides=(ld_out, 1, 0, 0), bias=bias, bias_rows=bias_rows,
                  bias_sb=self.cout if bias_rows else 0, residual=residual, static_b=True)
-        self.sv = (x if lo is not None else None, T, N, H, W)
+        self.sv = (x if (lo is not None or self.gwk is not None) else None, T, N, H, W)
         return y
 
     def bwd(self, dy: torch.Tensor, need_dx: bool = True) -> Optional[torch.Tensor]:
@@ -332,6 +411,16 @@ class Conv3:
                                                  Mat(U9, Mi, 9 * r, U9.stride(0), mn=True), Mi)],
                      d_strides=(1, self.cin, 0, 0), splits=_wgrad_splits(self.cin, Mi), atomic=True)
             extra = [(Mat(U9, Mi, 9 * r, U9.stride(0)), Mat(lo.A(), 9 * r, self.cin, self.cin, mn=True), 9 * r)]
+        if self.gwk is not None:
+            # dense fine-tune: dW[Cout, (kh,kw,c)] += dY^T . im2col(X), db += colsum(dY)
+            K9 = 9 * self.cin_p
+            col = ops.im2col3x3(x, N, H, W, self.cin_p, s)
+            ops.gemm(self.gwk, self.cout, K9, [(Mat(dy, Mo, self.cout, dy.stride(0), mn=True), Mat(col, Mo, K9, K9, mn=True), Mo)],
+                     d_strides=(K9, 1, 0, 0), splits=_dense_splits(self.cout, K9, Mo), atomic=True)
+            del col
+            if self.gb is not None:
+                dyc = dy if dy.is_contiguous() else dy.contiguous()
+                self.gb += ops.colsum(dyc, 1, Mo, dyc.shape[1])[0, :self.cout].float()
         if not need_dx:
             return None
         dx = torch.empty(Mi, self.cin, dtype=BF16, device=dy.device)
@@ -355,6 +444,7 @@ class GN:
         self.g, self.b, self.groups, self.eps, self.silu = gamma, beta, groups, eps, silu
         self.C = gamma.numel()
         self.sv = None
+        self.gg = self.gbt = None                     # fp32 gradient views (DenseStore) when the layer itself trains
 
     def fwd(self, x, batch: int, hw: int):
         y, stats = ops.groupnorm_fwd(x, self.g, self.b, batch, hw, self.C, self.groups, self.eps, self.silu)
@@ -364,6 +454,8 @@ class GN:
     def bwd(self, dy, dres=None):
         x, stats, batch, hw = self.sv
         self.sv = None
+        if self.gg is not None:
+            ops.norm_param_grad(dy, x, self.g, self.b, stats, self.gg, self.gbt, hw=hw, groups=self.groups, silu=self.silu)
         return ops.groupnorm_bwd(dy, x, self.g, self.b, stats, batch, hw, self.C, self.groups, self.silu, dres)
 
 
@@ -371,6 +463,7 @@ class LN:
     def __init__(self, gamma, beta):
         self.g, self.b = gamma, beta
         self.sv = None
+        self.gg = self.gbt = None
 
     def fwd(self, x):
         y, stats = ops.layernorm_fwd(x, self.g, self.b, 1e-5)
@@ -380,6 +473,8 @@ class LN:
     def bwd(self, dy, dres=None):
         x, stats = self.sv
         self.sv = None
+        if self.gg is not None:
+            ops.norm_param_grad(dy, x, None, None, stats, self.gg, self.gbt)
         return ops.layernorm_bwd(dy, x, self.g, stats, dres)
 
 
@@ -601,9 +696,13 @@ class Transformer2D:
 class Resnet:
     def __init__(self, norm1: GN, conv1: Conv3, tproj: Lin, norm2: GN, conv2: Conv3, shortcut: Optional[Lin]):
         self.norm1, self.conv1, self.tproj, self.norm2, self.conv2, self.shortcut = norm1, conv1, tproj, norm2, conv2, shortcut
+        # dense fine-tune: conv1.bias and time_emb_proj.bias are two parameters that enter the graph only as their sum
+        self.b_time = self.b_conv = self.g_time = self.g_conv = None
 
     def fwd(self, x, temb_act, N, H, W):
         hw = H * W
+        if self.b_time is not None:
+            self.tproj.b = ops.add(self.b_time, self.b_conv)
         tb = self.tproj.fwd(temb_act)                             # [N, Cout] = time_emb_proj(silu(emb)) + both biases
         h = self.conv1.fwd(self.norm1.fwd(x, N, hw), N, H, W, bias=tb, bias_rows=hw)
         sc = self.shortcut.fwd(x) if self.shortcut is not None else x
@@ -612,6 +711,10 @@ class Resnet:
     def bwd(self, dout, d_temb_act, N, H, W):
         dh1 = self.norm2.bwd(self.conv2.bwd(dout))
         self.tproj.bwd(ops.colsum(dh1, N, H * W, dh1.shape[1]), accum=d_temb_act)
+        if self.g_time is not None:                    # both biases see the gradient of their sum
+            self.g_time += self.tproj.gb
+            self.g_conv += self.tproj.gb
+            self.tproj.gb.zero_()
         dsc = self.shortcut.bwd(dout) if self.shortcut is not None else dout
         return self.norm1.bwd(self.conv1.bwd(dh1), dres=dsc)
 
@@ -622,12 +725,17 @@ class Resnet:
 class UNetB200:
     def __init__(self, arch: UNetArch, state_dict: Dict[str, torch.Tensor], lora_rank: int,
                  lora_alpha_multiplier: float = 1.0, device="cuda:0", ti_elems: int = 0, lora_seed: int = 0,
-                 batch_cross_kv: bool = True):
+                 batch_cross_kv: bool = True, dense: bool = False):
+        """dense=True: full-UNet fine-tune (main.py:143-148): every parameter trains, gradients land in ``self.dense``."""
         self.arch, self.device = arch, torch.device(device)
         sd = {k.replace("base_model.model.", "").replace(".base_layer.", "."): v for k, v in state_dict.items()}
         self._sd = sd
-        self.store = LoraStore(self.device, scaling=(lora_rank * lora_alpha_multiplier) / lora_rank)
+        self.store = LoraStore(self.device, scaling=(lora_rank * lora_alpha_multiplier) / max(lora_rank, 1))
         self.rank = lora_rank
+        self.dense: Optional[DenseStore] = DenseStore(self.device) if dense else None
+        self._convs: List[Conv3] = []
+        if dense:
+            batch_cross_kv = False            # every to_k / to_v keeps its own weight (and weight gradient)
         self.hooked: List[Attn] = []
         self._cross: Dict[str, Attn] = {}
         self.kv_groups: List[CrossKVBatch] = []
@@ -673,7 +781,7 @@ class UNetB200:
                                     a.transformer_layers_per_block[ri], True) for j in range(n)] if rev_attn[i] else None
             us = self._conv(f"{p}.upsamplers.0.conv") if i < len(boc) - 1 else None
             self.up.append((rs, at, us))
-        self.norm_out = GN(self._w("conv_norm_out.weight"), self._w("conv_norm_out.bias"), g, 1e-5, True)
+        self.norm_out = self._gn("conv_norm_out", 1e-5, True)
         self.conv_out = self._conv("conv_out")
         for width, paths in groups.items():
             names, ws = [], []
@@ -690,6 +798,8 @@ class UNetB200:
             self.kv_groups.append(grp)
         # the reference enumerates hooked processors down_blocks first, then up_blocks (ti_cross_attn_loss.py:95-110)
         self.store.finalize(extra=ti_elems)
+        if self.dense is not None:
+            self.dense.finalize()
         lora_keys = [k for k in sd if ".lora_A." in k]
         if lora_keys:
             self.store.load_peft(sd)
@@ -713,23 +823,54 @@ class UNetB200:
         if extra_bias is not None:
             b = (b.float() + extra_bias.float()).to(BF16) if b is not None else extra_bias
         lora = self.store.add(name, "linear", self.rank, W.shape[1], W.shape[0]) if self._is_target(name) else None
-        return Lin(W, b, lora)
+        lin = Lin(W, b, lora)
+        if self.dense is not None:
+            self.dense.add(lin, "W", "gW", f"{name}.weight", "mat", tuple(self._sd[f"{name}.weight"].shape))
+            if extra_bias is not None:                 # resnet time_emb_proj: its bias is registered by _resnet
+                lin.gb = torch.zeros(W.shape[0], dtype=torch.float32, device=self.device)
+            elif b is not None:
+                self.dense.add(lin, "b", "gb", f"{name}.bias", "vec")
+        return lin
+
+    def _gn(self, name: str, eps: float, silu: bool) -> GN:
+        gn = GN(self._w(f"{name}.weight"), self._w(f"{name}.bias"), self.arch.norm_num_groups, eps, silu)
+        if self.dense is not None:
+            self.dense.add(gn, "g", "gg", f"{name}.weight", "vec")
+            self.dense.add(gn, "b", "gbt", f"{name}.bias", "vec")
+        return gn
+
+    def _ln(self, name: str) -> LN:
+        ln = LN(self._w(f"{name}.weight"), self._w(f"{name}.bias"))
+        if self.dense is not None:
+            self.dense.add(ln, "g", "gg", f"{name}.weight", "vec")
+            self.dense.add(ln, "b", "gbt", f"{name}.bias", "vec")
+        return ln
 
     def _conv(self, name: str, stride: int = 1, need_dgrad: bool = True, use_bias: bool = True) -> Conv3:
         w = self._w(f"{name}.weight")
         b = self._w(f"{name}.bias") if use_bias else None
         lora = self.store.add(name, "conv", self.rank, w.shape[1], w.shape[0]) if self._is_target(name) else None
-        return Conv3(w, b, stride=stride, lora=lora, need_dgrad=need_dgrad)
+        conv = Conv3(w, b, stride=stride, lora=lora, need_dgrad=need_dgrad)
+        if self.dense is not None:
+            self.dense.add(conv, "wk", "gwk", f"{name}.weight", "conv", (conv.cout, conv.cin, conv.cin_p))
+            if b is not None:
+                self.dense.add(conv, "b", "gb", f"{name}.bias", "vec")
+            self._convs.append(conv)
+        return conv
 
     def _resnet(self, p: str) -> Resnet:
-        g = self.arch.norm_num_groups
-        n1 = GN(self._w(f"{p}.norm1.weight"), self._w(f"{p}.norm1.bias"), g, 1e-5, True)
-        n2 = GN(self._w(f"{p}.norm2.weight"), self._w(f"{p}.norm2.bias"), g, 1e-5, True)
+        n1 = self._gn(f"{p}.norm1", 1e-5, True)
+        n2 = self._gn(f"{p}.norm2", 1e-5, True)
         conv1 = self._conv(f"{p}.conv1", use_bias=False)
         tproj = self._lin(f"{p}.time_emb_proj", extra_bias=self._w(f"{p}.conv1.bias"))   # conv1 bias rides along
         conv2 = self._conv(f"{p}.conv2")
         sc = self._lin(f"{p}.conv_shortcut") if f"{p}.conv_shortcut.weight" in self._sd else None
-        return Resnet(n1, conv1, tproj, n2, conv2, sc)
+        res = Resnet(n1, conv1, tproj, n2, conv2, sc)
+        if self.dense is not None:
+            res.b_time, res.b_conv = self._w(f"{p}.time_emb_proj.bias"), self._w(f"{p}.conv1.bias")
+            self.dense.add(res, "b_time", "g_time", f"{p}.time_emb_proj.bias", "vec")
+            self.dense.add(res, "b_conv", "g_conv", f"{p}.conv1.bias", "vec")
+        return res
 
     def _attn(self, p: str, heads: int, cross: bool, hook: bool) -> Attn:
         at = Attn(heads, self._lin(f"{p}.to_q"), self._lin(f"{p}.to_k"), self._lin(f"{p}.to_v"),
@@ -741,15 +882,15 @@ class UNetB200:
         return at
 
     def _transformer(self, p: str, dim: int, heads: int, depth: int, hook: bool) -> Transformer2D:
-        norm = GN(self._w(f"{p}.norm.weight"), self._w(f"{p}.norm.bias"), self.arch.norm_num_groups, 1e-6, False)
+        norm = self._gn(f"{p}.norm", 1e-6, False)
         blocks = []
         for j in range(depth):
             b = f"{p}.transformer_blocks.{j}"
-            blocks.append(TBlock(LN(self._w(f"{b}.norm1.weight"), self._w(f"{b}.norm1.bias")),
+            blocks.append(TBlock(self._ln(f"{b}.norm1"),
                                  self._attn(f"{b}.attn1", heads, False, False),
-                                 LN(self._w(f"{b}.norm2.weight"), self._w(f"{b}.norm2.bias")),
+                                 self._ln(f"{b}.norm2"),
                                  self._attn(f"{b}.attn2", heads, True, hook),
-                                 LN(self._w(f"{b}.norm3.weight"), self._w(f"{b}.norm3.bias")),
+                                 self._ln(f"{b}.norm3"),
                                  self._lin(f"{b}.ff.net.0.proj"), self._lin(f"{b}.ff.net.2")))
         return Transformer2D(norm, self._lin(f"{p}.proj_in"), blocks, self._lin(f"{p}.proj_out"))
 
@@ -823,6 +964,8 @@ class UNetB200:
         d_temb_act = torch.zeros(B, a.time_embed_dim, dtype=BF16, device=dev)
         WGRAD.begin(os.environ.get("B200_WGRAD_STREAM", "0") == "1" and dev.type == "cuda")
         self.store.refresh_bt()                        # LoRA-B does not change between here and the optimizer
+        for conv in self._convs:                       # dense fine-tune: input-gradient tap copies follow the trained taps
+            conv.refresh_dgrad()
         # hooked layers were enumerated down_blocks..., up_blocks...; backward visits up (reversed) then down (reversed)
         n_down_hooks = sum(len(t.blocks) for rs, at, ds in self.down if at is not None for t in at)
         ds_down = list(dscores[:n_down_hooks]) if dscores is not None else None
@@ -870,6 +1013,8 @@ class UNetB200:
             da1 = ops.silu_bwd(self.add2.bwd(d_emb), a1)
             d_add_in = self.add1.bwd(da1)
             d_text = d_add_in[:, :a.projection_class_embeddings_input_dim - 6 * a.addition_time_embed_dim].contiguous()
+        if self.dense is not None:                   # the timestep MLP trains too: dW / db of linear_2 and linear_1
+            self.time1.bwd(ops.silu_bwd(self.time2.bwd(d_emb), e1), need_dx=False)
         self.time1.x = self.time2.x = None
         WGRAD.join()                                 # every dA / dB has landed in store.grads before the optimizer
         return d_ctx.view(B, Lctx, Dc), d_text

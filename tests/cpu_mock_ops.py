@@ -172,6 +172,22 @@ def layernorm_bwd(dy, x, gamma, stats, dres=None):
     return _bf(dx)
 
 
+def norm_param_grad(dy, x, gamma, beta, stats, dgamma, dbeta, hw=0, groups=0, silu=False):
+    rows, C_ = x.shape
+    g = (gamma.float() if gamma is not None else torch.ones(C_)).detach().clone().requires_grad_(True)
+    b = (beta.float() if beta is not None else torch.zeros(C_)).detach().clone().requires_grad_(True)
+    if groups:
+        batch = rows // hw
+        y = F.group_norm(x.float().view(batch, hw, C_).permute(0, 2, 1), groups, g, b, stats[0])
+        if silu:
+            y = F.silu(y)
+        y.backward(dy.float().view(batch, hw, C_).permute(0, 2, 1))
+    else:
+        F.layer_norm(x.float(), (C_,), g, b, 1e-5).backward(dy.float())
+    dgamma += g.grad
+    dbeta += b.grad
+
+
 def geglu_fwd(h):
     a, g = h.float().chunk(2, -1)
     return _bf(a * _bf(F.gelu(g)).float())

@@ -1,0 +1,108 @@
+"""CPU tests of the dense (full-UNet fine-tune, BASELINE config 5) backward's HOST logic: every UNet parameter's
+gradient - linear / conv weights and biases, GroupNorm / LayerNorm affine parameters, the separately trained conv1 /
+time_emb_proj biases, the timestep MLP - driven through tests/cpu_mock_ops.py and compared with the oracle's autograd
+(main.py:143-148: ``unet.requires_grad_(True)``, AdamW over ``unet.parameters()``)."""
+import pytest
+import torch
+
+from tests import cpu_mock_ops
+
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _setup(family, batch, hw, dt=BF):
+    from oracle.step import OracleTrainer, StepConfig, make_inputs
+    from sd_lora_trainer_b200.step import StepConfig as PCfg, TrainerB200
+    from oracle.text import build_text_encoders
+    cfg = StepConfig(family=family, tiny=True, resolution=hw * 8, is_lora=False, disable_ti=True, weight_dtype=dt)
+    orc = OracleTrainer(cfg, device="cpu")
+    g = torch.Generator().manual_seed(3)
+    for n, p in orc.unet.named_parameters():                  # non-trivial norm parameters
+        if "norm" in n:
+            p.data.add_((torch.randn(p.shape, generator=g) * 0.1).to(p.dtype))
+    inputs = make_inputs(cfg, batch=batch, latent_hw=hw, face_mask=True)
+    pcfg = PCfg(**{k: getattr(cfg, k) for k in PCfg.__dataclass_fields__ if hasattr(cfg, k)})
+    tes = build_text_encoders(cfg.family, cfg.tiny, seed=cfg.seed + 1)
+    tr = TrainerB200(pcfg, {k: v.to(BF) for k, v in orc.unet.state_dict().items()}, tes, device="cpu")
+    return cfg, orc, tr, inputs
+
+
+@pytest.mark.parametrize("family,batch,hw", [("sdxl", 2, 8), ("sd15", 1, 8)])
+def test_dense_step_matches_oracle(monkeypatch, family, batch, hw):
+    cpu_mock_ops.install(monkeypatch)
+    cfg, orc, tr, inputs = _setup(family, batch, hw)
+    assert tr.dense_mode and tr.store.n_lora == 0
+    # the flat buffer holds every parameter of the oracle UNet, under diffusers names and shapes
+    want = {k: tuple(v.shape) for k, v in orc.unet.state_dict().items()}
+    got = {k: tuple(v.shape) for k, v in tr.dense.export().items()}
+    assert got == want
+    assert tr.dense.numel_logical == sum(p.numel() for p in orc.unet.parameters())
+    before = tr.dense.export()
+    for k, v in orc.unet.state_dict().items():
+        assert torch.equal(before[k], v.to(BF)), k
+    out_o = orc.step(inputs, do_optimizer=False)
+    out_p = tr.step(inputs, do_optimizer=False)
+    for key in ("img_loss", "tot_loss"):
+        a, b = float(out_p[key]), float(out_o[key])
+        assert abs(a - b) / abs(b) <= 2e-3, f"{key}: ours {a} vs oracle {b}"
+    assert "token_attention_loss" not in out_p
+    grads = tr.dense.export(grads=True)
+    worst, n = (0.0, ""), 0
+    for name, p in orc.unet.named_parameters():
+        assert p.grad is not None, name
+        g = grads[name]
+        assert g.shape == p.grad.shape, name
+        e = rel(g, p.grad)
+        worst = max(worst, (e, name))
+        n += 1
+        # bf16-vs-bf16 backward noise (both sides round every op); the fp32-referenced bound is in the test below
+        assert e < 0.3 or float(p.grad.float().abs().max()) < 1e-6, (name, e)
+    assert n == len(want)
+    orc.optimizer_step()
+    tr.optimizer_step()
+    after = tr.dense.export()
+    moved = 0
+    for name, p in orc.unet.named_parameters():
+        d_o = p.detach().float() - before[name].float()
+        d_p = after[name].float() - before[name].float()
+        moved += int((d_o != 0).sum())
+        assert float((d_o - d_p).abs().max()) <= 2.5 * float(d_o.abs().max() + 1e-12), name
+    assert moved > 0 and float(tr.dense.grads.abs().max()) == 0.0
+
+
+def test_dense_gradients_against_fp32_autograd(monkeypatch):
+    """Same weights evaluated by the oracle in fp32: the executor's dense gradients must be as close to exact arithmetic as
+    the oracle's own bf16 backward is (x3 + floor), parameter by parameter."""
+    cpu_mock_ops.install(monkeypatch)
+    cfg, orc, tr, inputs = _setup("sdxl", 2, 8)
+    import dataclasses
+    from oracle.step import OracleTrainer
+    o32 = OracleTrainer(dataclasses.replace(cfg, weight_dtype=torch.float32), device="cpu")
+    o32.unet.load_state_dict({k: v.float() for k, v in orc.unet.state_dict().items()})
+    for t32, t16 in zip(o32.text_encoders, orc.text_encoders):
+        if t32 is not None:
+            t32.load_state_dict({k: v.float() for k, v in t16.state_dict().items()})
+    o32.step(inputs, do_optimizer=False)
+    orc.step(inputs, do_optimizer=False)
+    tr.step(inputs, do_optimizer=False)
+    grads = tr.dense.export(grads=True)
+    g32 = {n: p.grad for n, p in o32.unet.named_parameters()}
+    bad = []
+    for n, p in orc.unet.named_parameters():
+        e_ref, e_ours = rel(p.grad, g32[n]), rel(grads[n], g32[n])
+        if e_ours > 3.0 * e_ref + 2e-2:
+            bad.append((n, e_ours, e_ref))
+    assert not bad, bad[:8]
+
+
+def test_dense_mode_guards():
+    from sd_lora_trainer_b200.step import StepConfig, TrainerB200, lr_schedule
+    cfg = StepConfig(family="sd15", tiny=True, is_lora=False, disable_ti=False)
+    with pytest.raises(NotImplementedError):
+        TrainerB200(cfg, {}, (None, None), device="cpu")
+    assert lr_schedule(StepConfig(is_lora=False, disable_ti=True, unet_lr=1e-5), 0, 0.0)[1] == pytest.approx(1e-5)
