@@ -25,7 +25,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TRAIN_TFLOP_PER_IMAGE = {("sdxl", 16): 14.505, ("sdxl", 32): 14.676, ("sd15", 16): 1.761, ("sd15", 4): 1.742}
+TRAIN_TFLOP_PER_IMAGE = {("sdxl", 16): 14.505, ("sdxl", 32): 14.676, ("sd15", 16): 1.761, ("sd15", 4): 1.742,
+                         ("sdxl", "ft"): 20.284}
 
 
 def peaks():
@@ -109,14 +110,15 @@ def run_ours(args):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=torch.device(dev))
         pg = torch.distributed.group.WORLD
-    cfg = StepConfig(family=args.family, resolution=args.res, lora_rank=args.rank, disable_ti=False,
-                     max_train_steps=max(args.steps + args.warmup, 300))
+    cfg = StepConfig(family=args.family, resolution=args.res, lora_rank=args.rank, disable_ti=args.full_ft,
+                     is_lora=not args.full_ft, max_train_steps=max(args.steps + args.warmup, 300))
     sd = random_state_dict(cfg.arch(), seed=0, device=dev)
     tes = build_text_encoders(args.family, dev)
     tr = TrainerB200(cfg, sd, tes, device=dev, process_group=pg, use_cuda_graph=not args.no_graph)
     del sd
     B = args.batch
-    host_batches = [synthetic_inputs(args.family, B, args.res, cfg.n_tokens, seed=1000 + rank * 97 + i, face_mask=True,
+    host_batches = [synthetic_inputs(args.family, B, args.res, 0 if args.full_ft else cfg.n_tokens,
+                                     seed=1000 + rank * 97 + i, face_mask=True,
                                      vae_scaling_factor=cfg.arch().vae_scaling_factor, pin=True) for i in range(4)]
 
     def sync_all():
@@ -180,12 +182,13 @@ def run_ours(args):
         imgs = B * world * args.steps
         value = imgs / (ms / 1e3)
         e2e_value = imgs / (ms_e2e / 1e3)
-        tf_img = TRAIN_TFLOP_PER_IMAGE.get((args.family, args.rank))
+        tf_img = TRAIN_TFLOP_PER_IMAGE.get((args.family, "ft" if args.full_ft else args.rank))
         result = {
             "metric": "training images/sec", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.family.upper()} LoRA r={args.rank} face+TI(3 tokens) {args.res}x{args.res} "
+            "config": {"workload": (f"{args.family.upper()} full-UNet fine-tune (is_lora=false, disable_ti) " if args.full_ft else
+                                    f"{args.family.upper()} LoRA r={args.rank} face+TI(3 tokens) ") + f"{args.res}x{args.res} "
                                    f"bf16 batch {B}/GPU, fwd+bwd+AdamW, random-init full-size weights",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "working set (5 GB weights + ~25 GB activations per step) exceeds the 126 MB L2",
@@ -297,6 +300,8 @@ def main():
     ap.add_argument("--res", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--rank", type=int, default=16)
+    ap.add_argument("--full-ft", action="store_true",
+                    help="BASELINE config 5: full-UNet fine-tune (dense backward, AdamW over every parameter), disable_ti")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--profile-step", action="store_true",

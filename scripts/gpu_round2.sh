@@ -5,13 +5,17 @@
 #   gpurun --timeout 1500 -- bash scripts/gpu_round2.sh
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q --deselect tests/test_zvae_gpu.py --deselect tests/test_zclip_gpu.py \
+    --deselect tests/test_zdense_gpu.py \
     > gpurun_out/pytest_gpu.log 2>&1; echo "pytest (established) exit $?"; tail -3 gpurun_out/pytest_gpu.log
 timeout 400 python -m pytest tests/test_zclip_gpu.py -q -x > gpurun_out/pytest_zclip.log 2>&1; echo "pytest zclip exit $?"; tail -15 gpurun_out/pytest_zclip.log
 timeout 400 python -m pytest tests/test_zvae_gpu.py -q -x > gpurun_out/pytest_zvae.log 2>&1; echo "pytest zvae exit $?"; tail -15 gpurun_out/pytest_zvae.log
+timeout 400 python -m pytest tests/test_zdense_gpu.py -q -x > gpurun_out/pytest_zdense.log 2>&1; echo "pytest zdense exit $?"; tail -15 gpurun_out/pytest_zdense.log
 timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 echo "bench default exit $?"; cut -c1-300 gpurun_out/bench_default.json
 B200_NATIVE_CLIP=1 timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu --skip-roofline > gpurun_out/bench_native_clip.json 2> gpurun_out/bench_native_clip.err
 echo "bench native clip exit $?"; cut -c1-300 gpurun_out/bench_native_clip.json; tail -3 gpurun_out/bench_native_clip.err
+timeout 500 python bench.py --full-ft --batch 1 --steps 5 --warmup 3 --skip-cpu --no-graph > gpurun_out/bench_full_ft.json 2> gpurun_out/bench_full_ft.err
+echo "bench full-ft (BASELINE config 5) exit $?"; cut -c1-300 gpurun_out/bench_full_ft.json; tail -3 gpurun_out/bench_full_ft.err
 timeout 300 python scripts/time_vae.py > gpurun_out/vae_timing.txt 2>&1; cat gpurun_out/vae_timing.txt
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 3 -c 1 -o gpurun_out/gemm2_lora_full \
     python scripts/one_gemm.py 2048 1280 1280 lora > gpurun_out/ncu_full.log 2>&1
