@@ -8,9 +8,9 @@ offset noise, timesteps: main.py:311-324), gradient accumulation with the ``last
 cadence and the final-save rule (403-404, 466-469), the progress arithmetic (458-461).
 What changes: the body of the step is ONE call into ``TrainerB200`` (kernels behind the C ABI).
 What is not here (SURVEY.md 8 marks them out of scope): preprocessing / captioning, validation renders, debug plots,
-text-encoder LoRA, Prodigy / AdamW8bit, full fine-tuning.  The dataset arrives already cached (``CachedLatentDataset``,
-built from the VAE-encode prologue) and captions are turned into token ids by a caller-supplied ``tokenize`` (no CLIP
-vocabulary exists offline)."""
+text-encoder LoRA, Prodigy / AdamW8bit, full fine-tuning together with textual inversion.  The dataset arrives already
+cached (``CachedLatentDataset``, built from the VAE-encode prologue) and captions are turned into token ids by a
+caller-supplied ``tokenize`` (no CLIP vocabulary exists offline)."""
 from __future__ import annotations
 
 import json
@@ -109,7 +109,7 @@ class TrainingConfig:
             json.dump(self.dict(), f, indent=4)
 
     def step_config(self, family: str, tiny: bool = False) -> StepConfig:
-        return StepConfig(family=family, tiny=tiny, resolution=self.resolution, lora_rank=self.lora_rank,
+        return StepConfig(family=family, tiny=tiny, resolution=self.resolution, lora_rank=self.lora_rank, is_lora=self.is_lora,
                           lora_alpha_multiplier=self.lora_alpha_multiplier, lora_weight_decay=self.lora_weight_decay,
                           unet_lr=self.unet_lr, ti_lr=self.ti_lr, ti_weight_decay=self.ti_weight_decay,
                           disable_ti=self.disable_ti, n_tokens=self.n_tokens,
@@ -131,8 +131,8 @@ def seed_everything(seed: int):
 
 
 def _check_supported(config: TrainingConfig):
-    if not config.is_lora:
-        raise NotImplementedError("full-UNet fine-tuning is outside the B200 LoRA training step (DESIGN.md 7)")
+    if not config.is_lora and not config.disable_ti:
+        raise NotImplementedError("full-UNet fine-tuning runs with disable_ti=True here (BASELINE config 5, SURVEY.md 8d)")
     if config.unet_optimizer_type != "adamw":
         raise NotImplementedError(f"Invalid optimizer_name for the B200 unet path: {config.unet_optimizer_type}")
     if config.ti_optimizer != "adamw":
@@ -149,7 +149,8 @@ def _save(config: TrainingConfig, trainer: TrainerB200, handler: Optional[TokenE
     config.save_as_json(os.path.join(out_dir, "training_args.json"))
     save_checkpoint(output_dir=out_dir, global_step=global_step, unet=trainer.unet, embedding_handler=handler,
                     token_dict=config.token_dict, is_lora=config.is_lora,
-                    unet_lora_parameters=[trainer.store.params[:trainer.store.n_lora]], name=config.name,
+                    unet_lora_parameters=[trainer.store.params[:trainer.store.n_lora]] if config.is_lora else None,
+                    name=config.name,
                     pretrained_model_version=family, lora_alpha_multiplier=config.lora_alpha_multiplier)
 
 

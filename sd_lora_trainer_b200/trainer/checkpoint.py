@@ -7,6 +7,7 @@
   * ``special_params.json``                       - the token dictionary (checkpoint.py:163-168)
   * ``adapter_config.json``                       - what ``unet.save_pretrained`` of a PEFT model writes (:175)
   * ``{name}_{version}_lora.safetensors``         - the LoRA factors under kohya / WebUI keys (:84-102, 206-209)
+  * is_lora=False (:211-213): ``config.json`` + ``diffusion_pytorch_model.safetensors`` instead of the two LoRA files
 
 and deletes the intermediate ``pytorch_lora_weights.safetensors`` (:215-219), which is therefore never written here.
 
@@ -93,6 +94,21 @@ def adapter_config(rank: int, lora_alpha_multiplier: float, use_dora: bool = Fal
     }
 
 
+def unet_config_json(arch) -> dict:
+    """The architecture fields of diffusers' ``unet/config.json`` that the executor's graph description carries."""
+    attn = ["CrossAttnDownBlock2D" if a else "DownBlock2D" for a in arch.down_has_attn]
+    up = ["CrossAttnUpBlock2D" if a else "UpBlock2D" for a in reversed(arch.down_has_attn)]
+    return {"_class_name": "UNet2DConditionModel", "in_channels": arch.in_channels, "out_channels": arch.out_channels,
+            "block_out_channels": list(arch.block_out_channels), "down_block_types": attn, "up_block_types": up,
+            "layers_per_block": arch.layers_per_block,
+            "transformer_layers_per_block": list(arch.transformer_layers_per_block),
+            "attention_head_dim": list(arch.num_attention_heads), "cross_attention_dim": arch.cross_attention_dim,
+            "use_linear_projection": arch.use_linear_projection, "addition_embed_type": arch.addition_embed_type,
+            "addition_time_embed_dim": arch.addition_time_embed_dim if arch.addition_embed_type else None,
+            "projection_class_embeddings_input_dim": arch.projection_class_embeddings_input_dim if arch.addition_embed_type else None,
+            "norm_num_groups": arch.norm_num_groups}
+
+
 def save_checkpoint(output_dir: str, global_step: int, unet, embedding_handler, token_dict: dict, is_lora: bool,
                     unet_lora_parameters, pretrained_model_version: str, name: Optional[str] = None,
                     text_encoder_peft_models: Optional[list] = None, lora_alpha_multiplier: float = 1.0) -> None:
@@ -110,7 +126,14 @@ def save_checkpoint(output_dir: str, global_step: int, unet, embedding_handler, 
     with open(os.path.join(output_dir, "special_params.json"), "w") as f:
         json.dump(token_dict, f)
     if not is_lora:
-        raise NotImplementedError("full-UNet fine-tuning is outside the B200 LoRA training step (DESIGN.md 7)")
+        # checkpoint.py:211-213: ``unet.save_pretrained(output_dir)`` of a plain diffusers UNet = config.json +
+        # diffusion_pytorch_model.safetensors under diffusers parameter names
+        if getattr(unet, "dense", None) is None:
+            raise NotImplementedError("is_lora=False needs an executor built for full fine-tuning (UNetB200(dense=True))")
+        save_file(unet.dense.export(), os.path.join(output_dir, "diffusion_pytorch_model.safetensors"))
+        with open(os.path.join(output_dir, "config.json"), "w") as f:
+            json.dump(unet_config_json(unet.arch), f, indent=2, sort_keys=True)
+        return
     assert len(unet_lora_parameters) > 0, "Expected len(unet_lora_parameters) to be greater than zero if is_lora is True"
     with open(os.path.join(output_dir, "adapter_config.json"), "w") as f:
         json.dump(adapter_config(unet.rank, lora_alpha_multiplier), f, indent=2, sort_keys=True)

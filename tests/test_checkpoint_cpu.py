@@ -84,5 +84,29 @@ def test_save_checkpoint_rejects_what_the_step_does_not_train(tmp_path):
     unet = _trainer()
     with pytest.raises(ValueError):
         save_checkpoint(str(tmp_path), 0, unet, None, {}, True, [1], "sd21", name="x")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):           # is_lora=False on an executor that was not built for it
         save_checkpoint(str(tmp_path), 0, unet, None, {}, False, [1], "sdxl", name="x")
+
+
+def test_full_finetune_checkpoint_is_a_diffusers_unet_folder(tmp_path):
+    """checkpoint.py:211-213: ``unet.save_pretrained``: config.json + diffusion_pytorch_model.safetensors, diffusers names."""
+    import json
+    from safetensors.torch import load_file
+    from oracle.unet import UNet2DConditionModel, UNetConfig
+    from sd_lora_trainer_b200.arch import by_name
+    from sd_lora_trainer_b200.init import random_state_dict
+    from sd_lora_trainer_b200.trainer.checkpoint import save_checkpoint
+    from sd_lora_trainer_b200.unet import UNetB200
+    arch = by_name("tiny_sdxl")
+    sd0 = random_state_dict(arch, seed=0, device="cpu")
+    unet = UNetB200(arch, sd0, 0, device="cpu", dense=True)
+    save_checkpoint(str(tmp_path), 7, unet, None, {"TOK": "<s0>"}, False, None, "sdxl", name="ft run")
+    assert sorted(os.listdir(tmp_path)) == ["config.json", "diffusion_pytorch_model.safetensors", "special_params.json"]
+    sd = load_file(str(tmp_path / "diffusion_pytorch_model.safetensors"))
+    with torch.device("meta"):
+        ref = UNet2DConditionModel(UNetConfig.tiny_sdxl())
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    for k, v in sd0.items():
+        assert torch.equal(sd[k], v), k                    # native layouts (conv taps, padded channels) round-trip bit-exactly
+    cfg = json.load(open(tmp_path / "config.json"))
+    assert cfg["block_out_channels"] == [64, 128, 256] and cfg["down_block_types"][0] == "DownBlock2D"
