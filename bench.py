@@ -254,11 +254,12 @@ def cpu_baseline(args, steps: int, warmup: int):
     from oracle.step import OracleTrainer, StepConfig as OCfg, make_inputs
     torch.set_num_threads(os.cpu_count() or 1)
     dtype = torch.float32 if args.cpu_dtype == "fp32" else torch.bfloat16
-    cfg = OCfg(family=args.family, resolution=args.cpu_res, lora_rank=args.rank, weight_dtype=dtype)
+    cfg = OCfg(family=args.family, resolution=args.cpu_res, lora_rank=args.rank, weight_dtype=dtype,
+               is_lora=not args.full_ft, disable_ti=args.full_ft)
     t0 = time.time()
     orc = OracleTrainer(cfg, device="cpu")
     build_s = time.time() - t0
-    inp = make_inputs(cfg, batch=args.cpu_batch, face_mask=True, train_ids=orc.train_ids)
+    inp = make_inputs(cfg, batch=args.cpu_batch, face_mask=True, train_ids=orc.train_ids or None)
     for _ in range(warmup):
         orc.step(inp)
     t0 = time.time()
