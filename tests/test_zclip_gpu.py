@@ -29,9 +29,9 @@ def test_activation_kernels_match_torch(kind, n):
     ref.backward(dy.float())
     y, dx = ops.act_fwd(x, k), ops.act_bwd(dy, x, k)
     torch.cuda.synchronize()
-    # one bf16 rounding of an fp32 result: half an ulp (2^-9 relative) plus a small absolute floor
-    assert ((y.float() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-6).all()
-    assert ((dx.float() - xf.grad).abs() <= 2.0 ** -8 * xf.grad.abs() + 1e-6).all()
+    # one bf16 rounding of an fp32 result: half an ulp (<= 2^-8 relative) plus fp32 evaluation noise
+    assert ((y.float() - ref).abs() <= 1.01 * 2.0 ** -8 * ref.abs() + 2e-6).all()
+    assert ((dx.float() - xf.grad).abs() <= 1.01 * 2.0 ** -8 * xf.grad.abs() + 2e-6).all()
     # unaligned views take the scalar path
     if n > 8:
         y2 = ops.act_fwd(x[1:].clone()[1:].contiguous(), k)
