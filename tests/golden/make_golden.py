@@ -38,6 +38,35 @@ def make(family: str, rank: int, batch: int, hw: int):
     print(family, {k: v for k, v in fix.items() if isinstance(v, float)})
 
 
+def make_dense(family: str, batch: int, hw: int):
+    """Full-UNet fine-tune (is_lora=False, disable_ti=True; BASELINE config 5) on the tiny nets."""
+    torch.set_num_threads(4)
+    cfg = StepConfig(family=family, tiny=True, resolution=hw * 8, is_lora=False, disable_ti=True)
+    orc = OracleTrainer(cfg, device="cpu")
+    inputs = make_inputs(cfg, batch=batch, latent_hw=hw, face_mask=True)
+    out = orc.step(inputs, do_optimizer=False)
+    grads = {n: p.grad.float() for n, p in orc.unet.named_parameters()}
+    pick = sorted(grads)[::max(1, len(grads) // 12)][:12]
+    fix = {"family": family, "batch": batch, "hw": hw, "img_loss": float(out["img_loss"]), "tot_loss": float(out["tot_loss"]),
+           "model_pred": out["model_pred"].detach().float(), "n_params": len(grads),
+           "grad_norms": {n: float(grads[n].norm()) for n in pick},
+           "grad_sample": {n: grads[n].flatten()[:64].clone() for n in pick[:3]}}
+    torch.save(fix, os.path.join(HERE, f"dense_step_{family}_b{batch}.pt"))
+    print("dense", family, fix["img_loss"], fix["n_params"])
+
+
+def make_vae():
+    """AutoencoderKL.encode restatement (oracle/vae.py) on the tiny graph: image -> posterior parameters."""
+    from oracle.vae import VAEConfig, build_vae
+    torch.set_num_threads(4)
+    orc = build_vae(VAEConfig.tiny(), seed=3)
+    img = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(11)) * 2 - 1
+    torch.save({"image": img, "moments": orc.encode_moments(img)}, os.path.join(HERE, "vae_tiny_moments.pt"))
+    print("vae", float(orc.encode_moments(img).abs().mean()))
+
+
 if __name__ == "__main__":
     make("sdxl", 8, 2, 8)
     make("sd15", 4, 1, 8)
+    make_dense("sd15", 1, 8)
+    make_vae()

@@ -115,3 +115,27 @@ def test_timestep_embedding_layout():
     e = timestep_embedding(torch.tensor([0.0, 1.0]), 8)
     assert torch.allclose(e[0], torch.tensor([1.0, 1, 1, 1, 0, 0, 0, 0]))          # [cos | sin] (flip_sin_to_cos)
     assert abs(float(e[1, 0]) - math.cos(1.0)) < 1e-6 and abs(float(e[1, 4]) - math.sin(1.0)) < 1e-6
+
+
+def test_oracle_reproduces_golden_dense_step():
+    """Full-UNet fine-tune branch of the oracle (main.py:143-148) against its committed fixture."""
+    from oracle.step import OracleTrainer, StepConfig, make_inputs
+    fix = torch.load(os.path.join(GOLD, "dense_step_sd15_b1.pt"))
+    cfg = StepConfig(family=fix["family"], tiny=True, resolution=fix["hw"] * 8, is_lora=False, disable_ti=True)
+    orc = OracleTrainer(cfg, device="cpu")
+    out = orc.step(make_inputs(cfg, batch=fix["batch"], latent_hw=fix["hw"], face_mask=True), do_optimizer=False)
+    assert abs(float(out["img_loss"]) - fix["img_loss"]) / fix["img_loss"] < 2e-3
+    assert float(out["tot_loss"]) == float(out["img_loss"])                      # no L1 / TI terms without LoRA and TI
+    assert rel(out["model_pred"], fix["model_pred"]) < 2e-2
+    grads = {n: p.grad.float() for n, p in orc.unet.named_parameters()}
+    assert len(grads) == fix["n_params"] and all(p.requires_grad for p in orc.unet.parameters())
+    for n, v in fix["grad_norms"].items():
+        assert abs(float(grads[n].norm()) - v) / max(v, 1e-12) < 0.1, n
+
+
+def test_oracle_vae_reproduces_golden_moments():
+    from oracle.vae import VAEConfig, build_vae
+    fix = torch.load(os.path.join(GOLD, "vae_tiny_moments.pt"))
+    out = build_vae(VAEConfig.tiny(), seed=3).encode_moments(fix["image"])
+    assert out.shape == fix["moments"].shape == (2, 8, 8, 8)
+    assert rel(out, fix["moments"]) < 1e-5                                       # fp32; summation order only
