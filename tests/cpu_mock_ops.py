@@ -39,8 +39,51 @@ def _operand(m: Mat, b0: int, b1: int, mn_extent: int, k_extent: int) -> torch.T
     return out
 
 
+def _chk_tma(m: Mat, what: str):
+    """The constraints gemm_host.cu's tensor-map encoder enforces (encode_map_ex): bf16, 16-byte aligned base, every
+    stride a multiple of 16 bytes.  CPU allocations are 64-byte aligned, so the view's offset decides alignment here as
+    it does on the device."""
+    assert m.t.dtype == BF16, f"{what}: operand must be bf16"
+    assert (m.t.storage_offset() * 2) % 16 == 0, f"{what}: base not 16-byte aligned (offset {m.t.storage_offset()})"
+    for name, st in (("row", m.row_stride),) + ((("sb0", m.sb0), ("sb1", m.sb1)) if m.batched else ()):
+        st = st if st > 0 else 8
+        assert (st * 2) % 16 == 0, f"{what}: {name} stride {st} elements is not a multiple of 16 bytes"
+
+
+def _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out):
+    """Argument rules of b200_gemm (gemm_host.cu) that are not implied by the arithmetic."""
+    assert M >= 1 and N >= 1 and len(segs) in (1, 2) and nb0 >= 1 and nb1 >= 1 and splits >= 1
+    assert out.dtype in (torch.float32, BF16)
+    assert not atomic or out.dtype == torch.float32, "atomic accumulation needs an fp32 output"
+    conv = isinstance(segs[0][0], Conv3x3)
+    assert splits == 1 or (atomic and (len(segs) == 1 or group_out is not None) and not conv), "split-K rules"
+    for i, (a, b, k) in enumerate(segs):
+        assert k >= 1
+        if isinstance(a, Conv3x3):
+            assert i == 0 and conv_supported(a.H, a.W) and a.C % 8 == 0 and a.N * a.H * a.W == M, "conv geometry"
+            assert (a.t.storage_offset() * 2) % 16 == 0
+        else:
+            assert (a.rows >= k) if a.mn else (a.inner >= k), f"A[{i}] smaller than K"
+            _chk_tma(a, f"A[{i}]")
+            assert not a.batched or ((nb0 == 1 or a.sb0 > 0) and (nb1 == 1 or a.sb1 > 0)), "batched operand strides"
+        _chk_tma(b, f"B[{i}]")
+        assert not b.batched or ((nb0 == 1 or b.sb0 > 0) and (nb1 == 1 or b.sb1 > 0)), "batched operand strides"
+    kblocks0 = 9 * ((segs[0][0].C + 63) // 64) if conv else (segs[0][2] + 63) // 64
+    assert splits <= kblocks0, f"more splits ({splits}) than K blocks ({kblocks0})"
+    if side is not None:
+        s_mat, b2_mat, r, _, t_out = side
+        assert len(segs) == 1 and not conv and nb0 == 1 and nb1 == 1 and splits == 1 and 1 <= r <= 32, "side path rules"
+        _chk_tma(s_mat, "S")
+        _chk_tma(b2_mat, "B2")
+    if group_out is not None:
+        assert len(segs) == 2 and not conv and side is None and nb0 == 1 and nb1 == 1 and segs[0][2] == segs[1][2]
+        assert out.dtype == torch.float32 and atomic and group_out[0].dtype == torch.float32
+
+
 def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, bias_sb=0, residual=None,
          r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0, side=None, pair_mode=0, group_out=None, static_b=False):
+    _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out)
+    assert residual is None or residual.dtype == BF16
     if group_out is not None:                       # two independent problems sharing one launch
         out2, (sm2, sn2) = group_out
         gemm(out, M, N, [segs[0]], d_strides=d_strides, alpha=alpha, atomic=atomic)
@@ -125,6 +168,7 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale, dk=None, dv=None):
 
 
 def softmax_fwd(S, P, rows, cols, ld_s, ld_p):
+    assert cols >= 1 and ld_p >= cols and ld_s >= cols and S.dtype == torch.float32 and P.dtype == BF16
     s = _view(S, (rows, cols), (ld_s, 1))
     p = _view(P, (rows, ld_p), (ld_p, 1))
     p.zero_()
@@ -139,7 +183,16 @@ def softmax_bwd(P, dP, dS, rows, cols, ld_p, ld_dp):
     ds[:, :cols] = (p * (dp - (p * dp).sum(-1, keepdim=True))).to(BF16)
 
 
+def _chk_vec(*ts):
+    """Kernels that move 8 bf16 per thread (load8 / store8 / uint4) need 16-byte aligned, contiguous tensors."""
+    for t in ts:
+        if t is not None:
+            assert t.is_contiguous() and (t.storage_offset() * t.element_size()) % 16 == 0, "16-byte vector access"
+
+
 def groupnorm_fwd(x, gamma, beta, batch, hw, C_, groups, eps, silu):
+    assert C_ % 8 == 0 and C_ % groups == 0 and groups <= 64 and C_ // 8 <= 1024 and x.shape == (batch * hw, C_)
+    _chk_vec(x, gamma, beta)
     xr = x.float().view(batch, hw, C_).permute(0, 2, 1)
     y = F.group_norm(xr, groups, gamma.float(), beta.float(), eps)
     if silu:
@@ -160,6 +213,8 @@ def groupnorm_bwd(dy, x, gamma, beta, stats, batch, hw, C_, groups, silu, dres=N
 
 
 def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    assert x.shape[1] % 8 == 0 and x.shape[1] <= 2560
+    _chk_vec(x, gamma, beta)
     return _bf(F.layer_norm(x.float(), (x.shape[1],), gamma.float(), beta.float(), eps)), None
 
 
@@ -174,6 +229,10 @@ def layernorm_bwd(dy, x, gamma, stats, dres=None):
 
 def norm_param_grad(dy, x, gamma, beta, stats, dgamma, dbeta, hw=0, groups=0, silu=False):
     rows, C_ = x.shape
+    assert C_ % 8 == 0 and dgamma.dtype == torch.float32 and dbeta.dtype == torch.float32
+    assert not groups or (C_ % groups == 0 and hw >= 1 and rows % hw == 0)
+    assert not silu or (groups and gamma is not None and beta is not None)
+    _chk_vec(dy, x, gamma, beta)
     g = (gamma.float() if gamma is not None else torch.ones(C_)).detach().clone().requires_grad_(True)
     b = (beta.float() if beta is not None else torch.zeros(C_)).detach().clone().requires_grad_(True)
     if groups:
@@ -189,6 +248,8 @@ def norm_param_grad(dy, x, gamma, beta, stats, dgamma, dbeta, hw=0, groups=0, si
 
 
 def geglu_fwd(h):
+    assert (h.shape[1] // 2) % 8 == 0
+    _chk_vec(h)
     a, g = h.float().chunk(2, -1)
     return _bf(a * _bf(F.gelu(g)).float())
 
@@ -241,6 +302,8 @@ def add(a, b, c=None, out=None):
 
 
 def upsample2x_fwd(x, N, H, W, C_):
+    assert C_ % 8 == 0
+    _chk_vec(x)
     xn = x.float().view(N, H, W, C_).permute(0, 3, 1, 2)
     return _bf(F.interpolate(xn, scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).reshape(-1, C_))
 
@@ -250,6 +313,8 @@ def upsample2x_bwd(dy, N, H, W, C_):
 
 
 def im2col3x3(x, N, H, W, C_, stride):
+    assert C_ % 8 == 0 and stride in (1, 2) and x.numel() == N * H * W * C_
+    _chk_vec(x)
     xn = x.float().view(N, H, W, C_).permute(0, 3, 1, 2)
     unf = F.unfold(xn, 3, padding=1, stride=stride)
     L = unf.shape[-1]
@@ -275,6 +340,8 @@ def shift_stack9(U, N, H, W, r):
 
 
 def colsum(x, batch, hw, C_):
+    assert C_ % 8 == 0 and x.numel() == batch * hw * C_
+    _chk_vec(x)
     return _bf(x.float().view(batch, hw, C_).sum(1))
 
 
