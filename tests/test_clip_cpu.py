@@ -134,3 +134,42 @@ def test_step_with_native_text_matches_oracle(monkeypatch, family, rank, batch, 
         gref = te.text_model.embeddings.token_embedding.weight.grad[-cfg.n_tokens:]
         assert rel(tr.store.grads[off:off + rows.numel()].view_as(rows), gref) < 0.25
         off += rows.numel()
+
+
+def test_native_clip_full_size_sdxl(monkeypatch):
+    """CLIP-L (12 x 768, quick_gelu) + OpenCLIP bigG (32 x 1280, gelu, projection) at full size: descriptors pass the C
+    wrappers' rules (cpu_mock_ops enforces them) and the result tracks transformers' bf16 path."""
+    cpu_mock_ops.install(monkeypatch)
+    import copy
+    from oracle.text import build_text_encoders, encode_prompt, initialize_new_tokens
+    from sd_lora_trainer_b200.clip import TextStackB200
+    tes = build_text_encoders("sdxl", tiny=False, seed=1)
+    initialize_new_tokens(tes, 3, seed=1)
+    tes = [t.to(BF) for t in tes]
+    vocab = 49408
+    ids = torch.full((1, 77), 49407, dtype=torch.long)
+    seq = [49406, vocab, vocab + 1, vocab + 2, 320, 1125, 539, 49407]
+    ids[0, :len(seq)] = torch.tensor(seq)
+    ids = [ids, ids.clone()]
+    rows, frozen = [], []
+    for te in tes:
+        te.requires_grad_(False)
+        te.text_model.embeddings.token_embedding.weight.requires_grad_(True)
+        rows.append(te.text_model.embeddings.token_embedding.weight.data[-3:].clone())
+        t2 = copy.deepcopy(te)
+        emb = t2.text_model.embeddings.token_embedding
+        emb.weight = torch.nn.Parameter(emb.weight.data[:-3].clone(), requires_grad=False)
+        frozen.append(t2)
+    pe, pooled = encode_prompt(True, tes, ids)
+    g = torch.Generator().manual_seed(5)
+    d_pe, d_pool = (torch.randn(pe.shape, generator=g) * 0.1).to(BF), (torch.randn(pooled.shape, generator=g) * 0.1).to(BF)
+    torch.autograd.backward([pe, pooled], [d_pe, d_pool])
+    stack = TextStackB200(True, frozen, rows, "cpu")
+    assert len(stack.encs[0].blocks) == 11 and len(stack.encs[1].blocks) == 32       # encoder 1 skips its last layer
+    out_pe, out_pool = stack.encode_prompt(ids)
+    assert out_pe.shape == (1, 77, 2048) and out_pool.shape == (1, 1280)
+    assert rel(out_pe, pe) < 4e-2 and rel(out_pool, pooled) < 5e-2                   # bf16 vs bf16 over 32 layers
+    gb = [torch.zeros(3, r.shape[1]) for r in rows]
+    stack.backward(d_pe, d_pool, gb)
+    for te, g_ in zip(tes, gb):
+        assert rel(g_, te.text_model.embeddings.token_embedding.weight.grad[-3:]) < 6e-2

@@ -52,7 +52,7 @@ def test_oracle_downsample_is_bottom_right_padded():
     assert float(y[0, 0, 1, 1]) == float(x[0, 0, 2:4, 2:4].sum())            # bottom/right zero padding
 
 
-@pytest.mark.parametrize("B,H,W,full", [(2, 32, 32, False), (1, 16, 48, False), (1, 32, 32, True)])
+@pytest.mark.parametrize("B,H,W,full", [(2, 32, 32, False), (1, 16, 48, False), (1, 32, 32, True), (1, 256, 256, True)])
 def test_vae_encoder_host_logic_matches_oracle(monkeypatch, B, H, W, full):
     _install(monkeypatch)
     from oracle.vae import VAEConfig, build_vae, state_dict_of
