@@ -37,7 +37,7 @@ def _setup(family, rank, batch, hw, disable_ti=False):
     return cfg, orc, tr, inputs
 
 
-@pytest.mark.parametrize("family,rank,batch,hw", [("sdxl", 8, 2, 8), ("sd15", 4, 1, 8)])
+@pytest.mark.parametrize("family,rank,batch,hw", [("sdxl", 8, 2, 8), ("sd15", 4, 1, 8), ("sdxl", 32, 1, 8)])
 def test_step_host_logic_matches_oracle(monkeypatch, family, rank, batch, hw):
     cpu_mock_ops.install(monkeypatch)
     cfg, orc, tr, inputs = _setup(family, rank, batch, hw)
