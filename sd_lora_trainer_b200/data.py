@@ -4,7 +4,7 @@ main.py:294-324): fp32 VAE latents scaled by the VAE scaling factor, bf16 noise,
 and CLIP token ids with the trainable tokens at positions 1..n (no tokenizer vocabulary exists offline)."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 

@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 from .arch import UNetArch, by_name
-from .text import TIEmbedding, add_time_ids, encode_prompt, init_ti_rows, install_ti_rows
+from .text import add_time_ids, encode_prompt, init_ti_rows, install_ti_rows
 from .trainer.loss import (DistributionLoss, alphas_cumprod_table, compute_diffusion_loss,
                            token_attention_loss_tensors)
 from .unet import UNetB200

@@ -4,7 +4,7 @@ cache (dataset.py:141-179) is outside the step; this class 
 ``parameters`` tensor diffusers' ``DiagonalGaussianDistribution`` wraps ([1, 8, h, w]: mean | logvar) - as given."""
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 

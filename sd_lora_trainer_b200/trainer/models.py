@@ -8,7 +8,7 @@ tokenizers are outside the accelerated path and are returned as N
 from __future__ import annotations
 
 from types import SimpleNamespace
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 

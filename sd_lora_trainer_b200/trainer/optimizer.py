@@ -5,7 +5,7 @@ The reference builds torch.optim.AdamW objects over PEFT parameter lists and wri
 buffer updated by ONE fused kernel; the param_groups surface is kept so the caller's LR writes still work."""
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+from typing import Iterable, Optional
 
 import torch
 

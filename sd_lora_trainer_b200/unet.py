@@ -15,7 +15,6 @@ Parameter names follow diffusers / PEFT so reference checkpoints load unchanged.
 """
 from __future__ import annotations
 
-import math
 import os
 from typing import Dict, List, Optional, Tuple
 

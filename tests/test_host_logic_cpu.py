@@ -1,8 +1,6 @@
 """CPU tests of the executor's HOST logic: the product's forward/backward graph (operand descriptors, strides, skip and
 gradient plumbing, LoRA slot layout, optimizer wiring) driven through tests/cpu_mock_ops.py and compared with the
 oracle.  The CUDA kernels themselves are covered by the `-m gpu` tests."""
-import copy
-
 import pytest
 import torch
 

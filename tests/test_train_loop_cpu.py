@@ -39,7 +39,6 @@ def test_train_generator_contract(monkeypatch, tmp_path, family):
     from sd_lora_trainer_b200.arch import by_name
     from sd_lora_trainer_b200.init import random_state_dict
     from sd_lora_trainer_b200.main import TrainingConfig, train
-    from sd_lora_trainer_b200.trainer.checkpoint import load_lora_weights
     cfg = TrainingConfig(lora_training_urls="unit/test concept", concept_mode="face", sd_model_version=family, seed=1,
                          resolution=64, train_batch_size=2, max_train_steps=6, checkpointing_steps=2,
                          gradient_accumulation_steps=2, lora_rank=4, output_dir=str(tmp_path), device="cpu",
