@@ -331,6 +331,7 @@ extern "C" int b200_groupnorm_bwd(const void* dy, const void* x, const void* gam
     return 0;
 }
 
+namespace b200 {
 // ---------------------------------------------------------------------------------------------
 // Affine-parameter gradients of GroupNorm(+SiLU) / LayerNorm for the dense (full fine-tune) backward, BASELINE config 5:
 //   dgamma[c] += sum_rows dz * xhat      dbeta[c] += sum_rows dz,     dz = dy (* silu'(xhat*gamma+beta) when fused)
@@ -395,6 +396,7 @@ __global__ void norm_param_grad_kernel(const bf16* __restrict__ dy, const bf16* 
         else atomicAdd(dbeta + cv * 8 + (j - 8), sum);
     }
 }
+}  // namespace b200
 
 extern "C" int b200_norm_param_grad(const void* dy, const void* x, const void* gamma, const void* beta, const float* stats,
                                     float* dgamma, float* dbeta, int64_t rows, int64_t hw, int32_t C, int32_t groups,
