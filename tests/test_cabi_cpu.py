@@ -36,6 +36,13 @@ def test_errors_are_status_codes():
     assert lib.b200_gemm(ctypes.byref(d), None) != 0
     assert b"empty problem" in lib.b200_last_error()
     assert lib.b200_geglu_fwd(None, None, 4, 7, None) != 0          # inner % 8 != 0
+    assert lib.b200_act_fwd(None, None, 8, 0, None) != 0 and b"act_fwd" in lib.b200_last_error()          # null buffers
+    assert lib.b200_act_bwd(1, 1, 1, 8, 2, None) != 0 and b"kind 2" in lib.b200_last_error()              # unknown activation
+    assert lib.b200_norm_param_grad(1, 1, None, None, 1, 1, 1, 8, 4, 12, 0, 0, None) != 0                 # C % 8 != 0
+    assert lib.b200_norm_param_grad(1, 1, None, None, 1, 1, 1, 10, 4, 16, 4, 0, None) != 0                # rows % hw != 0
+    assert b"norm_param_grad" in lib.b200_last_error()
+    assert lib.b200_norm_param_grad(1, 1, None, None, 1, 1, 1, 8, 4, 16, 0, 1, None) != 0                 # SiLU without GroupNorm
+    assert lib.b200_latent_sample(None, None, None, 1.0, None, 0, None) != 0
     with pytest.raises(_lib.B200Error):
         _lib.check(2, "x")
 
