@@ -8,7 +8,7 @@ offset noise, timesteps: main.py:311-324), gradient accumulation with the ``last
 cadence and the final-save rule (403-404, 466-469), the progress arithmetic (458-461).
 What changes: the body of the step is ONE call into ``TrainerB200`` (kernels behind the C ABI).
 What is not here (SURVEY.md 8 marks them out of scope): preprocessing / captioning, validation renders, debug plots,
-text-encoder LoRA, Prodigy / AdamW8bit, full fine-tuning together with textual inversion.  The dataset arrives already
+text-encoder LoRA, Prodigy / AdamW8bit.  The dataset arrives already
 cached (``CachedLatentDataset``, built from the VAE-encode prologue) and captions are turned into token ids by a
 caller-supplied ``tokenize`` (no CLIP vocabulary exists offline)."""
 from __future__ import annotations
@@ -131,8 +131,6 @@ def seed_everything(seed: int):
 
 
 def _check_supported(config: TrainingConfig):
-    if not config.is_lora and not config.disable_ti:
-        raise NotImplementedError("full-UNet fine-tuning runs with disable_ti=True here (BASELINE config 5, SURVEY.md 8d)")
     if config.unet_optimizer_type != "adamw":
         raise NotImplementedError(f"Invalid optimizer_name for the B200 unet path: {config.unet_optimizer_type}")
     if config.ti_optimizer != "adamw":

@@ -92,8 +92,6 @@ class TrainerB200:
         ntok = 0 if cfg.disable_ti else cfg.n_tokens
         ti_elems = sum(ntok * d for d in dims)
         self.dense_mode = not cfg.is_lora
-        if self.dense_mode and ntok:
-            raise NotImplementedError("full-UNet fine-tuning runs with disable_ti=True here (BASELINE config 5, SURVEY.md 8d)")
         self.unet = UNetB200(cfg.arch(), unet_state_dict, 0 if self.dense_mode else cfg.lora_rank,
                              cfg.lora_alpha_multiplier, self.device, ti_elems=ti_elems, lora_seed=cfg.seed + 2,
                              dense=self.dense_mode)
@@ -271,19 +269,25 @@ class TrainerB200:
                              lr2=ti_lr or 0.0, wd2=self.cfg.ti_weight_decay, step=self.opt_step + 1, grad_scale=1.0)
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
 
-    def _train_state(self):
-        """(params, grads, m, v, n_first) of the buffer set the optimizer walks: the flat LoRA + TI buffers, or every UNet
-        parameter in dense (full fine-tune) mode."""
+    def _train_sets(self):
+        """The (params, grads, m, v, n_first) buffer sets the optimizer walks: the flat LoRA + TI buffers; in dense (full
+        fine-tune) mode every UNet parameter, plus the TI rows (the LoRA store then holds nothing else, n_first = 0)."""
+        sets = []
         if self.dense_mode:
             d = self.dense
-            return d.params, d.grads, d.m, d.v, d.params.numel()
-        return self.store.params, self.store.grads, self.store.m, self.store.v, self.store.n_lora
+            sets.append((d.params, d.grads, d.m, d.v, d.params.numel()))
+        if self.store.params.numel() > 0:
+            sets.append((self.store.params, self.store.grads, self.store.m, self.store.v, self.store.n_lora))
+        return sets
+
+    def _train_tensors(self):
+        return [t for st in self._train_sets() for t in st[:4]]
 
     def _optimizer_body(self, collective: bool = True):
-        p, g, m, v, n_first = self._train_state()
-        if collective and self.pg is not None and self.world > 1:
-            torch.distributed.all_reduce(g, group=self.pg)                    # the step's only collective
-        ops.adamw_dev(p, g, m, v, n_first, self._hyper_dev, zero_grad=True)
+        for p, g, m, v, n_first in self._train_sets():
+            if collective and self.pg is not None and self.world > 1:
+                torch.distributed.all_reduce(g, group=self.pg)                # the step's only collective (LoRA mode: one)
+            ops.adamw_dev(p, g, m, v, n_first, self._hyper_dev, zero_grad=True)
 
     def optimizer_step(self):
         self._set_hyper()
@@ -350,7 +354,7 @@ class TrainerB200:
         """Eager, instrumented pass over one step: every distinct tcgen05 GEMM signature is timed live (CUDA events
         around a graph of 10 launches of the very call, ops._profile_gemm) and weighted by its launch count.
         Training state is restored afterwards."""
-        snap = [t.clone() for t in self._train_state()[:4]]
+        snap = [t.clone() for t in self._train_tensors()]
         st = self._stage_inputs(inputs)
         ops.GEMM_PROFILE = {}
         try:
@@ -361,7 +365,7 @@ class TrainerB200:
             recs = ops.GEMM_PROFILE
         finally:
             ops.GEMM_PROFILE = None
-        for t, s_ in zip(self._train_state()[:4], snap):
+        for t, s_ in zip(self._train_tensors(), snap):
             t.copy_(s_)
         for rows in self.ti_rows:
             rows.grad = None
@@ -381,7 +385,7 @@ class TrainerB200:
     def _capture(self, st, ti_active: bool, opt_now: bool):
         """Warm up eagerly on a side stream, then capture.  The warm-up runs must not change training state, so the
         flat buffers are snapshotted and restored around them."""
-        snap = [t.clone() for t in self._train_state()[:4]]
+        snap = [t.clone() for t in self._train_tensors()]
 
         def run():
             out = self._body(st, ti_active)
@@ -398,7 +402,7 @@ class TrainerB200:
                 run()
                 self.launches_per_step = _lib.launch_count() - l0     # our kernels per step (graph replays them)
         torch.cuda.current_stream().wait_stream(side)
-        for t, s_ in zip(self._train_state()[:4], snap):
+        for t, s_ in zip(self._train_tensors(), snap):
             t.copy_(s_)
         for rows in self.ti_rows:
             rows.grad = None

@@ -15,20 +15,24 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-12))
 
 
-def _setup(family, batch, hw, dt=BF):
+def _setup(family, batch, hw, dt=BF, disable_ti=True):
     from oracle.step import OracleTrainer, StepConfig, make_inputs
     from sd_lora_trainer_b200.step import StepConfig as PCfg, TrainerB200
     from oracle.text import build_text_encoders
-    cfg = StepConfig(family=family, tiny=True, resolution=hw * 8, is_lora=False, disable_ti=True, weight_dtype=dt)
+    cfg = StepConfig(family=family, tiny=True, resolution=hw * 8, is_lora=False, disable_ti=disable_ti, weight_dtype=dt)
     orc = OracleTrainer(cfg, device="cpu")
     g = torch.Generator().manual_seed(3)
     for n, p in orc.unet.named_parameters():                  # non-trivial norm parameters
         if "norm" in n:
             p.data.add_((torch.randn(p.shape, generator=g) * 0.1).to(p.dtype))
-    inputs = make_inputs(cfg, batch=batch, latent_hw=hw, face_mask=True)
+    inputs = make_inputs(cfg, batch=batch, latent_hw=hw, face_mask=True, train_ids=orc.train_ids or None)
     pcfg = PCfg(**{k: getattr(cfg, k) for k in PCfg.__dataclass_fields__ if hasattr(cfg, k)})
     tes = build_text_encoders(cfg.family, cfg.tiny, seed=cfg.seed + 1)
-    tr = TrainerB200(pcfg, {k: v.to(BF) for k, v in orc.unet.state_dict().items()}, tes, device="cpu")
+    ti_init = None
+    if not disable_ti:
+        ti_init = [te.text_model.embeddings.token_embedding.weight.data[-cfg.n_tokens:].clone()
+                   for te in orc.text_encoders if te is not None]
+    tr = TrainerB200(pcfg, {k: v.to(BF) for k, v in orc.unet.state_dict().items()}, tes, device="cpu", ti_init=ti_init)
     return cfg, orc, tr, inputs
 
 
@@ -100,11 +104,39 @@ def test_dense_gradients_against_fp32_autograd(monkeypatch):
     assert not bad, bad[:8]
 
 
-def test_dense_mode_guards():
-    from sd_lora_trainer_b200.step import StepConfig, TrainerB200, lr_schedule
-    cfg = StepConfig(family="sd15", tiny=True, is_lora=False, disable_ti=False)
-    with pytest.raises(NotImplementedError):
-        TrainerB200(cfg, {}, (None, None), device="cpu")
+def test_dense_step_with_textual_inversion(monkeypatch):
+    """is_lora=False with the reference's default disable_ti=False: the UNet trains densely AND the token rows train
+    (score hook, token-attention and token-std regularisers, CLIP backward); two AdamW launches share one hyper block."""
+    cpu_mock_ops.install(monkeypatch)
+    cfg, orc, tr, inputs = _setup("sdxl", 2, 8, disable_ti=False)
+    assert tr.dense_mode and tr.store.n_lora == 0 and tr.store.params.numel() == 3 * (64 + 64)
+    out_o = orc.step(inputs, do_optimizer=False)
+    out_p = tr.step(inputs, do_optimizer=False)
+    for key in ("img_loss", "token_attention_loss", "token_std_loss", "tot_loss"):
+        a, b = float(out_p[key]), float(out_o[key])
+        assert abs(a - b) / abs(b) <= 2e-3, f"{key}: ours {a} vs oracle {b}"
+    grads = tr.dense.export(grads=True)
+    for name, p in orc.unet.named_parameters():
+        assert rel(grads[name], p.grad) < 0.3 or float(p.grad.float().abs().max()) < 1e-6, name
+    off = 0
+    for te, rows in zip([t for t in orc.text_encoders if t is not None], tr.ti_rows):
+        gref = te.text_model.embeddings.token_embedding.weight.grad[-cfg.n_tokens:]
+        assert rel(tr.store.grads[off:off + rows.numel()].view_as(rows), gref) < 0.25
+        off += rows.numel()
+    rows_before = [r.detach().clone() for r in tr.ti_rows]
+    w_before = tr.dense.params.clone()
+    orc.optimizer_step()
+    tr.optimizer_step()
+    assert not torch.equal(tr.dense.params, w_before) and all(not torch.equal(a, b) for a, b in zip(rows_before, tr.ti_rows))
+    for te, rows in zip([t for t in orc.text_encoders if t is not None], tr.ti_rows):
+        want = te.text_model.embeddings.token_embedding.weight.data[-cfg.n_tokens:]
+        # same AdamW step from nearly equal gradients: the updated rows agree to a fraction of the step size (lr = 1e-3)
+        assert float((rows.detach().float() - want.float()).abs().max()) <= 2.5e-3
+    assert float(tr.dense.grads.abs().max()) == 0.0 and float(tr.store.grads.abs().max()) == 0.0
+
+
+def test_dense_mode_lr_schedule():
+    from sd_lora_trainer_b200.step import StepConfig, lr_schedule
     assert lr_schedule(StepConfig(is_lora=False, disable_ti=True, unet_lr=1e-5), 0, 0.0)[1] == pytest.approx(1e-5)
 
 
