@@ -190,7 +190,10 @@ class TrainerB200:
         B, Cc, H, W = latent.shape
         offset = st["offset_noise"] if cfg.noise_offset > 0 else None
         token_ids = [st[f"token_ids_{i}"] for i in range(2 if self.sdxl else 1)]
-        need_text_grad = bool(self.ti_rows)
+        # Once the TI learning rate is frozen at 0 (main.py:273-274, completion_f > freeze_ti_after_completion_f, and it
+        # never rises again) the token rows cannot change: AdamW with lr = 0 is the identity on them.  The reference still
+        # back-propagates through both text encoders; here that backward is skipped - same parameters after the step.
+        need_text_grad = bool(self.ti_rows) and ti_active
         if self.text is not None:
             self.text.prepare(token_ids[0].shape[1])
             prompt_embeds, pooled = self.text.encode_prompt(token_ids, need_bwd=need_text_grad)
@@ -222,7 +225,7 @@ class TrainerB200:
             l1 = torch.zeros(1, dtype=torch.float32, device=dev)
             ops.abs_sum(self.store.params[:self.store.n_lora], l1)
             total = total + cfg.l1_penalty * l1 / self.store.numel_logical
-        d_ctx, d_text = self.unet.backward(dpred8, dscores)
+        d_ctx, d_text = self.unet.backward(dpred8, dscores, need_dctx=need_text_grad or self.text_encoders[0] is None)
         out["d_prompt_embeds"] = d_ctx
         if need_text_grad:
             roots, grads = [], []

@@ -577,9 +577,9 @@ class Attn:
         dx = self.to_q.bwd(dQ)
         if self.kv_batch is not None:
             pass                                       # dK / dV already sit in the group's buffer; handled at the end
-        elif self.cross:
-            self.to_k.bwd(dK, accum=d_ctx_accum)
-            self.to_v.bwd(dV, accum=d_ctx_accum)
+        elif self.cross:                               # d_ctx_accum is None: nobody needs d(prompt embedding)
+            self.to_k.bwd(dK, need_dx=d_ctx_accum is not None, accum=d_ctx_accum)
+            self.to_v.bwd(dV, need_dx=d_ctx_accum is not None, accum=d_ctx_accum)
         else:
             self.to_k.bwd(dK, accum=dx)
             self.to_v.bwd(dV, accum=dx)
@@ -630,7 +630,8 @@ class CrossKVBatch:
     def dkv(self, i: int):
         return self.sv[3][2 * i], self.sv[3][2 * i + 1]
 
-    def bwd(self, d_ctx: torch.Tensor):
+    def bwd(self, d_ctx: Optional[torch.Tensor]):
+        """d_ctx None: only the LoRA weight gradients are produced (the prompt embedding needs no gradient)."""
         ctx2, T, _, dKV = self.sv
         self.sv = None
         M, n, C, Kc = ctx2.shape[0], self.n, self.C, self.Kc
@@ -650,6 +651,8 @@ class CrossKVBatch:
             ops.gemm(gA_all, Kc, r, [(Mat(ctx2, M, Kc, Kc, mn=True), Mat(U, M, r, rs, mn=True, sb0=M * rs, batched=True), M)],
                      d_strides=(1, Kc, self.stride, 0), nb0=n, atomic=True)
             segs.append((Mat(U, M, r, rs, sb0=M * rs, batched=True), Mat(A_all, r, Kc, Kc, mn=True, sb0=self.stride, batched=True), r))
+        if d_ctx is None:
+            return
         dctx_all = torch.empty(n, M, Kc, dtype=BF16, device=dev)
         ops.gemm(dctx_all, M, Kc, segs, d_strides=(Kc, 1, M * Kc, 0), nb0=n)
         d_ctx.add_(dctx_all.sum(dim=0))               # plumbing: one reduction over the layer axis
@@ -952,14 +955,15 @@ class UNetB200:
         return pred, scores
 
     # ---- backward -------------------------------------------------------------------------------
-    def backward(self, dpred8: torch.Tensor, dscores: Optional[List[torch.Tensor]] = None):
+    def backward(self, dpred8: torch.Tensor, dscores: Optional[List[torch.Tensor]] = None, need_dctx: bool = True):
         """dpred8: [B*H*W, 8] bf16 (channels >= 4 zero).  LoRA gradients ACCUMULATE into store.grads.
-        Returns (d_ctx [B, Lctx, Dc], d_text_embeds [B, P] or None)."""
+        Returns (d_ctx [B, Lctx, Dc], d_text_embeds [B, P] or None); need_dctx=False (frozen text side) skips the
+        input gradients of the cross-attention K/V projections and returns d_ctx = None."""
         a = self.arch
         B, H, W, Lctx, Dc, e1, emb, a1, cat_splits = self._fw
         self._fw = None
         dev = dpred8.device
-        d_ctx = torch.zeros(B * Lctx, Dc, dtype=BF16, device=dev)
+        d_ctx = torch.zeros(B * Lctx, Dc, dtype=BF16, device=dev) if need_dctx else None
         d_temb_act = torch.zeros(B, a.time_embed_dim, dtype=BF16, device=dev)
         WGRAD.begin(os.environ.get("B200_WGRAD_STREAM", "0") == "1" and dev.type == "cuda")
         self.store.refresh_bt()                        # LoRA-B does not change between here and the optimizer
@@ -1016,4 +1020,4 @@ class UNetB200:
             self.time1.bwd(ops.silu_bwd(self.time2.bwd(d_emb), e1), need_dx=False)
         self.time1.x = self.time2.x = None
         WGRAD.join()                                 # every dA / dB has landed in store.grads before the optimizer
-        return d_ctx.view(B, Lctx, Dc), d_text
+        return (d_ctx.view(B, Lctx, Dc) if d_ctx is not None else None), d_text

@@ -128,3 +128,33 @@ def test_param_shapes_match_oracle_state_dict(name):
     want = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
     got = dict(param_shapes(by_name(name)))
     assert got == want
+
+
+def test_frozen_ti_phase_skips_text_backward_without_changing_the_step(monkeypatch):
+    """completion_f > freeze_ti_after_completion_f: ti_lr = 0 (main.py:273-274).  The product skips the CLIP backward;
+    losses, LoRA gradients and the post-step parameters (LoRA factors AND token rows) still match the oracle, which
+    back-propagates into the embedding tables and applies AdamW with lr = 0."""
+    cpu_mock_ops.install(monkeypatch)
+    cfg, orc, tr, inputs = _setup("sdxl", 8, 2, 8)
+    rows_before = [r.detach().clone() for r in tr.ti_rows]
+    tabs_before = [te.text_model.embeddings.token_embedding.weight.data[-cfg.n_tokens:].clone()
+                   for te in orc.text_encoders if te is not None]
+    p_before = tr.store.export_peft()
+    out_o = orc.step(inputs, completion_f=0.9, do_optimizer=False)
+    out_p = tr.step(inputs, completion_f=0.9, do_optimizer=False)
+    assert "token_std_loss" not in out_o and "token_std_loss" not in out_p           # regulariser is off with ti_lr = 0
+    for key in ("img_loss", "token_attention_loss", "tot_loss"):
+        a, b = float(out_p[key]), float(out_o[key])
+        assert abs(a - b) / abs(b) <= 2e-3, f"{key}: ours {a} vs oracle {b}"
+    assert float(tr.store.grads[tr.store.n_lora:].abs().max()) == 0.0               # no TI gradient was produced
+    ours = tr.store.export_peft(grads=True)
+    for n, p in orc.unet.named_parameters():
+        if p.grad is not None:
+            assert rel(ours[n].reshape(p.grad.shape), p.grad) < 0.25, n
+    orc.optimizer_step()
+    tr.optimizer_step()
+    for r0, r1, t0, te in zip(rows_before, tr.ti_rows, tabs_before, [t for t in orc.text_encoders if t is not None]):
+        assert torch.equal(r0, r1.detach())                                          # ours: untouched
+        assert torch.equal(t0, te.text_model.embeddings.token_embedding.weight.data[-cfg.n_tokens:])   # oracle: lr = 0
+    after = tr.store.export_peft()
+    assert any(not torch.equal(after[k], p_before[k]) for k in after)               # the LoRA factors did move
