@@ -231,6 +231,20 @@ int b200_adamw_pack_hyper(double lr, double wd, double l1_coeff, double lr2, dou
 int b200_adamw_dev(void* p, float* grad, void* m, void* v, int64_t n, int64_t n_first, const float* hyper_dev12,
                    int32_t zero_grad, void* stream);
 
+/* Prodigy ([3P] prodigyopt==1.0 as trainer/optimizer.py:22-34 (UNet) and 134-144 (textual inversion) configure it:
+   decouple=True, use_bias_correction=True, safeguard_warmup=True, betas=(0.9, 0.99)) over n bf16 parameters with the
+   fp32 flat gradient buffer; state s / p0 / exp_avg / exp_avg_sq are bf16 like the parameters (p0 = the parameters at
+   construction, the others zero).  scal8: 8 device doubles, initialised {d0, d0, 0, 0, 0, 0, 0, d0}: [0] d, [1] d_max,
+   [2] d_numerator, [3..4] the step's global sums, [5] dlr, [6] skip flag, [7] d_hat.  hyper_dev12: device copy of what
+   b200_prodigy_pack_hyper packs on the host (k = optimizer steps taken so far; lr = the value main.py:286-291 writes
+   into param_groups[0]['lr'] for the UNet, 1.0 for textual inversion).  Three launches: state update + global sums,
+   the scalar d update (one thread, double), the parameter update.  Gradients are zeroed when zero_grad != 0. */
+int b200_prodigy_pack_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, double d_coef,
+                            double growth_rate, double d0, int32_t k, int32_t use_bias_correction, double l1_coeff,
+                            double grad_scale, float* out_host12);
+int b200_prodigy_step(void* p, float* grad, void* s, const void* p0, void* exp_avg, void* exp_avg_sq, int64_t n,
+                      double* scal8, const float* hyper_dev12, int32_t zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

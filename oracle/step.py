@@ -42,6 +42,10 @@ class StepConfig:
     max_train_steps: int = 300
     unet_lr_warmup_steps: Optional[int] = None
     freeze_ti_after_completion_f: float = 0.7
+    unet_optimizer_type: str = "adamw"
+    ti_optimizer: str = "adamw"
+    prodigy_d_coef: float = 1.0
+    unet_prodigy_growth_factor: float = 1.05
     weight_dtype: torch.dtype = torch.bfloat16
     seed: int = 0
 
@@ -96,9 +100,15 @@ class OracleTrainer:
                 self.std_regs[f"txt_encoder_{i}"] = DistributionLossOracle(w.data)   # loss.py:179-194
                 w.requires_grad_(True)                                    # optimizer.py:116-121
                 self.ti_params.append(w)
-            self.opt_ti = torch.optim.AdamW(
-                [{"params": self.ti_params, "lr": cfg.ti_lr, "weight_decay": cfg.ti_weight_decay}],
-                weight_decay=cfg.ti_weight_decay)                         # optimizer.py:144-148
+            if cfg.ti_optimizer == "prodigy":                             # optimizer.py:134-144
+                from .prodigy import Prodigy
+                self.opt_ti = Prodigy([{"params": self.ti_params, "lr": 1.0, "weight_decay": cfg.ti_weight_decay}],
+                                      d_coef=1.0, lr=1.0, decouple=True, use_bias_correction=True, safeguard_warmup=True,
+                                      weight_decay=cfg.ti_weight_decay, betas=(0.9, 0.99))
+            else:
+                self.opt_ti = torch.optim.AdamW(
+                    [{"params": self.ti_params, "lr": cfg.ti_lr, "weight_decay": cfg.ti_weight_decay}],
+                    weight_decay=cfg.ti_weight_decay)                     # optimizer.py:144-148
         else:
             self.opt_ti = None
         if cfg.is_lora:
@@ -112,9 +122,16 @@ class OracleTrainer:
             self.unet.requires_grad_(True)
             self.lora_params = []                                         # unet_lora_parameters = None: no L1 penalty
             trainable = list(self.unet.parameters())
-        self.opt_unet = torch.optim.AdamW(
-            [{"params": trainable, "weight_decay": cfg.lora_weight_decay}],
-            lr=1e-4, weight_decay=cfg.lora_weight_decay)                  # optimizer.py:16-17
+        if cfg.unet_optimizer_type == "prodigy":                          # optimizer.py:22-34
+            from .prodigy import Prodigy
+            self.opt_unet = Prodigy([{"params": trainable, "weight_decay": cfg.lora_weight_decay}], d_coef=cfg.prodigy_d_coef,
+                                    lr=1.0, decouple=True, use_bias_correction=True, safeguard_warmup=True,
+                                    weight_decay=cfg.lora_weight_decay, betas=(0.9, 0.99),
+                                    growth_rate=cfg.unet_prodigy_growth_factor)
+        else:
+            self.opt_unet = torch.optim.AdamW(
+                [{"params": trainable, "weight_decay": cfg.lora_weight_decay}],
+                lr=1e-4, weight_decay=cfg.lora_weight_decay)              # optimizer.py:16-17
         self.global_step = 0
         self._accum = 0
 
@@ -162,7 +179,7 @@ class OracleTrainer:
 
     def set_lrs(self, completion_f: float):
         ti_lr, unet_lr = lr_schedule(self.cfg, self.global_step, completion_f)
-        if self.opt_ti is not None:
+        if self.opt_ti is not None and self.cfg.ti_optimizer != "prodigy":        # main.py:269
             self.opt_ti.param_groups[0]["lr"] = ti_lr
         self.opt_unet.param_groups[0]["lr"] = unet_lr
 

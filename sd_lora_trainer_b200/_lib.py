@@ -79,6 +79,10 @@ SIGNATURES = {
     "b200_adamw_pack_hyper": [c_double, c_double, c_double, c_double, c_double, c_double, c_double, c_double, c_int32,
                               c_double, c_void_p],
     "b200_adamw_dev": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p],
+    "b200_prodigy_pack_hyper": [c_double, c_double, c_double, c_double, c_double, c_double, c_double, c_double, c_int32,
+                                c_int32, c_double, c_double, c_void_p],
+    "b200_prodigy_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32,
+                          c_void_p],
 }
 _RESTYPES = {"b200_last_error": C.c_char_p, "b200_launch_count": C.c_longlong}
 

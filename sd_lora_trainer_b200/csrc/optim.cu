@@ -174,6 +174,113 @@ static AdamHyper make_hyper(double lr, double wd, double l1_coeff, double lr2, d
     return h;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Prodigy (prodigyopt 1.0 as trainer/optimizer.py:22-34, 134-144 configures it: decouple, use_bias_correction,
+// safeguard_warmup) on bf16 parameters with bf16 state and the flat fp32 gradient buffer.  Three launches per step:
+//   accumulate: exp_avg / exp_avg_sq / s updates (op-for-op bf16 rounding) + the two global sums <g, p0 - p>, |s|_1
+//   update_d  : one thread folds the sums into d_numerator, forms d_hat and advances d (double, like the Python code)
+//   apply     : p -= decay*dlr*p ; p -= dlr * exp_avg / (sqrt(exp_avg_sq) + d*eps)
+// scal (device doubles): [0] d  [1] d_max  [2] d_numerator  [3] sum|s|  [4] sum<g,p0-p>  [5] dlr of this step
+//                        [6] skip flag (d_denom == 0: the package returns before touching anything)  [7] d_hat
+// ---------------------------------------------------------------------------------------------------------
+struct ProdigyHyper {   // 12 floats, device resident (refreshed by a 48-byte copy per step)
+    float lr, beta1, beta2, beta3, eps, decay, d_coef, growth, d0, bias_corr, l1, grad_scale;
+};
+
+__global__ void prodigy_accumulate_kernel(const bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ s,
+                                          const bf16* __restrict__ p0, bf16* __restrict__ m, bf16* __restrict__ v,
+                                          long long n, double* __restrict__ scal, const ProdigyHyper* __restrict__ h_dev,
+                                          int zero_grad) {
+    pdl_launch();
+    pdl_wait();
+    __shared__ float red[32];
+    const ProdigyHyper h = *h_dev;
+    const double d = scal[0];
+    const bool live = h.lr > 0.f;
+    const float a_m = static_cast<float>(d * (1.0 - static_cast<double>(h.beta1)));
+    const float a_v = static_cast<float>(d * d * (1.0 - static_cast<double>(h.beta2)));
+    const float a_s = static_cast<float>((d / static_cast<double>(h.d0)) * d);
+    float dot = 0.f, den = 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float pv = __bfloat162float(p[i]);
+        float g = bfr(grad[i] * h.grad_scale);
+        if (h.l1 != 0.f) g = bfr(g + h.l1 * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f)));
+        if (zero_grad) grad[i] = 0.f;
+        if (!live) continue;
+        dot += g * bfr(__bfloat162float(p0[i]) - pv);
+        float mv = bfr(__bfloat162float(m[i]) * h.beta1);
+        mv = bfr(mv + a_m * g);
+        float vv = bfr(__bfloat162float(v[i]) * h.beta2);
+        vv = bfr(vv + a_v * (g * g));
+        float sv = bfr(__bfloat162float(s[i]) * h.beta3);
+        sv = bfr(sv + a_s * g);
+        den += fabsf(sv);
+        m[i] = __float2bfloat16_rn(mv);
+        v[i] = __float2bfloat16_rn(vv);
+        s[i] = __float2bfloat16_rn(sv);
+    }
+    dot = block_sum(dot, red);
+    __syncthreads();
+    den = block_sum(den, red);
+    if (threadIdx.x == 0 && live) {
+        atomicAdd(scal + 4, static_cast<double>(dot));
+        atomicAdd(scal + 3, static_cast<double>(den));
+    }
+}
+
+__global__ void prodigy_update_d_kernel(double* __restrict__ scal, const ProdigyHyper* __restrict__ h_dev) {
+    pdl_launch();
+    pdl_wait();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const ProdigyHyper h = *h_dev;
+    double d = scal[0], d_max = scal[1];
+    const double d0 = static_cast<double>(h.d0), den = scal[3];
+    const double dlr = d * static_cast<double>(h.lr) * static_cast<double>(h.bias_corr);
+    double num = scal[2] * static_cast<double>(h.beta3);
+    if (h.lr > 0.f) num += (d / d0) * dlr * scal[4];
+    scal[5] = dlr;
+    if (den == 0.0) {
+        scal[6] = 1.0;                      // nothing is written back, nothing is applied
+    } else {
+        double d_hat = d;
+        if (h.lr > 0.f) {
+            d_hat = static_cast<double>(h.d_coef) * num / den;
+            if (d == d0) d = fmax(d, d_hat);
+            d_max = fmax(d_max, d_hat);
+            d = fmin(d_max, d * static_cast<double>(h.growth));
+        }
+        scal[0] = d;
+        scal[1] = d_max;
+        scal[2] = num;
+        scal[6] = 0.0;
+        scal[7] = d_hat;
+    }
+    scal[3] = 0.0;
+    scal[4] = 0.0;
+}
+
+__global__ void prodigy_apply_kernel(bf16* __restrict__ p, const bf16* __restrict__ m, const bf16* __restrict__ v, long long n,
+                                     const double* __restrict__ scal, const ProdigyHyper* __restrict__ h_dev) {
+    pdl_launch();
+    pdl_wait();
+    if (scal[6] != 0.0) return;
+    const ProdigyHyper h = *h_dev;
+    const float dlr = static_cast<float>(scal[5]);
+    const float eps_d = static_cast<float>(scal[0] * static_cast<double>(h.eps));
+    const float dec = static_cast<float>(-static_cast<double>(h.decay) * scal[5]);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float denom = bfr(sqrtf(__bfloat162float(v[i])));
+        denom = bfr(denom + eps_d);
+        float pv = __bfloat162float(p[i]);
+        if (h.decay != 0.f) pv = bfr(pv + dec * pv);
+        pv = bfr(pv - dlr * (__bfloat162float(m[i]) / denom));
+        p[i] = __float2bfloat16_rn(pv);
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -254,5 +361,45 @@ extern "C" int b200_adamw_dev(void* p, float* grad, void* m, void* v, int64_t n,
                                                    static_cast<bf16*>(v), n, n_first, h,
                                                    reinterpret_cast<const AdamHyper*>(hyper_dev12), zero_grad);
     B200_CHECK_LAUNCH("adamw_dev");
+    return 0;
+}
+
+extern "C" int b200_prodigy_pack_hyper(double lr, double beta1, double beta2, double eps, double weight_decay, double d_coef,
+                                       double growth_rate, double d0, int32_t k, int32_t use_bias_correction, double l1_coeff,
+                                       double grad_scale, float* out_host12) {
+    B200_CHECK_ARG(k >= 0 && out_host12 != nullptr && d0 > 0.0, "prodigy_pack_hyper: bad arguments");
+    ProdigyHyper h;
+    const double bc = use_bias_correction ? sqrt(1.0 - pow(beta2, k + 1.0)) / (1.0 - pow(beta1, k + 1.0)) : 1.0;
+    h.lr = static_cast<float>(lr);
+    h.beta1 = static_cast<float>(beta1);
+    h.beta2 = static_cast<float>(beta2);
+    h.beta3 = static_cast<float>(sqrt(beta2));
+    h.eps = static_cast<float>(eps);
+    h.decay = static_cast<float>(weight_decay);
+    h.d_coef = static_cast<float>(d_coef);
+    h.growth = static_cast<float>(growth_rate);     // inf stays inf
+    h.d0 = static_cast<float>(d0);
+    h.bias_corr = static_cast<float>(bc);
+    h.l1 = static_cast<float>(l1_coeff);
+    h.grad_scale = static_cast<float>(grad_scale);
+    static_assert(sizeof(ProdigyHyper) == 12 * sizeof(float), "ProdigyHyper layout");
+    memcpy(out_host12, &h, sizeof(h));
+    return 0;
+}
+
+extern "C" int b200_prodigy_step(void* p, float* grad, void* s, const void* p0, void* exp_avg, void* exp_avg_sq, int64_t n,
+                                 double* scal8, const float* hyper_dev12, int32_t zero_grad, void* stream) {
+    B200_CHECK_ARG(n >= 1 && p && grad && s && p0 && exp_avg && exp_avg_sq && scal8 && hyper_dev12, "prodigy_step: bad arguments");
+    const ProdigyHyper* hd = reinterpret_cast<const ProdigyHyper*>(hyper_dev12);
+    launch_pdl(prodigy_accumulate_kernel, dim3(grid_for(n, 256, kNumSMs * 8)), dim3(256), 0, ST, static_cast<const bf16*>(p), grad,
+               static_cast<bf16*>(s), static_cast<const bf16*>(p0), static_cast<bf16*>(exp_avg), static_cast<bf16*>(exp_avg_sq),
+               static_cast<long long>(n), scal8, hd, static_cast<int>(zero_grad));
+    B200_CHECK_LAUNCH("prodigy_accumulate");
+    launch_pdl(prodigy_update_d_kernel, dim3(1), dim3(32), 0, ST, scal8, hd);
+    B200_CHECK_LAUNCH("prodigy_update_d");
+    launch_pdl(prodigy_apply_kernel, dim3(grid_for(n, 256, kNumSMs * 8)), dim3(256), 0, ST, static_cast<bf16*>(p),
+               static_cast<const bf16*>(exp_avg), static_cast<const bf16*>(exp_avg_sq), static_cast<long long>(n),
+               static_cast<const double*>(scal8), hd);
+    B200_CHECK_LAUNCH("prodigy_apply");
     return 0;
 }

@@ -8,7 +8,7 @@ offset noise, timesteps: main.py:311-324), gradient accumulation with the ``last
 cadence and the final-save rule (403-404, 466-469), the progress arithmetic (458-461).
 What changes: the body of the step is ONE call into ``TrainerB200`` (kernels behind the C ABI).
 What is not here (SURVEY.md 8 marks them out of scope): preprocessing / captioning, validation renders, debug plots,
-text-encoder LoRA, Prodigy / AdamW8bit.  The dataset arrives already
+text-encoder LoRA, AdamW8bit.  The dataset arrives already
 cached (``CachedLatentDataset``, built from the VAE-encode prologue) and captions are turned into token ids by a
 caller-supplied ``tokenize`` (no CLIP vocabulary exists offline)."""
 from __future__ import annotations
@@ -49,6 +49,8 @@ class TrainingConfig:
     unet_optimizer_type: str = "adamw"
     unet_lr_warmup_steps: Optional[int] = None
     unet_lr: float = 0.0003
+    prodigy_d_coef: float = 1.0
+    unet_prodigy_growth_factor: float = 1.05
     lora_weight_decay: float = 0.004
     ti_lr: float = 0.001
     ti_weight_decay: float = 0.0
@@ -118,7 +120,10 @@ class TrainingConfig:
                           gradient_accumulation_steps=self.gradient_accumulation_steps,
                           max_train_steps=self.max_train_steps, unet_lr_warmup_steps=self.unet_lr_warmup_steps,
                           freeze_ti_after_completion_f=self.freeze_ti_after_completion_f,
-                          freeze_unet_before_completion_f=self.freeze_unet_before_completion_f, seed=self.seed)
+                          freeze_unet_before_completion_f=self.freeze_unet_before_completion_f,
+                          unet_optimizer_type=self.unet_optimizer_type, ti_optimizer=self.ti_optimizer,
+                          prodigy_d_coef=self.prodigy_d_coef, unet_prodigy_growth_factor=self.unet_prodigy_growth_factor,
+                          seed=self.seed)
 
 
 def seed_everything(seed: int):
@@ -131,9 +136,9 @@ def seed_everything(seed: int):
 
 
 def _check_supported(config: TrainingConfig):
-    if config.unet_optimizer_type != "adamw":
-        raise NotImplementedError(f"Invalid optimizer_name for the B200 unet path: {config.unet_optimizer_type}")
-    if config.ti_optimizer != "adamw":
+    if config.unet_optimizer_type not in ("adamw", "prodigy"):
+        raise NotImplementedError(f"Invalid optimizer_name for unet: {config.unet_optimizer_type}")
+    if config.ti_optimizer not in ("adamw", "prodigy"):
         raise NotImplementedError(f"Invalid optimizer_name: '{config.ti_optimizer}'")
     if config.text_encoder_lora_optimizer is not None:
         raise NotImplementedError("text-encoder LoRA is outside the accelerated path (SURVEY.md 2, row 3)")

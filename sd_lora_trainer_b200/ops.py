@@ -450,3 +450,28 @@ def adamw_dev(p, grad, m, v, n_first: int, hyper_dev: torch.Tensor, zero_grad: b
     assert hyper_dev.is_cuda and hyper_dev.dtype == torch.float32 and hyper_dev.numel() == 12
     check(_lib.load().b200_adamw_dev(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), n_first,
                                      hyper_dev.data_ptr(), int(zero_grad), _stream()), "adamw_dev")
+
+
+# ---- Prodigy (unet_optimizer_type / ti_optimizer = "prodigy") ---------------------------------------------------
+def prodigy_init_scalars(d0: float, device) -> torch.Tensor:
+    """The 8 device doubles b200_prodigy_step keeps: d = d_max = d0 (as the float the kernels compare against)."""
+    d0f = float(torch.tensor(d0, dtype=torch.float32))
+    return torch.tensor([d0f, d0f, 0.0, 0.0, 0.0, 0.0, 0.0, d0f], dtype=torch.float64, device=device)
+
+
+def prodigy_pack_hyper(out_host: torch.Tensor, *, lr: float, weight_decay: float, d_coef: float, growth_rate: float, k: int,
+                       beta1: float = 0.9, beta2: float = 0.99, eps: float = 1e-8, d0: float = 1e-6,
+                       use_bias_correction: bool = True, l1_coeff: float = 0.0, grad_scale: float = 1.0):
+    assert out_host.dtype == torch.float32 and out_host.numel() == 12 and not out_host.is_cuda
+    check(_lib.load().b200_prodigy_pack_hyper(lr, beta1, beta2, eps, weight_decay, d_coef, growth_rate, d0, k,
+                                              int(use_bias_correction), l1_coeff, grad_scale, out_host.data_ptr()),
+          "prodigy_pack_hyper")
+
+
+def prodigy_step(p, grad, s, p0, exp_avg, exp_avg_sq, scal: torch.Tensor, hyper_dev: torch.Tensor, zero_grad: bool = True):
+    assert p.dtype == BF16 and grad.dtype == torch.float32 and scal.dtype == torch.float64 and scal.numel() == 8
+    assert all(t.dtype == BF16 and t.numel() == p.numel() for t in (s, p0, exp_avg, exp_avg_sq))
+    assert hyper_dev.is_cuda and hyper_dev.dtype == torch.float32 and hyper_dev.numel() == 12
+    check(_lib.load().b200_prodigy_step(p.data_ptr(), grad.data_ptr(), s.data_ptr(), p0.data_ptr(), exp_avg.data_ptr(),
+                                        exp_avg_sq.data_ptr(), p.numel(), scal.data_ptr(), hyper_dev.data_ptr(),
+                                        int(zero_grad), _stream()), "prodigy_step")

@@ -50,6 +50,10 @@ class StepConfig:
     unet_lr_warmup_steps: Optional[int] = None
     freeze_ti_after_completion_f: float = 0.7
     freeze_unet_before_completion_f: float = 0.0
+    unet_optimizer_type: str = "adamw"       # "adamw" | "prodigy" (trainer/optimizer.py:6-39); AdamW8bit: not built
+    ti_optimizer: str = "adamw"              # "adamw" | "prodigy" (trainer/optimizer.py:107-155)
+    prodigy_d_coef: float = 1.0
+    unet_prodigy_growth_factor: float = 1.05
     seed: int = 0
 
     def arch(self) -> UNetArch:
@@ -64,6 +68,8 @@ def lr_schedule(cfg: StepConfig, global_step: int, completion_f: float):
         ti_lr = cfg.ti_lr * (1 - completion_f) ** 1.7
         if completion_f > cfg.freeze_ti_after_completion_f:
             ti_lr = 0.0
+        if cfg.ti_optimizer == "prodigy":                      # main.py:269: no decay, no freeze; the group lr stays 1.0
+            ti_lr = 1.0
     base = 2.0e-4 if cfg.disable_ti else 5.0e-5
     if not cfg.is_lora:
         base = 1.0e-5                                           # main.py:239-240
@@ -80,6 +86,9 @@ class TrainerB200:
     def __init__(self, cfg: StepConfig, unet_state_dict: Dict[str, torch.Tensor], text_encoders: Sequence,
                  device="cuda:0", ti_init: Optional[List[torch.Tensor]] = None, process_group=None,
                  use_cuda_graph: bool = False, native_text: Optional[bool] = None):
+        for name in (cfg.unet_optimizer_type, cfg.ti_optimizer):
+            if name not in ("adamw", "prodigy"):
+                raise NotImplementedError(f"Invalid optimizer_name for the B200 path: {name}")
         self.cfg, self.device = cfg, torch.device(device)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
@@ -124,6 +133,26 @@ class TrainerB200:
         if native_text and self.text_encoders[0] is not None:
             from .clip import TextStackB200
             self.text = TextStackB200(self.sdxl, self.text_encoders, self.ti_rows, self.device)
+        self._prodigy = {}                                     # segment -> (lo, hi, scalars, hyper_host, hyper_dev, kwargs)
+        segs = []
+        if cfg.unet_optimizer_type == "prodigy":
+            if self.dense_mode:
+                raise NotImplementedError("prodigy drives the LoRA factors here; full fine-tuning runs on AdamW")
+            segs.append(("unet", 0, self.store.n_lora, dict(weight_decay=cfg.lora_weight_decay, d_coef=cfg.prodigy_d_coef,
+                                                            growth_rate=cfg.unet_prodigy_growth_factor)))
+        if cfg.ti_optimizer == "prodigy" and ntok:
+            segs.append(("ti", self.store.n_lora, self.store.params.numel(),
+                         dict(weight_decay=cfg.ti_weight_decay, d_coef=1.0, growth_rate=float("inf"))))
+        if segs:
+            # prodigy state beside the Adam moments: s and the start point p0 (trainer/optimizer.py:24-34, 135-144)
+            self._prodigy_s = torch.zeros_like(self.store.params)
+            self._prodigy_p0 = self.store.params.detach().clone()
+            for name, lo, hi, kw in segs:
+                host = torch.zeros(12, dtype=torch.float32)
+                if torch.cuda.is_available():
+                    host = host.pin_memory()
+                self._prodigy[name] = (lo, hi, ops.prodigy_init_scalars(1e-6, self.device), host,
+                                       torch.zeros(12, dtype=torch.float32, device=self.device), kw)
         self.global_step = 0
         self.opt_step = 0
         self._accum = 0
@@ -271,6 +300,11 @@ class TrainerB200:
         ops.adamw_pack_hyper(self._hyper_host, lr=unet_lr, wd=self.cfg.lora_weight_decay, l1_coeff=self._l1_coeff(),
                              lr2=ti_lr or 0.0, wd2=self.cfg.ti_weight_decay, step=self.opt_step + 1, grad_scale=1.0)
         self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+        for name, (lo, hi, scal, host, dev, kw) in self._prodigy.items():
+            # k counts this optimizer's steps (the package skips the increment only when every gradient is exactly zero)
+            ops.prodigy_pack_hyper(host, lr=unet_lr if name == "unet" else 1.0, k=self.opt_step,
+                                   l1_coeff=self._l1_coeff() if name == "unet" else 0.0, **kw)
+            dev.copy_(host, non_blocking=True)
 
     def _train_sets(self):
         """The (params, grads, m, v, n_first) buffer sets the optimizer walks: the flat LoRA + TI buffers; in dense (full
@@ -284,13 +318,29 @@ class TrainerB200:
         return sets
 
     def _train_tensors(self):
-        return [t for st in self._train_sets() for t in st[:4]]
+        ts = [t for st in self._train_sets() for t in st[:4]]
+        if self._prodigy:
+            ts += [self._prodigy_s] + [v[2] for v in self._prodigy.values()]
+        return ts
 
     def _optimizer_body(self, collective: bool = True):
         for p, g, m, v, n_first in self._train_sets():
             if collective and self.pg is not None and self.world > 1:
                 torch.distributed.all_reduce(g, group=self.pg)                # the step's only collective (LoRA mode: one)
-            ops.adamw_dev(p, g, m, v, n_first, self._hyper_dev, zero_grad=True)
+            if not self._prodigy or p is not self.store.params:
+                ops.adamw_dev(p, g, m, v, n_first, self._hyper_dev, zero_grad=True)
+                continue
+            # mixed / prodigy optimizers: one launch set per segment of the flat buffer (LoRA factors | TI rows)
+            for name, lo, hi in (("unet", 0, n_first), ("ti", n_first, p.numel())):
+                if hi <= lo:
+                    continue
+                if name in self._prodigy:
+                    _, _, scal, _, dev, _ = self._prodigy[name]
+                    ops.prodigy_step(p[lo:hi], g[lo:hi], self._prodigy_s[lo:hi], self._prodigy_p0[lo:hi], m[lo:hi], v[lo:hi],
+                                     scal, dev, zero_grad=True)
+                else:
+                    ops.adamw_dev(p[lo:hi], g[lo:hi], m[lo:hi], v[lo:hi], hi - lo if name == "unet" else 0, self._hyper_dev,
+                                  zero_grad=True)
 
     def optimizer_step(self):
         self._set_hyper()

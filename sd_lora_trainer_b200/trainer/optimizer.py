@@ -27,6 +27,31 @@ class FlatAdamW:
         pass            # the fused kernel zeroes the gradients it consumes
 
 
+class FlatProdigy(FlatAdamW):
+    """prodigyopt.Prodigy-shaped handle (trainer/optimizer.py:22-34, 134-144) on a segment of the flat buffer: same
+    ``param_groups[0]['lr']`` surface; the state (s, p0, the d scalars) lives here, exp_avg / exp_avg_sq reuse the
+    store's moment buffers."""
+
+    def __init__(self, store, segment: str, lr: float, weight_decay: float, d_coef: float, growth_rate: float):
+        super().__init__(store, segment, lr, weight_decay)
+        lo, hi = (0, store.n_lora) if segment == "lora" else (store.n_lora, store.params.numel())
+        self.lo, self.hi, self.d_coef, self.growth_rate, self.k = lo, hi, d_coef, growth_rate, 0
+        self.s = torch.zeros(hi - lo, dtype=BF16, device=store.params.device)
+        self.p0 = store.params[lo:hi].detach().clone()
+        self.scal = ops.prodigy_init_scalars(1e-6, store.params.device)
+        self.hyper_host = torch.zeros(12, dtype=torch.float32)
+        self.hyper_dev = torch.zeros(12, dtype=torch.float32, device=store.params.device)
+
+    def step(self, l1_coeff: float = 0.0):
+        g, st = self.param_groups[0], self.store
+        ops.prodigy_pack_hyper(self.hyper_host, lr=g["lr"], weight_decay=g["weight_decay"], d_coef=self.d_coef,
+                               growth_rate=self.growth_rate, k=self.k, l1_coeff=l1_coeff)
+        self.hyper_dev.copy_(self.hyper_host)
+        sl = slice(self.lo, self.hi)
+        ops.prodigy_step(st.params[sl], st.grads[sl], self.s, self.p0, st.m[sl], st.v[sl], self.scal, self.hyper_dev)
+        self.k += 1
+
+
 class OptimizerCollection:
     """optimizer.py:237-275: .optimizers[key], .step(), .zero_grad(), .get_lr(key)."""
 
@@ -54,8 +79,20 @@ class OptimizerCollection:
         l1c = float(torch.tensor(self.l1_penalty, dtype=BF16) / store.numel_logical) if self.l1_penalty > 0 else 0.0
         g_u = unet_opt.param_groups[0] if unet_opt is not None else {"lr": 0.0, "weight_decay": 0.0}
         g_t = ti_opt.param_groups[0] if ti_opt is not None else {"lr": 0.0, "weight_decay": 0.0}
-        ops.adamw(store.params, store.grads, store.m, store.v, store.n_lora, lr=g_u["lr"], wd=g_u["weight_decay"],
-                  l1_coeff=l1c, lr2=g_t["lr"], wd2=g_t["weight_decay"], step=self.steps, zero_grad=True)
+        if not isinstance(unet_opt, FlatProdigy) and not isinstance(ti_opt, FlatProdigy):
+            ops.adamw(store.params, store.grads, store.m, store.v, store.n_lora, lr=g_u["lr"], wd=g_u["weight_decay"],
+                      l1_coeff=l1c, lr2=g_t["lr"], wd2=g_t["weight_decay"], step=self.steps, zero_grad=True)
+        else:                                          # per segment: LoRA factors | token rows
+            n, nl = store.params.numel(), store.n_lora
+            for opt, lo, hi, grp, l1 in ((unet_opt, 0, nl, g_u, l1c), (ti_opt, nl, n, g_t, 0.0)):
+                if hi <= lo:
+                    continue
+                if isinstance(opt, FlatProdigy):
+                    opt.step(l1)
+                else:
+                    sl = slice(lo, hi)
+                    ops.adamw(store.params[sl], store.grads[sl], store.m[sl], store.v[sl], hi - lo, lr=grp["lr"],
+                              wd=grp["weight_decay"], l1_coeff=l1, lr2=0.0, wd2=0.0, step=self.steps, zero_grad=True)
         if self.debug:
             for key in self.optimizers:
                 if self.optimizers[key] is not None:
@@ -80,18 +117,26 @@ def get_unet_lora_parameters(lora_rank, lora_alpha_multiplier: float, lora_weigh
 def get_unet_optimizer(prodigy_d_coef: float, prodigy_growth_factor: float, lora_weight_decay: float, use_dora: bool,
                        unet_trainable_params: Iterable, optimizer_name="adamw", unet: Optional[UNetB200] = None):
     """optimizer.py:6-39.  Only 'adamw' runs on the fused kernel; the placeholder lr 1e-4 is overwritten each step."""
-    if optimizer_name != "adamw":
-        raise NotImplementedError(f"Invalid optimizer_name for the B200 unet path: {optimizer_name} "
-                                  "(prodigy / AdamW8bit are listed as next, SURVEY.md 8f)")
+    wd = lora_weight_decay if not use_dora else 0.0
+    if optimizer_name == "adamw":
+        opt = FlatAdamW(unet.store, "lora", 1e-4, wd)
+    elif optimizer_name == "prodigy":
+        opt = FlatProdigy(unet.store, "lora", 1.0, wd, prodigy_d_coef, prodigy_growth_factor)
+    else:
+        raise NotImplementedError(f"Invalid optimizer_name for unet: {optimizer_name} (AdamW8bit needs bitsandbytes' "
+                                  "quantisation maps, absent here: SURVEY.md 8f row 4)")
     print(f"Created {optimizer_name} optimizer for unet!")
-    return FlatAdamW(unet.store, "lora", 1e-4, lora_weight_decay if not use_dora else 0.0)
+    return opt
 
 
 def get_textual_inversion_optimizer(text_encoders: list, textual_inversion_lr: float, textual_inversion_weight_decay,
                                     optimizer_name: str, unet: Optional[UNetB200] = None):
     """optimizer.py:107-155.  Returns (optimizer, parameter list); the parameters are the n_tokens rows only."""
-    if optimizer_name != "adamw":
+    if optimizer_name == "prodigy":
+        opt = FlatProdigy(unet.store, "ti", 1.0, textual_inversion_weight_decay, 1.0, float("inf"))
+    elif optimizer_name == "adamw":
+        opt = FlatAdamW(unet.store, "ti", textual_inversion_lr, textual_inversion_weight_decay)
+    else:
         raise NotImplementedError(f"Invalid optimizer_name: '{optimizer_name}'")
     print(f"Created {optimizer_name} optimizer for textual inversion!")
-    opt = FlatAdamW(unet.store, "ti", textual_inversion_lr, textual_inversion_weight_decay)
     return opt, [unet.store.params[unet.store.n_lora:]]

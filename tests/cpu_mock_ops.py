@@ -465,6 +465,63 @@ def adamw_dev(p, grad, m, v, n_first, hyper_dev, zero_grad=True):
         grad.zero_()
 
 
+prodigy_init_scalars, prodigy_pack_hyper = real.prodigy_init_scalars, real.prodigy_pack_hyper     # host-only helpers
+
+
+def prodigy_step(p, grad, s, p0, exp_avg, exp_avg_sq, scal, hyper_dev, zero_grad=True):
+    """The three Prodigy kernels (optim.cu) in torch: per-op bf16 rounding, global sums in fp32 / double."""
+    f32 = torch.float32
+    lr, beta1, beta2, beta3, eps, decay, d_coef, growth, d0, bc, l1, gscale = [float(x) for x in hyper_dev.tolist()]
+    t32 = lambda x: float(torch.tensor(x, dtype=f32))
+    d = float(scal[0])
+    pv = p.float()
+    g = (grad * gscale).to(BF16).float()
+    if l1 != 0.0:
+        g = (g + l1 * torch.sign(pv)).to(BF16).float()
+    if zero_grad:
+        grad.zero_()
+    if lr > 0.0:
+        dot = float((g * (p0.float() - pv).to(BF16).float()).sum())
+        mv = (exp_avg.float() * beta1).to(BF16).float()
+        mv = (mv + t32(d * (1.0 - beta1)) * g).to(BF16)
+        vv = (exp_avg_sq.float() * beta2).to(BF16).float()
+        vv = (vv + t32(d * d * (1.0 - beta2)) * (g * g)).to(BF16)
+        sv = (s.float() * beta3).to(BF16).float()
+        sv = (sv + t32((d / d0) * d) * g).to(BF16)
+        exp_avg.copy_(mv)
+        exp_avg_sq.copy_(vv)
+        s.copy_(sv)
+        scal[4] += dot
+        scal[3] += float(sv.float().abs().sum())
+    den = float(scal[3])
+    dlr = d * lr * bc
+    num = float(scal[2]) * beta3
+    if lr > 0.0:
+        num += (d / d0) * dlr * float(scal[4])
+    scal[5] = dlr
+    scal[3] = 0.0
+    scal[4] = 0.0
+    if den == 0.0:
+        scal[6] = 1.0
+        return
+    d_max = float(scal[1])
+    d_hat = d
+    if lr > 0.0:
+        d_hat = d_coef * num / den
+        if d == d0:
+            d = max(d, d_hat)
+        d_max = max(d_max, d_hat)
+        d = min(d_max, d * growth)
+    scal[0], scal[1], scal[2], scal[6], scal[7] = d, d_max, num, 0.0, d_hat
+    denom = exp_avg_sq.float().sqrt().to(BF16).float()
+    denom = (denom + t32(d * eps)).to(BF16).float()
+    pv = p.float()
+    if decay != 0.0:
+        pv = (pv + t32(-decay * dlr) * pv).to(BF16).float()
+    pv = (pv - t32(dlr) * (exp_avg.float() / denom)).to(BF16)
+    p.copy_(pv)
+
+
 def install(monkeypatch):
     """Patch every product module that holds a reference to ops."""
     import sd_lora_trainer_b200.step as step_mod
