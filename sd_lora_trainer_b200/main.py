@@ -167,7 +167,12 @@ def train(config: TrainingConfig, dataset, text_encoders: Sequence, unet_state_d
     tokenize: captions -> ([B, 77] int64 ids per text encoder, the unpadded id list of every caption as
               ``pipe.tokenizer.encode`` returns it - trainer/loss.py:33)."""
     _check_supported(config)
-    seed_everything(config.seed)
+    # data parallel (SURVEY.md 8e): one process per GPU, every rank runs this generator; a step's global batch is
+    # train_batch_size x world images, the shuffle is shared (seeded by config.seed), the random draws are per rank
+    world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+    rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
+    seed_everything(config.seed + rank)
+    perm_gen = torch.Generator().manual_seed(config.seed)
     family = config.sd_model_version or ("sdxl" if "add_embedding.linear_1.weight" in unet_state_dict else "sd15")
     config.sd_model_version = family
     config.pretrained_model = dict(config.pretrained_model or {}, version=family)
@@ -180,12 +185,14 @@ def train(config: TrainingConfig, dataset, text_encoders: Sequence, unet_state_d
     dev = trainer.device
     n = len(dataset)
     bs = config.train_batch_size
-    n_batches = int(math.ceil(n / bs))                         # DataLoader(drop_last=False)
+    gbs = bs * world
+    n_batches = int(math.ceil(n / gbs))                        # DataLoader(drop_last=False)
     config.num_train_epochs = int(math.ceil(config.max_train_steps / n_batches))
     checkpoint_dir = os.path.join(str(config.output_dir), "checkpoints")
-    if os.path.exists(checkpoint_dir):
-        shutil.rmtree(checkpoint_dir)
-    os.makedirs(checkpoint_dir)
+    if rank == 0:
+        if os.path.exists(checkpoint_dir):
+            shutil.rmtree(checkpoint_dir)
+        os.makedirs(checkpoint_dir)
     global_step, last_save_step = 0, 0
     losses: Dict[str, List[float]] = {"img_loss": [], "tot_loss": [], "token_std_loss": [], "token_attention_loss": []}
     config.training_attributes = dict(config.training_attributes, losses=losses)
@@ -193,9 +200,12 @@ def train(config: TrainingConfig, dataset, text_encoders: Sequence, unet_state_d
     start_time, images_done = time.time(), 0
 
     for epoch in range(config.num_train_epochs):
-        order = torch.randperm(n).tolist()                     # DataLoader(shuffle=True)
+        order = torch.randperm(n, generator=perm_gen).tolist()  # DataLoader(shuffle=True)
         for step in range(n_batches):
-            idx = order[step * bs:(step + 1) * bs]
+            if world == 1:
+                idx = order[step * bs:(step + 1) * bs]          # the last batch of an epoch may be short
+            else:                                               # every rank needs a full micro-batch: wrap around
+                idx = [order[(step * gbs + rank * bs + j) % n] for j in range(bs)]
             completion_f = (epoch + step / n_batches) / config.num_train_epochs
             items = [dataset[i] for i in idx]
             captions = [it[0] for it in items]
@@ -220,11 +230,12 @@ def train(config: TrainingConfig, dataset, text_encoders: Sequence, unet_state_d
                     losses[k].append(float(out[k]))
 
             if (global_step % config.checkpointing_steps == 0) and (global_step < (config.max_train_steps - 25)):
-                print(f"\n---- avg training fps: {images_done / (time.time() - start_time):.2f}", end="\r", flush=True)
                 output_save_dir = f"{checkpoint_dir}/checkpoint-{global_step}"
-                _save(config, trainer, handler, output_save_dir, global_step, family)
+                if rank == 0:                                   # replicas are identical: one writer
+                    print(f"\n---- avg training fps: {images_done / (time.time() - start_time):.2f}", end="\r", flush=True)
+                    _save(config, trainer, handler, output_save_dir, global_step, family)
                 last_save_step = global_step
-            images_done += bs
+            images_done += gbs
             global_step += 1
             if global_step % progress_every == 0:
                 yield float(min(global_step / config.max_train_steps + 0.05, 1.0))
@@ -236,11 +247,13 @@ def train(config: TrainingConfig, dataset, text_encoders: Sequence, unet_state_d
         output_save_dir = f"{checkpoint_dir}/checkpoint-{global_step}"
     else:
         output_save_dir = f"{checkpoint_dir}/checkpoint-{last_save_step}"
-    if not os.path.exists(output_save_dir):
-        _save(config, trainer, handler, output_save_dir, global_step, family)
-    else:
-        print(f"Skipping final save, {output_save_dir} already exists")
+    if rank == 0:                                              # replicas are identical: one writer
+        if not os.path.exists(output_save_dir):
+            _save(config, trainer, handler, output_save_dir, global_step, family)
+        else:
+            print(f"Skipping final save, {output_save_dir} already exists")
     config.job_time = time.time() - config.start_time
-    config.save_as_json(os.path.join(output_save_dir, "training_args.json"))
+    if rank == 0:
+        config.save_as_json(os.path.join(output_save_dir, "training_args.json"))
     print("Training job complete, saving outputs...", flush=True)
     return config, output_save_dir

@@ -82,3 +82,60 @@ def test_dp2_equals_gradient_accumulation(tmp_path):
     frac_diff = float((diff > 0).float().mean())
     assert frac_diff < 5e-3, frac_diff
     assert float(diff.max()) <= 2.5 * float((tr.store.params.float() - p0.float()).abs().max())
+
+
+def _train_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _patch_ops()
+    import sd_lora_trainer_b200.trainer.dataset as ds_mod
+    from tests import cpu_mock_ops
+    ds_mod.ops = cpu_mock_ops
+    from oracle.text import build_text_encoders
+    from sd_lora_trainer_b200 import main as main_mod
+    from sd_lora_trainer_b200.arch import by_name
+    from sd_lora_trainer_b200.init import random_state_dict
+    from tests.test_train_loop_cpu import _dataset, _tokenize_factory
+    seen = []
+    real_step = main_mod.TrainerB200.step
+
+    holder = {}
+
+    def spy(self, inputs, completion_f=0.0, do_optimizer=True, optimizer_now=None):
+        seen.append(inputs["vae_latent"].clone())
+        holder["trainer"] = self
+        return real_step(self, inputs, completion_f, do_optimizer, optimizer_now)
+
+    main_mod.TrainerB200.step = spy
+    cfg = main_mod.TrainingConfig(lora_training_urls="dp", sd_model_version="sd15", seed=5, resolution=64, train_batch_size=1,
+                                  max_train_steps=3, lora_rank=4, output_dir=os.path.join(out_dir, "run"), device="cpu",
+                                  caption_dropout=0.0)
+    gen = main_mod.train(cfg, _dataset(5, 8), build_text_encoders("sd15", tiny=True, seed=2),
+                         random_state_dict(by_name("tiny_sd15"), seed=0, device="cpu"), _tokenize_factory("sd15"), tiny=True,
+                         process_group=dist.group.WORLD)
+    try:
+        while True:
+            next(gen)
+    except StopIteration as stop:
+        out_cfg, out_path = stop.value
+    torch.save({"latents": torch.stack(seen), "out_path": out_path, "done": gen.gi_frame is None,
+                "params": holder["trainer"].store.params.clone()}, os.path.join(out_dir, f"t{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_train_generator_shards_batches_across_ranks(tmp_path):
+    """train() under data parallelism: the ranks share the shuffle but take different images of every global batch, stay
+    in lock-step through the in-step all-reduce, and only rank 0 writes the checkpoint."""
+    world = 2
+    mp.spawn(_train_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    t0, t1 = torch.load(tmp_path / "t0.pt"), torch.load(tmp_path / "t1.pt")
+    assert t0["done"] and t1["done"] and t0["out_path"] == t1["out_path"]
+    assert torch.equal(t0["params"], t1["params"]), "replicas diverged"
+    assert t0["latents"].shape == t1["latents"].shape and t0["latents"].shape[0] >= 3
+    for a, b in zip(t0["latents"], t1["latents"]):
+        assert not torch.equal(a, b)                       # different images (and different posterior draws) per rank
+    files = sorted(os.listdir(t0["out_path"]))
+    assert "dp_sd15_lora.safetensors" in files and "training_args.json" in files
+    assert sorted(os.listdir(os.path.join(tmp_path, "run", "checkpoints"))) == [os.path.basename(t0["out_path"])]
