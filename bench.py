@@ -114,7 +114,8 @@ def run_ours(args):
                      is_lora=not args.full_ft, max_train_steps=max(args.steps + args.warmup, 300))
     sd = random_state_dict(cfg.arch(), seed=0, device=dev)
     tes = build_text_encoders(args.family, dev)
-    tr = TrainerB200(cfg, sd, tes, device=dev, process_group=pg, use_cuda_graph=not args.no_graph)
+    tr = TrainerB200(cfg, sd, tes, device=dev, process_group=pg, use_cuda_graph=not args.no_graph,
+                     native_text=True if args.native_clip else None)
     del sd
     B = args.batch
     host_batches = [synthetic_inputs(args.family, B, args.res, 0 if args.full_ft else cfg.n_tokens,
@@ -192,7 +193,7 @@ def run_ours(args):
                                    f"bf16 batch {B}/GPU, fwd+bwd+AdamW, random-init full-size weights",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "working set (5 GB weights + ~25 GB activations per step) exceeds the 126 MB L2",
-                       "cuda_graph": not args.no_graph},
+                       "cuda_graph": not args.no_graph, "text_encoders": "native" if tr.text is not None else "transformers"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": tr.h2d_bytes_last, "d2h_bytes_per_step": 4},
@@ -303,6 +304,8 @@ def main():
     ap.add_argument("--rank", type=int, default=16)
     ap.add_argument("--full-ft", action="store_true",
                     help="BASELINE config 5: full-UNet fine-tune (dense backward, AdamW over every parameter), disable_ti")
+    ap.add_argument("--native-clip", action="store_true",
+                    help="text encoders on the native CLIP executor (clip.py) instead of the stock transformers modules")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
