@@ -129,6 +129,9 @@ class TrainerB200:
         # our kernels (clip.py; B200_NATIVE_CLIP=1 / native_text=True).
         if native_text is None:
             native_text = os.environ.get("B200_NATIVE_CLIP", "0") == "1"
+        # conditioning cache for the phases without a trainable token row (B200_TEXT_CACHE=0 turns it off)
+        self.cache_text = os.environ.get("B200_TEXT_CACHE", "1") != "0"
+        self._text_cache: Dict[tuple, tuple] = {}
         self.text = None
         if native_text and self.text_encoders[0] is not None:
             from .clip import TextStackB200
@@ -175,7 +178,32 @@ class TrainerB200:
         return self._tid
 
     # ---- inputs: host dict -> device tensors (static buffers when the step is graph-captured) ------
-    def _stage_inputs(self, inputs: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    # ---- conditioning cache: with no trainable token row in play, a caption's embeddings never change ----------
+    def _cached_text(self, token_ids: Sequence[torch.Tensor]):
+        """(prompt_embeds [B, 77, D], pooled [B, P] | None) from a per-caption cache keyed by the token ids; only the
+        captions not seen yet go through the (frozen) text encoders, without autograd.  Used when the token rows are
+        absent (disable_ti) or frozen (ti_lr = 0): the reference re-encodes every caption every step (main.py:306)."""
+        ids = [t.long().cpu() for t in token_ids]
+        B = ids[0].shape[0]
+        keys = [tuple(int(v) for t in ids for v in t[b].tolist()) for b in range(B)]
+        miss = [b for b in range(B) if keys[b] not in self._text_cache]
+        miss = [b for i, b in enumerate(miss) if keys[b] not in [keys[c] for c in miss[:i]]]     # one encode per caption
+        if miss:
+            sub = [t[miss].to(self.device) for t in ids]
+            with torch.no_grad():
+                if self.text is not None:
+                    self.text.prepare(sub[0].shape[1])
+                    pe, pooled = self.text.encode_prompt(sub, need_bwd=False)
+                else:
+                    pe, pooled = encode_prompt(self.sdxl, self.text_encoders, sub)
+            for j, b in enumerate(miss):
+                self._text_cache[keys[b]] = (pe[j].detach().clone(), None if pooled is None else pooled[j].detach().clone())
+        got = [self._text_cache[k] for k in keys]
+        pe = torch.stack([g[0] for g in got])
+        pooled = None if got[0][1] is None else torch.stack([g[1] for g in got])
+        return pe, pooled
+
+    def _stage_inputs(self, inputs: Dict[str, torch.Tensor], ti_active: bool = True) -> Dict[str, torch.Tensor]:
         """Copies one step's inputs to the device.  Returns the dict the step body reads; under CUDA graphs the
         same tensors are reused (and overwritten) every step so the captured pointers stay valid."""
         cfg, dev = self.cfg, self.device
@@ -192,6 +220,12 @@ class TrainerB200:
         if not cfg.disable_ti:
             from .trainer.loss import token_index_tensors
             staged["tok_len"], staged["ti_pos"] = token_index_tensors(inputs["token_indices"], self.train_ids)
+        if bool(self.ti_rows) and ti_active:
+            self._text_cache.clear()                            # the rows are about to move: cached embeddings go stale
+        elif self.cache_text and self.text_encoders[0] is not None:
+            staged["prompt_embeds"], pooled = self._cached_text(inputs["token_ids"])
+            if pooled is not None:
+                staged["pooled"] = pooled
         key = tuple((k, tuple(v.shape)) for k, v in staged.items())
         if self.sdxl:
             self._time_ids(B)
@@ -203,13 +237,14 @@ class TrainerB200:
         for k, v in staged.items():
             src = v if (v.is_cuda or v.is_pinned() or not torch.cuda.is_available()) else v.contiguous().pin_memory()
             self._static[k].copy_(src, non_blocking=True)
-            nbytes += v.numel() * v.element_size()
+            if not v.is_cuda:
+                nbytes += v.numel() * v.element_size()          # host -> device traffic only
         self.h2d_bytes_last = nbytes
         return self._static
 
     # ---- one micro-step: forward, losses, backward ------------------------------------------------
     def forward_backward(self, inputs: Dict[str, torch.Tensor], ti_active: bool = True) -> Dict[str, torch.Tensor]:
-        return self._body(self._stage_inputs(inputs), ti_active)
+        return self._body(self._stage_inputs(inputs, ti_active), ti_active)
 
     def _body(self, st: Dict[str, torch.Tensor], ti_active: bool) -> Dict[str, torch.Tensor]:
         cfg, dev = self.cfg, self.device
@@ -223,7 +258,9 @@ class TrainerB200:
         # never rises again) the token rows cannot change: AdamW with lr = 0 is the identity on them.  The reference still
         # back-propagates through both text encoders; here that backward is skipped - same parameters after the step.
         need_text_grad = bool(self.ti_rows) and ti_active
-        if self.text is not None:
+        if "prompt_embeds" in st and not need_text_grad:        # staged from the conditioning cache (or a kernel-only probe)
+            prompt_embeds, pooled = st["prompt_embeds"], st.get("pooled")
+        elif self.text is not None:
             self.text.prepare(token_ids[0].shape[1])
             prompt_embeds, pooled = self.text.encode_prompt(token_ids, need_bwd=need_text_grad)
         elif self.text_encoders[0] is not None:
@@ -372,7 +409,7 @@ class TrainerB200:
 
     # ---- CUDA-graph path: the whole step (text encoders, UNet fwd/bwd, losses, all-reduce, AdamW) is ONE graph ----
     def _graph_step(self, inputs, ti_active: bool, opt_now: bool):
-        st = self._stage_inputs(inputs)
+        st = self._stage_inputs(inputs, ti_active)
         if opt_now:
             self._set_hyper()
         key = (ti_active, opt_now)

@@ -158,3 +158,37 @@ def test_frozen_ti_phase_skips_text_backward_without_changing_the_step(monkeypat
         assert torch.equal(t0, te.text_model.embeddings.token_embedding.weight.data[-cfg.n_tokens:])   # oracle: lr = 0
     after = tr.store.export_peft()
     assert any(not torch.equal(after[k], p_before[k]) for k in after)               # the LoRA factors did move
+
+
+def test_conditioning_cache_encodes_each_caption_once(monkeypatch):
+    """disable_ti (or frozen TI): a caption's embeddings cannot change, so the step caches them per token-id row and only
+    unseen captions reach the text encoders; the step's results equal the uncached path bit for bit."""
+    cpu_mock_ops.install(monkeypatch)
+    import sd_lora_trainer_b200.step as step_mod
+    calls = []
+    real = step_mod.encode_prompt
+
+    def spy(is_sdxl, tes, ids):
+        calls.append(int(ids[0].shape[0]))
+        return real(is_sdxl, tes, ids)
+
+    monkeypatch.setattr(step_mod, "encode_prompt", spy)
+    cfg, orc, tr, inputs = _setup("sdxl", 8, 2, 8, disable_ti=True)
+    assert tr.cache_text and not tr.ti_rows
+    out1 = tr.step(inputs, do_optimizer=False)
+    assert calls == [2]                                         # both captions of the batch were new
+    g1 = tr.store.grads.clone()
+    tr.store.grads.zero_()
+    out2 = tr.step(inputs, do_optimizer=False)
+    assert calls == [2]                                         # second visit: served from the cache
+    assert float(out1["tot_loss"]) == float(out2["tot_loss"]) and torch.equal(g1, tr.store.grads)
+    swapped = dict(inputs, token_ids=[t.flip(0) for t in inputs["token_ids"]])
+    tr.step(swapped, do_optimizer=False)
+    assert calls == [2]                                         # same captions in another order: still no encoder call
+    monkeypatch.setenv("B200_TEXT_CACHE", "0")
+    cfg, orc, tr2, _ = _setup("sdxl", 8, 2, 8, disable_ti=True)
+    tr2.store.params.copy_(tr.store.params)
+    tr2.store.grads.zero_()
+    out3 = tr2.step(inputs, do_optimizer=False)
+    assert not tr2.cache_text and calls == [2, 2]                # the uncached path encodes inside the step
+    assert float(out3["tot_loss"]) == float(out1["tot_loss"]) and torch.equal(tr2.store.grads, g1)
