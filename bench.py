@@ -116,6 +116,7 @@ def run_ours(args):
     tes = build_text_encoders(args.family, dev)
     tr = TrainerB200(cfg, sd, tes, device=dev, process_group=pg, use_cuda_graph=not args.no_graph,
                      native_text=True if args.native_clip else None)
+    tr.cache_text = False      # timed steps encode every caption every step, as the reference does (no cached outputs)
     del sd
     B = args.batch
     host_batches = [synthetic_inputs(args.family, B, args.res, 0 if args.full_ft else cfg.n_tokens,
