@@ -136,7 +136,7 @@ def seed_everything(seed: int):
 
 
 def _check_supported(config: TrainingConfig):
-    if config.unet_optimizer_type not in ("adamw", "prodigy"):
+    if config.unet_optimizer_type not in ("adamw", "prodigy", "AdamW8bit"):      # AdamW8bit: declared substitution, step.py
         raise NotImplementedError(f"Invalid optimizer_name for unet: {config.unet_optimizer_type}")
     if config.ti_optimizer not in ("adamw", "prodigy"):
         raise NotImplementedError(f"Invalid optimizer_name: '{config.ti_optimizer}'")

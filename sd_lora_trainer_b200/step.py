@@ -86,9 +86,16 @@ class TrainerB200:
     def __init__(self, cfg: StepConfig, unet_state_dict: Dict[str, torch.Tensor], text_encoders: Sequence,
                  device="cuda:0", ti_init: Optional[List[torch.Tensor]] = None, process_group=None,
                  use_cuda_graph: bool = False, native_text: Optional[bool] = None):
-        for name in (cfg.unet_optimizer_type, cfg.ti_optimizer):
-            if name not in ("adamw", "prodigy"):
-                raise NotImplementedError(f"Invalid optimizer_name for the B200 path: {name}")
+        if cfg.unet_optimizer_type == "AdamW8bit":
+            # declared substitution: bitsandbytes' blockwise 8-bit states need its quantisation maps,
+            # which are not available offline; the step runs AdamW with bf16 states instead - same update rule, the
+            # moments are kept at higher precision than the reference keeps them
+            import warnings
+            warnings.warn("unet_optimizer_type='AdamW8bit' runs as AdamW with bf16 moments on the B200 path")
+        elif cfg.unet_optimizer_type not in ("adamw", "prodigy"):
+            raise NotImplementedError(f"Invalid optimizer_name for unet: {cfg.unet_optimizer_type}")
+        if cfg.ti_optimizer not in ("adamw", "prodigy"):
+            raise NotImplementedError(f"Invalid optimizer_name: '{cfg.ti_optimizer}'")
         self.cfg, self.device = cfg, torch.device(device)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1

@@ -118,13 +118,17 @@ def get_unet_optimizer(prodigy_d_coef: float, prodigy_growth_factor: float, lora
                        unet_trainable_params: Iterable, optimizer_name="adamw", unet: Optional[UNetB200] = None):
     """optimizer.py:6-39.  Only 'adamw' runs on the fused kernel; the placeholder lr 1e-4 is overwritten each step."""
     wd = lora_weight_decay if not use_dora else 0.0
-    if optimizer_name == "adamw":
+    if optimizer_name == "AdamW8bit":
+        # declared substitution (SURVEY.md 8f row 4): bitsandbytes' quantisation maps are not available offline
+        import warnings
+        warnings.warn("optimizer_name='AdamW8bit' runs as AdamW with bf16 moments on the B200 path")
+        opt = FlatAdamW(unet.store, "lora", 1e-4, lora_weight_decay)
+    elif optimizer_name == "adamw":
         opt = FlatAdamW(unet.store, "lora", 1e-4, wd)
     elif optimizer_name == "prodigy":
         opt = FlatProdigy(unet.store, "lora", 1.0, wd, prodigy_d_coef, prodigy_growth_factor)
     else:
-        raise NotImplementedError(f"Invalid optimizer_name for unet: {optimizer_name} (AdamW8bit needs bitsandbytes' "
-                                  "quantisation maps, absent here: SURVEY.md 8f row 4)")
+        raise NotImplementedError(f"Invalid optimizer_name for unet: {optimizer_name}")
     print(f"Created {optimizer_name} optimizer for unet!")
     return opt
 

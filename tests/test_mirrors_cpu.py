@@ -52,6 +52,9 @@ def test_reference_call_sequence(monkeypatch, unet_opt, ti_opt):
         assert not torch.equal(unet.store.params[nl:], before[nl:])
     assert coll.get_lr("unet") == (3e-4 if unet_opt == "adamw" else 1.0)
     with pytest.raises(NotImplementedError):
-        get_unet_optimizer(1.0, 1.05, 0.004, False, lora_params, optimizer_name="AdamW8bit", unet=unet)
+        get_unet_optimizer(1.0, 1.05, 0.004, False, lora_params, optimizer_name="lion", unet=unet)
+    with pytest.warns(UserWarning, match="AdamW8bit"):                                              # declared substitution
+        assert not isinstance(get_unet_optimizer(1.0, 1.05, 0.004, False, lora_params, optimizer_name="AdamW8bit", unet=unet),
+                              FlatProdigy)
     with pytest.raises(NotImplementedError):
         get_unet_lora_parameters(4, 1.0, 0.004, True, None, pipe)                                   # DoRA

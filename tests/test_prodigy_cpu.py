@@ -141,5 +141,8 @@ def test_training_steps_with_prodigy_match_oracle(monkeypatch, unet_opt, ti_opt)
 def test_prodigy_guards():
     from sd_lora_trainer_b200.step import StepConfig, TrainerB200, lr_schedule
     with pytest.raises(NotImplementedError):
-        TrainerB200(StepConfig(family="sd15", tiny=True, unet_optimizer_type="AdamW8bit"), {}, (None, None), device="cpu")
+        TrainerB200(StepConfig(family="sd15", tiny=True, unet_optimizer_type="lion"), {}, (None, None), device="cpu")
+    with pytest.warns(UserWarning, match="AdamW8bit"):           # declared substitution: AdamW with bf16 moments
+        with pytest.raises(KeyError):                            # (the empty state dict ends construction right after)
+            TrainerB200(StepConfig(family="sd15", tiny=True, unet_optimizer_type="AdamW8bit"), {}, (None, None), device="cpu")
     assert lr_schedule(StepConfig(ti_optimizer="prodigy"), 10, 0.9)[0] == 1.0             # never decayed, never frozen
