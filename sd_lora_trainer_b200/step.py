@@ -77,6 +77,8 @@ def lr_schedule(cfg: StepConfig, global_step: int, completion_f: float):
     unet_lr = base * (cfg.unet_lr / base) ** (global_step / warm)
     if completion_f < cfg.freeze_unet_before_completion_f:     # main.py:290-291
         unet_lr = 0.0
+    if cfg.unet_lr <= 0.0:                                     # main.py:164-176: no UNet optimizer at all (ti_SDXL.json)
+        unet_lr = 0.0
     return ti_lr, unet_lr
 
 

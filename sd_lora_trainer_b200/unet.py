@@ -25,6 +25,7 @@ from .arch import UNetArch
 from .ops import BF16, Conv3x3, Mat, kmajor, mnmajor
 
 LORA_TARGETS = ("to_k", "to_q", "to_v", "to_out.0", "conv2")      # trainer/optimizer.py:84
+MAX_SIDE_RANK = 32                                                # widest in-kernel LoRA side path (b200_gemm_t.side_r)
 _SMS = 148
 
 
@@ -274,13 +275,21 @@ class Lin:
         M = x.shape[0]
         y = torch.empty(M, self.N, dtype=BF16, device=x.device)
         T, side = None, None
+        segs = [(kmajor(x), kmajor(self.W), self.K)]
         if self.lora is not None:
-            # ONE launch: the rank-r product T = s.x.A^T accumulates in TMEM beside the main tile, is rounded to bf16
-            # in-kernel and multiplied with B by a final MMA; T also leaves for the dB weight-gradient GEMM.
             lo = self.lora
             T = torch.empty(M, lo.rs, dtype=BF16, device=x.device)
-            side = (Mat(lo.A(), lo.r, self.K, self.K), Mat(lo.B(), self.N, lo.r, lo.rs), lo.r, lo.store.scaling, T)
-        ops.gemm(y, M, self.N, [(kmajor(x), kmajor(self.W), self.K)], bias=self.b if bias is None else bias,
+            if lo.r <= MAX_SIDE_RANK:
+                # ONE launch: the rank-r product T = s.x.A^T accumulates in TMEM beside the main tile, is rounded to
+                # bf16 in-kernel and multiplied with B by a final MMA; T also leaves for the dB weight-gradient GEMM.
+                side = (Mat(lo.A(), lo.r, self.K, self.K), Mat(lo.B(), self.N, lo.r, lo.rs), lo.r, lo.store.scaling, T)
+            else:
+                # ranks beyond the in-kernel side path (e.g. train_configs/training_args_style_sd15_noti.json: 64): T by
+                # its own GEMM, then T.B^T as a second K segment of the main launch (the conv-LoRA form)
+                ops.gemm(T, M, lo.r, [(kmajor(x), Mat(lo.A(), lo.r, self.K, self.K), self.K)], d_strides=(lo.rs, 1, 0, 0),
+                         alpha=lo.store.scaling)
+                segs.append((Mat(T, M, lo.r, lo.rs), Mat(lo.B(), self.N, lo.r, lo.rs), lo.r))
+        ops.gemm(y, M, self.N, segs, bias=self.b if bias is None else bias,
                  bias_rows=bias_rows, bias_sb=self.N if bias_rows else 0, residual=residual, side=side, static_b=True)
         if save:
             self.x, self.T = x, T
@@ -291,10 +300,15 @@ class Lin:
         x, lo, T = self.x, self.lora, self.T
         self.x = self.T = None
         dx, U, side = None, None, None
+        segs = [(kmajor(dy), mnmajor(self.W), self.N)]
         if lo is not None:
             r, rs = lo.r, lo.rs
             U = torch.empty(M, rs, dtype=BF16, device=dy.device)
-            if need_dx:
+            if need_dx and r > MAX_SIDE_RANK:
+                ops.gemm(U, M, r, [(kmajor(dy), Mat(lo.B(), self.N, r, rs, mn=True), self.N)], d_strides=(rs, 1, 0, 0),
+                         alpha=lo.store.scaling)
+                segs.append((Mat(U, M, r, rs), Mat(lo.A(), r, self.K, self.K, mn=True), r))
+            elif need_dx:
                 # dX = dY.W + (s.dY.B).A in ONE launch; U = s.dY.B leaves for the dA weight-gradient GEMM
                 # (S = the K-major copy of B: read in place it is a tiny MN-major box every CTA re-fetches per k-block)
                 side = (Mat(lo.Bt(), r, self.N, self.N), Mat(lo.A(), r, self.K, self.K, mn=True), r, lo.store.scaling, U)
@@ -303,7 +317,7 @@ class Lin:
                          alpha=lo.store.scaling)
         if need_dx:
             dx = accum if accum is not None else torch.empty(M, self.K, dtype=BF16, device=dy.device)
-            ops.gemm(dx, M, self.K, [(kmajor(dy), mnmajor(self.W), self.N)], residual=accum, side=side, static_b=True)
+            ops.gemm(dx, M, self.K, segs, residual=accum, side=side, static_b=True)
         if lo is not None:
             # dB[N, r] += dY^T . T      dA[r, K] += U^T . X   (both operands MN-major, split-K fp32 atomics)
             def wgrad():

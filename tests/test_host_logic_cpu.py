@@ -192,3 +192,28 @@ def test_conditioning_cache_encodes_each_caption_once(monkeypatch):
     out3 = tr2.step(inputs, do_optimizer=False)
     assert not tr2.cache_text and calls == [2, 2]                # the uncached path encodes inside the step
     assert float(out3["tot_loss"]) == float(out1["tot_loss"]) and torch.equal(tr2.store.grads, g1)
+
+
+def test_step_host_logic_rank64_falls_back_to_two_launch_lora(monkeypatch):
+    """train_configs/training_args_style_sd15_noti.json trains rank 64, beyond the in-kernel side path (rank <= 32): the
+    linear layers compute T / U by their own GEMM and add the low-rank product as a second K segment."""
+    cpu_mock_ops.install(monkeypatch)
+    cfg, orc, tr, inputs = _setup("sd15", 64, 1, 8, disable_ti=True)
+    out_o = orc.step(inputs, do_optimizer=False)
+    out_p = tr.step(inputs, do_optimizer=False)
+    a, b = float(out_p["tot_loss"]), float(out_o["tot_loss"])
+    assert abs(a - b) / abs(b) <= 1e-2, (a, b)                   # 64 random rank-1 terms per layer: bf16 paths drift more
+    ours = tr.store.export_peft(grads=True)
+    n = 0
+    for name, p in orc.unet.named_parameters():
+        if p.grad is not None:
+            assert rel(ours[name].reshape(p.grad.shape), p.grad) < 0.3, name
+            n += 1
+    assert n == 2 * len(tr.store.slots) and all(s.r == 64 for s in tr.store.slots)
+
+
+def test_unet_lr_zero_means_no_unet_update():
+    """ti_SDXL.json: unet_lr = 0 -> the reference builds no UNet optimizer (main.py:164-176)."""
+    from sd_lora_trainer_b200.step import StepConfig, lr_schedule
+    cfg = StepConfig(unet_lr=0.0)
+    assert lr_schedule(cfg, 0, 0.0)[1] == 0.0 and lr_schedule(cfg, 10, 0.1)[1] == 0.0
