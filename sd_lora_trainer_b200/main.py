@@ -58,6 +58,11 @@ class TrainingConfig:
     freeze_ti_after_completion_f: float = 0.7
     freeze_unet_before_completion_f: float = 0.0
     token_attention_loss_w: float = 3e-7
+    cond_reg_w: float = 0.0
+    tok_cond_reg_w: float = 0.0
+    tok_cov_reg_w: float = 0.0
+    token_warmup_steps: int = 0
+    aspect_ratio_bucketing: bool = False
     l1_penalty: float = 0.03
     noise_offset: float = 0.02
     snr_gamma: float = 5.0
@@ -140,6 +145,13 @@ def _check_supported(config: TrainingConfig):
         raise NotImplementedError(f"Invalid optimizer_name for unet: {config.unet_optimizer_type}")
     if config.ti_optimizer not in ("adamw", "prodigy"):
         raise NotImplementedError(f"Invalid optimizer_name: '{config.ti_optimizer}'")
+    # experimental switches of the reference that are off in its defaults and in every shipped train_config: refuse them
+    # loudly rather than train something else (trainer/loss.py:203-225, embedding_handler.py:321-333, dataset.py bucketing)
+    for name in ("cond_reg_w", "tok_cond_reg_w", "tok_cov_reg_w", "token_warmup_steps"):
+        if getattr(config, name) > 0:
+            raise NotImplementedError(f"{name} > 0 is outside the accelerated path (off by default in the reference)")
+    if config.aspect_ratio_bucketing:
+        raise NotImplementedError("aspect_ratio_bucketing is outside the accelerated path (dataset-side feature)")
     if config.text_encoder_lora_optimizer is not None:
         raise NotImplementedError("text-encoder LoRA is outside the accelerated path (SURVEY.md 2, row 3)")
     if config.weight_type != "bf16":

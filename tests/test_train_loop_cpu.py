@@ -122,7 +122,8 @@ def test_train_checkpoint_cadence_and_accumulation(monkeypatch, tmp_path):
 
 def test_train_rejects_unsupported_modes(tmp_path):
     from sd_lora_trainer_b200.main import TrainingConfig, train
-    for kw, exc in ((dict(unet_optimizer_type="lion"), NotImplementedError), (dict(ti_optimizer="adagrad"), NotImplementedError), (dict(weight_type="fp16"), ValueError),
+    for kw, exc in ((dict(unet_optimizer_type="lion"), NotImplementedError), (dict(ti_optimizer="adagrad"), NotImplementedError),
+                    (dict(tok_cov_reg_w=1e-3), NotImplementedError), (dict(aspect_ratio_bucketing=True), NotImplementedError), (dict(weight_type="fp16"), ValueError),
                     (dict(text_encoder_lora_optimizer="adamw"), NotImplementedError)):
         cfg = TrainingConfig(lora_training_urls="x", output_dir=str(tmp_path), device="cpu", **kw)
         with pytest.raises(exc):
