@@ -5,12 +5,12 @@
 #   gpurun --timeout 1500 -- bash scripts/gpu_round2.sh
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q --deselect tests/test_z5_vae_gpu.py --deselect tests/test_z4_clip_gpu.py \
-    --deselect tests/test_z3_dense_gpu.py --deselect tests/test_z2_prodigy_gpu.py --deselect tests/test_z1_train_gpu.py \
+    --deselect tests/test_z3_dense_gpu.py --deselect tests/test_z2_prodigy_gpu.py --deselect tests/test_z1_train_gpu.py --deselect tests/test_z6_shapes_gpu.py \
     > gpurun_out/pytest_gpu.log 2>&1; echo "pytest (established) exit $?"; tail -3 gpurun_out/pytest_gpu.log
 timeout 400 python -m pytest tests/test_z4_clip_gpu.py -q -x > gpurun_out/pytest_zclip.log 2>&1; echo "pytest zclip exit $?"; tail -15 gpurun_out/pytest_zclip.log
 timeout 400 python -m pytest tests/test_z5_vae_gpu.py -q -x > gpurun_out/pytest_zvae.log 2>&1; echo "pytest zvae exit $?"; tail -15 gpurun_out/pytest_zvae.log
 timeout 400 python -m pytest tests/test_z3_dense_gpu.py -q -x > gpurun_out/pytest_zdense.log 2>&1; echo "pytest zdense exit $?"; tail -15 gpurun_out/pytest_zdense.log
-timeout 300 python -m pytest tests/test_z2_prodigy_gpu.py tests/test_z1_train_gpu.py -q > gpurun_out/pytest_zprodigy_ztrain.log 2>&1; echo "pytest zprodigy+ztrain exit $?"; tail -8 gpurun_out/pytest_zprodigy_ztrain.log
+timeout 300 python -m pytest tests/test_z2_prodigy_gpu.py tests/test_z1_train_gpu.py tests/test_z6_shapes_gpu.py -q > gpurun_out/pytest_zprodigy_ztrain.log 2>&1; echo "pytest zprodigy+ztrain exit $?"; tail -8 gpurun_out/pytest_zprodigy_ztrain.log
 timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 echo "bench default exit $?"; cut -c1-300 gpurun_out/bench_default.json
 B200_NATIVE_CLIP=1 timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu --skip-roofline > gpurun_out/bench_native_clip.json 2> gpurun_out/bench_native_clip.err

@@ -51,42 +51,3 @@ def test_train_generator_on_gpu(tmp_path, family, graph):
     assert not torch.equal(fresh.store.params, before)          # trained factors differ from a fresh init
     assert float(fresh.store.params[:fresh.store.n_lora].float().abs().max()) > 0
 
-
-def test_rank64_step_matches_oracle():
-    """train_configs/training_args_style_sd15_noti.json: LoRA rank 64 (> the in-kernel side path's 32), disable_ti: the
-    two-launch LoRA form of the linear layers on the real kernels; the conditioning cache serves the second step."""
-    from tests.test_unet_gpu import _build, _product, rel
-    cfg, orc, inputs = _build("sd15", rank=64, batch=2, disable_ti=True)
-    tr = _product(cfg, orc)
-    out_o = orc.step(inputs, completion_f=0.0, do_optimizer=False)
-    out_p = tr.step(inputs, completion_f=0.0, do_optimizer=False)
-    torch.cuda.synchronize()
-    a, b = float(out_p["tot_loss"]), float(out_o["tot_loss"])
-    assert abs(a - b) / abs(b) <= 1e-2, (a, b)
-    ours = tr.store.export_peft(grads=True)
-    bad = [(n, rel(ours[n].reshape(p.grad.shape), p.grad)) for n, p in orc.unet.named_parameters() if p.grad is not None]
-    assert len(bad) == 2 * len(tr.store.slots) and not [x for x in bad if x[1] > 0.3], [x for x in bad if x[1] > 0.3][:5]
-    g1 = tr.store.grads.clone()
-    tr.store.grads.zero_()
-    out_2 = tr.step(inputs, completion_f=0.0, do_optimizer=False)            # captions come from the conditioning cache
-    torch.cuda.synchronize()
-    # (split-K atomics / stream-K reduce-adds make the kernels' summation order run-dependent: closeness, not identity)
-    assert len(tr._text_cache) == 2 and abs(float(out_2["tot_loss"]) - a) <= 1e-3 * abs(a) and rel(tr.store.grads, g1) < 1e-2
-
-
-@pytest.mark.parametrize("family,hw", [("sd15", 12), ("sdxl", 24)])
-def test_latent_width_that_does_not_divide_128(family, hw):
-    """768x768 training (training_args_face_sd15.json) has 96 / 48 / 24 / 12-wide maps, which the implicit-convolution
-    TMA boxes do not tile: every 3x3 convolution, its input gradient and the conv-LoRA take the im2col / col2im path."""
-    from tests.test_unet_gpu import _build, _product, rel
-    cfg, orc, inputs = _build(family, rank=8, batch=1, hw=hw)
-    tr = _product(cfg, orc)
-    out_o = orc.step(inputs, completion_f=0.0, do_optimizer=False)
-    out_p = tr.step(inputs, completion_f=0.0, do_optimizer=False)
-    torch.cuda.synchronize()
-    for key in ("img_loss", "token_attention_loss", "tot_loss"):
-        a, b = float(out_p[key]), float(out_o[key])
-        assert abs(a - b) / abs(b) <= 2e-3, f"{key}: ours {a} vs bf16 oracle {b}"
-    ours = tr.store.export_peft(grads=True)
-    bad = [(n, rel(ours[n].reshape(p.grad.shape), p.grad)) for n, p in orc.unet.named_parameters() if p.grad is not None]
-    assert not [x for x in bad if x[1] > 0.25], [x for x in bad if x[1] > 0.25][:5]
