@@ -219,3 +219,33 @@ def test_unet_lr_zero_means_no_unet_update():
     from sd_lora_trainer_b200.step import StepConfig, lr_schedule
     cfg = StepConfig(unet_lr=0.0)
     assert lr_schedule(cfg, 0, 0.0)[1] == 0.0 and lr_schedule(cfg, 10, 0.1)[1] == 0.0
+
+
+@pytest.mark.parametrize("family,rank,n_tokens", [("sd15", 6, 4), ("sdxl", 20, 2)])
+def test_odd_rank_and_token_count(monkeypatch, family, rank, n_tokens):
+    """predict.py lets lora_rank be any integer and n_tokens 1..4: ranks that are not multiples of 8 (padded slots) and
+    other token counts through one full step incl. the optimizer."""
+    cpu_mock_ops.install(monkeypatch)
+    from oracle.step import OracleTrainer, StepConfig, make_inputs
+    from oracle.text import build_text_encoders
+    from sd_lora_trainer_b200.step import StepConfig as PCfg, TrainerB200
+    cfg = StepConfig(family=family, tiny=True, resolution=64, lora_rank=rank, n_tokens=n_tokens)
+    orc = OracleTrainer(cfg, device="cpu")
+    g = torch.Generator().manual_seed(7)
+    for n, p in orc.unet.named_parameters():
+        if "lora_B" in n:
+            p.data.copy_((torch.randn(p.shape, generator=g) * 0.05).to(BF))
+    inputs = make_inputs(cfg, batch=2, latent_hw=8, face_mask=True, train_ids=orc.train_ids)
+    pcfg = PCfg(**{k: getattr(cfg, k) for k in PCfg.__dataclass_fields__ if hasattr(cfg, k)})
+    ti_init = [te.text_model.embeddings.token_embedding.weight.data[-n_tokens:].clone() for te in orc.text_encoders if te is not None]
+    tr = TrainerB200(pcfg, orc.unet.state_dict(), build_text_encoders(family, True, seed=cfg.seed + 1), device="cpu", ti_init=ti_init)
+    assert all(r.shape[0] == n_tokens for r in tr.ti_rows) and all(s.rs == (rank + 7) // 8 * 8 for s in tr.store.slots)
+    out_o, out_p = orc.step(inputs), tr.step(inputs)
+    a, b = float(out_p["tot_loss"]), float(out_o["tot_loss"])
+    assert abs(a - b) / abs(b) <= 3e-3, (a, b)
+    after = tr.store.export_peft()
+    for n, p in orc.unet.named_parameters():
+        if "lora_" in n:
+            assert rel(after[n].reshape(p.shape), p) < 2e-3, n          # same AdamW step from nearly equal gradients
+    for s in tr.store.slots:
+        assert float(s.B()[:, s.r:].abs().max()) == 0.0 if s.rs > s.r else True      # rank padding never leaves zero
