@@ -134,6 +134,16 @@ class TrainerB200:
                 self.train_ids = list(range(vocab, vocab + ntok))
                 off += ntok * dim
             self.unet.set_capture(True)                        # init_daam_loss, main.py:50-52
+        # disable_ti: the reference still ADDS the tokens (main.py:92-100 runs unconditionally) - their rows are initialised
+        # and simply never trained, and captions / caption dropout (main.py:302-305) keep using their ids
+        self.frozen_rows: List[torch.Tensor] = []
+        if cfg.disable_ti and cfg.n_tokens > 0:
+            g = torch.Generator().manual_seed(cfg.seed)
+            for i, te in enumerate(t for t in self.text_encoders if t is not None):
+                table = te.text_model.embeddings.token_embedding.weight.data
+                rows = (ti_init[i].to(self.device, BF16) if ti_init is not None else init_ti_rows(table, cfg.n_tokens, g)).detach()
+                install_ti_rows(te, rows)
+                self.frozen_rows.append(rows)
         # Text encoders: stock transformers modules under autograd (default), or the explicit fwd/bwd executor over
         # our kernels (clip.py; B200_NATIVE_CLIP=1 / native_text=True).
         if native_text is None:
@@ -144,7 +154,7 @@ class TrainerB200:
         self.text = None
         if native_text and self.text_encoders[0] is not None:
             from .clip import TextStackB200
-            self.text = TextStackB200(self.sdxl, self.text_encoders, self.ti_rows, self.device)
+            self.text = TextStackB200(self.sdxl, self.text_encoders, self.ti_rows or self.frozen_rows, self.device)
         self._prodigy = {}                                     # segment -> (lo, hi, scalars, hyper_host, hyper_dev, kwargs)
         segs = []
         if cfg.unet_optimizer_type == "prodigy":

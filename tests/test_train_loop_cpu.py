@@ -143,3 +143,35 @@ def test_training_config_json_roundtrip(tmp_path):
     assert cfg.checkpointing_steps == 300 and cfg.name == "y.zip"
     cfg.save_as_json(str(p))
     assert json.load(open(p))["lora_rank"] == 16
+
+
+def test_train_full_finetune_like_the_reference_example(monkeypatch, tmp_path):
+    """train_configs/full_finetuning_example.json in miniature: is_lora=false, disable_ti=true, AdamW8bit (a declared
+    substitution: AdamW with bf16 moments, announced by a warning); the checkpoint is a diffusers UNet folder."""
+    cpu_mock_ops.install(monkeypatch)
+    from safetensors.torch import load_file
+    from oracle.text import build_text_encoders
+    from sd_lora_trainer_b200.arch import by_name
+    from sd_lora_trainer_b200.init import random_state_dict
+    from sd_lora_trainer_b200.main import TrainingConfig, train
+    cfg = TrainingConfig(lora_training_urls="ft/stitchly", concept_mode="style", sd_model_version="sd15", seed=1, resolution=64,
+                         train_batch_size=2, max_train_steps=3, is_lora=False, disable_ti=True, unet_optimizer_type="AdamW8bit",
+                         unet_lr=1e-4, lora_rank=4, output_dir=str(tmp_path), device="cpu", caption_dropout=0.2)
+    sd = random_state_dict(by_name("tiny_sd15"), seed=0, device="cpu")
+    gen = train(cfg, _dataset(4, 8, tok="stitchly"), build_text_encoders("sd15", tiny=True, seed=2), sd, _tokenize_factory("sd15"),
+                tiny=True)
+    with pytest.warns(UserWarning, match="AdamW8bit"):
+        try:
+            while True:
+                next(gen)
+        except StopIteration as stop:
+            out_cfg, out_dir = stop.value
+    assert sorted(os.listdir(out_dir)) == ["config.json", "diffusion_pytorch_model.safetensors", "special_params.json",
+                                           "training_args.json"]
+    trained = load_file(os.path.join(out_dir, "diffusion_pytorch_model.safetensors"))
+    assert set(trained) == set(sd) and all(trained[k].shape == sd[k].shape for k in sd)
+    changed = sum(int(not torch.equal(trained[k], sd[k])) for k in sd)
+    # most tensors moved; bf16 norm weights sitting at 1.0 (ulp 0.0078) swallow steps of 1e-4, in the reference too
+    assert changed > 0.7 * len(sd)
+    hist = json.load(open(os.path.join(out_dir, "training_args.json")))["training_attributes"]["losses"]
+    assert len(hist["tot_loss"]) == 4 and hist["token_attention_loss"] == [] and hist["tot_loss"] == hist["img_loss"]
