@@ -33,7 +33,7 @@ class StepConfig:
     tiny: bool = False
     resolution: int = 1024
     lora_rank: int = 16
-    is_lora: bool = True               # False: full-UNet fine-tune (BASELINE config 5; needs disable_ti=True here)
+    is_lora: bool = True               # False: full-UNet fine-tune (main.py:143-148; BASELINE config 5)
     lora_alpha_multiplier: float = 1.0
     lora_weight_decay: float = 0.004
     unet_lr: float = 0.0003
@@ -50,7 +50,7 @@ class StepConfig:
     unet_lr_warmup_steps: Optional[int] = None
     freeze_ti_after_completion_f: float = 0.7
     freeze_unet_before_completion_f: float = 0.0
-    unet_optimizer_type: str = "adamw"       # "adamw" | "prodigy" (trainer/optimizer.py:6-39); AdamW8bit: not built
+    unet_optimizer_type: str = "adamw"       # "adamw" | "prodigy" | "AdamW8bit" -> AdamW (trainer/optimizer.py:6-39)
     ti_optimizer: str = "adamw"              # "adamw" | "prodigy" (trainer/optimizer.py:107-155)
     prodigy_d_coef: float = 1.0
     unet_prodigy_growth_factor: float = 1.05
