@@ -224,7 +224,14 @@ def run_ours(args):
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(prof["by_shape"], open(os.path.join(ROOT, "gpurun_out", "gemm_by_shape.json"), "w"), indent=1)
     if rank == 0 and world == 1 and not args.skip_cpu:
-        result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
+        keep = None if args.full_ft else {}                    # (full fine-tune: the snapshot would copy every weight)
+        result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0, keep=keep)
+        if keep is not None:
+            try:                                                # never lose the measured line to this extra leg
+                result["step_loss_delta"] = step_loss_delta(keep, dev)
+            except Exception as e:                              # noqa: BLE001
+                result["step_loss_delta"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        del keep
     if rank == 0:
         print(json.dumps(result), flush=True)
     faulthandler.cancel_dump_traceback_later()
@@ -250,7 +257,7 @@ def run_ours(args):
         os._exit(0)
 
 
-def cpu_baseline(args, steps: int, warmup: int):
+def cpu_baseline(args, steps: int, warmup: int, keep=None):
     """The oracle (a port of the reference step, oracle/) on the host cores: SAME model and config, batch 1 so that a
     step stays bounded.  fp32 on the CPU - the reference's bf16 path is several times slower there (no AMX needed)."""
     from oracle.step import OracleTrainer, StepConfig as OCfg, make_inputs
@@ -260,6 +267,16 @@ def cpu_baseline(args, steps: int, warmup: int):
                is_lora=not args.full_ft, disable_ti=args.full_ft)
     t0 = time.time()
     orc = OracleTrainer(cfg, device="cpu")
+    if keep is not None:
+        # the oracle computes in fp32 on the values bf16 weights hold (what the GPU step loads), so that the two losses
+        # differ by arithmetic only; the trainable tensors are snapshotted because the timed step updates them
+        with torch.no_grad():
+            for mod in [orc.unet] + [te for te in orc.text_encoders if te is not None]:
+                for p_ in mod.parameters():
+                    p_.copy_(p_.to(torch.bfloat16).to(p_.dtype))
+        keep["pre"] = {n: p_.detach().clone() for n, p_ in orc.unet.named_parameters() if p_.requires_grad}
+        keep["ti"] = [te.text_model.embeddings.token_embedding.weight.data[-cfg.n_tokens:].clone()
+                      for te in orc.text_encoders if te is not None] if not cfg.disable_ti else None
     build_s = time.time() - t0
     inp = make_inputs(cfg, batch=args.cpu_batch, face_mask=True, train_ids=orc.train_ids or None)
     for _ in range(warmup):
@@ -269,11 +286,37 @@ def cpu_baseline(args, steps: int, warmup: int):
         out = orc.step(inp)
         float(out["tot_loss"])
     dt = time.time() - t0
+    if keep is not None:
+        keep.update(orc=orc, cfg=cfg, inputs=inp, loss=float(out["tot_loss"]), img_loss=float(out["img_loss"]))
     return {"value": args.cpu_batch * steps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{steps} step(s) of the same SDXL r={args.rank} face+TI step, batch {args.cpu_batch}, "
                       f"{args.cpu_res}x{args.cpu_res}, {args.cpu_dtype} oracle on the host cores (fwd+bwd+AdamW), "
                       f"build {build_s:.0f}s not timed",
             "seconds": dt}
+
+
+def step_loss_delta(keep, dev):
+    """BASELINE.json metric, second half ("step-loss delta vs ref") at FULL size: the GPU step on the oracle's own
+    weights (bf16 values), token rows and inputs - the state the oracle's timed step started from - against the loss that
+    step reported.  Oracle: fp32 arithmetic on the host; GPU: bf16 kernels with fp32 accumulation."""
+    from oracle.text import build_text_encoders
+    from sd_lora_trainer_b200.step import StepConfig, TrainerB200
+    orc, ocfg = keep["orc"], keep["cfg"]
+    sd = dict(orc.unet.state_dict())
+    sd.update(keep["pre"])                                     # trainable tensors as they were before the oracle's update
+    pcfg = StepConfig(**{k: getattr(ocfg, k) for k in StepConfig.__dataclass_fields__ if hasattr(ocfg, k)})
+    tes = build_text_encoders(ocfg.family, ocfg.tiny, seed=ocfg.seed + 1)       # the seed OracleTrainer builds them with
+    tr2 = TrainerB200(pcfg, sd, tes, device=dev, ti_init=keep["ti"])
+    tr2.cache_text = False
+    out = tr2.step(keep["inputs"], completion_f=0.0, do_optimizer=False)
+    a, b = float(out["tot_loss"]), keep["loss"]
+    ai, bi = float(out["img_loss"]), keep["img_loss"]
+    del tr2
+    torch.cuda.empty_cache()
+    return {"ours": a, "oracle_fp32_cpu": b, "rel": abs(a - b) / abs(b), "img_loss_ours": ai, "img_loss_oracle": bi,
+            "img_loss_rel": abs(ai - bi) / abs(bi), "config": f"same {ocfg.family} r={ocfg.lora_rank} step, batch "
+            f"{keep['inputs']['vae_latent'].shape[0]}, {ocfg.resolution}x{ocfg.resolution}, identical weights / rows / inputs",
+            "north_star_bound": 1e-3}
 
 
 def run_reference(args):
