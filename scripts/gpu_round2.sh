@@ -17,6 +17,8 @@ B200_NATIVE_CLIP=1 timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu 
 echo "bench native clip exit $?"; cut -c1-300 gpurun_out/bench_native_clip.json; tail -3 gpurun_out/bench_native_clip.err
 timeout 500 python bench.py --full-ft --batch 1 --steps 5 --warmup 3 --skip-cpu --no-graph > gpurun_out/bench_full_ft.json 2> gpurun_out/bench_full_ft.err
 echo "bench full-ft (BASELINE config 5) exit $?"; cut -c1-300 gpurun_out/bench_full_ft.json; tail -3 gpurun_out/bench_full_ft.err
+B200_SHARED_DSCORES=1 timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu --skip-roofline > gpurun_out/bench_shared_dscores.json 2> gpurun_out/bench_shared_dscores.err
+echo "bench shared dscores exit $?"; cut -c1-300 gpurun_out/bench_shared_dscores.json
 timeout 300 python bench.py --family sd15 --res 512 --batch 4 --rank 16 --steps 10 --warmup 3 --skip-cpu --skip-roofline > gpurun_out/bench_config2_sd15.json 2> gpurun_out/bench_config2_sd15.err
 echo "bench BASELINE config 2 (SD1.5 r16 512 B4) exit $?"; cut -c1-300 gpurun_out/bench_config2_sd15.json
 timeout 300 python bench.py --rank 32 --steps 10 --warmup 3 --skip-cpu --skip-roofline > gpurun_out/bench_config4_r32_1gpu.json 2> gpurun_out/bench_config4_r32_1gpu.err

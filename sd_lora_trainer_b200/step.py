@@ -148,6 +148,8 @@ class TrainerB200:
         # our kernels (clip.py; B200_NATIVE_CLIP=1 / native_text=True).
         if native_text is None:
             native_text = os.environ.get("B200_NATIVE_CLIP", "0") == "1"
+        # token-attention backward with one shared gradient map per resolution (off until measured on the GPU)
+        self.shared_dscores = os.environ.get("B200_SHARED_DSCORES", "0") == "1"
         # conditioning cache for the phases without a trainable token row (B200_TEXT_CACHE=0 turns it off)
         self.cache_text = os.environ.get("B200_TEXT_CACHE", "1") != "0"
         self._text_cache: Dict[tuple, tuple] = {}
@@ -299,10 +301,13 @@ class TrainerB200:
         total = img_loss.clone()
         dscores = None
         if not cfg.disable_ti:
-            leaves = [s.detach().requires_grad_(True) for s in scores]
-            tal = token_attention_loss_tensors(leaves, mask, st["tok_len"], st["ti_pos"])
-            (cfg.token_attention_loss_w * tal / ga).backward()
-            dscores = [l.grad if l.grad is not None else torch.zeros_like(l) for l in leaves]
+            if self.shared_dscores:
+                tal, dscores = self._token_attention_shared(scores, mask, st["tok_len"], st["ti_pos"], ga)
+            else:
+                leaves = [s.detach().requires_grad_(True) for s in scores]
+                tal = token_attention_loss_tensors(leaves, mask, st["tok_len"], st["ti_pos"])
+                (cfg.token_attention_loss_w * tal / ga).backward()
+                dscores = [l.grad if l.grad is not None else torch.zeros_like(l) for l in leaves]
             out["token_attention_loss"] = tal.detach()
             out["attention_scores"] = scores
             total = total + cfg.token_attention_loss_w * tal.detach().float()
@@ -342,6 +347,37 @@ class TrainerB200:
                 off += n
         out["tot_loss"] = total
         return out
+
+    def _token_attention_shared(self, scores, mask, tok_len, ti_pos, ga):
+        """B200_SHARED_DSCORES=1: the regulariser only sees the mean of the stacked maps over layers, so every hooked layer
+        of a resolution receives the SAME gradient map.  Differentiate once with the stacked tensor as the leaf, pad that
+        one map to the score buffers' 80-column rows and hand the same tensor to every layer (one bicubic adjoint for the
+        layers that were resized) - instead of 60 per-layer gradients, 60 zero-fill + copy pairs and 10 bicubic adjoints.
+        Values are identical to the per-layer path."""
+        import torch.nn.functional as F
+        from .trainer.loss import process_and_stack_attention_scores, token_attention_loss_from_maps
+        img_ratio = mask.shape[-1] / mask.shape[-2]
+        with torch.no_grad():
+            maps = process_and_stack_attention_scores([s.detach() for s in scores], img_ratio)
+        maps.requires_grad_(True)
+        tal = token_attention_loss_from_maps(maps, mask, tok_len, ti_pos)
+        (self.cfg.token_attention_loss_w * tal / ga).backward()
+        n_text = maps.shape[-1]
+        pad = (n_text + 7) // 8 * 8 - n_text
+        if maps.grad is None:
+            return tal, [torch.zeros_like(s) for s in scores]
+        G = maps.grad[0]                                          # [B, h, w, 77]; maps.grad[l] is the same for every l
+        Bsz, h, w = G.shape[:3]
+        shared = {h * w: F.pad(G.reshape(Bsz, h * w, n_text), (0, pad))}
+        out = []
+        for s in scores:
+            L = s.shape[1]
+            if L not in shared:                                   # a layer that was bicubic-resized down to (h, w)
+                wi = round((L * img_ratio) ** 0.5)
+                hi = round(wi / img_ratio)
+                shared[L] = F.pad(ops.bicubic_bwd(G, hi, wi).reshape(Bsz, L, n_text), (0, pad))
+            out.append(shared[L])
+        return tal, out
 
     # ---- optimizer: ONE kernel over LoRA factors + TI rows -------------------------------------------
     def _l1_coeff(self) -> float:

@@ -93,9 +93,16 @@ def token_attention_loss_tensors(scores: Sequence[torch.Tensor], masks: torch.Te
                                  ti_pos: torch.Tensor) -> torch.Tensor:
     """trainer/loss.py:10-80 with the per-caption Python loop replaced by index tensors (same arithmetic, same
     dtypes), so the whole regulariser is shape-static and can sit inside a CUDA graph."""
-    masks = masks[:, 0].float()
     img_ratio = masks.shape[-1] / masks.shape[-2]
     maps = process_and_stack_attention_scores(scores, img_ratio)              # [layers, B, h, w, 77]
+    return token_attention_loss_from_maps(maps, masks, tok_len, ti_pos)
+
+
+def token_attention_loss_from_maps(maps: torch.Tensor, masks: torch.Tensor, tok_len: torch.Tensor,
+                                   ti_pos: torch.Tensor) -> torch.Tensor:
+    """The regulariser on the stacked maps [layers, B, h, w, 77] (everything after ti_cross_attn_loss.py:239-268).  It sees
+    the maps only through their mean over layers (and over pixels), so its gradient is the same map for every layer."""
+    masks = masks[:, 0].float()
     n_layers, B, h, w, n_text = maps.shape
     masks = F.interpolate(masks.unsqueeze(1), size=(h, w)).squeeze(1)         # [B, h, w] (nearest)
     # (1) mean attention of every real caption token (positions 1 .. len-2)

@@ -579,8 +579,11 @@ class Attn:
                                   Mat(q, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
                      d_strides=(C, 1, d, Lk * C), alpha=scale, nb0=H, nb1=B)
         if dscores is not None:
-            dsc = torch.zeros(B, L, Lp, dtype=BF16, device=dev)
-            dsc[:, :, :Lk] = dscores
+            if dscores.shape[-1] == Lp and dscores.is_contiguous():
+                dsc = dscores                              # already in the padded row layout (shared across layers; read-only)
+            else:
+                dsc = torch.zeros(B, L, Lp, dtype=BF16, device=dev)
+                dsc[:, :, :Lk] = dscores
             ops.gemm(dQ, L, C, [(Mat(dsc, L, Lk, Lp, sb1=L * Lp, batched=True),
                                  Mat(k, Lk, C, C, mn=True, sb1=Lk * C, batched=True), Lk)],
                      d_strides=(C, 1, 0, L * C), alpha=scale, residual=dQ, r_strides=(C, 1, 0, L * C), nb0=1, nb1=B)

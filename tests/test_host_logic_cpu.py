@@ -249,3 +249,21 @@ def test_odd_rank_and_token_count(monkeypatch, family, rank, n_tokens):
             assert rel(after[n].reshape(p.shape), p) < 2e-3, n          # same AdamW step from nearly equal gradients
     for s in tr.store.slots:
         assert float(s.B()[:, s.r:].abs().max()) == 0.0 if s.rs > s.r else True      # rank padding never leaves zero
+
+
+@pytest.mark.parametrize("family,hw", [("sdxl", 8), ("sd15", 12)])
+def test_shared_dscores_path_is_value_identical(monkeypatch, family, hw):
+    """B200_SHARED_DSCORES=1: one gradient map per resolution handed to every hooked layer (the regulariser only sees the
+    layer mean) must reproduce the per-layer autograd path bit for bit: losses, LoRA gradients, token-row gradients."""
+    cpu_mock_ops.install(monkeypatch)
+    cfg, orc, tr_a, inputs = _setup(family, 8, 2, hw)
+    out_a = tr_a.step(inputs, do_optimizer=False)
+    monkeypatch.setenv("B200_SHARED_DSCORES", "1")
+    cfg, orc, tr_b, inputs = _setup(family, 8, 2, hw)
+    assert tr_b.shared_dscores and not tr_a.shared_dscores
+    sizes = {s.shape[1] for s in out_a["attention_scores"]}
+    assert len(sizes) >= 2                                       # at least one resolution goes through the bicubic adjoint
+    out_b = tr_b.step(inputs, do_optimizer=False)
+    for k in ("img_loss", "token_attention_loss", "token_std_loss", "tot_loss"):
+        assert float(out_a[k]) == float(out_b[k]), k
+    assert torch.equal(tr_a.store.grads, tr_b.store.grads)

@@ -45,3 +45,20 @@ def test_latent_width_that_does_not_divide_128(family, hw):
     ours = tr.store.export_peft(grads=True)
     bad = [(n, rel(ours[n].reshape(p.grad.shape), p.grad)) for n, p in orc.unet.named_parameters() if p.grad is not None]
     assert not [x for x in bad if x[1] > 0.25], [x for x in bad if x[1] > 0.25][:5]
+
+
+def test_shared_dscores_path_matches_per_layer_path(monkeypatch):
+    """B200_SHARED_DSCORES=1 on the real kernels: same losses and gradients as the per-layer autograd path (closeness: the
+    weight-gradient atomics sum in a run-dependent order)."""
+    from tests.test_unet_gpu import _build, _product, rel
+    cfg, orc, inputs = _build("sdxl", rank=8, batch=2)
+    tr_a = _product(cfg, orc)
+    out_a = tr_a.step(inputs, completion_f=0.0, do_optimizer=False)
+    monkeypatch.setenv("B200_SHARED_DSCORES", "1")
+    tr_b = _product(cfg, orc)
+    assert tr_b.shared_dscores and not tr_a.shared_dscores
+    out_b = tr_b.step(inputs, completion_f=0.0, do_optimizer=False)
+    torch.cuda.synchronize()
+    for k in ("img_loss", "token_attention_loss", "tot_loss"):
+        assert abs(float(out_a[k]) - float(out_b[k])) <= 1e-4 * abs(float(out_a[k])), k
+    assert rel(tr_b.store.grads, tr_a.store.grads) < 1e-2
