@@ -194,7 +194,8 @@ def run_ours(args):
                                    f"bf16 batch {B}/GPU, fwd+bwd+AdamW, random-init full-size weights",
                        "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "working set (5 GB weights + ~25 GB activations per step) exceeds the 126 MB L2",
-                       "cuda_graph": not args.no_graph, "text_encoders": "native" if tr.text is not None else "transformers"},
+                       "cuda_graph": not args.no_graph, "text_encoders": "native" if tr.text is not None else "transformers",
+                       "shared_dscores": bool(tr.shared_dscores)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": tr.h2d_bytes_last, "d2h_bytes_per_step": 4},
