@@ -225,14 +225,26 @@ def run_ours(args):
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(prof["by_shape"], open(os.path.join(ROOT, "gpurun_out", "gemm_by_shape.json"), "w"), indent=1)
     if rank == 0 and world == 1 and not args.skip_cpu:
-        keep = None if args.full_ft else {}                    # (full fine-tune: the snapshot would copy every weight)
-        result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0, keep=keep)
-        if keep is not None:
-            try:                                                # never lose the measured line to this extra leg
-                result["step_loss_delta"] = step_loss_delta(keep, dev)
-            except Exception as e:                              # noqa: BLE001
-                result["step_loss_delta"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        del keep
+        # CPU baseline + full-size step-loss delta in a CHILD process with a timeout: a fault or a hang in that extra leg
+        # (it runs GPU shapes - batch 1 - that the timed workload does not) cannot cost the measured line.  The parent is
+        # idle meanwhile, so the oracle has the host cores to itself.  (Full fine-tune: no delta leg, in-process baseline.)
+        child = None
+        if not args.full_ft:
+            try:
+                cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--delta-only", "--family", args.family,
+                                     "--rank", str(args.rank), "--cpu-res", str(args.cpu_res), "--cpu-batch", str(args.cpu_batch),
+                                     "--cpu-dtype", args.cpu_dtype], capture_output=True, text=True, timeout=args.delta_timeout)
+                lines = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")]
+                child = json.loads(lines[-1]) if lines else None
+                child_err = None if child else f"exit {cp.returncode}: {cp.stderr[-300:]}"
+            except Exception as e:                              # noqa: BLE001  (timeout, launch failure, bad output)
+                child_err = f"{type(e).__name__}: {e}"[:300]
+        if child is not None:
+            result["cpu_baseline"], result["step_loss_delta"] = child["cpu_baseline"], child["step_loss_delta"]
+        else:
+            result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
+            if not args.full_ft:
+                result["step_loss_delta"] = {"error": child_err}
     if rank == 0:
         print(json.dumps(result), flush=True)
     faulthandler.cancel_dump_traceback_later()
@@ -290,7 +302,7 @@ def cpu_baseline(args, steps: int, warmup: int, keep=None):
     if keep is not None:
         keep.update(orc=orc, cfg=cfg, inputs=inp, loss=float(out["tot_loss"]), img_loss=float(out["img_loss"]))
     return {"value": args.cpu_batch * steps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} step(s) of the same SDXL r={args.rank} face+TI step, batch {args.cpu_batch}, "
+            "sample": f"{steps} step(s) of the same {args.family.upper()} r={args.rank} face+TI step, batch {args.cpu_batch}, "
                       f"{args.cpu_res}x{args.cpu_res}, {args.cpu_dtype} oracle on the host cores (fwd+bwd+AdamW), "
                       f"build {build_s:.0f}s not timed",
             "seconds": dt}
@@ -318,6 +330,17 @@ def step_loss_delta(keep, dev):
             "img_loss_rel": abs(ai - bi) / abs(bi), "config": f"same {ocfg.family} r={ocfg.lora_rank} step, batch "
             f"{keep['inputs']['vae_latent'].shape[0]}, {ocfg.resolution}x{ocfg.resolution}, identical weights / rows / inputs",
             "north_star_bound": 1e-3}
+
+
+def run_delta_only(args):
+    """Child process of the default run: the bounded CPU-oracle step, then the GPU step on the oracle's own state."""
+    keep = {}
+    cb = cpu_baseline(args, steps=1, warmup=0, keep=keep)
+    try:
+        delta = step_loss_delta(keep, "cuda:0")
+    except Exception as e:                                      # noqa: BLE001
+        delta = {"error": f"{type(e).__name__}: {e}"[:300]}
+    print(json.dumps({"cpu_baseline": cb, "step_loss_delta": delta}), flush=True)
 
 
 def run_reference(args):
@@ -360,9 +383,13 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=1)
     ap.add_argument("--cpu-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--ref-max-steps", type=int, default=10)
+    ap.add_argument("--delta-only", action="store_true", help="internal: CPU baseline + step-loss delta, printed as JSON")
+    ap.add_argument("--delta-timeout", type=int, default=600, help="seconds granted to the --delta-only child process")
     ap.add_argument("--watchdog", type=int, default=1500, help="seconds after which a stuck run dumps its stacks and exits 1")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.delta_only:
+        run_delta_only(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
