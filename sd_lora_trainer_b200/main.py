@@ -177,7 +177,10 @@ def train(config: TrainingConfig, dataset, text_encoders: Sequence, unet_state_d
     dataset: ``len()`` / ``[i] -> (caption, vae_latent [4, h, w] fp32 already scaled, mask [4, h, w])``
              (``trainer.dataset.CachedLatentDataset``).
     tokenize: captions -> ([B, 77] int64 ids per text encoder, the unpadded id list of every caption as
-              ``pipe.tokenizer.encode`` returns it - trainer/loss.py:33)."""
+              ``pipe.tokenizer.encode`` returns it - trainer/loss.py:33).
+    text_encoders: (CLIPTextModel, CLIPTextModelWithProjection | None) with their ORIGINAL embedding tables: ids at or beyond
+             the table's row count address the ``n_tokens`` trainable rows (the tokenizer has the new tokens, the encoders are
+             not resized)."""
     _check_supported(config)
     # data parallel (SURVEY.md 8e): one process per GPU, every rank runs this generator; a step's global batch is
     # train_batch_size x world images, the shuffle is shared (seeded by config.seed), the random draws are per rank
