@@ -292,6 +292,9 @@ def cpu_baseline(args, steps: int, warmup: int, keep=None):
                       for te in orc.text_encoders if te is not None] if not cfg.disable_ti else None
     build_s = time.time() - t0
     inp = make_inputs(cfg, batch=args.cpu_batch, face_mask=True, train_ids=orc.train_ids or None)
+    if keep is not None:                                       # inputs at the values the bf16 step sees (main.py:311-312)
+        for k in ("vae_latent", "noise"):
+            inp[k] = inp[k].to(torch.bfloat16).to(inp[k].dtype)
     for _ in range(warmup):
         orc.step(inp)
     t0 = time.time()
