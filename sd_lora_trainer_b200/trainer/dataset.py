@@ -11,6 +11,21 @@ import torch
 from .. import ops
 
 
+def prepare_captions(captions: Sequence[Optional[str]], substitute_caption_map: Optional[dict] = None):
+    """dataset.py:46-52: captions are lower-cased, every key of ``substitute_caption_map`` (``config.token_dict``:
+    {"TOK": "<s0><s1><s2>"}) is replaced - key lower-cased too - by its value, missing captions become ''."""
+    out = []
+    for c in captions:
+        if c is None or (isinstance(c, float) and c != c):
+            out.append("")
+            continue
+        c = str(c).lower()
+        for key, value in (substitute_caption_map or {}).items():
+            c = c.replace(key.lower(), value)
+        out.append(c)
+    return out
+
+
 class CachedLatentDataset:
     """``PreprocessedDataset`` with ``do_cache=True`` after its constructor ran: captions, posterior parameters, masks."""
 
@@ -24,7 +39,8 @@ class CachedLatentDataset:
 
     @classmethod
     def from_images(cls, vae_encoder, captions: Sequence[str], images: Sequence[torch.Tensor],
-                    masks: Optional[Sequence[Optional[torch.Tensor]]], vae_scaling_factor: float) -> "CachedLatentDataset":
+                    masks: Optional[Sequence[Optional[torch.Tensor]]], vae_scaling_factor: float,
+                    substitute_caption_map: Optional[dict] = None) -> "CachedLatentDataset":
         """The constructor's caching pass (dataset.py:85-99 -> ``_process`` 141-179): every image ([3, H, W] in [-1, 1],
         what ``prepare_image`` returns) goes through the VAE encoder once and its posterior parameters are kept; a mask
         ([1, H, W] or [H, W] in [0, 1], what ``prepare_mask`` returns) is resized to the latent grid with nearest
@@ -42,6 +58,8 @@ class CachedLatentDataset:
                 m = torch.nn.functional.interpolate(m, size=(h, w), mode="nearest").repeat(1, c, 1, 1).squeeze(0)
             params.append(p)
             out_masks.append(m)
+        if substitute_caption_map is not None:
+            captions = prepare_captions(captions, substitute_caption_map)
         return cls(captions, params, out_masks, vae_scaling_factor)
 
     def __len__(self) -> int:

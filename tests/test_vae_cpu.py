@@ -146,3 +146,11 @@ def test_vae_param_shapes_match_oracle_state_dict(tiny):
     if tiny:
         sd = random_vae_encoder_state_dict(seed=1, **kw)
         assert float(sd["encoder.conv_norm_out.weight"].min()) == 1.0 and float(sd["encoder.conv_in.weight"].abs().max()) <= 27 ** -0.5
+
+
+def test_prepare_captions_like_the_reference_dataset():
+    """dataset.py:46-52: lower-case, TOK substitution (key lower-cased), missing caption -> ''."""
+    from sd_lora_trainer_b200.trainer.dataset import prepare_captions
+    got = prepare_captions(["A photo of TOK, smiling", "tok and TOK", None, float("nan"), "No Token Here"], {"TOK": "<s0><s1><s2>"})
+    assert got == ["a photo of <s0><s1><s2>, smiling", "<s0><s1><s2> and <s0><s1><s2>", "", "", "no token here"]
+    assert prepare_captions(["Keep CASE?"], None) == ["keep case?"]
