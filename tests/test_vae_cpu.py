@@ -152,5 +152,6 @@ def test_prepare_captions_like_the_reference_dataset():
     """dataset.py:46-52: lower-case, TOK substitution (key lower-cased), missing caption -> ''."""
     from sd_lora_trainer_b200.trainer.dataset import prepare_captions
     got = prepare_captions(["A photo of TOK, smiling", "tok and TOK", None, float("nan"), "No Token Here"], {"TOK": "<s0><s1><s2>"})
-    assert got == ["a photo of <s0><s1><s2>, smiling", "<s0><s1><s2> and <s0><s1><s2>", "", "", "no token here"]
+    # the replacement is a plain substring replace of the lower-cased key, so "token" is hit too - as in the reference
+    assert got == ["a photo of <s0><s1><s2>, smiling", "<s0><s1><s2> and <s0><s1><s2>", "", "", "no <s0><s1><s2>en here"]
     assert prepare_captions(["Keep CASE?"], None) == ["keep case?"]
