@@ -1,8 +1,11 @@
 #!/bin/bash
-# First GPU call of round 2 (one B200): (1) the established GPU suite, (2) the widenings finished after round 1's GPU
-# budget ran out - VAE-encode prologue, native CLIP stack - which have never run on a GPU, (3) bench A/B of the native
-# text path, (4) VAE-encode timing at 1024^2, (5) the ncu --set full captures of the final pair / flash kernels.
-#   gpurun --timeout 1500 -- bash scripts/gpu_round2.sh
+# First GPU call(s) of round 2 (one B200; ~30 GPU-minutes in all - split at the blank-line groups if needed):
+# (1) the established GPU suite, (2) everything finished after round 1's GPU budget ran out and never run on a GPU -
+# tests/test_z1..z6 (train() generator, Prodigy, dense backward, native CLIP, VAE-encode prologue, rank 64 / odd widths /
+# shared dscores), (3) the default bench WITH its CPU leg (first full-size step_loss_delta), then A/Bs: native CLIP, shared
+# dscores; BASELINE configs 5 (--full-ft), 2 (SD1.5) and 4 (rank 32), (4) VAE-encode timing, (5) the ncu --set full
+# captures of the final pair / flash kernels.
+#   gpurun --timeout 2400 -- bash scripts/gpu_round2.sh
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q --deselect tests/test_z5_vae_gpu.py --deselect tests/test_z4_clip_gpu.py \
     --deselect tests/test_z3_dense_gpu.py --deselect tests/test_z2_prodigy_gpu.py --deselect tests/test_z1_train_gpu.py --deselect tests/test_z6_shapes_gpu.py \
@@ -11,8 +14,8 @@ timeout 400 python -m pytest tests/test_z4_clip_gpu.py -q -x > gpurun_out/pytest
 timeout 400 python -m pytest tests/test_z5_vae_gpu.py -q -x > gpurun_out/pytest_zvae.log 2>&1; echo "pytest zvae exit $?"; tail -15 gpurun_out/pytest_zvae.log
 timeout 400 python -m pytest tests/test_z3_dense_gpu.py -q -x > gpurun_out/pytest_zdense.log 2>&1; echo "pytest zdense exit $?"; tail -15 gpurun_out/pytest_zdense.log
 timeout 300 python -m pytest tests/test_z2_prodigy_gpu.py tests/test_z1_train_gpu.py tests/test_z6_shapes_gpu.py -q > gpurun_out/pytest_zprodigy_ztrain.log 2>&1; echo "pytest zprodigy+ztrain exit $?"; tail -8 gpurun_out/pytest_zprodigy_ztrain.log
-timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-echo "bench default exit $?"; cut -c1-300 gpurun_out/bench_default.json
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+echo "bench default exit $?"; cut -c1-300 gpurun_out/bench_default.json; grep -o '"step_loss_delta": {[^}]*}' gpurun_out/bench_default.json
 B200_NATIVE_CLIP=1 timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu --skip-roofline > gpurun_out/bench_native_clip.json 2> gpurun_out/bench_native_clip.err
 echo "bench native clip exit $?"; cut -c1-300 gpurun_out/bench_native_clip.json; tail -3 gpurun_out/bench_native_clip.err
 timeout 500 python bench.py --full-ft --batch 1 --steps 5 --warmup 3 --skip-cpu --no-graph > gpurun_out/bench_full_ft.json 2> gpurun_out/bench_full_ft.err
