@@ -120,10 +120,11 @@ def token_attention_loss_from_maps(maps: torch.Tensor, masks: torch.Tensor, tok_
     hm = torch.gather(layer_mean, 3, idx).permute(0, 3, 1, 2).float()         # [B, n_tok, h, w]
     mk = masks[:, None]                                                       # [B, 1, h, w]
     vw = valid.float()[:, None, None, None]
-    denom = nv * hm.shape[1] * h * w
+    nv_safe = nv.clamp(min=1.0)                                               # nv == 0: every masked sum is 0, the
+    denom = nv_safe * hm.shape[1] * h * w                                     # result is discarded below, grads stay 0
     reg1 = 1.0 * ((torch.relu(hm * mk) ** 2) * vw).sum() / denom
     reg2 = 2.0 * ((torch.relu(hm * (1 - mk) + 10) ** 2) * vw).sum() / denom
-    reg3 = 1.0 * (hm.mean(dim=[2, 3]).var(dim=1) * valid.float()).sum() / nv
+    reg3 = 1.0 * (hm.mean(dim=[2, 3]).var(dim=1) * valid.float()).sum() / nv_safe
     total = (reg0 + reg1 + reg2 + reg3).to(masks.dtype)
     return torch.where(nv > 0, total, torch.zeros_like(total))                # loss.py:55-56
 

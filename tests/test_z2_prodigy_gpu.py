@@ -44,8 +44,11 @@ def test_prodigy_kernels_track_the_package_restatement(wd, growth, n_extra):
     assert float(grads.abs().max()) == 0.0
     for k, (d_ref, d_ours) in enumerate(ds):
         assert abs(d_ours - d_ref) <= 3e-2 * d_ref, (k, d_ref, d_ours)      # per-tensor bf16 .item() sums vs fp32 global sums
-    assert ds[-1][0] > 5 * ds[0][0]
-    ref = torch.cat([p.detach().flatten() for p in params]).float()
+    if not n_extra:
+        # d leaves d0 only while zero-initialised tensors dominate |s|_1; with a 1 M-element non-zero bf16 tensor the
+        # package's own d stays at d0 = 1e-6 - the tracking check above is the parity statement there
+        assert ds[-1][0] > 5 * ds[0][0]
+    ref =torch.cat([p.detach().flatten() for p in params]).float()
     step_sz = float((ref - p0.float()).abs().max())
     assert step_sz > 0 and float((ref - flat.float()).abs().max()) <= 0.15 * step_sz
     exp_avg = torch.cat([st["exp_avg"].flatten() for st in opt.state.values()]).float()
