@@ -245,6 +245,20 @@ def run_ours(args):
             result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
             if not args.full_ft:
                 result["step_loss_delta"] = {"error": child_err}
+    if rank == 0 and world == 1 and not args.skip_gpu_baseline:
+        # stock-torch-on-the-same-B200 comparator, in a child process (its own CUDA context and memory; bounded by a timeout)
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--gpu-baseline-only", "--family", args.family, "--rank",
+                   str(args.rank), "--res", str(args.res), "--batch", str(args.batch)] + (["--full-ft"] if args.full_ft else [])
+            cp = subprocess.run(cmd, capture_output=True, text=True, timeout=args.delta_timeout)
+            lines = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")]
+            result["gpu_baseline"] = json.loads(lines[-1])["gpu_baseline"] if lines else \
+                {"error": f"exit {cp.returncode}: {cp.stderr[-300:]}"}
+        except Exception as e:                                  # noqa: BLE001
+            result["gpu_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        gb = result["gpu_baseline"]
+        if "value" in gb:
+            gb["ours_over_stock_torch"] = result["value"] / gb["value"]
     if rank == 0:
         print(json.dumps(result), flush=True)
     faulthandler.cancel_dump_traceback_later()
@@ -335,6 +349,43 @@ def step_loss_delta(keep, dev):
             "north_star_bound": 1e-3}
 
 
+def gpu_baseline(args, steps: int = 5, warmup: int = 2):
+    """SURVEY 2.3 / BASELINE.md section 3: the bar is the reference's own code path on stock torch (cuBLAS / cuDNN SDPA / ATen
+    autograd / torch.optim.AdamW) ON THE SAME B200.  diffusers / peft cannot be installed, so this is the oracle port of that
+    step (oracle/) in bf16 on cuda:0 - same model, same batch, same synthetic inputs as the timed workload - between CUDA
+    events.  A comparator leg like cpu_baseline: nothing of it is on the product path."""
+    from oracle.step import OracleTrainer, StepConfig as OCfg, make_inputs
+    cfg = OCfg(family=args.family, resolution=args.res, lora_rank=args.rank, weight_dtype=torch.bfloat16,
+               is_lora=not args.full_ft, disable_ti=args.full_ft)
+    orc = OracleTrainer(cfg, device="cuda:0")
+    inp = make_inputs(cfg, batch=args.batch, face_mask=True, train_ids=orc.train_ids or None)
+    inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    inp["token_ids"] = [t.cuda() for t in inp["token_ids"]]
+    for _ in range(warmup):
+        float(orc.step(inp)["tot_loss"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        out = orc.step(inp)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": args.batch / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "kind": "port", "steps": steps,
+            "warmup": warmup, "loss": float(out["tot_loss"]), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+            "sample": f"oracle port of the reference step on stock torch {torch.__version__} (cuBLAS, SDPA, ATen autograd, "
+                      f"torch.optim.AdamW incl. the full embedding tables) in bf16 on the same B200, {args.family.upper()} "
+                      f"r={args.rank} {args.res}x{args.res} batch {args.batch}, inputs resident, eager"}
+
+
+def run_gpu_baseline_only(args):
+    try:
+        gb = gpu_baseline(args)
+    except Exception as e:                                      # noqa: BLE001
+        gb = {"error": f"{type(e).__name__}: {e}"[:300]}
+    print(json.dumps({"gpu_baseline": gb}), flush=True)
+
+
 def run_delta_only(args):
     """Child process of the default run: the bounded CPU-oracle step, then the GPU step on the oracle's own state."""
     keep = {}
@@ -387,11 +438,15 @@ def main():
     ap.add_argument("--cpu-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--ref-max-steps", type=int, default=10)
     ap.add_argument("--delta-only", action="store_true", help="internal: CPU baseline + step-loss delta, printed as JSON")
+    ap.add_argument("--gpu-baseline-only", action="store_true", help="internal: the stock-torch-on-B200 comparator leg")
+    ap.add_argument("--skip-gpu-baseline", action="store_true")
     ap.add_argument("--delta-timeout", type=int, default=600, help="seconds granted to the --delta-only child process")
     ap.add_argument("--watchdog", type=int, default=1500, help="seconds after which a stuck run dumps its stacks and exits 1")
     args = ap.parse_args()
     if args.delta_only:
         run_delta_only(args)
+    elif args.gpu_baseline_only:
+        run_gpu_baseline_only(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -163,6 +163,12 @@ int b200_add(const void* a, const void* b, const void* c, void* y, int64_t n, vo
 /* ---------------------------------------------------------------------------------------------------------
  * Layout helpers (NHWC).
  * --------------------------------------------------------------------------------------------------------- */
+/* Head re-pitch around the fused attention kernel (replaces the head split of [3P] diffusers Attention.head_to_batch_dim
+   on the AttnProcessor2_0 / DAAMLossAttnProcessor2_0 path, trainer/ti_cross_attn_loss.py:167-175, for head dims the
+   tcgen05 kernel does not take natively): src [rows, heads * d_src] -> dst [rows, heads * d_dst]; per head the first
+   min(d_src, d_dst) channels are copied, the rest zero-filled.  d_src, d_dst, ld_* multiples of 8 elements. */
+int b200_head_pad(const void* src, void* dst, int64_t rows, int32_t heads, int32_t d_src, int32_t d_dst, int64_t ld_src,
+                  int64_t ld_dst, void* stream);
 int b200_upsample2x_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 int b200_upsample2x_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 /* 3x3 pad-1 im2col with stride: col[N*Ho*Wo, 9*C], tap-major (kh,kw,c) */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200_act_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_void_p],
     "b200_act_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
     "b200_add": [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
+    "b200_head_pad": [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
     "b200_upsample2x_fwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_upsample2x_bwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_im2col3x3": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],

@@ -236,6 +236,27 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restri
     }
 }
 
+// Head re-pitch for the fused attention kernel (head_dim 64 only): [rows, H * d_src] -> [rows, H * d_dst], per head the first
+// min(d_src, d_dst) channels are copied and the rest zero-filled.  d = 40 (SD1.5's 64x64-latent layers) -> 64 makes
+// QK^T, PV and every gradient exact (the padded channels are zero in q, k and v); 64 -> 40 drops them again.
+// One 16-byte chunk per thread; d_src, d_dst multiples of 8.
+__global__ void head_pad_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long long rows, int H, int cs, int cd,
+                                long long ld_src, long long ld_dst) {
+    pdl_launch();
+    pdl_wait();
+    const long long per_row = static_cast<long long>(H) * cd;
+    const long long total = rows * per_row;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / per_row;
+        const int c = static_cast<int>(i - row * per_row);
+        const int head = c / cd, j = c - head * cd;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (j < cs) w = *reinterpret_cast<const uint4*>(src + row * ld_src + (static_cast<long long>(head) * cs + j) * 8);
+        *reinterpret_cast<uint4*>(dst + row * ld_dst + static_cast<long long>(c) * 8) = w;
+    }
+}
+
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ c,
                            bf16* __restrict__ y, long long n8, long long n) {
     pdl_launch();
@@ -647,6 +668,18 @@ extern "C" int b200_add(const void* a, const void* b, const void* c, void* y, in
     launch_pdl(add_kernel, dim3(grid_for(n8 > 0 ? n8 : 1, 256)), dim3(256), 0, ST, static_cast<const bf16*>(a), static_cast<const bf16*>(b),
                                                                static_cast<const bf16*>(c), static_cast<bf16*>(y), n8, n);
     B200_CHECK_LAUNCH("add");
+    return 0;
+}
+extern "C" int b200_head_pad(const void* src, void* dst, int64_t rows, int32_t heads, int32_t d_src, int32_t d_dst,
+                             int64_t ld_src, int64_t ld_dst, void* stream) {
+    B200_CHECK_ARG(rows >= 1 && heads >= 1 && d_src >= 8 && d_dst >= 8 && d_src % 8 == 0 && d_dst % 8 == 0 &&
+                       ld_src % 8 == 0 && ld_dst % 8 == 0 && ld_src >= 1LL * heads * d_src && ld_dst >= 1LL * heads * d_dst,
+                   "head_pad: head dims / row strides must be multiples of 8 elements");
+    B200_CHECK_ARG(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0, "head_pad: unaligned base");
+    launch_pdl(head_pad_kernel, dim3(grid_for(rows * heads * (d_dst / 8), 256)), dim3(256), 0, ST, static_cast<const bf16*>(src),
+               static_cast<bf16*>(dst), static_cast<long long>(rows), static_cast<int>(heads), static_cast<int>(d_src / 8),
+               static_cast<int>(d_dst / 8), static_cast<long long>(ld_src), static_cast<long long>(ld_dst));
+    B200_CHECK_LAUNCH("head_pad");
     return 0;
 }
 extern "C" int b200_upsample2x_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream) {

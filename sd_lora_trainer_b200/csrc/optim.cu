@@ -124,36 +124,87 @@ struct AdamHyper {    // 12 floats; also the layout of the device-resident copy 
     float one_minus_b1, beta2, one_minus_b2, eps, bc2_sqrt, grad_scale;
 };
 
-__device__ __forceinline__ void adam_update(bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ m,
-                                            bf16* __restrict__ v, long long i, const AdamSeg s, const AdamHyper& h,
-                                            int zero_grad) {
-    float pv = __bfloat162float(p[i]);
-    float g = bfr(grad[i] * h.grad_scale);
+// one element, registers in / registers out (shared by the 8-wide body and the scalar tail)
+__device__ __forceinline__ void adam_elem(float& pv, float& gq, float& mv, float& vv, const AdamSeg s, const AdamHyper& h) {
+    float g = bfr(gq * h.grad_scale);
     if (s.l1 != 0.f) g = bfr(g + s.l1 * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f)));
-    if (zero_grad) grad[i] = 0.f;
     if (s.decay != 1.f) pv = bfr(pv * s.decay);
-    float mv = __bfloat162float(m[i]);
     mv = bfr(mv + h.one_minus_b1 * (g - mv));
-    float vv = bfr(__bfloat162float(v[i]) * h.beta2);
+    vv = bfr(vv * h.beta2);
     vv = bfr(vv + h.one_minus_b2 * (g * g));   // ATen foreach addcmul: self + scalar * (t1 * t2)
     float d = bfr(sqrtf(vv));
     d = bfr(d / h.bc2_sqrt);
     d = bfr(d + h.eps);
     pv = bfr(pv + s.neg_step * (mv / d));
-    p[i] = __float2bfloat16_rn(pv);
-    m[i] = __float2bfloat16_rn(mv);
-    v[i] = __float2bfloat16_rn(vv);
 }
 
-__global__ void adamw_kernel(bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ m, bf16* __restrict__ v,
-                             long long n, long long n_first, AdamHyper h, const AdamHyper* __restrict__ h_dev,
-                             int zero_grad) {
+__device__ __forceinline__ void unpack8(const uint4 w, float (&f)[8]) {
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        f[2 * q] = __uint_as_float(u[q] << 16);
+        f[2 * q + 1] = __uint_as_float(u[q] & 0xffff0000u);
+    }
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {   // inputs already hold bf16-representable values
+    uint32_t u[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) u[q] = (__float_as_uint(f[2 * q]) >> 16) | (__float_as_uint(f[2 * q + 1]) & 0xffff0000u);
+    return make_uint4(u[0], u[1], u[2], u[3]);
+}
+
+// 8 elements per thread and iteration: 16-byte loads / stores of p, m, v (bf16) and 2 x 16 bytes of the fp32 gradient -
+// 14 algorithmic bytes per element (r+w of p, m, v; read + zero of g), all fully coalesced.  `vec` = every base pointer is
+// 16-byte aligned (32 for grad); otherwise (odd slices) the scalar loop covers everything.
+__global__ void __launch_bounds__(256) adamw_kernel(bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ m,
+                                                    bf16* __restrict__ v, long long n, long long n_first, AdamHyper h,
+                                                    const AdamHyper* __restrict__ h_dev, int zero_grad, int vec) {
     pdl_launch();
     pdl_wait();
     if (h_dev) h = *h_dev;     // CUDA-graph replay: hyper-parameters live in device memory, refreshed by a memcpy
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x)
-        adam_update(p, grad, m, v, i, i < n_first ? h.s0 : h.s1, h, zero_grad);
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long n8 = vec ? (n >> 3) : 0;
+    for (long long c = tid; c < n8; c += nthreads) {
+        const long long i0 = c << 3;
+        float pf[8], mf[8], vf[8], gf[8];
+        unpack8(reinterpret_cast<const uint4*>(p)[c], pf);
+        unpack8(reinterpret_cast<const uint4*>(m)[c], mf);
+        unpack8(reinterpret_cast<const uint4*>(v)[c], vf);
+        const float4 g0 = reinterpret_cast<const float4*>(grad)[2 * c], g1 = reinterpret_cast<const float4*>(grad)[2 * c + 1];
+        gf[0] = g0.x, gf[1] = g0.y, gf[2] = g0.z, gf[3] = g0.w, gf[4] = g1.x, gf[5] = g1.y, gf[6] = g1.z, gf[7] = g1.w;
+        if (i0 + 8 <= n_first || i0 >= n_first) {
+            const AdamSeg sg = i0 < n_first ? h.s0 : h.s1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) adam_elem(pf[j], gf[j], mf[j], vf[j], sg, h);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) adam_elem(pf[j], gf[j], mf[j], vf[j], i0 + j < n_first ? h.s0 : h.s1, h);
+        }
+        reinterpret_cast<uint4*>(p)[c] = pack8(pf);
+        reinterpret_cast<uint4*>(m)[c] = pack8(mf);
+        reinterpret_cast<uint4*>(v)[c] = pack8(vf);
+        if (zero_grad) {
+            reinterpret_cast<float4*>(grad)[2 * c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            reinterpret_cast<float4*>(grad)[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    for (long long i = (n8 << 3) + tid; i < n; i += nthreads) {
+        float pv = __bfloat162float(p[i]), mv = __bfloat162float(m[i]), vv = __bfloat162float(v[i]), g = grad[i];
+        adam_elem(pv, g, mv, vv, i < n_first ? h.s0 : h.s1, h);
+        p[i] = __float2bfloat16_rn(pv);
+        m[i] = __float2bfloat16_rn(mv);
+        v[i] = __float2bfloat16_rn(vv);
+        if (zero_grad) grad[i] = 0.f;
+    }
+}
+
+static inline int aligned16(const void* a, const void* b, const void* c, const void* g, const void* e = nullptr,
+                            const void* f = nullptr) {
+    const uintptr_t x = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                        reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f);
+    return (x & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 31) == 0;
 }
 
 static AdamHyper make_hyper(double lr, double wd, double l1_coeff, double lr2, double wd2, double beta1, double beta2,
@@ -188,10 +239,25 @@ struct ProdigyHyper {   // 12 floats, device resident (refreshed by a 48-byte co
     float lr, beta1, beta2, beta3, eps, decay, d_coef, growth, d0, bias_corr, l1, grad_scale;
 };
 
-__global__ void prodigy_accumulate_kernel(const bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ s,
-                                          const bf16* __restrict__ p0, bf16* __restrict__ m, bf16* __restrict__ v,
-                                          long long n, double* __restrict__ scal, const ProdigyHyper* __restrict__ h_dev,
-                                          int zero_grad) {
+__device__ __forceinline__ void prodigy_acc_elem(float pv, float gq, float p0v, float& mv, float& vv, float& sv, float& dot,
+                                                 float& den, const ProdigyHyper& h, float a_m, float a_v, float a_s) {
+    float g = bfr(gq * h.grad_scale);
+    if (h.l1 != 0.f) g = bfr(g + h.l1 * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f)));
+    dot += g * bfr(p0v - pv);
+    mv = bfr(mv * h.beta1);
+    mv = bfr(mv + a_m * g);
+    vv = bfr(vv * h.beta2);
+    vv = bfr(vv + a_v * (g * g));
+    sv = bfr(sv * h.beta3);
+    sv = bfr(sv + a_s * g);
+    den += fabsf(sv);
+}
+
+__global__ void __launch_bounds__(256) prodigy_accumulate_kernel(const bf16* __restrict__ p, float* __restrict__ grad,
+                                                                 bf16* __restrict__ s, const bf16* __restrict__ p0,
+                                                                 bf16* __restrict__ m, bf16* __restrict__ v, long long n,
+                                                                 double* __restrict__ scal,
+                                                                 const ProdigyHyper* __restrict__ h_dev, int zero_grad, int vec) {
     pdl_launch();
     pdl_wait();
     __shared__ float red[32];
@@ -202,21 +268,36 @@ __global__ void prodigy_accumulate_kernel(const bf16* __restrict__ p, float* __r
     const float a_v = static_cast<float>(d * d * (1.0 - static_cast<double>(h.beta2)));
     const float a_s = static_cast<float>((d / static_cast<double>(h.d0)) * d);
     float dot = 0.f, den = 0.f;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const float pv = __bfloat162float(p[i]);
-        float g = bfr(grad[i] * h.grad_scale);
-        if (h.l1 != 0.f) g = bfr(g + h.l1 * (pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f)));
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long n8 = vec ? (n >> 3) : 0;
+    for (long long c = tid; c < n8; c += nthreads) {
+        if (live) {
+            float pf[8], p0f[8], mf[8], vf[8], sf[8], gf[8];
+            unpack8(reinterpret_cast<const uint4*>(p)[c], pf);
+            unpack8(reinterpret_cast<const uint4*>(p0)[c], p0f);
+            unpack8(reinterpret_cast<const uint4*>(m)[c], mf);
+            unpack8(reinterpret_cast<const uint4*>(v)[c], vf);
+            unpack8(reinterpret_cast<const uint4*>(s)[c], sf);
+            const float4 g0 = reinterpret_cast<const float4*>(grad)[2 * c], g1 = reinterpret_cast<const float4*>(grad)[2 * c + 1];
+            gf[0] = g0.x, gf[1] = g0.y, gf[2] = g0.z, gf[3] = g0.w, gf[4] = g1.x, gf[5] = g1.y, gf[6] = g1.z, gf[7] = g1.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) prodigy_acc_elem(pf[j], gf[j], p0f[j], mf[j], vf[j], sf[j], dot, den, h, a_m, a_v, a_s);
+            reinterpret_cast<uint4*>(m)[c] = pack8(mf);
+            reinterpret_cast<uint4*>(v)[c] = pack8(vf);
+            reinterpret_cast<uint4*>(s)[c] = pack8(sf);
+        }
+        if (zero_grad) {
+            reinterpret_cast<float4*>(grad)[2 * c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            reinterpret_cast<float4*>(grad)[2 * c + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    for (long long i = (n8 << 3) + tid; i < n; i += nthreads) {
+        const float g = grad[i];
         if (zero_grad) grad[i] = 0.f;
         if (!live) continue;
-        dot += g * bfr(__bfloat162float(p0[i]) - pv);
-        float mv = bfr(__bfloat162float(m[i]) * h.beta1);
-        mv = bfr(mv + a_m * g);
-        float vv = bfr(__bfloat162float(v[i]) * h.beta2);
-        vv = bfr(vv + a_v * (g * g));
-        float sv = bfr(__bfloat162float(s[i]) * h.beta3);
-        sv = bfr(sv + a_s * g);
-        den += fabsf(sv);
+        float mv = __bfloat162float(m[i]), vv = __bfloat162float(v[i]), sv = __bfloat162float(s[i]);
+        prodigy_acc_elem(__bfloat162float(p[i]), g, __bfloat162float(p0[i]), mv, vv, sv, dot, den, h, a_m, a_v, a_s);
         m[i] = __float2bfloat16_rn(mv);
         v[i] = __float2bfloat16_rn(vv);
         s[i] = __float2bfloat16_rn(sv);
@@ -261,8 +342,18 @@ __global__ void prodigy_update_d_kernel(double* __restrict__ scal, const Prodigy
     scal[4] = 0.0;
 }
 
-__global__ void prodigy_apply_kernel(bf16* __restrict__ p, const bf16* __restrict__ m, const bf16* __restrict__ v, long long n,
-                                     const double* __restrict__ scal, const ProdigyHyper* __restrict__ h_dev) {
+__device__ __forceinline__ float prodigy_apply_elem(float pv, float mv, float vv, const ProdigyHyper& h, float dlr, float eps_d,
+                                                    float dec) {
+    float denom = bfr(sqrtf(vv));
+    denom = bfr(denom + eps_d);
+    if (h.decay != 0.f) pv = bfr(pv + dec * pv);
+    return bfr(pv - dlr * (mv / denom));
+}
+
+__global__ void __launch_bounds__(256) prodigy_apply_kernel(bf16* __restrict__ p, const bf16* __restrict__ m,
+                                                            const bf16* __restrict__ v, long long n,
+                                                            const double* __restrict__ scal,
+                                                            const ProdigyHyper* __restrict__ h_dev, int vec) {
     pdl_launch();
     pdl_wait();
     if (scal[6] != 0.0) return;
@@ -270,15 +361,21 @@ __global__ void prodigy_apply_kernel(bf16* __restrict__ p, const bf16* __restric
     const float dlr = static_cast<float>(scal[5]);
     const float eps_d = static_cast<float>(scal[0] * static_cast<double>(h.eps));
     const float dec = static_cast<float>(-static_cast<double>(h.decay) * scal[5]);
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        float denom = bfr(sqrtf(__bfloat162float(v[i])));
-        denom = bfr(denom + eps_d);
-        float pv = __bfloat162float(p[i]);
-        if (h.decay != 0.f) pv = bfr(pv + dec * pv);
-        pv = bfr(pv - dlr * (__bfloat162float(m[i]) / denom));
-        p[i] = __float2bfloat16_rn(pv);
+    const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long nthreads = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long n8 = vec ? (n >> 3) : 0;
+    for (long long c = tid; c < n8; c += nthreads) {
+        float pf[8], mf[8], vf[8];
+        unpack8(reinterpret_cast<const uint4*>(p)[c], pf);
+        unpack8(reinterpret_cast<const uint4*>(m)[c], mf);
+        unpack8(reinterpret_cast<const uint4*>(v)[c], vf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pf[j] = prodigy_apply_elem(pf[j], mf[j], vf[j], h, dlr, eps_d, dec);
+        reinterpret_cast<uint4*>(p)[c] = pack8(pf);
     }
+    for (long long i = (n8 << 3) + tid; i < n; i += nthreads)
+        p[i] = __float2bfloat16_rn(prodigy_apply_elem(__bfloat162float(p[i]), __bfloat162float(m[i]), __bfloat162float(v[i]), h,
+                                                      dlr, eps_d, dec));
 }
 
 }  // namespace b200
@@ -337,8 +434,9 @@ extern "C" int b200_adamw(void* p, float* grad, void* m, void* v, int64_t n, int
                           double grad_scale, int32_t zero_grad, void* stream) {
     B200_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
     const AdamHyper h = make_hyper(lr, wd, l1_coeff, lr2, wd2, beta1, beta2, eps, step, grad_scale);
-    launch_pdl(adamw_kernel, dim3(grid_for(n, 256)), dim3(256), 0, ST, static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
-                                                   static_cast<bf16*>(v), n, n_first, h, nullptr, zero_grad);
+    launch_pdl(adamw_kernel, dim3(grid_for((n + 7) / 8, 256, kNumSMs * 8)), dim3(256), 0, ST, static_cast<bf16*>(p), grad,
+               static_cast<bf16*>(m), static_cast<bf16*>(v), static_cast<long long>(n), static_cast<long long>(n_first), h,
+               static_cast<const AdamHyper*>(nullptr), static_cast<int>(zero_grad), aligned16(p, m, v, grad));
     B200_CHECK_LAUNCH("adamw");
     return 0;
 }
@@ -357,9 +455,9 @@ extern "C" int b200_adamw_dev(void* p, float* grad, void* m, void* v, int64_t n,
     B200_CHECK_ARG(hyper_dev12 != nullptr, "adamw_dev: null hyper-parameter buffer");
     AdamHyper h;
     memset(&h, 0, sizeof(h));
-    launch_pdl(adamw_kernel, dim3(grid_for(n, 256)), dim3(256), 0, ST, static_cast<bf16*>(p), grad, static_cast<bf16*>(m),
-                                                   static_cast<bf16*>(v), n, n_first, h,
-                                                   reinterpret_cast<const AdamHyper*>(hyper_dev12), zero_grad);
+    launch_pdl(adamw_kernel, dim3(grid_for((n + 7) / 8, 256, kNumSMs * 8)), dim3(256), 0, ST, static_cast<bf16*>(p), grad,
+               static_cast<bf16*>(m), static_cast<bf16*>(v), static_cast<long long>(n), static_cast<long long>(n_first), h,
+               reinterpret_cast<const AdamHyper*>(hyper_dev12), static_cast<int>(zero_grad), aligned16(p, m, v, grad));
     B200_CHECK_LAUNCH("adamw_dev");
     return 0;
 }
@@ -391,15 +489,16 @@ extern "C" int b200_prodigy_step(void* p, float* grad, void* s, const void* p0, 
                                  double* scal8, const float* hyper_dev12, int32_t zero_grad, void* stream) {
     B200_CHECK_ARG(n >= 1 && p && grad && s && p0 && exp_avg && exp_avg_sq && scal8 && hyper_dev12, "prodigy_step: bad arguments");
     const ProdigyHyper* hd = reinterpret_cast<const ProdigyHyper*>(hyper_dev12);
-    launch_pdl(prodigy_accumulate_kernel, dim3(grid_for(n, 256, kNumSMs * 8)), dim3(256), 0, ST, static_cast<const bf16*>(p), grad,
-               static_cast<bf16*>(s), static_cast<const bf16*>(p0), static_cast<bf16*>(exp_avg), static_cast<bf16*>(exp_avg_sq),
-               static_cast<long long>(n), scal8, hd, static_cast<int>(zero_grad));
+    const int vec = aligned16(p, exp_avg, exp_avg_sq, grad, s, p0);
+    launch_pdl(prodigy_accumulate_kernel, dim3(grid_for((n + 7) / 8, 256, kNumSMs * 8)), dim3(256), 0, ST,
+               static_cast<const bf16*>(p), grad, static_cast<bf16*>(s), static_cast<const bf16*>(p0), static_cast<bf16*>(exp_avg),
+               static_cast<bf16*>(exp_avg_sq), static_cast<long long>(n), scal8, hd, static_cast<int>(zero_grad), vec);
     B200_CHECK_LAUNCH("prodigy_accumulate");
     launch_pdl(prodigy_update_d_kernel, dim3(1), dim3(32), 0, ST, scal8, hd);
     B200_CHECK_LAUNCH("prodigy_update_d");
-    launch_pdl(prodigy_apply_kernel, dim3(grid_for(n, 256, kNumSMs * 8)), dim3(256), 0, ST, static_cast<bf16*>(p),
+    launch_pdl(prodigy_apply_kernel, dim3(grid_for((n + 7) / 8, 256, kNumSMs * 8)), dim3(256), 0, ST, static_cast<bf16*>(p),
                static_cast<const bf16*>(exp_avg), static_cast<const bf16*>(exp_avg_sq), static_cast<long long>(n),
-               static_cast<const double*>(scal8), hd);
+               static_cast<const double*>(scal8), hd, vec);
     B200_CHECK_LAUNCH("prodigy_apply");
     return 0;
 }

@@ -306,6 +306,17 @@ def add(a: torch.Tensor, b: torch.Tensor, c: Optional[torch.Tensor] = None, out:
 
 
 # ---- layout helpers ------------------------------------------------------------------------------
+def head_pad(x: torch.Tensor, heads: int, d_src: int, d_dst: int, out: Optional[torch.Tensor] = None):
+    """[rows, heads*d_src] -> [rows, heads*d_dst] bf16: per head copy min(d_src, d_dst) channels, zero-fill the rest."""
+    assert x.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] == heads * d_src
+    rows = x.shape[0]
+    y = torch.empty(rows, heads * d_dst, dtype=BF16, device=x.device) if out is None else out
+    assert y.shape == (rows, heads * d_dst) and y.stride(1) == 1
+    check(_lib.load().b200_head_pad(x.data_ptr(), y.data_ptr(), rows, heads, d_src, d_dst, x.stride(0), y.stride(0), _stream()),
+          "head_pad")
+    return y
+
+
 def upsample2x_fwd(x: torch.Tensor, N: int, H: int, W: int, C_: int):
     y = torch.empty(N * 4 * H * W, C_, dtype=BF16, device=x.device)
     check(_lib.load().b200_upsample2x_fwd(x.data_ptr(), y.data_ptr(), N, H, W, C_, _stream()), "upsample2x_fwd")

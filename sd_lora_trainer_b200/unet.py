@@ -515,9 +515,15 @@ class Attn:
         Lp = _r8(Lk)
         dev = x.device
         P = lse = None
-        if d == 64:
-            # fused tcgen05 attention: S and O live in TMEM, P only ever exists as a swizzled smem tile
-            O, lse = ops.flash_attn_fwd(q, k, v, B, H, L, Lk, scale)
+        fa = None
+        if d == 64 or (d < 64 and d % 8 == 0):
+            # fused tcgen05 attention: S and O live in TMEM, P only ever exists as a swizzled smem tile.  The kernel takes
+            # 64-wide heads; narrower ones (SD1.5's d = 40 on the 64x64 latent: L = 4096, where a materialised [B,H,L,L]
+            # would be gigabytes) are re-pitched to 64 with zero channels - exact for QK^T, PV and every gradient
+            qf, kf, vf = (q, k, v) if d == 64 else tuple(ops.head_pad(t, H, d, 64) for t in (q, k, v))
+            Of, lse = ops.flash_attn_fwd(qf, kf, vf, B, H, L, Lk, scale)
+            O = Of if d == 64 else ops.head_pad(Of, H, 64, d)
+            fa = (qf, kf, vf, Of)
         else:
             S = torch.empty(B, H, L, Lp, dtype=torch.float32, device=dev)
             P = torch.empty(B, H, L, Lp, dtype=BF16, device=dev)
@@ -538,11 +544,11 @@ class Attn:
                      d_strides=(Lp, 1, 0, L * Lp), alpha=scale, nb0=1, nb1=B)
             self.scores = sc[:, :, :Lk]
         y = self.to_out.fwd(O, residual=residual)
-        self.sv = (q, k, v, P, B, L, Lk, O if d == 64 else None, lse)
+        self.sv = (q, k, v, P, B, L, Lk, fa, lse)
         return y
 
     def bwd(self, dy, d_ctx_accum, dscores: Optional[torch.Tensor]):
-        q, k, v, P, B, L, Lk, O, lse = self.sv
+        q, k, v, P, B, L, Lk, fa, lse = self.sv
         self.sv = None
         C = self.to_q.N
         H, d = self.h, C // self.h
@@ -553,8 +559,15 @@ class Attn:
         dK_out = dV_out = None
         if self.kv_batch is not None:
             dK_out, dV_out = self.kv_batch.dkv(self.kv_index)
-        if d == 64:
-            dQ, dK, dV = ops.flash_attn_bwd(q, k, v, O, dO, lse, B, H, L, Lk, scale, dk=dK_out, dv=dV_out)
+        if fa is not None and d == 64:
+            qf, kf, vf, Of = fa
+            dQ, dK, dV = ops.flash_attn_bwd(qf, kf, vf, Of, dO, lse, B, H, L, Lk, scale, dk=dK_out, dv=dV_out)
+        elif fa is not None:
+            qf, kf, vf, Of = fa
+            dQf, dKf, dVf = ops.flash_attn_bwd(qf, kf, vf, Of, ops.head_pad(dO, H, d, 64), lse, B, H, L, Lk, scale)
+            dQ = ops.head_pad(dQf, H, 64, d)
+            dK = ops.head_pad(dKf, H, 64, d, out=dK_out)
+            dV = ops.head_pad(dVf, H, 64, d, out=dV_out)
         else:
             sS = (Lp, 1, L * Lp, H * L * Lp)
             # dV = P^T dO

@@ -301,6 +301,19 @@ def add(a, b, c=None, out=None):
     return y
 
 
+def head_pad(x, heads, d_src, d_dst, out=None):
+    assert x.dtype == BF16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[1] == heads * d_src
+    assert d_src % 8 == 0 and d_dst % 8 == 0 and x.stride(0) % 8 == 0 and (x.storage_offset() * 2) % 16 == 0
+    rows = x.shape[0]
+    y = torch.empty(rows, heads * d_dst, dtype=BF16) if out is None else out
+    assert y.shape == (rows, heads * d_dst) and y.stride(1) == 1 and y.stride(0) % 8 == 0 and (y.storage_offset() * 2) % 16 == 0
+    n = min(d_src, d_dst)
+    full = torch.zeros(rows, heads, d_dst, dtype=BF16)
+    full[:, :, :n] = x.reshape(rows, heads, d_src)[:, :, :n]
+    y.copy_(full.reshape(rows, heads * d_dst))
+    return y
+
+
 def upsample2x_fwd(x, N, H, W, C_):
     assert C_ % 8 == 0
     _chk_vec(x)
