@@ -63,3 +63,48 @@ def test_flash_attention_fwd_bwd(B, H, L, Lk):
         fl = 4.0 * B * H * L * Lk * 64
         tf, tb = ev[0].elapsed_time(ev[1]) / 5, ev[1].elapsed_time(ev[2]) / 5
         print(f"\nflash fwd {tf:.3f} ms ({fl / tf / 1e9:.0f} TFLOP/s)  bwd {tb:.3f} ms ({2.5 * fl / tb / 1e9:.0f} TFLOP/s)")
+
+
+@pytest.mark.parametrize("rows,H,d_src,d_dst", [(300, 8, 40, 64), (300, 8, 64, 40), (77, 2, 32, 64), (513, 5, 64, 64)])
+def test_head_pad_is_an_exact_repitch(rows, H, d_src, d_dst):
+    from sd_lora_trainer_b200 import ops
+    x = torch.randn(rows, H * d_src, device="cuda").to(BF)
+    y = ops.head_pad(x, H, d_src, d_dst)
+    torch.cuda.synchronize()
+    n = min(d_src, d_dst)
+    ref = torch.zeros(rows, H, d_dst, device="cuda", dtype=BF)
+    ref[:, :, :n] = x.view(rows, H, d_src)[:, :, :n]
+    assert torch.equal(y, ref.view(rows, H * d_dst))
+
+
+@pytest.mark.parametrize("B,H,L,Lk,d", [(2, 8, 1024, 1024, 40), (2, 8, 512, 77, 40), (1, 2, 256, 256, 32), (4, 8, 4096, 4096, 40)])
+def test_narrow_heads_through_the_fused_kernel(B, H, L, Lk, d):
+    """SD1.5's head dims below 64 (d = 40 at the 64x64-latent level, L = 4096) run on the 64-wide fused kernel after a zero
+    re-pitch of q / k / v (unet.Attn): same softmax(q k^T / sqrt(d)) v and gradients as torch attention on the d-wide heads."""
+    from sd_lora_trainer_b200 import ops
+    C = H * d
+    g = torch.Generator(device="cuda").manual_seed(L + Lk + d)
+    q, k, v, do = (torch.randn(B * n, C, device="cuda", generator=g).to(BF) for n in (L, Lk, Lk, L))
+    scale = d ** -0.5
+    qf, kf, vf, dof = (ops.head_pad(t, H, d, 64) for t in (q, k, v, do))
+    of, lse = ops.flash_attn_fwd(qf, kf, vf, B, H, L, Lk, scale)
+    dqf, dkf, dvf = ops.flash_attn_bwd(qf, kf, vf, of, dof, lse, B, H, L, Lk, scale)
+    o, dq, dk, dv = (ops.head_pad(t, H, 64, d) for t in (of, dqf, dkf, dvf))
+    torch.cuda.synchronize()
+    # the padded channels of every output are exactly zero
+    for t in (of, dqf, dkf, dvf):
+        assert float(t.view(-1, H, 64)[:, :, d:].abs().max()) == 0.0
+    qr, kr, vr = (t.view(B, n, H, d).transpose(1, 2).detach().requires_grad_(True) for t, n in ((q, L), (k, Lk), (v, Lk)))
+    if L * Lk <= 1024 * 1024:
+        qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (qr, kr, vr))
+        ref = torch.softmax(qr @ kr.transpose(-1, -2) * scale, -1) @ vr
+        ref.backward(do.float().view(B, L, H, d).transpose(1, 2))
+        tol = (1e-2, 2e-2)
+    else:
+        ref = torch.nn.functional.scaled_dot_product_attention(qr, kr, vr)       # torch's own fused bf16 kernel (memory-safe)
+        ref.backward(do.view(B, L, H, d).transpose(1, 2))
+        tol = (2e-2, 4e-2)
+    unh = lambda t, n: t.transpose(1, 2).reshape(B * n, C)
+    assert rel(o, unh(ref, L)) < tol[0], ("o", rel(o, unh(ref, L)))
+    for name, a, b_, n in (("dq", dq, qr.grad, L), ("dk", dk, kr.grad, Lk), ("dv", dv, vr.grad, Lk)):
+        assert rel(a, unh(b_, n)) < tol[1], (name, rel(a, unh(b_, n)))
