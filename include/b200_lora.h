@@ -110,17 +110,37 @@ int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int
                      int64_t ld_dp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Batched LoRA weight gradients (replaces autograd's dW of every lora_A / lora_B nn.Linear of a transformer block,
+ * main.py:363 -> [3P] peft lora.Linear): out_p[n, j] += sum_m X_p[m, n] * Y_p[m, j] for up to 32 independent problems in ONE
+ * launch - dB = dY^T.T (X = dY [M, N], Y = T = s.x.A^T [M, r], out = dB [N, r]) and dA = U^T.x (X = x [M, K],
+ * Y = U = s.dY.B [M, r], out[k, j] = dA[j, k]).  bf16 operands with 16-byte aligned rows, r <= 32; fp32 atomic output
+ * addressed out[n*out_sn + j*out_sj].  No tensor maps: any operand addresses batch.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* X;                /* bf16 [M, Nout], row stride ld_x */
+    const void* Y;                /* bf16 [M, >= roundup8(r)], row stride ld_y */
+    float* out;                   /* fp32, accumulated in place */
+    int64_t ld_x, ld_y, out_sn, out_sj;
+    int32_t M, Nout, r;
+} b200_wgrad_problem_t;
+int b200_lora_wgrad_batch(const b200_wgrad_problem_t* problems, int32_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Fused attention for head_dim 64 (every SDXL head): replaces F.scaled_dot_product_attention forward and its
  * autograd backward (trainer/ti_cross_attn_loss.py:197-199, diffusers AttnProcessor2_0) without ever writing an
  * [L, Lk] tensor to HBM.  q: [B*L, ld], k/v: [B*Lk, ld] bf16 with head h at columns [h*64, h*64+64); o likewise.
  * lse: [B, H, L] fp32 (natural log), saved by the forward for the backward.
  * Backward workspaces (caller-owned): delta_ws fp32 [B*H*L], dq_acc_ws fp32 [B*L*ld].
+ * split_ws (optional, may be NULL): fp32 [2*B*Lk*ld + B*H] that is ZERO on entry and is left zero by the kernel; with it,
+ * a single-key-block problem (Lk <= 128: every cross-attention layer) whose (H, B) grid would leave SMs idle splits its
+ * query blocks over more CTAs (partial dK / dV summed with fp32 atomics, last CTA of a head rounds them to bf16).
  * --------------------------------------------------------------------------------------------------------- */
 int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t H,
                         int32_t L, int32_t Lk, int64_t ld, float scale, void* stream);
 int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                         float* delta_ws, float* dq_acc_ws, void* dq, void* dk, void* dv, int32_t B, int32_t H,
-                        int32_t L, int32_t Lk, int64_t ld, float scale, void* stream);
+                        int32_t L, int32_t Lk, int64_t ld, float scale, float* split_ws, int64_t split_ws_floats,
+                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Normalisation / activation kernels on NHWC ([rows, C]) bf16 activations; replace ATen GroupNorm / LayerNorm /
@@ -177,6 +197,11 @@ int b200_col2im3x3(const void* col, void* dx, int32_t N, int32_t H, int32_t W, i
 /* U9[p, tap*r + j] = U[p - offset(tap), j] (zero outside the image): lets the conv-LoRA backward run as plain GEMMs */
 int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, int32_t W, int32_t r, int32_t ld_in, int32_t ld_out,
                       void* stream);
+/* T[p, j] = bf16(alpha * sum_tap Z[p + off(tap), tap*r + j]): the 3x3 lora_A convolution of [3P] peft lora.Conv2d.forward
+   (trainer/optimizer.py:84-95) from ONE plain GEMM Z = X . A_taps^T (fp32 [N*H*W, ld_z >= 9r]) instead of a 16-wide
+   implicit convolution; zero padding at the image border.  T: bf16 [N*H*W, ld_t >= r]. */
+int b200_shift_sum9(const float* Z, void* T, int32_t N, int32_t H, int32_t W, int32_t r, int32_t ld_z, int32_t ld_t,
+                    float alpha, void* stream);
 /* out[b, c] = sum_p x[b, p, c]  (x: [batch, hw, C] bf16, C % 8 == 0) - gradient of the per-image time-embedding bias.
  * scratch: batch*C fp32 (zeroed by the call; rows are split over CTAs and combined with fp32 reductions). */
 int b200_colsum(const void* x, void* out, float* scratch, int32_t batch, int64_t hw, int32_t C, void* stream);

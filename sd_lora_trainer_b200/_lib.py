@@ -30,16 +30,23 @@ class GemmDesc(C.Structure):
                 ("group", c_int32), ("D2", c_void_p), ("d2_sm", c_int64), ("d2_sn", c_int64), ("b_static", c_int32)]
 
 
+class WgradProblem(C.Structure):
+    _fields_ = [("X", c_void_p), ("Y", c_void_p), ("out", c_void_p), ("ld_x", c_int64), ("ld_y", c_int64),
+                ("out_sn", c_int64), ("out_sj", c_int64), ("M", c_int32), ("Nout", c_int32), ("r", c_int32)]
+
+
 # name -> argtypes (restype is int unless listed in _RESTYPES); must match include/b200_lora.h exactly.
 SIGNATURES = {
     "b200_version": [],
     "b200_last_error": [],
     "b200_launch_count": [],
     "b200_gemm": [C.POINTER(GemmDesc), c_void_p],
+    "b200_lora_wgrad_batch": [C.POINTER(WgradProblem), c_int32, c_void_p],
     "b200_flash_attn_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64,
                             c_float, c_void_p],
     "b200_flash_attn_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                            c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64, c_float, c_void_p],
+                            c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64, c_float, c_void_p, c_int64,
+                            c_void_p],
     "b200_softmax_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_softmax_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_groupnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32,
@@ -63,6 +70,7 @@ SIGNATURES = {
     "b200_im2col3x3": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_col2im3x3": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
     "b200_shift_stack9": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p],
+    "b200_shift_sum9": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p],
     "b200_colsum": [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p],
     "b200_lora_transpose_b": [c_void_p, c_void_p, c_void_p, c_int32, c_void_p],
     "b200_bicubic_fwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],

@@ -567,6 +567,31 @@ __global__ void shift_stack9_kernel(const bf16* __restrict__ U, bf16* __restrict
     }
 }
 
+// T[p, j] = bf16(alpha * sum_tap Z[p + off(tap), tap*r + j])  - the 3x3 conv-LoRA A product from ONE plain GEMM
+// Z = X . A_taps^T ([M, 9r], fp32): gather-form adjoint of shift_stack9, zero padding at the image border.
+__global__ void shift_sum9_kernel(const float* __restrict__ Z, bf16* __restrict__ T, int N, int H, int W, int r, int ld_z,
+                                  int ld_t, float alpha) {
+    pdl_launch();
+    pdl_wait();
+    const long long total = static_cast<long long>(N) * H * W * r;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(idx % r);
+        long long p = idx / r;
+        const int w = static_cast<int>(p % W);
+        const long long nh = p / W;
+        const int h = static_cast<int>(nh % H);
+        const long long n = nh / H;
+        float acc = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hs = h + tap / 3 - 1, ws = w + tap % 3 - 1;
+            if (hs >= 0 && hs < H && ws >= 0 && ws < W) acc += Z[((n * H + hs) * W + ws) * ld_z + tap * r + j];
+        }
+        T[p * ld_t + j] = __float2bfloat16_rn(acc * alpha);
+    }
+}
+
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, bf16* __restrict__ out, int n, int dim) {
     pdl_launch();
     pdl_wait();
@@ -767,6 +792,15 @@ extern "C" int b200_shift_stack9(const void* U, void* U9, int32_t N, int32_t H, 
     launch_pdl(shift_stack9_kernel, dim3(grid_for(9LL * N * H * W * r, 256)), dim3(256), 0, ST, 
         static_cast<const bf16*>(U), static_cast<bf16*>(U9), N, H, W, r, ld_in, ld_out);
     B200_CHECK_LAUNCH("shift_stack9");
+    return 0;
+}
+extern "C" int b200_shift_sum9(const float* Z, void* T, int32_t N, int32_t H, int32_t W, int32_t r, int32_t ld_z, int32_t ld_t,
+                               float alpha, void* stream) {
+    B200_CHECK_ARG(N >= 1 && H >= 1 && W >= 1 && r >= 1 && ld_z >= 9 * r && ld_t >= r, "shift_sum9: bad extents / leading dims");
+    launch_pdl(shift_sum9_kernel, dim3(grid_for(1LL * N * H * W * r, 256)), dim3(256), 0, ST, Z, static_cast<bf16*>(T),
+               static_cast<int>(N), static_cast<int>(H), static_cast<int>(W), static_cast<int>(r), static_cast<int>(ld_z),
+               static_cast<int>(ld_t), alpha);
+    B200_CHECK_LAUNCH("shift_sum9");
     return 0;
 }
 extern "C" int b200_timestep_embedding(const float* t, void* out, int32_t n, int32_t dim, void* stream) {

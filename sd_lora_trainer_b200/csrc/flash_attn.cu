@@ -43,7 +43,8 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
 
 extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                                    const float* lse, float* delta_ws, float* dq_acc_ws, void* dq, void* dk, void* dv,
-                                   int32_t B, int32_t H, int32_t L, int32_t Lk, int64_t ld, float scale, void* stream) {
+                                   int32_t B, int32_t H, int32_t L, int32_t Lk, int64_t ld, float scale, float* split_ws,
+                                   int64_t split_ws_floats, void* stream) {
     B200_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && Lk >= 1 && ld == static_cast<int64_t>(H) * 64,
                    "flash_attn_bwd: needs contiguous [rows, H*64] tensors");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -65,7 +66,8 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     if (int rc = head_map(&g.mapDO, d_o, L, H, B, ld, 128)) return rc;
     if (int rc = head_map(&g.mapK, k, Lk, H, B, ld, 128)) return rc;
     if (int rc = head_map(&g.mapV, v, Lk, H, B, ld, 128)) return rc;
-    {
+    if (!dq_direct) {
+        B200_CHECK_ARG(dq_acc_ws != nullptr, "flash_attn_bwd: Lk > 128 needs the fp32 dQ accumulator workspace");
         const long long dims[4] = {ld, L, B, 1};
         const long long strides[3] = {ld, static_cast<long long>(L) * ld, 0};
         const int box[4] = {32, 128, 1, 1};
@@ -84,6 +86,23 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     g.ld = ld;
     g.scale = scale;
     dim3 grid((Lk + 127) / 128, H, B);
+    // single key block (cross-attention) on a grid that would leave SMs idle: split the query blocks over blockIdx.x
+    g.nsplit = 1;
+    const int nq = (L + 127) / 128;
+    const long long plane = static_cast<long long>(B) * Lk * ld;
+    if (dq_direct && split_ws != nullptr && nq >= 2 && B * H < kNumSMs &&
+        split_ws_floats >= 2 * plane + static_cast<long long>(B) * H) {
+        int ns = kNumSMs / (B * H);
+        if (ns > nq) ns = nq;
+        if (ns >= 2) {
+            B200_CHECK_ARG(reinterpret_cast<uintptr_t>(split_ws) % 16 == 0, "flash_attn_bwd: split workspace not 16-byte aligned");
+            g.nsplit = ns;
+            g.nbatch_rows = B * Lk;
+            g.dKVacc = split_ws;
+            g.counters = reinterpret_cast<int*>(split_ws + 2 * plane);
+            grid.x = ns;
+        }
+    }
     launch_pdl(flash_bwd_kernel, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     B200_CHECK_LAUNCH("flash_bwd");
     if (!dq_direct) {

@@ -345,6 +345,15 @@ struct FlashBwdArgs {
     int L, Lk, H;
     long long ld;
     float scale;
+    // Query split (single key block only, i.e. cross-attention: Lk <= 128).  A grid of (1, H, B) CTAs that each walk all
+    // L/128 query blocks leaves most SMs idle (40 CTAs at SDXL's 1280-wide level), so blockIdx.x cuts the query blocks into
+    // nsplit contiguous ranges.  dQ blocks are disjoint (written directly); every CTA adds its partial dK / dV (fp32
+    // atomics) into dKVacc [2][B*Lk, ld], and the LAST CTA of a (b, h) to finish - counted in `counters` - rounds the sums
+    // to bf16 into dK / dV and re-zeroes accumulators and counter, so the workspace is clean for the next launch.
+    int nsplit;
+    int nbatch_rows;                           // B * Lk: rows of one accumulator plane
+    float* dKVacc;
+    int* counters;
 };
 
 __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_constant__ FlashBwdArgs g) {
@@ -363,8 +372,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-    const int nq = (g.L + 127) >> 7;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int nq_all = (g.L + 127) >> 7;
+    const int nsplit = g.nsplit;
+    // query blocks [qb0, qb0 + nq) of this CTA; ring stages / barrier phases follow the LOCAL block index
+    const int k0 = nsplit > 1 ? 0 : static_cast<int>(blockIdx.x) * 128;
+    const int qb0 = nsplit > 1 ? static_cast<int>((static_cast<long long>(nq_all) * blockIdx.x) / nsplit) : 0;
+    const int nq = nsplit > 1 ? static_cast<int>((static_cast<long long>(nq_all) * (blockIdx.x + 1)) / nsplit) - qb0 : nq_all;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&g.mapQ);
@@ -406,8 +420,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 const int s = i & 1;
                 mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[s], 2 * kFaTile);
-                tma_load_4d(smem + kBwdQ + s * kFaTile, &g.mapQ, &qdo_full[s], 0, i * 128, h, b);
-                tma_load_4d(smem + kBwdDO + s * kFaTile, &g.mapDO, &qdo_full[s], 0, i * 128, h, b);
+                tma_load_4d(smem + kBwdQ + s * kFaTile, &g.mapQ, &qdo_full[s], 0, (qb0 + i) * 128, h, b);
+                tma_load_4d(smem + kBwdDO + s * kFaTile, &g.mapDO, &qdo_full[s], 0, (qb0 + i) * 128, h, b);
             }
         }
         __syncwarp();
@@ -478,13 +492,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             //      instructions per row and block), so two warps share every TMEM lane quarter. ----
             const int chalf = (warp >= 10) ? 2 : 0;
             for (int i = 0; i < nq; ++i) {
-                const int q = i * 128 + row;
+                const int q = (qb0 + i) * 128 + row;
                 const bool qok = q < g.L;
                 const float lse2 = qok ? g.LSE[stat_base + q] * 1.4426950408889634f : 0.f;
                 const float delta = qok ? g.Delta[stat_base + q] : 0.f;
                 mbar_wait(sdp_full, i & 1);
                 tc_fence_after();
-                const bool full_blk = (kvalid == 128) && (i * 128 + 128 <= g.L);     // warp-uniform
+                const bool full_blk = (kvalid == 128) && ((qb0 + i) * 128 + 128 <= g.L);     // warp-uniform
                 uint32_t pp[2][16], pd[2][16];                 // this thread's 64 P and dS values, packed bf16
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
@@ -540,7 +554,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 tc_fence_after();
                 if (g.dq_direct) {
                     // single key block: no accumulation over blocks -> straight to bf16, thread <-> query row
-                    const int q = i * 128 + row;
+                    const int q = (qb0 + i) * 128 + row;
                     __nv_bfloat16* dst = g.dQ + (static_cast<long long>(b) * g.L + q) * g.ld + h * 64;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
@@ -586,8 +600,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 if (lane == 0) mbar_arrive(dq_free);            // TMEM dQ drained: the next block's MMA may overwrite it
                 named_bar_sync(2, 128);
                 if (issuer) {
-                    tma_reduce_add_4d(&g.mapDQ, stg, h * 64, i * 128, b, 0);
-                    tma_reduce_add_4d(&g.mapDQ, stg + kFaTile, h * 64 + 32, i * 128, b, 0);
+                    tma_reduce_add_4d(&g.mapDQ, stg, h * 64, (qb0 + i) * 128, b, 0);
+                    tma_reduce_add_4d(&g.mapDQ, stg + kFaTile, h * 64 + 32, (qb0 + i) * 128, b, 0);
                     bulk_commit();
                 }
                 __syncwarp();
@@ -600,6 +614,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
         const int key = k0 + row;
         const uint32_t src = (warp < 6) ? t_dV : t_dK;
         __nv_bfloat16* out = ((warp < 6) ? g.dV : g.dK) + (static_cast<long long>(b) * g.Lk + key) * g.ld + h * 64;
+        float* acc = nsplit > 1 ? g.dKVacc + ((warp < 6) ? static_cast<long long>(g.nbatch_rows) * g.ld : 0LL) +
+                                      (static_cast<long long>(b) * g.Lk + key) * g.ld + h * 64
+                                : nullptr;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             if (warp >= 10) break;                 // the second softmax group has no output tile of its own (warp-uniform)
@@ -607,21 +624,57 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             tmem_ld32(src + lane_off + c * 32, r);
             tmem_ld_wait();
             if (key < g.Lk) {
+                if (acc != nullptr) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    uint4 w;
-                    w.x = pack_bf16(__uint_as_float(r[8 * e + 0]), __uint_as_float(r[8 * e + 1]));
-                    w.y = pack_bf16(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]));
-                    w.z = pack_bf16(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]));
-                    w.w = pack_bf16(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]));
-                    *reinterpret_cast<uint4*>(out + c * 32 + e * 8) = w;
+                    for (int e = 0; e < 8; ++e)
+                        atomicAdd(reinterpret_cast<float4*>(acc + c * 32 + e * 4),
+                                  make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
+                                              __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3])));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint4 w;
+                        w.x = pack_bf16(__uint_as_float(r[8 * e + 0]), __uint_as_float(r[8 * e + 1]));
+                        w.y = pack_bf16(__uint_as_float(r[8 * e + 2]), __uint_as_float(r[8 * e + 3]));
+                        w.z = pack_bf16(__uint_as_float(r[8 * e + 4]), __uint_as_float(r[8 * e + 5]));
+                        w.w = pack_bf16(__uint_as_float(r[8 * e + 6]), __uint_as_float(r[8 * e + 7]));
+                        *reinterpret_cast<uint4*>(out + c * 32 + e * 8) = w;
+                    }
                 }
             }
         }
         tc_fence_before();
+        if (nsplit > 1) __threadfence();           // this thread's partial sums are visible before the CTA is counted
     }
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 512);
+    if (nsplit > 1) {
+        // the last CTA of this (b, h) to arrive owns the final rounding: fp32 sums -> bf16 dK / dV, workspace re-zeroed
+        __shared__ int s_last;
+        if (threadIdx.x == 0) {
+            const int prev = atomicAdd(&g.counters[b * g.H + h], 1);
+            s_last = (prev == nsplit - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const long long half = static_cast<long long>(g.nbatch_rows) * g.ld;
+            for (int idx = threadIdx.x; idx < g.Lk * 16 * 2; idx += blockDim.x) {
+                const int which = idx / (g.Lk * 16);               // 0: dK, 1: dV
+                const int rem = idx - which * g.Lk * 16;
+                const int key = rem >> 4, c4 = (rem & 15) * 4;
+                const long long off = (static_cast<long long>(b) * g.Lk + key) * g.ld + h * 64 + c4;
+                float4* ap = reinterpret_cast<float4*>(g.dKVacc + which * half + off);
+                const float4 v = __ldcg(ap);
+                __stcg(ap, make_float4(0.f, 0.f, 0.f, 0.f));
+                uint2 w;
+                w.x = pack_bf16(v.x, v.y);
+                w.y = pack_bf16(v.z, v.w);
+                *reinterpret_cast<uint2*>((which ? g.dV : g.dK) + off) = w;
+            }
+            if (threadIdx.x == 0) g.counters[b * g.H + h] = 0;
+        }
+    }
 }
 
 // delta[b, h, l] = sum_d dO * O   (one thread per (row, head), 64-wide dot product)

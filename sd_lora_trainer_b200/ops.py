@@ -170,6 +170,24 @@ def _profile_gemm(d: GemmDesc, segs, M: int, N: int, nbatch: int, atomic: bool, 
     rec["flop"] += 2.0 * M * N * sum(ks) * nbatch
 
 
+WGRAD_MAX_BATCH = 32
+
+
+def lora_wgrad_batch(problems: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int, int, int, int, int]]):
+    """ONE launch (per 32 problems) for a list of LoRA weight-gradient problems (X [M, Nout] bf16, Y [M, >= r] bf16,
+    out fp32, M, Nout, r, out_sn, out_sj):  out[n*out_sn + j*out_sj] += sum_m X[m, n] * Y[m, j]."""
+    lib = _lib.load()
+    for lo in range(0, len(problems), WGRAD_MAX_BATCH):
+        chunk = problems[lo:lo + WGRAD_MAX_BATCH]
+        arr = (_lib.WgradProblem * len(chunk))()
+        for i, (X, Y, out, M, Nout, r, sn, sj) in enumerate(chunk):
+            _chk_dev(X, Y, out)
+            assert X.dtype == BF16 and Y.dtype == BF16 and out.dtype == torch.float32
+            assert X.stride(-1) == 1 and Y.stride(-1) == 1
+            arr[i] = _lib.WgradProblem(X.data_ptr(), Y.data_ptr(), out.data_ptr(), X.stride(0), Y.stride(0), sn, sj, M, Nout, r)
+        check(lib.b200_lora_wgrad_batch(arr, len(chunk), _stream()), "lora_wgrad_batch")
+
+
 # ---- fused attention (head_dim 64) -----------------------------------------------------------------
 def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, L: int, Lk: int, scale: float):
     """q: [B*L, H*64], k/v: [B*Lk, H*64] bf16.  Returns (o [B*L, H*64] bf16, lse [B, H, L] fp32)."""
@@ -182,6 +200,18 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H:
     return o, lse
 
 
+_SPLIT_WS: dict = {}
+
+
+def _flash_split_ws(device, floats: int) -> torch.Tensor:
+    """Persistent zero-initialised workspace of the query-split backward (the kernel leaves it zero again)."""
+    key = str(device)          # one stream per device drives the step: launches that share the workspace are serialised
+    ws = _SPLIT_WS.get(key)
+    if ws is None or ws.numel() < floats:
+        ws = _SPLIT_WS[key] = torch.zeros(max(floats, 1 << 20), dtype=torch.float32, device=device)
+    return ws
+
+
 def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale: float, dk=None, dv=None):
     """Returns (dq [B*L, C], dk [B*Lk, C], dv [B*Lk, C]) bf16; dk / dv may be caller-provided contiguous buffers."""
     C_ = H * 64
@@ -191,10 +221,14 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale:
     dv = torch.empty(B * Lk, C_, dtype=BF16, device=dev) if dv is None else dv
     assert dk.is_contiguous() and dv.is_contiguous()
     delta = torch.empty(B * H * L, dtype=torch.float32, device=dev)
-    dq_acc = torch.empty(B * L * C_, dtype=torch.float32, device=dev)
+    single = Lk <= 128                                # one key block: dQ is written directly, no fp32 accumulator needed
+    dq_acc = None if single else torch.empty(B * L * C_, dtype=torch.float32, device=dev)
+    ws_floats = 2 * B * Lk * C_ + B * H if (single and L > 128) else 0
+    ws = _flash_split_ws(dev, ws_floats) if ws_floats else None
     check(_lib.load().b200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
-                                          lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr(), dq.data_ptr(),
-                                          dk.data_ptr(), dv.data_ptr(), B, H, L, Lk, C_, scale, _stream()), "flash_attn_bwd")
+                                          lse.data_ptr(), delta.data_ptr(), _p(dq_acc), dq.data_ptr(),
+                                          dk.data_ptr(), dv.data_ptr(), B, H, L, Lk, C_, scale, _p(ws),
+                                          ws.numel() if ws is not None else 0, _stream()), "flash_attn_bwd")
     return dq, dk, dv
 
 
@@ -349,6 +383,14 @@ def shift_stack9(U: torch.Tensor, N: int, H: int, W: int, r: int):
     U9 = torch.empty(N * H * W, ld_out, dtype=BF16, device=U.device)
     check(_lib.load().b200_shift_stack9(U.data_ptr(), U9.data_ptr(), N, H, W, r, ld_in, ld_out, _stream()), "shift_stack9")
     return U9
+
+
+def shift_sum9(Z: torch.Tensor, N: int, H: int, W: int, r: int, alpha: float, ld_t: int):
+    """Z: fp32 [N*H*W, >= 9r] (Z = X . A_taps^T) -> T bf16 [N*H*W, ld_t]: T[p, j] = alpha * sum_tap Z[p + off(tap), tap*r + j]."""
+    assert Z.dtype == torch.float32 and Z.dim() == 2 and Z.stride(1) == 1 and Z.shape[0] == N * H * W
+    T = torch.empty(N * H * W, ld_t, dtype=BF16, device=Z.device)
+    check(_lib.load().b200_shift_sum9(Z.data_ptr(), T.data_ptr(), N, H, W, r, Z.stride(0), ld_t, alpha, _stream()), "shift_sum9")
+    return T
 
 
 def colsum(x: torch.Tensor, batch: int, hw: int, C_: int):

@@ -69,6 +69,29 @@ WGRAD = _WgradLane()
 GROUP_WGRAD = os.environ.get("B200_GROUP_WGRAD", "1") != "0"
 
 
+class _WgradQueue:
+    """The dA / dB weight-gradient problems of the LoRA linears are queued during a transformer block's backward and leave
+    as ONE table-driven launch at its end (ops.lora_wgrad_batch; 12 problems per SDXL block) instead of one tcgen05 GEMM
+    launch per layer - 84 MFLOP problems whose cost was launch latency (B200_WGRAD_BATCH=0 restores the per-layer form).
+    The queued operands stay referenced until the flush, so the caching allocator cannot recycle them."""
+
+    def __init__(self):
+        self.enabled = os.environ.get("B200_WGRAD_BATCH", "1") != "0"
+        self.active = False
+        self.items: List[tuple] = []
+
+    def accepts(self, *mats_rows) -> bool:
+        return self.active and all(t.stride(0) % 8 == 0 and t.stride(-1) == 1 for t in mats_rows)
+
+    def flush(self):
+        if self.items:
+            ops.lora_wgrad_batch(self.items)
+            self.items = []
+
+
+WQ = _WgradQueue()
+
+
 def _wgrad_splits(out_rows: int, reduce_len: int) -> int:
     tiles = (out_rows + 127) // 128
     kblocks = (reduce_len + 63) // 64
@@ -318,7 +341,11 @@ class Lin:
         if need_dx:
             dx = accum if accum is not None else torch.empty(M, self.K, dtype=BF16, device=dy.device)
             ops.gemm(dx, M, self.K, segs, residual=accum, side=side, static_b=True)
-        if lo is not None:
+        if lo is not None and lo.r <= 32 and self.N % 8 == 0 and self.K % 8 == 0 and WQ.accepts(dy, T, x, U):
+            # dB[N, r] += dY^T . T      dA[r, K] += U^T . X : queued, one batched launch per transformer block
+            WQ.items.append((dy, T, lo.gB(), M, self.N, r, rs, 1))
+            WQ.items.append((x, U, lo.gA(), M, self.K, r, 1, self.K))
+        elif lo is not None:
             # dB[N, r] += dY^T . T      dA[r, K] += U^T . X   (both operands MN-major, split-K fp32 atomics)
             def wgrad():
                 seg_b = (Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(T, M, r, rs, mn=True), M)
@@ -385,12 +412,16 @@ class Conv3:
         segs = [(a0, kmajor(self.wk), 9 * self.cin_p)]
         if lo is not None:
             assert s == 1
-            T = torch.empty(Mo, lo.rs, dtype=BF16, device=x.device)
             if col is None:
-                ops.gemm(T, Mo, lo.r, [(Conv3x3(x, N, H, W, self.cin_p, b_tap_k=0, b_tap_n=lo.r),
-                                        Mat(lo.A(), 9 * lo.r, self.cin, self.cin), 9 * self.cin_p)],
-                         d_strides=(lo.rs, 1, 0, 0), alpha=lo.store.scaling)
+                # the rank-r 3x3 convolution as ONE plain GEMM over all nine taps, Z[p, (tap, j)] = X[p, :] . A[tap, j, :]
+                # (N = 9r, fp32 out), and a 9-point shift-sum: as a 16-wide implicit convolution it walked 180 k-blocks on
+                # 16 CTAs (98 us per 1280-wide layer, 8 TFLOP/s - profiles/r01j_gemm_roofline_table.md)
+                Z = torch.empty(Mo, 9 * lo.r, dtype=torch.float32, device=x.device)
+                ops.gemm(Z, Mo, 9 * lo.r, [(Mat(x, Mo, self.cin, x.stride(0)), Mat(lo.A(), 9 * lo.r, self.cin, self.cin), self.cin)],
+                         static_b=True)
+                T = ops.shift_sum9(Z, N, H, W, lo.r, lo.store.scaling, lo.rs)
             else:   # unsupported image geometry: T = col . A_flat^T needs A as [r, (tap, c)]
+                T = torch.empty(Mo, lo.rs, dtype=BF16, device=x.device)
                 af = lo.A().view(9, lo.r, self.cin).permute(1, 0, 2).reshape(lo.r, 9 * self.cin).contiguous()
                 ops.gemm(T, Mo, lo.r, [(kmajor(col), kmajor(af), 9 * self.cin)], d_strides=(lo.rs, 1, 0, 0),
                          alpha=lo.store.scaling)
@@ -705,7 +736,9 @@ class TBlock:
         self.h = None
         dx2 = self.ln3.bwd(self.ff1.bwd(dh), dres=dx3)
         dx1 = self.ln2.bwd(self.attn2.bwd(dx2, d_ctx, dscores), dres=dx2)
-        return self.ln1.bwd(self.attn1.bwd(dx1, None, None), dres=dx1)
+        dx0 = self.attn1.bwd(dx1, None, None)
+        WQ.flush()                                   # the block's LoRA weight gradients: one launch
+        return self.ln1.bwd(dx0, dres=dx1)
 
 
 class Transformer2D:
@@ -996,6 +1029,7 @@ class UNetB200:
         d_ctx = torch.zeros(B * Lctx, Dc, dtype=BF16, device=dev) if need_dctx else None
         d_temb_act = torch.zeros(B, a.time_embed_dim, dtype=BF16, device=dev)
         WGRAD.begin(os.environ.get("B200_WGRAD_STREAM", "0") == "1" and dev.type == "cuda")
+        WQ.active, WQ.items = WQ.enabled and self.dense is None, []
         self.store.refresh_bt()                        # LoRA-B does not change between here and the optimizer
         for conv in self._convs:                       # dense fine-tune: input-gradient tap copies follow the trained taps
             conv.refresh_dgrad()
@@ -1049,5 +1083,7 @@ class UNetB200:
         if self.dense is not None:                   # the timestep MLP trains too: dW / db of linear_2 and linear_1
             self.time1.bwd(ops.silu_bwd(self.time2.bwd(d_emb), e1), need_dx=False)
         self.time1.x = self.time2.x = None
+        WQ.flush()
+        WQ.active = False
         WGRAD.join()                                 # every dA / dB has landed in store.grads before the optimizer
         return (d_ctx.view(B, Lctx, Dc) if d_ctx is not None else None), d_text

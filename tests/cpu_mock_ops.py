@@ -139,6 +139,17 @@ def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, 
     return out
 
 
+def lora_wgrad_batch(problems):
+    for X, Y, out, M, Nout, r, sn, sj in problems:
+        assert X.dtype == BF16 and Y.dtype == BF16 and out.dtype == torch.float32 and r <= 32
+        assert X.stride(0) % 8 == 0 and Y.stride(0) % 8 == 0 and Nout % 8 == 0 and X.stride(-1) == 1 and Y.stride(-1) == 1
+        assert (X.storage_offset() * 2) % 16 == 0 and (Y.storage_offset() * 2) % 16 == 0
+        assert X.shape[0] >= M and X.shape[1] >= Nout and Y.shape[0] >= M and Y.shape[1] >= r
+        upd = X[:M, :Nout].float().t() @ Y[:M, :r].float()              # [Nout, r]
+        view = _view(out, (Nout, r), (sn, sj))
+        view += upd
+
+
 def flash_attn_fwd(q, k, v, B, H, L, Lk, scale):
     C_ = H * 64
     q4 = q.float().view(B, L, H, 64).transpose(1, 2)
@@ -350,6 +361,19 @@ def shift_stack9(U, N, H, W, r):
         hsrc, wsrc = slice(max(-dh, 0), H + min(-dh, 0)), slice(max(-dw, 0), W + min(-dw, 0))
         out[:, hs, ws, tap * r:(tap + 1) * r] = Un[:, hsrc, wsrc]
     return _bf(out.reshape(N * H * W, ld_out))
+
+
+def shift_sum9(Z, N, H, W, r, alpha, ld_t):
+    assert Z.dtype == torch.float32 and Z.shape[0] == N * H * W and Z.shape[1] >= 9 * r and ld_t >= r
+    z = Z[:, :9 * r].reshape(N, H, W, 9, r)
+    zp = F.pad(z, (0, 0, 0, 0, 1, 1, 1, 1))                      # pad W and H by one pixel
+    acc = torch.zeros(N, H, W, r)
+    for tap in range(9):
+        kh, kw = tap // 3, tap % 3
+        acc += zp[:, kh:kh + H, kw:kw + W, tap]
+    T = torch.zeros(N * H * W, ld_t, dtype=BF16)
+    T[:, :r] = (acc * torch.tensor(alpha, dtype=torch.float32)).reshape(N * H * W, r).to(BF16)
+    return T
 
 
 def colsum(x, batch, hw, C_):

@@ -256,6 +256,7 @@ def test_shared_dscores_path_is_value_identical(monkeypatch, family, hw):
     """B200_SHARED_DSCORES=1: one gradient map per resolution handed to every hooked layer (the regulariser only sees the
     layer mean) must reproduce the per-layer autograd path bit for bit: losses, LoRA gradients, token-row gradients."""
     cpu_mock_ops.install(monkeypatch)
+    monkeypatch.setenv("B200_SHARED_DSCORES", "0")
     cfg, orc, tr_a, inputs = _setup(family, 8, 2, hw)
     out_a = tr_a.step(inputs, do_optimizer=False)
     monkeypatch.setenv("B200_SHARED_DSCORES", "1")

@@ -54,6 +54,7 @@ def test_shared_dscores_path_matches_per_layer_path(monkeypatch):
     weight-gradient atomics sum in a run-dependent order)."""
     from tests.test_unet_gpu import _build, _product, rel
     cfg, orc, inputs = _build("sdxl", rank=8, batch=2)
+    monkeypatch.setenv("B200_SHARED_DSCORES", "0")
     tr_a = _product(cfg, orc)
     out_a = tr_a.step(inputs, completion_f=0.0, do_optimizer=False)
     monkeypatch.setenv("B200_SHARED_DSCORES", "1")
