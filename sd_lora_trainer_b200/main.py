@@ -193,10 +193,17 @@ def train(config: TrainingConfig, dataset, text_encoders: Sequence, unet_state_d
     config.pretrained_model = dict(config.pretrained_model or {}, version=family)
     trainer = TrainerB200(config.step_config(family, tiny), unet_state_dict, text_encoders, device=config.device,
                           process_group=process_group, use_cuda_graph=use_cuda_graph)
-    handler = None
-    if not config.disable_ti:
-        handler = TokenEmbeddingsHandler(list(text_encoders))
-        handler.inserting_toks, handler.train_ids, handler.rows = config.inserting_list_tokens, trainer.train_ids, trainer.ti_rows
+    # The reference adds the tokens and builds the handler unconditionally (main.py:92-100) and every checkpoint carries
+    # {name}_{version}_embeddings.safetensors - its own load_checkpoint indexes that file ([0] over *embeddings.safetensors).
+    # With disable_ti the rows are the initialised-but-never-trained ones the UNet was conditioned on (TOK captions).
+    handler = TokenEmbeddingsHandler(list(text_encoders))
+    handler.inserting_toks = config.inserting_list_tokens
+    if config.disable_ti:
+        te0 = next(te for te in trainer.text_encoders if te is not None) if any(te is not None for te in trainer.text_encoders) else None
+        vocab = te0.text_model.embeddings.token_embedding.weight.shape[0] if te0 is not None else 0
+        handler.train_ids, handler.rows = list(range(vocab, vocab + config.n_tokens)), trainer.frozen_rows
+    else:
+        handler.train_ids, handler.rows = trainer.train_ids, trainer.ti_rows
     dev = trainer.device
     n = len(dataset)
     bs = config.train_batch_size

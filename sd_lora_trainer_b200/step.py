@@ -82,6 +82,32 @@ def lr_schedule(cfg: StepConfig, global_step: int, completion_f: float):
     return ti_lr, unet_lr
 
 
+class _PinnedRing:
+    """A small ring of pinned host buffers for the per-step scalar block: the async H2D copy of step n must have READ its
+    buffer before the host repacks it, and a host that runs ahead of the stream (graph replay, no per-step read-back) would
+    otherwise overwrite it.  next() hands out the oldest slot after waiting for its copy; push() enqueues the copy."""
+
+    def __init__(self, numel: int, slots: int = 8):
+        cuda = torch.cuda.is_available()
+        self.bufs = [torch.zeros(numel, dtype=torch.float32).pin_memory() if cuda else torch.zeros(numel, dtype=torch.float32)
+                     for _ in range(slots)]
+        self.events = [None] * slots
+        self.i = -1
+
+    def next(self) -> torch.Tensor:
+        self.i = (self.i + 1) % len(self.bufs)
+        if self.events[self.i] is not None:
+            self.events[self.i].synchronize()
+        return self.bufs[self.i]
+
+    def push(self, dev: torch.Tensor):
+        dev.copy_(self.bufs[self.i], non_blocking=True)
+        if dev.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.events[self.i] = ev
+
+
 class TrainerB200:
     """Owns the UNet executor, the flat parameter/gradient/moment buffers and the text encoders."""
 
@@ -190,9 +216,9 @@ class TrainerB200:
         self._tid = None
         self.launches_per_step = 0
         self._hyper_dev = torch.zeros(12, dtype=torch.float32, device=self.device)
-        self._hyper_host = torch.zeros(12, dtype=torch.float32)
-        if torch.cuda.is_available():
-            self._hyper_host = self._hyper_host.pin_memory()
+        self._hyper_ring = _PinnedRing(12)
+        for name, (lo, hi, scal, host, dev, kw) in list(self._prodigy.items()):
+            self._prodigy[name] = (lo, hi, scal, _PinnedRing(12), dev, kw)
 
     def _time_ids(self, B: int) -> torch.Tensor:
         if self._tid is None or self._tid.shape[0] != B:      # built once, outside any graph capture
@@ -380,6 +406,22 @@ class TrainerB200:
             out.append(shared[L])
         return tal, out
 
+    def reset_optimizer_state(self):
+        """After parameters were overwritten from a checkpoint (load_lora_weights / load_embeddings): Adam moments and
+        Prodigy's s restart from zero, Prodigy's start point p0 is re-snapshotted, the d estimate restarts, cached
+        conditioning is dropped (the reference builds fresh optimizers after loading, main.py:116-176)."""
+        for p, g, m, v, _ in self._train_sets():
+            g.zero_()
+            m.zero_()
+            v.zero_()
+        if self._prodigy:
+            self._prodigy_s.zero_()
+            self._prodigy_p0.copy_(self.store.params)
+            for name, (lo, hi, scal, ring, dev, kw) in self._prodigy.items():
+                scal.copy_(ops.prodigy_init_scalars(1e-6, self.device))
+        self._text_cache.clear()
+        self.opt_step = 0
+
     # ---- optimizer: ONE kernel over LoRA factors + TI rows -------------------------------------------
     def _l1_coeff(self) -> float:
         if self.cfg.l1_penalty <= 0.0 or self.store.n_lora == 0:
@@ -390,14 +432,16 @@ class TrainerB200:
     def _set_hyper(self):
         """Pack this optimizer step's scalars on the host and refresh the device copy (outside any graph)."""
         ti_lr, unet_lr = self.last_lrs
-        ops.adamw_pack_hyper(self._hyper_host, lr=unet_lr, wd=self.cfg.lora_weight_decay, l1_coeff=self._l1_coeff(),
+        host = self._hyper_ring.next()
+        ops.adamw_pack_hyper(host, lr=unet_lr, wd=self.cfg.lora_weight_decay, l1_coeff=self._l1_coeff(),
                              lr2=ti_lr or 0.0, wd2=self.cfg.ti_weight_decay, step=self.opt_step + 1, grad_scale=1.0)
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
-        for name, (lo, hi, scal, host, dev, kw) in self._prodigy.items():
+        self._hyper_ring.push(self._hyper_dev)
+        for name, (lo, hi, scal, ring, dev, kw) in self._prodigy.items():
             # k counts this optimizer's steps (the package skips the increment only when every gradient is exactly zero)
+            host = ring.next()
             ops.prodigy_pack_hyper(host, lr=unet_lr if name == "unet" else 1.0, k=self.opt_step,
                                    l1_coeff=self._l1_coeff() if name == "unet" else 0.0, **kw)
-            dev.copy_(host, non_blocking=True)
+            ring.push(dev)
 
     def _train_sets(self):
         """The (params, grads, m, v, n_first) buffer sets the optimizer walks: the flat LoRA + TI buffers; in dense (full

@@ -142,12 +142,16 @@ def save_checkpoint(output_dir: str, global_step: int, unet, embedding_handler, 
               os.path.join(output_dir, f"{name}_{pretrained_model_version}_lora.safetensors"))
 
 
-def load_lora_weights(lora_path: str, unet) -> None:
+def load_lora_weights(lora_path: str, unet, trainer=None) -> None:
     """Read a ``*_lora.safetensors`` written by save_checkpoint back into the executor's flat LoRA buffer (the training-side
-    counterpart of the reference's inference-only load_checkpoint, checkpoint.py:223-297)."""
+    counterpart of the reference's inference-only load_checkpoint, checkpoint.py:223-297).  Pass the owning ``trainer``
+    (TrainerB200) when training continues afterwards: its optimizer state (Adam moments, Prodigy's p0 / s / d) and
+    conditioning cache refer to the parameters they were built on and are reset."""
     from safetensors.torch import load_file
     sd = kohya_to_peft_keys(load_file(lora_path), [s.name for s in unet.store.slots])
     missing = [s.name for s in unet.store.slots if f"{s.name}.lora_A.default.weight" not in sd]
     if missing:
         raise KeyError(f"LoRA file lacks {len(missing)} modules, e.g. {missing[:3]}")
     unet.store.load_peft(sd)
+    if trainer is not None:
+        trainer.reset_optimizer_state()

@@ -76,7 +76,8 @@ class TokenEmbeddingsHandler:
             i += 1
         save_file(tensors, file_path)
 
-    def load_embeddings(self, file_path: str, txt_encoder_keys=("clip_l", "clip_g")):
+    def load_embeddings(self, file_path: str, txt_encoder_keys=("clip_l", "clip_g"), trainer=None):
+        """``trainer`` (TrainerB200, optional): reset its optimizer state / conditioning cache after the rows changed."""
         from safetensors.torch import load_file
         tensors, i = load_file(file_path), 0
         for idx, te in enumerate(self.text_encoders):
@@ -85,3 +86,5 @@ class TokenEmbeddingsHandler:
             with torch.no_grad():
                 self.rows[i].copy_(tensors[txt_encoder_keys[idx]].to(self.rows[i].device, self.rows[i].dtype))
             i += 1
+        if trainer is not None:
+            trainer.reset_optimizer_state()

@@ -58,3 +58,23 @@ def test_reference_call_sequence(monkeypatch, unet_opt, ti_opt):
                               FlatProdigy)
     with pytest.raises(NotImplementedError):
         get_unet_lora_parameters(4, 1.0, 0.004, True, None, pipe)                                   # DoRA
+
+
+def test_token_attention_loss_without_ti_tokens_has_finite_zero_gradients():
+    """trainer/loss.py:55-56: when no caption of the batch holds every trainable token the reference returns a grad-less
+    0.0; the tensorised form must give loss 0 and exactly-zero (not NaN) gradients."""
+    import torch
+    from sd_lora_trainer_b200.trainer.loss import token_attention_loss_from_maps, token_index_tensors
+    maps = torch.randn(3, 2, 4, 4, 77, dtype=torch.bfloat16).requires_grad_(True)
+    masks = torch.rand(2, 4, 8, 8)
+    tok_len, ti_pos = token_index_tensors([[1, 5, 6, 2], [1, 7, 2]], train_ids=[100, 101, 102])
+    assert int((ti_pos >= 0).sum()) == 0
+    loss = token_attention_loss_from_maps(maps, masks, tok_len, ti_pos)
+    loss.backward()
+    assert float(loss) == 0.0 and torch.isfinite(maps.grad).all() and float(maps.grad.abs().max()) == 0.0
+    # one caption with the tokens, one without: finite, non-zero
+    maps2 = maps.detach().clone().requires_grad_(True)
+    tok_len, ti_pos = token_index_tensors([[1, 100, 101, 102, 6, 2], [1, 7, 2]], train_ids=[100, 101, 102])
+    loss2 = token_attention_loss_from_maps(maps2, masks, tok_len, ti_pos)
+    loss2.backward()
+    assert float(loss2) > 0.0 and torch.isfinite(maps2.grad).all()

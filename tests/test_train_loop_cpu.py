@@ -117,7 +117,11 @@ def test_train_checkpoint_cadence_and_accumulation(monkeypatch, tmp_path):
     assert [c[2] for c in calls[:3]] == [2, 2, 1]
     assert [c[1] for c in calls[:6]] == [False, True, True, False, True, True]
     assert calls[0][0] == 0.0 and abs(calls[4][0] - (1 + 1 / 3) / 14) < 1e-6
-    assert not os.path.exists(os.path.join(out[1], "cadence_sd15_embeddings.safetensors"))      # disable_ti
+    # disable_ti still writes the (never-trained) token rows, as the reference does (main.py:92-100; its load_checkpoint
+    # indexes *embeddings.safetensors unconditionally)
+    from safetensors.torch import load_file
+    emb = load_file(os.path.join(out[1], "cadence_sd15_embeddings.safetensors"))
+    assert set(emb) == {"clip_l"} and emb["clip_l"].shape[0] == cfg.n_tokens
 
 
 def test_train_rejects_unsupported_modes(tmp_path):
@@ -167,7 +171,7 @@ def test_train_full_finetune_like_the_reference_example(monkeypatch, tmp_path):
         except StopIteration as stop:
             out_cfg, out_dir = stop.value
     assert sorted(os.listdir(out_dir)) == ["config.json", "diffusion_pytorch_model.safetensors", "special_params.json",
-                                           "training_args.json"]
+                                           "stitchly_sd15_embeddings.safetensors", "training_args.json"]
     trained = load_file(os.path.join(out_dir, "diffusion_pytorch_model.safetensors"))
     assert set(trained) == set(sd) and all(trained[k].shape == sd[k].shape for k in sd)
     changed = sum(int(not torch.equal(trained[k], sd[k])) for k in sd)

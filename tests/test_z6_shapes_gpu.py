@@ -25,10 +25,11 @@ def test_rank64_step_matches_oracle():
     tr.store.grads.zero_()
     out_2 = tr.step(inputs, completion_f=0.0, do_optimizer=False)            # captions come from the conditioning cache
     torch.cuda.synchronize()
-    # (stream-K adds its partial tiles with bf16 TMA reduce-adds in arrival order, split-K weight gradients use fp32 atomics:
-    #  the summation order is run-dependent, so two runs agree to bf16 noise - measured 2e-4 on the loss, 2e-2 on the
-    #  gradients of this tiny net (scripts/determinism.py; bit-identical with B200_STREAMK=0) - not bit for bit)
-    assert len(tr._text_cache) == 2 and abs(float(out_2["tot_loss"]) - a) <= 1e-3 * abs(a) and rel(tr.store.grads, g1) < 5e-2
+    # Two runs agree to bf16 noise, not bit for bit: the GroupNorm statistics are combined with fp32 shared-memory atomics
+    # (arrival order), stream-K adds its partial tiles with bf16 TMA reduce-adds, split-K / batched weight gradients use
+    # fp32 atomics.  scripts/determinism_trace.py pins the first differing op of two identical passes to groupnorm_fwd;
+    # profiles/r02b_determinism_trace.txt: loss spread 3e-4 (stream-K off) .. 1e-3 on these tiny random-weight nets.
+    assert len(tr._text_cache) == 2 and abs(float(out_2["tot_loss"]) - a) <= 3e-3 * abs(a) and rel(tr.store.grads, g1) < 5e-2
 
 
 @pytest.mark.parametrize("family,hw", [("sd15", 12), ("sdxl", 24)])
@@ -64,5 +65,5 @@ def test_shared_dscores_path_matches_per_layer_path(monkeypatch):
     torch.cuda.synchronize()
     # two runs of the SAME path already differ by bf16 summation-order noise (stream-K reduce-adds, see above)
     for k in ("img_loss", "token_attention_loss", "tot_loss"):
-        assert abs(float(out_a[k]) - float(out_b[k])) <= 1e-3 * abs(float(out_a[k])), k
+        assert abs(float(out_a[k]) - float(out_b[k])) <= 3e-3 * abs(float(out_a[k])), k
     assert rel(tr_b.store.grads, tr_a.store.grads) < 5e-2
