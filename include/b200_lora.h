@@ -130,17 +130,20 @@ int b200_lora_wgrad_batch(const b200_wgrad_problem_t* problems, int32_t n, void*
  * autograd backward (trainer/ti_cross_attn_loss.py:197-199, diffusers AttnProcessor2_0) without ever writing an
  * [L, Lk] tensor to HBM.  q: [B*L, ld], k/v: [B*Lk, ld] bf16 with head h at columns [h*64, h*64+64); o likewise.
  * lse: [B, H, L] fp32 (natural log), saved by the forward for the backward.
- * Backward workspaces (caller-owned): delta_ws fp32 [B*H*L], dq_acc_ws fp32 [B*L*ld].
+ * Row strides (elements, multiples of 8, >= H*64): forward ld for q / k / v and ld_o for o; backward ld_qkv for q / k / v,
+ * ld_o for o and d_o, ld_d for dq / dk / dv - so q | k | v (and their gradients) may be column slices of one [rows, 3C]
+ * buffer, the output of the fused q|k|v projection.
+ * Backward workspaces (caller-owned): delta_ws fp32 [B*H*L], dq_acc_ws fp32 [B*L*H*64] (NULL when Lk <= 128).
  * split_ws (optional, may be NULL): fp32 [2*B*Lk*ld + B*H] that is ZERO on entry and is left zero by the kernel; with it,
  * a single-key-block problem (Lk <= 128: every cross-attention layer) whose (H, B) grid would leave SMs idle splits its
  * query blocks over more CTAs (partial dK / dV summed with fp32 atomics, last CTA of a head rounds them to bf16).
  * --------------------------------------------------------------------------------------------------------- */
 int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t H,
-                        int32_t L, int32_t Lk, int64_t ld, float scale, void* stream);
+                        int32_t L, int32_t Lk, int64_t ld, int64_t ld_o, float scale, void* stream);
 int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                         float* delta_ws, float* dq_acc_ws, void* dq, void* dk, void* dv, int32_t B, int32_t H,
-                        int32_t L, int32_t Lk, int64_t ld, float scale, float* split_ws, int64_t split_ws_floats,
-                        void* stream);
+                        int32_t L, int32_t Lk, int64_t ld_qkv, int64_t ld_o, int64_t ld_d, float scale, float* split_ws,
+                        int64_t split_ws_floats, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Normalisation / activation kernels on NHWC ([rows, C]) bf16 activations; replace ATen GroupNorm / LayerNorm /
@@ -209,6 +212,12 @@ int b200_colsum(const void* x, void* out, float* scratch, int32_t batch, int64_t
  * elements into the flat buffers - bt[off_Bt + j*N + n] = params[off_B + n*rs + j].  The fused input-gradient GEMM
  * (dX = dY.W + (s.dY.B).A, peft lora.Linear backward) reads the copy as its side operand. table: device int64 [n, 4]. */
 int b200_lora_transpose_b(const void* params, void* bt, const int64_t* table, int32_t n_entries, void* stream);
+/* Derived LoRA-B operands of the fused q|k|v projection (to_q / to_k / to_v of a self-attention block as ONE N = 3C GEMM
+ * with a rank-3r side path, [3P] peft lora.Linear x3): per table row (off_B, off_dst, N, rs, dst_ld, transpose) - offsets
+ * in elements - dst[off_dst + n*dst_ld + j] = B[n, j] (transpose 0: a diagonal block of the [3C, 3r] block-diagonal
+ * factor) or dst[off_dst + j*dst_ld + n] = B[n, j] (transpose 1: its K-major transpose [3r, 3C] for the input gradient).
+ * table: device int64 [n, 6]; one launch per step refreshes every block. */
+int b200_lora_pack(const void* params, void* dst, const int64_t* table, int32_t n_entries, void* stream);
 /* Bicubic resize of channels-last bf16 maps: F.interpolate(x, size=(Ho, Wo), mode="bicubic") exactly as the reference
  * applies it to the captured cross-attention maps (trainer/ti_cross_attn_loss.py:262-266: align_corners=False, no
  * antialias, A = -0.75, clamped taps).  x: [B, Hi, Wi, C] with pixel stride ld_in, y: [B, Ho, Wo, C] with pixel stride

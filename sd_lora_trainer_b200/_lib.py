@@ -43,10 +43,10 @@ SIGNATURES = {
     "b200_gemm": [C.POINTER(GemmDesc), c_void_p],
     "b200_lora_wgrad_batch": [C.POINTER(WgradProblem), c_int32, c_void_p],
     "b200_flash_attn_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64,
-                            c_float, c_void_p],
+                            c_int64, c_float, c_void_p],
     "b200_flash_attn_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                            c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64, c_float, c_void_p, c_int64,
-                            c_void_p],
+                            c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_float, c_void_p,
+                            c_int64, c_void_p],
     "b200_softmax_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_softmax_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_groupnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32,
@@ -73,6 +73,7 @@ SIGNATURES = {
     "b200_shift_sum9": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p],
     "b200_colsum": [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p],
     "b200_lora_transpose_b": [c_void_p, c_void_p, c_void_p, c_int32, c_void_p],
+    "b200_lora_pack": [c_void_p, c_void_p, c_void_p, c_int32, c_void_p],
     "b200_bicubic_fwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
     "b200_bicubic_bwd": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_void_p],
     "b200_timestep_embedding": [c_void_p, c_void_p, c_int32, c_int32, c_void_p],

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 namespace b200 {
@@ -46,6 +47,13 @@ int encode_map_ex(CUtensorMap* map, const void* ptr, int elem_bytes, const long 
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// B200_PDL=0 (profiling aid): launch without the programmatic-serialization attribute, so kernels run strictly one after
+// the other and a profiler's per-kernel durations no longer include the time spent in griddepcontrol.wait.
+inline int pdl_enabled() {
+    static const int on = getenv("B200_PDL") ? atoi(getenv("B200_PDL")) : 1;
+    return on;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -55,7 +63,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
@@ -72,7 +80,7 @@ inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = cluster_x;
     attr[1].val.clusterDim.y = 1;

@@ -447,6 +447,31 @@ __global__ void lora_bt_kernel(const bf16* __restrict__ params, bf16* __restrict
     }
 }
 
+// Derived copies of LoRA-B factors for the fused q|k|v projection, one CTA per table row
+// (src_off, dst_off, N, rs, dst_ld, transpose):   transpose == 0: dst[n * dst_ld + j] = B[n, j]   (a diagonal block of the
+// block-diagonal [3C, 3r] factor of the forward);  transpose == 1: dst[j * dst_ld + n] = B[n, j]  (its K-major transpose,
+// the side operand of the input-gradient GEMM).  Everything outside the blocks stays zero (written once at allocation).
+__global__ void lora_pack_kernel(const bf16* __restrict__ params, bf16* __restrict__ dst_base, const long long* __restrict__ table) {
+    pdl_launch();
+    pdl_wait();
+    const long long* e = table + 6LL * blockIdx.x;
+    const bf16* src = params + e[0];
+    bf16* dst = dst_base + e[1];
+    const int N = static_cast<int>(e[2]), rs = static_cast<int>(e[3]);
+    const long long dst_ld = e[4];
+    if (e[5] == 0) {
+        for (int idx = threadIdx.x; idx < N * rs; idx += blockDim.x) {
+            const int n = idx / rs, j = idx - n * rs;
+            dst[n * dst_ld + j] = src[idx];
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < N * rs; idx += blockDim.x) {
+            const int j = idx / N, n = idx - j * N;           // consecutive threads -> consecutive n: coalesced writes
+            dst[j * dst_ld + n] = src[static_cast<long long>(n) * rs + j];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Bicubic resize of channels-last maps (F.interpolate(mode="bicubic", align_corners=False, antialias=False) as the
 // reference applies it to the captured cross-attention maps, ti_cross_attn_loss.py:262-266): A = -0.75, taps clamped
@@ -764,6 +789,13 @@ extern "C" int b200_lora_transpose_b(const void* params, void* bt, const int64_t
     launch_pdl(lora_bt_kernel, dim3(n_entries), dim3(256), 0, ST, static_cast<const bf16*>(params), static_cast<bf16*>(bt),
                reinterpret_cast<const long long*>(table));
     B200_CHECK_LAUNCH("lora_transpose_b");
+    return 0;
+}
+extern "C" int b200_lora_pack(const void* params, void* dst, const int64_t* table, int32_t n_entries, void* stream) {
+    B200_CHECK_ARG(n_entries >= 1 && params && dst && table, "lora_pack: bad arguments");
+    launch_pdl(lora_pack_kernel, dim3(n_entries), dim3(256), 0, ST, static_cast<const bf16*>(params), static_cast<bf16*>(dst),
+               reinterpret_cast<const long long*>(table));
+    B200_CHECK_LAUNCH("lora_pack");
     return 0;
 }
 extern "C" int b200_bicubic_fwd(const void* x, void* y, int32_t B, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t C,

@@ -14,8 +14,9 @@ static int head_map(CUtensorMap* map, const void* ptr, int rows, int H, int B, l
 }
 
 extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B,
-                                   int32_t H, int32_t L, int32_t Lk, int64_t ld, float scale, void* stream) {
-    B200_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && Lk >= 1 && ld >= static_cast<int64_t>(H) * 64 && ld % 8 == 0,
+                                   int32_t H, int32_t L, int32_t Lk, int64_t ld, int64_t ld_o, float scale, void* stream) {
+    B200_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && Lk >= 1 && ld >= static_cast<int64_t>(H) * 64 && ld % 8 == 0 &&
+                       ld_o >= static_cast<int64_t>(H) * 64 && ld_o % 8 == 0,
                    "flash_attn_fwd: bad extents");
     static bool attr = false;
     if (!attr) {
@@ -33,7 +34,7 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
     g.L = L;
     g.Lk = Lk;
     g.H = H;
-    g.o_ld = ld;
+    g.o_ld = ld_o;
     g.scale = scale;
     dim3 grid((L + 127) / 128, H, B);
     launch_pdl(flash_fwd_kernel, dim3(grid), dim3(kFaThreads), kFwdSmem, static_cast<cudaStream_t>(stream), g);
@@ -43,10 +44,14 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
 
 extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                                    const float* lse, float* delta_ws, float* dq_acc_ws, void* dq, void* dk, void* dv,
-                                   int32_t B, int32_t H, int32_t L, int32_t Lk, int64_t ld, float scale, float* split_ws,
-                                   int64_t split_ws_floats, void* stream) {
-    B200_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && Lk >= 1 && ld == static_cast<int64_t>(H) * 64,
-                   "flash_attn_bwd: needs contiguous [rows, H*64] tensors");
+                                   int32_t B, int32_t H, int32_t L, int32_t Lk, int64_t ld_qkv, int64_t ld_o, int64_t ld,
+                                   float scale, float* split_ws, int64_t split_ws_floats, void* stream) {
+    // ld_qkv: row stride of q / k / v; ld_o: of o and d_o; ld: of the outputs dq / dk / dv (the fused q|k|v projection hands
+    // column slices of one [rows, 3C] buffer in and takes the three gradients back the same way)
+    const int64_t C64 = static_cast<int64_t>(H) * 64;
+    B200_CHECK_ARG(B >= 1 && H >= 1 && L >= 1 && Lk >= 1 && ld_qkv >= C64 && ld_o >= C64 && ld >= C64 && ld_qkv % 8 == 0 &&
+                       ld_o % 8 == 0 && ld % 8 == 0,
+                   "flash_attn_bwd: row strides must be multiples of 8 elements and at least H*64");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static bool attr = false;
     if (!attr) {
@@ -54,22 +59,22 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
         if (e != cudaSuccess) return set_error(3, "flash_attn_bwd: %s", cudaGetErrorString(e));
         attr = true;
     }
-    const long long nq_elems = static_cast<long long>(B) * L * ld;
+    const long long nq_elems = static_cast<long long>(B) * L * C64;        // fp32 dQ accumulator: contiguous [B*L, H*64]
     const bool dq_direct = Lk <= 128;          // one key block: dQ is written once, as bf16, by the kernel itself
     if (!dq_direct) cudaMemsetAsync(dq_acc_ws, 0, sizeof(float) * nq_elems, st);
     launch_pdl(flash_delta_kernel, dim3(grid_for(static_cast<long long>(B) * L * H, 256)), dim3(256), 0, st, 
-        static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta_ws, B, L, H, ld);
+        static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta_ws, B, L, H, ld_o);
     B200_CHECK_LAUNCH("flash_delta");
     FlashBwdArgs g;
     memset(&g, 0, sizeof(g));
-    if (int rc = head_map(&g.mapQ, q, L, H, B, ld, 128)) return rc;
-    if (int rc = head_map(&g.mapDO, d_o, L, H, B, ld, 128)) return rc;
-    if (int rc = head_map(&g.mapK, k, Lk, H, B, ld, 128)) return rc;
-    if (int rc = head_map(&g.mapV, v, Lk, H, B, ld, 128)) return rc;
+    if (int rc = head_map(&g.mapQ, q, L, H, B, ld_qkv, 128)) return rc;
+    if (int rc = head_map(&g.mapDO, d_o, L, H, B, ld_o, 128)) return rc;
+    if (int rc = head_map(&g.mapK, k, Lk, H, B, ld_qkv, 128)) return rc;
+    if (int rc = head_map(&g.mapV, v, Lk, H, B, ld_qkv, 128)) return rc;
     if (!dq_direct) {
         B200_CHECK_ARG(dq_acc_ws != nullptr, "flash_attn_bwd: Lk > 128 needs the fp32 dQ accumulator workspace");
-        const long long dims[4] = {ld, L, B, 1};
-        const long long strides[3] = {ld, static_cast<long long>(L) * ld, 0};
+        const long long dims[4] = {C64, L, B, 1};
+        const long long strides[3] = {C64, static_cast<long long>(L) * C64, 0};
         const int box[4] = {32, 128, 1, 1};
         if (int rc = encode_map_ex(&g.mapDQ, dq_acc_ws, 4, dims, strides, box, 128)) return rc;
     }
@@ -106,7 +111,8 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     launch_pdl(flash_bwd_kernel, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     B200_CHECK_LAUNCH("flash_bwd");
     if (!dq_direct) {
-        launch_pdl(f32_to_bf16_kernel, dim3(grid_for(nq_elems / 4, 256)), dim3(256), 0, st, dq_acc_ws, static_cast<__nv_bfloat16*>(dq), nq_elems / 4);
+        launch_pdl(f32_to_bf16_kernel, dim3(grid_for(nq_elems / 4, 256)), dim3(256), 0, st, dq_acc_ws, static_cast<__nv_bfloat16*>(dq),
+                   nq_elems / 4, static_cast<int>(C64 / 4), static_cast<long long>(ld));
         B200_CHECK_LAUNCH("flash_dq_convert");
     }
     return 0;

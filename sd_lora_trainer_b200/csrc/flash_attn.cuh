@@ -707,7 +707,9 @@ __global__ void flash_delta_kernel(const __nv_bfloat16* __restrict__ O, const __
     }
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+// x: contiguous fp32 rows of 4*row4 elements -> y: bf16 rows with stride ld_y (elements)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4, int row4,
+                                   long long ld_y) {
     pdl_launch();
     pdl_wait();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
@@ -716,7 +718,9 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* _
         uint2 w;
         w.x = pack_bf16(v.x, v.y);
         w.y = pack_bf16(v.z, v.w);
-        reinterpret_cast<uint2*>(y)[i] = w;
+        const long long row = i / row4;
+        const int c4 = static_cast<int>(i - row * row4);
+        *reinterpret_cast<uint2*>(y + row * ld_y + 4 * c4) = w;
     }
 }
 

@@ -622,46 +622,50 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                 mbar_wait(&side_full_bar[acc], acc_phase);
                 tc_fence_after();
                 if (warp == 2 && lane == 0 && first_item) dbg_stamp(dbg, 8);
-                uint32_t raw[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
-                              static_cast<uint32_t>(acc_stages == 1 ? 256 : acc * 256 + kSideCol), raw);
-                tmem_ld_wait();
                 const int row = lane_base + lane;
                 uint8_t* trow = smem + k2TOff + row * 128;
-                uint32_t packed[16];
+                const int m = m_warp + lane;
+                __nv_bfloat16* tp = (n_blk == 0 && T_out != nullptr && m < e.M) ? T_out + static_cast<long long>(m) * t_ld : nullptr;
+                const bool t_vec = (side_r & 7) == 0 && (t_ld & 7) == 0;
+                // up to 64 side columns (rank 48 = the fused q|k|v projection), 32 at a time
+                for (int cc = 0; cc * 32 < r16; ++cc) {
+                    uint32_t raw[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
+                                  static_cast<uint32_t>((acc_stages == 1 ? 256 : acc * 256 + kSideCol) + cc * 32), raw);
+                    tmem_ld_wait();
+                    uint32_t packed[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(raw[2 * j]) * side_alpha,
-                                                                    __uint_as_float(raw[2 * j + 1]) * side_alpha);
-                    packed[j] = *reinterpret_cast<const uint32_t*>(&hh);
-                }
+                    for (int j = 0; j < 16; ++j) {
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(raw[2 * j]) * side_alpha,
+                                                                        __uint_as_float(raw[2 * j + 1]) * side_alpha);
+                        packed[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j * 8 < r16)
-                        *reinterpret_cast<uint4*>(trow + ((j ^ (row & 7)) * 16)) =
-                            make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) {
+                        if (cc * 32 + j * 8 < r16)
+                            *reinterpret_cast<uint4*>(trow + (((cc * 4 + j) ^ (row & 7)) * 16)) =
+                                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    }
+                    // T also leaves for the dB / dA weight-gradient GEMM
+                    if (tp != nullptr) {
+                        const __nv_bfloat16* pv = reinterpret_cast<const __nv_bfloat16*>(packed);
+                        if (t_vec) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (cc * 32 + j * 8 < side_r)
+                                    *reinterpret_cast<uint4*>(tp + cc * 32 + j * 8) =
+                                        make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (cc * 32 + j < side_r) tp[cc * 32 + j] = pv[j];
+                        }
+                    }
                 }
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(t_ready_leader);      // release.cluster: the leader's MMA reads this smem
-                // T also leaves for the dB / dA weight-gradient GEMM (after the hand-off: it is not on the critical path)
-                const int m = m_warp + lane;
-                if (n_blk == 0 && T_out != nullptr && m < e.M) {
-                    __nv_bfloat16* tp = T_out + static_cast<long long>(m) * t_ld;
-                    const __nv_bfloat16* pv = reinterpret_cast<const __nv_bfloat16*>(packed);
-                    if ((side_r & 7) == 0 && (t_ld & 7) == 0) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            if (j * 8 < side_r)
-                                *reinterpret_cast<uint4*>(tp + j * 8) =
-                                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < side_r) tp[j] = pv[j];
-                    }
-                }
             }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();

@@ -256,7 +256,7 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
         if (b2_bytes > b_bytes) b_bytes = b2_bytes;
     }
     if (d->side) {
-        B200_CHECK_ARG(d->side_r >= 1 && d->side_r <= 32, "gemm2: side rank %d out of range", d->side_r);
+        B200_CHECK_ARG(d->side_r >= 1 && d->side_r <= 64, "gemm2: side rank %d out of range", d->side_r);
         g.side = 1;
         g.side_r = d->side_r;
         g.side_r16 = ((d->side_r + 15) / 16) * 16;

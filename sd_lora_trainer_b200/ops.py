@@ -190,13 +190,14 @@ def lora_wgrad_batch(problems: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.
 
 # ---- fused attention (head_dim 64) -----------------------------------------------------------------
 def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, H: int, L: int, Lk: int, scale: float):
-    """q: [B*L, H*64], k/v: [B*Lk, H*64] bf16.  Returns (o [B*L, H*64] bf16, lse [B, H, L] fp32)."""
+    """q: [B*L, H*64], k/v: [B*Lk, H*64] bf16 (row-strided views allowed: column slices of a fused q|k|v buffer).
+    Returns (o [B*L, H*64] bf16, lse [B, H, L] fp32)."""
     ld = q.stride(0)
-    assert k.stride(0) == ld and v.stride(0) == ld and q.stride(1) == 1
+    assert k.stride(0) == ld and v.stride(0) == ld and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
     o = torch.empty(B * L, H * 64, dtype=BF16, device=q.device)
     lse = torch.empty(B, H, L, dtype=torch.float32, device=q.device)
     check(_lib.load().b200_flash_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), lse.data_ptr(),
-                                          B, H, L, Lk, ld, scale, _stream()), "flash_attn_fwd")
+                                          B, H, L, Lk, ld, o.stride(0), scale, _stream()), "flash_attn_fwd")
     return o, lse
 
 
@@ -212,23 +213,26 @@ def _flash_split_ws(device, floats: int) -> torch.Tensor:
     return ws
 
 
-def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale: float, dk=None, dv=None):
-    """Returns (dq [B*L, C], dk [B*Lk, C], dv [B*Lk, C]) bf16; dk / dv may be caller-provided contiguous buffers."""
+def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale: float, dk=None, dv=None, dq=None):
+    """Returns (dq [B*L, C], dk [B*Lk, C], dv [B*Lk, C]) bf16; dq / dk / dv may be caller-provided buffers that share one
+    row stride (e.g. the three column slices of a [rows, 3C] gradient buffer)."""
     C_ = H * 64
     dev = q.device
-    dq = torch.empty(B * L, C_, dtype=BF16, device=dev)
+    dq = torch.empty(B * L, C_, dtype=BF16, device=dev) if dq is None else dq
     dk = torch.empty(B * Lk, C_, dtype=BF16, device=dev) if dk is None else dk
     dv = torch.empty(B * Lk, C_, dtype=BF16, device=dev) if dv is None else dv
-    assert dk.is_contiguous() and dv.is_contiguous()
+    ld_d = dq.stride(0)
+    assert dk.stride(0) == ld_d and dv.stride(0) == ld_d and dq.stride(1) == 1 and dk.stride(1) == 1 and dv.stride(1) == 1
+    assert k.stride(0) == q.stride(0) and v.stride(0) == q.stride(0) and o.stride(0) == d_o.stride(0)
     delta = torch.empty(B * H * L, dtype=torch.float32, device=dev)
     single = Lk <= 128                                # one key block: dQ is written directly, no fp32 accumulator needed
     dq_acc = None if single else torch.empty(B * L * C_, dtype=torch.float32, device=dev)
-    ws_floats = 2 * B * Lk * C_ + B * H if (single and L > 128) else 0
+    ws_floats = 2 * B * Lk * ld_d + B * H if (single and L > 128) else 0
     ws = _flash_split_ws(dev, ws_floats) if ws_floats else None
     check(_lib.load().b200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
                                           lse.data_ptr(), delta.data_ptr(), _p(dq_acc), dq.data_ptr(),
-                                          dk.data_ptr(), dv.data_ptr(), B, H, L, Lk, C_, scale, _p(ws),
-                                          ws.numel() if ws is not None else 0, _stream()), "flash_attn_bwd")
+                                          dk.data_ptr(), dv.data_ptr(), B, H, L, Lk, q.stride(0), o.stride(0), ld_d, scale,
+                                          _p(ws), ws.numel() if ws is not None else 0, _stream()), "flash_attn_bwd")
     return dq, dk, dv
 
 
@@ -405,6 +409,12 @@ def lora_transpose_b(params: torch.Tensor, bt: torch.Tensor, table: torch.Tensor
     assert table.dtype == torch.int64 and table.is_cuda and table.dim() == 2 and table.shape[1] == 4
     check(_lib.load().b200_lora_transpose_b(params.data_ptr(), bt.data_ptr(), table.data_ptr(), table.shape[0], _stream()),
           "lora_transpose_b")
+
+
+def lora_pack(params: torch.Tensor, dst: torch.Tensor, table: torch.Tensor):
+    """Derived LoRA-B copies of the fused q|k|v projections: table rows (off_B, off_dst, N, rs, dst_ld, transpose), device int64."""
+    assert table.dtype == torch.int64 and table.is_cuda and table.dim() == 2 and table.shape[1] == 6
+    check(_lib.load().b200_lora_pack(params.data_ptr(), dst.data_ptr(), table.data_ptr(), table.shape[0], _stream()), "lora_pack")
 
 
 def bicubic_fwd(x: torch.Tensor, Ho: int, Wo: int):

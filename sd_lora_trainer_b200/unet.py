@@ -144,6 +144,9 @@ class LoraStore:
         self.by_name: Dict[str, LoraSlot] = {}
         self.total = 0
         self.params = self.grads = self.m = self.v = None
+        self.pack_rows: List[List[int]] = []
+        self.pack_total = 0
+        self.packed = self.pack_table = None
 
     def add(self, name: str, kind: str, r: int, fan_in: int, fan_out: int) -> LoraSlot:
         if name in self.by_name:                       # pre-allocated (contiguous batched groups)
@@ -158,11 +161,38 @@ class LoraStore:
         self.by_name[name] = s
         return s
 
+    def add_fused(self, names: List[str], r: int, fan_in: int, fan_outs: List[int]) -> List[LoraSlot]:
+        """Linear slots whose A factors sit back to back ([len(names)*r, fan_in] is one contiguous matrix): the q|k|v
+        projections of a self-attention block, run as ONE GEMM with a rank-3r side path (LinQKV)."""
+        slots = [LoraSlot(n, "linear", r, fan_in, fo) for n, fo in zip(names, fan_outs)]
+        for s in slots:
+            assert s.name not in self.by_name and (s.a_rows * fan_in) % 8 == 0
+            s.offA = self.total
+            self.total += s.a_rows * fan_in
+        for s in slots:
+            s.offB = self.total
+            self.total += _r8(s.fan_out * s.rs)
+            s.store = self
+            self.slots.append(s)
+            self.by_name[s.name] = s
+        return slots
+
+    def add_pack(self, rows: List[List[int]], numel: int) -> int:
+        """Reserve `numel` elements of the derived-operand buffer (zero except for the listed blocks) and register the
+        lora_pack table rows [off_B, off_dst (relative), N, rs, dst_ld, transpose]; returns the base offset."""
+        base = self.pack_total
+        for r_ in rows:
+            self.pack_rows.append([r_[0], base + r_[1], r_[2], r_[3], r_[4], r_[5]])
+        self.pack_total += _r8(numel)
+        return base
+
     def finalize(self, extra: int = 0):
         """`extra` trailing elements hold the trainable textual-inversion rows (same optimizer kernel)."""
         n = self.total + extra
         self.n_lora = self.total
         self.params = torch.zeros(n, dtype=BF16, device=self.device)
+        self.packed = torch.zeros(max(self.pack_total, 8), dtype=BF16, device=self.device)
+        self.pack_table = torch.tensor(self.pack_rows, dtype=torch.int64, device=self.device) if self.pack_rows else None
         # K-major copies of the linear layers' B factors (side operand of the fused input-gradient GEMM)
         rows, off = [], 0
         for s in self.slots:
@@ -179,6 +209,11 @@ class LoraStore:
     def refresh_bt(self):
         if self.bt_table is not None:
             ops.lora_transpose_b(self.params, self.params_bt, self.bt_table)
+
+    def refresh_packed(self):
+        """Block-diagonal LoRA-B operands of the fused q|k|v projections follow the trained factors (once per step)."""
+        if self.pack_table is not None:
+            ops.lora_pack(self.params, self.packed, self.pack_table)
 
     @property
     def numel_logical(self) -> int:
@@ -368,6 +403,79 @@ class Lin:
         return dx
 
 
+class LinQKV:
+    """to_q | to_k | to_v of a self-attention block as ONE projection: y[M, 3C] = x.W_qkv^T + (s.x.A_qkv^T).B_bd^T
+    with the three frozen weights stacked, the three LoRA-A factors contiguous ([3r, K]) and B_bd the block-diagonal
+    [3C, 3r] arrangement of the three LoRA-B factors (a derived buffer, LoraStore.refresh_packed); the input gradient
+    dx = dqkv.W_qkv + (s.dqkv.B_bd).A_qkv is ONE launch as well (side operand: the packed transpose of B_bd).  q, k, v and
+    their gradients are column slices of one [M, 3C] buffer.  Needs the CTA-pair kernel (side rank 3r <= 64, M >= 256);
+    smaller problems run the three projections separately."""
+
+    def __init__(self, lq: Lin, lk: Lin, lv: Lin):
+        self.lins = (lq, lk, lv)
+        self.C, self.K = lq.N, lq.K
+        self.W_all = torch.cat([lq.W, lk.W, lv.W], dim=0).contiguous()
+        for i, l in enumerate(self.lins):                           # views: the stacked copy is the only copy
+            l.W = self.W_all[i * self.C:(i + 1) * self.C]
+        self.bias = None
+        if any(l.b is not None for l in self.lins):
+            self.bias = torch.cat([l.b if l.b is not None else torch.zeros(self.C, dtype=BF16, device=lq.W.device) for l in self.lins])
+        lo = lq.lora
+        self.r, self.rs, self.store = lo.r, lo.rs, lo.store
+        assert self.r == self.rs and all(l.lora.offA == lo.offA + i * self.r * self.K for i, l in enumerate(self.lins))
+        C, rs = self.C, self.rs
+        rows = []
+        for i, l in enumerate(self.lins):
+            rows.append([l.lora.offB, i * C * 3 * rs + i * rs, C, rs, 3 * rs, 0])                      # B_bd [3C, 3rs]
+            rows.append([l.lora.offB, 3 * C * 3 * rs + i * rs * 3 * C + i * C, C, rs, 3 * C, 1])        # Bt_bd [3rs, 3C]
+        self.pack_off = self.store.add_pack(rows, 2 * 3 * C * 3 * rs)
+        self.x = self.T = None
+
+    def usable(self, M: int) -> bool:
+        return M >= 256 and self.K >= 64 and self.C >= 64      # what the CTA-pair kernel takes (gemm_host.cu: pair_eligible)
+
+    def _a_all(self):
+        lo = self.lins[0].lora
+        return self.store.params[lo.offA:lo.offA + 3 * self.r * self.K].view(3 * self.r, self.K)
+
+    def _b_bd(self):
+        n = 3 * self.C * 3 * self.rs
+        return self.store.packed[self.pack_off:self.pack_off + n].view(3 * self.C, 3 * self.rs)
+
+    def _bt_bd(self):
+        n = 3 * self.C * 3 * self.rs
+        return self.store.packed[self.pack_off + n:self.pack_off + 2 * n].view(3 * self.rs, 3 * self.C)
+
+    def fwd(self, x: torch.Tensor) -> torch.Tensor:
+        M, C, K, r3 = x.shape[0], self.C, self.K, 3 * self.r
+        y = torch.empty(M, 3 * C, dtype=BF16, device=x.device)
+        T = torch.empty(M, 3 * self.rs, dtype=BF16, device=x.device)
+        side = (Mat(self._a_all(), r3, K, K), Mat(self._b_bd(), 3 * C, r3, 3 * self.rs), r3, self.store.scaling, T)
+        ops.gemm(y, M, 3 * C, [(kmajor(x), kmajor(self.W_all), K)], bias=self.bias, side=side, static_b=True, pair_mode=1)
+        self.x, self.T = x, T
+        return y
+
+    def bwd(self, dqkv: torch.Tensor) -> torch.Tensor:
+        M, C, K, r, rs = dqkv.shape[0], self.C, self.K, self.r, self.rs
+        x, T = self.x, self.T
+        self.x = self.T = None
+        U = torch.empty(M, 3 * rs, dtype=BF16, device=dqkv.device)
+        dx = torch.empty(M, K, dtype=BF16, device=dqkv.device)
+        side = (Mat(self._bt_bd(), 3 * r, 3 * C, 3 * C), Mat(self._a_all(), 3 * r, K, K, mn=True), 3 * r, self.store.scaling, U)
+        ops.gemm(dx, M, K, [(kmajor(dqkv), mnmajor(self.W_all), 3 * C)], side=side, static_b=True, pair_mode=1)
+        # six weight-gradient problems: dB_i = dqkv_i^T . T_i, dA_i = U_i^T . x  (column slices of the fused buffers)
+        items = []
+        for i, l in enumerate(self.lins):
+            lo = l.lora
+            items.append((dqkv[:, i * C:(i + 1) * C], T[:, i * rs:(i + 1) * rs], lo.gB(), M, C, r, rs, 1))
+            items.append((x, U[:, i * rs:(i + 1) * rs], lo.gA(), M, K, r, 1, K))
+        if WQ.active:
+            WQ.items.extend(items)
+        else:
+            ops.lora_wgrad_batch(items)
+        return dx
+
+
 class Conv3:
     """Frozen 3x3 / pad 1 convolution on NHWC activations as an implicit GEMM (stride 1) or im2col GEMM (stride 2),
     optionally with the PEFT conv-LoRA side path (3x3 A: C->r, 1x1 B: r->C)."""
@@ -532,16 +640,22 @@ class Attn:
         self.sv = None
         self.kv_batch: Optional["CrossKVBatch"] = None     # set for cross-attention layers whose K/V are batched
         self.kv_index = -1
+        self.qkv: Optional[LinQKV] = None                  # set for self-attention layers whose q|k|v run as one projection
 
     def fwd(self, x, ctx, B: int, L: int, Lk: int, residual):
         C = self.to_q.N
         H, d = self.h, C // self.h
         src = ctx if self.cross else x
-        q = self.to_q.fwd(x)
-        if self.kv_batch is not None:
-            k, v = self.kv_batch.kv(self.kv_index)
+        fused = self.qkv is not None and self.qkv.usable(x.shape[0])
+        if fused:
+            qkv = self.qkv.fwd(x)
+            q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
         else:
-            k, v = self.to_k.fwd(src), self.to_v.fwd(src)
+            q = self.to_q.fwd(x)
+            if self.kv_batch is not None:
+                k, v = self.kv_batch.kv(self.kv_index)
+            else:
+                k, v = self.to_k.fwd(src), self.to_v.fwd(src)
         scale = d ** -0.5
         Lp = _r8(Lk)
         dev = x.device
@@ -575,11 +689,11 @@ class Attn:
                      d_strides=(Lp, 1, 0, L * Lp), alpha=scale, nb0=1, nb1=B)
             self.scores = sc[:, :, :Lk]
         y = self.to_out.fwd(O, residual=residual)
-        self.sv = (q, k, v, P, B, L, Lk, fa, lse)
+        self.sv = (q, k, v, P, B, L, Lk, fa, lse, fused)
         return y
 
     def bwd(self, dy, d_ctx_accum, dscores: Optional[torch.Tensor]):
-        q, k, v, P, B, L, Lk, fa, lse = self.sv
+        q, k, v, P, B, L, Lk, fa, lse, fused = self.sv
         self.sv = None
         C = self.to_q.N
         H, d = self.h, C // self.h
@@ -587,16 +701,19 @@ class Attn:
         Lp = _r8(Lk)
         dev = dy.device
         dO = self.to_out.bwd(dy)
-        dK_out = dV_out = None
+        dQ_out = dK_out = dV_out = dqkv = None
         if self.kv_batch is not None:
             dK_out, dV_out = self.kv_batch.dkv(self.kv_index)
+        if fused:                                      # the three gradients land in column slices of one [M, 3C] buffer
+            dqkv = torch.empty(B * L, 3 * C, dtype=BF16, device=dev)
+            dQ_out, dK_out, dV_out = dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]
         if fa is not None and d == 64:
             qf, kf, vf, Of = fa
-            dQ, dK, dV = ops.flash_attn_bwd(qf, kf, vf, Of, dO, lse, B, H, L, Lk, scale, dk=dK_out, dv=dV_out)
+            dQ, dK, dV = ops.flash_attn_bwd(qf, kf, vf, Of, dO, lse, B, H, L, Lk, scale, dk=dK_out, dv=dV_out, dq=dQ_out)
         elif fa is not None:
             qf, kf, vf, Of = fa
             dQf, dKf, dVf = ops.flash_attn_bwd(qf, kf, vf, Of, ops.head_pad(dO, H, d, 64), lse, B, H, L, Lk, scale)
-            dQ = ops.head_pad(dQf, H, 64, d)
+            dQ = ops.head_pad(dQf, H, 64, d, out=dQ_out)
             dK = ops.head_pad(dKf, H, 64, d, out=dK_out)
             dV = ops.head_pad(dVf, H, 64, d, out=dV_out)
         else:
@@ -635,6 +752,8 @@ class Attn:
                                   Mat(q, L, C, C, mn=True, sb1=L * C, batched=True), L)],
                      d_strides=(C, 1, 0, Lk * C), alpha=scale, residual=dK, r_strides=(C, 1, 0, Lk * C), nb0=1, nb1=B)
         self.scores = None
+        if fused:
+            return self.qkv.bwd(dqkv)
         dx = self.to_q.bwd(dQ)
         if self.kv_batch is not None:
             pass                                       # dK / dV already sit in the group's buffer; handled at the end
@@ -817,6 +936,15 @@ class UNetB200:
                         for proj in ("to_k", "to_v"):
                             w = sd[f"{pth}.{proj}.weight"]
                             self.store.add(f"{pth}.{proj}", "linear", lora_rank, w.shape[1], w.shape[0])
+        # self-attention q|k|v as one projection: the three LoRA-A factors of a block are allocated back to back
+        self.fuse_qkv = (os.environ.get("B200_FUSE_QKV", "1") != "0" and not dense and lora_rank > 0 and lora_rank % 8 == 0
+                         and 3 * lora_rank <= 64)
+        if self.fuse_qkv:
+            for key in sd:
+                if key.endswith(".attn1.to_q.weight"):
+                    pth = key[:-len(".to_q.weight")]
+                    w = sd[key]
+                    self.store.add_fused([f"{pth}.to_q", f"{pth}.to_k", f"{pth}.to_v"], lora_rank, w.shape[1], [w.shape[0]] * 3)
         a, boc, g = arch, arch.block_out_channels, arch.norm_num_groups
         ted = a.time_embed_dim
         self.time1, self.time2 = self._lin("time_embedding.linear_1"), self._lin("time_embedding.linear_2")
@@ -944,6 +1072,9 @@ class UNetB200:
             self._cross[p] = at
         if cross and hook:
             self.hooked.append(at)
+        d = at.to_q.N // heads
+        if not cross and self.fuse_qkv and (d == 64 or (d < 64 and d % 8 == 0)) and at.to_q.K == at.to_k.K == at.to_v.K:
+            at.qkv = LinQKV(at.to_q, at.to_k, at.to_v)
         return at
 
     def _transformer(self, p: str, dim: int, heads: int, depth: int, hook: bool) -> Transformer2D:
@@ -971,6 +1102,7 @@ class UNetB200:
         Returns (pred [B*H*W, 8] with channels 0..3 valid, [head-summed scores [B, HW_l, Lctx]] per hooked layer)."""
         a = self.arch
         Lctx = ctx.shape[1]
+        self.store.refresh_packed()                    # derived LoRA-B operands follow the optimizer's last update
         ctx2 = ctx.reshape(B * Lctx, ctx.shape[2]).contiguous()
         t_emb = ops.timestep_embedding(timesteps, a.block_out_channels[0])
         e1 = self.time1.fwd(t_emb)

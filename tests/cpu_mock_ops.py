@@ -50,7 +50,7 @@ def _chk_tma(m: Mat, what: str):
         assert (st * 2) % 16 == 0, f"{what}: {name} stride {st} elements is not a multiple of 16 bytes"
 
 
-def _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out):
+def _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out, pair_mode=0):
     """Argument rules of b200_gemm (gemm_host.cu) that are not implied by the arithmetic."""
     assert M >= 1 and N >= 1 and len(segs) in (1, 2) and nb0 >= 1 and nb1 >= 1 and splits >= 1
     assert out.dtype in (torch.float32, BF16)
@@ -72,7 +72,10 @@ def _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out):
     assert splits <= kblocks0, f"more splits ({splits}) than K blocks ({kblocks0})"
     if side is not None:
         s_mat, b2_mat, r, _, t_out = side
-        assert len(segs) == 1 and not conv and nb0 == 1 and nb1 == 1 and splits == 1 and 1 <= r <= 32, "side path rules"
+        assert len(segs) == 1 and not conv and nb0 == 1 and nb1 == 1 and splits == 1 and 1 <= r <= 64, "side path rules"
+        # ranks above 32 exist only in the CTA-pair kernel (gemm_host.cu: pair_eligible + the size gate)
+        assert r <= 32 or (M >= 256 and N >= 64 and (pair_mode > 0 or M * N >= 256 * 512) and segs[0][2] >= 64
+                           and not segs[0][0].mn and out.dtype == BF16), "side rank > 32 needs a pair-kernel problem"
         _chk_tma(s_mat, "S")
         _chk_tma(b2_mat, "B2")
     if group_out is not None:
@@ -82,7 +85,7 @@ def _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out):
 
 def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, bias_sb=0, residual=None,
          r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0, side=None, pair_mode=0, group_out=None, static_b=False):
-    _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out)
+    _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out, pair_mode)
     assert residual is None or residual.dtype == BF16
     if group_out is not None:                       # two independent problems sharing one launch
         out2, (sm2, sn2) = group_out
@@ -152,21 +155,25 @@ def lora_wgrad_batch(problems):
 
 def flash_attn_fwd(q, k, v, B, H, L, Lk, scale):
     C_ = H * 64
-    q4 = q.float().view(B, L, H, 64).transpose(1, 2)
-    k4 = k.float().view(B, Lk, H, 64).transpose(1, 2)
-    v4 = v.float().view(B, Lk, H, 64).transpose(1, 2)
+    assert q.stride(0) % 8 == 0 and k.stride(0) == q.stride(0) and v.stride(0) == q.stride(0)
+    q4 = q.float().reshape(B, L, H, 64).transpose(1, 2)
+    k4 = k.float().reshape(B, Lk, H, 64).transpose(1, 2)
+    v4 = v.float().reshape(B, Lk, H, 64).transpose(1, 2)
     s = q4 @ k4.transpose(-1, -2) * scale
     o = torch.softmax(s, -1).to(BF16).float() @ v4
     return _bf(o.transpose(1, 2).reshape(B * L, C_)), torch.logsumexp(s, -1)
 
 
-def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale, dk=None, dv=None):
+def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale, dk=None, dv=None, dq=None):
     C_ = H * 64
-    q4 = q.float().view(B, L, H, 64).transpose(1, 2).detach().requires_grad_(True)
-    k4 = k.float().view(B, Lk, H, 64).transpose(1, 2).detach().requires_grad_(True)
-    v4 = v.float().view(B, Lk, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    assert k.stride(0) == q.stride(0) and v.stride(0) == q.stride(0) and o.stride(0) == d_o.stride(0)
+    for t in (dq, dk, dv):
+        assert t is None or (t.stride(1) == 1 and t.stride(0) % 8 == 0 and (t.storage_offset() * 2) % 16 == 0)
+    q4 = q.float().reshape(B, L, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    k4 = k.float().reshape(B, Lk, H, 64).transpose(1, 2).detach().requires_grad_(True)
+    v4 = v.float().reshape(B, Lk, H, 64).transpose(1, 2).detach().requires_grad_(True)
     out = torch.softmax(q4 @ k4.transpose(-1, -2) * scale, -1) @ v4
-    out.backward(d_o.float().view(B, L, H, 64).transpose(1, 2))
+    out.backward(d_o.float().reshape(B, L, H, 64).transpose(1, 2))
     unh = lambda t, n: _bf(t.transpose(1, 2).reshape(B * n, C_))
     gk, gv = unh(k4.grad, Lk), unh(v4.grad, Lk)
     if dk is not None:
@@ -175,7 +182,11 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale, dk=None, dv=None):
     if dv is not None:
         dv.copy_(gv)
         gv = dv
-    return unh(q4.grad, L), gk, gv
+    gq = unh(q4.grad, L)
+    if dq is not None:
+        dq.copy_(gq)
+        gq = dq
+    return gq, gk, gv
 
 
 def softmax_fwd(S, P, rows, cols, ld_s, ld_p):
@@ -385,6 +396,15 @@ def colsum(x, batch, hw, C_):
 def lora_transpose_b(params, bt, table):
     for off_b, off_bt, n, rs in table.tolist():
         bt[off_bt:off_bt + n * rs].view(rs, n).copy_(params[off_b:off_b + n * rs].view(n, rs).t())
+
+
+def lora_pack(params, dst, table):
+    for off_b, off_d, N, rs, dst_ld, tr in table.tolist():
+        src = params[off_b:off_b + N * rs].view(N, rs)
+        if tr:
+            _view(dst, (rs, N), (dst_ld, 1), off_d).copy_(src.t())
+        else:
+            _view(dst, (N, rs), (dst_ld, 1), off_d).copy_(src)
 
 
 def bicubic_fwd(x, Ho, Wo):

@@ -74,7 +74,9 @@ def test_pair_b_mn_major_dgrad(M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K,r", [(256, 128, 128, 16), (2048, 1280, 1280, 16), (300, 640, 320, 8), (2048, 640, 2048, 32),
-                                     (1000, 200, 136, 4), (8192, 640, 640, 16), (4096, 2560, 640, 16)])
+                                     (1000, 200, 136, 4), (8192, 640, 640, 16), (4096, 2560, 640, 16),
+                                     (2048, 3840, 1280, 48), (8192, 1920, 640, 48), (512, 384, 128, 24), (300, 264, 200, 64),
+                                     (2048, 3840, 1280, 40)])
 def test_pair_fused_side_path_forward(M, N, K, r):
     """Y = X.W^T + (s.X.A^T).B^T as ONE launch on CTA pairs (incl. the single-accumulator BN = 256 configuration)."""
     from sd_lora_trainer_b200 import ops
@@ -107,6 +109,23 @@ def test_pair_fused_side_block_n(bn):
     Tref = (x.float() @ A.float().T).to(BF)
     _close(T, Tref, what=f"pair T bn={bn}")
     _close(y, x.float() @ w.float().T + Tref.float() @ Bm.float().T, what=f"pair side bn={bn}")
+
+
+@pytest.mark.parametrize("M,N,K,r", [(2048, 3840, 1280, 48), (8192, 1920, 640, 48), (512, 384, 128, 24), (300, 264, 200, 64)])
+def test_pair_wide_side_path_dgrad_kmajor_s(M, N, K, r):
+    """The fused q|k|v input gradient: dX[M, K] = dY[M, N=3C].W + (s.dY.Bt^T).A with the side operand S = Bt [r, N] K-major
+    (the packed transpose of the block-diagonal LoRA-B) and rank up to 64."""
+    from sd_lora_trainer_b200 import ops
+    dy, w = _rand(M, N), _rand(N, K, seed=1, scale=0.05)
+    A = _rand(r, K, seed=2, scale=0.1)
+    Bt = _rand(r, N, seed=3, scale=0.1)
+    U = torch.empty(M, r, dtype=BF, device="cuda")
+    dx = torch.empty(M, K, dtype=BF, device="cuda")
+    ops.gemm(dx, M, K, [(ops.kmajor(dy), ops.mnmajor(w), N)], side=(ops.Mat(Bt, r, N, N), ops.Mat(A, r, K, K, mn=True), r, 2.0, U),
+             pair_mode=1, static_b=True)
+    Uref = (2.0 * (dy.float() @ Bt.float().T)).to(BF)
+    _close(U, Uref, what="pair wide U out")
+    _close(dx, dy.float() @ w.float() + Uref.float() @ A.float(), what="pair wide side dgrad")
 
 
 @pytest.mark.parametrize("M,N,K,r", [(512, 640, 320, 16), (2048, 1280, 1280, 16), (300, 264, 200, 8), (2048, 1280, 1280, 32),

@@ -37,7 +37,9 @@ def _setup(family, rank, batch, hw, disable_ti=False):
 
 # hw = 12: a latent width that does not divide 128 (768x768 trains 96-wide maps, training_args_face_sd15.json): every 3x3
 # convolution and conv-LoRA takes the im2col fallback
-@pytest.mark.parametrize("family,rank,batch,hw", [("sdxl", 8, 2, 8), ("sd15", 4, 1, 8), ("sd15", 8, 1, 12)])
+# ("sdxl", 16, 2, 32): 512 tokens at the first attention level - the fused q|k|v projection (rank-48 side path, LinQKV) runs
+# there, the separate-projection fallback below it
+@pytest.mark.parametrize("family,rank,batch,hw", [("sdxl", 8, 2, 8), ("sd15", 4, 1, 8), ("sd15", 8, 1, 12), ("sdxl", 16, 2, 32)])
 def test_step_host_logic_matches_oracle(monkeypatch, family, rank, batch, hw):
     cpu_mock_ops.install(monkeypatch)
     cfg, orc, tr, inputs = _setup(family, rank, batch, hw)

@@ -67,3 +67,25 @@ def test_shared_dscores_path_matches_per_layer_path(monkeypatch):
     for k in ("img_loss", "token_attention_loss", "tot_loss"):
         assert abs(float(out_a[k]) - float(out_b[k])) <= 3e-3 * abs(float(out_a[k])), k
     assert rel(tr_b.store.grads, tr_a.store.grads) < 5e-2
+
+
+@pytest.mark.parametrize("family,rank,hw", [("sdxl", 16, 32), ("sdxl", 8, 32), ("sd15", 8, 32)])
+def test_fused_qkv_projection_step_matches_oracle(family, rank, hw):
+    """Latents large enough (>= 256 tokens per attention level) for the fused q|k|v projection (unet.LinQKV: one N = 3C GEMM
+    with a rank-3r side path, q / k / v and their gradients as column slices of one buffer; sd15: plus the 32 -> 64 head
+    re-pitch on those slices) and the batched weight-gradient launch, on the real kernels against the bf16 oracle."""
+    from tests.test_unet_gpu import _build, _product, rel
+    import sd_lora_trainer_b200.unet as U
+    cfg, orc, inputs = _build(family, rank=rank, batch=2, hw=hw)
+    tr = _product(cfg, orc)
+    assert tr.unet.fuse_qkv and any(isinstance(getattr(b.attn1, "qkv", None), U.LinQKV)
+                                    for rs, at, ds in tr.unet.down if at is not None for t in at for b in t.blocks)
+    out_o = orc.step(inputs, completion_f=0.0, do_optimizer=False)
+    out_p = tr.step(inputs, completion_f=0.0, do_optimizer=False)
+    torch.cuda.synchronize()
+    for key in ("img_loss", "token_attention_loss", "tot_loss"):
+        a, b = float(out_p[key]), float(out_o[key])
+        assert abs(a - b) / abs(b) <= 2e-3, f"{key}: ours {a} vs bf16 oracle {b}"
+    ours = tr.store.export_peft(grads=True)
+    bad = [(n, rel(ours[n].reshape(p.grad.shape), p.grad)) for n, p in orc.unet.named_parameters() if p.grad is not None]
+    assert len(bad) == 2 * len(tr.store.slots) and not [x for x in bad if x[1] > 0.25], [x for x in bad if x[1] > 0.25][:5]
