@@ -146,16 +146,45 @@ __device__ __forceinline__ float block_max(float v, float* red) {
     return r;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+// Activations on the hardware special-function path.  Inputs and outputs are bf16 (relative resolution 4e-3); the kernels
+// that use these were bound by the libm forms (expf / erff / IEEE division: ~40-50 instructions per element, measured
+// 1.4 TB/s in gn_reduce_kernel<bwd, silu> - profiles/r02c), so:  sigmoid = rcp(1 + ex2(-x log2e)) with MUFU ex2 / rcp
+// (~2 ulp), erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7) sharing ONE exponential with the Gaussian pdf.
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float dsilu_f(float x) {
-    const float s = 1.f / (1.f + expf(-x));
+    const float s = sigmoid_f(x);
     return s * (1.f + x * (1.f - s));
 }
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// Phi(x) (standard normal cdf) and phi(x) (pdf) from one exponential
+__device__ __forceinline__ void normal_cdf_pdf(float x, float& cdf, float& pdf) {
+    const float e = __expf(-0.5f * x * x);                       // exp(-u^2) with u = |x| / sqrt(2)
+    const float u = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, u, 1.f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    const float tail = 0.5f * (p * t) * e;                       // 0.5 * erfc(u)
+    cdf = x >= 0.f ? 1.f - tail : tail;
+    pdf = 0.39894228040143267794f * e;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+    float cdf, pdf;
+    normal_cdf_pdf(x, cdf, pdf);
+    return x * cdf;
+}
 __device__ __forceinline__ float dgelu_f(float x) {
-    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-    return cdf + x * pdf;
+    float cdf, pdf;
+    normal_cdf_pdf(x, cdf, pdf);
+    return fmaf(x, pdf, cdf);
+}
+// gelu(x) and gelu'(x) together (GEGLU backward needs both for the same gate value)
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+    float cdf, pdf;
+    normal_cdf_pdf(x, cdf, pdf);
+    g = x * cdf;
+    dg = fmaf(x, pdf, cdf);
 }
 
 inline int grid_for(long long work_items, int threads, int max_blocks = kNumSMs * 16) {

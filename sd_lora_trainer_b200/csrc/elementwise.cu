@@ -169,8 +169,10 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __rest
         load8(dy + r * inner + v * 8, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            da[i] = d[i] * bfr(gelu_f(g[i]));
-            dg[i] = bfr(d[i] * a[i]) * dgelu_f(g[i]);
+            float gl, dgl;
+            gelu_both(g[i], gl, dgl);
+            da[i] = d[i] * bfr(gl);
+            dg[i] = bfr(d[i] * a[i]) * dgl;
         }
         store8(dh + r * 2 * inner + v * 8, da);
         store8(dh + r * 2 * inner + inner + v * 8, dg);

@@ -627,13 +627,15 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                 const int m = m_warp + lane;
                 __nv_bfloat16* tp = (n_blk == 0 && T_out != nullptr && m < e.M) ? T_out + static_cast<long long>(m) * t_ld : nullptr;
                 const bool t_vec = (side_r & 7) == 0 && (t_ld & 7) == 0;
-                // up to 64 side columns (rank 48 = the fused q|k|v projection), 32 at a time
-                for (int cc = 0; cc * 32 < r16; ++cc) {
+                // up to 64 side columns (rank 48 = the fused q|k|v projection), 32 at a time.  Columns 32.. (wide ranks only)
+                // go first, T_out copy included; columns 0..31 follow, and their T_out copy (the common rank-16 / 32 case)
+                // comes AFTER the hand-off to the MMA warp, off the critical path - one 16-register chunk stays live.
+                const uint32_t side_taddr = tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
+                                            static_cast<uint32_t>(acc_stages == 1 ? 256 : acc * 256 + kSideCol);
+                auto t_chunk = [&](int cc, uint32_t (&packed)[16]) {
                     uint32_t raw[32];
-                    tmem_ld32(tmem_base + (static_cast<uint32_t>(lane_base) << 16) +
-                                  static_cast<uint32_t>((acc_stages == 1 ? 256 : acc * 256 + kSideCol) + cc * 32), raw);
+                    tmem_ld32(side_taddr + cc * 32, raw);
                     tmem_ld_wait();
-                    uint32_t packed[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(raw[2 * j]) * side_alpha,
@@ -646,26 +648,34 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                             *reinterpret_cast<uint4*>(trow + (((cc * 4 + j) ^ (row & 7)) * 16)) =
                                 make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
                     }
-                    // T also leaves for the dB / dA weight-gradient GEMM
-                    if (tp != nullptr) {
+                };
+                auto t_out_chunk = [&](int cc, const uint32_t (&packed)[16]) {
+                    if (tp == nullptr) return;
+                    if (t_vec) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (cc * 32 + j * 8 < side_r)
+                                *reinterpret_cast<uint4*>(tp + cc * 32 + j * 8) =
+                                    make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    } else {
                         const __nv_bfloat16* pv = reinterpret_cast<const __nv_bfloat16*>(packed);
-                        if (t_vec) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (cc * 32 + j * 8 < side_r)
-                                    *reinterpret_cast<uint4*>(tp + cc * 32 + j * 8) =
-                                        make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (cc * 32 + j < side_r) tp[cc * 32 + j] = pv[j];
-                        }
+                        for (int j = 0; j < 32; ++j)
+                            if (cc * 32 + j < side_r) tp[cc * 32 + j] = pv[j];
                     }
+                };
+                if (r16 > 32) {
+                    uint32_t hi[16];
+                    t_chunk(1, hi);
+                    t_out_chunk(1, hi);
                 }
+                uint32_t lo16[16];
+                t_chunk(0, lo16);
                 tc_fence_before();
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(t_ready_leader);      // release.cluster: the leader's MMA reads this smem
+                t_out_chunk(0, lo16);
             }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
