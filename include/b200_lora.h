@@ -110,6 +110,28 @@ int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int
                      int64_t ld_dp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Token-attention regulariser, forward and gradient (replaces compute_token_attention_loss, trainer/loss.py:10-80, and its
+ * autograd backward): maps[l] -> bf16 [B, h*w, 77] cross-attention score maps of hooked layer l (row stride lds[l]
+ * elements), already at the common (smallest) resolution h x w (process_and_stack_attention_scores,
+ * trainer/ti_cross_attn_loss.py:239-268: larger maps go through b200_bicubic_fwd first).  mask: fp32 [B, Hm, Wm] with
+ * batch stride mask_sb elements (mask[:, 0], resized in-kernel like F.interpolate(mode="nearest")); tok_len[b] = len(tokenizer.encode(caption_b)),
+ * ti_pos[b, j] = position of trainable token j in caption b or -1.  loss_out[0] <- the regulariser; G (bf16
+ * [B, h*w, ld_g], may be NULL) <- grad_scale * d loss / d maps[l] - the SAME map for every layer l (the loss sees only the
+ * layer mean).  ws: fp32 workspace of B*h*w*77 + 8*B floats.  n_layers <= 64, 77 <= 80 text positions, <= 8 tokens.
+ * --------------------------------------------------------------------------------------------------------- */
+int b200_token_attention_loss(const void* const* maps, const int64_t* lds, int32_t n_layers, int32_t B, int32_t h, int32_t w,
+                              int32_t n_text, const float* mask, int64_t mask_sb, int32_t Hm, int32_t Wm, const int64_t* tok_len,
+                              const int64_t* ti_pos, int32_t n_tok, float grad_scale, float* ws, int64_t ws_floats,
+                              float* loss_out, void* G, int64_t ld_g, void* stream);
+/* Token-std regulariser (ConditioningRegularizer.apply_regularization -> DistributionLoss.compute_std_loss,
+ * trainer/loss.py:222-231, 291-297) over the n_rows trainable embedding rows of 1 or 2 text encoders:
+ * loss_out[0] += mean_e mean_rows (mu_t[e] - std(row))^2 / var_t[e]; grads_e (fp32 [n_rows, dim_e], may be NULL) +=
+ * coeff * d/d rows of that mean (coeff = 0.01 / gradient accumulation in the step). */
+int b200_token_std_loss(const void* rows0, const void* rows1, float* grads0, float* grads1, int32_t n_enc, int32_t n_rows,
+                        int32_t dim0, int32_t dim1, float mu_t0, float var_t0, float mu_t1, float var_t1, float coeff,
+                        float* loss_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Batched LoRA weight gradients (replaces autograd's dW of every lora_A / lora_B nn.Linear of a transformer block,
  * main.py:363 -> [3P] peft lora.Linear): out_p[n, j] += sum_m X_p[m, n] * Y_p[m, j] for up to 32 independent problems in ONE
  * launch - dB = dY^T.T (X = dY [M, N], Y = T = s.x.A^T [M, r], out = dB [N, r]) and dA = U^T.x (X = x [M, K],

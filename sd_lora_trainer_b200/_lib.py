@@ -41,6 +41,10 @@ SIGNATURES = {
     "b200_last_error": [],
     "b200_launch_count": [],
     "b200_gemm": [C.POINTER(GemmDesc), c_void_p],
+    "b200_token_attention_loss": [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int64, c_int32, c_int32,
+                                  c_void_p, c_void_p, c_int32, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p],
+    "b200_token_std_loss": [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_float,
+                            c_float, c_float, c_float, c_void_p, c_void_p],
     "b200_lora_wgrad_batch": [C.POINTER(WgradProblem), c_int32, c_void_p],
     "b200_flash_attn_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int64,
                             c_int64, c_float, c_void_p],

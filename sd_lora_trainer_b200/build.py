@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200_lora.so")
-SOURCES = ["gemm_host.cu", "flash_attn.cu", "norms.cu", "elementwise.cu", "optim.cu", "wgrad_batch.cu"]
+SOURCES = ["gemm_host.cu", "flash_attn.cu", "norms.cu", "elementwise.cu", "optim.cu", "wgrad_batch.cu", "losses.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -487,6 +487,48 @@ def diffusion_loss(pred: torch.Tensor, ld_pred: int, noise: torch.Tensor, mask: 
     return loss, dpred
 
 
+def token_attention_loss(maps: Sequence[torch.Tensor], h: int, w: int, n_text: int, mask3: torch.Tensor, tok_len: torch.Tensor,
+                         ti_pos: torch.Tensor, grad_scale: float, want_grad: bool = True):
+    """maps[l]: bf16 [B, h*w, >= n_text] views (unit inner stride, dense rows of any pitch), all at the common resolution.
+    mask3: fp32 [B, Hm, Wm] (rows dense, any batch stride).  Returns (loss fp32 [1], G bf16 [B, h*w, roundup8(n_text)] or
+    None): G = grad_scale * d loss / d maps[l], the same for every layer."""
+    B, hw = maps[0].shape[0], h * w
+    n = len(maps)
+    assert mask3.dtype == torch.float32 and mask3.dim() == 3 and mask3.stride(2) == 1 and mask3.stride(1) == mask3.shape[2]
+    assert tok_len.dtype == torch.int64 and ti_pos.dtype == torch.int64 and ti_pos.is_contiguous() and ti_pos.shape[0] == B
+    ptrs, lds = (C.c_void_p * n)(), (C.c_int64 * n)()
+    for i, m in enumerate(maps):
+        _chk_dev(m)
+        assert m.dtype == BF16 and m.shape[0] == B and m.shape[1] == hw and m.shape[2] >= n_text and m.stride(2) == 1
+        assert m.stride(0) == hw * m.stride(1)
+        ptrs[i], lds[i] = m.data_ptr(), m.stride(1)
+    dev = maps[0].device
+    ld_g = (n_text + 7) // 8 * 8
+    ws = torch.empty(B * hw * n_text + 8 * B, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    G = torch.empty(B, hw, ld_g, dtype=BF16, device=dev) if want_grad else None
+    check(_lib.load().b200_token_attention_loss(ptrs, lds, n, B, h, w, n_text, mask3.data_ptr(), mask3.stride(0), mask3.shape[1],
+                                                mask3.shape[2], tok_len.data_ptr(), ti_pos.data_ptr(), ti_pos.shape[1],
+                                                grad_scale, ws.data_ptr(), ws.numel(), loss.data_ptr(), _p(G), ld_g, _stream()),
+          "token_attention_loss")
+    return loss, G
+
+
+def token_std_loss(rows: Sequence[torch.Tensor], grads: Sequence[Optional[torch.Tensor]], mu_t: Sequence[float],
+                   var_t: Sequence[float], coeff: float):
+    """rows[e]: bf16 [n_rows, dim_e] contiguous trainable embedding rows of text encoder e (1 or 2 encoders); grads[e]: fp32
+    [n_rows, dim_e] views accumulated in place (or None).  Returns the unweighted loss, fp32 [1]."""
+    n_enc = len(rows)
+    assert n_enc in (1, 2) and all(r.dtype == BF16 and r.is_contiguous() and r.shape[0] == rows[0].shape[0] for r in rows)
+    assert all(g is None or (g.dtype == torch.float32 and g.is_contiguous() and g.shape == r.shape) for g, r in zip(grads, rows))
+    loss = torch.zeros(1, dtype=torch.float32, device=rows[0].device)
+    r1, g1 = (rows[1], grads[1]) if n_enc == 2 else (None, None)
+    check(_lib.load().b200_token_std_loss(rows[0].data_ptr(), _p(r1), _p(grads[0]), _p(g1), n_enc, rows[0].shape[0], rows[0].shape[1],
+                                          r1.shape[1] if r1 is not None else 0, mu_t[0], var_t[0], mu_t[1] if n_enc == 2 else 0.0,
+                                          var_t[1] if n_enc == 2 else 1.0, coeff, loss.data_ptr(), _stream()), "token_std_loss")
+    return loss
+
+
 def abs_sum(p: torch.Tensor, out: torch.Tensor):
     check(_lib.load().b200_abs_sum(p.data_ptr(), p.numel(), out.data_ptr(), _stream()), "abs_sum")
     return out

@@ -145,6 +145,8 @@ class TrainerB200:
         self.train_ids: List[int] = []
         self.ti_rows: List[torch.Tensor] = []
         self.std_regs: List[DistributionLoss] = []
+        self._std_mu: List[float] = []
+        self._std_var: List[float] = []
         if ntok:
             g = torch.Generator().manual_seed(cfg.seed)
             off = self.store.n_lora
@@ -154,6 +156,8 @@ class TrainerB200:
                 rows = self.store.params[off:off + ntok * dim].view(ntok, dim)
                 rows.copy_(ti_init[i].to(self.device, BF16) if ti_init is not None else init_ti_rows(table, ntok, g))
                 self.std_regs.append(DistributionLoss(torch.cat([table, rows], dim=0)))      # loss.py:179-194
+                self._std_mu.append(float(self.std_regs[-1].target_stds_mean))
+                self._std_var.append(float(self.std_regs[-1].target_stds_var))
                 rows.requires_grad_(True)
                 install_ti_rows(te, rows)
                 self.ti_rows.append(rows)
@@ -177,6 +181,9 @@ class TrainerB200:
         # token-attention backward with one shared gradient map per resolution (measured on the B200: 78.2 vs 78.7 ms/step,
         # same losses / gradients - profiles/r02a_*; B200_SHARED_DSCORES=0 restores the per-layer autograd path)
         self.shared_dscores = os.environ.get("B200_SHARED_DSCORES", "1") == "1"
+        # the regulariser itself as kernels (b200_token_attention_loss; forward and gradient map in three launches) instead of
+        # ~40 torch ops + autograd on the stacked maps; B200_TAL_KERNEL=0 keeps the torch form of trainer/loss.py
+        self.tal_kernel = os.environ.get("B200_TAL_KERNEL", "1") == "1"
         # conditioning cache for the phases without a trainable token row (B200_TEXT_CACHE=0 turns it off)
         self.cache_text = os.environ.get("B200_TEXT_CACHE", "1") != "0"
         self._text_cache: Dict[tuple, tuple] = {}
@@ -328,16 +335,18 @@ class TrainerB200:
         total = img_loss.clone()
         dscores = None
         if not cfg.disable_ti:
-            if self.shared_dscores:
+            if self.tal_kernel:
+                tal, dscores = self._token_attention_kernel(scores, mask, st["tok_len"], st["ti_pos"], ga)
+            elif self.shared_dscores:
                 tal, dscores = self._token_attention_shared(scores, mask, st["tok_len"], st["ti_pos"], ga)
             else:
                 leaves = [s.detach().requires_grad_(True) for s in scores]
                 tal = token_attention_loss_tensors(leaves, mask, st["tok_len"], st["ti_pos"])
                 (cfg.token_attention_loss_w * tal / ga).backward()
                 dscores = [l.grad if l.grad is not None else torch.zeros_like(l) for l in leaves]
-            out["token_attention_loss"] = tal.detach()
+            out["token_attention_loss"] = tal.detach().reshape(())
             out["attention_scores"] = scores
-            total = total + cfg.token_attention_loss_w * tal.detach().float()
+            total = total + cfg.token_attention_loss_w * tal.detach().float().reshape(())
         if cfg.l1_penalty > 0.0 and self.store.n_lora > 0:      # main.py:353: only with LoRA parameters
             l1 = torch.zeros(1, dtype=torch.float32, device=dev)
             ops.abs_sum(self.store.params[:self.store.n_lora], l1)
@@ -357,12 +366,14 @@ class TrainerB200:
                 if pooled is not None and d_text is not None:
                     roots.append(pooled)
                     grads.append(d_text.to(pooled.dtype))
-            if ti_active:                                     # token-std regulariser, loss.py:222-231
-                std = torch.stack([reg.compute_std_loss(rows) for reg, rows in zip(self.std_regs, self.ti_rows)]).mean()
-                out["token_std_loss"] = std.detach()
-                total = total + 0.01 * std.detach().float()
-                roots.append(0.01 * std / ga)
-                grads.append(torch.ones_like(std))
+            if ti_active:                                     # token-std regulariser, loss.py:222-231 (kernel: value + row gradients)
+                off, gviews = self.store.n_lora, []
+                for rows in self.ti_rows:
+                    gviews.append(self.store.grads[off:off + rows.numel()].view(rows.shape))
+                    off += rows.numel()
+                std = ops.token_std_loss([r.detach() for r in self.ti_rows], gviews, self._std_mu, self._std_var, 0.01 / ga)
+                out["token_std_loss"] = std.reshape(())
+                total = total + 0.01 * std.reshape(())
             if roots:
                 torch.autograd.backward(roots, grads)
             off = self.store.n_lora
@@ -374,6 +385,33 @@ class TrainerB200:
                 off += n
         out["tot_loss"] = total
         return out
+
+    def _token_attention_kernel(self, scores, mask, tok_len, ti_pos, ga):
+        """compute_token_attention_loss (trainer/loss.py:10-80) and its gradient as kernels: the larger maps are resized to
+        the smallest one (process_and_stack_attention_scores, ti_cross_attn_loss.py:239-268) by the bicubic kernel, the layer
+        sum / regularisers / gradient map by b200_token_attention_loss; the gradient is the same map for every layer (one
+        bicubic adjoint per larger resolution)."""
+        import math
+        img_ratio = mask.shape[-1] / mask.shape[-2]
+        shapes = []
+        for s_ in scores:
+            wd = round(math.sqrt(s_.shape[1] * img_ratio))
+            shapes.append((round(wd / img_ratio), wd))
+        h, w = min(shapes, key=lambda hw_: hw_[0] * hw_[1])
+        Bsz, n_text = scores[0].shape[0], scores[0].shape[2]
+        maps = []
+        for s_, (hi, wi) in zip(scores, shapes):
+            if hi * wi != h * w:
+                s_ = ops.bicubic_fwd(s_.reshape(Bsz, hi, wi, n_text), h, w).reshape(Bsz, h * w, n_text)
+            maps.append(s_)
+        tal, G = ops.token_attention_loss(maps, h, w, n_text, mask[:, 0], tok_len, ti_pos, self.cfg.token_attention_loss_w / ga)
+        shared, out = {h * w: G}, []
+        for s_, (hi, wi) in zip(scores, shapes):
+            L = hi * wi
+            if L not in shared:                                   # one adjoint resize per larger resolution
+                shared[L] = ops.bicubic_bwd(G.reshape(Bsz, h, w, G.shape[2]), hi, wi).reshape(Bsz, L, G.shape[2])
+            out.append(shared[L])
+        return tal, out
 
     def _token_attention_shared(self, scores, mask, tok_len, ti_pos, ga):
         """Default path (B200_SHARED_DSCORES=0 turns it off): the regulariser only sees the mean of the stacked maps over layers, so every hooked layer

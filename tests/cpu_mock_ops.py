@@ -460,6 +460,39 @@ def diffusion_loss(pred, ld_pred, noise, mask, weights, loss_scale, want_grad=Tr
     return l.detach().float().view(1), (d8 if want_grad else None)
 
 
+def token_attention_loss(maps, h, w, n_text, mask3, tok_len, ti_pos, grad_scale, want_grad=True):
+    """Reference arithmetic of the kernel: the tensorised regulariser of trainer/loss.py under torch autograd."""
+    from sd_lora_trainer_b200.trainer.loss import token_attention_loss_from_maps
+    B, hw = maps[0].shape[0], h * w
+    assert len(maps) <= 64 and n_text <= 80 and ti_pos.shape[1] <= 8 and mask3.dtype == torch.float32
+    for m in maps:
+        assert m.dtype == BF16 and m.shape[:2] == (B, hw) and m.shape[2] >= n_text and m.stride(2) == 1
+    stacked = torch.stack([m[:, :, :n_text].reshape(B, h, w, n_text) for m in maps]).detach().clone().requires_grad_(want_grad)
+    loss = token_attention_loss_from_maps(stacked, mask3[:, None], tok_len, ti_pos)
+    G = None
+    if want_grad:
+        ld_g = (n_text + 7) // 8 * 8
+        G = torch.zeros(B, hw, ld_g, dtype=BF16)
+        if loss.requires_grad:
+            loss.backward()
+            if stacked.grad is not None:
+                G[:, :, :n_text] = (stacked.grad[0].float() * grad_scale).reshape(B, hw, n_text).to(BF16)
+    return loss.detach().float().reshape(1), G
+
+
+def token_std_loss(rows, grads, mu_t, var_t, coeff):
+    total = torch.zeros(1)
+    for e, r in enumerate(rows):
+        x = r.detach().clone().requires_grad_(True)
+        mu, var = torch.tensor(mu_t[e], dtype=BF16), torch.tensor(var_t[e], dtype=BF16)
+        le = ((mu - x.std(-1)) ** 2 / var).mean()
+        (le * coeff / len(rows)).backward()
+        if grads[e] is not None:
+            grads[e] += x.grad.float()
+        total += le.detach().float() / len(rows)
+    return total
+
+
 def abs_sum(p, out):
     out += p.float().abs().sum()
     return out
