@@ -37,6 +37,14 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["dram_bytes_read"] + d["dram_bytes_write"]
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -214,9 +222,9 @@ def run_ours(args):
         result["roofline"] = {"bound": "tensor", "kernel": "tcgen05 GEMM family (gemm2_kernel CTA pairs + gemm_tcgen05_kernel)",
                               "achieved": prof["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                               "frac": prof["tflops"] / pk["bf16_tflops"],
-                              # DRAM bytes of the dominant launch (2048x1280x1280 LoRA-fused projection, 744 per step)
-                              # from profiles/r01b_gemm2_ncu_full.md (ncu --set full): read 8.64 MB + write 0
-                              "traffic": 8.64e6,
+                              # dram__bytes_read.sum + dram__bytes_write.sum of the family's most frequent launch, per launch,
+                              # from the committed `ncu --set full` capture (profiles/ncu_traffic.json names it); null if absent
+                              "traffic": ncu_traffic(),
                               "peak_source": pk_src + " (burst: every GEMM signature is timed alone, as a CUDA graph of "
                                                       "10 launches of the step's own call, between CUDA events)",
                               "launches_per_step": prof["launches"], "gemm_ms_per_step": prof["ms"],
@@ -263,12 +271,10 @@ def run_ours(args):
         print(json.dumps(result), flush=True)
     faulthandler.cancel_dump_traceback_later()
     if world > 1:
-        # Measured on 2 x B200 (gpurun_out of round 1): every rank finished its work and rank 0 printed its line, but the
-        # closing barrier + destroy_process_group() never returned - the step's CUDA graphs hold the NCCL kernels they
-        # captured, and tearing the communicator down under them blocks.  Nothing is left to communicate, so: flush
-        # and leave without running the NCCL / graph destructors.  (The rank-0-only passes above issue no collective.)
-        # Non-zero ranks stay alive until rank 0 has printed (its peers' communicators must not vanish while it still
-        # runs GPU work); the hand-shake goes through the rendezvous store, not through NCCL.
+        # Tear-down: destroy_process_group() blocks while CUDA graphs that captured NCCL kernels are alive (measured on
+        # 2 x B200 in round 1), so the graphs are released first (TrainerB200.close) and the group destroyed from a helper
+        # thread with a deadline; if it still does not return, leave without the NCCL / graph destructors (the line is out).
+        # Non-zero ranks wait (rendezvous store, not NCCL) until rank 0 has printed.
         try:
             import datetime
             store = torch.distributed.distributed_c10d._get_default_store()
@@ -279,9 +285,20 @@ def run_ours(args):
         except Exception:                                    # best effort: never turn a finished run into a failure
             pass
         sys.stdout.flush()
+        clean = False
+        try:
+            tr.close()
+            th = threading.Thread(target=torch.distributed.destroy_process_group, daemon=True)
+            th.start()
+            th.join(timeout=20)
+            clean = not th.is_alive()
+        except Exception:                                    # noqa: BLE001
+            clean = False
+        print(f"[bench] rank {rank}: process group {'destroyed cleanly' if clean else 'NOT destroyed within 20 s - leaving via os._exit'}",
+              file=sys.stderr, flush=True)
         sys.stderr.flush()
-        torch.cuda.synchronize()
-        os._exit(0)
+        if not clean:
+            os._exit(0)
 
 
 def cpu_baseline(args, steps: int, warmup: int, keep=None):

@@ -278,4 +278,5 @@ def train(config: TrainingConfig, dataset, text_encoders: Sequence, unet_state_d
     if rank == 0:
         config.save_as_json(os.path.join(output_save_dir, "training_args.json"))
     print("Training job complete, saving outputs...", flush=True)
-    return config, output_save_dir
+    trainer.close()                     # captured graphs hold the NCCL kernels of the in-step all-reduce: release them so the
+    return config, output_save_dir      # caller can destroy_process_group() (it blocks while such graphs are alive)

@@ -444,6 +444,19 @@ class TrainerB200:
             out.append(shared[L])
         return tal, out
 
+    def close(self):
+        """Release the captured CUDA graphs and their static buffers.  Under data parallelism the graphs hold the NCCL
+        all-reduce kernels they captured; measured on 2 x B200, destroy_process_group() does not return while they are
+        alive - call this first (main.train does at its end)."""
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self._graphs = {}
+        self._static, self._static_key = None, None
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def reset_optimizer_state(self):
         """After parameters were overwritten from a checkpoint (load_lora_weights / load_embeddings): Adam moments and
         Prodigy's s restart from zero, Prodigy's start point p0 is re-snapshotted, the d estimate restarts, cached
