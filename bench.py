@@ -235,24 +235,23 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.skip_cpu:
         # CPU baseline + full-size step-loss delta in a CHILD process with a timeout: a fault or a hang in that extra leg
         # (it runs GPU shapes - batch 1 - that the timed workload does not) cannot cost the measured line.  The parent is
-        # idle meanwhile, so the oracle has the host cores to itself.  (Full fine-tune: no delta leg, in-process baseline.)
-        child = None
-        if not args.full_ft:
-            try:
-                cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--delta-only", "--family", args.family,
-                                     "--rank", str(args.rank), "--cpu-res", str(args.cpu_res), "--cpu-batch", str(args.cpu_batch),
-                                     "--cpu-dtype", args.cpu_dtype], capture_output=True, text=True, timeout=args.delta_timeout)
-                lines = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")]
-                child = json.loads(lines[-1]) if lines else None
-                child_err = None if child else f"exit {cp.returncode}: {cp.stderr[-300:]}"
-            except Exception as e:                              # noqa: BLE001  (timeout, launch failure, bad output)
-                child_err = f"{type(e).__name__}: {e}"[:300]
+        # idle meanwhile, so the oracle has the host cores to itself.
+        child, child_err = None, None
+        try:
+            cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--delta-only", "--family", args.family,
+                                 "--rank", str(args.rank), "--cpu-res", str(args.cpu_res), "--cpu-batch", str(args.cpu_batch),
+                                 "--cpu-dtype", args.cpu_dtype] + (["--full-ft"] if args.full_ft else []),
+                                capture_output=True, text=True, timeout=args.delta_timeout)
+            lines = [ln for ln in cp.stdout.splitlines() if ln.startswith("{")]
+            child = json.loads(lines[-1]) if lines else None
+            child_err = None if child else f"exit {cp.returncode}: {cp.stderr[-300:]}"
+        except Exception as e:                              # noqa: BLE001  (timeout, launch failure, bad output)
+            child_err = f"{type(e).__name__}: {e}"[:300]
         if child is not None:
             result["cpu_baseline"], result["step_loss_delta"] = child["cpu_baseline"], child["step_loss_delta"]
         else:
             result["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
-            if not args.full_ft:
-                result["step_loss_delta"] = {"error": child_err}
+            result["step_loss_delta"] = {"error": child_err}
     if rank == 0 and world == 1 and not args.skip_gpu_baseline:
         # stock-torch-on-the-same-B200 comparator, in a child process (its own CUDA context and memory; bounded by a timeout)
         try:
@@ -450,7 +449,7 @@ def main():
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step inside cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--skip-roofline", action="store_true")
-    ap.add_argument("--cpu-res", type=int, default=1024)
+    ap.add_argument("--cpu-res", type=int, default=None, help="resolution of the CPU-oracle legs (default: --res)")
     ap.add_argument("--cpu-batch", type=int, default=1)
     ap.add_argument("--cpu-dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--ref-max-steps", type=int, default=10)
@@ -460,6 +459,8 @@ def main():
     ap.add_argument("--delta-timeout", type=int, default=600, help="seconds granted to the --delta-only child process")
     ap.add_argument("--watchdog", type=int, default=1500, help="seconds after which a stuck run dumps its stacks and exits 1")
     args = ap.parse_args()
+    if args.cpu_res is None:
+        args.cpu_res = args.res
     if args.delta_only:
         run_delta_only(args)
     elif args.gpu_baseline_only:

@@ -41,6 +41,8 @@ struct Gemm2Args {
     // scalars first: they fit in a few constant-cache lines and are read once, before griddepcontrol.wait
     int M, N, BN, tiles_n, total_tiles, kblocks, ktail16;
     int b_mn, side, side_mn, b2_mn, side_r16, side_r;
+    int a_mn;                 // segment 0's A operand is MN-major ([K, M] with M contiguous: dY^T of a weight gradient): two 64 x 64 boxes per CTA
+    int d_accum;              // fp32 output: D += result (each tile element is owned by one CTA: plain read-modify-write)
     int stage_bytes, num_stages, side_off, acc_stages;
     int vec_ok, bias_rows;
     // implicit 3x3 / pad 1 / stride 1 convolution on segment 0's A operand (NHWC; mapA dims C, W, H, N)
@@ -101,7 +103,7 @@ struct Epi2 {
     const __nv_bfloat16* bias;
     const __nv_bfloat16* R;
     long long d_sm, r_sm, bias_sb;
-    int M, N, bias_rows, vec_ok;
+    int M, N, bias_rows, vec_ok, accum;
     float alpha;
 };
 
@@ -153,7 +155,12 @@ __device__ __forceinline__ void epi2_chunk(const Epi2& e, const uint32_t (&raw)[
                 v3 += __uint_as_float(rr[it].y & 0xffff0000u);
             }
             if (kEpi == 1) {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.D) + doff + it * d_step) = make_float4(v0, v1, v2, v3);
+                float4* dp4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.D) + doff + it * d_step);
+                if (e.accum) {
+                    const float4 old = *dp4;
+                    v0 += old.x, v1 += old.y, v2 += old.z, v3 += old.w;
+                }
+                *dp4 = make_float4(v0, v1, v2, v3);
             } else {
                 const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1);
                 const __nv_bfloat162 h1 = __floats2bfloat162_rn(v2, v3);
@@ -175,8 +182,12 @@ __device__ __forceinline__ void epi2_chunk(const Epi2& e, const uint32_t (&raw)[
                     float x = q[c] * alpha + bv[c];
                     if (bias_per_row) x += __bfloat162float(e.bias[(m / e.bias_rows) * e.bias_sb + n + c]);
                     if (rp) x += __bfloat162float(rp[it * r_step + c]);
-                    if (kEpi == 1) reinterpret_cast<float*>(e.D)[doff + it * d_step + c] = x;
-                    else reinterpret_cast<__nv_bfloat16*>(e.D)[doff + it * d_step + c] = __float2bfloat16_rn(x);
+                    if (kEpi == 1) {
+                        float* dp1 = reinterpret_cast<float*>(e.D) + doff + it * d_step + c;
+                        *dp1 = e.accum ? *dp1 + x : x;
+                    } else {
+                        reinterpret_cast<__nv_bfloat16*>(e.D)[doff + it * d_step + c] = __float2bfloat16_rn(x);
+                    }
                 }
             }
         }
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
     const int BN = g.BN, tiles_n = g.tiles_n, total_tiles = g.total_tiles, kblocks = g.kblocks;
     const int num_stages = g.num_stages, stage_bytes = g.stage_bytes, acc_stages = g.acc_stages;
     const int side = g.side, side_off = g.side_off, r16 = g.side_r16;
-    const int b_mn = g.b_mn, side_mn = g.side_mn, b2_mn = g.b2_mn;
+    const int b_mn = g.b_mn, side_mn = g.side_mn, b2_mn = g.b2_mn, a_mn = g.a_mn;
     const int conv = g.conv, nseg = g.nseg, kblocks2 = g.kblocks2, streamk = g.streamk;
     const int npairs = static_cast<int>(gridDim.x >> 1), pair = static_cast<int>(blockIdx.x >> 1);
     long long* const dbg = g.dbg;
@@ -369,6 +380,9 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     const int tap = kb / conv_cblocks, cb = kb - tap * conv_cblocks;
                     const int kh = tap / 3, kw = tap - kh * 3;
                     tma2_load_4d(sa, &g.mapA, fb, cb * kBK, kw - 1, ch0 + kh - 1, cn0);
+                } else if (a_mn) {
+                    tma2_load_4d(sa, &g.mapA, fb, m0, kb * kBK, 0, 0);
+                    tma2_load_4d(sa + 8192, &g.mapA, fb, m0 + 64, kb * kBK, 0, 0);
                 } else {
                     tma2_load_4d(sa, &g.mapA, fb, kb * kBK, m0, 0, 0);
                 }
@@ -433,7 +447,12 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                         uint8_t* sa = smem + stage * stage_bytes;
                         uint8_t* sb = sa + k2ABytes;
                         const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
-                        tma2_load_4d(sa, &g.mapA, fb, k, m0, 0, 0);
+                        if (a_mn) {
+                            tma2_load_4d(sa, &g.mapA, fb, m0, k, 0, 0);
+                            tma2_load_4d(sa + 8192, &g.mapA, fb, m0 + 64, k, 0, 0);
+                        } else {
+                            tma2_load_4d(sa, &g.mapA, fb, k, m0, 0, 0);
+                        }
                         if (!b_mn) {
                             tma2_load_4d(sb, &g.mapB, fb, k, nh0, 0, 0);
                         } else {
@@ -489,10 +508,12 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             uint32_t phase = 0, acc_phase = 0, t_phase = 0;
             const uint32_t smem_base = smem_u32(smem);
             const bool leader = elect_one();
-            const uint32_t idesc = umma2_idesc_bf16(BN, 0, b_mn);
+            const uint32_t idesc = umma2_idesc_bf16(BN, a_mn, b_mn);
             const uint32_t idesc_s = umma2_idesc_bf16(r16, 0, side_mn);
             const uint32_t idesc_2 = umma2_idesc_bf16(BN, 0, b2_mn);
-            const uint64_t a_hi = umma_desc(0, 16, 1024);
+            const uint64_t a_hi = umma_desc(0, 16, 1024);                 // K-major A (and the T tile of the side path)
+            const uint64_t a0_hi = umma_desc(0, a_mn ? 8192u : 16u, 1024);   // segment 0's A: MN-major for weight gradients
+            const uint64_t a_step = a_mn ? 128u : 2u;
             const uint64_t b_hi = umma_desc(0, b_mn ? 8192u : 16u, 1024);
             const uint64_t s_hi = umma_desc(0, side_mn ? 8192u : 16u, 1024);
             const uint64_t b2_hi = umma_desc(0, b2_mn ? 8192u : 16u, 1024);
@@ -513,18 +534,18 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     if (leader) {
                         if (dbg != nullptr && first_item && (kb == kb0 || kb == kb1 - 1)) dbg_stamp(dbg, kb == kb0 ? 3 : 4);
                         const uint32_t sa = smem_base + static_cast<uint32_t>(stage * stage_bytes);
-                        const uint64_t ad = a_hi | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
+                        const uint64_t ad = a0_hi | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
                         const uint64_t bd = b_hi | static_cast<uint64_t>(((sa + k2ABytes) & 0x3FFFF) >> 4);
                         const int n16 = (kb == kblocks - 1) ? ktail : 4;
                         if (side) {
                             const uint64_t sd = s_hi | static_cast<uint64_t>(((sa + k2ABytes + side_off) & 0x3FFFF) >> 4);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                if (k < n16) umma2_bf16(tmem_s, ad + 2u * k, sd + s_step * k, idesc_s, accum | (k > 0));
+                                if (k < n16) umma2_bf16(tmem_s, ad + a_step * k, sd + s_step * k, idesc_s, accum | (k > 0));
                         }
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < n16) umma2_bf16(tmem_d, ad + 2u * k, bd + b_step * k, idesc, accum | (k > 0));
+                            if (k < n16) umma2_bf16(tmem_d, ad + a_step * k, bd + b_step * k, idesc, accum | (k > 0));
                         umma2_commit_mc(&empty_bar[stage]);      // frees this ring slot in BOTH CTAs
                     }
                     __syncwarp();
@@ -601,6 +622,7 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
         e.N = g.N;
         e.bias_rows = g.bias_rows;
         e.vec_ok = g.vec_ok;
+        e.accum = g.d_accum;
         e.alpha = g.alpha;
         const float side_alpha = g.side_alpha;
         const int side_r = g.side_r;

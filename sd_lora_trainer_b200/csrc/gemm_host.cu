@@ -126,7 +126,8 @@ extern "C" void b200_debug_gemm_stamps(long long* dev_buf) { g_gemm_dbg = dev_bu
 static int pair_k0(const b200_gemm_t* d) { return d->conv ? 9 * ((d->conv_C + 63) / 64) * 64 : d->K[0]; }
 
 static bool pair_eligible(const b200_gemm_t* d) {
-    if (d->nb0 != 1 || d->nb1 != 1 || d->splits != 1 || d->d_atomic || d->d_sn != 1) return false;
+    if (d->nb0 != 1 || d->nb1 != 1 || d->splits != 1 || d->d_sn != 1) return false;
+    if (d->d_atomic && !d->d_fp32) return false;           // accumulate mode: fp32 output, plain read-modify-write per tile
     if (d->num_seg < 1 || d->num_seg > 2 || (d->side && (d->num_seg != 1 || d->conv))) return false;
     if (d->conv) {
         const int W = d->conv_W, H = d->conv_H;
@@ -137,8 +138,8 @@ static bool pair_eligible(const b200_gemm_t* d) {
         const int bimg = 128 / (W * bh);
         if (!(bimg == 1 || bh == H) || d->conv_C % 8) return false;
         if (static_cast<long long>(d->conv_N) * H * W != d->M) return false;
-    } else if (d->A[0].mn_major) {
-        return false;
+    } else if (d->A[0].mn_major && (d->side || d->num_seg != 1 || d->A[0].inner % 8)) {
+        return false;                                      // MN-major A (weight gradients): one plain segment
     }
     if (d->num_seg == 2 && (d->A[1].mn_major || d->A[1].batched || d->B[1].batched)) return false;
     if (d->M < 256 || d->N < 64 || pair_k0(d) < 64) return false;
@@ -224,10 +225,11 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
         g.kblocks = 9 * g.conv_cblocks;
         g.ktail16 = 4;                       // channel tails are zero-filled by TMA on the A side
     } else {
-        B200_CHECK_ARG(A.inner >= K, "gemm2: A smaller than K");
+        B200_CHECK_ARG(A.mn_major ? A.rows >= K : A.inner >= K, "gemm2: A smaller than K");
         const long long dA[4] = {A.inner, A.rows, 1, 1}, sA[3] = {A.row_stride, 0, 0};
-        const int boxA[4] = {64, 128, 1, 1};
+        const int boxA[4] = {64, A.mn_major ? 64 : 128, 1, 1};   // MN-major: dims (M, K), two 64 x 64 boxes per CTA and k-block
         if (int rc = encode_map(&g.mapA, A.ptr, dA, sA, boxA)) return rc;
+        g.a_mn = A.mn_major;
         g.kblocks = (K + kBK - 1) / kBK;
         g.ktail16 = (K - (g.kblocks - 1) * kBK + 15) / 16;
     }
@@ -286,6 +288,7 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
     g.b_static = (d->b_static && prefetch_env) ? 1 : 0;
     g.D = d->D;
     g.d_sm = d->d_sm;
+    g.d_accum = d->d_atomic ? 1 : 0;
     g.alpha = d->alpha;
     g.bias = static_cast<const __nv_bfloat16*>(d->bias);
     g.bias_rows = d->bias_rows;

@@ -310,6 +310,15 @@ class DenseStore:
         return out
 
 
+PAIR_WGRAD = os.environ.get("B200_PAIR_WGRAD", "1") != "0"
+
+
+def _pair_wgrad_ok(out_rows: int, out_cols: int, reduce_len: int) -> bool:
+    """Dense weight gradient dW[N, K] += dY^T . X on the CTA-pair kernel (MN-major A): what gemm_host.cu's pair_eligible takes,
+    and enough output tiles to be worth it (otherwise the split-K single-CTA form)."""
+    return PAIR_WGRAD and out_rows >= 256 and out_cols >= 128 and reduce_len >= 64 and out_rows % 8 == 0 and out_cols % 8 == 0
+
+
 def _dense_splits(out_rows: int, out_cols: int, reduce_len: int) -> int:
     tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
     kblocks = (reduce_len + 63) // 64
@@ -395,9 +404,12 @@ class Lin:
             WGRAD.run(wgrad, dy, T, x, U)
         if self.gW is not None:
             # dense fine-tune: dW[N, K] += dY^T . X (both operands MN-major, split-K fp32 atomics), db += colsum(dY)
-            ops.gemm(self.gW, self.N, self.K, [(Mat(dy, M, self.N, dy.stride(0), mn=True),
-                                                Mat(x, M, self.K, x.stride(0), mn=True), M)],
-                     d_strides=(self.K, 1, 0, 0), splits=_dense_splits(self.N, self.K, M), atomic=True)
+            seg = (Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(x, M, self.K, x.stride(0), mn=True), M)
+            if _pair_wgrad_ok(self.N, self.K, M):
+                # CTA-pair kernel: both operands MN-major, every [256 x BN] tile of dW read-modify-written by its one owner
+                ops.gemm(self.gW, self.N, self.K, [seg], d_strides=(self.K, 1, 0, 0), atomic=True, pair_mode=1)
+            else:
+                ops.gemm(self.gW, self.N, self.K, [seg], d_strides=(self.K, 1, 0, 0), splits=_dense_splits(self.N, self.K, M), atomic=True)
             if self.gb is not None:
                 self.gb += ops.colsum(dy if dy.is_contiguous() else dy.contiguous(), 1, M, self.N)[0].float()
         return dx
@@ -567,8 +579,11 @@ class Conv3:
             # dense fine-tune: dW[Cout, (kh,kw,c)] += dY^T . im2col(X), db += colsum(dY)
             K9 = 9 * self.cin_p
             col = ops.im2col3x3(x, N, H, W, self.cin_p, s)
-            ops.gemm(self.gwk, self.cout, K9, [(Mat(dy, Mo, self.cout, dy.stride(0), mn=True), Mat(col, Mo, K9, K9, mn=True), Mo)],
-                     d_strides=(K9, 1, 0, 0), splits=_dense_splits(self.cout, K9, Mo), atomic=True)
+            seg = (Mat(dy, Mo, self.cout, dy.stride(0), mn=True), Mat(col, Mo, K9, K9, mn=True), Mo)
+            if _pair_wgrad_ok(self.cout, K9, Mo):
+                ops.gemm(self.gwk, self.cout, K9, [seg], d_strides=(K9, 1, 0, 0), atomic=True, pair_mode=1)
+            else:
+                ops.gemm(self.gwk, self.cout, K9, [seg], d_strides=(K9, 1, 0, 0), splits=_dense_splits(self.cout, K9, Mo), atomic=True)
             del col
             if self.gb is not None:
                 dyc = dy if dy.is_contiguous() else dy.contiguous()

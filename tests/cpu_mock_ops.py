@@ -68,6 +68,12 @@ def _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out, pair_m
             assert not a.batched or ((nb0 == 1 or a.sb0 > 0) and (nb1 == 1 or a.sb1 > 0)), "batched operand strides"
         _chk_tma(b, f"B[{i}]")
         assert not b.batched or ((nb0 == 1 or b.sb0 > 0) and (nb1 == 1 or b.sb1 > 0)), "batched operand strides"
+    if pair_mode > 0:                               # forced CTA-pair kernel: gemm_host.cu pair_eligible
+        k0 = 9 * ((segs[0][0].C + 63) // 64) * 64 if conv else segs[0][2]
+        assert M >= 256 and N >= 64 and k0 >= 64 and nb0 == 1 and nb1 == 1 and splits == 1 and group_out is None, "pair kernel rules"
+        assert not atomic or out.dtype == torch.float32
+        if not conv and segs[0][0].mn:
+            assert side is None and len(segs) == 1 and segs[0][0].inner % 8 == 0, "MN-major A: one plain segment"
     kblocks0 = 9 * ((segs[0][0].C + 63) // 64) if conv else (segs[0][2] + 63) // 64
     assert splits <= kblocks0, f"more splits ({splits}) than K blocks ({kblocks0})"
     if side is not None:

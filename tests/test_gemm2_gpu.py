@@ -148,6 +148,24 @@ def test_pair_fused_side_path_dgrad(M, N, K, r):
     _close(dx, dy.float() @ w.float() + Uref.float() @ A.float() + acc.float(), what="pair fused side dgrad")
 
 
+@pytest.mark.parametrize("N,K,M", [(1280, 1280, 1024), (10240, 1280, 1024), (640, 2560, 4096), (304, 264, 200), (1280, 11520, 2048),
+                                   (256, 128, 64), (320, 2880, 16384)])
+def test_pair_dense_weight_gradient_mn_major_a_accumulates(N, K, M):
+    """dW[N, K] += dY[M, N]^T . X[M, K] (full fine-tune): both operands MN-major from their forward layouts, fp32 output
+    accumulated in place by the tile's one owner."""
+    from sd_lora_trainer_b200 import ops
+    dy, x = _rand(M, N, scale=0.5), _rand(M, K, seed=1, scale=0.5)
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    dw = torch.randn(N, K, device="cuda", generator=g)
+    before = dw.clone()
+    ops.gemm(dw, N, K, [(ops.Mat(dy, M, N, N, mn=True), ops.Mat(x, M, K, K, mn=True), M)], d_strides=(K, 1, 0, 0), atomic=True, pair_mode=1)
+    torch.cuda.synchronize()
+    ref = dy.float().T @ x.float()
+    _close(dw - before, ref, tol=5e-3, what=f"pair dense wgrad {N}x{K}x{M}")
+    ops.gemm(dw, N, K, [(ops.Mat(dy, M, N, N, mn=True), ops.Mat(x, M, K, K, mn=True), M)], d_strides=(K, 1, 0, 0), atomic=True, pair_mode=1)
+    _close(dw - before, 2 * ref, tol=5e-3, what="second accumulation")
+
+
 def test_pair_back_to_back_launches_are_ordered():
     """Programmatic dependent launch + clusters: a chain of dependent GEMMs (each reads the previous output)."""
     from sd_lora_trainer_b200 import ops
