@@ -335,7 +335,8 @@ def cpu_baseline(args, steps: int, warmup: int, keep=None):
     if keep is not None:
         keep.update(orc=orc, cfg=cfg, inputs=inp, loss=float(out["tot_loss"]), img_loss=float(out["img_loss"]))
     return {"value": args.cpu_batch * steps / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} step(s) of the same {args.family.upper()} r={args.rank} face+TI step, batch {args.cpu_batch}, "
+            "sample": f"{steps} step(s) of the same {args.family.upper()} " +
+                      ("full-UNet fine-tune" if args.full_ft else f"r={args.rank} face+TI") + f" step, batch {args.cpu_batch}, "
                       f"{args.cpu_res}x{args.cpu_res}, {args.cpu_dtype} oracle on the host cores (fwd+bwd+AdamW), "
                       f"build {build_s:.0f}s not timed",
             "seconds": dt}
@@ -360,7 +361,8 @@ def step_loss_delta(keep, dev):
     del tr2
     torch.cuda.empty_cache()
     return {"ours": a, "oracle_fp32_cpu": b, "rel": abs(a - b) / abs(b), "img_loss_ours": ai, "img_loss_oracle": bi,
-            "img_loss_rel": abs(ai - bi) / abs(bi), "config": f"same {ocfg.family} r={ocfg.lora_rank} step, batch "
+            "img_loss_rel": abs(ai - bi) / abs(bi),
+            "config": f"same {ocfg.family} " + (f"r={ocfg.lora_rank}" if ocfg.is_lora else "full-UNet fine-tune") + " step, batch "
             f"{keep['inputs']['vae_latent'].shape[0]}, {ocfg.resolution}x{ocfg.resolution}, identical weights / rows / inputs",
             "north_star_bound": 1e-3}
 
