@@ -259,6 +259,45 @@ __device__ __forceinline__ void epi2_chunk_tma(const Epi2& e, const CUtensorMap*
     __syncwarp();
 }
 
+// One [32 x 32] chunk, fp32 output, through TMA: two [32 rows x 16 columns] boxes (64-byte rows, the same 64B-swizzled
+// staging layout as the bf16 boxes).  accumulate = cp.reduce.async.bulk.tensor .add (the fp32 sum happens at the L2: the
+// SMs never read the 10 GB of dense weight gradients back), else a plain bulk store.  alpha (+ bias) only; M / N edges
+// are clipped by the tensor map.
+__device__ __forceinline__ void epi2_chunk_tma_f32(const Epi2& e, const CUtensorMap* mapD, const uint32_t (&raw)[32], uint8_t* box,
+                                                   int lane, int m_warp, int n_chunk, bool accumulate, bool with_bias) {
+    float v[32];
+    const float alpha = e.alpha;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]) * alpha;
+    if (e.bias != nullptr && with_bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (n_chunk + i < e.N) v[i] += __bfloat162float(e.bias[n_chunk + i]);
+    }
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {
+        uint8_t* rowp = box + hb * 2048 + lane * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(rowp + ((j ^ sw) * 16)) =
+                make_float4(v[hb * 16 + 4 * j], v[hb * 16 + 4 * j + 1], v[hb * 16 + 4 * j + 2], v[hb * 16 + 4 * j + 3]);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        if (accumulate) {
+            tma_reduce_add_4d(mapD, box, n_chunk, m_warp, 0, 0);
+            if (n_chunk + 16 < e.N) tma_reduce_add_4d(mapD, box + 2048, n_chunk + 16, m_warp, 0, 0);
+        } else {
+            tma_store_4d(mapD, box, n_chunk, m_warp, 0, 0);
+            if (n_chunk + 16 < e.N) tma_store_4d(mapD, box + 2048, n_chunk + 16, m_warp, 0, 0);
+        }
+        bulk_commit();
+    }
+    __syncwarp();
+}
+
 // Ragged chunk (fewer than 32 valid columns at the N edge) when the TMA-store path owns the staging memory: plain
 // thread <-> row scalar stores.  Rare (none of the step's shapes has a ragged edge), so simplicity wins.
 __device__ __forceinline__ void epi2_chunk_direct(const Epi2& e, const uint32_t (&raw)[32], int lane, int m_warp, int n_chunk,
@@ -719,6 +758,12 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                         // (the host only selects stream-K for problems without a ragged N edge)
                         epi2_chunk_direct(e, raw, lane, m_warp, n0 + c0, min(32, BN - c0), with_bias);
                     }
+                } else if (kEpi == 1 && tma_store) {
+                    if (m_warp >= e.M) return;         // rows past the M edge (warp-uniform)
+                    // fp32 through TMA (dense weight gradients: reduce-add when accumulating): both staging boxes are one chunk
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    epi2_chunk_tma_f32(e, &g.mapD, raw, tma_box, lane, m_warp, n0 + c0, e.accum != 0, with_bias);
                 } else {
                     epi2_chunk<kEpi>(e, raw, stage_buf, lane, m_warp, n0 + c0, min(32, BN - c0));
                 }

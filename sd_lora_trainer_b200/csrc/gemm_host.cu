@@ -307,13 +307,22 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
         if (int rc = encode_map_ex(&g.mapD, d->D, 2, dD, sD, boxD, 64)) return rc;
         g.tma_store = 1;
     }
+    static const int tma_f32_env = getenv("B200_TMA_EPI_F32") ? atoi(getenv("B200_TMA_EPI_F32")) : 1;
+    if (tma_f32_env && d->d_fp32 && !d->R && !d->bias_rows && bn % 32 == 0 && al16(d->D) && d->d_sm % 4 == 0 && d->N % 4 == 0) {
+        // fp32 outputs (dense weight gradients, the conv-LoRA tap products) leave through TMA as [32 x 16] boxes; accumulate
+        // mode uses the reduce-add form, so the SMs never read the old gradient values
+        const long long dD[4] = {d->N, d->M, 1, 1}, sD[3] = {d->d_sm, 0, 0};
+        const int boxD[4] = {16, 32, 1, 1};
+        if (int rc = encode_map_ex(&g.mapD, d->D, 4, dD, sD, boxD, 64)) return rc;
+        g.tma_store = 1;
+    }
     int pairs = g.total_tiles < kNumSMs / 2 ? g.total_tiles : kNumSMs / 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // stream-K: few tiles, long K (FF down-projection and its input gradient, the deep convs): cut the (tile, k-block)
     // space into 74 equal ranges so every SM works; partial tiles are added to D by TMA reduce-add, so D is pre-set
     // here to the residual (or zero) and the kernel sees no residual.
     static const int streamk_env = getenv("B200_STREAMK") ? atoi(getenv("B200_STREAMK")) : 1;
-    if (streamk_env && g.tma_store && !d->side && g.kblocks >= 32 && g.total_tiles * 4 <= (kNumSMs / 2) * 3 &&
+    if (streamk_env && g.tma_store && !d->d_fp32 && !d->side && g.kblocks >= 32 && g.total_tiles * 4 <= (kNumSMs / 2) * 3 &&
         d->N % 32 == 0 && static_cast<long long>(g.total_tiles) * g.kblocks >= kNumSMs / 2) {
         const size_t row_bytes = static_cast<size_t>(d->N) * 2;
         cudaError_t e = cudaSuccess;
