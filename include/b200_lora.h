@@ -159,13 +159,16 @@ int b200_lora_wgrad_batch(const b200_wgrad_problem_t* problems, int32_t n, void*
  * split_ws (optional, may be NULL): fp32 [2*B*Lk*ld + B*H] that is ZERO on entry and is left zero by the kernel; with it,
  * a single-key-block problem (Lk <= 128: every cross-attention layer) whose (H, B) grid would leave SMs idle splits its
  * query blocks over more CTAs (partial dK / dV summed with fp32 atomics, last CTA of a head rounds them to bf16).
+ * dsc (optional, may be NULL): bf16 [B, L, ld_dsc], the gradient of the head-summed pre-softmax scores captured by
+ * DAAMLossAttnProcessor2_0 (trainer/ti_cross_attn_loss.py:201-212) - the score is sum_h scale*q_h.k_h, so its gradient
+ * joins dS inside the kernel (dQ_h += scale*dsc.K_h, dK_h += scale*dsc^T.Q_h); columns [0, dsc_cols) of a row are read.
  * --------------------------------------------------------------------------------------------------------- */
 int b200_flash_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t B, int32_t H,
                         int32_t L, int32_t Lk, int64_t ld, int64_t ld_o, float scale, void* stream);
 int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o, const float* lse,
                         float* delta_ws, float* dq_acc_ws, void* dq, void* dk, void* dv, int32_t B, int32_t H,
                         int32_t L, int32_t Lk, int64_t ld_qkv, int64_t ld_o, int64_t ld_d, float scale, float* split_ws,
-                        int64_t split_ws_floats, void* stream);
+                        int64_t split_ws_floats, const void* dsc, int64_t ld_dsc, int32_t dsc_cols, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Normalisation / activation kernels on NHWC ([rows, C]) bf16 activations; replace ATen GroupNorm / LayerNorm /

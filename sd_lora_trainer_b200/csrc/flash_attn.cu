@@ -45,7 +45,8 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
 extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                                    const float* lse, float* delta_ws, float* dq_acc_ws, void* dq, void* dk, void* dv,
                                    int32_t B, int32_t H, int32_t L, int32_t Lk, int64_t ld_qkv, int64_t ld_o, int64_t ld,
-                                   float scale, float* split_ws, int64_t split_ws_floats, void* stream) {
+                                   float scale, float* split_ws, int64_t split_ws_floats, const void* dsc, int64_t ld_dsc,
+                                   int32_t dsc_cols, void* stream) {
     // ld_qkv: row stride of q / k / v; ld_o: of o and d_o; ld: of the outputs dq / dk / dv (the fused q|k|v projection hands
     // column slices of one [rows, 3C] buffer in and takes the three gradients back the same way)
     const int64_t C64 = static_cast<int64_t>(H) * 64;
@@ -55,7 +56,8 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+        cudaError_t e = cudaFuncSetAttribute(flash_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem);
         if (e != cudaSuccess) return set_error(3, "flash_attn_bwd: %s", cudaGetErrorString(e));
         attr = true;
     }
@@ -90,6 +92,14 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     g.H = H;
     g.ld = ld;
     g.scale = scale;
+    if (dsc != nullptr) {
+        B200_CHECK_ARG(ld_dsc % 8 == 0 && dsc_cols % 8 == 0 && dsc_cols >= 0 && dsc_cols <= ld_dsc &&
+                           reinterpret_cast<uintptr_t>(dsc) % 16 == 0,
+                       "flash_attn_bwd: the score-gradient rows must be 16-byte aligned with a multiple of 8 readable columns");
+        g.dSc = static_cast<const __nv_bfloat16*>(dsc);
+        g.ld_dsc = ld_dsc;
+        g.dsc_cols = dsc_cols;
+    }
     dim3 grid((Lk + 127) / 128, H, B);
     // single key block (cross-attention) on a grid that would leave SMs idle: split the query blocks over blockIdx.x
     g.nsplit = 1;
@@ -108,7 +118,8 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
             grid.x = ns;
         }
     }
-    launch_pdl(flash_bwd_kernel, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
+    if (g.dSc != nullptr) launch_pdl(flash_bwd_kernel<true>, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
+    else launch_pdl(flash_bwd_kernel<false>, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     B200_CHECK_LAUNCH("flash_bwd");
     if (!dq_direct) {
         launch_pdl(f32_to_bf16_kernel, dim3(grid_for(nq_elems / 4, 256)), dim3(256), 0, st, dq_acc_ws, static_cast<__nv_bfloat16*>(dq),

@@ -350,12 +350,20 @@ struct FlashBwdArgs {
     // nsplit contiguous ranges.  dQ blocks are disjoint (written directly); every CTA adds its partial dK / dV (fp32
     // atomics) into dKVacc [2][B*Lk, ld], and the LAST CTA of a (b, h) to finish - counted in `counters` - rounds the sums
     // to bf16 into dK / dV and re-zeroes accumulators and counter, so the workspace is clean for the next launch.
+    // Gradient of the head-summed pre-softmax scores (the DAAM hook, trainer/ti_cross_attn_loss.py:201-212): the hook's
+    // score is sum_h scale * q_h . k_h, so its gradient dSc[b, q, key] (bf16, the same for every head) enters exactly where
+    // dS does:  dQ_h = (dS_h + scale * dSc) . K_h,  dK_h = (dS_h + scale * dSc)^T . Q_h - no separate GEMMs.  Columns
+    // [0, dsc_cols) of each row are readable (a multiple of 8; the padding beyond Lk is zero).  NULL: no hook.
+    const __nv_bfloat16* dSc;
+    long long ld_dsc;
+    int dsc_cols;
     int nsplit;
     int nbatch_rows;                           // B * Lk: rows of one accumulator plane
     float* dKVacc;
     int* counters;
 };
 
+template <bool kHook>
 __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_constant__ FlashBwdArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdBar);
@@ -508,18 +516,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                     tmem_ld32(t_dP + lane_off + c * 32, rp);
                     tmem_ld_wait();
                     float p[32], ds[32];
+                    float hk[kHook ? 32 : 1];                       // the hook instantiation only (cross-attention layers)
+#pragma unroll
+                    for (int e = 0; e < (kHook ? 32 : 1); ++e) hk[e] = 0.f;
+                    if (kHook && qok) {
+                        // this thread's slice of the hook gradient: columns k0 + c*32 .. +32 of its query row
+                        const int col0 = k0 + c * 32;
+                        const __nv_bfloat16* hp = g.dSc + (static_cast<long long>(b) * g.L + q) * g.ld_dsc + col0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (col0 + j * 8 + 8 <= g.dsc_cols) {
+                                const uint4 w = *reinterpret_cast<const uint4*>(hp + j * 8);
+                                const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                                for (int t2 = 0; t2 < 4; ++t2) {
+                                    hk[kHook ? j * 8 + 2 * t2 : 0] = __uint_as_float(u[t2] << 16) * g.scale;
+                                    hk[kHook ? j * 8 + 2 * t2 + 1 : 0] = __uint_as_float(u[t2] & 0xffff0000u) * g.scale;
+                                }
+                            }
+                        }
+                    }
                     if (full_blk) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             p[e] = fast_exp2(fmaf(__uint_as_float(rs[e]), sl2, -lse2));
-                            ds[e] = p[e] * (__uint_as_float(rp[e]) - delta) * g.scale;
+                            ds[e] = fmaf(p[e] * (__uint_as_float(rp[e]) - delta), g.scale, hk[kHook ? e : 0]);
                         }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             const bool ok = qok && (c * 32 + e < kvalid);
                             p[e] = ok ? fast_exp2(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
-                            ds[e] = p[e] * (__uint_as_float(rp[e]) - delta) * g.scale;
+                            ds[e] = ok ? fmaf(p[e] * (__uint_as_float(rp[e]) - delta), g.scale, hk[kHook ? e : 0]) : 0.f;
                         }
                     }
 #pragma unroll

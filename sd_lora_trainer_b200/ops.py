@@ -213,9 +213,10 @@ def _flash_split_ws(device, floats: int) -> torch.Tensor:
     return ws
 
 
-def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale: float, dk=None, dv=None, dq=None):
+def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale: float, dk=None, dv=None, dq=None, dsc=None):
     """Returns (dq [B*L, C], dk [B*Lk, C], dv [B*Lk, C]) bf16; dq / dk / dv may be caller-provided buffers that share one
-    row stride (e.g. the three column slices of a [rows, 3C] gradient buffer)."""
+    row stride (e.g. the three column slices of a [rows, 3C] gradient buffer).  dsc: optional bf16 [B, L, Lp] (Lp a multiple
+    of 8, zero beyond Lk): gradient of the head-summed pre-softmax scores, folded into dS inside the kernel."""
     C_ = H * 64
     dev = q.device
     dq = torch.empty(B * L, C_, dtype=BF16, device=dev) if dq is None else dq
@@ -224,6 +225,9 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale:
     ld_d = dq.stride(0)
     assert dk.stride(0) == ld_d and dv.stride(0) == ld_d and dq.stride(1) == 1 and dk.stride(1) == 1 and dv.stride(1) == 1
     assert k.stride(0) == q.stride(0) and v.stride(0) == q.stride(0) and o.stride(0) == d_o.stride(0)
+    if dsc is not None:
+        assert dsc.dtype == BF16 and dsc.shape[:2] == (B, L) and dsc.stride(2) == 1 and dsc.stride(0) == L * dsc.stride(1)
+        assert dsc.shape[2] % 8 == 0 and dsc.shape[2] >= Lk and Lk <= 128
     delta = torch.empty(B * H * L, dtype=torch.float32, device=dev)
     single = Lk <= 128                                # one key block: dQ is written directly, no fp32 accumulator needed
     dq_acc = None if single else torch.empty(B * L * C_, dtype=torch.float32, device=dev)
@@ -232,7 +236,9 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale:
     check(_lib.load().b200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
                                           lse.data_ptr(), delta.data_ptr(), _p(dq_acc), dq.data_ptr(),
                                           dk.data_ptr(), dv.data_ptr(), B, H, L, Lk, q.stride(0), o.stride(0), ld_d, scale,
-                                          _p(ws), ws.numel() if ws is not None else 0, _stream()), "flash_attn_bwd")
+                                          _p(ws), ws.numel() if ws is not None else 0, _p(dsc),
+                                          dsc.stride(1) if dsc is not None else 0, dsc.shape[2] if dsc is not None else 0,
+                                          _stream()), "flash_attn_bwd")
     return dq, dk, dv
 
 

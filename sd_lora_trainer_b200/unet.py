@@ -722,12 +722,22 @@ class Attn:
         if fused:                                      # the three gradients land in column slices of one [M, 3C] buffer
             dqkv = torch.empty(B * L, 3 * C, dtype=BF16, device=dev)
             dQ_out, dK_out, dV_out = dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]
+        dsc = None
+        if dscores is not None:
+            if dscores.shape[-1] == Lp and dscores.is_contiguous():
+                dsc = dscores                              # already in the padded row layout (shared across layers; read-only)
+            else:
+                dsc = torch.zeros(B, L, Lp, dtype=BF16, device=dev)
+                dsc[:, :, :Lk] = dscores
+        fold = dsc is not None and fa is not None and Lk <= 128      # the hook's gradient joins dS inside the fused kernel
         if fa is not None and d == 64:
             qf, kf, vf, Of = fa
-            dQ, dK, dV = ops.flash_attn_bwd(qf, kf, vf, Of, dO, lse, B, H, L, Lk, scale, dk=dK_out, dv=dV_out, dq=dQ_out)
+            dQ, dK, dV = ops.flash_attn_bwd(qf, kf, vf, Of, dO, lse, B, H, L, Lk, scale, dk=dK_out, dv=dV_out, dq=dQ_out,
+                                            dsc=dsc if fold else None)
         elif fa is not None:
             qf, kf, vf, Of = fa
-            dQf, dKf, dVf = ops.flash_attn_bwd(qf, kf, vf, Of, ops.head_pad(dO, H, d, 64), lse, B, H, L, Lk, scale)
+            dQf, dKf, dVf = ops.flash_attn_bwd(qf, kf, vf, Of, ops.head_pad(dO, H, d, 64), lse, B, H, L, Lk, scale,
+                                               dsc=dsc if fold else None)
             dQ = ops.head_pad(dQf, H, 64, d, out=dQ_out)
             dK = ops.head_pad(dKf, H, 64, d, out=dK_out)
             dV = ops.head_pad(dVf, H, 64, d, out=dV_out)
@@ -754,12 +764,7 @@ class Attn:
             ops.gemm(dK, Lk, d, [(Mat(dS, L, Lk, Lp, mn=True, sb0=L * Lp, sb1=H * L * Lp, batched=True),
                                   Mat(q, L, d, C, mn=True, sb0=d, sb1=L * C, batched=True), L)],
                      d_strides=(C, 1, d, Lk * C), alpha=scale, nb0=H, nb1=B)
-        if dscores is not None:
-            if dscores.shape[-1] == Lp and dscores.is_contiguous():
-                dsc = dscores                              # already in the padded row layout (shared across layers; read-only)
-            else:
-                dsc = torch.zeros(B, L, Lp, dtype=BF16, device=dev)
-                dsc[:, :, :Lk] = dscores
+        if dsc is not None and not fold:
             ops.gemm(dQ, L, C, [(Mat(dsc, L, Lk, Lp, sb1=L * Lp, batched=True),
                                  Mat(k, Lk, C, C, mn=True, sb1=Lk * C, batched=True), Lk)],
                      d_strides=(C, 1, 0, L * C), alpha=scale, residual=dQ, r_strides=(C, 1, 0, L * C), nb0=1, nb1=B)

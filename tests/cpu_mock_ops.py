@@ -170,7 +170,7 @@ def flash_attn_fwd(q, k, v, B, H, L, Lk, scale):
     return _bf(o.transpose(1, 2).reshape(B * L, C_)), torch.logsumexp(s, -1)
 
 
-def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale, dk=None, dv=None, dq=None):
+def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale, dk=None, dv=None, dq=None, dsc=None):
     C_ = H * 64
     assert k.stride(0) == q.stride(0) and v.stride(0) == q.stride(0) and o.stride(0) == d_o.stride(0)
     for t in (dq, dk, dv):
@@ -180,6 +180,12 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, B, H, L, Lk, scale, dk=None, dv=None, d
     v4 = v.float().reshape(B, Lk, H, 64).transpose(1, 2).detach().requires_grad_(True)
     out = torch.softmax(q4 @ k4.transpose(-1, -2) * scale, -1) @ v4
     out.backward(d_o.float().reshape(B, L, H, 64).transpose(1, 2))
+    if dsc is not None:                              # hook: score = sum_h scale * q_h.k_h  ->  its gradient joins dS for every head
+        assert dsc.dtype == BF16 and dsc.shape[:2] == (B, L) and dsc.shape[2] % 8 == 0 and dsc.shape[2] >= Lk and Lk <= 128
+        assert (dsc.storage_offset() * 2) % 16 == 0 and dsc.stride(1) % 8 == 0
+        g_ = dsc[:, :, :Lk].float()[:, None] * scale                      # [B, 1, L, Lk]
+        q4.grad += g_ @ k4.detach()
+        k4.grad += g_.transpose(-1, -2) @ q4.detach()
     unh = lambda t, n: _bf(t.transpose(1, 2).reshape(B * n, C_))
     gk, gv = unh(k4.grad, Lk), unh(v4.grad, Lk)
     if dk is not None:

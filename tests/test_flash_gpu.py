@@ -108,3 +108,34 @@ def test_narrow_heads_through_the_fused_kernel(B, H, L, Lk, d):
     assert rel(o, unh(ref, L)) < tol[0], ("o", rel(o, unh(ref, L)))
     for name, a, b_, n in (("dq", dq, qr.grad, L), ("dk", dk, kr.grad, Lk), ("dv", dv, vr.grad, Lk)):
         assert rel(a, unh(b_, n)) < tol[1], (name, rel(a, unh(b_, n)))
+
+
+@pytest.mark.parametrize("B,H,L,Lk,d", [(2, 20, 1024, 77, 64), (2, 10, 4096, 77, 64), (1, 3, 300, 77, 64), (2, 8, 256, 77, 40), (1, 2, 130, 64, 64)])
+def test_score_hook_gradient_folded_into_the_backward(B, H, L, Lk, d):
+    """The DAAM hook's head-summed pre-softmax score  sc[b, l, t] = sum_h scale * q_h . k_h  has the gradient dsc (one map,
+    shared by all heads); passed to the fused backward it must add  scale * dsc . K_h  to dQ_h and  scale * dsc^T . Q_h
+    to dK_h - what the two extra GEMMs of the unfused form computed."""
+    from sd_lora_trainer_b200 import ops
+    C = H * d
+    g = torch.Generator(device="cuda").manual_seed(L + Lk + d)
+    q, k, v, do = (torch.randn(B * n, C, device="cuda", generator=g).to(BF) for n in (L, Lk, Lk, L))
+    Lp = (Lk + 7) // 8 * 8
+    dsc = torch.zeros(B, L, Lp, device="cuda", dtype=BF)
+    dsc[:, :, :Lk] = (torch.randn(B, L, Lk, device="cuda", generator=g) * 0.3).to(BF)
+    scale = d ** -0.5
+    if d != 64:
+        qf, kf, vf, dof = (ops.head_pad(t, H, d, 64) for t in (q, k, v, do))
+    else:
+        qf, kf, vf, dof = q, k, v, do
+    of, lse = ops.flash_attn_fwd(qf, kf, vf, B, H, L, Lk, scale)
+    dq0, dk0, dv0 = ops.flash_attn_bwd(qf, kf, vf, of, dof, lse, B, H, L, Lk, scale)
+    dq1, dk1, dv1 = ops.flash_attn_bwd(qf, kf, vf, of, dof, lse, B, H, L, Lk, scale, dsc=dsc)
+    torch.cuda.synchronize()
+    assert rel(dv1, dv0) < 1e-6                                                    # dV does not see the hook
+    qh = qf.float().view(B, L, H, 64).transpose(1, 2)
+    kh = kf.float().view(B, Lk, H, 64).transpose(1, 2)
+    gs = dsc[:, :, :Lk].float()[:, None] * scale                                      # [B, 1, L, Lk]
+    add_q = (gs @ kh).transpose(1, 2).reshape(B * L, H * 64)
+    add_k = (gs.transpose(-1, -2) @ qh).transpose(1, 2).reshape(B * Lk, H * 64)
+    assert rel(dq1.float() - dq0.float(), add_q) < 3e-2, rel(dq1.float() - dq0.float(), add_q)
+    assert rel(dk1.float() - dk0.float(), add_k) < 3e-2, rel(dk1.float() - dk0.float(), add_k)
