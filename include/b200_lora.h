@@ -95,6 +95,12 @@ typedef struct {
     /* 1: the B operands (B[*], S, B2 - frozen weights and LoRA factors) are NOT written by the kernel that precedes
        this launch on the stream, so the pair kernel may fetch them before its programmatic-dependency wait. */
     int32_t b_static;
+    /* GEGLU backward fused into the epilogue (CTA-pair kernel, bf16 row-major output, N % 32 == 0, no bias / residual /
+       side path): the product is dy[M, N], the input gradient of diffusers' GEGLU output (FeedForward.net.2's dgrad); with
+       geglu_h = the saved projection h = [value | gate] (bf16 [M, 2N], row stride geglu_h_ld) the kernel writes
+       D[m, j] = dy * gelu(gate) and D[m, N + j] = dy * value * gelu'(gate) - D is [M, 2N] - and dy is never stored. */
+    const void* geglu_h;
+    int64_t geglu_h_ld;
 } b200_gemm_t;
 
 int b200_gemm(const b200_gemm_t* desc, void* stream);

@@ -27,7 +27,8 @@ class GemmDesc(C.Structure):
                 ("R", c_void_p), ("r_sm", c_int64), ("r_sn", c_int64), ("r_sb0", c_int64), ("r_sb1", c_int64),
                 ("side", c_int32), ("side_r", c_int32), ("S", Operand), ("B2", Operand), ("side_alpha", c_float),
                 ("T_out", c_void_p), ("t_ld", c_int64),
-                ("group", c_int32), ("D2", c_void_p), ("d2_sm", c_int64), ("d2_sn", c_int64), ("b_static", c_int32)]
+                ("group", c_int32), ("D2", c_void_p), ("d2_sm", c_int64), ("d2_sn", c_int64), ("b_static", c_int32),
+                ("geglu_h", c_void_p), ("geglu_h_ld", c_int64)]
 
 
 class WgradProblem(C.Structure):

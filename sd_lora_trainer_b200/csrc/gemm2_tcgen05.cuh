@@ -41,6 +41,12 @@ struct Gemm2Args {
     // scalars first: they fit in a few constant-cache lines and are read once, before griddepcontrol.wait
     int M, N, BN, tiles_n, total_tiles, kblocks, ktail16;
     int b_mn, side, side_mn, b2_mn, side_r16, side_r;
+    // GEGLU backward fused into the epilogue (the input-gradient GEMM of FeedForward.net.2, diffusers GEGLU): the tile is
+    // dy[m, j] (j < N); with h = [value | gate] ([M, 2N], row stride h_ld) the epilogue writes dh[m, j] = dy * gelu(gate) and
+    // dh[m, N + j] = dy * value * gelu'(gate) into D ([M, 2N]) instead of dy itself
+    int geglu_bwd;
+    long long h_ld;
+    const __nv_bfloat16* H;
     int a_mn;                 // segment 0's A operand is MN-major ([K, M] with M contiguous: dY^T of a weight gradient): two 64 x 64 boxes per CTA
     int d_accum;              // fp32 output: D += result (each tile element is owned by one CTA: plain read-modify-write)
     int stage_bytes, num_stages, side_off, acc_stages;
@@ -293,6 +299,65 @@ __device__ __forceinline__ void epi2_chunk_tma_f32(const Epi2& e, const CUtensor
             tma_store_4d(mapD, box, n_chunk, m_warp, 0, 0);
             if (n_chunk + 16 < e.N) tma_store_4d(mapD, box + 2048, n_chunk + 16, m_warp, 0, 0);
         }
+        bulk_commit();
+    }
+    __syncwarp();
+}
+
+// GEGLU backward in the epilogue: one [32 x 32] chunk of dy (registers, rounded to bf16 like the stored tensor it replaces)
+// + the value / gate chunks of h -> two [32 x 32] chunks of dh (value half at column n_chunk, gate half at N + n_chunk),
+// each through one of this warp's two staging boxes.
+__device__ __forceinline__ void epi2_chunk_tma_geglu_bwd(const Epi2& e, const CUtensorMap* mapD, const uint32_t (&raw)[32],
+                                                         uint8_t* box, int lane, int m_warp, int n_chunk,
+                                                         const __nv_bfloat16* H, long long h_ld) {
+    const int m = m_warp + lane;
+    const bool rok = m < e.M;
+    const __nv_bfloat16* hv = H + static_cast<long long>(rok ? m : 0) * h_ld + n_chunk;
+    const __nv_bfloat16* hg = hv + e.N;
+    uint8_t* row_a = box + lane * 64;
+    uint8_t* row_g = box + 2048 + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    const float alpha = e.alpha;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 wa = make_uint4(0u, 0u, 0u, 0u), wg = wa;
+        if (rok) {
+            wa = *reinterpret_cast<const uint4*>(hv + 8 * j);
+            wg = *reinterpret_cast<const uint4*>(hg + 8 * j);
+        }
+        const uint32_t ua[4] = {wa.x, wa.y, wa.z, wa.w}, ug[4] = {wg.x, wg.y, wg.z, wg.w};
+        float da[8], dg[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int i = 2 * q + s2;
+                const float a = s2 ? __uint_as_float(ua[q] & 0xffff0000u) : __uint_as_float(ua[q] << 16);
+                const float gt = s2 ? __uint_as_float(ug[q] & 0xffff0000u) : __uint_as_float(ug[q] << 16);
+                const float d = bfr(__uint_as_float(raw[8 * j + i]) * alpha);
+                float gl, dgl;
+                gelu_both(gt, gl, dgl);
+                da[i] = d * bfr(gl);
+                dg[i] = bfr(d * a) * dgl;
+            }
+        }
+        uint4 oa, og;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(da[0], da[1]), t1 = __floats2bfloat162_rn(da[2], da[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(da[4], da[5]), t3 = __floats2bfloat162_rn(da[6], da[7]);
+        oa.x = *reinterpret_cast<const uint32_t*>(&t0), oa.y = *reinterpret_cast<const uint32_t*>(&t1);
+        oa.z = *reinterpret_cast<const uint32_t*>(&t2), oa.w = *reinterpret_cast<const uint32_t*>(&t3);
+        t0 = __floats2bfloat162_rn(dg[0], dg[1]), t1 = __floats2bfloat162_rn(dg[2], dg[3]);
+        t2 = __floats2bfloat162_rn(dg[4], dg[5]), t3 = __floats2bfloat162_rn(dg[6], dg[7]);
+        og.x = *reinterpret_cast<const uint32_t*>(&t0), og.y = *reinterpret_cast<const uint32_t*>(&t1);
+        og.z = *reinterpret_cast<const uint32_t*>(&t2), og.w = *reinterpret_cast<const uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(row_a + ((j ^ sw) * 16)) = oa;
+        *reinterpret_cast<uint4*>(row_g + ((j ^ sw) * 16)) = og;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_4d(mapD, box, n_chunk, m_warp, 0, 0);
+        tma_store_4d(mapD, box + 2048, e.N + n_chunk, m_warp, 0, 0);
         bulk_commit();
     }
     __syncwarp();
@@ -745,7 +810,12 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
             // converted / staged / stored (two register buffers)
             auto drain = [&](const uint32_t (&raw)[32], int c0) {
                 if (n0 + c0 >= e.N) return;            // warp-uniform
-                if (kEpi == 0 && tma_store) {
+                if (kEpi == 0 && tma_store && g.geglu_bwd) {
+                    if (m_warp >= e.M) return;         // (the host admits the mode only for N % 32 == 0: no ragged chunk)
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    epi2_chunk_tma_geglu_bwd(e, &g.mapD, raw, tma_box, lane, m_warp, n0 + c0, g.H, g.h_ld);
+                } else if (kEpi == 0 && tma_store) {
                     if (m_warp >= e.M) return;         // rows past the M edge (warp-uniform)
                     if (n0 + c0 + 32 <= e.N) {
                         // double-buffered staging box: the store issued two chunks ago must have read its smem

@@ -316,13 +316,25 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
         if (int rc = encode_map_ex(&g.mapD, d->D, 4, dD, sD, boxD, 64)) return rc;
         g.tma_store = 1;
     }
+    if (d->geglu_h != nullptr) {
+        B200_CHECK_ARG(g.tma_store && !d->d_fp32 && !d->side && !d->R && !d->bias && d->N % 32 == 0 && d->num_seg == 1 &&
+                           al16(d->geglu_h) && d->geglu_h_ld % 8 == 0 && d->geglu_h_ld >= 2LL * d->N && d->d_sm >= 2LL * d->N,
+                       "gemm2: fused GEGLU backward needs a plain bf16 TMA-store problem with N %% 32 == 0 and [M, 2N] h / D");
+        // the output tensor map spans both halves of dh
+        const long long dD[4] = {2LL * d->N, d->M, 1, 1}, sD[3] = {d->d_sm, 0, 0};
+        const int boxD[4] = {32, 32, 1, 1};
+        if (int rc = encode_map_ex(&g.mapD, d->D, 2, dD, sD, boxD, 64)) return rc;
+        g.geglu_bwd = 1;
+        g.H = static_cast<const __nv_bfloat16*>(d->geglu_h);
+        g.h_ld = d->geglu_h_ld;
+    }
     int pairs = g.total_tiles < kNumSMs / 2 ? g.total_tiles : kNumSMs / 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // stream-K: few tiles, long K (FF down-projection and its input gradient, the deep convs): cut the (tile, k-block)
     // space into 74 equal ranges so every SM works; partial tiles are added to D by TMA reduce-add, so D is pre-set
     // here to the residual (or zero) and the kernel sees no residual.
     static const int streamk_env = getenv("B200_STREAMK") ? atoi(getenv("B200_STREAMK")) : 1;
-    if (streamk_env && g.tma_store && !d->d_fp32 && !d->side && g.kblocks >= 32 && g.total_tiles * 4 <= (kNumSMs / 2) * 3 &&
+    if (streamk_env && g.tma_store && !d->d_fp32 && !d->side && !g.geglu_bwd && g.kblocks >= 32 && g.total_tiles * 4 <= (kNumSMs / 2) * 3 &&
         d->N % 32 == 0 && static_cast<long long>(g.total_tiles) * g.kblocks >= kNumSMs / 2) {
         const size_t row_bytes = static_cast<size_t>(d->N) * 2;
         cudaError_t e = cudaSuccess;
@@ -366,6 +378,7 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
         B200_CHECK_ARG(d->pair_mode <= 0, "gemm: pair_mode forced on a problem the pair kernel does not cover");
     }
 
+    B200_CHECK_ARG(d->geglu_h == nullptr, "gemm: the fused GEGLU backward exists only in the CTA-pair kernel (M >= 256, N >= 64, K >= 64)");
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);

@@ -89,12 +89,15 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
          residual: Optional[torch.Tensor] = None, r_strides: Optional[Tuple[int, int, int, int]] = None,
          nb0: int = 1, nb1: int = 1, splits: int = 1, atomic: bool = False, block_n: int = 0,
          side: Optional[Tuple[Mat, Mat, int, float, Optional[torch.Tensor]]] = None, pair_mode: int = 0,
-         group_out: Optional[Tuple[torch.Tensor, Tuple[int, int]]] = None, static_b: bool = False) -> torch.Tensor:
+         group_out: Optional[Tuple[torch.Tensor, Tuple[int, int]]] = None, static_b: bool = False,
+         geglu_h: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b1][b0][m, n] = alpha * sum_seg A_seg.B_seg^T (+bias) (+residual).  segs: (A | Conv3x3, B, K).
     side = (S, B2, r, side_alpha, T_out): fused low-rank path  out += (side_alpha * A.S^T).B2^T, T_out <- the inner
     product (bf16) - see include/b200_lora.h.
     group_out = (out2, (sm, sn)): the two segments are independent problems; segment 1 accumulates into out2.
-    static_b: every B-side operand is a parameter tensor the preceding kernel does not write (weights, LoRA factors)."""
+    static_b: every B-side operand is a parameter tensor the preceding kernel does not write (weights, LoRA factors).
+    geglu_h: h = [value | gate] bf16 [M, 2N]: the product is the GEGLU output's gradient dy and `out` ([M, 2N]) receives the
+    GEGLU backward  [dy * gelu(gate) | dy * value * gelu'(gate)]  straight from the epilogue (CTA-pair kernel only)."""
     _chk_dev(out, bias, residual)
     d = GemmDesc()
     d.M, d.N, d.num_seg = M, N, len(segs)
@@ -119,6 +122,10 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
         out2, (sm2, sn2) = group_out
         assert atomic and len(segs) == 2 and out2.dtype == torch.float32
         d.group, d.D2, d.d2_sm, d.d2_sn = 1, out2.data_ptr(), sm2, sn2
+    if geglu_h is not None:
+        assert geglu_h.dtype == BF16 and geglu_h.dim() == 2 and geglu_h.stride(1) == 1 and geglu_h.shape == (M, 2 * N)
+        assert out.shape == (M, 2 * N) and out.dtype == BF16
+        d.geglu_h, d.geglu_h_ld = geglu_h.data_ptr(), geglu_h.stride(0)
     d.D = out.data_ptr()
     d.d_fp32 = int(out.dtype == torch.float32)
     assert out.dtype in (torch.float32, BF16)

@@ -415,6 +415,32 @@ class Lin:
         return dx
 
 
+def _lin_bwd_geglu(self, dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+    """Input gradient of FeedForward.net.2 with the GEGLU backward fused into the GEMM's epilogue: returns
+    dh [M, 2K] = [dY.W * gelu(gate) | dY.W * value * gelu'(gate)] for h = [value | gate]; dY.W itself is never stored.
+    (B200_FUSE_GEGLU=0, small problems and LoRA-wrapped layers take the two-kernel form.)"""
+    M = dy.shape[0]
+    if not (FUSE_GEGLU and self.lora is None and M >= 256 and self.K >= 64 and self.K % 32 == 0 and self.N >= 64
+            and h.shape == (M, 2 * self.K) and h.stride(1) == 1):
+        return ops.geglu_bwd(self.bwd(dy), h)
+    x = self.x
+    self.x = self.T = None
+    dh = torch.empty(M, 2 * self.K, dtype=BF16, device=dy.device)
+    ops.gemm(dh, M, self.K, [(kmajor(dy), mnmajor(self.W), self.N)], geglu_h=h, static_b=True, pair_mode=1)
+    if self.gW is not None:                            # dense fine-tune: this layer's own weight / bias gradients
+        seg = (Mat(dy, M, self.N, dy.stride(0), mn=True), Mat(x, M, self.K, x.stride(0), mn=True), M)
+        if _pair_wgrad_ok(self.N, self.K, M):
+            ops.gemm(self.gW, self.N, self.K, [seg], d_strides=(self.K, 1, 0, 0), atomic=True, pair_mode=1)
+        else:
+            ops.gemm(self.gW, self.N, self.K, [seg], d_strides=(self.K, 1, 0, 0), splits=_dense_splits(self.N, self.K, M), atomic=True)
+        if self.gb is not None:
+            self.gb += ops.colsum(dy if dy.is_contiguous() else dy.contiguous(), 1, M, self.N)[0].float()
+    return dh
+
+
+FUSE_GEGLU = os.environ.get("B200_FUSE_GEGLU", "1") != "0"
+
+
 class LinQKV:
     """to_q | to_k | to_v of a self-attention block as ONE projection: y[M, 3C] = x.W_qkv^T + (s.x.A_qkv^T).B_bd^T
     with the three frozen weights stacked, the three LoRA-A factors contiguous ([3r, K]) and B_bd the block-diagonal
@@ -486,6 +512,9 @@ class LinQKV:
         else:
             ops.lora_wgrad_batch(items)
         return dx
+
+
+Lin.bwd_geglu = _lin_bwd_geglu
 
 
 class Conv3:
@@ -871,7 +900,7 @@ class TBlock:
         return self.ff2.fwd(ops.geglu_fwd(h), residual=x2)
 
     def bwd(self, dx3, d_ctx, dscores):
-        dh = ops.geglu_bwd(self.ff2.bwd(dx3), self.h)
+        dh = self.ff2.bwd_geglu(dx3, self.h)         # GEGLU backward in the epilogue of ff2's input-gradient GEMM
         self.h = None
         dx2 = self.ln3.bwd(self.ff1.bwd(dh), dres=dx3)
         dx1 = self.ln2.bwd(self.attn2.bwd(dx2, d_ctx, dscores), dres=dx2)

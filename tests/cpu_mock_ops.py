@@ -90,8 +90,18 @@ def _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out, pair_m
 
 
 def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, bias_sb=0, residual=None,
-         r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0, side=None, pair_mode=0, group_out=None, static_b=False):
+         r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0, side=None, pair_mode=0, group_out=None, static_b=False,
+         geglu_h=None):
     _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out, pair_mode)
+    if geglu_h is not None:
+        # fused GEGLU backward (CTA-pair kernel only): the product is dy [M, N]; out [M, 2N] <- geglu_bwd(bf16(dy), h)
+        assert M >= 256 and N >= 64 and N % 32 == 0 and segs[0][2] >= 64 and len(segs) == 1 and side is None and bias is None
+        assert residual is None and not atomic and nb0 == 1 and nb1 == 1 and out.dtype == BF16 and out.shape == (M, 2 * N)
+        assert geglu_h.dtype == BF16 and geglu_h.shape == (M, 2 * N) and geglu_h.stride(0) % 8 == 0 and (geglu_h.storage_offset() * 2) % 16 == 0
+        dy = torch.empty(M, N, dtype=BF16)
+        gemm(dy, M, N, segs, alpha=alpha)
+        out.copy_(geglu_bwd(dy, geglu_h))
+        return out
     assert residual is None or residual.dtype == BF16
     if group_out is not None:                       # two independent problems sharing one launch
         out2, (sm2, sn2) = group_out

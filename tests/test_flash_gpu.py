@@ -131,7 +131,7 @@ def test_score_hook_gradient_folded_into_the_backward(B, H, L, Lk, d):
     dq0, dk0, dv0 = ops.flash_attn_bwd(qf, kf, vf, of, dof, lse, B, H, L, Lk, scale)
     dq1, dk1, dv1 = ops.flash_attn_bwd(qf, kf, vf, of, dof, lse, B, H, L, Lk, scale, dsc=dsc)
     torch.cuda.synchronize()
-    assert rel(dv1, dv0) < 1e-6                                                    # dV does not see the hook
+    assert rel(dv1, dv0) < 1e-3                # dV does not see the hook (query-split launches sum dV with fp32 atomics: order noise)
     qh = qf.float().view(B, L, H, 64).transpose(1, 2)
     kh = kf.float().view(B, Lk, H, 64).transpose(1, 2)
     gs = dsc[:, :, :Lk].float()[:, None] * scale                                      # [B, 1, L, Lk]

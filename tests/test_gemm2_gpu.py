@@ -166,6 +166,30 @@ def test_pair_dense_weight_gradient_mn_major_a_accumulates(N, K, M):
     _close(dw - before, 2 * ref, tol=5e-3, what="second accumulation")
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 5120, 1280), (8192, 2560, 640), (512, 512, 128), (300, 160, 200), (256, 64, 64)])
+def test_pair_fused_geglu_backward_epilogue(M, N, K):
+    """dh = geglu_bwd(dY . W, h) from the epilogue of the input-gradient GEMM of FeedForward.net.2 (W [K, N] read MN-major):
+    same result as the GEMM followed by the stand-alone GEGLU backward kernel."""
+    from sd_lora_trainer_b200 import ops
+    dy, w = _rand(M, K, scale=0.5), _rand(K, N, seed=1, scale=0.05)
+    h = _rand(M, 2 * N, seed=2)
+    dh = torch.full((M, 2 * N), 7.0, dtype=BF, device="cuda")
+    ops.gemm(dh, M, N, [(ops.kmajor(dy), ops.mnmajor(w), K)], geglu_h=h, pair_mode=1, static_b=True)
+    mid = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(mid, M, N, [(ops.kmajor(dy), ops.mnmajor(w), K)], pair_mode=1)
+    ref = ops.geglu_bwd(mid, h)
+    torch.cuda.synchronize()
+    _close(dh, ref, tol=1e-2, what=f"fused geglu bwd {M}x{N}x{K}")
+    # and against plain torch on the fp32 product
+    d32 = (dy.float() @ w.float()).to(BF).float()
+    val, gate = h[:, :N].float(), h[:, N:].float()
+    gl = torch.nn.functional.gelu(gate)
+    cdf = 0.5 * (1 + torch.erf(gate / 2 ** 0.5))
+    pdf = torch.exp(-0.5 * gate * gate) / (2 * 3.141592653589793) ** 0.5
+    _close(dh[:, :N], d32 * gl, tol=2e-2, what="value half")
+    _close(dh[:, N:], d32 * val * (cdf + gate * pdf), tol=2e-2, what="gate half")
+
+
 def test_pair_back_to_back_launches_are_ordered():
     """Programmatic dependent launch + clusters: a chain of dependent GEMMs (each reads the previous output)."""
     from sd_lora_trainer_b200 import ops
