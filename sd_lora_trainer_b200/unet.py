@@ -418,7 +418,7 @@ class Lin:
 def _lin_bwd_geglu(self, dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
     """Input gradient of FeedForward.net.2 with the GEGLU backward fused into the GEMM's epilogue: returns
     dh [M, 2K] = [dY.W * gelu(gate) | dY.W * value * gelu'(gate)] for h = [value | gate]; dY.W itself is never stored.
-    (B200_FUSE_GEGLU=0, small problems and LoRA-wrapped layers take the two-kernel form.)"""
+    (Only with B200_FUSE_GEGLU=1 - see FUSE_GEGLU below; otherwise, and for small problems, the two-kernel form.)"""
     M = dy.shape[0]
     if not (FUSE_GEGLU and self.lora is None and M >= 256 and self.K >= 64 and self.K % 32 == 0 and self.N >= 64
             and h.shape == (M, 2 * self.K) and h.stride(1) == 1):
@@ -438,7 +438,10 @@ def _lin_bwd_geglu(self, dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
     return dh
 
 
-FUSE_GEGLU = os.environ.get("B200_FUSE_GEGLU", "1") != "0"
+# Measured on the B200 (profiles/r02h_*): correct (test_gemm2_gpu.py::test_pair_fused_geglu_backward_epilogue) but SLOWER than
+# the two-kernel form, 70.0 vs 68.9 ms/step - the epilogue warps now wait on two dependent global loads of h per chunk and
+# run the erf arithmetic, so the epilogue (not the 5.4 us mainloop) bounds each tile.  Off by default; kept for the A/B.
+FUSE_GEGLU = os.environ.get("B200_FUSE_GEGLU", "0") == "1"
 
 
 class LinQKV:
