@@ -7,7 +7,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sd_lora_trainer_b200 import ops  # noqa: E402
 
-B, H, L = 2, 10, int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+B, L = 2, int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 C = H * 64
 BF = torch.bfloat16
 q, k, v, do = (torch.randn(B * L, C, device="cuda").to(BF) for _ in range(4))
