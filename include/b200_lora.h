@@ -162,9 +162,10 @@ int b200_lora_wgrad_batch(const b200_wgrad_problem_t* problems, int32_t n, void*
  * ld_o for o and d_o, ld_d for dq / dk / dv - so q | k | v (and their gradients) may be column slices of one [rows, 3C]
  * buffer, the output of the fused q|k|v projection.
  * Backward workspaces (caller-owned): delta_ws fp32 [B*H*L], dq_acc_ws fp32 [B*L*H*64] (NULL when Lk <= 128).
- * split_ws (optional, may be NULL): fp32 [2*B*Lk*ld + B*H] that is ZERO on entry and is left zero by the kernel; with it,
- * a single-key-block problem (Lk <= 128: every cross-attention layer) whose (H, B) grid would leave SMs idle splits its
- * query blocks over more CTAs (partial dK / dV summed with fp32 atomics, last CTA of a head rounds them to bf16).
+ * split_ws (optional, may be NULL): fp32 [2*B*Lk*ld_d + B*H*ceil(Lk/128)] that is ZERO on entry and is left zero by the
+ * kernel; with it, a problem whose (key blocks, H, B) grid would leave SMs idle (Lk <= 128: every cross-attention layer) or
+ * quantise badly over the 148 SMs (self-attention at L = 1024) splits its query blocks over more CTAs (partial dK / dV
+ * summed with fp32 atomics, the last CTA of a (b, h, key block) rounds them to bf16).
  * dsc (optional, may be NULL): bf16 [B, L, ld_dsc], the gradient of the head-summed pre-softmax scores captured by
  * DAAMLossAttnProcessor2_0 (trainer/ti_cross_attn_loss.py:201-212) - the score is sum_h scale*q_h.k_h, so its gradient
  * joins dS inside the kernel (dQ_h += scale*dsc.K_h, dK_h += scale*dsc^T.Q_h); columns [0, dsc_cols) of a row are read.
@@ -181,8 +182,10 @@ int b200_flash_attn_bwd(const void* q, const void* k, const void* v, const void*
  * SiLU / GELU kernels under diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock, GEGLU.
  * Affine parameters are frozen, so the backward kernels emit dX only.
  * --------------------------------------------------------------------------------------------------------- */
-/* stats: [batch, groups, 2] fp32 (mean, rstd) followed by a [batch, groups, 2] fp64 scratch area, i.e. the caller
-   allocates 6 floats per (image, group), 8-byte aligned; the backward reuses the scratch area. */
+/* stats: [batch, groups, 2] fp32 (mean, rstd) followed by fp64 scratch (the per-(image, group) sums and the per-block
+   partial sums they are added from, in block order - no atomics, so the statistics are bit-reproducible); the caller
+   allocates b200_groupnorm_stats_floats(batch, hw, C, groups) floats, 8-byte aligned; the backward reuses the scratch. */
+int64_t b200_groupnorm_stats_floats(int32_t batch, int64_t hw, int32_t C, int32_t groups);
 int b200_groupnorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats, int32_t batch,
                        int64_t hw, int32_t C, int32_t groups, float eps, int32_t silu, void* stream);
 /* dx = dGroupNorm(dy) (+ dres when non-NULL: the gradient arriving through the residual/shortcut branch) */

@@ -1,5 +1,6 @@
 // Host side of the fused attention kernels (head_dim 64): tensor maps over the [B*L, C] projection outputs with the
 // head as a strided batch dimension, launch configuration, and the small helper kernels of the backward.
+#include <stdlib.h>
 #include "common.cuh"
 #include "flash_attn.cuh"
 #include "../../include/b200_lora.h"
@@ -101,21 +102,42 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
         g.dsc_cols = dsc_cols;
     }
     dim3 grid((Lk + 127) / 128, H, B);
-    // single key block (cross-attention) on a grid that would leave SMs idle: split the query blocks over blockIdx.x
+    // Query split: (a) single key block (cross-attention) on a grid that would leave SMs idle; (b) several key blocks whose
+    // CTA count quantises badly over the 148 SMs (one CTA per SM): pick the split that minimises rounds x blocks per CTA,
+    // charging each extra CTA its fixed cost (K / V load, prologue, atomic epilogue ~ 1.5 query blocks).
     g.nsplit = 1;
-    const int nq = (L + 127) / 128;
+    const int nq = (L + 127) / 128, nkb = (Lk + 127) / 128;
+    g.nkb = nkb;
     const long long plane = static_cast<long long>(B) * Lk * ld;
-    if (dq_direct && split_ws != nullptr && nq >= 2 && B * H < kNumSMs &&
-        split_ws_floats >= 2 * plane + static_cast<long long>(B) * H) {
-        int ns = kNumSMs / (B * H);
-        if (ns > nq) ns = nq;
-        if (ns >= 2) {
+    // (b) is opt-in (B200_FLASH_QSPLIT=1): with a uniform split the extra CTAs' fixed cost eats the rounds it saves (the model
+    // below picks 1 for SDXL's L = 1024 layers); a non-uniform, stream-K-style cut of the (key block, query block) grid is
+    // what would pay
+    static const int split_env = getenv("B200_FLASH_QSPLIT") ? atoi(getenv("B200_FLASH_QSPLIT")) : 0;
+    if (split_ws != nullptr && nq >= 2 && split_ws_floats >= 2 * plane + static_cast<long long>(B) * H * nkb) {
+        int best = 1;
+        if (dq_direct && B * H < kNumSMs) {
+            best = kNumSMs / (B * H);
+            if (best > nq) best = nq;
+        } else if (!dq_direct && split_env) {
+            double best_cost = 1e30;
+            for (int ns = 1; ns <= 4 && ns <= nq; ++ns) {
+                const long long ctas = static_cast<long long>(nkb) * H * B * ns;
+                const long long rounds = (ctas + kNumSMs - 1) / kNumSMs;
+                const double per_cta = (nq + ns - 1) / ns + (ns > 1 ? 1.5 : 0.5);
+                const double cost = rounds * per_cta;
+                if (cost < best_cost - 1e-9) {
+                    best_cost = cost;
+                    best = ns;
+                }
+            }
+        }
+        if (best >= 2) {
             B200_CHECK_ARG(reinterpret_cast<uintptr_t>(split_ws) % 16 == 0, "flash_attn_bwd: split workspace not 16-byte aligned");
-            g.nsplit = ns;
+            g.nsplit = best;
             g.nbatch_rows = B * Lk;
             g.dKVacc = split_ws;
             g.counters = reinterpret_cast<int*>(split_ws + 2 * plane);
-            grid.x = ns;
+            grid.x = nkb * best;
         }
     }
     if (g.dSc != nullptr) launch_pdl(flash_bwd_kernel<true>, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);

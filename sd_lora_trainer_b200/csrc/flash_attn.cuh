@@ -345,9 +345,10 @@ struct FlashBwdArgs {
     int L, Lk, H;
     long long ld;
     float scale;
-    // Query split (single key block only, i.e. cross-attention: Lk <= 128).  A grid of (1, H, B) CTAs that each walk all
-    // L/128 query blocks leaves most SMs idle (40 CTAs at SDXL's 1280-wide level), so blockIdx.x cuts the query blocks into
-    // nsplit contiguous ranges.  dQ blocks are disjoint (written directly); every CTA adds its partial dK / dV (fp32
+    // Query split.  A grid of (key blocks, H, B) CTAs that each walk all L/128 query blocks leaves SMs idle when it is small
+    // (cross-attention: 40 CTAs at SDXL's 1280-wide level) or quantises badly (self-attention at L = 1024: 320 CTAs on 148
+    // SMs = 3 rounds for 2.16 rounds of work), so blockIdx.x additionally cuts the query blocks into nsplit contiguous
+    // ranges.  dQ blocks are disjoint (written directly or reduce-added as before); every CTA adds its partial dK / dV (fp32
     // atomics) into dKVacc [2][B*Lk, ld], and the LAST CTA of a (b, h) to finish - counted in `counters` - rounds the sums
     // to bf16 into dK / dV and re-zeroes accumulators and counter, so the workspace is clean for the next launch.
     // Gradient of the head-summed pre-softmax scores (the DAAM hook, trainer/ti_cross_attn_loss.py:201-212): the hook's
@@ -358,6 +359,7 @@ struct FlashBwdArgs {
     long long ld_dsc;
     int dsc_cols;
     int nsplit;
+    int nkb;                                   // key blocks (counters are per (b, h, key block))
     int nbatch_rows;                           // B * Lk: rows of one accumulator plane
     float* dKVacc;
     int* counters;
@@ -384,9 +386,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
     const int nq_all = (g.L + 127) >> 7;
     const int nsplit = g.nsplit;
     // query blocks [qb0, qb0 + nq) of this CTA; ring stages / barrier phases follow the LOCAL block index
-    const int k0 = nsplit > 1 ? 0 : static_cast<int>(blockIdx.x) * 128;
-    const int qb0 = nsplit > 1 ? static_cast<int>((static_cast<long long>(nq_all) * blockIdx.x) / nsplit) : 0;
-    const int nq = nsplit > 1 ? static_cast<int>((static_cast<long long>(nq_all) * (blockIdx.x + 1)) / nsplit) - qb0 : nq_all;
+    // blockIdx.x = key block * nsplit + query split
+    const int kblk = static_cast<int>(blockIdx.x) / nsplit, qsp = static_cast<int>(blockIdx.x) - kblk * nsplit;
+    const int k0 = kblk * 128;
+    const int qb0 = nsplit > 1 ? static_cast<int>((static_cast<long long>(nq_all) * qsp) / nsplit) : 0;
+    const int nq = nsplit > 1 ? static_cast<int>((static_cast<long long>(nq_all) * (qsp + 1)) / nsplit) - qb0 : nq_all;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&g.mapQ);
@@ -680,17 +684,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
         // the last CTA of this (b, h) to arrive owns the final rounding: fp32 sums -> bf16 dK / dV, workspace re-zeroed
         __shared__ int s_last;
         if (threadIdx.x == 0) {
-            const int prev = atomicAdd(&g.counters[b * g.H + h], 1);
+            const int prev = atomicAdd(&g.counters[(b * g.H + h) * g.nkb + kblk], 1);
             s_last = (prev == nsplit - 1);
         }
         __syncthreads();
         if (s_last) {
             __threadfence();
             const long long half = static_cast<long long>(g.nbatch_rows) * g.ld;
-            for (int idx = threadIdx.x; idx < g.Lk * 16 * 2; idx += blockDim.x) {
-                const int which = idx / (g.Lk * 16);               // 0: dK, 1: dV
-                const int rem = idx - which * g.Lk * 16;
-                const int key = rem >> 4, c4 = (rem & 15) * 4;
+            const int kvalid2 = min(128, g.Lk - k0);               // keys of this block
+            for (int idx = threadIdx.x; idx < kvalid2 * 16 * 2; idx += blockDim.x) {
+                const int which = idx / (kvalid2 * 16);            // 0: dK, 1: dV
+                const int rem = idx - which * kvalid2 * 16;
+                const int key = k0 + (rem >> 4), c4 = (rem & 15) * 4;
                 const long long off = (static_cast<long long>(b) * g.Lk + key) * g.ld + h * 64 + c4;
                 float4* ap = reinterpret_cast<float4*>(g.dKVacc + which * half + off);
                 const float4 v = __ldcg(ap);
@@ -700,7 +705,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 w.y = pack_bf16(v.z, v.w);
                 *reinterpret_cast<uint2*>((which ? g.dV : g.dK) + off) = w;
             }
-            if (threadIdx.x == 0) g.counters[b * g.H + h] = 0;
+            if (threadIdx.x == 0) g.counters[(b * g.H + h) * g.nkb + kblk] = 0;
         }
     }
 }

@@ -7,8 +7,9 @@
 namespace b200 {
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm.  Pass 1 reduces per-(image, group) sums into a double workspace; pass 2 finalises
-// (mean, rstd); pass 3 normalises.  A block owns `k` rows x all channels per iteration so each
+// GroupNorm.  Pass 1 writes per-block partial sums of every (image, group) - combined inside the block in a fixed order,
+// no atomics, so the statistics (and with them the whole forward pass) are bit-reproducible run to run; pass 2 adds the
+// blocks' partials in block order and finalises (mean, rstd); pass 3 normalises.  A block owns `k` rows x all channels per iteration so each
 // thread keeps a FIXED 8-channel vector and accumulates in registers.
 // ---------------------------------------------------------------------------------------------
 template <bool kBackward, bool kSilu>
@@ -18,15 +19,12 @@ __global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restr
                                  int groups, int rows_per_block) {
     pdl_launch();
     pdl_wait();
-    __shared__ float gsum[2 * 64];
+    __shared__ float4 part[1024];              // one (lo0, lo1, hi0, hi1) per thread
     const int C8 = C >> 3, cpg = C / groups;
     const int b = blockIdx.y;
     const int v = threadIdx.x % C8, roff = threadIdx.x / C8, k = blockDim.x / C8;
     const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
     const long long r1 = min(r0 + rows_per_block, hw);
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) gsum[i] = 0.f;
-    __syncthreads();
-
     float a0[8], a1[8], gm[8], bt[8], mean[8], rstd[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
@@ -65,28 +63,64 @@ __global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restr
             }
         }
     }
+    // ---- deterministic combine (no atomics): a thread's 8 channels touch its first group g0 and, when the group width is
+    //      not a multiple of 8, g0 + 1; partials go to shared memory and one thread per (group, statistic) sums its
+    //      contributors in a fixed order; the block's sums land in ITS slot of the partial buffer ----
+    {
+        const int g0 = (v * 8) / cpg;
+        float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int g = (v * 8 + i) / cpg;
-        atomicAdd(&gsum[2 * g], a0[i]);
-        atomicAdd(&gsum[2 * g + 1], a1[i]);
+        for (int i = 0; i < 8; ++i) {
+            if ((v * 8 + i) / cpg == g0) {
+                lo0 += a0[i];
+                lo1 += a1[i];
+            } else {
+                hi0 += a0[i];
+                hi1 += a1[i];
+            }
+        }
+        part[threadIdx.x] = make_float4(lo0, lo1, hi0, hi1);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
-        atomicAdd(&ws[static_cast<long long>(b) * groups * 2 + i], static_cast<double>(gsum[i]));
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) {
+        const int g = i >> 1, stat = i & 1;
+        const int v_lo = (g * cpg) >> 3, v_hi = ((g + 1) * cpg - 1) >> 3;
+        float acc = 0.f;
+        for (int vv = v_lo; vv <= v_hi; ++vv) {
+            const bool is_lo = (vv * 8) / cpg == g;            // else this vector's upper channels belong to g
+            for (int rl = 0; rl < k; ++rl) {
+                const float4 pv = part[rl * C8 + vv];
+                acc += is_lo ? (stat ? pv.y : pv.x) : (stat ? pv.w : pv.z);
+            }
+        }
+        ws[(static_cast<long long>(b) * gridDim.x + blockIdx.x) * groups * 2 + i] = static_cast<double>(acc);
+    }
 }
 
-__global__ void gn_finalize_kernel(const double* __restrict__ ws, float* __restrict__ stats, int n, double count,
-                                   float eps) {
+// Sums the per-block partials [batch, splits, groups, 2] in block order (deterministic) into sums [batch, groups, 2] and,
+// for the forward, finalises (mean, rstd).
+__global__ void gn_finalize_kernel(const double* __restrict__ partials, double* __restrict__ sums, float* __restrict__ stats,
+                                   int batch, int groups, int splits, double count, float eps, int write_stats) {
     pdl_launch();
     pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double mean = ws[2 * i] / count;
-    double var = ws[2 * i + 1] / count - mean * mean;
-    if (var < 0) var = 0;
-    stats[2 * i] = static_cast<float>(mean);
-    stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (b, g)
+    if (i >= batch * groups) return;
+    const int b = i / groups, g = i - b * groups;
+    double s0 = 0.0, s1 = 0.0;
+    for (int sp = 0; sp < splits; ++sp) {
+        const double* pp = partials + ((static_cast<long long>(b) * splits + sp) * groups + g) * 2;
+        s0 += pp[0];
+        s1 += pp[1];
+    }
+    sums[2 * i] = s0;
+    sums[2 * i + 1] = s1;
+    if (write_stats) {
+        const double mean = s0 / count;
+        double var = s1 / count - mean * mean;
+        if (var < 0) var = 0;
+        stats[2 * i] = static_cast<float>(mean);
+        stats[2 * i + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
 }
 
 template <bool kSilu>
@@ -256,6 +290,16 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restr
     }
 }
 
+// stats layout (floats): [batch*groups*2 fp32 (mean, rstd)] [batch*groups*2 fp64 sums] [batch*splits*groups*2 fp64 partials]
+static void gn_geometry(int batch, long long hw, int C8, int k, long long* splits_out, long long* rpb_out) {
+    long long splits = (kNumSMs * 4 + batch - 1) / batch;
+    long long rpb = (hw + splits - 1) / splits;
+    if (rpb < k * 4) rpb = k * 4;
+    splits = (hw + rpb - 1) / rpb;
+    *splits_out = splits;
+    *rpb_out = rpb;
+}
+
 static int gn_block_threads(int C8) {
     int k = 256 / C8;
     if (k < 1) k = 1;
@@ -266,26 +310,33 @@ static int gn_block_threads(int C8) {
 
 using namespace b200;
 
+extern "C" int64_t b200_groupnorm_stats_floats(int32_t batch, int64_t hw, int32_t C, int32_t groups) {
+    if (batch < 1 || hw < 1 || C < 8 || groups < 1) return 0;
+    const int C8 = C / 8, T = gn_block_threads(C8), k = T / C8;
+    long long splits, rpb;
+    gn_geometry(batch, hw, C8, k, &splits, &rpb);
+    const long long bg = static_cast<long long>(batch) * groups;
+    return bg * 2 + 2 * (bg * 2) + 2 * (bg * 2 * splits);
+}
+
 extern "C" int b200_groupnorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* stats,
                                   int32_t batch, int64_t hw, int32_t C, int32_t groups, float eps, int32_t silu,
                                   void* stream) {
     B200_CHECK_ARG(C % 8 == 0 && C % groups == 0 && groups <= 64 && C / 8 <= 1024, "groupnorm: unsupported C=%d groups=%d", C, groups);
+    B200_CHECK_ARG(reinterpret_cast<uintptr_t>(stats) % 8 == 0, "groupnorm: stats must be 8-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // workspace: the double accumulators live right behind the float stats the caller allocated
-    // ([batch, groups, 2] fp32 stats + [batch, groups, 2] fp64 workspace => caller passes 6 floats per (b, g)).
-    double* ws = reinterpret_cast<double*>(stats + static_cast<size_t>(batch) * groups * 2);
-    cudaMemsetAsync(ws, 0, sizeof(double) * batch * groups * 2, st);
     const int C8 = C / 8, T = gn_block_threads(C8), k = T / C8;
-    long long splits = (kNumSMs * 4 + batch - 1) / batch;
-    long long rpb = (hw + splits - 1) / splits;
-    if (rpb < k * 4) rpb = k * 4;
-    splits = (hw + rpb - 1) / rpb;
+    long long splits, rpb;
+    gn_geometry(batch, hw, C8, k, &splits, &rpb);
+    double* sums = reinterpret_cast<double*>(stats + static_cast<size_t>(batch) * groups * 2);
+    double* partials = sums + static_cast<size_t>(batch) * groups * 2;
     dim3 grid(static_cast<unsigned>(splits), batch);
     launch_pdl(gn_reduce_kernel<false, false>, dim3(grid), dim3(T), 0, st, static_cast<const bf16*>(x), nullptr, nullptr, nullptr, nullptr,
-                                                       ws, hw, C, groups, static_cast<int>(rpb));
+                                                       partials, hw, C, groups, static_cast<int>(rpb));
     B200_CHECK_LAUNCH("gn_reduce");
-    launch_pdl(gn_finalize_kernel, dim3((batch * groups + 127) / 128), dim3(128), 0, st, ws, stats, batch * groups,
-                                                                     static_cast<double>(hw) * (C / groups), eps);
+    launch_pdl(gn_finalize_kernel, dim3((batch * groups + 127) / 128), dim3(128), 0, st, static_cast<const double*>(partials), sums, stats,
+               static_cast<int>(batch), static_cast<int>(groups), static_cast<int>(splits),
+               static_cast<double>(hw) * (C / groups), eps, 1);
     B200_CHECK_LAUNCH("gn_finalize");
     const long long total = static_cast<long long>(batch) * hw * C8;
     const int blocks = grid_for(total, 256);
@@ -306,23 +357,25 @@ extern "C" int b200_groupnorm_bwd(const void* dy, const void* x, const void* gam
                                   int32_t groups, int32_t silu, void* stream) {
     B200_CHECK_ARG(C % 8 == 0 && C % groups == 0 && groups <= 64 && C / 8 <= 1024, "groupnorm_bwd: unsupported C=%d groups=%d", C, groups);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    double* ws = reinterpret_cast<double*>(const_cast<float*>(stats) + static_cast<size_t>(batch) * groups * 2);
-    cudaMemsetAsync(ws, 0, sizeof(double) * batch * groups * 2, st);
     const int C8 = C / 8, T = gn_block_threads(C8), k = T / C8;
-    long long splits = (kNumSMs * 4 + batch - 1) / batch;
-    long long rpb = (hw + splits - 1) / splits;
-    if (rpb < k * 4) rpb = k * 4;
-    splits = (hw + rpb - 1) / rpb;
+    long long splits, rpb;
+    gn_geometry(batch, hw, C8, k, &splits, &rpb);
+    double* sums = reinterpret_cast<double*>(const_cast<float*>(stats) + static_cast<size_t>(batch) * groups * 2);
+    double* partials = sums + static_cast<size_t>(batch) * groups * 2;
     dim3 grid(static_cast<unsigned>(splits), batch);
     const bf16 *xp = static_cast<const bf16*>(x), *dyp = static_cast<const bf16*>(dy);
     const bf16 *gp = static_cast<const bf16*>(gamma), *bp = static_cast<const bf16*>(beta);
     if (silu)
-        launch_pdl(gn_reduce_kernel<true, true>, dim3(grid), dim3(T), 0, st, xp, dyp, gp, bp, stats, ws, hw, C, groups, static_cast<int>(rpb));
+        launch_pdl(gn_reduce_kernel<true, true>, dim3(grid), dim3(T), 0, st, xp, dyp, gp, bp, stats, partials, hw, C, groups, static_cast<int>(rpb));
     else
-        launch_pdl(gn_reduce_kernel<true, false>, dim3(grid), dim3(T), 0, st, xp, dyp, gp, bp, stats, ws, hw, C, groups, static_cast<int>(rpb));
+        launch_pdl(gn_reduce_kernel<true, false>, dim3(grid), dim3(T), 0, st, xp, dyp, gp, bp, stats, partials, hw, C, groups, static_cast<int>(rpb));
     B200_CHECK_LAUNCH("gn_bwd_reduce");
+    launch_pdl(gn_finalize_kernel, dim3((batch * groups + 127) / 128), dim3(128), 0, st, static_cast<const double*>(partials), sums,
+               const_cast<float*>(stats), static_cast<int>(batch), static_cast<int>(groups), static_cast<int>(splits), 1.0, 0.f, 0);
+    B200_CHECK_LAUNCH("gn_bwd_sum");
     const long long total = static_cast<long long>(batch) * hw * C8;
     const int blocks = grid_for(total, 256);
+    const double* ws = sums;
     if (silu)
         launch_pdl(gn_bwd_apply_kernel<true>, dim3(blocks), dim3(256), 0, st, dyp, xp, gp, bp, stats, ws, static_cast<const bf16*>(dres), static_cast<bf16*>(dx), hw, C, groups, total);
     else

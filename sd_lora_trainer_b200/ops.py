@@ -238,7 +238,7 @@ def flash_attn_bwd(q, k, v, o, d_o, lse, B: int, H: int, L: int, Lk: int, scale:
     delta = torch.empty(B * H * L, dtype=torch.float32, device=dev)
     single = Lk <= 128                                # one key block: dQ is written directly, no fp32 accumulator needed
     dq_acc = None if single else torch.empty(B * L * C_, dtype=torch.float32, device=dev)
-    ws_floats = 2 * B * Lk * ld_d + B * H if (single and L > 128) else 0
+    ws_floats = 2 * B * Lk * ld_d + B * H * ((Lk + 127) // 128) if L > 128 else 0     # query-split workspace (kept zero)
     ws = _flash_split_ws(dev, ws_floats) if ws_floats else None
     check(_lib.load().b200_flash_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr(),
                                           lse.data_ptr(), delta.data_ptr(), _p(dq_acc), dq.data_ptr(),
@@ -263,7 +263,7 @@ def softmax_bwd(P: torch.Tensor, dP: torch.Tensor, dS: torch.Tensor, rows: int, 
 def groupnorm_fwd(x: torch.Tensor, gamma, beta, batch: int, hw: int, C_: int, groups: int, eps: float, silu: bool):
     """x: [batch*hw, C] NHWC.  Returns (y, stats) where stats also carries the fp64 scratch area."""
     y = torch.empty_like(x)
-    stats = torch.empty(batch * groups * 6, dtype=torch.float32, device=x.device)
+    stats = torch.empty(int(_lib.load().b200_groupnorm_stats_floats(batch, hw, C_, groups)), dtype=torch.float32, device=x.device)
     check(_lib.load().b200_groupnorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
                                          stats.data_ptr(), batch, hw, C_, groups, eps, int(silu), _stream()), "groupnorm_fwd")
     return y, stats
