@@ -66,7 +66,7 @@ __global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restr
     // ---- deterministic combine (no atomics): a thread's 8 channels touch its first group g0 and, when the group width is
     //      not a multiple of 8, g0 + 1; partials go to shared memory and one thread per (group, statistic) sums its
     //      contributors in a fixed order; the block's sums land in ITS slot of the partial buffer ----
-    {
+    if (cpg >= 8) {
         const int g0 = (v * 8) / cpg;
         float lo0 = 0.f, lo1 = 0.f, hi0 = 0.f, hi1 = 0.f;
 #pragma unroll
@@ -80,20 +80,37 @@ __global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restr
             }
         }
         part[threadIdx.x] = make_float4(lo0, lo1, hi0, hi1);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) {
-        const int g = i >> 1, stat = i & 1;
-        const int v_lo = (g * cpg) >> 3, v_hi = ((g + 1) * cpg - 1) >> 3;
-        float acc = 0.f;
-        for (int vv = v_lo; vv <= v_hi; ++vv) {
-            const bool is_lo = (vv * 8) / cpg == g;            // else this vector's upper channels belong to g
-            for (int rl = 0; rl < k; ++rl) {
-                const float4 pv = part[rl * C8 + vv];
-                acc += is_lo ? (stat ? pv.y : pv.x) : (stat ? pv.w : pv.z);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) {
+            const int g = i >> 1, stat = i & 1;
+            const int v_lo = (g * cpg) >> 3, v_hi = ((g + 1) * cpg - 1) >> 3;
+            float acc = 0.f;
+            for (int vv = v_lo; vv <= v_hi; ++vv) {
+                const bool is_lo = (vv * 8) / cpg == g;            // else this vector's upper channels belong to g
+                for (int rl = 0; rl < k; ++rl) {
+                    const float4 pv = part[rl * C8 + vv];
+                    acc += is_lo ? (stat ? pv.y : pv.x) : (stat ? pv.w : pv.z);
+                }
             }
+            ws[(static_cast<long long>(b) * gridDim.x + blockIdx.x) * groups * 2 + i] = static_cast<double>(acc);
         }
-        ws[(static_cast<long long>(b) * gridDim.x + blockIdx.x) * groups * 2 + i] = static_cast<double>(acc);
+    } else {
+        // narrow groups (fewer than 8 channels: only the scaled-down test nets): a vector spans several groups, so every
+        // thread publishes all 16 channel sums (<= 256 threads here: 16 KiB) and the combine walks channels
+        float* vals = reinterpret_cast<float*>(part);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            vals[threadIdx.x * 16 + i] = a0[i];
+            vals[threadIdx.x * 16 + 8 + i] = a1[i];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) {
+            const int g = i >> 1, stat = i & 1;
+            float acc = 0.f;
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+                for (int rl = 0; rl < k; ++rl) acc += vals[(rl * C8 + (c >> 3)) * 16 + stat * 8 + (c & 7)];
+            ws[(static_cast<long long>(b) * gridDim.x + blockIdx.x) * groups * 2 + i] = static_cast<double>(acc);
+        }
     }
 }
 
@@ -103,15 +120,22 @@ __global__ void gn_finalize_kernel(const double* __restrict__ partials, double* 
                                    int batch, int groups, int splits, double count, float eps, int write_stats) {
     pdl_launch();
     pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (b, g)
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // one warp per (b, g)
+    const int lane = threadIdx.x & 31;
     if (i >= batch * groups) return;
     const int b = i / groups, g = i - b * groups;
     double s0 = 0.0, s1 = 0.0;
-    for (int sp = 0; sp < splits; ++sp) {
+    for (int sp = lane; sp < splits; sp += 32) {                     // lane-strided, then a fixed shuffle tree: deterministic
         const double* pp = partials + ((static_cast<long long>(b) * splits + sp) * groups + g) * 2;
         s0 += pp[0];
         s1 += pp[1];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (lane != 0) return;
     sums[2 * i] = s0;
     sums[2 * i + 1] = s1;
     if (write_stats) {
@@ -334,7 +358,7 @@ extern "C" int b200_groupnorm_fwd(const void* x, const void* gamma, const void* 
     launch_pdl(gn_reduce_kernel<false, false>, dim3(grid), dim3(T), 0, st, static_cast<const bf16*>(x), nullptr, nullptr, nullptr, nullptr,
                                                        partials, hw, C, groups, static_cast<int>(rpb));
     B200_CHECK_LAUNCH("gn_reduce");
-    launch_pdl(gn_finalize_kernel, dim3((batch * groups + 127) / 128), dim3(128), 0, st, static_cast<const double*>(partials), sums, stats,
+    launch_pdl(gn_finalize_kernel, dim3((batch * groups + 7) / 8), dim3(256), 0, st, static_cast<const double*>(partials), sums, stats,
                static_cast<int>(batch), static_cast<int>(groups), static_cast<int>(splits),
                static_cast<double>(hw) * (C / groups), eps, 1);
     B200_CHECK_LAUNCH("gn_finalize");
@@ -370,7 +394,7 @@ extern "C" int b200_groupnorm_bwd(const void* dy, const void* x, const void* gam
     else
         launch_pdl(gn_reduce_kernel<true, false>, dim3(grid), dim3(T), 0, st, xp, dyp, gp, bp, stats, partials, hw, C, groups, static_cast<int>(rpb));
     B200_CHECK_LAUNCH("gn_bwd_reduce");
-    launch_pdl(gn_finalize_kernel, dim3((batch * groups + 127) / 128), dim3(128), 0, st, static_cast<const double*>(partials), sums,
+    launch_pdl(gn_finalize_kernel, dim3((batch * groups + 7) / 8), dim3(256), 0, st, static_cast<const double*>(partials), sums,
                const_cast<float*>(stats), static_cast<int>(batch), static_cast<int>(groups), static_cast<int>(splits), 1.0, 0.f, 0);
     B200_CHECK_LAUNCH("gn_bwd_sum");
     const long long total = static_cast<long long>(batch) * hw * C8;
