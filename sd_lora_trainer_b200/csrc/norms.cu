@@ -242,6 +242,17 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restr
         }
         float mean, rstd;
         if (!kBackward) {
+            // affine parameters are fetched BEFORE the two reductions: their L2 round trip overlaps the shuffles instead of
+            // following them (the kernel is latency-bound: one row per warp, ~14 warps per SM)
+            bf16x8 gr[NV], br[NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int v = lane + j * 32;
+                if (v < C8) {
+                    gr[j] = *reinterpret_cast<const bf16x8*>(gamma + v * 8);
+                    br[j] = *reinterpret_cast<const bf16x8*>(beta + v * 8);
+                }
+            }
             mean = warp_sum(s) / C;
             float q = 0.f;
 #pragma unroll
@@ -263,11 +274,12 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restr
             for (int j = 0; j < NV; ++j) {
                 const int v = lane + j * 32;
                 if (v < C8) {
-                    float gm[8], bt[8], o[8];
-                    load8(gamma + v * 8, gm);
-                    load8(beta + v * 8, bt);
+                    float o[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = (f[j][i] - mean) * rstd * gm[i] + bt[i];
+                    for (int i = 0; i < 4; ++i) {
+                        o[2 * i] = (f[j][2 * i] - mean) * rstd * __bfloat162float(gr[j].h[i].x) + __bfloat162float(br[j].h[i].x);
+                        o[2 * i + 1] = (f[j][2 * i + 1] - mean) * rstd * __bfloat162float(gr[j].h[i].y) + __bfloat162float(br[j].h[i].y);
+                    }
                     store8(out + row * C + v * 8, o);
                 }
             }
@@ -276,6 +288,14 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restr
             rstd = stats[row * 2 + 1];
             float t[NV][8];
             float s1 = 0.f, s2 = 0.f;
+            bf16x8 rres[NV];                                  // residual-branch gradient, fetched ahead of the reductions
+            if (beta) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const int v = lane + j * 32;
+                    if (v < C8) rres[j] = *reinterpret_cast<const bf16x8*>(beta + row * C + v * 8);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 const int v = lane + j * 32;
@@ -302,10 +322,11 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, const bf16* __restr
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] = rstd * (t[j][i] - s1 - f[j][i] * s2);
                     if (beta) {   // backward: `beta` carries the residual-branch gradient to add
-                        float rr[8];
-                        load8(beta + row * C + v * 8, rr);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = bfr(o[i]) + rr[i];
+                        for (int i = 0; i < 4; ++i) {
+                            o[2 * i] = bfr(o[2 * i]) + __bfloat162float(rres[j].h[i].x);
+                            o[2 * i + 1] = bfr(o[2 * i + 1]) + __bfloat162float(rres[j].h[i].y);
+                        }
                     }
                     store8(out + row * C + v * 8, o);
                 }

@@ -25,10 +25,9 @@ def test_rank64_step_matches_oracle():
     tr.store.grads.zero_()
     out_2 = tr.step(inputs, completion_f=0.0, do_optimizer=False)            # captions come from the conditioning cache
     torch.cuda.synchronize()
-    # Two runs agree to bf16 noise, not bit for bit: the GroupNorm statistics are combined with fp32 shared-memory atomics
-    # (arrival order), stream-K adds its partial tiles with bf16 TMA reduce-adds, split-K / batched weight gradients use
-    # fp32 atomics.  scripts/determinism_trace.py pins the first differing op of two identical passes to groupnorm_fwd;
-    # profiles/r02b_determinism_trace.txt: loss spread 3e-4 (stream-K off) .. 1e-3 on these tiny random-weight nets.
+    # Two runs agree to summation-order noise, not bit for bit: stream-K adds its partial tiles with bf16 TMA reduce-adds and
+    # the weight-gradient kernels use fp32 atomics (the forward itself is bit-reproducible with stream-K off since the
+    # GroupNorm statistics lost their atomics - scripts/determinism_trace.py, profiles/r02i_determinism_trace.txt).
     assert len(tr._text_cache) == 2 and abs(float(out_2["tot_loss"]) - a) <= 3e-3 * abs(a) and rel(tr.store.grads, g1) < 5e-2
 
 
