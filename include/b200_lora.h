@@ -101,6 +101,12 @@ typedef struct {
        D[m, j] = dy * gelu(gate) and D[m, N + j] = dy * value * gelu'(gate) - D is [M, 2N] - and dy is never stored. */
     const void* geglu_h;
     int64_t geglu_h_ld;
+    /* GEGLU forward fused into the epilogue (CTA-pair kernel, bf16 output, N % 256 == 0, no residual / side path): the B
+       operand is FeedForward.net.0.proj's weight with its rows interleaved in blocks of 128 (128 value rows, the matching
+       128 gate rows, ...; bias likewise), D [M, N] receives the projection in that interleaved column layout (kept for the
+       backward) and geglu_y [M, N/2] (row stride geglu_y_ld) = value * gelu(gate), diffusers' GEGLU.forward. */
+    void* geglu_y;
+    int64_t geglu_y_ld;
 } b200_gemm_t;
 
 int b200_gemm(const b200_gemm_t* desc, void* stream);
@@ -205,8 +211,10 @@ int b200_layernorm_fwd(const void* x, const void* gamma, const void* beta, void*
 int b200_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* stats, const void* dres, void* dx,
                        int64_t rows, int32_t C, void* stream);
 /* h: [rows, 2*inner] = (value | gate); y = value * gelu(gate) (exact erf gelu, rounded like torch's op-by-op bf16) */
-int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, void* stream);
-int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, void* stream);
+/* interleave = 0: h = [value (inner) | gate (inner)] as diffusers' GEGLU chunks it; interleave = il > 0: blocks of il value
+   columns alternate with blocks of il gate columns (the layout the FF up-projection writes with its fused GEGLU epilogue) */
+int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, int32_t interleave, void* stream);
+int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, int32_t interleave, void* stream);
 int b200_silu_fwd(const void* x, void* y, int64_t n, void* stream);
 int b200_silu_bwd(const void* dy, const void* x, void* dx, int64_t n, void* stream);
 /* CLIP text-encoder MLP activation ([3P] transformers CLIPMLP.activation_fn on the get_conditioning_signals path,

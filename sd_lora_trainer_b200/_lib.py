@@ -28,7 +28,7 @@ class GemmDesc(C.Structure):
                 ("side", c_int32), ("side_r", c_int32), ("S", Operand), ("B2", Operand), ("side_alpha", c_float),
                 ("T_out", c_void_p), ("t_ld", c_int64),
                 ("group", c_int32), ("D2", c_void_p), ("d2_sm", c_int64), ("d2_sn", c_int64), ("b_static", c_int32),
-                ("geglu_h", c_void_p), ("geglu_h_ld", c_int64)]
+                ("geglu_h", c_void_p), ("geglu_h_ld", c_int64), ("geglu_y", c_void_p), ("geglu_y_ld", c_int64)]
 
 
 class WgradProblem(C.Structure):
@@ -61,8 +61,8 @@ SIGNATURES = {
                            c_int32, c_int32, c_int32, c_void_p],
     "b200_layernorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p],
     "b200_layernorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
-    "b200_geglu_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_void_p],
-    "b200_geglu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p],
+    "b200_geglu_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p],
+    "b200_geglu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p],
     "b200_silu_fwd": [c_void_p, c_void_p, c_int64, c_void_p],
     "b200_silu_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_void_p],
     "b200_norm_param_grad": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,

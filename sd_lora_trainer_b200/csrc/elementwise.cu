@@ -135,18 +135,26 @@ __global__ void softmax_bwd_kernel(const bf16* __restrict__ P, const float* __re
 // ------------------------------------------------------------------------------------------------
 // GEGLU / SiLU / add
 // ------------------------------------------------------------------------------------------------
-__global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ y, long long rows, int inner) {
+// h = [value | gate] ([rows, 2*inner]).  il == 0: value in columns [0, inner), gate in [inner, 2*inner) (diffusers' chunk(2)).
+// il > 0 (a multiple of 8 dividing inner; 128 in the step): blocks of il value columns alternate with blocks of il gate
+// columns - the layout the FF up-projection writes when GEGLU is fused into its epilogue (one 256-wide tile = 128 value +
+// the matching 128 gate columns): value column j sits at (j / il) * 2 il + j % il, its gate il further.
+__device__ __forceinline__ long long geglu_value_col(int j, int il) { return il ? static_cast<long long>(j / il) * 2 * il + j % il : j; }
+
+__global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ y, long long rows, int inner, int il) {
     pdl_launch();
     pdl_wait();
     const int I8 = inner >> 3;
     const long long total = rows * I8;
+    const int goff = il ? il : inner;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = idx / I8;
         const int v = static_cast<int>(idx % I8);
+        const long long vc = geglu_value_col(v * 8, il);
         float a[8], g[8], o[8];
-        load8(h + r * 2 * inner + v * 8, a);
-        load8(h + r * 2 * inner + inner + v * 8, g);
+        load8(h + r * 2 * inner + vc, a);
+        load8(h + r * 2 * inner + vc + goff, g);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = a[i] * bfr(gelu_f(g[i]));
         store8(y + r * inner + v * 8, o);
@@ -154,18 +162,20 @@ __global__ void geglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ 
 }
 
 __global__ void geglu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ h, bf16* __restrict__ dh,
-                                 long long rows, int inner) {
+                                 long long rows, int inner, int il) {
     pdl_launch();
     pdl_wait();
     const int I8 = inner >> 3;
     const long long total = rows * I8;
+    const int goff = il ? il : inner;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = idx / I8;
         const int v = static_cast<int>(idx % I8);
+        const long long vc = geglu_value_col(v * 8, il);
         float a[8], g[8], d[8], da[8], dg[8];
-        load8(h + r * 2 * inner + v * 8, a);
-        load8(h + r * 2 * inner + inner + v * 8, g);
+        load8(h + r * 2 * inner + vc, a);
+        load8(h + r * 2 * inner + vc + goff, g);
         load8(dy + r * inner + v * 8, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -174,8 +184,8 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __rest
             da[i] = d[i] * bfr(gl);
             dg[i] = bfr(d[i] * a[i]) * dgl;
         }
-        store8(dh + r * 2 * inner + v * 8, da);
-        store8(dh + r * 2 * inner + inner + v * 8, dg);
+        store8(dh + r * 2 * inner + vc, da);
+        store8(dh + r * 2 * inner + vc + goff, dg);
     }
 }
 
@@ -668,17 +678,20 @@ extern "C" int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_
     return 0;
 }
 
-extern "C" int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, void* stream) {
-    B200_CHECK_ARG(inner % 8 == 0, "geglu: inner %% 8 != 0");
+extern "C" int b200_geglu_fwd(const void* h, void* y, int64_t rows, int32_t inner, int32_t interleave, void* stream) {
+    B200_CHECK_ARG(inner % 8 == 0 && interleave >= 0 && interleave % 8 == 0 && (interleave == 0 || inner % interleave == 0),
+                   "geglu: inner %% 8 != 0 or a bad interleave");
     launch_pdl(geglu_fwd_kernel, dim3(grid_for(rows * (inner / 8), 256)), dim3(256), 0, ST, static_cast<const bf16*>(h),
-                                                                         static_cast<bf16*>(y), rows, inner);
+               static_cast<bf16*>(y), static_cast<long long>(rows), static_cast<int>(inner), static_cast<int>(interleave));
     B200_CHECK_LAUNCH("geglu_fwd");
     return 0;
 }
-extern "C" int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, void* stream) {
-    B200_CHECK_ARG(inner % 8 == 0, "geglu: inner %% 8 != 0");
-    launch_pdl(geglu_bwd_kernel, dim3(grid_for(rows * (inner / 8), 256)), dim3(256), 0, ST, 
-        static_cast<const bf16*>(dy), static_cast<const bf16*>(h), static_cast<bf16*>(dh), rows, inner);
+extern "C" int b200_geglu_bwd(const void* dy, const void* h, void* dh, int64_t rows, int32_t inner, int32_t interleave, void* stream) {
+    B200_CHECK_ARG(inner % 8 == 0 && interleave >= 0 && interleave % 8 == 0 && (interleave == 0 || inner % interleave == 0),
+                   "geglu: inner %% 8 != 0 or a bad interleave");
+    launch_pdl(geglu_bwd_kernel, dim3(grid_for(rows * (inner / 8), 256)), dim3(256), 0, ST, static_cast<const bf16*>(dy),
+               static_cast<const bf16*>(h), static_cast<bf16*>(dh), static_cast<long long>(rows), static_cast<int>(inner),
+               static_cast<int>(interleave));
     B200_CHECK_LAUNCH("geglu_bwd");
     return 0;
 }

@@ -44,6 +44,10 @@ struct Gemm2Args {
     // GEGLU backward fused into the epilogue (the input-gradient GEMM of FeedForward.net.2, diffusers GEGLU): the tile is
     // dy[m, j] (j < N); with h = [value | gate] ([M, 2N], row stride h_ld) the epilogue writes dh[m, j] = dy * gelu(gate) and
     // dh[m, N + j] = dy * value * gelu'(gate) into D ([M, 2N]) instead of dy itself
+    // GEGLU forward fused into the epilogue (FeedForward.net.0.proj with its rows interleaved in blocks of 128: every 256-wide
+    // tile holds 128 value columns and the matching 128 gate columns): D <- the projection (kept for the backward),
+    // mapD2 ([M, N/2]) <- value * gelu(gate).  BN = 256 only.
+    int geglu_fwd;
     int geglu_bwd;
     long long h_ld;
     const __nv_bfloat16* H;
@@ -72,7 +76,7 @@ struct Gemm2Args {
     const __nv_bfloat16* R;
     __nv_bfloat16* T_out;
     long long* dbg;           // developer probe: per-CTA globaltimer stamps [cta][16] (nullptr in production)
-    CUtensorMap mapA, mapB, mapS, mapB2, mapA2, mapD;
+    CUtensorMap mapA, mapB, mapS, mapB2, mapA2, mapD, mapD2;
 };
 
 // The (tile, k-block range) work items of one CTA pair; producer, MMA and epilogue warps walk the same sequence.
@@ -299,6 +303,76 @@ __device__ __forceinline__ void epi2_chunk_tma_f32(const Epi2& e, const CUtensor
             tma_store_4d(mapD, box, n_chunk, m_warp, 0, 0);
             if (n_chunk + 16 < e.N) tma_store_4d(mapD, box + 2048, n_chunk + 16, m_warp, 0, 0);
         }
+        bulk_commit();
+    }
+    __syncwarp();
+}
+
+// GEGLU forward in the epilogue: the value chunk (columns n_val .. +32 of the tile's first half) and its gate chunk (128
+// columns further) -> both stored to the projection output through the warp's two staging boxes, then
+// y = bf16(value) * bf16(gelu(bf16(gate))) staged into the first box again and stored through mapD2.
+__device__ __forceinline__ void epi2_pair_tma_geglu_fwd(const Epi2& e, const CUtensorMap* mapD, const CUtensorMap* mapY,
+                                                        const uint32_t (&rv)[32], const uint32_t (&rg)[32], uint8_t* box, int lane,
+                                                        int m_warp, int n_val, int y_col) {
+    const float alpha = e.alpha;
+    uint8_t* row_a = box + lane * 64;
+    uint8_t* row_g = box + 2048 + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    uint32_t yp[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a[8], gt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a[i] = __uint_as_float(rv[8 * j + i]) * alpha;
+            gt[i] = __uint_as_float(rg[8 * j + i]) * alpha;
+        }
+        if (e.bias != nullptr) {
+            const uint4 wa = __ldg(reinterpret_cast<const uint4*>(e.bias + n_val + 8 * j));
+            const uint4 wg = __ldg(reinterpret_cast<const uint4*>(e.bias + n_val + 128 + 8 * j));
+            const uint32_t ua[4] = {wa.x, wa.y, wa.z, wa.w}, ug[4] = {wg.x, wg.y, wg.z, wg.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[2 * q] += __uint_as_float(ua[q] << 16);
+                a[2 * q + 1] += __uint_as_float(ua[q] & 0xffff0000u);
+                gt[2 * q] += __uint_as_float(ug[q] << 16);
+                gt[2 * q + 1] += __uint_as_float(ug[q] & 0xffff0000u);
+            }
+        }
+        uint4 oa, og;
+        uint32_t* pa = reinterpret_cast<uint32_t*>(&oa);
+        uint32_t* pg = reinterpret_cast<uint32_t*>(&og);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat162 ha = __floats2bfloat162_rn(a[2 * q], a[2 * q + 1]);
+            const __nv_bfloat162 hg = __floats2bfloat162_rn(gt[2 * q], gt[2 * q + 1]);
+            pa[q] = *reinterpret_cast<const uint32_t*>(&ha);
+            pg[q] = *reinterpret_cast<const uint32_t*>(&hg);
+            // y from the ROUNDED projection values, as the stand-alone kernel reads them back
+            const float y0 = __bfloat162float(ha.x) * bfr(gelu_f(__bfloat162float(hg.x)));
+            const float y1 = __bfloat162float(ha.y) * bfr(gelu_f(__bfloat162float(hg.y)));
+            const __nv_bfloat162 hy = __floats2bfloat162_rn(y0, y1);
+            yp[4 * j + q] = *reinterpret_cast<const uint32_t*>(&hy);
+        }
+        *reinterpret_cast<uint4*>(row_a + ((j ^ sw) * 16)) = oa;
+        *reinterpret_cast<uint4*>(row_g + ((j ^ sw) * 16)) = og;
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_4d(mapD, box, n_val, m_warp, 0, 0);
+        tma_store_4d(mapD, box + 2048, n_val + 128, m_warp, 0, 0);
+        bulk_commit();
+        bulk_wait_read<0>();                       // both boxes read: the first is restaged with y
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(row_a + ((j ^ sw) * 16)) = make_uint4(yp[4 * j], yp[4 * j + 1], yp[4 * j + 2], yp[4 * j + 3]);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_4d(mapY, box, y_col, m_warp, 0, 0);
         bulk_commit();
     }
     __syncwarp();
@@ -838,7 +912,21 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                     epi2_chunk<kEpi>(e, raw, stage_buf, lane, m_warp, n0 + c0, min(32, BN - c0));
                 }
             };
-            {
+            if (kEpi == 0 && g.geglu_fwd) {
+                // BN = 256: chunks 0..3 are value columns, 4..7 their gates; this warp pairs (half, half + 4), (half + 2, half + 6)
+                if (m_warp < e.M) {
+#pragma unroll 1
+                    for (int p = half; p < 4; p += 2) {
+                        uint32_t ra[32], rb[32];
+                        tmem_ld32(taddr + p * 32, ra);
+                        tmem_ld32(taddr + 128 + p * 32, rb);
+                        tmem_ld_wait();
+                        if (lane == 0) bulk_wait_read<0>();
+                        __syncwarp();
+                        epi2_pair_tma_geglu_fwd(e, &g.mapD, &g.mapD2, ra, rb, tma_box, lane, m_warp, n0 + p * 32, (n0 >> 1) + p * 32);
+                    }
+                }
+            } else {
                 uint32_t ra[32], rb[32];
                 int c0 = half * 32;
                 if (c0 < BN) tmem_ld32(taddr + c0, ra);

@@ -316,6 +316,16 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
         if (int rc = encode_map_ex(&g.mapD, d->D, 4, dD, sD, boxD, 64)) return rc;
         g.tma_store = 1;
     }
+    if (d->geglu_y != nullptr) {
+        B200_CHECK_ARG(g.tma_store && !d->d_fp32 && !d->side && !d->R && !d->bias_rows && bn == 256 && d->N % 256 == 0 &&
+                           d->num_seg == 1 && d->geglu_h == nullptr && al16(d->geglu_y) && d->geglu_y_ld % 8 == 0 &&
+                           d->geglu_y_ld >= d->N / 2,
+                       "gemm2: fused GEGLU forward needs a plain bf16 TMA-store problem with 256-wide tiles and N %% 256 == 0");
+        const long long dY[4] = {d->N / 2, d->M, 1, 1}, sY[3] = {d->geglu_y_ld, 0, 0};
+        const int boxY[4] = {32, 32, 1, 1};
+        if (int rc = encode_map_ex(&g.mapD2, d->geglu_y, 2, dY, sY, boxY, 64)) return rc;
+        g.geglu_fwd = 1;
+    }
     if (d->geglu_h != nullptr) {
         B200_CHECK_ARG(g.tma_store && !d->d_fp32 && !d->side && !d->R && !d->bias && d->N % 32 == 0 && d->num_seg == 1 &&
                            al16(d->geglu_h) && d->geglu_h_ld % 8 == 0 && d->geglu_h_ld >= 2LL * d->N && d->d_sm >= 2LL * d->N,
@@ -334,7 +344,7 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
     // space into 74 equal ranges so every SM works; partial tiles are added to D by TMA reduce-add, so D is pre-set
     // here to the residual (or zero) and the kernel sees no residual.
     static const int streamk_env = getenv("B200_STREAMK") ? atoi(getenv("B200_STREAMK")) : 1;
-    if (streamk_env && g.tma_store && !d->d_fp32 && !d->side && !g.geglu_bwd && g.kblocks >= 32 && g.total_tiles * 4 <= (kNumSMs / 2) * 3 &&
+    if (streamk_env && g.tma_store && !d->d_fp32 && !d->side && !g.geglu_bwd && !g.geglu_fwd && g.kblocks >= 32 && g.total_tiles * 4 <= (kNumSMs / 2) * 3 &&
         d->N % 32 == 0 && static_cast<long long>(g.total_tiles) * g.kblocks >= kNumSMs / 2) {
         const size_t row_bytes = static_cast<size_t>(d->N) * 2;
         cudaError_t e = cudaSuccess;
@@ -368,6 +378,7 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
     static const int pair_env = getenv("B200_GEMM2") ? atoi(getenv("B200_GEMM2")) : 1;
     if (d->pair_mode >= 0 && (pair_env || d->pair_mode > 0) && pair_eligible(d)) {
         int bn2 = d->block_n;
+        if (d->geglu_y != nullptr) bn2 = 256;              // one tile = 128 value + 128 gate columns
         if (bn2 <= 0) bn2 = pick_pair_bn(d, nullptr);
         const bool bn_ok = bn2 >= 32 && bn2 % 16 == 0 && bn2 <= 256 &&
                            (!(d->B[0].mn_major || (d->side && d->B2.mn_major) || (d->num_seg == 2 && d->B[1].mn_major)) ||
@@ -378,7 +389,8 @@ extern "C" int b200_gemm(const b200_gemm_t* d, void* stream) {
         B200_CHECK_ARG(d->pair_mode <= 0, "gemm: pair_mode forced on a problem the pair kernel does not cover");
     }
 
-    B200_CHECK_ARG(d->geglu_h == nullptr, "gemm: the fused GEGLU backward exists only in the CTA-pair kernel (M >= 256, N >= 64, K >= 64)");
+    B200_CHECK_ARG(d->geglu_h == nullptr && d->geglu_y == nullptr,
+                   "gemm: the fused GEGLU epilogues exist only in the CTA-pair kernel (M >= 256, N >= 64, K >= 64)");
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);

@@ -90,14 +90,16 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
          nb0: int = 1, nb1: int = 1, splits: int = 1, atomic: bool = False, block_n: int = 0,
          side: Optional[Tuple[Mat, Mat, int, float, Optional[torch.Tensor]]] = None, pair_mode: int = 0,
          group_out: Optional[Tuple[torch.Tensor, Tuple[int, int]]] = None, static_b: bool = False,
-         geglu_h: Optional[torch.Tensor] = None) -> torch.Tensor:
+         geglu_h: Optional[torch.Tensor] = None, geglu_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b1][b0][m, n] = alpha * sum_seg A_seg.B_seg^T (+bias) (+residual).  segs: (A | Conv3x3, B, K).
     side = (S, B2, r, side_alpha, T_out): fused low-rank path  out += (side_alpha * A.S^T).B2^T, T_out <- the inner
     product (bf16) - see include/b200_lora.h.
     group_out = (out2, (sm, sn)): the two segments are independent problems; segment 1 accumulates into out2.
     static_b: every B-side operand is a parameter tensor the preceding kernel does not write (weights, LoRA factors).
     geglu_h: h = [value | gate] bf16 [M, 2N]: the product is the GEGLU output's gradient dy and `out` ([M, 2N]) receives the
-    GEGLU backward  [dy * gelu(gate) | dy * value * gelu'(gate)]  straight from the epilogue (CTA-pair kernel only)."""
+    GEGLU backward  [dy * gelu(gate) | dy * value * gelu'(gate)]  straight from the epilogue (CTA-pair kernel only).
+    geglu_out: bf16 [M, N/2]: B is the FF up-projection with rows interleaved in blocks of 128 (value / gate); `out` gets the
+    projection in that column layout and geglu_out = value * gelu(gate) from the same epilogue (CTA-pair kernel only)."""
     _chk_dev(out, bias, residual)
     d = GemmDesc()
     d.M, d.N, d.num_seg = M, N, len(segs)
@@ -122,6 +124,9 @@ def gemm(out: torch.Tensor, M: int, N: int, segs: Sequence[Tuple[object, Mat, in
         out2, (sm2, sn2) = group_out
         assert atomic and len(segs) == 2 and out2.dtype == torch.float32
         d.group, d.D2, d.d2_sm, d.d2_sn = 1, out2.data_ptr(), sm2, sn2
+    if geglu_out is not None:
+        assert geglu_out.dtype == BF16 and geglu_out.shape == (M, N // 2) and geglu_out.stride(1) == 1 and N % 256 == 0
+        d.geglu_y, d.geglu_y_ld = geglu_out.data_ptr(), geglu_out.stride(0)
     if geglu_h is not None:
         assert geglu_h.dtype == BF16 and geglu_h.dim() == 2 and geglu_h.stride(1) == 1 and geglu_h.shape == (M, 2 * N)
         assert out.shape == (M, 2 * N) and out.dtype == BF16
@@ -305,17 +310,19 @@ def norm_param_grad(dy: torch.Tensor, x: torch.Tensor, gamma, beta, stats: torch
                                            int(silu), _stream()), "norm_param_grad")
 
 
-def geglu_fwd(h: torch.Tensor):
+def geglu_fwd(h: torch.Tensor, interleave: int = 0):
+    """h [rows, 2*inner] = [value | gate] (interleave = 0) or alternating blocks of `interleave` value / gate columns."""
     rows, two_inner = h.shape
     y = torch.empty(rows, two_inner // 2, dtype=BF16, device=h.device)
-    check(_lib.load().b200_geglu_fwd(h.data_ptr(), y.data_ptr(), rows, two_inner // 2, _stream()), "geglu_fwd")
+    check(_lib.load().b200_geglu_fwd(h.data_ptr(), y.data_ptr(), rows, two_inner // 2, interleave, _stream()), "geglu_fwd")
     return y
 
 
-def geglu_bwd(dy: torch.Tensor, h: torch.Tensor):
+def geglu_bwd(dy: torch.Tensor, h: torch.Tensor, interleave: int = 0):
     rows, two_inner = h.shape
     dh = torch.empty_like(h)
-    check(_lib.load().b200_geglu_bwd(dy.data_ptr(), h.data_ptr(), dh.data_ptr(), rows, two_inner // 2, _stream()), "geglu_bwd")
+    check(_lib.load().b200_geglu_bwd(dy.data_ptr(), h.data_ptr(), dh.data_ptr(), rows, two_inner // 2, interleave, _stream()),
+          "geglu_bwd")
     return dh
 
 

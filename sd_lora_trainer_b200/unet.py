@@ -415,14 +415,45 @@ class Lin:
         return dx
 
 
-def _lin_bwd_geglu(self, dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
+def _interleave_geglu_rows(lin: "Lin", il: int = 128):
+    """FeedForward.net.0.proj for the fused GEGLU epilogue: rows (and bias) re-ordered so that blocks of `il` value rows
+    alternate with the matching `il` gate rows - every 256-wide output tile then holds both halves of 128 GEGLU outputs.
+    The layer is frozen (LoRA mode), so the permutation is invisible outside: its output h is only ever read by the GEGLU
+    kernels (told the layout) and its input gradient sums over all rows."""
+    inner = lin.N // 2
+    if inner % il:
+        return
+    W = lin.W
+    lin.W = torch.stack([W[:inner].view(inner // il, il, lin.K), W[inner:].view(inner // il, il, lin.K)], dim=1) \
+        .reshape(lin.N, lin.K).contiguous()
+    if lin.b is not None:
+        b = lin.b
+        lin.b = torch.stack([b[:inner].view(inner // il, il), b[inner:].view(inner // il, il)], dim=1).reshape(lin.N).contiguous()
+    lin.geglu_il = il
+
+
+def _lin_fwd_geglu(self, x: torch.Tensor):
+    """(h, y): the FF up-projection h = x.W^T + b and y = GEGLU(h); one launch when the rows are interleaved and the problem
+    fits the CTA-pair kernel (the GEGLU arithmetic rides in the epilogue, under the next tile's mainloop)."""
+    M, il = x.shape[0], getattr(self, "geglu_il", 0)
+    if il and FUSE_GEGLU_FWD and self.lora is None and M >= 256 and self.N % 256 == 0 and self.K >= 64:
+        h = torch.empty(M, self.N, dtype=BF16, device=x.device)
+        y = torch.empty(M, self.N // 2, dtype=BF16, device=x.device)
+        ops.gemm(h, M, self.N, [(kmajor(x), kmajor(self.W), self.K)], bias=self.b, geglu_out=y, static_b=True, pair_mode=1)
+        self.x, self.T = x, None
+        return h, y
+    h = self.fwd(x)
+    return h, ops.geglu_fwd(h, il)
+
+
+def _lin_bwd_geglu(self, dy: torch.Tensor, h: torch.Tensor, il: int = 0) -> torch.Tensor:
     """Input gradient of FeedForward.net.2 with the GEGLU backward fused into the GEMM's epilogue: returns
     dh [M, 2K] = [dY.W * gelu(gate) | dY.W * value * gelu'(gate)] for h = [value | gate]; dY.W itself is never stored.
     (Only with B200_FUSE_GEGLU=1 - see FUSE_GEGLU below; otherwise, and for small problems, the two-kernel form.)"""
     M = dy.shape[0]
-    if not (FUSE_GEGLU and self.lora is None and M >= 256 and self.K >= 64 and self.K % 32 == 0 and self.N >= 64
+    if not (FUSE_GEGLU and il == 0 and self.lora is None and M >= 256 and self.K >= 64 and self.K % 32 == 0 and self.N >= 64
             and h.shape == (M, 2 * self.K) and h.stride(1) == 1):
-        return ops.geglu_bwd(self.bwd(dy), h)
+        return ops.geglu_bwd(self.bwd(dy), h, il)
     x = self.x
     self.x = self.T = None
     dh = torch.empty(M, 2 * self.K, dtype=BF16, device=dy.device)
@@ -442,6 +473,8 @@ def _lin_bwd_geglu(self, dy: torch.Tensor, h: torch.Tensor) -> torch.Tensor:
 # the two-kernel form, 70.0 vs 68.9 ms/step - the epilogue warps now wait on two dependent global loads of h per chunk and
 # run the erf arithmetic, so the epilogue (not the 5.4 us mainloop) bounds each tile.  Off by default; kept for the A/B.
 FUSE_GEGLU = os.environ.get("B200_FUSE_GEGLU", "0") == "1"
+# The forward fusion needs no extra loads (both halves are in the tile's accumulator): on by default in LoRA mode
+FUSE_GEGLU_FWD = os.environ.get("B200_FUSE_GEGLU_FWD", "1") != "0"
 
 
 class LinQKV:
@@ -518,6 +551,7 @@ class LinQKV:
 
 
 Lin.bwd_geglu = _lin_bwd_geglu
+Lin.fwd_geglu = _lin_fwd_geglu
 
 
 class Conv3:
@@ -898,12 +932,12 @@ class TBlock:
     def fwd(self, x, ctx, B, L, Lctx):
         x1 = self.attn1.fwd(self.ln1.fwd(x), None, B, L, L, residual=x)
         x2 = self.attn2.fwd(self.ln2.fwd(x1), ctx, B, L, Lctx, residual=x1)
-        h = self.ff1.fwd(self.ln3.fwd(x2))
+        h, y = self.ff1.fwd_geglu(self.ln3.fwd(x2))
         self.h = h
-        return self.ff2.fwd(ops.geglu_fwd(h), residual=x2)
+        return self.ff2.fwd(y, residual=x2)
 
     def bwd(self, dx3, d_ctx, dscores):
-        dh = self.ff2.bwd_geglu(dx3, self.h)         # GEGLU backward in the epilogue of ff2's input-gradient GEMM
+        dh = self.ff2.bwd_geglu(dx3, self.h, getattr(self.ff1, "geglu_il", 0))
         self.h = None
         dx2 = self.ln3.bwd(self.ff1.bwd(dh), dres=dx3)
         dx1 = self.ln2.bwd(self.attn2.bwd(dx2, d_ctx, dscores), dres=dx2)
@@ -1134,12 +1168,15 @@ class UNetB200:
         blocks = []
         for j in range(depth):
             b = f"{p}.transformer_blocks.{j}"
+            ff1 = self._lin(f"{b}.ff.net.0.proj")
+            if self.dense is None and FUSE_GEGLU_FWD:
+                _interleave_geglu_rows(ff1)
             blocks.append(TBlock(self._ln(f"{b}.norm1"),
                                  self._attn(f"{b}.attn1", heads, False, False),
                                  self._ln(f"{b}.norm2"),
                                  self._attn(f"{b}.attn2", heads, True, hook),
                                  self._ln(f"{b}.norm3"),
-                                 self._lin(f"{b}.ff.net.0.proj"), self._lin(f"{b}.ff.net.2")))
+                                 ff1, self._lin(f"{b}.ff.net.2")))
         return Transformer2D(norm, self._lin(f"{p}.proj_in"), blocks, self._lin(f"{p}.proj_out"))
 
     def set_capture(self, on: bool):

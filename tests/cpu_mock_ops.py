@@ -91,8 +91,17 @@ def _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out, pair_m
 
 def gemm(out, M, N, segs, *, d_strides=None, alpha=1.0, bias=None, bias_rows=0, bias_sb=0, residual=None,
          r_strides=None, nb0=1, nb1=1, splits=1, atomic=False, block_n=0, side=None, pair_mode=0, group_out=None, static_b=False,
-         geglu_h=None):
+         geglu_h=None, geglu_out=None):
     _chk_gemm(out, M, N, segs, nb0, nb1, splits, atomic, side, group_out, pair_mode)
+    if geglu_out is not None:
+        # fused GEGLU forward (CTA-pair kernel, 256-wide tiles): out [M, N] is the projection in the 128-interleaved layout,
+        # geglu_out [M, N/2] <- value * gelu(gate)
+        assert M >= 256 and N % 256 == 0 and segs[0][2] >= 64 and len(segs) == 1 and side is None and residual is None
+        assert not atomic and nb0 == 1 and nb1 == 1 and out.dtype == BF16 and geglu_out.dtype == BF16 and geglu_out.shape == (M, N // 2)
+        assert pair_mode > 0 and block_n in (0, 256) and geglu_out.stride(1) == 1 and geglu_out.stride(0) % 8 == 0
+        gemm(out, M, N, segs, alpha=alpha, bias=bias)
+        geglu_out.copy_(geglu_fwd(out, 128))
+        return out
     if geglu_h is not None:
         # fused GEGLU backward (CTA-pair kernel only): the product is dy [M, N]; out [M, 2N] <- geglu_bwd(bf16(dy), h)
         assert M >= 256 and N >= 64 and N % 32 == 0 and segs[0][2] >= 64 and len(segs) == 1 and side is None and bias is None
@@ -291,18 +300,36 @@ def norm_param_grad(dy, x, gamma, beta, stats, dgamma, dbeta, hw=0, groups=0, si
     dbeta += b.grad
 
 
-def geglu_fwd(h):
+def _geglu_split(h, interleave):
+    """(value, gate) halves of h for the plain ([value | gate]) or interleaved (blocks of `interleave` columns) layout."""
+    if not interleave:
+        return h.chunk(2, -1)
+    rows, two_inner = h.shape
+    assert interleave % 8 == 0 and (two_inner // 2) % interleave == 0
+    hb = h.reshape(rows, two_inner // (2 * interleave), 2, interleave)
+    return hb[:, :, 0].reshape(rows, -1), hb[:, :, 1].reshape(rows, -1)
+
+
+def _geglu_join(a, g, interleave):
+    if not interleave:
+        return torch.cat([a, g], -1)
+    rows, inner = a.shape
+    return torch.stack([a.reshape(rows, inner // interleave, interleave), g.reshape(rows, inner // interleave, interleave)],
+                       dim=2).reshape(rows, 2 * inner)
+
+
+def geglu_fwd(h, interleave=0):
     assert (h.shape[1] // 2) % 8 == 0
     _chk_vec(h)
-    a, g = h.float().chunk(2, -1)
+    a, g = _geglu_split(h.float(), interleave)
     return _bf(a * _bf(F.gelu(g)).float())
 
 
-def geglu_bwd(dy, h):
-    hr = h.float().detach().requires_grad_(True)
-    a, g = hr.chunk(2, -1)
+def geglu_bwd(dy, h, interleave=0):
+    a, g = _geglu_split(h.float(), interleave)
+    a, g = a.detach().requires_grad_(True), g.detach().requires_grad_(True)
     (a * F.gelu(g)).backward(dy.float())
-    return _bf(hr.grad)
+    return _bf(_geglu_join(a.grad, g.grad, interleave))
 
 
 def silu_fwd(x):

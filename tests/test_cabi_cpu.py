@@ -35,7 +35,7 @@ def test_errors_are_status_codes():
     d.M, d.N, d.num_seg = 0, 8, 1
     assert lib.b200_gemm(ctypes.byref(d), None) != 0
     assert b"empty problem" in lib.b200_last_error()
-    assert lib.b200_geglu_fwd(None, None, 4, 7, None) != 0          # inner % 8 != 0
+    assert lib.b200_geglu_fwd(None, None, 4, 7, 0, None) != 0       # inner % 8 != 0
     assert lib.b200_act_fwd(None, None, 8, 0, None) != 0 and b"act_fwd" in lib.b200_last_error()          # null buffers
     assert lib.b200_act_bwd(1, 1, 1, 8, 2, None) != 0 and b"kind 2" in lib.b200_last_error()              # unknown activation
     assert lib.b200_norm_param_grad(1, 1, None, None, 1, 1, 1, 8, 4, 12, 0, 0, None) != 0                 # C % 8 != 0

@@ -190,6 +190,43 @@ def test_pair_fused_geglu_backward_epilogue(M, N, K):
     _close(dh[:, N:], d32 * val * (cdf + gate * pdf), tol=2e-2, what="gate half")
 
 
+def _interleave(t, il=128):
+    """[value | gate] along dim 0 (rows of a weight / entries of a bias) -> blocks of il value rows alternating with il gate rows."""
+    inner = t.shape[0] // 2
+    rest = t.shape[1:]
+    return torch.stack([t[:inner].reshape(inner // il, il, *rest), t[inner:].reshape(inner // il, il, *rest)], dim=1).reshape(t.shape).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(2048, 10240, 1280, True), (8192, 5120, 640, True), (512, 512, 128, False), (300, 256, 200, True)])
+def test_pair_fused_geglu_forward_epilogue(M, N, K, bias):
+    """FeedForward.net.0.proj with rows interleaved in blocks of 128 + GEGLU in the epilogue: h (interleaved layout) equals the
+    plain projection re-ordered, y equals diffusers' GEGLU  value * gelu(gate)  of the rounded projection."""
+    from sd_lora_trainer_b200 import ops
+    x, w = _rand(M, K, scale=0.5), _rand(N, K, seed=1, scale=0.05)
+    b = _rand(N, seed=2) if bias else None
+    wi, bi = _interleave(w), (_interleave(b) if bias else None)
+    h = torch.full((M, N), 7.0, dtype=BF, device="cuda")
+    y = torch.full((M, N // 2), 7.0, dtype=BF, device="cuda")
+    ops.gemm(h, M, N, [(ops.kmajor(x), ops.kmajor(wi), K)], bias=bi, geglu_out=y, pair_mode=1, static_b=True)
+    plain = torch.empty(M, N, dtype=BF, device="cuda")
+    ops.gemm(plain, M, N, [(ops.kmajor(x), ops.kmajor(w), K)], bias=b, pair_mode=1)
+    torch.cuda.synchronize()
+    inner = N // 2
+    hv = h.view(M, inner // 128, 2, 128)
+    _close(hv[:, :, 0].reshape(M, inner), plain[:, :inner], tol=1e-2, what="value half of h")
+    _close(hv[:, :, 1].reshape(M, inner), plain[:, inner:], tol=1e-2, what="gate half of h")
+    ref = hv[:, :, 0].reshape(M, inner).float() * torch.nn.functional.gelu(hv[:, :, 1].reshape(M, inner).float()).to(BF).float()
+    _close(y, ref, tol=1e-2, what="fused GEGLU output")
+    # the stand-alone kernels read the interleaved layout too
+    _close(ops.geglu_fwd(h, 128), y, tol=1e-2, what="stand-alone geglu_fwd on the interleaved h")
+    dy = _rand(M, inner, seed=5)
+    dh_i = ops.geglu_bwd(dy, h, 128)
+    h_plain = torch.cat([hv[:, :, 0].reshape(M, inner), hv[:, :, 1].reshape(M, inner)], dim=1).contiguous()
+    dh_p = ops.geglu_bwd(dy, h_plain, 0)
+    dv = dh_i.view(M, inner // 128, 2, 128)
+    assert torch.equal(dv[:, :, 0].reshape(M, inner), dh_p[:, :inner]) and torch.equal(dv[:, :, 1].reshape(M, inner), dh_p[:, inner:])
+
+
 def test_pair_back_to_back_launches_are_ordered():
     """Programmatic dependent launch + clusters: a chain of dependent GEMMs (each reads the previous output)."""
     from sd_lora_trainer_b200 import ops
