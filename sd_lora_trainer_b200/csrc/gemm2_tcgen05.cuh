@@ -312,13 +312,13 @@ __device__ __forceinline__ void epi2_chunk_tma_f32(const Epi2& e, const CUtensor
 // columns further) -> both stored to the projection output through the warp's two staging boxes, then
 // y = bf16(value) * bf16(gelu(bf16(gate))) staged into the first box again and stored through mapD2.
 __device__ __forceinline__ void epi2_pair_tma_geglu_fwd(const Epi2& e, const CUtensorMap* mapD, const CUtensorMap* mapY,
-                                                        const uint32_t (&rv)[32], const uint32_t (&rg)[32], uint8_t* box, int lane,
-                                                        int m_warp, int n_val, int y_col) {
+                                                        const uint32_t (&rv)[32], const uint32_t (&rg)[32], uint8_t* box,
+                                                        uint8_t* ybox, int lane, int m_warp, int n_val, int y_col) {
     const float alpha = e.alpha;
     uint8_t* row_a = box + lane * 64;
     uint8_t* row_g = box + 2048 + lane * 64;
+    uint8_t* row_y = ybox + lane * 64;             // third staging box (the idle T tile of the side path): no mid-chunk wait
     const int sw = (lane >> 1) & 3;
-    uint32_t yp[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float a[8], gt[8];
@@ -339,9 +339,10 @@ __device__ __forceinline__ void epi2_pair_tma_geglu_fwd(const Epi2& e, const CUt
                 gt[2 * q + 1] += __uint_as_float(ug[q] & 0xffff0000u);
             }
         }
-        uint4 oa, og;
+        uint4 oa, og, oy;
         uint32_t* pa = reinterpret_cast<uint32_t*>(&oa);
         uint32_t* pg = reinterpret_cast<uint32_t*>(&og);
+        uint32_t* py = reinterpret_cast<uint32_t*>(&oy);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const __nv_bfloat162 ha = __floats2bfloat162_rn(a[2 * q], a[2 * q + 1]);
@@ -352,27 +353,18 @@ __device__ __forceinline__ void epi2_pair_tma_geglu_fwd(const Epi2& e, const CUt
             const float y0 = __bfloat162float(ha.x) * bfr(gelu_f(__bfloat162float(hg.x)));
             const float y1 = __bfloat162float(ha.y) * bfr(gelu_f(__bfloat162float(hg.y)));
             const __nv_bfloat162 hy = __floats2bfloat162_rn(y0, y1);
-            yp[4 * j + q] = *reinterpret_cast<const uint32_t*>(&hy);
+            py[q] = *reinterpret_cast<const uint32_t*>(&hy);
         }
         *reinterpret_cast<uint4*>(row_a + ((j ^ sw) * 16)) = oa;
         *reinterpret_cast<uint4*>(row_g + ((j ^ sw) * 16)) = og;
+        *reinterpret_cast<uint4*>(row_y + ((j ^ sw) * 16)) = oy;
     }
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
         tma_store_4d(mapD, box, n_val, m_warp, 0, 0);
         tma_store_4d(mapD, box + 2048, n_val + 128, m_warp, 0, 0);
-        bulk_commit();
-        bulk_wait_read<0>();                       // both boxes read: the first is restaged with y
-    }
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(row_a + ((j ^ sw) * 16)) = make_uint4(yp[4 * j], yp[4 * j + 1], yp[4 * j + 2], yp[4 * j + 3]);
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-        tma_store_4d(mapY, box, y_col, m_warp, 0, 0);
+        tma_store_4d(mapY, ybox, y_col, m_warp, 0, 0);
         bulk_commit();
     }
     __syncwarp();
@@ -923,7 +915,8 @@ __global__ void __launch_bounds__(k2Threads, 1) gemm2_kernel(const __grid_consta
                         tmem_ld_wait();
                         if (lane == 0) bulk_wait_read<0>();
                         __syncwarp();
-                        epi2_pair_tma_geglu_fwd(e, &g.mapD, &g.mapD2, ra, rb, tma_box, lane, m_warp, n0 + p * 32, (n0 >> 1) + p * 32);
+                        epi2_pair_tma_geglu_fwd(e, &g.mapD, &g.mapD2, ra, rb, tma_box, smem + k2TOff + ew * 2048, lane, m_warp,
+                                                n0 + p * 32, (n0 >> 1) + p * 32);
                     }
                 }
             } else {
