@@ -447,7 +447,8 @@ __global__ void colsum_finish_kernel(const float* __restrict__ acc, bf16* __rest
 // the copy as its rank-r side operand: read in place (MN-major) that operand is a 64 x 32-byte box every CTA re-fetches
 // at every k-block - an L2 hot spot that cost 3.7 us per launch.
 __global__ void lora_bt_kernel(const bf16* __restrict__ params, bf16* __restrict__ bt, const long long* __restrict__ table) {
-    pdl_launch();
+    // (parameter-writing kernel: NO early launch_dependents - a dependent's pre-wait section, e.g. a weight prefetch,
+    //  must not overlap these stores; the implicit trigger at grid completion applies)
     pdl_wait();
     const long long* e = table + 4LL * blockIdx.x;
     const bf16* src = params + e[0];
@@ -464,7 +465,8 @@ __global__ void lora_bt_kernel(const bf16* __restrict__ params, bf16* __restrict
 // block-diagonal [3C, 3r] factor of the forward);  transpose == 1: dst[j * dst_ld + n] = B[n, j]  (its K-major transpose,
 // the side operand of the input-gradient GEMM).  Everything outside the blocks stays zero (written once at allocation).
 __global__ void lora_pack_kernel(const bf16* __restrict__ params, bf16* __restrict__ dst_base, const long long* __restrict__ table) {
-    pdl_launch();
+    // (parameter-writing kernel: NO early launch_dependents - a dependent's pre-wait section, e.g. a weight prefetch,
+    //  must not overlap these stores; the implicit trigger at grid completion applies)
     pdl_wait();
     const long long* e = table + 6LL * blockIdx.x;
     const bf16* src = params + e[0];

@@ -229,7 +229,7 @@ __device__ __forceinline__ void epi2_chunk_tma(const Epi2& e, const CUtensorMap*
             }
         }
     }
-    if (e.R != nullptr && m < e.M) {
+    if (e.R != nullptr && with_bias && m < e.M) {          // (stream-K: with the range that holds k-block 0, like the bias)
         const uint4* rp = reinterpret_cast<const uint4*>(e.R + static_cast<long long>(m) * e.r_sm + n_chunk);
         uint4 w4[4];
 #pragma unroll
@@ -437,7 +437,7 @@ __device__ __forceinline__ void epi2_chunk_direct(const Epi2& e, const uint32_t 
     if (m >= e.M) return;
     const __nv_bfloat16* bp = (e.bias && with_bias) ? e.bias + (e.bias_rows ? (m / e.bias_rows) * e.bias_sb : 0) : nullptr;
     __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(e.D) + static_cast<long long>(m) * e.d_sm;
-    const __nv_bfloat16* rp = e.R ? e.R + static_cast<long long>(m) * e.r_sm : nullptr;
+    const __nv_bfloat16* rp = (e.R && with_bias) ? e.R + static_cast<long long>(m) * e.r_sm : nullptr;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const int n = n_chunk + j;

@@ -348,12 +348,12 @@ static int launch_gemm2(const b200_gemm_t* d, int bn, void* stream) {
         d->N % 32 == 0 && static_cast<long long>(g.total_tiles) * g.kblocks >= kNumSMs / 2) {
         const size_t row_bytes = static_cast<size_t>(d->N) * 2;
         cudaError_t e = cudaSuccess;
-        if (d->R == nullptr) e = cudaMemset2DAsync(d->D, static_cast<size_t>(d->d_sm) * 2, 0, row_bytes, d->M, st);
-        else if (d->R != d->D) e = cudaMemcpy2DAsync(d->D, static_cast<size_t>(d->d_sm) * 2, d->R, static_cast<size_t>(d->r_sm) * 2,
-                                                     row_bytes, d->M, cudaMemcpyDeviceToDevice, st);
+        // D starts at zero; a residual that lives elsewhere rides (like the bias) with the range that holds k-block 0 of a tile -
+        // a memset instead of a device-to-device copy of the residual; R == D: D already holds it
+        if (d->R != d->D || d->R == nullptr) e = cudaMemset2DAsync(d->D, static_cast<size_t>(d->d_sm) * 2, 0, row_bytes, d->M, st);
         if (e != cudaSuccess) return set_error(3, "gemm2: stream-K output initialisation: %s", cudaGetErrorString(e));
         g.streamk = 1;
-        g.R = nullptr;
+        if (d->R == d->D) g.R = nullptr;
         pairs = kNumSMs / 2;
     }
     cudaError_t le;

@@ -169,7 +169,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {   // inputs alread
 __global__ void __launch_bounds__(256) adamw_kernel(bf16* __restrict__ p, float* __restrict__ grad, bf16* __restrict__ m,
                                                     bf16* __restrict__ v, long long n, long long n_first, AdamHyper h,
                                                     const AdamHyper* __restrict__ h_dev, int zero_grad, int vec) {
-    pdl_launch();
+    // (parameter-writing kernel: NO early launch_dependents - a dependent's pre-wait section, e.g. a weight prefetch,
+    //  must not overlap these stores; the implicit trigger at grid completion applies)
     pdl_wait();
     if (h_dev) h = *h_dev;     // CUDA-graph replay: hyper-parameters live in device memory, refreshed by a memcpy
     const float rc_bc2 = 1.f / h.bc2_sqrt;
@@ -364,7 +365,8 @@ __global__ void __launch_bounds__(256) prodigy_apply_kernel(bf16* __restrict__ p
                                                             const bf16* __restrict__ v, long long n,
                                                             const double* __restrict__ scal,
                                                             const ProdigyHyper* __restrict__ h_dev, int vec) {
-    pdl_launch();
+    // (parameter-writing kernel: NO early launch_dependents - a dependent's pre-wait section, e.g. a weight prefetch,
+    //  must not overlap these stores; the implicit trigger at grid completion applies)
     pdl_wait();
     if (scal[6] != 0.0) return;
     const ProdigyHyper h = *h_dev;

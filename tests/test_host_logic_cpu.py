@@ -270,3 +270,34 @@ def test_shared_dscores_path_is_value_identical(monkeypatch, family, hw):
     for k in ("img_loss", "token_attention_loss", "token_std_loss", "tot_loss"):
         assert float(out_a[k]) == float(out_b[k]), k
     assert torch.equal(tr_a.store.grads, tr_b.store.grads)
+
+
+def test_reset_optimizer_state_and_close(monkeypatch):
+    """After a checkpoint is loaded into a live trainer the optimizer state must restart from the loaded parameters
+    (Adam moments zero, Prodigy's start point = the new parameters, d back at d0, conditioning cache empty); close() drops
+    the captured graphs / static buffers (what lets destroy_process_group() return under data parallelism)."""
+    cpu_mock_ops.install(monkeypatch)
+    from oracle.step import OracleTrainer, StepConfig, make_inputs
+    from oracle.text import build_text_encoders
+    from sd_lora_trainer_b200.step import StepConfig as PCfg, TrainerB200
+    cfg = StepConfig(family="sd15", tiny=True, resolution=64, lora_rank=4, unet_optimizer_type="prodigy", ti_optimizer="prodigy")
+    orc = OracleTrainer(cfg, device="cpu")
+    inputs = make_inputs(cfg, batch=1, latent_hw=8, face_mask=True, train_ids=orc.train_ids)
+    pcfg = PCfg(**{k: getattr(cfg, k) for k in PCfg.__dataclass_fields__ if hasattr(cfg, k)})
+    tr = TrainerB200(pcfg, orc.unet.state_dict(), build_text_encoders(cfg.family, cfg.tiny, seed=cfg.seed + 1), device="cpu")
+    for _ in range(2):
+        tr.step(inputs)
+    assert float(tr.store.m.float().abs().max()) > 0 and tr.opt_step == 2
+    tr.store.params[:tr.store.n_lora].mul_(0.5)                  # "a checkpoint was loaded"
+    tr._text_cache[("x",)] = (None, None)
+    tr.reset_optimizer_state()
+    assert float(tr.store.m.float().abs().max()) == 0 and float(tr.store.v.float().abs().max()) == 0
+    assert float(tr.store.grads.abs().max()) == 0 and float(tr._prodigy_s.float().abs().max()) == 0
+    assert torch.equal(tr._prodigy_p0, tr.store.params) and tr.opt_step == 0 and not tr._text_cache
+    for name, (lo, hi, scal, ring, dev, kw) in tr._prodigy.items():
+        assert float(scal[0]) == float(scal[1]) and abs(float(scal[0]) - 1e-6) < 1e-12 and float(scal[2]) == 0.0
+    tr._graphs[("k",)] = object()
+    tr._static = {"a": torch.zeros(1)}
+    tr.close()
+    assert tr._graphs == {} and tr._static is None
+    tr.step(inputs)                                              # and the trainer keeps working afterwards
