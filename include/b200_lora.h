@@ -129,8 +129,10 @@ int b200_softmax_bwd(const void* P, const float* dP, void* dS, int64_t rows, int
  * batch stride mask_sb elements (mask[:, 0], resized in-kernel like F.interpolate(mode="nearest")); tok_len[b] = len(tokenizer.encode(caption_b)),
  * ti_pos[b, j] = position of trainable token j in caption b or -1.  loss_out[0] <- the regulariser; G (bf16
  * [B, h*w, ld_g], may be NULL) <- grad_scale * d loss / d maps[l] - the SAME map for every layer l (the loss sees only the
- * layer mean).  ws: fp32 workspace of B*h*w*77 + 8*B floats.  n_layers <= 64, 77 <= 80 text positions, <= 8 tokens.
+ * layer mean).  ws: fp32 workspace of b200_token_attention_loss_floats(B, h, w, n_text) floats.  n_layers <= 64, 77 <= 80 text
+ * positions, <= 8 tokens.
  * --------------------------------------------------------------------------------------------------------- */
+int64_t b200_token_attention_loss_floats(int32_t B, int32_t h, int32_t w, int32_t n_text);
 int b200_token_attention_loss(const void* const* maps, const int64_t* lds, int32_t n_layers, int32_t B, int32_t h, int32_t w,
                               int32_t n_text, const float* mask, int64_t mask_sb, int32_t Hm, int32_t Wm, const int64_t* tok_len,
                               const int64_t* ti_pos, int32_t n_tok, float grad_scale, float* ws, int64_t ws_floats,

@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200_softmax_fwd": [c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_softmax_bwd": [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_void_p],
     "b200_groupnorm_stats_floats": [c_int32, c_int64, c_int32, c_int32],
+    "b200_token_attention_loss_floats": [c_int32, c_int32, c_int32, c_int32],
     "b200_groupnorm_fwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_int32,
                            c_float, c_int32, c_void_p],
     "b200_groupnorm_bwd": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64,
@@ -100,7 +101,8 @@ SIGNATURES = {
     "b200_prodigy_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32,
                           c_void_p],
 }
-_RESTYPES = {"b200_last_error": C.c_char_p, "b200_launch_count": C.c_longlong, "b200_groupnorm_stats_floats": C.c_int64}
+_RESTYPES = {"b200_last_error": C.c_char_p, "b200_launch_count": C.c_longlong, "b200_groupnorm_stats_floats": C.c_int64,
+             "b200_token_attention_loss_floats": C.c_int64}
 
 _lib = None
 

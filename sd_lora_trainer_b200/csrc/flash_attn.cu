@@ -20,8 +20,11 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
                        ld_o >= static_cast<int64_t>(H) * 64 && ld_o % 8 == 0,
                    "flash_attn_fwd: bad extents");
     static bool attr = false;
+    // B200_FLASH_FWD_TS=0: the variant that stages P in shared memory (kept for A/B measurements)
+    static const bool ts_mode = !(getenv("B200_FLASH_FWD_TS") && atoi(getenv("B200_FLASH_FWD_TS")) == 0);
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtsSmem);
         if (e != cudaSuccess) return set_error(3, "flash_attn_fwd: %s", cudaGetErrorString(e));
         attr = true;
     }
@@ -38,7 +41,8 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
     g.o_ld = ld_o;
     g.scale = scale;
     dim3 grid((L + 127) / 128, H, B);
-    launch_pdl(flash_fwd_kernel, dim3(grid), dim3(kFaThreads), kFwdSmem, static_cast<cudaStream_t>(stream), g);
+    if (ts_mode) launch_pdl(flash_fwd_ts_kernel, dim3(grid), dim3(kFaThreads), kFtsSmem, static_cast<cudaStream_t>(stream), g);
+    else launch_pdl(flash_fwd_kernel, dim3(grid), dim3(kFaThreads), kFwdSmem, static_cast<cudaStream_t>(stream), g);
     B200_CHECK_LAUNCH("flash_fwd");
     return 0;
 }
@@ -101,45 +105,44 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
         g.ld_dsc = ld_dsc;
         g.dsc_cols = dsc_cols;
     }
-    dim3 grid((Lk + 127) / 128, H, B);
-    // Query split: (a) single key block (cross-attention) on a grid that would leave SMs idle; (b) several key blocks whose
-    // CTA count quantises badly over the 148 SMs (one CTA per SM): pick the split that minimises rounds x blocks per CTA,
-    // charging each extra CTA its fixed cost (K / V load, prologue, atomic epilogue ~ 1.5 query blocks).
-    g.nsplit = 1;
+    // Query split (see FlashBwdArgs): (a) a grid smaller than the machine - every item is cut so that the pieces fill it;
+    // (b) a grid of several rounds whose last round is partial - only that round's items are cut (the full rounds cost the
+    // same for every SM, so the pieces start together and the step ends one short round later instead of one full round
+    // later).
     const int nq = (L + 127) / 128, nkb = (Lk + 127) / 128;
+    const long long items = static_cast<long long>(nkb) * H * B;
+    g.nsplit = 1;
+    g.n_unsplit = static_cast<int>(items);
     g.nkb = nkb;
     const long long plane = static_cast<long long>(B) * Lk * ld;
-    // (b) is opt-in (B200_FLASH_QSPLIT=1): with a uniform split the extra CTAs' fixed cost eats the rounds it saves (the model
-    // below picks 1 for SDXL's L = 1024 layers); a non-uniform, stream-K-style cut of the (key block, query block) grid is
-    // what would pay
-    static const int split_env = getenv("B200_FLASH_QSPLIT") ? atoi(getenv("B200_FLASH_QSPLIT")) : 0;
-    if (split_ws != nullptr && nq >= 2 && split_ws_floats >= 2 * plane + static_cast<long long>(B) * H * nkb) {
-        int best = 1;
-        if (dq_direct && B * H < kNumSMs) {
-            best = kNumSMs / (B * H);
-            if (best > nq) best = nq;
-        } else if (!dq_direct && split_env) {
-            double best_cost = 1e30;
-            for (int ns = 1; ns <= 4 && ns <= nq; ++ns) {
-                const long long ctas = static_cast<long long>(nkb) * H * B * ns;
-                const long long rounds = (ctas + kNumSMs - 1) / kNumSMs;
-                const double per_cta = (nq + ns - 1) / ns + (ns > 1 ? 1.5 : 0.5);
-                const double cost = rounds * per_cta;
-                if (cost < best_cost - 1e-9) {
-                    best_cost = cost;
-                    best = ns;
-                }
+    // B200_FLASH_TAILSPLIT: most pieces an item of the partial round is cut into (0 / 1: never cut)
+    static const int tail_env = getenv("B200_FLASH_TAILSPLIT") ? atoi(getenv("B200_FLASH_TAILSPLIT")) : 8;
+    long long n_ctas = items;
+    if (split_ws != nullptr && nq >= 2 && split_ws_floats >= 2 * plane + items) {
+        const long long full = items / kNumSMs * kNumSMs, tail = items - full;
+        int ns = 1;
+        if (tail > 0 && (full == 0 || (tail_env >= 2 && !dq_direct))) {
+            ns = static_cast<int>(kNumSMs / tail);
+            if (ns > nq) ns = nq;
+            if (full > 0) {
+                if (ns > tail_env) ns = tail_env;
+                // Measured (scripts/gpu_r2v.sh, gpu_r2x.sh): a CTA's fixed cost (prologue, K / V load, pipeline fill, atomic
+                // epilogue, last-arriver rounding) is worth ~4 query blocks, so pieces shorter than 8 blocks do not pay:
+                // L = 1024 (8 blocks per item) is left whole, L = 4096 (32 blocks, 3 pieces of ~11) gains 6.5 %.
+                if (ns > nq / 8) ns = nq / 8;
             }
         }
-        if (best >= 2) {
+        if (ns >= 2) {
             B200_CHECK_ARG(reinterpret_cast<uintptr_t>(split_ws) % 16 == 0, "flash_attn_bwd: split workspace not 16-byte aligned");
-            g.nsplit = best;
+            g.nsplit = ns;
+            g.n_unsplit = static_cast<int>(full);
             g.nbatch_rows = B * Lk;
             g.dKVacc = split_ws;
             g.counters = reinterpret_cast<int*>(split_ws + 2 * plane);
-            grid.x = nkb * best;
+            n_ctas = full + tail * ns;
         }
     }
+    dim3 grid(static_cast<unsigned>(n_ctas));
     if (g.dSc != nullptr) launch_pdl(flash_bwd_kernel<true>, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     else launch_pdl(flash_bwd_kernel<false>, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     B200_CHECK_LAUNCH("flash_bwd");

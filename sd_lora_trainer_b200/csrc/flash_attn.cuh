@@ -316,6 +316,259 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_kernel(const __grid_c
     if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Forward, P kept in tensor memory.  ncu on the kernel above: the shared-memory data pipe is the busiest unit (per
+// 128-key block: 80 KB of MMA operand reads + 32 KB of P stores + 32 KB of TMA writes ~ 1260 clk of 128 B/clk, twice per
+// SM with two resident CTAs), ahead of MUFU (1024 clk) and the tensor pipe (512 clk).  Here the softmax warps write P
+// (bf16, two keys per 32-bit column) straight into TMEM with tcgen05.st and O += P.V reads its A operand from there:
+// no P tile in shared memory, no generic->async proxy fence, and half the operand traffic of the P.V product.
+// TMEM (256 columns): S [0,128), O [128,192), P [192,256).  One O accumulator means the two softmax warp groups (keys
+// 0-63 / 64-127 of every block) must exponentiate against the same reference maximum: they swap their half-row maxima
+// through a 2 KB shared-memory slot (double-buffered by block parity, one 64-thread named barrier per block).
+// -----------------------------------------------------------------------------------------------------------------
+constexpr int kFtsQ = 0;
+constexpr int kFtsK = kFtsQ + kFaTile;         // 2 stages
+constexpr int kFtsV = kFtsK + 2 * kFaTile;     // 2 stages
+constexpr int kFtsX = kFtsV + 2 * kFaTile;     // [2 parities][2 halves][128 rows] fp32
+constexpr int kFtsBar = kFtsX + 2048;
+constexpr int kFtsSmem = kFtsBar + 128;
+
+// 64-thread named barrier 2 + quarter with an immediate id (a register id makes ptxas reserve all 16 barriers of the CTA)
+__device__ __forceinline__ void pair_bar_sync(int quarter) {
+    switch (quarter) {
+        case 0: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 5, 64;" ::: "memory"); break;
+    }
+}
+
+__global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __grid_constant__ FlashFwdArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFtsBar);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;      // [2]
+    uint64_t* v_full = bars + 3;      // [2]
+    uint64_t* kv_empty = bars + 5;    // [2]
+    uint64_t* s_full = bars + 7;
+    uint64_t* s_free = bars + 8;
+    uint64_t* p_full = bars + 9;
+    uint64_t* o_done = bars + 10;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int nkv = (g.Lk + 127) >> 7;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&g.mapQ);
+        tma_prefetch_desc(&g.mapK);
+        tma_prefetch_desc(&g.mapV);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 8);
+        mbar_init(p_full, 8);
+        mbar_init(o_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_ptr, 256);
+        tmem_relinquish();
+    }
+    pdl_launch();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_wait();                                   // nothing above touched global memory
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t tmem_S = tmem, tmem_O = tmem + 128, tmem_P = tmem + 192;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, kFaTile);
+            tma_load_4d(smem + kFtsQ, &g.mapQ, q_full, 0, q0, h, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_expect_tx(&k_full[s], kFaTile);
+                tma_load_4d(smem + kFtsK + s * kFaTile, &g.mapK, &k_full[s], 0, j * 128, h, b);
+                mbar_expect_tx(&v_full[s], kFaTile);
+                tma_load_4d(smem + kFtsV + s * kFaTile, &g.mapV, &v_full[s], 0, j * 128, h, b);
+                tma_load_4d(smem + kFtsV + s * kFaTile + 8192, &g.mapV, &v_full[s], 0, j * 128 + 64, h, b);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_bf16(128, 0, 0);     // S[128q x 128k] = Q (K-major) . K^T (K-major)
+            const uint32_t idesc_o = umma_idesc_bf16(64, 0, 1);      // O[128q x 64d] += P (TMEM) . V (MN-major)
+            const uint32_t sq = smem_u32(smem + kFtsQ);
+            auto issue_s = [&](int j) {
+                const uint32_t sk = smem_u32(smem + kFtsK + (j & 1) * kFaTile);
+                const uint64_t ad = umma_desc(sq, 16, 1024), bd = umma_desc(sk, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
+                umma_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&k_full[0], 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                if (j + 1 < nkv) {
+                    mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    mbar_wait(s_free, j & 1);              // the softmax warps have pulled S_j out of TMEM
+                    tc_fence_after();
+                    issue_s(j + 1);
+                }
+                mbar_wait(p_full, j & 1);                   // P_j written to TMEM, O rescaled
+                mbar_wait(&v_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t sv = smem_u32(smem + kFtsV + s * kFaTile);
+                const uint64_t vd = umma_desc(sv, 8192, 1024);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)                 // 16 keys = 8 packed columns of P per step
+                    umma_bf16_ts(tmem_O, tmem_P + 8 * k, vd + 128 * k, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&kv_empty[s]);
+                umma_commit(o_done);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- softmax / correction / epilogue: thread <-> (query row, half of the keys of every block) ----
+        const int lane_base = (warp & 3) * 32;
+        const int row = lane_base + lane;
+        const int half = (warp >= 6) ? 1 : 0;
+        const int quarter = warp & 3;                               // the two warps of a TMEM lane quarter share a named barrier
+        const uint32_t lane_off = static_cast<uint32_t>(lane_base) << 16;
+        const float sl2 = g.scale * 1.4426950408889634f;           // scores are used in the log2 domain
+        float* xch = reinterpret_cast<float*>(smem + kFtsX);
+        // m: the reference maximum the exponentials are taken against (common to both halves of a row).  It only moves
+        // when the row's running maximum outgrows it by more than 2^8 (log2 domain), so O (in TMEM) is rescaled on a few
+        // blocks instead of on every one; the final O / l and LSE = m.scale + ln(l) are exact whatever reference was used.
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kvalid = min(128, g.Lk - j * 128) - half * 64;   // valid keys among this group's 64 (may be <= 0)
+            const bool full_blk = kvalid >= 64;                     // warp-uniform
+            // pass 1: row maximum over this group's keys, then over both groups
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_S + lane_off + half * 64 + c * 32, raw);
+                tmem_ld_wait();
+                if (full_blk) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
+                }
+            }
+            xch[((j & 1) * 2 + half) * 128 + row] = mx;
+            pair_bar_sync(quarter);
+            mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * 128 + row]);
+            const float m_cand = fmaxf(m, mx);
+            const bool need = (m_cand - m) * sl2 > 8.f;             // true on the first block (m = -inf)
+            const bool any_need = __any_sync(0xffffffffu, need);
+            if (j > 0) {
+                // the previous P.V must have retired before O is rescaled and before P is overwritten
+                mbar_wait(o_done, (j - 1) & 1);
+                tc_fence_after();
+            }
+            if (any_need) {
+                const float alpha = need ? fast_exp2((m - m_cand) * sl2) : 1.f;   // 0 when m was -inf
+                if (need) m = m_cand;
+                l *= alpha;
+                if (j > 0) {                                        // this group rescales its 32 columns of O
+                    uint32_t o[32];
+                    tmem_ld32(tmem_O + lane_off + half * 32, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st32(tmem_O + lane_off + half * 32, o);
+                }
+            }
+            const float moff = m * sl2;
+            // pass 2: exponentials, row sum, P -> TMEM (bf16 pairs)
+            float sum = 0.f;
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_S + lane_off + half * 64 + c * 32, raw);
+                tmem_ld_wait();
+                if (c == 1) {                                       // S_j is out of TMEM: the next Q.K^T may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(s_free);
+                }
+                float p[32];
+                if (full_blk) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        p[i] = fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, -moff));
+                        sum += p[i];
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        p[i] = (c * 32 + i < kvalid) ? fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, -moff)) : 0.f;
+                        sum += p[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[c * 16 + i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+            }
+            l += sum;
+            tmem_st32(tmem_P + lane_off + half * 32, pk);           // keys [half*64, +64) = packed columns [half*32, +32)
+            tmem_st_wait();                                         // P (and a rescaled O) are in TMEM
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(o_done, (nkv - 1) & 1);
+        tc_fence_after();
+        // ---- row sums of the two halves (same reference m) ----
+        xch[(nkv & 1) * 256 + half * 128 + row] = l;
+        pair_bar_sync(quarter);
+        const float l_all = l + xch[(nkv & 1) * 256 + (half ^ 1) * 128 + row];
+        const int q = q0 + row;
+        const float inv = 1.f / l_all;
+        // this thread writes output columns [half*32, half*32 + 32) of its row
+        __nv_bfloat16* op = g.O + (static_cast<long long>(b) * g.L + q) * g.o_ld + h * 64 + half * 32;
+        {
+            uint32_t oa[32];
+            tmem_ld32(tmem_O + lane_off + half * 32, oa);
+            tmem_ld_wait();
+            if (q < g.L) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 w;
+                    w.x = pack_bf16(__uint_as_float(oa[8 * i + 0]) * inv, __uint_as_float(oa[8 * i + 1]) * inv);
+                    w.y = pack_bf16(__uint_as_float(oa[8 * i + 2]) * inv, __uint_as_float(oa[8 * i + 3]) * inv);
+                    w.z = pack_bf16(__uint_as_float(oa[8 * i + 4]) * inv, __uint_as_float(oa[8 * i + 5]) * inv);
+                    w.w = pack_bf16(__uint_as_float(oa[8 * i + 6]) * inv, __uint_as_float(oa[8 * i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(op + i * 8) = w;
+                }
+            }
+        }
+        if (half == 0 && q < g.L) g.LSE[(static_cast<long long>(b) * g.H + h) * g.L + q] = m * g.scale + logf(l_all);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
 
 // =================================================================================================================
 // backward
@@ -345,11 +598,12 @@ struct FlashBwdArgs {
     int L, Lk, H;
     long long ld;
     float scale;
-    // Query split.  A grid of (key blocks, H, B) CTAs that each walk all L/128 query blocks leaves SMs idle when it is small
-    // (cross-attention: 40 CTAs at SDXL's 1280-wide level) or quantises badly (self-attention at L = 1024: 320 CTAs on 148
-    // SMs = 3 rounds for 2.16 rounds of work), so blockIdx.x additionally cuts the query blocks into nsplit contiguous
-    // ranges.  dQ blocks are disjoint (written directly or reduce-added as before); every CTA adds its partial dK / dV (fp32
-    // atomics) into dKVacc [2][B*Lk, ld], and the LAST CTA of a (b, h) to finish - counted in `counters` - rounds the sums
+    // Query split.  One CTA per (key block, h, b) that walks all L/128 query blocks leaves SMs idle when the grid is small
+    // (cross-attention: 40 CTAs at SDXL's 1280-wide level) and quantises badly otherwise (self-attention at L = 1024: 320
+    // CTAs on 148 SMs = 3 rounds for 2.16 rounds of work).  So the items of the last, partial round (or all of them, for a
+    // small grid) are cut into nsplit contiguous query ranges, sized so that the pieces fill the machine once.  dQ blocks
+    // are disjoint (written directly or reduce-added as before); every piece adds its partial dK / dV (fp32 atomics) into
+    // dKVacc [2][B*Lk, ld], and the LAST piece of a (b, h, key block) to finish - counted in `counters` - rounds the sums
     // to bf16 into dK / dV and re-zeroes accumulators and counter, so the workspace is clean for the next launch.
     // Gradient of the head-summed pre-softmax scores (the DAAM hook, trainer/ti_cross_attn_loss.py:201-212): the hook's
     // score is sum_h scale * q_h . k_h, so its gradient dSc[b, q, key] (bf16, the same for every head) enters exactly where
@@ -358,7 +612,8 @@ struct FlashBwdArgs {
     const __nv_bfloat16* dSc;
     long long ld_dsc;
     int dsc_cols;
-    int nsplit;
+    int nsplit;                                // query ranges per split item
+    int n_unsplit;                             // leading work items that are not split
     int nkb;                                   // key blocks (counters are per (b, h, key block))
     int nbatch_rows;                           // B * Lk: rows of one accumulator plane
     float* dKVacc;
@@ -382,12 +637,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.y, b = blockIdx.z;
     const int nq_all = (g.L + 127) >> 7;
-    const int nsplit = g.nsplit;
+    // 1-D grid over work items (key block fastest, then head, then batch).  Items [0, n_unsplit) are walked whole by one CTA
+    // each; every later item is cut into g.nsplit contiguous query ranges (one CTA each) - the tail of the last, partial round
+    // over the SMs, or every item when the whole grid is smaller than the machine.
+    int item = static_cast<int>(blockIdx.x), qsp = 0, nsplit = 1;
+    if (item >= g.n_unsplit) {
+        const int t = item - g.n_unsplit;
+        nsplit = g.nsplit;
+        item = g.n_unsplit + t / nsplit;
+        qsp = t - (t / nsplit) * nsplit;
+    }
+    const int kblk = item % g.nkb, h = (item / g.nkb) % g.H, b = item / (g.nkb * g.H);
     // query blocks [qb0, qb0 + nq) of this CTA; ring stages / barrier phases follow the LOCAL block index
-    // blockIdx.x = key block * nsplit + query split
-    const int kblk = static_cast<int>(blockIdx.x) / nsplit, qsp = static_cast<int>(blockIdx.x) - kblk * nsplit;
     const int k0 = kblk * 128;
     const int qb0 = nsplit > 1 ? static_cast<int>((static_cast<long long>(nq_all) * qsp) / nsplit) : 0;
     const int nq = nsplit > 1 ? static_cast<int>((static_cast<long long>(nq_all) * (qsp + 1)) / nsplit) - qb0 : nq_all;
@@ -692,18 +954,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             __threadfence();
             const long long half = static_cast<long long>(g.nbatch_rows) * g.ld;
             const int kvalid2 = min(128, g.Lk - k0);               // keys of this block
-            for (int idx = threadIdx.x; idx < kvalid2 * 16 * 2; idx += blockDim.x) {
-                const int which = idx / (kvalid2 * 16);            // 0: dK, 1: dV
-                const int rem = idx - which * kvalid2 * 16;
-                const int key = k0 + (rem >> 4), c4 = (rem & 15) * 4;
-                const long long off = (static_cast<long long>(b) * g.Lk + key) * g.ld + h * 64 + c4;
-                float4* ap = reinterpret_cast<float4*>(g.dKVacc + which * half + off);
-                const float4 v = __ldcg(ap);
-                __stcg(ap, make_float4(0.f, 0.f, 0.f, 0.f));
-                uint2 w;
-                w.x = pack_bf16(v.x, v.y);
-                w.y = pack_bf16(v.z, v.w);
-                *reinterpret_cast<uint2*>((which ? g.dV : g.dK) + off) = w;
+            // <= 128 keys x 16 float4 x {dK, dV} = 4096 float4 over 448 threads: all of a thread's loads are issued before its
+            // first store (a plain load-store loop exposes one L2 round trip per iteration at the very end of the kernel)
+            constexpr int kPer = (128 * 16 * 2 + kBwdThreads - 1) / kBwdThreads;
+            const int total = kvalid2 * 16 * 2;
+            float4 v[kPer];
+            long long offs[kPer];
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int idx = threadIdx.x + u * kBwdThreads;
+                offs[u] = -1;
+                if (idx < total) {
+                    const int which = idx / (kvalid2 * 16);        // 0: dK, 1: dV
+                    const int rem = idx - which * kvalid2 * 16;
+                    const int key = k0 + (rem >> 4), c4 = (rem & 15) * 4;
+                    offs[u] = which * half + (static_cast<long long>(b) * g.Lk + key) * g.ld + h * 64 + c4;
+                    v[u] = __ldcg(reinterpret_cast<const float4*>(g.dKVacc + offs[u]));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                if (offs[u] >= 0) {
+                    __stcg(reinterpret_cast<float4*>(g.dKVacc + offs[u]), make_float4(0.f, 0.f, 0.f, 0.f));
+                    const bool is_dv = offs[u] >= half;
+                    uint2 w;
+                    w.x = pack_bf16(v[u].x, v[u].y);
+                    w.y = pack_bf16(v[u].z, v[u].w);
+                    *reinterpret_cast<uint2*>((is_dv ? g.dV : g.dK) + (offs[u] - (is_dv ? half : 0))) = w;
+                }
             }
             if (threadIdx.x == 0) g.counters[(b * g.H + h) * g.nkb + kblk] = 0;
         }

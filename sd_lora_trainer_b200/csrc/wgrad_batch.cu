@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kWgThreads) lora_wgrad_batch_kernel(const __gr
     const int n0 = n_tile * kWgTileN;
     const int m_begin = m_chunk * P.mchunk;
     const int m_end = min(P.M, m_begin + P.mchunk);
-    const int M = P.M, Nout = P.Nout, r = P.r;
+    const int Nout = P.Nout, r = P.r;
     const bf16* __restrict__ X = P.X;
     const bf16* __restrict__ Y = P.Y;
     const long long ld_x = P.ld_x, ld_y = P.ld_y;

@@ -524,7 +524,7 @@ def token_attention_loss(maps: Sequence[torch.Tensor], h: int, w: int, n_text: i
         ptrs[i], lds[i] = m.data_ptr(), m.stride(1)
     dev = maps[0].device
     ld_g = (n_text + 7) // 8 * 8
-    ws = torch.empty(B * hw * n_text + 8 * B, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(_lib.load().b200_token_attention_loss_floats(B, h, w, n_text)), dtype=torch.float32, device=dev)
     loss = torch.empty(1, dtype=torch.float32, device=dev)
     G = torch.empty(B, hw, ld_g, dtype=BF16, device=dev) if want_grad else None
     check(_lib.load().b200_token_attention_loss(ptrs, lds, n, B, h, w, n_text, mask3.data_ptr(), mask3.stride(0), mask3.shape[1],

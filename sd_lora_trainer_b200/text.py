@@ -28,8 +28,10 @@ class TIEmbedding(nn.Module):
         if self.ti_rows is None:
             return base
         is_ti = ids >= self.vocab
-        rows = self.ti_rows[(ids - self.vocab).clamp(min=0)]
-        return torch.where(is_ti[..., None], rows, base)
+        # one-hot matmul instead of ti_rows[index]: the gather's backward (indexing_backward_kernel) serialises over duplicate
+        # indices - 119 us per encoder with every non-TI position clamped onto row 0; this form's backward is one tiny GEMM
+        sel = (ids[..., None] == self.vocab + torch.arange(self.ti_rows.shape[0], device=ids.device)).to(self.ti_rows.dtype)
+        return torch.where(is_ti[..., None], sel @ self.ti_rows, base)
 
 
 def install_ti_rows(text_encoder, ti_rows: Optional[torch.Tensor]):
