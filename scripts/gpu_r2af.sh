@@ -1,0 +1,7 @@
+#!/bin/bash
+# attention backward: share of the exponentials on the FMA pipe (B200_FLASH_POLY_BWD = every n-th pair; 0 = none)
+timeout 600 python -m pytest tests/test_flash_gpu.py -x -q -m gpu 2>&1 | tail -2
+for L in "1024 20" "4096 10"; do
+  for P in 0 4 2; do TIME=1 B200_FLASH_POLY_BWD=$P timeout 300 python scripts/one_flash.py $L 2>&1 | tail -1 | sed "s/\$/ POLY_BWD=$P/"; done
+done
+B200_FLASH_TIMELINE=1 timeout 300 python scripts/one_flash.py 1024 9 2>&1 | grep -A8 "flash_bwd timeline" | tail -4 | cut -c1-170

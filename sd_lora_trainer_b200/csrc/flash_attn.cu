@@ -24,7 +24,8 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
     static const bool ts_mode = !(getenv("B200_FLASH_FWD_TS") && atoi(getenv("B200_FLASH_FWD_TS")) == 0);
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_fwd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_fwd_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtsSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(flash_fwd_ts_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFtsSmem);
         if (e != cudaSuccess) return set_error(3, "flash_attn_fwd: %s", cudaGetErrorString(e));
         attr = true;
     }
@@ -41,9 +42,34 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
     g.o_ld = ld_o;
     g.scale = scale;
     dim3 grid((L + 127) / 128, H, B);
-    if (ts_mode) launch_pdl(flash_fwd_ts_kernel, dim3(grid), dim3(kFaThreads), kFtsSmem, static_cast<cudaStream_t>(stream), g);
+    // B200_FLASH_TIMELINE=1 (debug, synchronises): clock64 stamps of CTA (0,0,0) printed to stderr after every launch -
+    // per key block: s_full seen, row max done, o_done seen, exponentials done, P published | MMA: S(j+1) issued, P.V(j) issued
+    static const bool timeline = kFaTimeline && getenv("B200_FLASH_TIMELINE") && atoi(getenv("B200_FLASH_TIMELINE")) != 0;
+    static long long* tl_buf = nullptr;
+    const int nkv_dbg = (Lk + 127) / 128;
+    if (timeline && ts_mode && nkv_dbg <= 64) {
+        if (!tl_buf) cudaMalloc(&tl_buf, 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(tl_buf, 0, 64 * 8 * sizeof(long long), static_cast<cudaStream_t>(stream));
+        g.timeline = tl_buf;
+    }
+    // B200_FLASH_POLY=0: every exponential on MUFU (default: every 4th on the FMA pipe, see flash_fwd_ts_kernel)
+    static const bool poly = !(getenv("B200_FLASH_POLY") && atoi(getenv("B200_FLASH_POLY")) == 0);
+    const cudaStream_t st_f = static_cast<cudaStream_t>(stream);
+    if (ts_mode && poly) launch_pdl(flash_fwd_ts_kernel<4>, dim3(grid), dim3(kFaThreads), kFtsSmem, st_f, g);
+    else if (ts_mode) launch_pdl(flash_fwd_ts_kernel<0>, dim3(grid), dim3(kFaThreads), kFtsSmem, st_f, g);
     else launch_pdl(flash_fwd_kernel, dim3(grid), dim3(kFaThreads), kFwdSmem, static_cast<cudaStream_t>(stream), g);
     B200_CHECK_LAUNCH("flash_fwd");
+    if (g.timeline != nullptr) {
+        long long hbuf[64 * 8];
+        cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        cudaMemcpy(hbuf, tl_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        const long long t0 = hbuf[7];
+        fprintf(stderr, "flash_fwd timeline (clk since first S issue) B=%d H=%d L=%d Lk=%d\n", B, H, L, Lk);
+        for (int j = 0; j < nkv_dbg; ++j)
+            fprintf(stderr, "  blk %2d: s_full %6lld  max %6lld  o_done %6lld  exp %6lld  p_pub %6lld | S(j+1) issue %6lld  PV(j) issue %6lld\n", j,
+                    hbuf[j * 8 + 0] - t0, hbuf[j * 8 + 1] - t0, hbuf[j * 8 + 2] - t0, hbuf[j * 8 + 3] - t0, hbuf[j * 8 + 4] - t0,
+                    hbuf[j * 8 + 5] ? hbuf[j * 8 + 5] - t0 : 0, hbuf[j * 8 + 6] - t0);
+    }
     return 0;
 }
 
@@ -143,9 +169,27 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
         }
     }
     dim3 grid(static_cast<unsigned>(n_ctas));
+    static const bool timeline = kFaTimeline && getenv("B200_FLASH_TIMELINE") && atoi(getenv("B200_FLASH_TIMELINE")) != 0;
+    static long long* tl_buf = nullptr;
+    if (timeline && nq <= 64) {                    // debug, synchronises: see b200_flash_attn_fwd
+        if (!tl_buf) cudaMalloc(&tl_buf, 64 * 8 * sizeof(long long));
+        cudaMemsetAsync(tl_buf, 0, 64 * 8 * sizeof(long long), st);
+        g.timeline = tl_buf;
+    }
     if (g.dSc != nullptr) launch_pdl(flash_bwd_kernel<true>, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     else launch_pdl(flash_bwd_kernel<false>, dim3(grid), dim3(kBwdThreads), kBwdSmem, st, g);
     B200_CHECK_LAUNCH("flash_bwd");
+    if (g.timeline != nullptr) {
+        long long hbuf[64 * 8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hbuf, tl_buf, sizeof(hbuf), cudaMemcpyDeviceToHost);
+        const long long t0 = hbuf[7];
+        fprintf(stderr, "flash_bwd timeline (clk since first S/dP issue) B=%d H=%d L=%d Lk=%d\n", B, H, L, Lk);
+        for (int i = 0; i < nq && i < 10; ++i)
+            fprintf(stderr, "  qblk %2d: sdp_full %6lld  first half done %6lld  pds_free %6lld  P/dS published %6lld | S/dP(i+1) issued %6lld  grads(i) issued %6lld | dq_full %6lld\n",
+                    i, hbuf[i * 8 + 0] - t0, hbuf[i * 8 + 1] - t0, hbuf[i * 8 + 2] - t0, hbuf[i * 8 + 3] - t0,
+                    hbuf[i * 8 + 4] ? hbuf[i * 8 + 4] - t0 : 0, hbuf[i * 8 + 5] - t0, hbuf[i * 8 + 6] - t0);
+    }
     if (!dq_direct) {
         launch_pdl(f32_to_bf16_kernel, dim3(grid_for(nq_elems / 4, 256)), dim3(256), 0, st, dq_acc_ws, static_cast<__nv_bfloat16*>(dq),
                    nq_elems / 4, static_cast<int>(C64 / 4), static_cast<long long>(ld));

@@ -18,6 +18,13 @@
 
 namespace b200 {
 
+// Debug timelines (clock64 stamps of CTA 0, printed by the host wrappers when B200_FLASH_TIMELINE=1): compiled out unless this
+// is set to true - profiles/r02m_flash_timelines.txt holds the ones the comments below quote.
+#ifndef B200_FLASH_TIMELINE_BUILD
+#define B200_FLASH_TIMELINE_BUILD 0
+#endif
+constexpr bool kFaTimeline = B200_FLASH_TIMELINE_BUILD != 0;
+
 constexpr int kFaThreads = 320;                // TMA, MMA, 2 x 4 softmax warps (keys 0-63 / 64-127 of every block)
 constexpr int kFaTile = 128 * 64 * 2;          // one [128 x 64] bf16 tile: 16 KiB
 // forward smem map
@@ -35,6 +42,7 @@ struct FlashFwdArgs {
     int L, Lk, H;
     long long o_ld;                            // row stride of O in elements (= C)
     float scale;                               // 1/sqrt(d)
+    long long* timeline;                       // debug (B200_FLASH_TIMELINE=1): clock64 stamps of CTA (0,0,0), [block][8]; else NULL
 };
 
 // 2^x on the MUFU pipe, denormal results flushed to zero (softmax weights below 2^-126 are zero for every purpose
@@ -43,6 +51,36 @@ __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// 2^x on the FMA / ALU pipes (no MUFU): floor by the round-down magic-number add, degree-3 minimax polynomial of 2^f on
+// [0, 1) (max relative error 8.8e-5 - P is rounded to bf16, 3.9e-3, right after), exponent spliced in with a shift-add.
+// x <= ~100; results below 2^-126 come out as 2^-126 (negligible in a row sum whose largest term is >= 2^-8).
+__device__ __forceinline__ float poly_exp2(float x) {
+    x = fmaxf(x, -126.f);
+    float t;
+    asm("add.rm.ftz.f32 %0, %1, 0f4B400000;" : "=f"(t) : "f"(x));       // 1.5 * 2^23 + floor(x)
+    const float f = x - (t - 12582912.f);
+    const float pf = fmaf(fmaf(fmaf(0.077119089663028717f, f, 0.227564394474029541f), f, 0.695146143436431885f), f, 1.f);
+    return __int_as_float(__float_as_int(pf) + (__float_as_int(t) << 23));
+}
+
+// two at a time, on FADD2 / FFMA2
+__device__ __forceinline__ float2 poly_exp2x2(float2 x) {
+    x = make_float2(fmaxf(x.x, -126.f), fmaxf(x.y, -126.f));
+    float2 t;
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+    asm("add.rm.ftz.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&t))
+        : "l"(*reinterpret_cast<const unsigned long long*>(&x)), "l"(*reinterpret_cast<const unsigned long long*>(&magic)));
+    const float2 fl = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+    const float2 f = __ffma2_rn(fl, make_float2(-1.f, -1.f), x);
+    float2 pf = __ffma2_rn(make_float2(0.077119089663028717f, 0.077119089663028717f), f,
+                           make_float2(0.227564394474029541f, 0.227564394474029541f));
+    pf = __ffma2_rn(pf, f, make_float2(0.695146143436431885f, 0.695146143436431885f));
+    pf = __ffma2_rn(pf, f, make_float2(1.f, 1.f));
+    return make_float2(__int_as_float(__float_as_int(pf.x) + (__float_as_int(t.x) << 23)),
+                       __int_as_float(__float_as_int(pf.y) + (__float_as_int(t.y) << 23)));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -73,6 +111,17 @@ __device__ __forceinline__ void store_packed_chunk(uint8_t* tile, int row, int c
     const int j0 = (c0 & 63) >> 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+        const int phys = (j0 + j) ^ (row & 7);
+        *reinterpret_cast<uint4*>(base + phys * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+}
+
+// same, 16 consecutive columns [c0, c0+16) (c0 a multiple of 16) as 8 packed pairs
+__device__ __forceinline__ void store_packed16(uint8_t* tile, int row, int c0, const uint32_t (&v)[8]) {
+    uint8_t* base = tile + (c0 >> 6) * kFaTile + row * 128;
+    const int j0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
         const int phys = (j0 + j) ^ (row & 7);
         *reinterpret_cast<uint4*>(base + phys * 16) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
@@ -343,6 +392,11 @@ __device__ __forceinline__ void pair_bar_sync(int quarter) {
     }
 }
 
+// kPoly: every kPoly-th exponential of a row goes to poly_exp2 instead of MUFU.EX2 (0: none).  Measured (scripts/gpu_r2ab.sh,
+// B = 2, H = 20, L = 1024): all MUFU 30.2 us, a quarter on the FMA pipe 30.0 us, all on the FMA pipe 37.9 us, NO exponential
+// at all 26.0 us - the exponentials are 14 % of the kernel; what bounds a block is the TMEM read port (64 B/clk per SM
+// sub-partition: S is read twice, 2 x 256 clk per block and CTA) and the barrier / commit latencies around it.
+template <int kPoly>
 __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __grid_constant__ FlashFwdArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFtsBar);
@@ -415,9 +469,11 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __gri
                 for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
                 umma_commit(s_full);
             };
+            const bool tlm = kFaTimeline && g.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
+            if (tlm) g.timeline[7] = clock64();
             issue_s(0);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j & 1;
@@ -425,11 +481,13 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __gri
                     mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
                     mbar_wait(s_free, j & 1);              // the softmax warps have pulled S_j out of TMEM
                     tc_fence_after();
+                    if (tlm) g.timeline[j * 8 + 5] = clock64();
                     issue_s(j + 1);
                 }
                 mbar_wait(p_full, j & 1);                   // P_j written to TMEM, O rescaled
                 mbar_wait(&v_full[s], (j >> 1) & 1);
                 tc_fence_after();
+                if (tlm) g.timeline[j * 8 + 6] = clock64();
                 const uint32_t sv = smem_u32(smem + kFtsV + s * kFaTile);
                 const uint64_t vd = umma_desc(sv, 8192, 1024);
 #pragma unroll
@@ -453,9 +511,11 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __gri
         // when the row's running maximum outgrows it by more than 2^8 (log2 domain), so O (in TMEM) is rescaled on a few
         // blocks instead of on every one; the final O / l and LSE = m.scale + ln(l) are exact whatever reference was used.
         float m = -INFINITY, l = 0.f;
+        const bool tl = kFaTimeline && g.timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == 2 && lane == 0;
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
+            if (tl) g.timeline[j * 8 + 0] = clock64();
             const int kvalid = min(128, g.Lk - j * 128) - half * 64;   // valid keys among this group's 64 (may be <= 0)
             const bool full_blk = kvalid >= 64;                     // warp-uniform
             // pass 1: row maximum over this group's keys, then over both groups
@@ -474,17 +534,20 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __gri
                         if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(raw[i]));
                 }
             }
+            if (tl) g.timeline[j * 8 + 1] = clock64();
             xch[((j & 1) * 2 + half) * 128 + row] = mx;
             pair_bar_sync(quarter);
             mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * 128 + row]);
             const float m_cand = fmaxf(m, mx);
             const bool need = (m_cand - m) * sl2 > 8.f;             // true on the first block (m = -inf)
             const bool any_need = __any_sync(0xffffffffu, need);
-            if (j > 0) {
-                // the previous P.V must have retired before O is rescaled and before P is overwritten
+            // the previous P.V must have retired before O is rescaled (rare) and before P is overwritten (after the
+            // exponentials: by then it has, and the wait costs nothing)
+            if (j > 0 && any_need) {
                 mbar_wait(o_done, (j - 1) & 1);
                 tc_fence_after();
             }
+            if (tl) g.timeline[j * 8 + 2] = clock64();
             if (any_need) {
                 const float alpha = need ? fast_exp2((m - m_cand) * sl2) : 1.f;   // 0 when m was -inf
                 if (need) m = m_cand;
@@ -514,11 +577,19 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __gri
                 }
                 float p[32];
                 if (full_blk) {
+                    // packed fp32x2 arithmetic (FFMA2 / FADD2): half the issue slots of the scalar form
+                    const float2 sl2v = make_float2(sl2, sl2), noff = make_float2(-moff, -moff);
+                    float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        p[i] = fast_exp2(fmaf(__uint_as_float(raw[i]), sl2, -moff));
-                        sum += p[i];
+                    for (int i = 0; i < 32; i += 2) {
+                        const float2 x = __ffma2_rn(make_float2(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), sl2v, noff);
+                        const bool on_fma = kPoly > 0 && ((i >> 1) % (kPoly > 0 ? kPoly : 1)) == (kPoly - 1);
+                        const float2 pv = on_fma ? poly_exp2x2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                        sum2 = __fadd2_rn(sum2, pv);
+                        p[i] = pv.x;
+                        p[i + 1] = pv.y;
                     }
+                    sum += sum2.x + sum2.y;
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
@@ -530,11 +601,17 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __gri
                 for (int i = 0; i < 16; ++i) pk[c * 16 + i] = pack_bf16(p[2 * i], p[2 * i + 1]);
             }
             l += sum;
+            if (tl) g.timeline[j * 8 + 3] = clock64();
+            if (j > 0 && !any_need) {
+                mbar_wait(o_done, (j - 1) & 1);
+                tc_fence_after();
+            }
             tmem_st32(tmem_P + lane_off + half * 32, pk);           // keys [half*64, +64) = packed columns [half*32, +32)
             tmem_st_wait();                                         // P (and a rescaled O) are in TMEM
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
+            if (tl) g.timeline[j * 8 + 4] = clock64();
         }
         mbar_wait(o_done, (nkv - 1) & 1);
         tc_fence_after();
@@ -576,9 +653,13 @@ __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __gri
 constexpr int kBwdThreads = 448;               // TMA, MMA, 4 softmax warps (keys 0-63), 4 dQ-epilogue warps, 4 softmax warps (keys 64-127)
 constexpr int kBwdK = 0;
 constexpr int kBwdV = kBwdK + kFaTile;
-constexpr int kBwdQ = kBwdV + kFaTile;         // 2 stages
-constexpr int kBwdDO = kBwdQ + 2 * kFaTile;    // 2 stages
-constexpr int kBwdP = kBwdDO + 2 * kFaTile;    // [128 q x 128 k] bf16
+// Q / dO ring: a stage is held from its S / dP product until the dK / dV products of the same block retire, and a refill
+// takes a TMA round trip (~1.5k clk) - with two stages the S / dP issue of block i+1 waited for that round trip after
+// block i-1 retired (timeline, B200_FLASH_TIMELINE=1: ~1300 clk per block); with three the refill is a block ahead.
+constexpr int kBwdStages = 3;
+constexpr int kBwdQ = kBwdV + kFaTile;                   // kBwdStages stages
+constexpr int kBwdDO = kBwdQ + kBwdStages * kFaTile;     // kBwdStages stages
+constexpr int kBwdP = kBwdDO + kBwdStages * kFaTile;     // [128 q x 128 k] bf16
 constexpr int kBwdDS = kBwdP + 2 * kFaTile;    // [128 q x 128 k] bf16
 constexpr int kBwdDQ = kBwdDS + 2 * kFaTile;   // dQ block staged as fp32: two [128 q x 32 d] 128B-swizzled boxes (32 KiB)
 constexpr int kBwdBar = kBwdDQ + 2 * kFaTile;
@@ -618,6 +699,7 @@ struct FlashBwdArgs {
     int nbatch_rows;                           // B * Lk: rows of one accumulator plane
     float* dKVacc;
     int* counters;
+    long long* timeline;                       // debug (B200_FLASH_TIMELINE=1): clock64 stamps of CTA 0, [query block][8]; else NULL
 };
 
 template <bool kHook>
@@ -625,16 +707,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdBar);
     uint64_t* kv_full = bars + 0;
-    uint64_t* qdo_full = bars + 1;     // [2]
-    uint64_t* qdo_empty = bars + 3;    // [2]
-    uint64_t* sdp_full = bars + 5;
-    uint64_t* sdp_free = bars + 6;
-    uint64_t* pds_full = bars + 7;
-    uint64_t* pds_free = bars + 8;
-    uint64_t* dq_full = bars + 9;
-    uint64_t* dq_free = bars + 10;
-    uint64_t* dkv_full = bars + 11;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* qdo_full = bars + 1;     // [kBwdStages]
+    uint64_t* qdo_empty = bars + 4;    // [kBwdStages]
+    uint64_t* sdp_full = bars + 7;
+    uint64_t* sdp_free = bars + 8;
+    uint64_t* pds_full = bars + 9;
+    uint64_t* pds_free = bars + 10;
+    uint64_t* dq_full = bars + 11;
+    uint64_t* dq_free = bars + 12;
+    uint64_t* dkv_full = bars + 13;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nq_all = (g.L + 127) >> 7;
@@ -660,7 +742,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
         tma_prefetch_desc(&g.mapK);
         tma_prefetch_desc(&g.mapV);
         mbar_init(kv_full, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kBwdStages; ++i) {
             mbar_init(&qdo_full[i], 1);
             mbar_init(&qdo_empty[i], 1);
         }
@@ -691,8 +773,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             tma_load_4d(smem + kBwdK, &g.mapK, kv_full, 0, k0, h, b);
             tma_load_4d(smem + kBwdV, &g.mapV, kv_full, 0, k0, h, b);
             for (int i = 0; i < nq; ++i) {
-                const int s = i & 1;
-                mbar_wait(&qdo_empty[s], ((i >> 1) & 1) ^ 1);
+                const int s = i % kBwdStages;
+                mbar_wait(&qdo_empty[s], ((i / kBwdStages) & 1) ^ 1);
                 mbar_expect_tx(&qdo_full[s], 2 * kFaTile);
                 tma_load_4d(smem + kBwdQ + s * kFaTile, &g.mapQ, &qdo_full[s], 0, (qb0 + i) * 128, h, b);
                 tma_load_4d(smem + kBwdDO + s * kFaTile, &g.mapDO, &qdo_full[s], 0, (qb0 + i) * 128, h, b);
@@ -711,9 +793,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             // warps have pulled S / dP of block i out of TMEM, so the softmax of block i+1 overlaps the three
             // gradient MMAs of block i (the loop used to be a strict MMA -> softmax -> MMA chain).
             auto issue_sdp = [&](int i) {
-                const int s = i & 1;
+                const int s = i % kBwdStages;
                 const uint32_t sq = smem_u32(smem + kBwdQ + s * kFaTile), sdo = smem_u32(smem + kBwdDO + s * kFaTile);
-                mbar_wait(&qdo_full[s], (i >> 1) & 1);
+                mbar_wait(&qdo_full[s], (i / kBwdStages) & 1);
                 mbar_wait(sdp_free, (i & 1) ^ 1);
                 tc_fence_after();
                 const uint64_t aq = umma_desc(sq, 16, 1024), bk = umma_desc(sk, 16, 1024);
@@ -724,14 +806,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 for (int k = 0; k < 4; ++k) umma_bf16(t_dP, ado + 2 * k, bv + 2 * k, id_kk, k > 0);
                 umma_commit(sdp_full);
             };
+            const bool tlm = kFaTimeline && g.timeline != nullptr && blockIdx.x == 0;
+            if (tlm) g.timeline[7] = clock64();
             issue_sdp(0);
             for (int i = 0; i < nq; ++i) {
-                const int s = i & 1;
+                const int s = i % kBwdStages;
                 const uint32_t sq = smem_u32(smem + kBwdQ + s * kFaTile), sdo = smem_u32(smem + kBwdDO + s * kFaTile);
-                if (i + 1 < nq) issue_sdp(i + 1);
+                if (i + 1 < nq) {
+                    issue_sdp(i + 1);
+                    if (tlm) g.timeline[i * 8 + 4] = clock64();
+                }
                 mbar_wait(pds_full, i & 1);
                 mbar_wait(dq_free, (i & 1) ^ 1);
                 tc_fence_after();
+                if (tlm) g.timeline[i * 8 + 5] = clock64();
                 {
                     const uint64_t apT = umma_desc(sp, kFaTile, 1024), adsT = umma_desc(sds, kFaTile, 1024);
                     const uint64_t bdo = umma_desc(sdo, 8192, 1024), bq = umma_desc(sq, 8192, 1024);
@@ -765,6 +853,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             //      128 keys): one warp per scheduler was the bottleneck of this kernel (issue-bound at ~1500
             //      instructions per row and block), so two warps share every TMEM lane quarter. ----
             const int chalf = (warp >= 10) ? 2 : 0;
+            const bool tl = kFaTimeline && g.timeline != nullptr && blockIdx.x == 0 && warp == 2 && lane == 0;
             for (int i = 0; i < nq; ++i) {
                 const int q = (qb0 + i) * 128 + row;
                 const bool qok = q < g.L;
@@ -772,25 +861,36 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 const float delta = qok ? g.Delta[stat_base + q] : 0.f;
                 mbar_wait(sdp_full, i & 1);
                 tc_fence_after();
+                if (tl) g.timeline[i * 8 + 0] = clock64();
                 const bool full_blk = (kvalid == 128) && ((qb0 + i) * 128 + 128 <= g.L);     // warp-uniform
-                uint32_t pp[2][16], pd[2][16];                 // this thread's 64 P and dS values, packed bf16
+                // This thread's 64 keys go through in four 16-column steps.  The TMEM loads of step c+1 are issued before the
+                // arithmetic of step c (tcgen05.wait::ld waits for every outstanding load, so the wait sits after it), the
+                // first half of the P / dS row is stored as soon as the gradient MMAs of block i-1 have released the tiles
+                // (they have, by then), and S / dP are handed back to the MMA warp before the last step's arithmetic.
+                uint32_t pp[4][8], pd[4][8];                   // packed bf16 pairs
+                uint32_t rs[2][16], rp[2][16];
+                const int col_base = chalf * 32;               // first of this thread's 64 columns
+                tmem_ld16(t_S + lane_off + col_base, rs[0]);
+                tmem_ld16(t_dP + lane_off + col_base, rp[0]);
+                tmem_ld_wait();
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = chalf + cc;
-                    uint32_t rs[32], rp[32];
-                    tmem_ld32(t_S + lane_off + c * 32, rs);
-                    tmem_ld32(t_dP + lane_off + c * 32, rp);
-                    tmem_ld_wait();
-                    float p[32], ds[32];
-                    float hk[kHook ? 32 : 1];                       // the hook instantiation only (cross-attention layers)
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int c0 = col_base + cc * 16;         // columns [c0, c0 + 16) of the block
+                    if (cc < 3) {
+                        tmem_ld16(t_S + lane_off + c0 + 16, rs[(cc + 1) & 1]);
+                        tmem_ld16(t_dP + lane_off + c0 + 16, rp[(cc + 1) & 1]);
+                    }
+                    const uint32_t(&xs)[16] = rs[cc & 1];
+                    const uint32_t(&xp)[16] = rp[cc & 1];
+                    float hk[kHook ? 16 : 1];                       // the hook instantiation only (cross-attention layers)
 #pragma unroll
-                    for (int e = 0; e < (kHook ? 32 : 1); ++e) hk[e] = 0.f;
+                    for (int e = 0; e < (kHook ? 16 : 1); ++e) hk[e] = 0.f;
                     if (kHook && qok) {
-                        // this thread's slice of the hook gradient: columns k0 + c*32 .. +32 of its query row
-                        const int col0 = k0 + c * 32;
+                        // this thread's slice of the hook gradient: columns k0 + c0 .. +16 of its query row
+                        const int col0 = k0 + c0;
                         const __nv_bfloat16* hp = g.dSc + (static_cast<long long>(b) * g.L + q) * g.ld_dsc + col0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
+                        for (int j = 0; j < 2; ++j) {
                             if (col0 + j * 8 + 8 <= g.dsc_cols) {
                                 const uint4 w = *reinterpret_cast<const uint4*>(hp + j * 8);
                                 const uint32_t u[4] = {w.x, w.y, w.z, w.w};
@@ -803,38 +903,62 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                         }
                     }
                     if (full_blk) {
+                        // packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2): the same roundings as the scalar form in half
+                        // the issue slots
+                        const float2 sl2v = make_float2(sl2, sl2), nlse = make_float2(-lse2, -lse2);
+                        const float2 ndel = make_float2(-delta, -delta), scv = make_float2(g.scale, g.scale);
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            p[e] = fast_exp2(fmaf(__uint_as_float(rs[e]), sl2, -lse2));
-                            ds[e] = fmaf(p[e] * (__uint_as_float(rp[e]) - delta), g.scale, hk[kHook ? e : 0]);
+                        for (int e = 0; e < 16; e += 2) {
+                            const float2 x = __ffma2_rn(make_float2(__uint_as_float(xs[e]), __uint_as_float(xs[e + 1])), sl2v, nlse);
+                            // (moving exponentials to the FMA pipe as the forward does buys nothing here: measured equal at a
+                            //  quarter, 3 % slower at a half - this loop is not MUFU-bound)
+                            const float2 pv = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                            const float2 t = __fadd2_rn(make_float2(__uint_as_float(xp[e]), __uint_as_float(xp[e + 1])), ndel);
+                            const float2 u = __fmul2_rn(pv, t);
+                            const float2 d = kHook ? __ffma2_rn(u, scv, make_float2(hk[kHook ? e : 0], hk[kHook ? e + 1 : 0]))
+                                                   : __fmul2_rn(u, scv);
+                            pp[cc][e >> 1] = pack_bf16(pv.x, pv.y);
+                            pd[cc][e >> 1] = pack_bf16(d.x, d.y);
                         }
                     } else {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const bool ok = qok && (c * 32 + e < kvalid);
-                            p[e] = ok ? fast_exp2(fmaf(__uint_as_float(rs[e]), sl2, -lse2)) : 0.f;
-                            ds[e] = ok ? fmaf(p[e] * (__uint_as_float(rp[e]) - delta), g.scale, hk[kHook ? e : 0]) : 0.f;
+                        for (int e = 0; e < 16; e += 2) {
+                            float pe[2], de[2];
+#pragma unroll
+                            for (int t2 = 0; t2 < 2; ++t2) {
+                                const bool ok = qok && (c0 + e + t2 < kvalid);
+                                pe[t2] = ok ? fast_exp2(fmaf(__uint_as_float(xs[e + t2]), sl2, -lse2)) : 0.f;
+                                de[t2] = ok ? fmaf(pe[t2] * (__uint_as_float(xp[e + t2]) - delta), g.scale, hk[kHook ? e + t2 : 0]) : 0.f;
+                            }
+                            pp[cc][e >> 1] = pack_bf16(pe[0], pe[1]);
+                            pd[cc][e >> 1] = pack_bf16(de[0], de[1]);
                         }
                     }
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        pp[cc][e] = pack_bf16(p[2 * e], p[2 * e + 1]);
-                        pd[cc][e] = pack_bf16(ds[2 * e], ds[2 * e + 1]);
+                    if (cc < 3) tmem_ld_wait();
+                    if (cc == 1) {
+                        if (tl) g.timeline[i * 8 + 1] = clock64();
+                        mbar_wait(pds_free, (i & 1) ^ 1);     // the gradient MMAs of block i-1 have read the P / dS tiles
+                        if (tl) g.timeline[i * 8 + 2] = clock64();
+                        store_packed16(smem + kBwdP, row, col_base, pp[0]);
+                        store_packed16(smem + kBwdP, row, col_base + 16, pp[1]);
+                        store_packed16(smem + kBwdDS, row, col_base, pd[0]);
+                        store_packed16(smem + kBwdDS, row, col_base + 16, pd[1]);
+                    }
+                    if (cc == 2) {
+                        // S / dP are out of TMEM: the MMA warp may start block i+1 while this block is still being finished
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(sdp_free);
                     }
                 }
-                // S / dP are out of TMEM: the MMA warp may start block i+1 while this block's tiles are still being staged
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sdp_free);
-                mbar_wait(pds_free, (i & 1) ^ 1);             // the gradient MMAs of block i-1 have read the P / dS tiles
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    store_packed_chunk(smem + kBwdP, row, (chalf + cc) * 32, pp[cc]);
-                    store_packed_chunk(smem + kBwdDS, row, (chalf + cc) * 32, pd[cc]);
-                }
+                store_packed16(smem + kBwdP, row, col_base + 32, pp[2]);
+                store_packed16(smem + kBwdP, row, col_base + 48, pp[3]);
+                store_packed16(smem + kBwdDS, row, col_base + 32, pd[2]);
+                store_packed16(smem + kBwdDS, row, col_base + 48, pd[3]);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pds_full);
+                if (tl) g.timeline[i * 8 + 3] = clock64();
             }
         } else {
             // ---- dQ epilogue warps: dQ_blk is summed over key blocks in an fp32 global accumulator.  It leaves through
@@ -843,9 +967,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
             //      by the L2 atomic units. ----
             const bool issuer = (warp == 6 && lane == 0);
             uint8_t* stg = smem + kBwdDQ;
+            const bool tlq = kFaTimeline && g.timeline != nullptr && blockIdx.x == 0 && warp == 6 && lane == 0;
             for (int i = 0; i < nq; ++i) {
                 mbar_wait(dq_full, i & 1);
                 tc_fence_after();
+                if (tlq) g.timeline[i * 8 + 6] = clock64();
                 if (g.dq_direct) {
                     // single key block: no accumulation over blocks -> straight to bf16, thread <-> query row
                     const int q = (qb0 + i) * 128 + row;
