@@ -1,5 +1,5 @@
 #!/bin/bash
-# Final evidence of round 2 (profiles/r02g_*): GPU suite, default bench with every leg, reference arm, launch list of one step,
+# Final evidence of round 2 (profiles/r02n_*, earlier passes r02g_ / r02k_): GPU suite, default bench with every leg, reference arm, launch list of one step,
 # ncu --set full of the dominant kernels of the FINAL build.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
@@ -17,7 +17,7 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm
     python scripts/one_gemm.py 2048 3840 1280 lora 48 >> gpurun_out/ncu_full.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 3 -c 1 -o gpurun_out/final_gemm2_ff \
     python scripts/one_gemm.py 2048 10240 1280 plain >> gpurun_out/ncu_full.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:flash_fwd_kernel -s 2 -c 1 -o gpurun_out/final_flash_fwd \
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:flash_fwd -s 2 -c 1 -o gpurun_out/final_flash_fwd \
     python scripts/one_flash.py 1024 20 >> gpurun_out/ncu_full.log 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:flash_bwd_kernel -s 2 -c 1 -o gpurun_out/final_flash_bwd \
     python scripts/one_flash.py 1024 20 >> gpurun_out/ncu_full.log 2>&1

@@ -28,6 +28,9 @@ WANT = [
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput % (gpu)"),
     ("lts__t_bytes.sum", "L2 bytes"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "smem wavefronts read by the tensor core"),
+    ("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem tensor-core wavefronts % of peak"),
+    ("l1tex__m_l1tex2xbar_write_bytes_mem_global_op_tma_red.sum", "TMA reduce-add bytes"),
     ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
     ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->SM fabric read bytes"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts (all)"),

@@ -43,7 +43,7 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
     g.scale = scale;
     dim3 grid((L + 127) / 128, H, B);
     // B200_FLASH_TIMELINE=1 (debug, synchronises): clock64 stamps of CTA (0,0,0) printed to stderr after every launch -
-    // per key block: s_full seen, row max done, o_done seen, exponentials done, P published | MMA: S(j+1) issued, P.V(j) issued
+    // per key block: s_full seen, row max done, half-row maxima exchanged, exponentials done, P published | MMA: S(j+1) issued, P.V(j) issued
     static const bool timeline = kFaTimeline && getenv("B200_FLASH_TIMELINE") && atoi(getenv("B200_FLASH_TIMELINE")) != 0;
     static long long* tl_buf = nullptr;
     const int nkv_dbg = (Lk + 127) / 128;
@@ -66,7 +66,7 @@ extern "C" int b200_flash_attn_fwd(const void* q, const void* k, const void* v, 
         const long long t0 = hbuf[7];
         fprintf(stderr, "flash_fwd timeline (clk since first S issue) B=%d H=%d L=%d Lk=%d\n", B, H, L, Lk);
         for (int j = 0; j < nkv_dbg; ++j)
-            fprintf(stderr, "  blk %2d: s_full %6lld  max %6lld  o_done %6lld  exp %6lld  p_pub %6lld | S(j+1) issue %6lld  PV(j) issue %6lld\n", j,
+            fprintf(stderr, "  blk %2d: s_full %6lld  max %6lld  xchg %6lld  exp %6lld  p_pub %6lld | S(j+1) issue %6lld  PV(j) issue %6lld\n", j,
                     hbuf[j * 8 + 0] - t0, hbuf[j * 8 + 1] - t0, hbuf[j * 8 + 2] - t0, hbuf[j * 8 + 3] - t0, hbuf[j * 8 + 4] - t0,
                     hbuf[j * 8 + 5] ? hbuf[j * 8 + 5] - t0 : 0, hbuf[j * 8 + 6] - t0);
     }
