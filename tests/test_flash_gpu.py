@@ -70,6 +70,40 @@ def test_flash_attention_fwd_bwd(B, H, L, Lk):
         print(f"\nflash fwd {tf:.3f} ms ({fl / tf / 1e9:.0f} TFLOP/s)  bwd {tb:.3f} ms ({2.5 * fl / tb / 1e9:.0f} TFLOP/s)")
 
 
+@pytest.mark.parametrize("B,H,L,Lk", [(1, 2, 256, 512), (2, 3, 200, 700)])
+def test_flash_forward_rescales_when_later_keys_dominate(B, H, L, Lk):
+    """Key blocks whose scores grow by far more than 2^8 from block to block: the running reference must move and O (in
+    tensor memory) must be rescaled on every block - a path random normal data never takes after the first block.  Both
+    key-half warp groups of a row have to agree on the new reference (the forward keeps one O accumulator)."""
+    from sd_lora_trainer_b200 import ops
+    C = H * 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q = (4.0 * torch.randn(B * L, C, device="cuda", generator=g)).to(BF)
+    k = torch.randn(B, Lk, C, device="cuda", generator=g)
+    grow = 1.0 + 3.0 * (torch.arange(Lk, device="cuda") // 128).float()          # x1, x4, x7, ... per 128-key block
+    grow[Lk // 2:Lk // 2 + 64] *= 0.05                                            # and one weak half block in between
+    k = (k * grow[None, :, None]).reshape(B * Lk, C).to(BF)
+    v = torch.randn(B * Lk, C, device="cuda", generator=g).to(BF)
+    do = torch.randn(B * L, C, device="cuda", generator=g).to(BF)
+    scale = 64 ** -0.5
+    o, lse = ops.flash_attn_fwd(q, k, v, B, H, L, Lk, scale)
+    dq, dk, dv = ops.flash_attn_bwd(q, k, v, o, do, lse, B, H, L, Lk, scale)
+    torch.cuda.synchronize()
+    qr = q.float().view(B, L, H, 64).transpose(1, 2).requires_grad_(True)
+    kr = k.float().view(B, Lk, H, 64).transpose(1, 2).requires_grad_(True)
+    vr = v.float().view(B, Lk, H, 64).transpose(1, 2).requires_grad_(True)
+    s = qr @ kr.transpose(-1, -2) * scale
+    blockmax = torch.stack([s[..., j:j + 128].amax(-1) for j in range(0, Lk, 128)], -1)
+    assert float((blockmax[..., 1:] - blockmax[..., :-1]).amax() * 1.4427) > 8.0       # the data does what the docstring says
+    ref = torch.softmax(s, -1) @ vr
+    ref.backward(do.float().view(B, L, H, 64).transpose(1, 2))
+    unh = lambda t, n: t.transpose(1, 2).reshape(B * n, C)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert rel(o, unh(ref, L)) < 1e-2, ("o", rel(o, unh(ref, L)))
+    assert rel(lse, torch.logsumexp(s, -1)) < 1e-3
+    assert rel(dv, unh(vr.grad, Lk)) < 2e-2 and rel(dq, unh(qr.grad, L)) < 2e-2 and rel(dk, unh(kr.grad, Lk)) < 2e-2
+
+
 @pytest.mark.parametrize("rows,H,d_src,d_dst", [(300, 8, 40, 64), (300, 8, 64, 40), (77, 2, 32, 64), (513, 5, 64, 64)])
 def test_head_pad_is_an_exact_repitch(rows, H, d_src, d_dst):
     from sd_lora_trainer_b200 import ops
