@@ -766,6 +766,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
     pdl_wait();
     const uint32_t tmem = *tmem_ptr;
     const uint32_t t_S = tmem, t_dP = tmem + 128, t_dV = tmem + 256, t_dK = tmem + 320, t_dQ = tmem + 384;
+    // dS once more, as bf16 pairs in the last 64 columns: the A operand of dQ = dS.K comes from tensor memory (TS-mode MMA), which
+    // takes its 32 KB per block off the shared-memory pipe this kernel is bound by (the smem copy still feeds dK = dS^T.Q)
+    const uint32_t t_dSp = tmem + 448;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -829,10 +832,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
 #pragma unroll
                     for (int k = 0; k < 8; ++k) umma_bf16(t_dK, adsT + 128 * k, bq + 128 * k, id_mm, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint64_t ads = umma_desc(sds + (k >> 2) * kFaTile, 16, 1024) + 2 * (k & 3);
-                        umma_bf16(t_dQ, ads, bkm + 128 * k, id_km, k > 0);
-                    }
+                    for (int k = 0; k < 8; ++k) umma_bf16_ts(t_dQ, t_dSp + 8 * k, bkm + 128 * k, id_km, k > 0);
                 }
                 umma_commit(&qdo_empty[s]);
                 umma_commit(pds_free);
@@ -943,6 +943,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                         store_packed16(smem + kBwdP, row, col_base + 16, pp[1]);
                         store_packed16(smem + kBwdDS, row, col_base, pd[0]);
                         store_packed16(smem + kBwdDS, row, col_base + 16, pd[1]);
+                        uint32_t w[16];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            w[e] = pd[0][e];
+                            w[8 + e] = pd[1][e];
+                        }
+                        tmem_st16(t_dSp + lane_off + (col_base >> 1), w);     // keys [col_base, +32) = packed columns [col_base/2, +16)
                     }
                     if (cc == 2) {
                         // S / dP are out of TMEM: the MMA warp may start block i+1 while this block is still being finished
@@ -955,6 +962,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) flash_bwd_kernel(const __grid_
                 store_packed16(smem + kBwdP, row, col_base + 48, pp[3]);
                 store_packed16(smem + kBwdDS, row, col_base + 32, pd[2]);
                 store_packed16(smem + kBwdDS, row, col_base + 48, pd[3]);
+                {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        w[e] = pd[2][e];
+                        w[8 + e] = pd[3][e];
+                    }
+                    tmem_st16(t_dSp + lane_off + (col_base >> 1) + 16, w);
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(pds_full);
