@@ -94,9 +94,10 @@ extern "C" int b200_flash_attn_bwd(const void* q, const void* k, const void* v, 
     }
     const long long nq_elems = static_cast<long long>(B) * L * C64;        // fp32 dQ accumulator: contiguous [B*L, H*64]
     const bool dq_direct = Lk <= 128;          // one key block: dQ is written once, as bf16, by the kernel itself
-    if (!dq_direct) cudaMemsetAsync(dq_acc_ws, 0, sizeof(float) * nq_elems, st);
-    launch_pdl(flash_delta_kernel, dim3(grid_for(static_cast<long long>(B) * L * H, 256)), dim3(256), 0, st, 
-        static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta_ws, B, L, H, ld_o);
+    B200_CHECK_ARG(dq_direct || dq_acc_ws != nullptr, "flash_attn_bwd: Lk > 128 needs the fp32 dQ accumulator workspace");
+    launch_pdl(flash_delta_kernel, dim3(grid_for(static_cast<long long>(B) * L * H * 8, 256)), dim3(256), 0, st,
+        static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta_ws,
+        dq_direct ? static_cast<float*>(nullptr) : dq_acc_ws, B, L, H, ld_o);    // also zeroes the dQ accumulator
     B200_CHECK_LAUNCH("flash_delta");
     FlashBwdArgs g;
     memset(&g, 0, sizeof(g));
