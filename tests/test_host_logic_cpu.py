@@ -301,3 +301,28 @@ def test_reset_optimizer_state_and_close(monkeypatch):
     tr.close()
     assert tr._graphs == {} and tr._static is None
     tr.step(inputs)                                              # and the trainer keeps working afterwards
+
+
+def test_ti_embedding_matches_a_table_with_appended_rows():
+    """text.TIEmbedding (frozen table + a small trainable leaf, looked up through a one-hot product) against the reference's
+    form: ONE trainable [vocab + n, dim] table indexed directly (main.py:92-100, 368-371) - same output, and the gradient of
+    the appended rows equals the gradient of the leaf, duplicates and absent tokens included."""
+    import torch
+    import torch.nn.functional as F
+    from sd_lora_trainer_b200.text import TIEmbedding
+    torch.manual_seed(0)
+    vocab, dim, n = 50, 16, 3
+    table = torch.randn(vocab, dim)
+    rows = torch.randn(n, dim, requires_grad=True)
+    emb = TIEmbedding(table, rows)
+    ids = torch.tensor([[1, 7, vocab + 0, vocab + 2, 7, vocab + 0, 49, 0], [vocab + 2, 3, 3, 3, 3, 3, 3, 3]])
+    out = emb(ids)
+    full = torch.cat([table, rows.detach()], 0).requires_grad_(True)
+    ref = F.embedding(ids, full)
+    assert torch.equal(out, ref)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    (ref * w).sum().backward()
+    assert torch.allclose(rows.grad, full.grad[vocab:], atol=1e-6)
+    assert float(rows.grad[1].abs().max()) == 0.0                  # token 1 does not occur
+    assert emb.num_embeddings == vocab + n and TIEmbedding(table, None)(ids.clamp(max=vocab - 1)).shape == (2, 8, dim)
