@@ -13,7 +13,9 @@ def rel(a, b):
 
 @pytest.mark.parametrize("B,H,L,Lk", [(2, 4, 256, 256), (2, 3, 384, 77), (1, 2, 1024, 1024), (2, 2, 200, 150),
                                       (1, 5, 128, 640), (2, 10, 4096, 4096), (1, 2, 130, 64), (1, 1, 128, 65), (2, 2, 256, 192),
-                                      (1, 1, 64, 3), (2, 20, 512, 512), (2, 20, 1024, 1024)])
+                                      (1, 1, 64, 3), (2, 20, 512, 512), (2, 20, 1024, 1024),
+                                      # one key block (cross-attention) at SDXL's tile counts: 320 / 640 CTAs on 296 slots
+                                      (2, 20, 1024, 77), (2, 20, 1000, 77), (2, 10, 4096, 77)])
 def test_flash_attention_fwd_bwd(B, H, L, Lk):
     from sd_lora_trainer_b200 import ops
     C = H * 64
