@@ -64,3 +64,26 @@ def test_adamw_hyper_packing_is_host_only():
     assert abs(float(h[0]) - (1 - 3e-4 * 0.004)) < 1e-7          # decay of the LoRA segment
     assert abs(float(h[1]) + 3e-4 / (1 - 0.9)) < 1e-6             # -(lr / bias_correction1) at step 1
     assert float(h[3]) == 1.0                                     # wd2 == 0 -> decay op skipped
+
+
+def test_library_sass_uses_the_blackwell_paths():
+    """The built sm_100a library really contains what DESIGN.md says it does (no GPU needed: cuobjdump reads the cubin):
+    tcgen05.mma as CTA pairs and single CTAs, TMEM loads AND stores (the attention kernels keep P / dS in tensor memory), TMA
+    loads / stores / reduce-adds, and packed fp32x2 arithmetic; mma.sync only in the batched LoRA weight-gradient kernel."""
+    import shutil
+    import subprocess
+    import pytest
+    from sd_lora_trainer_b200 import build
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True, check=True).stdout
+    for mnemonic in ("UTCHMMA.2CTA", "UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTCBAR", "FFMA2"):
+        assert mnemonic in sass, mnemonic
+    assert "sm_100a" in sass
+    fn, users = None, set()
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+        elif " HMMA" in line and fn:
+            users.add(fn)
+    assert users and all("lora_wgrad_batch" in u for u in users), users
