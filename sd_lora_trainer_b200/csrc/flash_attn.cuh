@@ -395,7 +395,8 @@ __device__ __forceinline__ void pair_bar_sync(int quarter) {
 // kPoly: every kPoly-th exponential of a row goes to poly_exp2 instead of MUFU.EX2 (0: none).  Measured (scripts/gpu_r2ab.sh,
 // B = 2, H = 20, L = 1024): all MUFU 30.2 us, a quarter on the FMA pipe 30.0 us, all on the FMA pipe 37.9 us, NO exponential
 // at all 26.0 us - the exponentials are 14 % of the kernel; what bounds a block is the TMEM read port (64 B/clk per SM
-// sub-partition: S is read twice, 2 x 256 clk per block and CTA) and the barrier / commit latencies around it.
+// sub-partition: S is read twice, 2 x 256 clk per block and CTA) and the barrier / commit latencies around it.  With the packed
+// arithmetic every 4th or 3rd pair on the FMA pipe measure the same (134.6 / 134.8 us at L = 4096), every 2nd is slower (142.5).
 template <int kPoly>
 __global__ void __launch_bounds__(kFaThreads, 2) flash_fwd_ts_kernel(const __grid_constant__ FlashFwdArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
